@@ -1,0 +1,177 @@
+"""ctypes binding of include/burst_b200.h (libburst_b200.so) for tests and bench.py.
+
+This is a thin mirror of the C ABI -- the production host driver is C (burst_b200/host/).  There
+is no fallback: if the CUDA library is missing or no device is present, construction raises.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libburst_b200.so")
+
+HIT_DTYPE = np.dtype([("task", "<u4"), ("lane", "u1"), ("ed", "u1"), ("gap_q", "u1"),
+                      ("gap_r", "u1"), ("final_pos", "<u4")])
+TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
+MODE_MIN, MODE_ALL = 0, 1
+
+
+class BgQueries(C.Structure):
+    _fields_ = [("codes", C.c_void_p), ("offset", C.c_void_p), ("budget", C.c_void_p),
+                ("slot", C.c_void_p), ("nq", C.c_uint32), ("nslots", C.c_uint32)]
+
+
+class BgStats(C.Structure):
+    _fields_ = [("tasks", C.c_uint64), ("nominal_cells", C.c_uint64), ("filter_cells", C.c_uint64),
+                ("survivors", C.c_uint64), ("band_cells", C.c_uint64), ("hits", C.c_uint64),
+                ("ms_filter", C.c_float), ("ms_extend", C.c_float), ("ms_select", C.c_float)]
+
+    def asdict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scoring", "bg_default_scoring",
+           "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
+           "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
+           "bg_align_batch", "bg_free_hits"]
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                           "(there is no CPU fallback for the DP path)" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.bg_last_error.restype = C.c_char_p
+    L.bg_batch_best_device.restype = C.c_void_p
+    L.bg_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+    L.bg_free.argtypes = [C.c_void_p]
+    L.bg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+    L.bg_set_scoring.argtypes = [C.c_void_p, C.c_void_p]
+    L.bg_default_scoring.argtypes = [C.c_int, C.c_void_p]
+    L.bg_load_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
+    L.bg_batch_upload.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64]
+    L.bg_batch_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.bg_batch_run_extend.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    L.bg_batch_best_device.argtypes = [C.c_void_p]
+    L.bg_batch_run_select.argtypes = [C.c_void_p, C.c_int]
+    L.bg_batch_count.argtypes = [C.c_void_p, C.POINTER(C.c_uint64)]
+    L.bg_batch_download.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    L.bg_batch_stats.argtypes = [C.c_void_p, C.POINTER(BgStats)]
+    L.bg_align_batch.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64, C.c_int,
+                                 C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.bg_free_hits.argtypes = [C.c_void_p]
+    return L
+
+
+def default_scoring(z=1):
+    S = np.zeros(256, np.uint8)
+    load_library().bg_default_scoring(z, S.ctypes.data)
+    return S
+
+
+class Engine:
+    def __init__(self, device=0, stream=None):
+        self.lib = load_library()
+        self.ctx = C.c_void_p()
+        self._check(self.lib.bg_init(device, C.byref(self.ctx)))
+        if stream is not None:
+            self._check(self.lib.bg_set_stream(self.ctx, C.c_void_p(stream)))
+        self._keep = []
+
+    def _check(self, rc):
+        if rc:
+            raise RuntimeError("burst_b200: %s (code %d)" % (self.lib.bg_last_error().decode(), rc))
+
+    def close(self):
+        if self.ctx:
+            self.lib.bg_free(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_scoring(self, S):
+        S = np.ascontiguousarray(S, np.uint8)
+        self._check(self.lib.bg_set_scoring(self.ctx, S.ctypes.data))
+
+    def load_db(self, packed, clump_len, first_clump=0):
+        packed = np.ascontiguousarray(packed, np.uint8)
+        clump_len = np.ascontiguousarray(clump_len, np.uint32)
+        self._check(self.lib.bg_load_db(self.ctx, packed.ctypes.data, clump_len.ctypes.data,
+                                        len(clump_len), first_clump))
+
+    def _queries(self, codes, offset, budget, slot, nslots):
+        codes = np.ascontiguousarray(codes, np.uint8)
+        offset = np.ascontiguousarray(offset, np.uint64)
+        budget = np.ascontiguousarray(budget, np.uint16)
+        nq = len(offset) - 1
+        if slot is None:
+            slot = np.arange(nq, dtype=np.uint32)
+            nslots = nq
+        slot = np.ascontiguousarray(slot, np.uint32)
+        q = BgQueries(codes.ctypes.data, offset.ctypes.data, budget.ctypes.data, slot.ctypes.data, nq, nslots)
+        self._keep = [codes, offset, budget, slot]
+        return q
+
+    @staticmethod
+    def _tasks(tasks):
+        if tasks is None:
+            return None, 0, None
+        t = np.ascontiguousarray(tasks, TASK_DTYPE) if getattr(tasks, "dtype", None) == TASK_DTYPE \
+            else np.ascontiguousarray(np.asarray(tasks, np.uint32).reshape(-1, 2)).view(TASK_DTYPE).reshape(-1)
+        return t, len(t), t.ctypes.data
+
+    # ---- resident three-step form ----
+    def upload(self, codes, offset, budget, tasks, slot=None, nslots=0):
+        q = self._queries(codes, offset, budget, slot, nslots)
+        t, n, p = self._tasks(tasks)
+        self._nslots = q.nslots
+        self._check(self.lib.bg_batch_upload(self.ctx, C.byref(q), p, n))
+
+    def run(self, mode=MODE_MIN, best_in=None):
+        b = None if best_in is None else np.ascontiguousarray(best_in, np.uint16)
+        self._check(self.lib.bg_batch_run(self.ctx, mode, None if b is None else b.ctypes.data))
+
+    def run_extend(self, mode=MODE_MIN, best_in=None):
+        b = None if best_in is None else np.ascontiguousarray(best_in, np.uint16)
+        self._check(self.lib.bg_batch_run_extend(self.ctx, mode, None if b is None else b.ctypes.data))
+
+    def best_device_ptr(self):
+        return self.lib.bg_batch_best_device(self.ctx)
+
+    def run_select(self, mode=MODE_MIN):
+        self._check(self.lib.bg_batch_run_select(self.ctx, mode))
+
+    def count(self):
+        n = C.c_uint64(0)
+        self._check(self.lib.bg_batch_count(self.ctx, C.byref(n)))
+        return int(n.value)
+
+    def download(self):
+        n = self.count()
+        hits = np.zeros(n, HIT_DTYPE)
+        best = np.zeros(self._nslots, np.uint16)
+        self._check(self.lib.bg_batch_download(self.ctx, hits.ctypes.data, n, best.ctypes.data))
+        return hits, best
+
+    def stats(self):
+        s = BgStats()
+        self._check(self.lib.bg_batch_stats(self.ctx, C.byref(s)))
+        return s.asdict()
+
+    # ---- one call, host buffers in, host buffers out ----
+    def align(self, codes, offset, budget, tasks, mode=MODE_MIN, slot=None, nslots=0, best=None):
+        q = self._queries(codes, offset, budget, slot, nslots)
+        t, n, p = self._tasks(tasks)
+        self._nslots = q.nslots
+        b = np.full(q.nslots, 0xFFFF, np.uint16) if best is None else np.ascontiguousarray(best, np.uint16).copy()
+        hp = C.c_void_p(); nh = C.c_uint64(0)
+        self._check(self.lib.bg_align_batch(self.ctx, C.byref(q), p, n, mode, b.ctypes.data, C.byref(hp), C.byref(nh)))
+        hits = np.zeros(nh.value, HIT_DTYPE)
+        if nh.value:
+            C.memmove(hits.ctypes.data, hp, nh.value * HIT_DTYPE.itemsize)
+        self.lib.bg_free_hits(hp)
+        return hits, b

@@ -1,0 +1,122 @@
+/* burst_b200.h -- C ABI of the B200 alignment engine (libburst_b200.so).
+ *
+ * This is the drop-in boundary for BURST's alignment hot path.  The reference has no
+ * plugin/FFI layer: the path is three static inline C functions called from one place each
+ * (SURVEY.md 8b).  Their per-call, latency-shaped signatures
+ *
+ *   uint32_t aded_mat16L(DualCoil *ref, char *query, uint32_t rwidth, uint32_t qlen, uint32_t width,
+ *                        uint32_t minlen, DualCoil *Matrix, DualCoil *profile, uint32_t maxED,
+ *                        uint32_t startQ, uint32_t *LoBound, uint32_t *HiBound, DualCoil *MinA)
+ *                                                                     burst.c:1106-1107
+ *   uint32_t aded_mat16 / aded_xalpha (same minus minlen)             burst.c:1097-1101
+ *   void reScoreM_mat16 / reScoreM_xalpha(DualCoil *ref, char *query, uint32_t rwidth, uint32_t qlen,
+ *                        uint32_t width, DualCoil *Matrix, DualCoil *Shifts, DualCoil *ShiftR,
+ *                        uint32_t maxED, DualCoil *profile, MetaPack *M16)   burst.c:890-896
+ *
+ * are replaced by ONE batched call over a list of (query, clump) tasks -- the pairs the
+ * reference's drivers enumerate at burst.c:4137/4157 (accelerated) and 4344/4365 (all-vs-all)
+ * -- returning, per task and lane, what the reference would have pushed as a ResultPod
+ * (burst.c:3999-4004, 4228-4238): the lanes whose edit distance equals the per-query minimum
+ * (BEST / ALLPATHS / CAPITALIST) or all lanes within budget (FORAGE), each with the pass-2
+ * integers of MetaPack (burst.c:222-226).  The float identity is derived on the host from
+ * these integers exactly as burst.c:844-860 does.
+ *
+ * Conventions: plain pointers and sizes; the caller owns every buffer it passes; every function
+ * returns 0 on success and a non-zero BG_E* code on failure, with a message available from
+ * bg_last_error() (the reference prints and exit()s; the CLI layer maps codes to its exit
+ * statuses).  A context is bound to one CUDA device and one host thread at
+ * a time.  There is no CPU fallback behind this ABI: without a CUDA device bg_init fails.
+ */
+#ifndef BURST_B200_H
+#define BURST_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct bg_ctx bg_ctx;
+
+enum { BG_OK = 0, BG_EINVAL = 1, BG_ECUDA = 3, BG_EOVERFLOW = 4, BG_ENOMEM = 5 };
+
+/* Which lanes are reported (burst.c:4219-4224): */
+enum { BG_MODE_MIN = 0,   /* lanes at the per-slot minimum: BEST, ALLPATHS, CAPITALIST */
+       BG_MODE_ALL = 1 }; /* every lane within budget: FORAGE */
+
+/* One DP task = one call pair aded_*() + reScoreM_*() of the reference: query j vs clump ri. */
+typedef struct { uint32_t query, clump; } bg_task;
+
+/* One reported lane = one ResultPod (burst.c:3999-4004) minus the host-only fields.
+ * refIx = tasks[task].clump * 16 + lane (burst.c:4234); ed = mismatches; gap_q = numGapQ
+ * (shift), gap_r = numGapR (shiftR), final_pos = 1-based end column in the clump. */
+typedef struct { uint32_t task; uint8_t lane, ed, gap_q, gap_r; uint32_t final_pos; } bg_hit;
+
+/* A batch of queries in BURST's translated form (burst.c:3005-3011): code bytes 0..15.
+ * budget[i] = Emac the reference would start query i with (ShrBin.ed, burst.c:3069-3081),
+ * slot[i]   = index of the running-minimum cell the query shares with its reverse complement
+ *             (Ub->six, burst.c:4158, 4218); slot[i] < nslots. */
+typedef struct {
+	const uint8_t  *codes;
+	const uint64_t *offset;     /* nq + 1 entries into codes */
+	const uint16_t *budget;     /* nq, each <= 254 */
+	const uint32_t *slot;       /* nq */
+	uint32_t nq, nslots;
+} bg_queries;
+
+typedef struct {
+	uint64_t tasks;             /* (query, clump) pairs evaluated */
+	uint64_t nominal_cells;     /* sum over tasks of 16 * qlen * ClumpLen */
+	uint64_t filter_cells;      /* DP cells covered by the bit-parallel prefix filter */
+	uint64_t survivors;         /* (task, lane) pairs handed to the banded pass */
+	uint64_t band_cells;        /* DP cells updated by the banded pass (x3 values each) */
+	uint64_t hits;              /* lanes reported */
+	float ms_filter, ms_extend, ms_select;   /* device time of the last bg_batch_run */
+} bg_stats;
+
+/* ---- lifetime ---- */
+int  bg_init(int device, bg_ctx **ctx);
+void bg_free(bg_ctx *ctx);
+const char *bg_last_error(void);
+/* Run every kernel and copy of this context on an existing CUDA stream (cudaStream_t). */
+int  bg_set_stream(bg_ctx *ctx, void *cuda_stream);
+
+/* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),
+ * S[q*16+r] in {0,1,255}; call before aligning (default: Z=1 table). */
+int  bg_set_scoring(bg_ctx *ctx, const uint8_t S[256]);
+/* Fill S with the reference's table for Z (1 = penalise N, the default; 0 = -y). */
+void bg_default_scoring(int z, uint8_t S[256]);
+
+/* ---- database: clumps in the .edx on-disk clump layout (burst.c:2810-2824): clump i is
+ * ceil(clump_len[i]/2) vectors of 16 bytes, byte k of a vector = lane k, low nibble = position
+ * 2v, high nibble = position 2v+1; clumps are contiguous in `packed`.  first_clump is the
+ * global id of packed clump 0 (non-zero when this device holds one shard of a larger DB;
+ * tasks naming clumps outside [first_clump, first_clump+num_clumps) are skipped). */
+int  bg_load_db(bg_ctx *ctx, const uint8_t *packed, const uint32_t *clump_len,
+                uint32_t num_clumps, uint32_t first_clump);
+
+/* ---- one batch, three steps (resident form used by bench.py's kernel-only timing) ---- */
+/* Host -> device copy of queries and tasks.  tasks == NULL means all-vs-all in the
+ * reference's fallback order (burst.c:4344, 4365): task t = clump (t / nq), query (t % nq). */
+int  bg_batch_upload(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint64_t ntasks);
+/* best_in: nslots running minima carried in from earlier batches (NULL = none). */
+int  bg_batch_run(bg_ctx *ctx, int mode, const uint16_t *best_in);
+/* Split form of bg_batch_run for a reference-sharded DB: filter+extend, then an external
+ * all-reduce(MIN) over the device array bg_batch_best_device() (nslots x uint32), then select. */
+int  bg_batch_run_extend(bg_ctx *ctx, int mode, const uint16_t *best_in);
+void *bg_batch_best_device(bg_ctx *ctx);
+int  bg_batch_run_select(bg_ctx *ctx, int mode);
+/* Device -> host: number of hits, then the hits sorted by (task, lane), and the per-slot
+ * minima (0xFFFF = no lane within budget).  Either output pointer may be NULL. */
+int  bg_batch_count(bg_ctx *ctx, uint64_t *nhits);
+int  bg_batch_download(bg_ctx *ctx, bg_hit *hits, uint64_t cap, uint16_t *best_out);
+int  bg_batch_stats(bg_ctx *ctx, bg_stats *out);
+
+/* ---- the one-call form the host driver uses: upload + run + download.  *hits is
+ * malloc()ed by the library (free with bg_free_hits). */
+int  bg_align_batch(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint64_t ntasks,
+                    int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits);
+void bg_free_hits(bg_hit *hits);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

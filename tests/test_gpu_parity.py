@@ -1,0 +1,180 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bit-exact on every integer the reference reports: edit distance, numGapQ, numGapR, finalPos,
+the set of reported (task, lane) pairs and the per-slot minima."""
+import numpy as np
+import pytest
+from burst_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from burst_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def all_vs_all(nq, nc):
+    tq = np.tile(np.arange(nq, dtype=np.uint32), nc)
+    tc = np.repeat(np.arange(nc, dtype=np.uint32), nq)
+    return tq, tc
+
+
+def check(eng, oracle, packed, off, clen, reads, budget, tasks=None, mode=0, slot=None, nslots=0, z=1, best=None):
+    codes, qoff = synth.concat_queries(reads)
+    nq = len(reads)
+    budget = np.asarray(budget, np.uint16)
+    if slot is None:
+        slot = np.arange(nq, dtype=np.uint32); nslots = nq
+    S = oracle.score_table(z)
+    eng.set_scoring(S)
+    eng.load_db(packed, clen)
+    if tasks is None:
+        tq, tc = all_vs_all(nq, len(clen))
+        gt = None
+    else:
+        tq, tc = tasks
+        gt = np.stack([tq, tc], 1).astype(np.uint32)
+    hits, gbest = eng.align(codes, qoff, budget, gt, mode, slot=slot, nslots=nslots, best=best)
+    ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nslots, tq, tc, S, mode, best=best)
+    assert np.array_equal(gbest, obest), "per-slot minima differ"
+    assert len(hits) == len(ohits), (len(hits), len(ohits))
+    assert np.array_equal(hits, ohits), "hits differ: first diff %s" % (
+        next(((tuple(a), tuple(b)) for a, b in zip(hits, ohits) if tuple(a) != tuple(b)), None),)
+    return hits, eng.stats()
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_c1_shape_all_vs_all(eng, oracle, mode):
+    """configs[0] shape, scaled: 100 bp reads, 0-3 edits vs 1 kb references, -i 0.97 (budget 3)."""
+    rng = np.random.default_rng(20261017)
+    refs = synth.random_refs(96, 1000, rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, _ = synth.reads_from_clumps(packed, off, clen, 300, 100, 3, rng)
+    budget = [oracle.budget(0.97, len(r)) for r in reads]
+    hits, st = check(eng, oracle, packed, off, clen, reads, budget, mode=mode)
+    assert len(hits) >= 290
+
+
+def test_acx_shape_task_list_with_shared_slots(eng, oracle):
+    """configs[1] shape: ~214-column clumps, 100 bp reads with exactly 2 edits, forward + reverse
+    complement copies sharing one running minimum (burst.c:4218), explicit candidate lists."""
+    rng = np.random.default_rng(5)
+    refs = synth.random_refs(16 * 200, 214, rng, jitter=8)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 400, 100, 2, rng, exact_edits=True, rc_rate=0.5)
+    fwd_rc = []
+    for r in reads:
+        fwd_rc += [r, synth.RC_TABLE[r[::-1]]]
+    nq = len(fwd_rc)
+    slot = (np.arange(nq) // 2).astype(np.uint32)
+    tq, tc = [], []
+    for i in range(nq):
+        cands = {int(origin[i // 2, 0])} | set(int(v) for v in rng.integers(0, len(clen), 6))
+        for c in sorted(cands):
+            tq.append(i); tc.append(c)
+    budget = [oracle.budget(0.98, len(r)) for r in fwd_rc]
+    hits, st = check(eng, oracle, packed, off, clen, fwd_rc, budget,
+                     tasks=(np.array(tq, np.uint32), np.array(tc, np.uint32)), slot=slot, nslots=nq // 2)
+    assert len(hits) >= 380
+
+
+@pytest.mark.parametrize("z", [1, 0])
+def test_iupac_and_ragged(eng, oracle, z):
+    """configs[4] shape: 50-320 bp queries with ambiguous bases, ragged clumps with pads, -i 0.95."""
+    rng = np.random.default_rng(99 + z)
+    refs = synth.random_refs(16 * 12, 500, rng, jitter=150, iupac_rate=0.01)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads = []
+    for i in range(120):
+        L = int(rng.integers(50, 321))
+        r, _ = synth.reads_from_clumps(packed, off, clen, 1, min(L, 340), int(0.04 * L), rng)
+        r = r[0]
+        m = rng.random(len(r)) < 0.005
+        r[m] = rng.integers(5, 16, size=int(m.sum()), dtype=np.uint8)
+        reads.append(r)
+    budget = [oracle.budget(0.95, len(r)) for r in reads]
+    hits, st = check(eng, oracle, packed, off, clen, reads, budget, mode=0, z=z)
+    assert len(hits) > 50
+    check(eng, oracle, packed, off, clen, reads[:40], budget[:40], mode=1, z=z)
+
+
+def test_short_queries_and_edges(eng, oracle):
+    """Queries shorter than the 32-row filter, hits hanging over either end of the window,
+    a clump shorter than the query, zero budget, a query containing a non-letter (code 0)."""
+    rng = np.random.default_rng(3)
+    refs = synth.random_refs(31, 120, rng, jitter=30) + [rng.integers(1, 5, 40, dtype=np.uint8)]
+    packed, off, clen = synth.pack_clumps(refs)
+    reads = []
+    for i in range(60):
+        r = refs[int(rng.integers(0, len(refs)))]
+        n = int(rng.integers(4, 60))
+        kind = i % 4
+        if kind == 0:   # inside
+            o = int(rng.integers(0, max(1, len(r) - n))); q = r[o:o + n].copy()
+        elif kind == 1:  # hangs over the left end by up to 2 bases
+            h = int(rng.integers(1, 3)); q = np.concatenate([rng.integers(1, 5, h, dtype=np.uint8), r[:n]])
+        elif kind == 2:  # hangs over the right end
+            h = int(rng.integers(1, 3)); q = np.concatenate([r[-n:], rng.integers(1, 5, h, dtype=np.uint8)])
+        else:
+            q = synth.mutate(r[:n], 1, rng)
+        reads.append(q.astype(np.uint8))
+    bad = reads[5].copy(); bad[len(bad) // 2] = 0; reads.append(bad)
+    reads.append(refs[0][:100].copy() if len(refs[0]) >= 100 else refs[0].copy())
+    for budget in (0, 1, 2, 4):
+        check(eng, oracle, packed, off, clen, reads, [budget] * len(reads), mode=0)
+    check(eng, oracle, packed, off, clen, reads, [3] * len(reads), mode=1)
+
+
+def test_large_budget_wide_bands(eng, oracle):
+    """Budgets where the 32-row filter is weak: wide hulls, the 64-wide and the generic band kernels."""
+    rng = np.random.default_rng(11)
+    refs = synth.random_refs(32, 420, rng, jitter=20)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, _ = synth.reads_from_clumps(packed, off, clen, 24, 300, 20, rng)
+    for k in (9, 16, 30):
+        check(eng, oracle, packed, off, clen, reads, [k] * len(reads), mode=0)
+    check(eng, oracle, packed, off, clen, reads[:8], [16] * 8, mode=1)
+
+
+def test_running_minimum_carried_between_batches(eng, oracle):
+    rng = np.random.default_rng(21)
+    refs = synth.random_refs(64, 300, rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, _ = synth.reads_from_clumps(packed, off, clen, 50, 100, 3, rng)
+    best = rng.integers(0, 4, len(reads)).astype(np.uint16)
+    check(eng, oracle, packed, off, clen, reads, [3] * len(reads), mode=0, best=best)
+
+
+def test_reference_shard_skips_foreign_clumps(eng, oracle):
+    """first_clump != 0: tasks naming clumps of other shards are skipped."""
+    rng = np.random.default_rng(8)
+    refs = synth.random_refs(16 * 8, 250, rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, _ = synth.reads_from_clumps(packed, off, clen, 64, 100, 2, rng)
+    codes, qoff = synth.concat_queries(reads)
+    nq = len(reads); budget = np.full(nq, 2, np.uint16)
+    tq, tc = all_vs_all(nq, len(clen))
+    eng.set_scoring(oracle.score_table(1))
+    full, fbest = None, None
+    eng.load_db(packed, clen)
+    full, fbest = eng.align(codes, qoff, budget, np.stack([tq, tc], 1))
+    # two shards of 4 clumps each, minima combined by MIN, then select
+    parts = []
+    bests = []
+    for s in range(2):
+        lo, hi = s * 4, s * 4 + 4
+        eng.load_db(packed[int(off[lo]):int(off[hi]) if hi < len(off) else len(packed)], clen[lo:hi], first_clump=lo)
+        eng.upload(codes, qoff, budget, np.stack([tq, tc], 1))
+        eng.run_extend(0)
+        eng.run_select(1)      # keep everything within budget; the host applies the global minimum
+        h, b = eng.download()
+        parts.append(h); bests.append(b)
+    gbest = np.minimum(bests[0], bests[1])
+    assert np.array_equal(gbest, fbest)
+    allh = np.concatenate(parts)
+    keep = allh[allh["ed"] == gbest[tq[allh["task"]]]]
+    keep = keep[np.lexsort((keep["lane"], keep["task"]))]
+    assert np.array_equal(keep, full)
