@@ -1,0 +1,283 @@
+#!/usr/bin/env python
+"""bench.py -- BURST alignment hot path on B200: reads/s and DP GCUPS (BASELINE.json metric).
+
+A "step" is one pass of the hot path (prefix filter -> banded extend/rescore -> select) over one
+batch: BASELINE.json configs[1] shape, 1 M synthetic 100 bp reads with exactly 2 edits (the
+reference simulator's model, embalmlets/LLsim.c) against a 2 GB synthetic .edx-layout database,
+-i 0.98 (budget 2), BEST-style minimum selection, forward + reverse-complement strands, task list
+= what the reference's accelerated driver enumerates (bunches of 16 sorted strands x the bunch's
+candidate clumps, burst.c:4077-4157).
+
+  value     whole-job reads/s with queries, tasks and DB resident in HBM (kernels only)
+  e2e       the same through bg_align_batch(): pinned host buffers in, hits in host memory out
+  roofline  dominant kernel (k_filter) algorithmic bytes / its CUDA-event time vs measured HBM peak
+            -- the kernel is integer-ALU bound, see "alu" and DESIGN.md
+  cpu_baseline / --impl reference
+            the reference's own aded_mat16L + reScoreM_mat16 (oracle/_ref/libburstref.so, built
+            from /root/reference/burst.c) driven in the reference's loop shape on the host cores
+
+Launch: python bench.py [--gpus N --steps K --warmup W]   (N>1 under torch.distributed.run)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--reads", type=int, default=1_000_000, help="reads per GPU per step")
+    ap.add_argument("--db-mb", type=int, default=2048)
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--edits", type=int, default=2)
+    ap.add_argument("--clump-len", type=int, default=214)
+    ap.add_argument("--cpu-sample-bunches", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.index = index
+        self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx = float(f[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def build_workload(args, rank):
+    from burst_b200 import synth
+    t0 = time.time()
+    w = synth.bunch_workload(args.reads, args.read_len, args.edits, args.db_mb << 20, args.clump_len, seed=20261017 + rank)
+    w["gen_s"] = time.time() - t0
+    return w
+
+
+def cpu_reference(args, w, steps=1, warmup=0):
+    """The reference's kernels on the host cores over a bounded sample of the same task list."""
+    from oracle import pyoracle
+    threads = os.cpu_count() or 1
+    qb = w["qbunch"]
+    nb_all = (len(w["qoff"]) - 1 + qb - 1) // qb
+    if pyoracle.Reference.available():
+        ref = pyoracle.Reference()
+        kind = "reference"
+        nb = args.cpu_sample_bunches
+        if not nb:
+            probe = min(nb_all, 256 * threads)
+            t0 = time.perf_counter(); pyoracle.reference_run_bunches(ref, w, probe, threads); dt = time.perf_counter() - t0
+            nb = int(min(nb_all, max(probe, probe * 4.0 / max(dt, 1e-3))))     # ~4 s per step
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            r = pyoracle.reference_run_bunches(ref, w, nb, threads)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        nq = r["nq"]
+        found = int((r["ed"][np.unique(w["slot"][:nq])] <= args.edits).sum())
+        desc = "reference kernels aded_mat16L+reScoreM_mat16 (burst.c) in the reference's bunch loop, first %d of %d bunches = %d strands (%d pass-1 calls, %d truncated, %d pass-2), %d threads" % (
+            nb, nb_all, nq, r["calls"], r["truncated"], r["rescore"], threads)
+    else:
+        # port: scalar oracle, one thread per OpenMP worker, far smaller sample
+        orc = pyoracle.Oracle()
+        kind = "port"
+        nb = args.cpu_sample_bunches or 8
+        nq = min(len(w["qoff"]) - 1, nb * qb)
+        tk = w["tasks"][w["tasks"][:, 0] < nq]
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            orc.run_tasks(w["packed"], w["clump_off"], w["clump_len"], w["qcodes"], w["qoff"], w["budget"], w["slot"], w["nslots"],
+                          tk[:, 0], tk[:, 1], orc.score_table(1), 0)
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+        desc = "scalar oracle port, first %d bunches = %d strands, %d tasks" % (nb, nq, len(tk))
+    dt = float(np.mean(times))
+    reads = nq / 2.0
+    return {"value": reads / dt, "unit": "reads/s", "cores": threads, "kind": kind, "sample": desc,
+            "seconds_per_step": dt, "reads_in_sample": reads}, dt
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": "configs[1]: %d x %d bp reads (exactly %d edits, LLsim model, fwd+rc strands) per GPU vs %d MB synthetic .edx-layout DB (%d-column clumps), -i 0.98 budget %d, BEST-style min selection, task list = reference bunch driver (QBUNCH 16 x bunch candidates)" % (
+        args.reads, args.read_len, args.edits, args.db_mb, args.clump_len, args.edits),
+        "reads_per_gpu": args.reads, "db_mb": args.db_mb, "sharding": "queries (DB replicated), no data-path collective",
+        "l2": "inputs (DB %d MB + tasks) exceed the 126 MB L2; no explicit flush" % args.db_mb}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        w = build_workload(args, 0)
+        cb, dt = cpu_reference(args, w, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        out = {"impl": "reference", "metric": "reads_per_sec", "value": cb["value"], "unit": "reads/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the DP path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from burst_b200.engine import Engine, MODE_MIN, TASK_DTYPE
+
+    w = build_workload(args, rank)
+    stream = torch.cuda.Stream()
+    eng = Engine(local, stream=stream.cuda_stream)
+    eng.load_db(w["packed"], w["clump_len"])
+    nq = len(w["qoff"]) - 1
+    tasks = np.ascontiguousarray(w["tasks"]).view(TASK_DTYPE).reshape(-1)
+
+    # pinned host staging for the e2e leg
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
+        return t.numpy().view(a.dtype).reshape(a.shape), t
+    p_codes, k1 = pin(w["qcodes"]); p_off, k2 = pin(w["qoff"]); p_bud, k3 = pin(w["budget"]); p_slot, k4 = pin(w["slot"]); p_tasks, k5 = pin(tasks)
+    h2d = p_codes.nbytes + p_off.nbytes + p_bud.nbytes + p_slot.nbytes + p_tasks.nbytes
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- kernel-only: inputs resident in HBM ----------------
+    eng.upload(p_codes, p_off, p_bud, p_tasks, slot=p_slot, nslots=w["nslots"])
+    for _ in range(args.warmup):
+        eng.run(MODE_MIN); eng.count()
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    ms_filter = []
+    with torch.cuda.stream(stream):
+        e0.record(stream)
+        for _ in range(args.steps):
+            eng.run(MODE_MIN)
+        e1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop()
+    ms_total = e0.elapsed_time(e1)
+    nhits = eng.count()
+    st = eng.stats()
+    hits, best = eng.download()
+    found = int((best[:w["n_reads"]] <= args.edits).sum())
+    # planted-read check: every read must be reported at the lane it was cut from
+    tq = w["tasks"][hits["task"], 0]; tc = w["tasks"][hits["task"], 1]
+    rd = w["slot"][tq]
+    ok = (tc == w["true_clump"][rd]) & (hits["lane"] == w["true_lane"][rd])
+    planted = int(len(np.unique(rd[ok])))
+
+    # ---------------- e2e: host buffers in, hits out, every step ----------------
+    d2h = 0
+    for _ in range(min(args.warmup, 2)):
+        eng.align(p_codes, p_off, p_bud, p_tasks, MODE_MIN, slot=p_slot, nslots=w["nslots"])
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        h, b = eng.align(p_codes, p_off, p_bud, p_tasks, MODE_MIN, slot=p_slot, nslots=w["nslots"])
+        d2h = h.nbytes + b.nbytes
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([ms_total, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = (float(x) for x in times.cpu())
+    ms_step = ms_total / args.steps
+    total_reads = args.reads * world
+    value = total_reads / (ms_step / 1e3)
+    e2e_value = total_reads / (e2e_ms / 1e3 / args.steps)
+
+    if rank == 0:
+        peak, how = peaks()
+        alg_bytes = float((8 * w["clump_len"][w["tasks"][:, 1]].astype(np.int64) + args.read_len + 16).sum()) + 12.0 * nhits
+        filt_ms = st["ms_filter"]
+        achieved = alg_bytes / (filt_ms / 1e3) / 1e9
+        out = {"metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-vectors / u32 packed keys (8-bit reference semantics)",
+               "data": "synthetic", "config": config,
+               "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
+               "gpu_launches": 8 * args.steps,
+               "dp_gcups_nominal": st["nominal_cells"] * world / (ms_step / 1e3) / 1e9,
+               "dp_gcups_executed": (st["filter_cells"] + st["band_cells"]) * world / (ms_step / 1e3) / 1e9,
+               "work": {"tasks": st["tasks"], "survivors": st["survivors"], "hits": st["hits"], "nominal_cells": st["nominal_cells"],
+                        "filter_cells": st["filter_cells"], "band_cells": st["band_cells"], "reads_found": found, "reads_at_planted_lane": planted,
+                        "ms_filter": st["ms_filter"], "ms_extend": st["ms_extend"], "ms_select": st["ms_select"]},
+               "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                            "kernel": "k_filter", "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst figure)",
+                            "note": "k_filter is integer-ALU bound, not HBM bound (see DESIGN.md); algorithmic bytes = sum over tasks of 8*ClumpLen+len+16, +12 per hit"},
+               "alu": {"filter_column_lanes_per_s": st["filter_cells"] / 32.0 / (filt_ms / 1e3) if args.read_len >= 32 else None},
+               "clocks": clocks, "workload_gen_s": w["gen_s"]}
+        if not args.no_cpu_baseline and world == 1:
+            cb, _ = cpu_reference(args, w)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -123,3 +123,138 @@ def to_fasta(path, names, seqs):
     with open(path, "w") as f:
         for n, s in zip(names, seqs):
             f.write(">%s\n%s\n" % (n, "".join(ALPHABET[int(c)] for c in s)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Vectorised generators for the bench-sized workloads (BASELINE.json configs[1] shape)
+# ---------------------------------------------------------------------------------------------
+
+def gather_windows(packed, nvec, clump, lane, offset, length):
+    """Codes of `length` consecutive positions starting at `offset` of (clump, lane), for arrays
+    of reads, from equal-length packed clumps (nvec vectors each)."""
+    x = offset[:, None].astype(np.int64) + np.arange(length, dtype=np.int64)[None, :]
+    byte = clump[:, None].astype(np.int64) * (nvec * 16) + (x >> 1) * 16 + lane[:, None].astype(np.int64)
+    b = packed[byte]
+    return np.where(x & 1, b >> 4, b & 15).astype(np.uint8)
+
+
+def llsim_reads(packed, nclumps, clump_len, n, read_len, n_err, rng, rc=True, chunk=1 << 17):
+    """n reads in the model of the reference's simulator embalmlets/LLsim.c:175-222: a window of
+    read_len reference bases, exactly n_err edits at distinct positions, each a substitution
+    (3/5), a deletion (1/5) or an insertion before the base (1/5); ~half reverse-complemented
+    when rc.  Returns (codes, offsets[n+1], clump[n], lane[n], start[n], rcflag[n])."""
+    nvec = (clump_len + 1) // 2
+    all_codes, lens = [], []
+    clump = rng.integers(0, nclumps, n, dtype=np.int64)
+    lane = rng.integers(0, 16, n, dtype=np.int64)
+    start = rng.integers(0, clump_len - read_len + 1, n, dtype=np.int64)
+    rcflag = (rng.random(n) < 0.5) if rc else np.zeros(n, bool)
+    for s in range(0, n, chunk):
+        e = min(n, s + chunk); m = e - s
+        w = gather_windows(packed, nvec, clump[s:e], lane[s:e], start[s:e], read_len)
+        ins = np.zeros((m, read_len), np.uint8)          # symbol emitted before the base (0 = none)
+        if n_err:
+            pos = np.argsort(rng.random((m, read_len), dtype=np.float32), axis=1)[:, :n_err]
+            typ = rng.integers(0, 5, (m, n_err))
+            rows = np.repeat(np.arange(m), n_err); cols = pos.reshape(-1); t = typ.reshape(-1)
+            sub = t < 3
+            old = w[rows[sub], cols[sub]].astype(np.int64)
+            w[rows[sub], cols[sub]] = ((old - 1 + 1 + t[sub]) % 4 + 1).astype(np.uint8)
+            w[rows[t == 3], cols[t == 3]] = 0                # deleted
+            i4 = t == 4
+            ins[rows[i4], cols[i4]] = rng.integers(1, 5, int(i4.sum()), dtype=np.uint8)
+        both = np.stack([ins, w], axis=2).reshape(m, -1)
+        keep = both != 0
+        lens.append(keep.sum(1))
+        all_codes.append(both[keep])
+    lens = np.concatenate(lens).astype(np.uint64)
+    off = np.zeros(n + 1, np.uint64); off[1:] = np.cumsum(lens)
+    codes = np.concatenate(all_codes)
+    if rc:
+        rcodes = reverse_complement_all(codes, off)
+        sel = np.repeat(rcflag, lens.astype(np.int64))
+        codes = np.where(sel, rcodes, codes)
+    return codes, off, clump, lane, start, rcflag
+
+
+def reverse_complement_all(codes, off):
+    """Reverse-complement every read of a concatenated (codes, offsets) set (burst.c:3095-3103)."""
+    lens = np.diff(off).astype(np.int64)
+    rid = np.repeat(np.arange(len(lens)), lens)
+    o = off[:-1].astype(np.int64)
+    idx = np.arange(len(codes), dtype=np.int64)
+    src = o[rid] + (lens[rid] - 1 - (idx - o[rid]))
+    return RC_TABLE[codes[src]]
+
+
+def sort_strands(codes, off):
+    """Order of the strands under strcmp on code bytes (burst.c:3021, 3181-3184)."""
+    lens = np.diff(off).astype(np.int64)
+    width = int(lens.max()) + 1
+    mat = np.zeros((len(lens), width), np.uint8)
+    rid = np.repeat(np.arange(len(lens)), lens)
+    col = np.arange(len(codes), dtype=np.int64) - off[:-1].astype(np.int64)[rid]
+    mat[rid, col] = codes
+    keys = mat.view("S%d" % width).reshape(-1)
+    return np.argsort(keys, kind="stable")
+
+
+def bunch_workload(n_reads, read_len, n_err, db_bytes, clump_len, seed, qbunch=16, budget=None):
+    """BASELINE.json configs[1] shape as the reference's accelerated driver sees it: forward and
+    reverse-complement strands of every read, sorted, cut into bunches of `qbunch`
+    (burst.c:4019-4021); every query of a bunch visits every candidate clump of the bunch
+    (burst.c:4137-4157).  Candidates = the clump each read was cut from (what the .acx lookup
+    returns for error-bounded reads on a random DB: random 15-mer hits never reach the
+    len-(ed+1)*N threshold, burst.c:4091-4095)."""
+    rng = np.random.default_rng(seed)
+    nvec = (clump_len + 1) // 2
+    nclumps = max(16, int(db_bytes // (nvec * 16)))
+    packed, coff, clens = random_clumps_fast(nclumps, clump_len, np.random.default_rng(1000003))
+    codes, off, clump, lane, start, rcflag = llsim_reads(packed, nclumps, clump_len, n_reads, read_len, n_err, rng)
+    rcodes = reverse_complement_all(codes, off)
+    lens = np.diff(off).astype(np.int64)
+    # strands: 2i = as sequenced, 2i+1 = its reverse complement; the strand equal to the DB lane matches
+    scodes = np.concatenate([codes, rcodes])
+    soff = np.zeros(2 * n_reads + 1, np.uint64)
+    soff[1:] = np.cumsum(np.concatenate([lens, lens]))
+    sread = np.concatenate([np.arange(n_reads), np.arange(n_reads)])
+    smatch = np.concatenate([~rcflag, rcflag])
+    order = sort_strands(scodes, soff)
+    # rebuild in sorted order
+    slen = np.diff(soff).astype(np.int64)[order]
+    qoff = np.zeros(len(order) + 1, np.uint64); qoff[1:] = np.cumsum(slen)
+    src = np.repeat(soff[:-1].astype(np.int64)[order], slen) + (np.arange(int(qoff[-1]), dtype=np.int64) - np.repeat(qoff[:-1].astype(np.int64), slen))
+    qcodes = scodes[src]
+    slot = sread[order].astype(np.uint32)
+    match = smatch[order]
+    nq = len(order)
+    bunch_of = np.arange(nq) // qbunch
+    pairs = np.unique(np.stack([bunch_of[match], clump[slot[match]]], 1), axis=0)   # (bunch, clump), sorted
+    nb = (nq + qbunch - 1) // qbunch
+    cand_off = np.zeros(nb + 1, np.uint64)
+    np.add.at(cand_off, pairs[:, 0] + 1, 1)
+    cand_off = np.cumsum(cand_off).astype(np.uint64)
+    cand = pairs[:, 1].astype(np.uint32)
+    # tasks in the reference's loop order: bunch, candidate clump, query of the bunch
+    qstart = pairs[:, 0] * qbunch
+    qcount = np.minimum(qbunch, nq - qstart)
+    tq = np.repeat(qstart, qcount) + (np.arange(int(qcount.sum())) - np.repeat(np.cumsum(qcount) - qcount, qcount))
+    tc = np.repeat(cand, qcount)
+    tasks = np.stack([tq, tc], 1).astype(np.uint32)
+    if budget is None:
+        budget = np.full(nq, n_err, np.uint16)
+    return dict(packed=packed, clump_off=coff, clump_len=clens, qcodes=qcodes, qoff=qoff, slot=slot,
+                nslots=n_reads, budget=budget, tasks=tasks, cand_off=cand_off, cand=cand, qbunch=qbunch,
+                true_clump=clump, true_lane=lane, true_start=start, n_reads=n_reads, match=match)
+
+
+def random_clumps_fast(nclumps, clump_len, rng):
+    """Uniform ACGT clumps of one length in packed .edx clump form, from raw random bytes."""
+    nv = (clump_len + 1) // 2
+    raw = np.frombuffer(rng.bytes(nclumps * nv * 16), np.uint8)
+    packed = ((raw & 3) + 1) | ((((raw >> 2) & 3) + 1) << 4)
+    packed = packed.astype(np.uint8)
+    if clump_len & 1:
+        packed.reshape(nclumps, nv, 16)[:, -1, :] &= 15
+    off = np.arange(nclumps, dtype=np.uint64) * np.uint64(nv * 16)
+    return packed, off, np.full(nclumps, clump_len, np.uint32)

@@ -142,3 +142,40 @@ class Reference:
             _p(np.ascontiguousarray(task_clump, np.uint32)), _p(np.ascontiguousarray(task_off, np.uint64)),
             C.c_int(threads), _p(best), C.byref(nres), C.byref(nhits))
         return int(calls), best, int(nres.value), int(nhits.value)
+
+
+def nul_terminated(qcodes, qoff):
+    """Concatenated code strings -> the reference's NUL-terminated form; returns (bytes, offsets, lens)."""
+    lens = np.diff(qoff).astype(np.int64)
+    n = len(lens)
+    out = np.zeros(int(lens.sum()) + n, np.uint8)
+    noff = (qoff[:-1].astype(np.int64) + np.arange(n)).astype(np.uint64)
+    rid = np.repeat(np.arange(n), lens)
+    dst = np.arange(len(qcodes), dtype=np.int64) + rid
+    out[dst] = qcodes
+    return out, noff, lens.astype(np.uint32)
+
+
+def reference_run_bunches(ref, w, nbunches=None, threads=1):
+    """Drive Reference (libburstref.so) over the first nbunches bunches of a synth.bunch_workload."""
+    qb = w["qbunch"]
+    nq_all = len(w["qoff"]) - 1
+    nb_all = (nq_all + qb - 1) // qb
+    nb = nb_all if nbunches is None else min(nbunches, nb_all)
+    nq = min(nq_all, nb * qb)
+    qc, noff, lens = nul_terminated(w["qcodes"][:int(w["qoff"][nq])], w["qoff"][:nq + 1])
+    ed = np.full(w["nslots"], 0, np.uint16)
+    ed[w["slot"][:nq]] = w["budget"][:nq]          # ShrBins[].ed starts at the budget (burst.c:3076)
+    budget0 = ed.copy()
+    nres = C.c_uint64(0); nhits = C.c_uint64(0); ninst = C.c_uint64(0)
+    L = ref.lib
+    L.refshim_run_bunches.restype = C.c_uint64
+    calls = L.refshim_run_bunches(
+        _p(w["packed"]), _p(np.ascontiguousarray(w["clump_off"], np.uint64)),
+        _p(np.ascontiguousarray(w["clump_len"], np.uint32)), C.c_uint32(int(w["clump_len"].max())),
+        _p(qc), _p(noff), _p(lens), _p(np.ascontiguousarray(w["slot"][:nq], np.uint32)), _p(ed),
+        C.c_uint64(nq), C.c_uint32(qb), _p(np.ascontiguousarray(w["cand_off"][:nb + 1], np.uint64)),
+        _p(np.ascontiguousarray(w["cand"], np.uint32)), C.c_int(threads),
+        C.byref(nres), C.byref(nhits), C.byref(ninst))
+    return dict(calls=int(calls), rescore=int(nres.value), lanes=int(nhits.value), truncated=int(ninst.value),
+                ed=ed, budget0=budget0, nq=nq, nb=nb)

@@ -158,3 +158,100 @@ uint64_t refshim_run_tasks(const uint8_t *packed, const uint64_t *clump_off, con
 	*n_rescore = resc; *n_hits = hits;
 	return calls;
 }
+
+/* CPU baseline in the reference's own loop shape: the accelerated driver of do_alignments
+ * (burst.c:4136-4279), restated around the reference's unmodified kernels.  Queries are the
+ * sorted unique query strands (NUL-terminated code strings, qoff[j] .. ), processed in bunches
+ * of `qbunch` consecutive queries (burst.c:4019-4021, 4077-4078); bunch b visits the candidate
+ * clumps cand[cand_off[b] .. cand_off[b+1]) in the given order, and inside a clump every query
+ * of the bunch, with
+ *   - Emac = the running minimum its slot has reached so far (burst.c:4159, 4220),
+ *   - prefix-row reuse: the first row to recompute is 1 + the prefix shared with the query
+ *     whose rows are still valid in the cached matrix, tracked with a stack of (Emac, query)
+ *     because rows computed under a budget are only reusable under budgets <= it
+ *     (burst.c:4185-4211), and the instant truncation signal when the shared prefix already
+ *     died (burst.c:1108),
+ *   - pass 2 whenever a lane reaches the running minimum (burst.c:4217-4227).
+ * The per-query k-mer-count skip (burst.c:4163-4168) is not applied: the caller expands exactly
+ * the same (query, clump) pairs for the GPU arm.  ed_slot is shared and unsynchronised, as
+ * ShrBins[].ed is in the reference.  Returns the number of pass-1 calls. */
+__attribute__((visibility("default")))
+uint64_t refshim_run_bunches(const uint8_t *packed, const uint64_t *clump_off, const uint32_t *clump_len,
+		uint32_t max_clump_len, const char *qcodes, const uint64_t *qoff, const uint32_t *qlen,
+		const uint32_t *slot, uint16_t *ed_slot, uint64_t nq, uint32_t qbunch,
+		const uint64_t *cand_off, const uint32_t *cand, int threads,
+		uint64_t *n_rescore, uint64_t *n_hits, uint64_t *n_instant) {
+	uint64_t calls = 0, resc = 0, hits = 0, instant = 0;
+	uint32_t maxq = 0;
+	for (uint64_t q = 0; q < nq; ++q) if (qlen[q] > maxq) maxq = qlen[q];
+	int savedCache = cacheSz;
+	cacheSz = MIN((int)maxq + 2, cacheSz);                          /* burst.c:3193 */
+	/* divergence of consecutive sorted queries, burst.c:3195-3201 */
+	uint16_t *Div = malloc(nq * sizeof(*Div));
+	uint32_t maxDiv = 1;
+	Div[0] = 1;
+	for (uint64_t i = 1; i < nq; ++i) {
+		const char *a = qcodes + qoff[i-1], *b = qcodes + qoff[i];
+		uint32_t d = 1;
+		while (*a && *a++ == *b++) ++d;
+		d = MIN((uint32_t)cacheSz, d); d = MIN(qlen[i-1], d);
+		Div[i] = d; if (d > maxDiv) maxDiv = d;
+	}
+	uint64_t nb = (nq + qbunch - 1) / qbunch;
+	if (threads < 1) threads = 1;
+	#pragma omp parallel num_threads(threads) reduction(+:calls,resc,hits,instant)
+	{
+		ShimScratch *S = shim_new(max_clump_len + 1, maxq);
+		uint32_t *stE = malloc((maxq + 2 + qbunch) * sizeof(*stE));
+		uint64_t *stQ = malloc((maxq + 2 + qbunch) * sizeof(*stQ));
+		#pragma omp for schedule(dynamic,1)
+		for (uint64_t b = 0; b < nb; ++b) {
+			uint64_t z = b * qbunch, bound = MIN(z + qbunch, nq);
+			uint32_t minlen = (uint32_t)-1;
+			for (uint64_t j = z; j < bound; ++j) if (qlen[j] < minlen) minlen = qlen[j];
+			for (uint64_t ci = cand_off[b]; ci < cand_off[b+1]; ++ci) {
+				uint32_t ri = cand[ci], rlen = clump_len[ri] + 1;
+				shim_unpack(S, packed + clump_off[ri], clump_len[ri]);
+				S->HiBound[1] = rlen;
+				uint32_t sp = 0; stQ[0] = z; stE[0] = (uint32_t)-1;
+				for (uint64_t j = z; j < bound; ++j) {
+					uint16_t *edp = ed_slot + slot[j];
+					uint32_t Emac = *edp, len = qlen[j];
+					uint32_t thisDiv = j == z ? 1 : Div[j];
+					char *q = (char *)qcodes + qoff[j];
+					if (Emac > stE[sp]) {                      /* rows on top were computed under a smaller budget */
+						while (Emac > stE[--sp]);
+						thisDiv = 1;
+						if (j != z && Div[j] > 1 && sp) {
+							uint64_t o = stQ[sp];
+							uint32_t lim = MIN(qlen[o], len) - 1;
+							const char *p = qcodes + qoff[o];
+							for (uint32_t w = 0; w < lim && thisDiv < maxDiv && q[w] == p[w]; ++w) ++thisDiv;
+						}
+					}
+					sp += Emac < stE[sp];
+					stQ[sp] = j; stE[sp] = Emac;
+					DualCoil m;
+					uint32_t min = aded_mat16L(S->rclump, q, rlen, len, S->rdim, minlen, S->Matrices, 0,
+						Emac, thisDiv, S->LoBound, S->HiBound, &m);
+					++calls;
+					instant += (min == (uint32_t)-1);   /* pass-1 calls that ended in truncation */
+					if (min <= *edp) {
+						*edp = min;
+						MetaPack MPK __attribute__((aligned(64)));
+						reScoreM_mat16(S->rclump, q, rlen, len, S->rdim, S->ScoresEX, S->ShiftsEX,
+							S->ShiftsBX, min, 0, &MPK);
+						++resc;
+						for (int l = 0; l < 16; ++l) hits += m.u8[l] <= min;
+					}
+				}
+			}
+		}
+		free(stE); free(stQ);
+		shim_free(S);
+	}
+	free(Div);
+	cacheSz = savedCache;
+	*n_rescore = resc; *n_hits = hits; *n_instant = instant;
+	return calls;
+}
