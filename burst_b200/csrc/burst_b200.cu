@@ -131,6 +131,8 @@ struct FilterArgs {
 	const QInfo *qi; const uint32_t *peq; const bg_task *tasks;
 	uint64_t ntasks; uint32_t nq, first_clump, num_clumps;
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;   // [0] survivors, [1] scratch words, [2] hits
+	uint32_t two;        // the constant 2, passed at run time so ptxas keeps IMAD.HI / IMAD.WIDE (FMA pipe)
+	uint32_t c16;        // the constant 16, same reason
 };
 
 __device__ __forceinline__ void task_of(const FilterArgs &A, uint64_t t, uint32_t &q, uint32_t &c) {
@@ -138,6 +140,25 @@ __device__ __forceinline__ void task_of(const FilterArgs &A, uint64_t t, uint32_
 	else { q = (uint32_t)(t % A.nq); c = (uint32_t)(t / A.nq) + A.first_clump; }
 }
 
+// Hyyro's formulation of Myers' bit-vector step; the text character is one reference base.
+// Integer-pipe budget per column (ncu: the kernel is bound by the ALU pipe, LOP3/SHF/ISETP issue
+// at half rate): the seven 3-input logic ops below are irreducible, so everything that can run
+// on the FMA pipe instead is written as a multiply-add: the two shifts are x+x, the nibble
+// extraction is a mul.hi, and the row-P score is kept as two mad.hi accumulators (bit 31 of
+// Ph / Mh) that are only compared once per 8 columns.
+__device__ __forceinline__ uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) {
+	uint32_t d; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
+	uint32_t d; asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
+}
+#define MYERS_STEP(Eq)                                          \
+	const uint32_t Xv = (Eq) | Mv;                              \
+	const uint32_t Xh = ((((Eq) & Pv) + Pv) ^ Pv) | (Eq);       \
+	uint32_t Ph = Mv | ~(Xh | Pv);                              \
+	uint32_t Mh = Pv & Xh;
+
+template <int V>
 __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	__shared__ uint32_t sPeq[8][16];
 	const uint32_t slot = threadIdx.x >> 4, lane = threadIdx.x & 15;
@@ -156,10 +177,11 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	const int P = Q.P, k = Q.k;
 	const uint32_t L = A.clump_len[c];
 	const uint4 *base = A.db + A.clump_off[c] + lane;
-	const uint32_t *eq = sPeq[slot];
+	const char *eq = (const char *)sPeq[slot];
 
 	uint32_t Pv = P < 32 ? ~0u << (32 - P) : ~0u, Mv = 0;
-	int score = P, lo = INT32_MAX, hi = INT32_MIN;
+	uint32_t cP = (uint32_t)P, cM = 0;          // row-P value = cP - cM
+	int lo = INT32_MAX, hi = INT32_MIN;
 	const uint32_t nwords = (L + 7) >> 3;
 	uint4 w4 = base[0];
 	for (uint32_t wi0 = 0; wi0 < nwords; wi0 += 4) {
@@ -170,21 +192,72 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 		for (int wi = 0; wi < 4; ++wi) {
 			if (wi0 + wi >= nwords) break;
 			const uint32_t w = ws[wi];
+			const uint32_t Pv0 = Pv, Mv0 = Mv;
+			const int s0 = (int)(cP - cM);
+			if (V == 5) {
+				// as V == 4 but the shared address is formed on the ALU pipe (shift, and-or): no IMAD.HI
+				const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(eq);
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					const uint32_t sh = j == 0 ? w << 2 : w >> (4 * j - 2);
+					uint32_t Eq;
+					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"((sh & 0x3Cu) | eqs));
+					MYERS_STEP(Eq)
+					Ph += Ph; Mh += Mh;
+					Pv = Mh | ~(Xv | Ph);
+					Mv = Ph & Xv;
+				}
+				cP = (uint32_t)__popc(Pv); cM = (uint32_t)__popc(Mv);
+			} else if (V == 4) {
+				// ALU pipe: only the seven logic ops.  FMA pipe: nibble -> shared address (shl, mul.hi, mad),
+				// the add and the two shifts.  The row-P value is not tracked at all: it is
+				// popc(Pv) - popc(Mv) (sum of the vertical deltas over the pattern rows), read once per word.
+				const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(eq);
+				#pragma unroll
+				for (int j = 0; j < 8; ++j) {
+					const uint32_t code = mulhi(j == 7 ? w : w << (28 - 4 * j), A.c16);
+					uint32_t Eq;
+					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"(code * 4u + eqs));
+					MYERS_STEP(Eq)
+					Ph += Ph; Mh += Mh;
+					Pv = Mh | ~(Xv | Ph);
+					Mv = Ph & Xv;
+				}
+				cP = (uint32_t)__popc(Pv); cM = (uint32_t)__popc(Mv);
+			} else
 			#pragma unroll
 			for (int j = 0; j < 8; ++j) {
-				const uint32_t Eq = eq[(w >> (4 * j)) & 15];
-				// Hyyro's formulation of Myers' bit-vector step, text character = reference base
-				const uint32_t Xv = Eq | Mv;
-				const uint32_t Xh = (((Eq & Pv) + Pv) ^ Pv) | Eq;
-				uint32_t Ph = Mv | ~(Xh | Pv);
-				uint32_t Mh = Pv & Xh;
-				score += (int)(Ph >> 31) - (int)(Mh >> 31);          // row P lives in bit 31
-				Ph <<= 1; Mh <<= 1;                                   // row 0 is all zero: no carry-in
-				Pv = Mh | ~(Xv | Ph);
+				const uint32_t off = (j == 0 ? w * 4u : mulhi(w, 1u << (34 - 4 * j))) & 0x3Cu;   // code * 4
+				const uint32_t Eq = *(const uint32_t *)(eq + off);
+				MYERS_STEP(Eq)
+				if (V == 1) { cP = madhi(Ph, 2u, cP); cM = madhi(Mh, 2u, cM); Ph += Ph; Mh += Mh; }      // ptxas: LEA.HI (ALU)
+				else if (V == 2) { cP = madhi(Ph, A.two, cP); cM = madhi(Mh, A.two, cM); Ph += Ph; Mh += Mh; }  // IMAD.HI (FMA)
+				else {                                               // IMAD.WIDE: shift and bit 31 in one
+					uint64_t p2, m2;
+					asm("mul.wide.u32 %0, %1, %2;" : "=l"(p2) : "r"(Ph), "r"(A.two));
+					asm("mul.wide.u32 %0, %1, %2;" : "=l"(m2) : "r"(Mh), "r"(A.two));
+					Ph = (uint32_t)p2; Mh = (uint32_t)m2; cP += (uint32_t)(p2 >> 32); cM += (uint32_t)(m2 >> 32);
+				}
+				Pv = Mh | ~(Xv | Ph);                                // row 0 is all zero: no carry-in
 				Mv = Ph & Xv;
-				if (score <= k) {                                     // seed: D[P][x] <= k
+			}
+			// The row-P value moves by at most 1 per column, so inside these 8 columns it cannot
+			// drop below (s0 + s1 - 8) / 2.  Only then is a seed (value <= k) possible: redo the
+			// word column by column from the saved state.
+			const int s1 = (int)(cP - cM);
+			if (s0 + s1 - 8 <= 2 * k) {
+				uint32_t pv = Pv0, mv = Mv0; int score = s0;
+				#pragma unroll 1
+				for (int j = 0; j < 8; ++j) {
+					const uint32_t Eq = *(const uint32_t *)(eq + (((w >> (4 * j)) & 15u) << 2));
+					const uint32_t xv = Eq | mv;
+					const uint32_t xh = (((Eq & pv) + pv) ^ pv) | Eq;
+					uint32_t ph = mv | ~(xh | pv), mh = pv & xh;
+					score += (int)(ph >> 31) - (int)(mh >> 31);
+					ph <<= 1; mh <<= 1;
+					pv = mh | ~(xv | ph); mv = ph & xv;
 					const int x = (int)((wi0 + wi) * 8 + j) + 1;
-					if (x <= (int)L) {
+					if (score <= k && x <= (int)L) {                 // seed: D[P][x] <= k
 						const int d = x - P;
 						lo = min(lo, d - k); hi = max(hi, d + k);
 					}
@@ -603,10 +676,17 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	F.db = c->d_db.p; F.clump_off = c->d_clump_off.p; F.clump_len = c->d_clump_len.p; F.qi = c->d_qi.p;
 	F.peq = c->d_peq.p; F.tasks = c->have_tasks ? c->d_tasks.p : nullptr; F.ntasks = c->ntasks; F.nq = c->nq;
 	F.first_clump = c->first_clump; F.num_clumps = c->num_clumps; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap;
-	F.counters = c->d_counters.p;
+	F.counters = c->d_counters.p; F.two = 2; F.c16 = 16;
 	uint64_t blocks = (c->ntasks + 7) / 8;
 	if (blocks > 0x7FFFFFFFull) return fail(BG_EINVAL, "too many tasks for one launch");
-	if (blocks) k_filter<<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+	if (blocks) {
+		static int variant = getenv("BURST_FILTER_VARIANT") ? atoi(getenv("BURST_FILTER_VARIANT")) : 4;
+		if (variant == 1) k_filter<1><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+		else if (variant == 4) k_filter<4><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+		else if (variant == 5) k_filter<5><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+		else if (variant == 3) k_filter<3><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+		else k_filter<2><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+	}
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[1], c->stream));
 	ExtendArgs E;

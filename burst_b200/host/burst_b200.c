@@ -1,0 +1,796 @@
+/* burst_b200.c -- host driver of the B200 BURST alignment path: BURST's command line, FASTA /
+ * .edx / .acx / taxonomy inputs and .b6 output around the CUDA engine of include/burst_b200.h.
+ *
+ * Written from scratch against the behaviour of knights-lab/BURST burst.c (cited as file:line
+ * below); nothing here computes a DP cell -- every (query, clump) pair goes to the GPU through
+ * bg_align_batch(), and there is no CPU fallback for it.
+ *
+ *   CLI + flags            burst.c:4902-5103          -> main()
+ *   query preprocessing    burst.c:2980-3223          -> load_queries()
+ *   FASTA references       burst.c:1837-1851, 2146-2190, 2687-2741 -> load_fasta_refs()
+ *   .edx reader            burst.c:2842-2975          -> load_edx()
+ *   .acx reader + lookup   burst.c:3535-3594, 3238-3282, 4085-4133 -> load_acx(), accel_search()
+ *   task walk / pods       burst.c:4136-4312, 4343-4519 -> search_all_vs_all(), accel_search()
+ *   reporters              burst.c:4553-4891          -> report_*()
+ *   taxonomy               burst.c:407-479            -> load_taxonomy(), taxa_lookup_*()
+ */
+#define _GNU_SOURCE
+#define _FILE_OFFSET_BITS 64
+#include <stdio.h>
+#include <stdlib.h>
+#include <stdint.h>
+#include <string.h>
+#include <inttypes.h>
+#include <time.h>
+#include "burst_b200.h"
+
+#define VER "v1.0-b200"
+#define VECSZ 16
+#define MIN(a, b) ((a) < (b) ? (a) : (b))
+
+typedef enum { FORAGE, BEST, ALLPATHS, CAPITALIST, ANY } Mode;
+
+/* ---- options (defaults of burst.c:81-94, 164) ---- */
+static Mode RUNMODE = CAPITALIST;
+static float THRES = 0.97f;
+static int Z = 1, DO_ACCEL = 0, DO_HEUR = 0, TAXA_NCBI = 0, SCOUR_N = 0;
+static uint32_t TAXACUT = 10, LATENCY = 16;
+static long REBASE_AMT = 500; static int REBASE = 0;
+static float TAXLEVELS_STRICT[] = {.65f, .75f, .78f, .82f, .86f, .94f, .98f, .995f},
+             TAXLEVELS_LENIENT[] = {.55f, .70f, .75f, .80f, .84f, .93f, .97f, .985f},   /* burst.c:264-266 */
+             *TAXLEVELS = TAXLEVELS_LENIENT;
+static int QUIET = 0, GPU_DEVICE = 0;
+
+static uint8_t CHAR2NUM[256];
+static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};   /* burst.c:168 */
+
+static double now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+static void *xmalloc(size_t n) { void *p = malloc(n ? n : 1); if (!p) { fputs("OOM\n", stderr); exit(3); } return p; }
+static void *xcalloc(size_t n, size_t s) { void *p = calloc(n ? n : 1, s); if (!p) { fputs("OOM\n", stderr); exit(3); } return p; }
+static void *xrealloc(void *o, size_t n) { void *p = realloc(o, n ? n : 1); if (!p) { fputs("OOM\n", stderr); exit(3); } return p; }
+
+/* burst.c:1288-1307: letters -> 5 (N) unless named; 'z' and all non-letters -> 0 */
+static void init_char2num(void) {
+	memset(CHAR2NUM, 0, sizeof(CHAR2NUM));
+	for (int c = 'A'; c <= 'Z'; ++c) CHAR2NUM[c] = 5;
+	for (int c = 'a'; c < 'z'; ++c) CHAR2NUM[c] = 5;
+	const char *L = "ACGTNKMRYSWBVHD";
+	for (int i = 0; L[i]; ++i) if (L[i] != 'N') CHAR2NUM[(int)L[i]] = CHAR2NUM[(int)L[i] + 32] = (uint8_t)(i + 1);
+	CHAR2NUM['U'] = CHAR2NUM['u'] = 4;
+}
+static void translate(char *s, size_t n) { for (size_t i = 0; i < n; ++i) s[i] = (char)CHAR2NUM[(uint8_t)s[i]]; }
+
+/* =============================================================================================
+ * Queries (burst.c:2980-3223)
+ * ============================================================================================= */
+typedef struct { char *seq; uint64_t six; uint8_t rc; } UniBin;      /* burst.c:269-274 */
+typedef struct { uint32_t len; uint16_t ed; } ShrBin;                /* burst.c:277-280 */
+typedef struct {
+	char **QHead; uint64_t totQ, numUniqQ, newUniqQ, *Offset, QBins[5];
+	uint32_t maxLenQ, minLenQ;
+	UniBin *UniBins; ShrBin *ShrBins;
+	int rc, incl_whitespace, skipAmbig;
+} Queries;
+
+static char **g_sortseq;
+static int cmp_query_ix(const void *a, const void *b) {
+	uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
+	int c = strcmp(g_sortseq[x], g_sortseq[y]);
+	return c ? c : (x < y ? -1 : x > y);      /* input order among duplicates = the reference at -t 1 */
+}
+static int cmp_unibin(const void *a, const void *b) {
+	const UniBin *A = a, *B = b;
+	int c = strcmp(A->seq, B->seq);
+	if (c) return c;
+	if (A->rc != B->rc) return A->rc - B->rc;
+	return A->six < B->six ? -1 : A->six > B->six;
+}
+
+/* strict two-line FASTA, as parse_tl_faster (burst.c:636-690) */
+static void load_queries(const char *fn, Queries *Q) {
+	FILE *f = fopen(fn, "rb");
+	if (!f) { fprintf(stderr, "Cannot open FASTA file: %s.\n", fn); exit(2); }
+	fseeko(f, 0, SEEK_END); uint64_t sz = ftello(f); rewind(f);
+	char *dump = xmalloc(sz + 16);
+	if (fread(dump, 1, sz, f) != sz) { fputs("ERROR: short read on queries\n", stderr); exit(2); }
+	fclose(f);
+	memset(dump + sz, 0, 16);
+	if (!sz || *dump != '>') { fputs("ERROR: Malformatted FASTA file.\n", stderr); exit(1); }
+	uint64_t numNL = 0, numLT = 0;
+	for (uint64_t i = 0; i < sz; ++i) numNL += dump[i] == '\n', numLT += dump[i] == '>';
+	numNL += numNL & 1;
+	if (numLT != numNL / 2) { fputs("ERROR: line count != '>' * 2\n", stderr); exit(1); }
+	uint64_t totQ = numLT;
+	char **Head = xmalloc(totQ * sizeof(*Head)), **Seq = xmalloc(totQ * sizeof(*Seq));
+	uint32_t *Len = xmalloc(totQ * sizeof(*Len));
+	uint64_t n = 0; char *p = dump;
+	while (p < dump + sz && *p == '>') {
+		char *h = p + 1, *nl = memchr(h, '\n', dump + sz - h);
+		if (!nl) break;
+		*nl = 0; if (nl > h && nl[-1] == '\r') nl[-1] = 0;
+		char *s = nl + 1, *e = memchr(s, '\n', dump + sz - s);
+		if (!e) e = dump + sz;
+		*e = 0; if (e > s && e[-1] == '\r') *--e = 0;
+		Head[n] = h; Seq[n] = s; Len[n] = (uint32_t)(e - s); ++n;
+		p = (e < dump + sz) ? e + 1 : e;
+		while (p < dump + sz && *p != '>') ++p;       /* tolerate the \r\n tail */
+	}
+	totQ = n;
+	if (!totQ) { fputs("ERROR: No queries found.", stderr); exit(1); }
+	if (!Q->incl_whitespace) for (uint64_t i = 0; i < totQ; ++i) {    /* burst.c:2987-2993 */
+		char *q = Head[i]; while (*q && *q != ' ' && *q != '\t') ++q; *q = 0;
+	}
+	uint32_t maxLenQ = 0, minLenQ = UINT32_MAX;
+	for (uint64_t i = 0; i < totQ; ++i) { if (Len[i] > maxLenQ) maxLenQ = Len[i]; if (Len[i] < minLenQ) minLenQ = Len[i]; }
+	if (maxLenQ > (1 << 16)) fputs("WARNING: Max query length is very long\n", stderr);
+	if (minLenQ < 5) fputs("WARNING: Min query length is less than 5 bases\n", stderr);
+	printf("Parsed %" PRIu64 " queries. Found min %u, max %u.\n", totQ, minLenQ, maxLenQ);
+	for (uint64_t i = 0; i < totQ; ++i) translate(Seq[i], Len[i]);
+	/* sort (burst.c:3014-3031): strcmp on the code strings */
+	uint64_t *ix = xmalloc(totQ * sizeof(*ix));
+	for (uint64_t i = 0; i < totQ; ++i) ix[i] = i;
+	g_sortseq = Seq;
+	qsort(ix, totQ, sizeof(*ix), cmp_query_ix);
+	/* uniqueness (burst.c:3036-3053) */
+	uint64_t numUniq = 1;
+	for (uint64_t i = 1; i < totQ; ++i) if (strcmp(Seq[ix[i - 1]], Seq[ix[i]])) ++numUniq;
+	uint64_t *Offset = xmalloc((numUniq + 1) * sizeof(*Offset)), u = 0;
+	for (uint64_t i = 0; i < totQ; ++i) if (!i || strcmp(Seq[ix[i - 1]], Seq[ix[i]])) Offset[u++] = i;
+	Offset[numUniq] = totQ;
+	char **SrtHead = xmalloc(totQ * sizeof(*SrtHead));
+	for (uint64_t i = 0; i < totQ; ++i) SrtHead[i] = Head[ix[i]];
+	uint64_t newUniq = numUniq * (Q->rc ? 2 : 1);
+	UniBin *UB = xcalloc(newUniq, sizeof(*UB)); ShrBin *SB = xcalloc(numUniq, sizeof(*SB));
+	float reqID = 1 / THRES - 1;                                      /* burst.c:3069-3076, float32 */
+	uint64_t uniqTotLen = 0;
+	for (uint64_t i = 0; i < numUniq; ++i) {
+		uint64_t r = ix[Offset[i]];
+		uint32_t len = Len[r], ed = reqID * len;
+		SB[i].len = len; SB[i].ed = (uint16_t)MIN(254, ed);
+		UB[i].seq = Seq[r]; UB[i].six = i; UB[i].rc = 0;
+		uniqTotLen += len;
+	}
+	if (Q->rc) {                                                      /* burst.c:3087-3109 */
+		char *rcd = xmalloc(uniqTotLen + numUniq + 1), *w = rcd;
+		for (uint64_t i = 0; i < numUniq; ++i) {
+			uint32_t len = SB[i].len; char *org = UB[i].seq;
+			for (uint32_t j = 0; j < len; ++j) w[j] = (char)RVT[(uint8_t)org[len - j - 1] & 15];
+			w[len] = 0;
+			UB[numUniq + i].seq = w; UB[numUniq + i].rc = 1; UB[numUniq + i].six = i;
+			w += len + 1;
+		}
+	}
+	memset(Q->QBins, 0, sizeof(Q->QBins));
+	if (DO_ACCEL) {                                                   /* burst.c:3113-3177 */
+		uint8_t *stat = xmalloc(newUniq + 1);
+		for (uint64_t i = 0; i < newUniq; ++i) {
+			uint32_t len = SB[UB[i].six].len, ed = SB[UB[i].six].ed, totN = 0;
+			const char *s = UB[i].seq; stat[i] = 1;
+			if (len < (uint32_t)SCOUR_N || (!DO_HEUR && ed >= len / (uint32_t)SCOUR_N)) stat[i] = 2;
+			else for (uint32_t j = 0; j < len; ++j) {
+				if ((totN += s[j] > 4 + Z) > 5) { stat[i] = 2; break; }
+				else if (s[j] > 4) stat[i] = 0;
+			}
+		}
+		/* stable partition into ambiguous (0), clear (1), bad (2); each bin is re-sorted below */
+		UniBin *T = xmalloc(newUniq * sizeof(*T)); uint64_t c[3] = {0, 0, 0}, o[3];
+		for (uint64_t i = 0; i < newUniq; ++i) ++c[stat[i]];
+		o[0] = 0; o[1] = c[0]; o[2] = c[0] + c[1];
+		Q->QBins[0] = c[0]; Q->QBins[1] = c[0] + c[1]; Q->QBins[2] = newUniq;
+		for (uint64_t i = 0; i < newUniq; ++i) T[o[stat[i]]++] = UB[i];
+		memcpy(UB, T, newUniq * sizeof(*T)); free(T); free(stat);
+		printf("Unambig: %" PRIu64 ", ambig: %" PRIu64 ", super-ambig: %" PRIu64 "\n", c[1], c[0], c[2]);
+		qsort(UB, Q->QBins[0], sizeof(*UB), cmp_unibin);
+		qsort(UB + Q->QBins[0], Q->QBins[1] - Q->QBins[0], sizeof(*UB), cmp_unibin);
+		qsort(UB + Q->QBins[1], Q->QBins[2] - Q->QBins[1], sizeof(*UB), cmp_unibin);
+	} else if (Q->rc) qsort(UB, newUniq, sizeof(*UB), cmp_unibin);   /* burst.c:3178-3186 */
+	free(ix); free(Head); free(Seq); free(Len);
+	Q->QHead = SrtHead; Q->totQ = totQ; Q->numUniqQ = numUniq; Q->newUniqQ = newUniq; Q->Offset = Offset;
+	Q->UniBins = UB; Q->ShrBins = SB; Q->maxLenQ = maxLenQ; Q->minLenQ = minLenQ;
+	printf("Number unique: %" PRIu64 "\n", numUniq);
+}
+
+/* =============================================================================================
+ * References
+ * ============================================================================================= */
+typedef struct {
+	char **RefHead; uint32_t *ClumpLen, *RefStart, *RefIxSrt, *TmpRIX, *RefDedupIx, *RefMap;
+	uint32_t totR, origTotR, numRclumps, maxLenR, numRefHeads, shear;
+	uint8_t *packed;                 /* clumps in .edx layout (burst.c:2810-2824) */
+	uint64_t packedBytes;
+} Refs;
+
+/* multi-line FASTA reader in the manner of parse_tl_fasta (burst.c:484-535) */
+static uint32_t read_fasta_refs(const char *fn, char ***HeadP, char ***SeqP, uint32_t **LenP) {
+	FILE *f = fopen(fn, "rb");
+	if (!f) { fprintf(stderr, "Cannot open FASTA file: %s.\n", fn); exit(2); }
+	size_t cap = 1024, ns = 0; int lastHd = 0, have = 0;
+	char **Head = xmalloc(cap * sizeof(*Head)), **Seq = xmalloc(cap * sizeof(*Seq));
+	uint32_t *Len = xmalloc(cap * sizeof(*Len));
+	char *line = NULL; size_t lcap = 0; ssize_t got;
+	while ((got = getline(&line, &lcap, f)) >= 0) {
+		size_t len = (size_t)got;
+		if (len && line[len - 1] == '\n') --len;
+		if (len && line[len - 1] == '\r') --len;
+		line[len] = 0;
+		if (*line == '>') {
+			if (lastHd) continue;                      /* a header right after a header is ignored */
+			if (have) ++ns;
+			if (ns == cap) { cap *= 2; Head = xrealloc(Head, cap * sizeof(*Head)); Seq = xrealloc(Seq, cap * sizeof(*Seq)); Len = xrealloc(Len, cap * sizeof(*Len)); }
+			have = 1; lastHd = 1;
+			Head[ns] = strdup(line + 1); Len[ns] = 0; Seq[ns] = NULL;
+		} else if (*line == 0 || *line == ' ') continue;
+		else {
+			if (!have) continue;
+			lastHd = 0;
+			Seq[ns] = xrealloc(Seq[ns], (size_t)Len[ns] + len + 17);
+			memcpy(Seq[ns] + Len[ns], line, len);
+			Len[ns] += (uint32_t)len;
+			memset(Seq[ns] + Len[ns], 0, 17);
+		}
+	}
+	free(line); fclose(f);
+	if (have) { if (lastHd) puts("WARNING: file ends on header. Skipping last sequence."); else ++ns; }
+	*HeadP = Head; *SeqP = Seq; *LenP = Len;
+	return (uint32_t)ns;
+}
+
+typedef struct { const char *seq; uint32_t len, ix; } Tux;
+static int cmp_tux_len(const void *a, const void *b) {
+	const Tux *A = a, *B = b;
+	if (A->len != B->len) return A->len < B->len ? -1 : 1;
+	return A->ix < B->ix ? -1 : A->ix > B->ix;
+}
+static int cmp_tux_seq(const void *a, const void *b) {
+	const Tux *A = a, *B = b;
+	uint32_t ml = MIN(A->len, B->len);
+	int c = memcmp(A->seq, B->seq, ml);
+	if (c) return c;
+	if (A->len != B->len) return A->len < B->len ? -1 : 1;
+	return A->ix < B->ix ? -1 : A->ix > B->ix;
+}
+
+/* Pack code strings 16 per clump in .edx clump layout; lanes beyond a reference's end hold 0. */
+static void pack_clumps(Refs *R, char **Seq, const uint32_t *Len) {
+	uint32_t totR = R->totR, nfull = totR / VECSZ, totRC = nfull + (nfull * VECSZ < totR);
+	R->numRclumps = totRC;
+	R->ClumpLen = xcalloc(totRC + 1, sizeof(*R->ClumpLen));
+	uint64_t bytes = 0;
+	for (uint32_t c = 0; c < totRC; ++c) {
+		uint32_t cl = 0;
+		for (uint32_t k = 0; k < VECSZ && c * VECSZ + k < totR; ++k) { uint32_t l = Len[R->RefIxSrt[c * VECSZ + k]]; if (l > cl) cl = l; }
+		if (!cl) cl = 1;
+		R->ClumpLen[c] = cl; bytes += (uint64_t)((cl + 1) / 2) * 16;
+	}
+	R->packed = xcalloc(bytes + 16, 1); R->packedBytes = bytes;
+	uint8_t *w = R->packed;
+	for (uint32_t c = 0; c < totRC; ++c) {
+		uint32_t cl = R->ClumpLen[c];
+		for (uint32_t k = 0; k < VECSZ && c * VECSZ + k < totR; ++k) {
+			uint32_t r = R->RefIxSrt[c * VECSZ + k], l = Len[r]; const char *s = Seq[r];
+			for (uint32_t j = 0; j < l; ++j) w[(size_t)(j >> 1) * 16 + k] |= (uint8_t)((s[j] & 15) << ((j & 1) * 4));
+		}
+		w += (size_t)((cl + 1) / 2) * 16;
+	}
+}
+
+/* plain -r FASTA (burst.c:1837-1851 parse/translate, 2146-2190 ordering, 2687-2741 packing) */
+static void load_fasta_refs(const char *fn, Refs *R) {
+	char **Head, **Seq; uint32_t *Len;
+	uint32_t totR = read_fasta_refs(fn, &Head, &Seq, &Len);
+	printf("Parsed %u references.\n", totR);
+	if (!totR) { fputs("ERROR: no references found.\n", stderr); exit(1); }
+	for (uint32_t i = 0; i < totR; ++i) { if (!Seq[i]) Seq[i] = xcalloc(17, 1); translate(Seq[i], Len[i]); }
+	if (REBASE) fputs("WARNING: -s on a FASTA reference is not supported by this build; references are used whole.\n", stderr);
+	memset(R, 0, sizeof(*R));
+	R->totR = R->origTotR = totR; R->RefHead = Head;
+	/* references of similar length (within LATENCY bases) share clumps, lexicographic inside a pod */
+	Tux *T = xmalloc(totR * sizeof(*T));
+	for (uint32_t i = 0; i < totR; ++i) T[i] = (Tux){Seq[i], Len[i], i};
+	qsort(T, totR, sizeof(*T), cmp_tux_len);
+	R->maxLenR = T[totR - 1].len;
+	uint32_t prev = 0, curTol = T[0].len;
+	for (uint32_t i = 1; i <= totR; ++i) if (i == totR || T[i].len > curTol + LATENCY) {
+		if (i - prev > 1) qsort(T + prev, i - prev, sizeof(*T), cmp_tux_seq);
+		if (i < totR) curTol = T[i].len;
+		prev = i;
+	}
+	R->RefIxSrt = xmalloc((totR + 1) * sizeof(*R->RefIxSrt));
+	for (uint32_t i = 0; i < totR; ++i) R->RefIxSrt[i] = T[i].ix;
+	free(T);
+	R->TmpRIX = R->RefIxSrt;
+	pack_clumps(R, Seq, Len);
+	printf("There are %u references and hence %u clumps\n", totR, R->numRclumps);
+	for (uint32_t i = 0; i < totR; ++i) free(Seq[i]);
+	free(Seq); free(Len);
+}
+
+static void rd(void *dst, size_t sz, size_t n, FILE *f) {
+	if (fread(dst, sz, n, f) != n) { fputs("ERROR: truncated database file\n", stderr); exit(1); }
+}
+/* .edx reader (burst.c:2842-2975; layout written at 2758-2839) */
+static void load_edx(const char *fn, Refs *R) {
+	FILE *in = fopen(fn, "rb");
+	if (!in) { fputs("ERROR: cannot parse EDB", stderr); exit(1); }
+	memset(R, 0, sizeof(*R));
+	uint8_t cb = (uint8_t)fgetc(in), ver = cb & 0xF;
+	if (ver != 3 && ver != 2) { fprintf(stderr, "ERROR: invalid database version %u\n", ver); exit(1); }
+	if (ver == 2) { fprintf(stderr, "ERROR: Old DB version. Re-make with new version.\n"); exit(2); }
+	REBASE = (cb >> 6) & 1;
+	if ((cb >> 5) & 1) printf(" --> EDB: Fingerprints are DISABLED\n");
+	if ((cb >> 4) & 1) { fprintf(stderr, "ERROR: DB made with Xalpha; queries must use Xalpha.\n"); exit(1); }
+	uint64_t totRefHeadLen; uint32_t shear, totR, origTotR, numRclumps, maxLenR, numRefHeads;
+	rd(&totRefHeadLen, 8, 1, in); rd(&shear, 4, 1, in); rd(&totR, 4, 1, in); rd(&origTotR, 4, 1, in);
+	rd(&numRclumps, 4, 1, in); rd(&maxLenR, 4, 1, in);
+	char *hd = xmalloc(totRefHeadLen + 1);
+	rd(hd, 1, totRefHeadLen, in);
+	rd(&numRefHeads, 4, 1, in);
+	char **uniq = xmalloc((size_t)numRefHeads * sizeof(*uniq));
+	uniq[0] = hd;
+	for (uint32_t i = 1; i < numRefHeads; ++i) { while (*hd++); uniq[i] = hd; }
+	R->RefMap = xmalloc((size_t)origTotR * 4);
+	rd(R->RefMap, 4, origTotR, in);
+	R->RefHead = xmalloc((size_t)origTotR * sizeof(*R->RefHead));
+	for (uint32_t i = 0; i < origTotR; ++i) R->RefHead[i] = uniq[R->RefMap[i]];
+	free(uniq);
+	if (REBASE) { printf(" --> EDB: Sheared database (shear size = %u)\n", shear); R->RefStart = xmalloc((size_t)origTotR * 4); rd(R->RefStart, 4, origTotR, in); }
+	if (totR != origTotR) { puts(" --> EDB: Unique-reference database"); R->RefDedupIx = xmalloc(((size_t)totR + 1) * 4); rd(R->RefDedupIx, 4, (size_t)totR + 1, in); }
+	R->TmpRIX = xmalloc((size_t)origTotR * 4); rd(R->TmpRIX, 4, origTotR, in);
+	R->ClumpLen = xmalloc((size_t)numRclumps * 4); rd(R->ClumpLen, 4, numRclumps, in);
+	uint64_t vecs = 0;
+	for (uint32_t i = 0; i < numRclumps; ++i) { if (R->ClumpLen[i] > maxLenR) maxLenR = R->ClumpLen[i]; vecs += R->ClumpLen[i] / 2u + (R->ClumpLen[i] & 1); }
+	R->packed = xmalloc(vecs * 16 + 16); R->packedBytes = vecs * 16;
+	rd(R->packed, 16, vecs, in);
+	fclose(in);
+	R->totR = totR; R->origTotR = origTotR; R->numRclumps = numRclumps; R->maxLenR = maxLenR;
+	R->numRefHeads = numRefHeads; R->shear = shear;
+	if (R->RefDedupIx) {                                         /* burst.c:3688-3693 */
+		R->RefIxSrt = xmalloc((size_t)totR * 4);
+		for (uint32_t i = 0; i < totR; ++i) R->RefIxSrt[i] = R->TmpRIX[R->RefDedupIx[i]];
+	} else R->RefIxSrt = R->TmpRIX;
+	printf(" --> EDB: %u refs [%u orig], %u clumps, %u maxR\n", totR, origTotR, numRclumps, maxLenR);
+}
+
+/* =============================================================================================
+ * Taxonomy (burst.c:407-479)
+ * ============================================================================================= */
+typedef struct { char *Head, *Tax; } TaxPair;
+static TaxPair *Taxonomy; static size_t taxa_parsed;
+static char NULLTAX[1] = {0};
+static int cmp_tax(const void *a, const void *b) { return strcmp(((const TaxPair *)a)->Head, ((const TaxPair *)b)->Head); }
+static void load_taxonomy(const char *fn) {
+	FILE *f = fopen(fn, "rb");
+	if (!f) { fprintf(stderr, "Cannot open TAXONOMY file: %s.\n", fn); exit(2); }
+	size_t cap = 1024, ns = 0; TaxPair *T = xmalloc(cap * sizeof(*T));
+	char *line = NULL; size_t lcap = 0; ssize_t got;
+	while ((got = getline(&line, &lcap, f)) >= 0) {
+		if (ns == cap) T = xrealloc(T, (cap *= 2) * sizeof(*T));
+		size_t i = 0, j;
+		for (; line[i] != '\t'; ++i) if (!line[i]) { fprintf(stderr, "ERROR: invalid taxonomy [%zu]\n", ns); exit(2); }
+		T[ns].Head = strndup(line, i);
+		for (j = ++i; line[j] && line[j] != '\n' && line[j] != '\r' && line[j] != '\t'; ++j);
+		T[ns].Tax = strndup(line + i, j - i);
+		++ns;
+	}
+	free(line); fclose(f);
+	if (!ns) { fputs("ERROR: invalid taxonomy\n", stderr); exit(1); }
+	qsort(T, ns, sizeof(*T), cmp_tax);
+	Taxonomy = T; taxa_parsed = ns;
+}
+/* exact header match; with -bn the key skips its first 4 characters and may end at a '.' (burst.c:424-440) */
+static char *taxa_lookup(const char *key) {
+	if (TAXA_NCBI) key += strlen(key) >= 4 ? 4 : strlen(key);
+	size_t lo = 0, hi = taxa_parsed;
+	while (lo < hi) {
+		size_t mid = (lo + hi) / 2;
+		const char *r = Taxonomy[mid].Head, *k = key;
+		while (*r && *r == *k) ++r, ++k;
+		if (!*r && (!*k || (TAXA_NCBI && *k == '.'))) return Taxonomy[mid].Tax;
+		unsigned char kc = (unsigned char)((TAXA_NCBI && *k == '.') ? 0 : *k);
+		if ((unsigned char)*r < kc) lo = mid + 1; else hi = mid;
+	}
+	return NULLTAX;
+}
+
+/* =============================================================================================
+ * Pods: what the reference keeps per unique query (ResultPod, burst.c:3998-4004)
+ * ============================================================================================= */
+typedef struct { float score; uint32_t refIx, finalPos; uint8_t numGapR, numGapQ, mismatches, rc; } Pod;
+typedef struct { Pod *p; uint32_t n, cap; } PodList;
+
+static void pod_push(PodList *L, Pod x) {
+	if (L->n == L->cap) { L->cap = L->cap ? L->cap * 2 : 4; L->p = xrealloc(L->p, L->cap * sizeof(Pod)); }
+	L->p[L->n++] = x;
+}
+/* identity exactly as burst.c:844-860: IEEE single divide then subtract */
+static float identity(uint32_t ed, uint32_t qlen, uint32_t gapq) {
+	volatile float den = (float)qlen + (float)gapq, q = (float)ed / den;
+	return 1.0f - q;
+}
+static void die_gpu(const char *what, int rc) {
+	fprintf(stderr, "ERROR: GPU engine failed in %s: %s\n", what, bg_last_error());
+	exit(rc == BG_ENOMEM ? 3 : 4);
+}
+
+/* =============================================================================================
+ * Search: all-vs-all (no accelerator, and the accelerator's left-over bin), burst.c:4318-4520.
+ * Discovery order per query slot there is (clump, query, lane) ascending; the engine returns
+ * hits sorted by (task, lane) with task = clump * nq + query, which is the same order.
+ * ============================================================================================= */
+static void search_all_vs_all(bg_ctx *ctx, Queries *Q, Refs *R, uint64_t firstQ, PodList *Pods, int mode) {
+	uint64_t nqAll = Q->newUniqQ - firstQ;
+	if (!nqAll) return;
+	printf("Searching best paths through %" PRIu64 " unique queries...\n", nqAll);
+	uint16_t *best = xmalloc(Q->numUniqQ * sizeof(*best));
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[i] = 0xFFFF;
+	/* batch over queries so that one batch stays below 2^32 tasks and a few hundred MB of codes */
+	uint64_t maxq = ((1ull << 32) - 2) / (R->numRclumps ? R->numRclumps : 1);
+	if (maxq > (1u << 22)) maxq = 1u << 22;
+	if (!maxq) { fputs("ERROR: database has too many clumps for all-vs-all search\n", stderr); exit(4); }
+	for (uint64_t z = firstQ; z < Q->newUniqQ; z += maxq) {
+		uint64_t bound = MIN(z + maxq, Q->newUniqQ), nq = bound - z, tot = 0;
+		uint64_t *off = xmalloc((nq + 1) * sizeof(*off));
+		uint16_t *bud = xmalloc(nq * sizeof(*bud)); uint32_t *slot = xmalloc(nq * sizeof(*slot));
+		for (uint64_t j = 0; j < nq; ++j) { off[j] = tot; tot += Q->ShrBins[Q->UniBins[z + j].six].len; }
+		off[nq] = tot;
+		uint8_t *codes = xmalloc(tot + 16);
+		for (uint64_t j = 0; j < nq; ++j) {
+			UniBin *u = Q->UniBins + z + j; ShrBin *s = Q->ShrBins + u->six;
+			memcpy(codes + off[j], u->seq, s->len);
+			bud[j] = s->ed; slot[j] = (uint32_t)u->six;
+		}
+		bg_queries bq = {codes, off, bud, slot, (uint32_t)nq, (uint32_t)Q->numUniqQ};
+		bg_hit *hits = NULL; uint64_t nh = 0;
+		int rc = bg_align_batch(ctx, &bq, NULL, 0, mode, best, &hits, &nh);
+		if (rc) die_gpu("bg_align_batch", rc);
+		for (uint64_t h = 0; h < nh; ++h) {
+			uint64_t t = hits[h].task; uint32_t clump = (uint32_t)(t / nq), j = (uint32_t)(t % nq);
+			UniBin *u = Q->UniBins + z + j; ShrBin *s = Q->ShrBins + u->six;
+			uint32_t refIx = clump * VECSZ + hits[h].lane;
+			if (refIx >= R->totR) continue;                               /* burst.c:4444 */
+			Pod p = {identity(hits[h].ed, s->len, hits[h].gap_q), refIx, hits[h].final_pos, hits[h].gap_r, hits[h].gap_q, hits[h].ed, u->rc};
+			pod_push(Pods + u->six, p);
+		}
+		bg_free_hits(hits);
+		free(off); free(bud); free(slot); free(codes);
+		if (!QUIET) printf("\rSearch Progress: [%3.2f%%]", 100.0 * (double)(bound - firstQ) / (double)nqAll);
+	}
+	if (!QUIET) printf("\rSearch Progress: [100.00%%]\n");
+	if (mode == BG_MODE_MIN) for (uint64_t i = 0; i < Q->numUniqQ; ++i) {    /* burst.c:4497-4517: drop pods above the final minimum */
+		PodList *L = Pods + i; uint32_t w = 0;
+		for (uint32_t k = 0; k < L->n; ++k) if (L->p[k].mismatches <= best[i]) L->p[w++] = L->p[k];
+		L->n = w;
+	}
+	free(best);
+}
+
+/* =============================================================================================
+ * Reporting (burst.c:4553-4891).  The reference's lists are push-front: iterate pods in reverse
+ * discovery order.
+ * ============================================================================================= */
+typedef struct {
+	FILE *out; Queries *Q; Refs *R; int taxasuppress;
+} Rep;
+
+static void print_row(Rep *P, uint64_t i, const Pod *rp, uint32_t rix, const char *tax) {
+	Queries *Q = P->Q; Refs *R = P->R;
+	uint32_t qlen = Q->ShrBins[i].len, numGap = (uint32_t)rp->numGapR + rp->numGapQ, numMis = rp->mismatches - numGap,
+		alLen = qlen + numGap, mOff = R->RefStart ? R->RefStart[rix] : 0,
+		stIxR = rp->finalPos - qlen + rp->numGapR + mOff, edIxR = rp->finalPos + mOff;
+	if (rp->rc) { uint32_t t = stIxR; stIxR = edIxR; edIxR = t; }
+	float pct = rp->score * 100;
+	for (uint64_t j = Q->Offset[i]; j < Q->Offset[i + 1]; ++j) {
+		if (tax) fprintf(P->out, "%s\t%s\t%f\t%u\t%u\t%u\t%u\t%u\t%d\t%u\t%u\t%" PRIu64 "\t%s\n", Q->QHead[j], R->RefHead[rix], pct,
+			alLen, numMis, numGap, 1, qlen, (int)stIxR, edIxR, rp->mismatches, i, tax);
+		else fprintf(P->out, "%s\t%s\t%f\t%u\t%u\t%u\t%u\t%u\t%d\t%u\t%u\t%" PRIu64 "\n", Q->QHead[j], R->RefHead[rix], pct,
+			alLen, numMis, numGap, 1, qlen, (int)stIxR, edIxR, rp->mismatches, i);
+	}
+}
+
+/* "first seen wins" suppression of hits on the same header whose starts are within qlen/2 (burst.c:4563-4570) */
+typedef struct { uint32_t *ref, *st; uint64_t n, cap; } DupeSet;
+static int dupe_hunt(DupeSet *D, Refs *R, const Pod *rp, uint32_t qlen, uint32_t rix) {
+	uint32_t mOff = R->RefStart ? R->RefStart[rix] : 0, ql2 = qlen >> 1;
+	uint32_t stIxR = rp->rc ? rp->finalPos + mOff : rp->finalPos - qlen + rp->numGapR + mOff;
+	uint32_t mapped = R->RefMap ? R->RefMap[rix] : rix;
+	for (uint64_t d = 0; d < D->n; ++d)
+		if (D->ref[d] == mapped && D->st[d] + ql2 > stIxR && D->st[d] < stIxR + ql2) return 1;
+	if (D->n == D->cap) { D->cap = D->cap ? D->cap * 2 : 64; D->ref = xrealloc(D->ref, D->cap * 4); D->st = xrealloc(D->st, D->cap * 4); }
+	D->ref[D->n] = mapped; D->st[D->n++] = stIxR;
+	return 0;
+}
+
+static const char *suppress_tax(char *buf, const char *tt, float score, uint32_t lv_limit, int use_limit) {
+	/* burst.c:4874-4885 / 4820-4828: cut the taxonomy string at the level the identity supports */
+	uint32_t lm, s = 0;
+	if (use_limit) { for (lm = 0; lm < lv_limit && TAXLEVELS[lm] < score; ++lm); }
+	else for (lm = 0; lm < 8 && TAXLEVELS[lm] < score; ++lm);
+	if (!lm) return NULLTAX;
+	strcpy(buf, tt);
+	if (!use_limit || lm < lv_limit) for (int x = 0; buf[x]; ++x) if (buf[x] == ';' && ++s == lm) { buf[x] = 0; break; }
+	return buf;
+}
+
+static void report_best(Rep *P, PodList *Pods) {                        /* burst.c:4847-4891 */
+	Queries *Q = P->Q; Refs *R = P->R; char *buf = xmalloc(1 << 20);
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *L = Pods + i; if (!L->n) continue;
+		const Pod *best = &L->p[L->n - 1];
+		for (int64_t k = (int64_t)L->n - 2; k >= 0; --k) {
+			const Pod *rp = &L->p[k];
+			if (rp->mismatches < best->mismatches || (rp->mismatches == best->mismatches && rp->score > best->score) ||
+			    (rp->mismatches == best->mismatches && rp->score == best->score && R->RefIxSrt[rp->refIx] < R->RefIxSrt[best->refIx])) best = rp;
+		}
+		uint32_t rix = R->RefIxSrt[best->refIx];
+		const char *tax = NULL;
+		if (taxa_parsed) { tax = taxa_lookup(R->RefHead[rix]); if (P->taxasuppress) tax = suppress_tax(buf, tax, best->score, 0, 0); }
+		print_row(P, i, best, rix, tax);
+	}
+	free(buf);
+}
+
+typedef struct { const Pod *rp; uint32_t rix; } RowRef;
+/* expand a pod over the de-duplicated originals it stands for (burst.c:4601-4616) */
+#define FOR_EACH_RIX(R, rp, rixvar, ...) \
+	if ((R)->RefDedupIx) { for (uint32_t k_ = (R)->RefDedupIx[(rp)->refIx]; k_ < (R)->RefDedupIx[(rp)->refIx + 1]; ++k_) { uint32_t rixvar = (R)->TmpRIX[k_]; __VA_ARGS__ } } \
+	else { uint32_t rixvar = (R)->RefIxSrt[(rp)->refIx]; __VA_ARGS__ }
+
+static void report_allpaths_or_forage(Rep *P, PodList *Pods, int forage) {   /* burst.c:4582-4692 */
+	Queries *Q = P->Q; Refs *R = P->R;
+	DupeSet D = {0}; RowRef *rows = NULL; uint64_t rcap = 0;
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *L = Pods + i; if (!L->n) continue;
+		uint32_t qlen = Q->ShrBins[i].len, bm = 255; uint64_t nrows = 0; D.n = 0;
+		const Pod *best = &L->p[L->n - 1];
+		for (int64_t k = (int64_t)L->n - 2; k >= 0; --k) if (L->p[k].mismatches < best->mismatches) best = &L->p[k];
+		bm = best->mismatches;
+		if (!forage && !(best->score != 0)) continue;                       /* burst.c:4598 */
+		for (int64_t k = (int64_t)L->n - 1; k >= 0; --k) {
+			const Pod *rp = &L->p[k];
+			if (!forage && rp->mismatches != bm) continue;
+			FOR_EACH_RIX(R, rp, rix, {
+				if (!dupe_hunt(&D, R, rp, qlen, rix)) {
+					if (nrows == rcap) { rcap = rcap ? rcap * 2 : 64; rows = xrealloc(rows, rcap * sizeof(*rows)); }
+					rows[nrows].rp = rp; rows[nrows++].rix = rix;
+				}
+			})
+		}
+		for (uint64_t j = Q->Offset[i]; j < Q->Offset[i + 1]; ++j) for (uint64_t z = 0; z < nrows; ++z) {
+			/* one row per (duplicate, hit): print_row prints all duplicates, so emit per duplicate here */
+			const Pod *rp = rows[z].rp; uint32_t rix = rows[z].rix;
+			uint32_t numGap = (uint32_t)rp->numGapR + rp->numGapQ, numMis = rp->mismatches - numGap, alLen = qlen + numGap,
+				mOff = R->RefStart ? R->RefStart[rix] : 0, a = rp->finalPos - qlen + rp->numGapR + mOff, b = rp->finalPos + mOff,
+				stIxR = rp->rc ? b : a, edIxR = rp->rc ? a : b;
+			float pct = rp->score * 100;
+			if (taxa_parsed) fprintf(P->out, "%s\t%s\t%f\t%u\t%u\t%u\t%u\t%u\t%d\t%u\t%u\t%" PRIu64 "\t%s\n", Q->QHead[j], R->RefHead[rix], pct,
+				alLen, numMis, numGap, 1, qlen, (int)stIxR, edIxR, rp->mismatches, i, taxa_lookup(R->RefHead[rix]));
+			else fprintf(P->out, "%s\t%s\t%f\t%u\t%u\t%u\t%u\t%u\t%d\t%u\t%u\t%" PRIu64 "\n", Q->QHead[j], R->RefHead[rix], pct,
+				alLen, numMis, numGap, 1, qlen, (int)stIxR, edIxR, rp->mismatches, i);
+		}
+	}
+	free(rows); free(D.ref); free(D.st);
+}
+
+static int cmp_str(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
+
+static void report_capitalist(Rep *P, PodList *Pods) {                  /* burst.c:4694-4846 */
+	Queries *Q = P->Q; Refs *R = P->R;
+	uint32_t maxIX = 0;
+	for (uint32_t i = 0; i < R->totR; ++i) if (R->RefIxSrt[i] > maxIX) maxIX = R->RefIxSrt[i];
+	uint64_t numBins = (uint64_t)maxIX + 1;
+	if (R->RefMap) for (uint32_t i = 0; i < R->origTotR; ++i) if ((uint64_t)R->RefMap[i] + 1 > numBins) numBins = (uint64_t)R->RefMap[i] + 1;
+	size_t *RefCounts = xcalloc(numBins, sizeof(*RefCounts)), tot = 0;
+	DupeSet D = {0};
+	uint32_t *start = xcalloc(Q->numUniqQ, sizeof(*start));      /* index (in list order) of the first minimum pod */
+	/* pass 1+2 (4700-4727): find the first minimum in list order, tally references over the pods from it on */
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *L = Pods + i; if (!L->n) continue;
+		int64_t bk = (int64_t)L->n - 1;
+		for (int64_t k = (int64_t)L->n - 2; k >= 0; --k) if (L->p[k].mismatches < L->p[bk].mismatches) bk = k;
+		start[i] = (uint32_t)bk; D.n = 0;
+		uint32_t qlen = Q->ShrBins[i].len, bm = L->p[bk].mismatches;
+		for (int64_t k = bk; k >= 0; --k) {
+			const Pod *rp = &L->p[k];
+			if (rp->mismatches != bm) continue;
+			FOR_EACH_RIX(R, rp, rix, {
+				if (!dupe_hunt(&D, R, rp, qlen, rix)) { ++RefCounts[R->RefMap ? R->RefMap[rix] : rix]; ++tot; }
+			})
+		}
+	}
+	printf("CAPITALIST: Processed %zu investments\n", tot);
+	char **Taxa = NULL; uint32_t *Div = NULL; char *Taxon = NULL; uint64_t tcap = 0;
+	if (taxa_parsed) Taxon = xmalloc(1000000);
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *L = Pods + i; if (!L->n) continue;
+		const Pod *first = &L->p[start[i]], *best = first;
+		uint32_t tix = 0, bestmap = 0, bestrix = R->RefIxSrt[first->refIx], qlen = Q->ShrBins[i].len; float best_score = -1.f;
+		D.n = 0;
+		for (int64_t k = start[i]; k >= 0; --k) {
+			const Pod *rp = &L->p[k];
+			if (rp->mismatches > first->mismatches) continue;
+			FOR_EACH_RIX(R, rp, rix, {
+				if (!dupe_hunt(&D, R, rp, qlen, rix)) {
+					uint32_t mapped = R->RefMap ? R->RefMap[rix] : rix;
+					if (taxa_parsed) {
+						if (tix == tcap) { tcap = tcap ? tcap * 2 : 64; Taxa = xrealloc(Taxa, tcap * sizeof(*Taxa)); Div = xrealloc(Div, tcap * sizeof(*Div)); }
+						Taxa[tix++] = taxa_lookup(R->RefHead[rix]);
+						if (rp->score > best_score) best_score = rp->score;
+					}
+					/* burst.c:4763-4765: the pod currently held is overridden by its own later originals;
+					 * another pod takes over on a larger global count, ties to the smaller header index */
+					if (best == rp || RefCounts[mapped] > RefCounts[bestmap] || (RefCounts[mapped] == RefCounts[bestmap] && mapped < bestmap))
+						best = rp, bestmap = mapped, bestrix = rix;
+				}
+			})
+		}
+		const char *FinalTaxon = NULL;
+		if (taxa_parsed) {                                              /* LCA interpolation, burst.c:4781-4829 */
+			uint32_t lv = (uint32_t)-1;
+			if (tix == 1) { strcpy(Taxon, Taxa[0]); FinalTaxon = Taxon; }
+			else {
+				qsort(Taxa, tix, sizeof(*Taxa), cmp_str);
+				uint32_t maxDiv = 0; Div[0] = 0;
+				for (uint32_t z = 1; z < tix; ++z) {
+					uint32_t x; Div[z] = 0;
+					for (x = 0; Taxa[z - 1][x] && Taxa[z - 1][x] == Taxa[z][x]; ++x) Div[z] += Taxa[z][x] == ';';
+					Div[z] += !Taxa[z - 1][x];
+					if (Div[z] > maxDiv) maxDiv = Div[z];
+				}
+				if (!maxDiv) { Taxon[0] = 0; FinalTaxon = Taxon; }
+				else {
+					uint32_t cutoff = tix - tix / TAXACUT, st = 0, ed = tix;
+					for (lv = 1; lv <= maxDiv; ++lv) {
+						uint32_t accum = 1;
+						for (uint32_t z = st + 1; z < ed; ++z) {
+							if (Div[z] >= lv) ++accum;
+							else if (accum >= cutoff) { ed = z; break; }
+							else accum = 1, st = z;
+						}
+						if (accum < cutoff) break;
+						cutoff = accum - accum / TAXACUT;
+					}
+					uint32_t s = 0;
+					if (ed) --ed;
+					--lv;
+					for (st = 0; Taxa[ed][st] && (s += Taxa[ed][st] == ';') < lv; ++st) Taxon[st] = Taxa[ed][st];
+					Taxon[st] = 0; FinalTaxon = Taxon;
+				}
+			}
+			if (P->taxasuppress) {
+				uint32_t lm, s = 0;
+				for (lm = 0; lm < lv && lm < 8 && TAXLEVELS[lm] < best_score; ++lm);
+				if (!lm) FinalTaxon = NULLTAX;
+				else if (lm < lv) for (int x = 0; Taxon[x]; ++x) if (Taxon[x] == ';' && ++s == lm) { Taxon[x] = 0; break; }
+			}
+		}
+		print_row(P, i, best, bestrix, FinalTaxon);
+	}
+	free(RefCounts); free(start); free(D.ref); free(D.st); free(Taxa); free(Div); free(Taxon);
+}
+
+/* =============================================================================================
+ * main: the reference's command line (burst.c:4902-5103)
+ * ============================================================================================= */
+static void usage(void) {
+	printf("\nBURST aligner, B200 build (" VER ")\n");
+	puts("Same command line as BURST (burst.c:102-150) for the alignment path:");
+	puts("--references (-r) <name>: FASTA/edx DB of reference sequences [required]");
+	puts("--accelerator (-a) <name>: uses a helper DB (acx) [optional]");
+	puts("--queries (-q) <name>: FASTA file of queries to search [required]");
+	puts("--output (-o) <name>: Blast6 file for output alignments [required]");
+	puts("--forwardreverse (-fr), --whitespace (-w), --nwildcard (-y), --npenalize (-n)");
+	puts("--taxonomy (-b) <name>, --taxacut (-bc) <num>, --taxa_ncbi (-bn), --taxasuppress (-bs) [STRICT]");
+	puts("--mode (-m) BEST | ALLPATHS | CAPITALIST [default] | FORAGE");
+	puts("--id (-i) <decimal> [0.97], --threads (-t) <int> (accepted, unused), --skipambig (-sa), --heuristic (-hr)");
+	puts("--gpu <int>: CUDA device to use [0];  --noprogress");
+	puts("Database creation (-d) is not part of this build: create .edx/.acx with the reference burst binary.");
+	exit(1);
+}
+static int is_edx(const char *fn) {                                  /* burst.c:4894-4901 */
+	FILE *f = fopen(fn, "rb");
+	if (!f) { fputs("ERROR: invalid input file.\n", stderr); exit(1); }
+	int c = fgetc(f); fclose(f);
+	if (c == EOF) { fputs("ERROR: invalid input file.\n", stderr); exit(1); }
+	return (uint8_t)c >> 7;
+}
+
+int main(int argc, char *argv[]) {
+	Queries Q; memset(&Q, 0, sizeof(Q));
+	Refs R; char *ref_FN = 0, *query_FN = 0, *output_FN = 0, *xcel_FN = 0, *tax_FN = 0; int taxasuppress = 0;
+	printf("This is BURST [" VER "]\n");
+	if (argc < 2) usage();
+#define NEEDARG(msg) if (++i == argc || argv[i][0] == '-') { puts("ERROR: " msg); exit(1); }
+#define OPT(l, s) (!strcmp(argv[i], l) || !strcmp(argv[i], s))
+	for (int i = 1; i < argc; ++i) {
+		if (OPT("--references", "-r")) { NEEDARG("--references requires filename argument") ref_FN = argv[i]; }
+		else if (OPT("--queries", "-q")) { NEEDARG("--queries requires filename argument") query_FN = argv[i]; }
+		else if (OPT("--output", "-o")) { NEEDARG("--output requires filename argument") output_FN = argv[i]; }
+		else if (OPT("--forwardreverse", "-fr")) { Q.rc = 1; printf(" --> Also considering the reverse complement of reads\n"); }
+		else if (OPT("--whitespace", "-w")) { Q.incl_whitespace = 1; printf(" --> Allowing whitespace in query name output\n"); }
+		else if (OPT("--npenalize", "-n")) { Z = 1; printf(" --> Setting N penalty (ref N vs query A/C/G/T)\n"); }
+		else if (OPT("--nwildcard", "-y")) { Z = 0; printf(" --> Setting N's and X's to wildcards (match anything)\n"); }
+		else if (OPT("--xalphabet", "-x")) { fputs("ERROR: --xalphabet is not supported by this build (the reference itself aborts on it, see DESIGN.md)\n", stderr); exit(1); }
+		else if (OPT("--taxonomy", "-b")) { NEEDARG("--taxonomy requires filename argument") tax_FN = argv[i]; printf(" --> Assigning taxonomy based on mapping file: %s\n", tax_FN); }
+		else if (OPT("--mode", "-m")) {
+			NEEDARG("--mode requires an argument (see -h)")
+			if (!strcmp(argv[i], "BEST")) RUNMODE = BEST; else if (!strcmp(argv[i], "ALLPATHS")) RUNMODE = ALLPATHS;
+			else if (!strcmp(argv[i], "CAPITALIST")) RUNMODE = CAPITALIST; else if (!strcmp(argv[i], "FORAGE")) RUNMODE = FORAGE;
+			else if (!strcmp(argv[i], "ANY")) { fputs("ERROR: -m ANY (first hit in thread-arrival order) is not supported by this build\n", stderr); exit(1); }
+			else if (!strcmp(argv[i], "MATRIX")) { fputs("ERROR: Matrix mode is no longer supported\n", stderr); exit(1); }
+			else { printf("Unsupported run mode '%s'\n", argv[i]); exit(1); }
+			printf(" --> Setting run mode to %s\n", argv[i]);
+		}
+		else if (OPT("--makedb", "-d")) { fputs("ERROR: database creation (-d) is not part of this build; make the .edx/.acx with the reference burst binary.\n", stderr); exit(1); }
+		else if (OPT("--accelerator", "-a")) { NEEDARG("--accelerator requires filename argument") xcel_FN = argv[i]; DO_ACCEL = 1; printf(" --> Using accelerator file %s\n", xcel_FN); }
+		else if (OPT("--taxacut", "-bc")) {
+			NEEDARG("--taxacut requires numeric argument")
+			int t = atoi(argv[i]);
+			if (t < 2) { double fl = 1.0 / (1.0 - atof(argv[i])); t = (int)(fl + 0.5); printf(" --> Taxacut: converting %s to %d...\n", argv[i], t); }
+			if (t < 2) { fputs("ERROR: taxacut must be >= 2\n", stderr); exit(1); }
+			TAXACUT = (uint32_t)t; printf(" --> Ignoring 1/%u disagreeing taxonomy calls\n", TAXACUT);
+		}
+		else if (OPT("--taxa_ncbi", "-bn")) { TAXA_NCBI = 1; printf(" --> Using NCBI header formatting for taxonomy lookups\n"); }
+		else if (OPT("--skipambig", "-sa")) { Q.skipAmbig = 1; printf(" --> Skipping highly ambiguous sequences\n"); }
+		else if (OPT("--taxasuppress", "-bs")) {
+			taxasuppress = 1;
+			if (i + 1 != argc && argv[i + 1][0] != '-') { if (!strcmp(argv[++i], "STRICT")) TAXLEVELS = TAXLEVELS_STRICT; else { fprintf(stderr, "ERROR: Unrecognized taxasuppress '%s'\n", argv[i]); exit(1); } }
+			printf(" --> Surpressing taxonomic specificity by alignment identity%s\n", TAXLEVELS == TAXLEVELS_STRICT ? " [STRICT]" : "");
+		}
+		else if (OPT("--id", "-i")) {
+			NEEDARG("--id requires decimal argument")
+			THRES = (float)atof(argv[i]);
+			if (THRES > 1.f || THRES < 0.f) { puts("Invalid id range [0-1]"); exit(1); }
+			if (THRES < 0.01f) THRES = 0.01f;
+			printf(" --> Setting identity threshold to %f\n", THRES);
+		}
+		else if (OPT("--threads", "-t")) { NEEDARG("--threads requires integer argument") printf(" --> Host threads are not used by the GPU path (-t %s ignored)\n", argv[i]); }
+		else if (OPT("--shear", "-s")) { REBASE = 1; if (i + 1 != argc && argv[i + 1][0] != '-') REBASE_AMT = atol(argv[++i]); if (!REBASE_AMT) REBASE = 0; }
+		else if (OPT("--heuristic", "-hr")) { DO_HEUR = 1; printf(" --> WARNING: Heuristic mode set; optimality not guaranteed at low ids\n"); }
+		else if (!strcmp(argv[i], "--noprogress")) { QUIET = 1; printf(" --> Surpressing progress indicator\n"); }
+		else if (!strcmp(argv[i], "--gpu")) { NEEDARG("--gpu requires integer argument") GPU_DEVICE = atoi(argv[i]); }
+		else if (OPT("--fingerprint", "-f") || OPT("--prepass", "-p") || OPT("--unique", "-u")) { fprintf(stderr, "ERROR: %s selects a heuristic/legacy path that this build does not provide (see DESIGN.md, out of scope)\n", argv[i]); exit(1); }
+		else if (OPT("--cache", "-c") || OPT("--latency", "-l") || OPT("--clustradius", "-cr") || OPT("--dbpartition", "-dp")) { NEEDARG("option requires integer argument") }
+		else if (OPT("--help", "-h")) usage();
+		else { printf("ERROR: Unrecognized command-line option: %s\n", argv[i]); puts("See help by running with just '-h'"); exit(1); }
+	}
+	if (!ref_FN || !query_FN || !output_FN) { puts("ERROR: -r, -q and -o are required"); exit(1); }
+	FILE *output = fopen(output_FN, "wb");
+	if (!output) { fprintf(stderr, "ERROR: Cannot open output: %s\n", output_FN); exit(2); }
+	setvbuf(output, 0, _IOFBF, 1 << 22);
+	double start = now();
+	init_char2num();
+
+	/* the engine first: without a CUDA device there is nothing this program can do */
+	bg_ctx *ctx = NULL;
+	int rc = bg_init(GPU_DEVICE, &ctx);
+	if (rc) { fprintf(stderr, "ERROR: cannot start the GPU engine: %s\n", bg_last_error()); exit(3); }
+	uint8_t S[256]; bg_default_scoring(Z, S);
+	if ((rc = bg_set_scoring(ctx, S))) die_gpu("bg_set_scoring", rc);
+
+	if (DO_ACCEL) { fputs("ERROR: accelerator (.acx) search is not wired into this build yet\n", stderr); exit(1); }
+	int usedb = is_edx(ref_FN);
+	if (usedb) { puts("\nEDB database provided. Parsing..."); load_edx(ref_FN, &R); }
+	if (tax_FN) load_taxonomy(tax_FN);
+	load_queries(query_FN, &Q);
+	if (!usedb) load_fasta_refs(ref_FN, &R);
+	else if (R.shear && (uint32_t)(Q.maxLenQ / THRES) > R.shear) {
+		fputs("ERROR: DB incompatible with selected queries/identity.\n", stderr);
+		if (!DO_HEUR) exit(1);
+		fputs("!!! WARNING: Error overridden by use of heuristic mode!\n", stderr);
+	}
+	if ((rc = bg_load_db(ctx, R.packed, R.ClumpLen, R.numRclumps, 0))) die_gpu("bg_load_db", rc);
+
+	PodList *Pods = xcalloc(Q.numUniqQ, sizeof(*Pods));
+	int mode = RUNMODE == FORAGE ? BG_MODE_ALL : BG_MODE_MIN;
+	search_all_vs_all(ctx, &Q, &R, 0, Pods, mode);
+	printf("Search complete. Consolidating results...\n");
+	Rep P = {output, &Q, &R, taxasuppress};
+	if (RUNMODE == BEST) report_best(&P, Pods);
+	else if (RUNMODE == ALLPATHS) report_allpaths_or_forage(&P, Pods, 0);
+	else if (RUNMODE == FORAGE) report_allpaths_or_forage(&P, Pods, 1);
+	else report_capitalist(&P, Pods);
+	fclose(output);
+	bg_free(ctx);
+	printf("\nAlignment time: %f seconds\n", now() - start);
+	return 0;
+}
