@@ -39,7 +39,7 @@ static long REBASE_AMT = 500; static int REBASE = 0;
 static float TAXLEVELS_STRICT[] = {.65f, .75f, .78f, .82f, .86f, .94f, .98f, .995f},
              TAXLEVELS_LENIENT[] = {.55f, .70f, .75f, .80f, .84f, .93f, .97f, .985f},   /* burst.c:264-266 */
              *TAXLEVELS = TAXLEVELS_LENIENT;
-static int QUIET = 0, GPU_DEVICE = 0;
+static int QUIET = 0, GPU_DEVICE = 0, THREADS = 1;
 
 static uint8_t CHAR2NUM[256];
 static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};   /* burst.c:168 */
@@ -412,6 +412,188 @@ static void die_gpu(const char *what, int rc) {
 	exit(rc == BG_ENOMEM ? 3 : 4);
 }
 
+
+/* =============================================================================================
+ * Accelerator (.acx): reader (burst.c:3535-3594) and candidate generation (burst.c:3232-3282,
+ * 4085-4133).  The file does not record N (12 or 15, a compile-time constant of the reference
+ * binary, burst.c:96-98); it is inferred from the file size.
+ * ============================================================================================= */
+typedef struct { uint64_t *off; uint8_t *post; uint32_t *bad, nbad; int big; uint64_t nk; } Acx;
+static const uint8_t AMBIG_N[16] = {0, 1, 1, 1, 1, 4, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3};
+static const uint8_t AMBIG_B[16][4] = {{0}, {0}, {1}, {2}, {3}, {0, 1, 2, 3}, {2, 3}, {0, 1}, {0, 2}, {1, 3}, {1, 2}, {0, 3},
+	{1, 2, 3}, {0, 1, 2}, {0, 1, 3}, {0, 2, 3}};                              /* burst.c:1372-1375 */
+
+static void load_acx(const char *fn, Acx *A) {
+	FILE *in = fopen(fn, "rb");
+	if (!in) { fprintf(stderr, "Cannot read accelerator '%s'\n", fn); exit(1); }
+	fseeko(in, 0, SEEK_END); uint64_t fsz = ftello(in); rewind(in);
+	uint8_t cb = (uint8_t)fgetc(in), ver = cb & 0xF, didZ = (cb >> 6) & 1;
+	if (didZ && !Z) { fprintf(stderr, "ERROR: Accelerator built without '-y'; can't use '-y'\n"); exit(1); }
+	if (cb < 128 || (ver != 0 && ver != 1)) { fprintf(stderr, "ERROR: invalid accelerator [%u:%u]\n", cb, ver); exit(1); }
+	uint32_t szBL; rd(&szBL, 4, 1, in);
+	memset(A, 0, sizeof(*A)); A->big = ver == 1;
+	int found = 0;
+	for (int n = 12; n <= 15 && !found; n += 3) {
+		uint64_t nk = 1ull << (2 * n);
+		if (fsz < 5 + nk * 4) continue;
+		uint32_t *Lens = xmalloc(nk * 4);
+		fseeko(in, 5, SEEK_SET); rd(Lens, 4, nk, in);
+		uint64_t bytes = 0;
+		for (uint64_t i = 0; i < nk; ++i) bytes += A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3;
+		if (5 + nk * 4 + bytes + (uint64_t)szBL * 4 == fsz) {
+			found = 1; SCOUR_N = n; A->nk = nk;
+			A->off = xmalloc((nk + 1) * 8); A->off[0] = 0;
+			for (uint64_t i = 0; i < nk; ++i) A->off[i + 1] = A->off[i] + (A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3);
+			A->post = xmalloc(bytes + 16); rd(A->post, 1, bytes, in); memset(A->post + bytes, 0, 16);
+			A->bad = xmalloc((uint64_t)szBL * 4 + 4); rd(A->bad, 4, szBL, in); A->nbad = szBL;
+		}
+		free(Lens);
+	}
+	fclose(in);
+	if (!found) { fputs("ERROR: accelerator size matches neither a DB12 nor a DB15 layout\n", stderr); exit(1); }
+	printf(" --> [Accel] Accelerator found (DB%d, %s format), %u ambiguous entries\n", SCOUR_N, A->big ? "LARGE" : "SMALL", szBL);
+}
+
+typedef struct { uint32_t v, i; } Split;
+static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }
+static int cmp_refcount(const void *a, const void *b) { const Split *A = a, *B = b; return A->i > B->i ? -1 : B->i > A->i; }   /* burst.c:4028-4031 */
+
+static void ambig_words(uint64_t *W, uint64_t *wix, const char *s, uint32_t j, uint32_t w, int ix) {      /* burst.c:3232-3236 */
+	if (ix == SCOUR_N) W[(*wix)++] = (uint64_t)w << 32 | j;
+	else for (int i = 0; i < AMBIG_N[(uint8_t)s[ix] & 15]; ++i) ambig_words(W, wix, s, j, w << 2 | AMBIG_B[(uint8_t)s[ix] & 15][i], ix + 1);
+}
+
+typedef struct { bg_task *t; uint64_t n, cap; } TaskVec;
+static void task_push(TaskVec *T, uint32_t q, uint32_t c) {
+	if (T->n == T->cap) { T->cap = T->cap ? T->cap * 2 : (1 << 16); T->t = xrealloc(T->t, T->cap * sizeof(bg_task)); }
+	T->t[T->n].query = q; T->t[T->n++].clump = c;
+}
+
+/* Accelerated search (burst.c:4018-4316).  Bunches of QBUNCH sorted queries share one candidate
+ * list; tasks are emitted in the reference's loop order (bunch; candidates by descending k-mer
+ * count, then the always-visited BadList; queries of the bunch), so hits sorted by task index are
+ * in discovery order.  The per-query skip uses the starting budget (the reference's running Emac
+ * is never larger), which can only add visits whose lanes are later discarded as non-minimal. */
+static void accel_search(bg_ctx *ctx, Queries *Q, Refs *R, Acx *A, PodList *Pods, int mode, int threads) {
+	uint64_t nAcc = Q->QBins[1], newUniqQ = Q->newUniqQ;
+	if (!nAcc) return;
+	uint64_t QBUNCH = newUniqQ / ((uint64_t)threads * 128);
+	if (QBUNCH > 16) QBUNCH = 16;
+	if (!QBUNCH) QBUNCH = 1;
+	printf("Setting QBUNCH to %" PRIu64 "\nUsing ACCELERATOR to align %" PRIu64 " unique queries...\n", QBUNCH, nAcc);
+	uint32_t N = (uint32_t)SCOUR_N, numRclumps = R->numRclumps;
+	uint16_t *Hash = xcalloc(numRclumps, sizeof(*Hash));
+	uint32_t *Cache = xmalloc(((uint64_t)numRclumps + 1) * 4);
+	Split *Cand = xmalloc(((uint64_t)numRclumps + 1) * sizeof(*Cand));
+	uint64_t wcap = 1 << 16, *W = xmalloc(wcap * 8);
+	uint16_t *best = xmalloc(Q->numUniqQ * sizeof(*best));
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[i] = 0xFFFF;
+	PodList *SPods = xcalloc(newUniqQ, sizeof(*SPods));                 /* per strand, folded below (4299-4312) */
+	TaskVec T = {0};
+	const uint64_t TASK_FLUSH = 1ull << 24;
+	uint64_t batch_q0 = 0;                                              /* first query (UniBins index) of the open batch */
+
+	for (uint64_t z = 0; z <= nAcc; z += QBUNCH) {
+		int last = z >= nAcc;
+		if (last || T.n >= TASK_FLUSH) {                                /* ---- run the open batch [batch_q0, z) ---- */
+			uint64_t qa = batch_q0, qb = last ? nAcc : z, nq = qb - qa;
+			if (nq && T.n) {
+				uint64_t *off = xmalloc((nq + 1) * 8), tot = 0;
+				uint16_t *bud = xmalloc(nq * 2); uint32_t *slot = xmalloc(nq * 4);
+				for (uint64_t j = 0; j < nq; ++j) { off[j] = tot; tot += Q->ShrBins[Q->UniBins[qa + j].six].len; }
+				off[nq] = tot;
+				uint8_t *codes = xmalloc(tot + 16);
+				for (uint64_t j = 0; j < nq; ++j) {
+					UniBin *u = Q->UniBins + qa + j; ShrBin *sb = Q->ShrBins + u->six;
+					memcpy(codes + off[j], u->seq, sb->len); bud[j] = sb->ed; slot[j] = (uint32_t)u->six;
+				}
+				bg_queries bq = {codes, off, bud, slot, (uint32_t)nq, (uint32_t)Q->numUniqQ};
+				bg_hit *hits = NULL; uint64_t nh = 0;
+				int rc = bg_align_batch(ctx, &bq, T.t, T.n, mode, best, &hits, &nh);
+				if (rc) die_gpu("bg_align_batch", rc);
+				for (uint64_t h = 0; h < nh; ++h) {
+					bg_task t = T.t[hits[h].task];
+					UniBin *u = Q->UniBins + qa + t.query; ShrBin *sb = Q->ShrBins + u->six;
+					uint32_t refIx = t.clump * VECSZ + hits[h].lane;
+					if (refIx >= R->totR) continue;                         /* burst.c:4229 */
+					Pod p = {identity(hits[h].ed, sb->len, hits[h].gap_q), refIx, hits[h].final_pos, hits[h].gap_r, hits[h].gap_q, hits[h].ed, u->rc};
+					pod_push(SPods + u->six + (u->rc ? Q->numUniqQ : 0), p);
+				}
+				bg_free_hits(hits); free(off); free(bud); free(slot); free(codes);
+			}
+			T.n = 0; batch_q0 = z;
+			if (!QUIET) printf("\rSearch Progress: [%3.2f%%]", 100.0 * (double)MIN(z, nAcc) / (double)nAcc);
+			if (last) break;
+		}
+		uint64_t bound = MIN(z + QBUNCH, nAcc), wix = 0;
+		uint32_t min_mmatch = UINT32_MAX, mm[16];
+		for (uint64_t j = z; j < bound; ++j) {                          /* burst.c:4085-4114 */
+			UniBin *u = Q->UniBins + j; ShrBin *sb = Q->ShrBins + u->six;
+			uint32_t len = sb->len, err = sb->ed, kload = err * N + N, mmatch = kload < len ? len - kload : 0;
+			uint32_t heur = DO_HEUR ? (len >> 4) + 1u : 0;
+			if (mmatch < heur) mmatch = heur;
+			if (mmatch < min_mmatch) min_mmatch = mmatch;
+			mm[j - z] = kload < len ? len - kload : 1;                    /* the per-query skip threshold, burst.c:4163-4164 */
+			const char *s = u->seq;
+			uint64_t need = wix + (uint64_t)len * (j >= Q->QBins[0] ? 1 : 1024) + 16;
+			if (need > wcap) { while (wcap < need) wcap *= 2; W = xrealloc(W, wcap * 8); }
+			if (j >= Q->QBins[0]) {                                       /* unambiguous: rolling 2-bit words */
+				uint32_t mask = N == 16 ? 0xFFFFFFFFu : (1u << (2 * N)) - 1, w = 0;
+				for (uint32_t k = 0; k < len; ++k) {
+					w = (w << 2 | (uint32_t)(s[k] - 1)) & mask;
+					if (k + 1 >= N) W[wix++] = (uint64_t)w << 32 | (uint32_t)(j - z);
+				}
+			} else for (uint32_t k = 0; k + N <= len; ++k) {              /* ambiguous: every variant of every window */
+				if (Z) { uint32_t p = k, e = k + N; for (; p < e; ++p) if (s[p] == 5) break; if (p < e) { k = p; continue; } }
+				uint64_t variants = 1;
+				for (uint32_t p = k; p < k + N; ++p) variants *= AMBIG_N[(uint8_t)s[p] & 15];
+				if (wix + variants + 16 > wcap) { while (wcap < wix + variants + 16) wcap *= 2; W = xrealloc(W, wcap * 8); }
+				ambig_words(W, &wix, s + k, (uint32_t)(j - z), 0, 0);
+			}
+		}
+		qsort(W, wix, 8, cmp_u64);                                      /* burst.c:4118 */
+		/* burst.c:3238-3282: each distinct word adds its largest per-query multiplicity to every clump it lists */
+		uint32_t cix = 0;
+		for (uint64_t i = 0; i < wix;) {
+			uint32_t v = (uint32_t)(W[i] >> 32), mx = 0; uint64_t e = i;
+			while (e < wix && (uint32_t)(W[e] >> 32) == v) { uint64_t r = e; while (r < wix && W[r] == W[e]) ++r; if (r - e > mx) mx = (uint32_t)(r - e); e = r; }
+			const uint8_t *p = A->post + A->off[v], *end = A->post + A->off[(uint64_t)v + 1];
+#define BUMP(px) do { uint32_t px_ = (px); if (px_ < numRclumps) { if (!Hash[px_]) Cache[cix++] = px_; uint32_t nv_ = mx + Hash[px_]; Hash[px_] = (uint16_t)(nv_ > 65535 ? 65535 : nv_); } } while (0)
+			if (A->big) for (; p < end; p += 3) { uint32_t px; memcpy(&px, p, 4); BUMP(px & 0xFFFFFF); }
+			else for (; p < end; p += 5) {
+				uint64_t PX; memcpy(&PX, p, 8);
+				BUMP((uint32_t)(PX & 0xFFFFF));
+				if (p + 3 >= end) break;
+				BUMP((uint32_t)((PX >> 20) & 0xFFFFF));
+			}
+			i = e;
+		}
+		uint32_t nref = 0;
+		for (uint32_t i = 0; i < cix; ++i) { uint16_t *h = Hash + Cache[i]; if (*h > min_mmatch) Cand[nref++] = (Split){Cache[i], *h}; *h = 0; }
+		if (nref > 24) qsort(Cand, nref, sizeof(*Cand), cmp_refcount);  /* burst.c:4038-4046 */
+		else for (uint32_t i = 1, j; i < nref; ++i) {
+			Split key = Cand[i];
+			for (j = i; j && Cand[j - 1].i < key.i; --j);
+			memmove(Cand + j + 1, Cand + j, sizeof(*Cand) * (i - j)); Cand[j] = key;
+		}
+		for (uint32_t i = 0; i < nref; ++i) for (uint64_t j = z; j < bound; ++j)       /* burst.c:4137-4168 */
+			if (Cand[i].i > mm[j - z]) task_push(&T, (uint32_t)(j - batch_q0), Cand[i].v);
+		if (!Q->skipAmbig) for (uint32_t i = 0; i < A->nbad; ++i) for (uint64_t j = z; j < bound; ++j)
+			if (A->bad[i] < numRclumps) task_push(&T, (uint32_t)(j - batch_q0), A->bad[i]);
+	}
+	if (!QUIET) printf("\rSearch Progress: [100.00%%]\n");
+	/* fold strands: forward list, then reverse-complement list (burst.c:4299-4312); lists are push-front */
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *F = SPods + i, *Rc = Q->rc ? SPods + Q->numUniqQ + i : NULL;
+		/* Pods[] is kept in discovery order and read backwards; "fwd list then rc list" read backwards is
+		 * rc pods (discovery order) followed by fwd pods (discovery order) */
+		if (Rc) for (uint32_t k = 0; k < Rc->n; ++k) if (mode != BG_MODE_MIN || Rc->p[k].mismatches <= best[i]) pod_push(Pods + i, Rc->p[k]);
+		for (uint32_t k = 0; k < F->n; ++k) if (mode != BG_MODE_MIN || F->p[k].mismatches <= best[i]) pod_push(Pods + i, F->p[k]);
+		free(F->p); if (Rc) free(Rc->p);
+	}
+	free(SPods); free(best); free(Hash); free(Cache); free(Cand); free(W); free(T.t);
+}
+
 /* =============================================================================================
  * Search: all-vs-all (no accelerator, and the accelerator's left-over bin), burst.c:4318-4520.
  * Discovery order per query slot there is (clump, query, lane) ascending; the engine returns
@@ -743,7 +925,7 @@ int main(int argc, char *argv[]) {
 			if (THRES < 0.01f) THRES = 0.01f;
 			printf(" --> Setting identity threshold to %f\n", THRES);
 		}
-		else if (OPT("--threads", "-t")) { NEEDARG("--threads requires integer argument") printf(" --> Host threads are not used by the GPU path (-t %s ignored)\n", argv[i]); }
+		else if (OPT("--threads", "-t")) { NEEDARG("--threads requires integer argument") THREADS = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1; printf(" --> Setting threads to %d (bunch size only; the DP runs on the GPU)\n", THREADS); }
 		else if (OPT("--shear", "-s")) { REBASE = 1; if (i + 1 != argc && argv[i + 1][0] != '-') REBASE_AMT = atol(argv[++i]); if (!REBASE_AMT) REBASE = 0; }
 		else if (OPT("--heuristic", "-hr")) { DO_HEUR = 1; printf(" --> WARNING: Heuristic mode set; optimality not guaranteed at low ids\n"); }
 		else if (!strcmp(argv[i], "--noprogress")) { QUIET = 1; printf(" --> Surpressing progress indicator\n"); }
@@ -767,7 +949,8 @@ int main(int argc, char *argv[]) {
 	uint8_t S[256]; bg_default_scoring(Z, S);
 	if ((rc = bg_set_scoring(ctx, S))) die_gpu("bg_set_scoring", rc);
 
-	if (DO_ACCEL) { fputs("ERROR: accelerator (.acx) search is not wired into this build yet\n", stderr); exit(1); }
+	Acx A; memset(&A, 0, sizeof(A));
+	if (DO_ACCEL) load_acx(xcel_FN, &A);
 	int usedb = is_edx(ref_FN);
 	if (usedb) { puts("\nEDB database provided. Parsing..."); load_edx(ref_FN, &R); }
 	if (tax_FN) load_taxonomy(tax_FN);
@@ -782,7 +965,10 @@ int main(int argc, char *argv[]) {
 
 	PodList *Pods = xcalloc(Q.numUniqQ, sizeof(*Pods));
 	int mode = RUNMODE == FORAGE ? BG_MODE_ALL : BG_MODE_MIN;
-	search_all_vs_all(ctx, &Q, &R, 0, Pods, mode);
+	if (DO_ACCEL) accel_search(ctx, &Q, &R, &A, Pods, mode, THREADS);
+	/* queries the accelerator cannot vouch for (or all of them without -a) go all-vs-all, burst.c:4320-4323 */
+	uint64_t firstQ = DO_ACCEL ? Q.QBins[1] : 0;
+	if (firstQ != Q.newUniqQ && !(DO_ACCEL && Q.skipAmbig)) search_all_vs_all(ctx, &Q, &R, firstQ, Pods, mode);
 	printf("Search complete. Consolidating results...\n");
 	Rep P = {output, &Q, &R, taxasuppress};
 	if (RUNMODE == BEST) report_best(&P, Pods);

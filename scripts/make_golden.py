@@ -95,7 +95,7 @@ def run_ref(args, cwd):
 
 
 def cli_case(name, seed, flags, nfam=10, per=5, length=420, nreads=260, lo=90, hi=130, err=0.04, iupac=0.0, tax=False,
-             edx=None, multiline=False):
+             edx=None, multiline=False, acx=False):
     rng = np.random.default_rng(seed)
     d = os.path.join(GOLD, "cli", name)
     shutil.rmtree(d, ignore_errors=True); os.makedirs(d)
@@ -117,11 +117,17 @@ def cli_case(name, seed, flags, nfam=10, per=5, length=420, nreads=260, lo=90, h
     if tax:
         write_tax(os.path.join(d, "tax.txt"), rnames, rng)
     ref_arg = "refs.fa"
+    acx_args = []
     if edx:
-        rc, log = run_ref(["-r", "refs.fa", "-o", "db.edx"] + edx, d)
+        rc, log = run_ref(["-r", "refs.fa", "-o", "db.edx"] + edx + (["-a", "db.acx"] if acx else []), d)
         assert rc == 0 and os.path.exists(os.path.join(d, "db.edx")), log
         ref_arg = "db.edx"
-    args = ["-r", ref_arg, "-q", "queries.fa", "-o", "expected.b6"] + flags + (["-b", "tax.txt"] if tax else [])
+        if acx:   # the 4^12-entry length table is almost all zeros: keep the accelerator gzip-compressed
+            import gzip
+            with open(os.path.join(d, "db.acx"), "rb") as fi, gzip.open(os.path.join(d, "db.acx.gz"), "wb", 9) as fo:
+                shutil.copyfileobj(fi, fo)
+            acx_args = ["-a", "db.acx"]
+    args = ["-r", ref_arg, "-q", "queries.fa", "-o", "expected.b6"] + acx_args + flags + (["-b", "tax.txt"] if tax else [])
     rc, log = run_ref(args, d)
     assert rc == 0, log
     rows = open(os.path.join(d, "expected.b6")).read().splitlines()
@@ -130,6 +136,9 @@ def cli_case(name, seed, flags, nfam=10, per=5, length=420, nreads=260, lo=90, h
               open(os.path.join(d, "case.json"), "w"), indent=1)
     print("%-28s %5d rows  %s" % (name, len(rows), " ".join(args)))
     assert len(rows) > 20, log
+    if acx:
+        os.remove(os.path.join(d, "db.acx"))
+        return log
 
 
 def main():
@@ -147,6 +156,13 @@ def main():
     cli_case("edx_allpaths_fr", 10, ["-m", "ALLPATHS", "-i", "0.97", "-fr"], length=900, edx=["-d", "DNA", "140", "-s", "1", "-i", "0.97"])
     cli_case("edx_capitalist_tax", 11, ["-m", "CAPITALIST", "-i", "0.97"], length=900, tax=True, edx=["-d", "DNA", "140", "-s", "1", "-i", "0.97"])
     cli_case("edx_quick_forage", 12, ["-m", "FORAGE", "-i", "0.96"], edx=["-d", "QUICK"])
+    DB = ["-d", "DNA", "140", "-s", "1", "-i", "0.97"]
+    cli_case("acx_best", 13, ["-m", "BEST", "-i", "0.97"], length=900, edx=DB, acx=True)
+    cli_case("acx_allpaths_fr", 14, ["-m", "ALLPATHS", "-i", "0.97", "-fr"], length=900, edx=DB, acx=True)
+    cli_case("acx_capitalist_tax_iupac", 15, ["-m", "CAPITALIST", "-i", "0.97", "-fr"], length=900, tax=True, iupac=0.003, edx=DB, acx=True)
+    cli_case("acx_forage_mixed_lengths", 16, ["-m", "FORAGE", "-i", "0.95", "-fr"], length=900, lo=30, hi=130, iupac=0.003, edx=DB, acx=True)
+    cli_case("acx_best_lowid_fallback_bin", 17, ["-m", "BEST", "-i", "0.90"], length=900, lo=60, hi=130, err=0.08, edx=["-d", "DNA", "140", "-s", "1", "-i", "0.90"], acx=True)
+    cli_case("acx_y_wildcard", 18, ["-m", "ALLPATHS", "-i", "0.96", "-y"], length=900, iupac=0.004, edx=["-d", "DNA", "140", "-s", "1", "-i", "0.96", "-y"], acx=True)
 
 
 if __name__ == "__main__":
