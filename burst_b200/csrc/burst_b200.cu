@@ -492,6 +492,7 @@ struct bg_ctx {
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t h_counters[4] = {0, 0, 0, 0};
 	bool ran = false;
+	bool by_runs = false; std::vector<uint32_t> run_key;      // run-list batches: task index -> run * BG_RUN_MAX + i
 };
 
 extern "C" void bg_default_scoring(int z, uint8_t S[256]) {
@@ -657,7 +658,7 @@ extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *ta
 	k_query_prep<<<(Q->nq * 16 + 255) / 256, 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, Q->nq, c->d_peq.p);
 	CU(cudaGetLastError());
 	CU(cudaStreamSynchronize(c->stream));     // the caller's host buffers may be reused after this returns
-	c->ran = false;
+	c->ran = false; c->by_runs = false;
 	return BG_OK;
 }
 
@@ -778,6 +779,7 @@ extern "C" int bg_batch_download(bg_ctx *c, bg_hit *hits, uint64_t cap, uint16_t
 	CU(cudaStreamSynchronize(c->stream));
 	if (best_out) for (uint32_t i = 0; i < c->nslots; ++i) best_out[i] = (uint16_t)std::min<uint32_t>(b32[i], 0xFFFF);
 	if (hits) std::sort(hits, hits + n, [](const bg_hit &a, const bg_hit &b) { return a.task != b.task ? a.task < b.task : a.lane < b.lane; });
+	if (hits && c->by_runs) for (uint64_t i = 0; i < n; ++i) hits[i].task = c->run_key[hits[i].task];
 	return BG_OK;
 }
 
@@ -799,6 +801,41 @@ extern "C" int bg_align_batch(bg_ctx *c, const bg_queries *Q, const bg_task *tas
 		uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
 	if (!hits || !nhits) return fail(BG_EINVAL, "bg_align_batch: null output");
 	int rc = bg_batch_upload(c, Q, tasks, ntasks); if (rc) return rc;
+	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
+	uint64_t n = 0;
+	rc = bg_batch_count(c, &n); if (rc) return rc;
+	bg_hit *h = (bg_hit *)malloc((n ? n : 1) * sizeof(bg_hit));
+	if (!h) return fail(BG_ENOMEM, "malloc hits");
+	rc = bg_batch_download(c, h, n, best_inout);
+	if (rc) { free(h); return rc; }
+	*hits = h; *nhits = n;
+	return BG_OK;
+}
+
+// Run lists (bg_run): expanded to tasks here; hits come back keyed run * BG_RUN_MAX + i.
+static int expand_runs(const bg_queries *Q, const bg_run *runs, uint64_t nruns, std::vector<bg_task> &tasks, std::vector<uint32_t> &key) {
+	if (!Q || !runs) return fail(BG_EINVAL, "bg_batch_upload_runs: null argument");
+	if (nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_batch_upload_runs: %llu runs in one batch (limit 2^28-1)", (unsigned long long)nruns);
+	tasks.clear(); key.clear();
+	for (uint64_t r = 0; r < nruns; ++r) {
+		if (!runs[r].nq || runs[r].nq > BG_RUN_MAX || (uint64_t)runs[r].query0 + runs[r].nq > Q->nq)
+			return fail(BG_EINVAL, "bg_batch_upload_runs: run %llu (query0 %u, nq %u) is malformed", (unsigned long long)r, runs[r].query0, runs[r].nq);
+		for (uint32_t i = 0; i < runs[r].nq; ++i) { tasks.push_back(bg_task{runs[r].query0 + i, runs[r].clump}); key.push_back((uint32_t)(r * BG_RUN_MAX + i)); }
+	}
+	return BG_OK;
+}
+extern "C" int bg_batch_upload_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns) {
+	if (!c) return fail(BG_EINVAL, "null ctx");
+	std::vector<bg_task> tasks;
+	int rc = expand_runs(Q, runs, nruns, tasks, c->run_key); if (rc) return rc;
+	rc = bg_batch_upload(c, Q, tasks.data(), tasks.size());
+	c->by_runs = rc == BG_OK;
+	return rc;
+}
+extern "C" int bg_align_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns, int mode,
+		uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
+	if (!hits || !nhits) return fail(BG_EINVAL, "bg_align_runs: null output");
+	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;
 	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
 	uint64_t n = 0;
 	rc = bg_batch_count(c, &n); if (rc) return rc;

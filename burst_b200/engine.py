@@ -13,6 +13,8 @@ LIB_PATH = os.path.join(HERE, "libburst_b200.so")
 HIT_DTYPE = np.dtype([("task", "<u4"), ("lane", "u1"), ("ed", "u1"), ("gap_q", "u1"),
                       ("gap_r", "u1"), ("final_pos", "<u4")])
 TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
+RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
+RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
 
 
@@ -33,7 +35,7 @@ class BgStats(C.Structure):
 EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scoring", "bg_default_scoring",
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
-           "bg_align_batch", "bg_free_hits"]
+           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs"]
 
 
 def load_library():
@@ -59,6 +61,9 @@ def load_library():
     L.bg_batch_stats.argtypes = [C.c_void_p, C.POINTER(BgStats)]
     L.bg_align_batch.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64, C.c_int,
                                  C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
+    L.bg_batch_upload_runs.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64]
+    L.bg_align_runs.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64, C.c_int,
+                                C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.bg_free_hits.argtypes = [C.c_void_p]
     return L
 
@@ -131,6 +136,12 @@ class Engine:
         self._nslots = q.nslots
         self._check(self.lib.bg_batch_upload(self.ctx, C.byref(q), p, n))
 
+    def upload_runs(self, codes, offset, budget, runs, slot=None, nslots=0):
+        q = self._queries(codes, offset, budget, slot, nslots)
+        r = np.ascontiguousarray(runs, RUN_DTYPE)
+        self._nslots = q.nslots
+        self._check(self.lib.bg_batch_upload_runs(self.ctx, C.byref(q), r.ctypes.data, len(r)))
+
     def run(self, mode=MODE_MIN, best_in=None):
         b = None if best_in is None else np.ascontiguousarray(best_in, np.uint16)
         self._check(self.lib.bg_batch_run(self.ctx, mode, None if b is None else b.ctypes.data))
@@ -163,13 +174,17 @@ class Engine:
         return s.asdict()
 
     # ---- one call, host buffers in, host buffers out ----
-    def align(self, codes, offset, budget, tasks, mode=MODE_MIN, slot=None, nslots=0, best=None):
+    def align(self, codes, offset, budget, tasks, mode=MODE_MIN, slot=None, nslots=0, best=None, runs=None):
         q = self._queries(codes, offset, budget, slot, nslots)
-        t, n, p = self._tasks(tasks)
         self._nslots = q.nslots
         b = np.full(q.nslots, 0xFFFF, np.uint16) if best is None else np.ascontiguousarray(best, np.uint16).copy()
         hp = C.c_void_p(); nh = C.c_uint64(0)
-        self._check(self.lib.bg_align_batch(self.ctx, C.byref(q), p, n, mode, b.ctypes.data, C.byref(hp), C.byref(nh)))
+        if runs is not None:
+            r = np.ascontiguousarray(runs, RUN_DTYPE)
+            self._check(self.lib.bg_align_runs(self.ctx, C.byref(q), r.ctypes.data, len(r), mode, b.ctypes.data, C.byref(hp), C.byref(nh)))
+        else:
+            t, n, p = self._tasks(tasks)
+            self._check(self.lib.bg_align_batch(self.ctx, C.byref(q), p, n, mode, b.ctypes.data, C.byref(hp), C.byref(nh)))
         hits = np.zeros(nh.value, HIT_DTYPE)
         if nh.value:
             C.memmove(hits.ctypes.data, hp, nh.value * HIT_DTYPE.itemsize)

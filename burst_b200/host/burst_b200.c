@@ -493,7 +493,7 @@ static void accel_search(bg_ctx *ctx, Queries *Q, Refs *R, Acx *A, PodList *Pods
 	const uint64_t TASK_FLUSH = 1ull << 24;
 	uint64_t batch_q0 = 0;                                              /* first query (UniBins index) of the open batch */
 
-	for (uint64_t z = 0; z <= nAcc; z += QBUNCH) {
+	for (uint64_t z = 0;; z += QBUNCH) {                              /* ends through `last` below */
 		int last = z >= nAcc;
 		if (last || T.n >= TASK_FLUSH) {                                /* ---- run the open batch [batch_q0, z) ---- */
 			uint64_t qa = batch_q0, qb = last ? nAcc : z, nq = qb - qa;

@@ -45,6 +45,14 @@ enum { BG_MODE_MIN = 0,   /* lanes at the per-slot minimum: BEST, ALLPATHS, CAPI
 /* One DP task = one call pair aded_*() + reScoreM_*() of the reference: query j vs clump ri. */
 typedef struct { uint32_t query, clump; } bg_task;
 
+/* One clump visit of the reference's bunch loop (burst.c:4137-4157: unpack clump ri once, then
+ * "for each query j in the bunch"): the nq <= BG_RUN_MAX consecutive queries query0 .. query0+nq-1
+ * of the batch against one clump.  A run is the unit the GPU schedules (one warp scans the clump
+ * once for all its queries); a bunch x candidate-list driver emits runs directly, 1/16th the bytes
+ * of the equivalent bg_task list.  Hits of a run-list batch carry task = run * BG_RUN_MAX + (query - query0). */
+#define BG_RUN_MAX 16
+typedef struct { uint32_t clump, query0, nq; } bg_run;
+
 /* One reported lane = one ResultPod (burst.c:3999-4004) minus the host-only fields.
  * refIx = tasks[task].clump * 16 + lane (burst.c:4234); ed = mismatches; gap_q = numGapQ
  * (shift), gap_r = numGapR (shiftR), final_pos = 1-based end column in the clump. */
@@ -97,6 +105,8 @@ int  bg_load_db(bg_ctx *ctx, const uint8_t *packed, const uint32_t *clump_len,
 /* Host -> device copy of queries and tasks.  tasks == NULL means all-vs-all in the
  * reference's fallback order (burst.c:4344, 4365): task t = clump (t / nq), query (t % nq). */
 int  bg_batch_upload(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint64_t ntasks);
+/* The same with the task list given as runs (see bg_run). */
+int  bg_batch_upload_runs(bg_ctx *ctx, const bg_queries *q, const bg_run *runs, uint64_t nruns);
 /* best_in: nslots running minima carried in from earlier batches (NULL = none). */
 int  bg_batch_run(bg_ctx *ctx, int mode, const uint16_t *best_in);
 /* Split form of bg_batch_run for a reference-sharded DB: filter+extend, then an external
@@ -114,6 +124,8 @@ int  bg_batch_stats(bg_ctx *ctx, bg_stats *out);
  * malloc()ed by the library (free with bg_free_hits). */
 int  bg_align_batch(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint64_t ntasks,
                     int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits);
+int  bg_align_runs(bg_ctx *ctx, const bg_queries *q, const bg_run *runs, uint64_t nruns,
+                   int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits);
 void bg_free_hits(bg_hit *hits);
 
 #ifdef __cplusplus

@@ -1,0 +1,68 @@
+"""CPU-only: the HOST logic of the drop-in binary (CLI, FASTA/.edx/.acx readers, query preprocessing,
+candidate generation, pod lists, BEST/ALLPATHS/CAPITALIST/FORAGE reporters, taxonomy) against the
+.b6 files the reference binary wrote (tests/golden/cli, made by scripts/make_golden.py).
+
+The binary under test is oracle/_sim/burst-b200-sim: burst_b200/host/burst_b200.c linked against
+oracle/abi_sim.c, a stand-in for the engine ABI backed by the scalar oracle -- test infrastructure
+that exists so this tier can run without a GPU.  The same cases run against the real binary and
+the CUDA engine in tests/test_gpu_golden.py."""
+import gzip
+import json
+import os
+import shutil
+import subprocess
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden", "cli")
+SIM = os.path.join(ROOT, "oracle", "_sim", "burst-b200-sim")
+CASES = sorted(os.listdir(GOLD))
+
+
+@pytest.fixture(scope="module")
+def sim():
+    subprocess.run(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "sim"], check=True)
+    return SIM
+
+
+def run_case(binary, case, tmp_path, extra=()):
+    d = os.path.join(GOLD, case)
+    meta = json.load(open(os.path.join(d, "case.json")))
+    out = str(tmp_path / "out.b6")
+    args = [out if a == "OUT" else a for a in meta["args"]]
+    if "db.acx" in args:
+        acx = str(tmp_path / "db.acx")
+        with gzip.open(os.path.join(d, "db.acx.gz"), "rb") as fi, open(acx, "wb") as fo:
+            shutil.copyfileobj(fi, fo)
+        args[args.index("db.acx")] = acx
+    r = subprocess.run([binary] + args + ["--noprogress"] + list(extra), cwd=d, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = sorted(open(out).read().splitlines())
+    want = sorted(open(os.path.join(d, "expected.b6")).read().splitlines())
+    return got, want
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_host_logic_matches_reference_b6(sim, case, tmp_path):
+    got, want = run_case(sim, case, tmp_path)
+    assert len(got) == len(want), (len(got), len(want))
+    diff = [(a, b) for a, b in zip(got, want) if a != b]
+    assert not diff, "%d rows differ, first: %s" % (len(diff), diff[0])
+
+
+@pytest.mark.parametrize("threads", ["7", "64"])
+def test_bunch_size_does_not_change_rows(sim, tmp_path, threads):
+    """-t only changes QBUNCH (burst.c:4019-4021), never the reported rows."""
+    got, want = run_case(sim, "acx_allpaths_fr", tmp_path, extra=["-t", threads])
+    assert got == want
+
+
+def test_usage_errors_exit_codes(sim, tmp_path):
+    r = subprocess.run([sim, "-r", "x.fa", "-q"], capture_output=True, text=True)
+    assert r.returncode == 1
+    # a missing reference is "invalid input file" -> 1 (burst.c:4894-4897); a missing query file -> 2 (burst.c:639)
+    r = subprocess.run([sim, "-r", "/nonexistent.fa", "-q", "/nonexistent.fa", "-o", str(tmp_path / "o.b6")], capture_output=True, text=True)
+    assert r.returncode == 1
+    refs = os.path.join(GOLD, "fasta_best", "refs.fa")
+    r = subprocess.run([sim, "-r", refs, "-q", "/nonexistent.fa", "-o", str(tmp_path / "o.b6")], capture_output=True, text=True)
+    assert r.returncode == 2
