@@ -10,7 +10,7 @@ candidate clumps, burst.c:4077-4157).
 
   value     whole-job reads/s with queries, tasks and DB resident in HBM (kernels only)
   e2e       the same through bg_align_batch(): pinned host buffers in, hits in host memory out
-  roofline  dominant kernel (k_filter) algorithmic bytes / its CUDA-event time vs measured HBM peak
+  roofline  dominant kernel (k_seed) algorithmic bytes / its CUDA-event time vs measured HBM peak
             -- the kernel is integer-ALU bound, see "alu" and DESIGN.md
   cpu_baseline / --impl reference
             the reference's own aded_mat16L + reScoreM_mat16 (oracle/_ref/libburstref.so, built
@@ -180,21 +180,21 @@ def main():
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    from burst_b200.engine import Engine, MODE_MIN, TASK_DTYPE
+    from burst_b200.engine import Engine, MODE_MIN, RUN_DTYPE
 
     w = build_workload(args, rank)
     stream = torch.cuda.Stream()
     eng = Engine(local, stream=stream.cuda_stream)
     eng.load_db(w["packed"], w["clump_len"])
     nq = len(w["qoff"]) - 1
-    tasks = np.ascontiguousarray(w["tasks"]).view(TASK_DTYPE).reshape(-1)
+    runs = np.ascontiguousarray(w["runs"], RUN_DTYPE)
 
     # pinned host staging for the e2e leg
     def pin(a):
         t = torch.from_numpy(np.ascontiguousarray(a).view(np.uint8).reshape(-1)).pin_memory()
         return t.numpy().view(a.dtype).reshape(a.shape), t
-    p_codes, k1 = pin(w["qcodes"]); p_off, k2 = pin(w["qoff"]); p_bud, k3 = pin(w["budget"]); p_slot, k4 = pin(w["slot"]); p_tasks, k5 = pin(tasks)
-    h2d = p_codes.nbytes + p_off.nbytes + p_bud.nbytes + p_slot.nbytes + p_tasks.nbytes
+    p_codes, k1 = pin(w["qcodes"]); p_off, k2 = pin(w["qoff"]); p_bud, k3 = pin(w["budget"]); p_slot, k4 = pin(w["slot"]); p_runs, k5 = pin(runs)
+    h2d = p_codes.nbytes + p_off.nbytes + p_bud.nbytes + p_slot.nbytes + p_runs.nbytes
 
     def barrier():
         if world > 1:
@@ -202,7 +202,7 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- kernel-only: inputs resident in HBM ----------------
-    eng.upload(p_codes, p_off, p_bud, p_tasks, slot=p_slot, nslots=w["nslots"])
+    eng.upload_runs(p_codes, p_off, p_bud, p_runs, slot=p_slot, nslots=w["nslots"])
     for _ in range(args.warmup):
         eng.run(MODE_MIN); eng.count()
     sampler = ClockSampler(local); sampler.start()
@@ -223,7 +223,7 @@ def main():
     hits, best = eng.download()
     found = int((best[:w["n_reads"]] <= args.edits).sum())
     # planted-read check: every read must be reported at the lane it was cut from
-    tq = w["tasks"][hits["task"], 0]; tc = w["tasks"][hits["task"], 1]
+    tq = runs["query0"][hits["task"] >> 4] + (hits["task"] & 15); tc = runs["clump"][hits["task"] >> 4]
     rd = w["slot"][tq]
     ok = (tc == w["true_clump"][rd]) & (hits["lane"] == w["true_lane"][rd])
     planted = int(len(np.unique(rd[ok])))
@@ -231,11 +231,11 @@ def main():
     # ---------------- e2e: host buffers in, hits out, every step ----------------
     d2h = 0
     for _ in range(min(args.warmup, 2)):
-        eng.align(p_codes, p_off, p_bud, p_tasks, MODE_MIN, slot=p_slot, nslots=w["nslots"])
+        eng.align(p_codes, p_off, p_bud, None, MODE_MIN, slot=p_slot, nslots=w["nslots"], runs=p_runs)
     barrier()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        h, b = eng.align(p_codes, p_off, p_bud, p_tasks, MODE_MIN, slot=p_slot, nslots=w["nslots"])
+        h, b = eng.align(p_codes, p_off, p_bud, None, MODE_MIN, slot=p_slot, nslots=w["nslots"], runs=p_runs)
         d2h = h.nbytes + b.nbytes
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
@@ -255,19 +255,20 @@ def main():
         filt_ms = st["ms_filter"]
         achieved = alg_bytes / (filt_ms / 1e3) / 1e9
         out = {"metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-vectors / u32 packed keys (8-bit reference semantics)",
+               "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32 (bit-parallel automata / packed DP keys; 8-bit reference semantics)",
                "data": "synthetic", "config": config,
                "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_ms / args.steps},
                "gpu_launches": 8 * args.steps,
                "dp_gcups_nominal": st["nominal_cells"] * world / (ms_step / 1e3) / 1e9,
                "dp_gcups_executed": (st["filter_cells"] + st["band_cells"]) * world / (ms_step / 1e3) / 1e9,
+               "seed_steps_per_s": st["seed_steps"] * world / (ms_step / 1e3),
                "work": {"tasks": st["tasks"], "survivors": st["survivors"], "hits": st["hits"], "nominal_cells": st["nominal_cells"],
-                        "filter_cells": st["filter_cells"], "band_cells": st["band_cells"], "reads_found": found, "reads_at_planted_lane": planted,
+                        "filter_cells": st["filter_cells"], "seed_steps": st["seed_steps"], "seed_queries": st["seed_queries"],
+                        "seed_layout": "%d pieces x %d bases" % (st["seed_pieces"], st["seed_piece_len"]), "band_cells": st["band_cells"], "reads_found": found, "reads_at_planted_lane": planted,
                         "ms_filter": st["ms_filter"], "ms_extend": st["ms_extend"], "ms_select": st["ms_select"]},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                            "kernel": "k_filter", "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst figure)",
-                            "note": "k_filter is integer-ALU bound, not HBM bound (see DESIGN.md); algorithmic bytes = sum over tasks of 8*ClumpLen+len+16, +12 per hit"},
-               "alu": {"filter_column_lanes_per_s": st["filter_cells"] / 32.0 / (filt_ms / 1e3) if args.read_len >= 32 else None},
+                            "kernel": "k_seed" if st["seed_queries"] else "k_filter", "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst figure)",
+                            "note": "algorithmic bytes = sum over clump visits (tasks) of 8*ClumpLen+len+16, +12 per hit (SURVEY 8d); the kernel is bound by integer issue + shared-memory lookups, and a bunch's 16 visits of a clump share one pass over it (see DESIGN.md)"},
                "clocks": clocks, "workload_gen_s": w["gen_s"]}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_reference(args, w)

@@ -3,22 +3,28 @@
 // What the reference does per (query, clump) pair:
 //   pass 1  aded_mat16L / aded_mat16   burst.c:1003-1204   16-lane banded edit distance
 //   pass 2  reScoreM_mat16             burst.c:713-886     (score, shift, shiftR) + end column
-// and how this file restructures it for the GPU (DESIGN.md has the full argument):
-//   k_query_prep   per query, 16 match bit-vectors over its first P <= 32 rows
-//   k_filter       one thread per (task, lane): bit-parallel (Myers/Hyyro) semi-global DP of
-//                  the query's first P rows over every column of the lane.  Any alignment
-//                  with <= k errors has a prefix with <= k errors, so columns whose row-P value
-//                  is <= k ("seeds") cover every cell of every <= k alignment within +-k
-//                  diagonals.  >92% of the reference's pass-1 calls die in these rows.
-//   k_extend       one thread per surviving (task, lane): exact banded DP over the hull of the
-//                  seed diagonals, carrying the reference's pass-2 triple packed in one 32-bit
-//                  key so that diag/up/left selection with its tie-break order is a 3-operand
-//                  min/add (DPX VIADDMNMX / VIMNMX3).  Yields pass 1's distance and pass 2's
-//                  (numGapQ, numGapR, finalPos) in one sweep; atomicMin keeps the per-slot best.
-//   k_select       keeps the lanes the reference would have kept (burst.c:4219-4229).
+// and how this file restructures it for the GPU (DESIGN.md section 2 has the full argument):
+//   k_qinfo/k_qtables  per query: budget/length record, Myers match vectors, Shift-And piece tables
+//   k_seed         one warp per RUN (= one clump visit by <= 16 consecutive queries, the reference's
+//                  "unpack the clump once, then loop over the bunch", burst.c:4141-4157).  Pigeonhole:
+//                  an alignment with <= k errors contains one of k+1 disjoint query pieces unchanged.
+//                  All pieces of a query form one 32-bit Shift-And automaton; 16 lanes x 2 column halves
+//                  per warp, the run's 16 automata in registers.  Exact piece matches = seeds ->
+//                  disjoint diagonal clusters [d-k, d+k].
+//   k_filter       queries k_seed cannot take (many errors / short pieces): Myers/Hyyro bit-vector
+//                  semi-global DP of the query's first P <= 32 rows; columns with row-P value <= k
+//                  are seeds (every <= k alignment has a <= k prefix); hull of the seed diagonals.
+//   k_extend       one thread per surviving (task, lane, cluster): exact banded DP, carrying the
+//                  reference's pass-2 triple packed in one 32-bit key so that diag/up/left selection
+//                  with its tie-break order is a 3-operand add-min (DPX VIADDMNMX).  Yields pass 1's
+//                  distance and pass 2's (numGapQ, numGapR, finalPos) in one sweep; atomicMin keeps
+//                  the per-slot best (ShrBins[].ed, burst.c:4220).
+//   k_select       merges the clusters of a lane and keeps the lanes the reference keeps
+//                  (burst.c:4219-4229, 4497).
 // Values <= budget are exact and identical to the reference's saturating u8 arithmetic because
 // every cell > maxED is treated as absent there too (burst.c:1053-1054, 802-803).
 #include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -49,15 +55,31 @@ struct QInfo {            // one query of the batch
 	uint32_t len;
 	uint32_t slot;
 	uint16_t k;           // budget (Emac)
-	uint16_t P;           // rows covered by the prefix filter = min(32, len)
+	uint8_t  P;           // rows covered by the Myers prefix filter = min(32, len)
+	uint8_t  cls;         // 1: handled by k_seed (piece automaton), 0: by k_filter (Myers)
 };
-struct Surv {             // one (task, lane) that survived the prefix filter
-	uint32_t task;
+struct Surv {             // one diagonal cluster of a (task, lane) that survived the filter
+	uint32_t task;        // run * 16 + query-in-run
 	int32_t  lo;          // lowest diagonal (x - y) of the band
-	uint32_t w_lane;      // band width << 8 | lane
+	uint32_t w_lane;      // band width << 8 | clusters-in-group << 4 (first of a group, else 0) | lane
 	uint32_t scratch;     // offset into the global band scratch (generic kernel only)
 };
 struct Res { uint32_t a, b; };   // a = ed | gap_q << 8 | gap_r << 16 | valid << 31 ; b = final_pos
+
+// Where the work list comes from: explicit runs, or all-vs-all tiles (run r = clump r / ntiles,
+// queries 16 * (r % ntiles) ..).
+struct Work {
+	const bg_run *runs; uint64_t nruns; uint32_t nq, ntiles, first_clump, num_clumps;
+};
+__device__ __forceinline__ bool get_run(const Work &W, uint64_t r, uint32_t &c, uint32_t &q0, uint32_t &n) {
+	if (W.runs) { const bg_run R = W.runs[r]; c = R.clump; q0 = R.query0; n = R.nq; }
+	else { c = (uint32_t)(r / W.ntiles) + W.first_clump; q0 = (uint32_t)(r % W.ntiles) * BG_RUN_MAX; n = min((uint32_t)BG_RUN_MAX, W.nq - q0); }
+	c -= W.first_clump;
+	return c < W.num_clumps;                      // other shards' clumps are skipped
+}
+
+// counters: [0] survivors, [1] scratch words, [2] hits, [3] error flag
+enum { C_SURV = 0, C_SCRATCH = 1, C_HITS = 2, C_ERR = 3 };
 
 // The pass-2 cell (score, shift, shiftR) of burst.c:763-799 as ONE ordered key:
 //   bits 31..22 score   (min wins)
@@ -104,51 +126,222 @@ __global__ void k_relayout(const uint8_t *__restrict__ in, const uint64_t *__res
 	}
 }
 
+// word `wi` (8 columns) of one lane: lanew points at the lane's first piece
+__device__ __forceinline__ uint32_t lane_word(const uint32_t *lanew, uint32_t wi) {
+	return __ldg(lanew + (size_t)(wi >> 2) * 64 + (wi & 3));
+}
+
 // ---------------------------------------------------------------------------------------------
-// Query prep: Peq[q][c] bit (32-P+y-1) = 1 iff row y (1-based) of the query matches reference
-// code c (S == 0).  The pattern is left-aligned so that row P sits in bit 31; the unused low
-// 32-P bits are set for every code: with Pv = Mv = 0 there they behave as extra copies of the
-// all-zero row 0 of the semi-global matrix and never generate a carry.
+// Query prep.
+// k_qinfo: raw (offset, budget, slot) arrays -> QInfo, validation, histogram of pieces needed.
+//   hist[p] (p = 0..4) counts queries needing p+1 pieces (k+1), hist[4] everything above 4.
+// k_qtables: per (query, reference code c)
+//   peq: Myers match vector, bit (32-P+y-1) = 1 iff row y (1-based) matches c (S == 0).  The
+//        pattern is left-aligned so that row P sits in bit 31; the unused low 32-P bits are set for
+//        every code: with Pv = Mv = 0 there they behave as extra copies of the all-zero row 0.
+//   seq: Shift-And table, bit (p*ws + i) = 1 iff base i of piece p matches c; piece p = the LAST w bases
+//        of the p-th of k+1 equal stretches of the query (ending at offset (p+1) * (len / (k+1))): sorted
+//        neighbours of a bunch share their first ~log4(#queries) bases, so a piece taken from the very
+//        start of the query would seed at every bunch-mate's true hit.  All zero when not seed-eligible.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_query_prep(const uint8_t *__restrict__ codes, const QInfo *__restrict__ qi,
-		const uint32_t *__restrict__ Sterm, uint32_t nq, uint32_t *__restrict__ peq) {
+struct SeedLayout { uint32_t np, ws, w, I, F; };   // pieces per word, slot width, piece length, start bits, final bits
+
+__global__ void k_qinfo(const uint64_t *__restrict__ off, const uint16_t *__restrict__ budget, const uint32_t *__restrict__ slot,
+		uint32_t nq, uint32_t nslots, QInfo *__restrict__ qi, uint32_t *__restrict__ hist, uint32_t *__restrict__ counters) {
+	uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q >= nq) return;
+	uint64_t o = off[q], len = off[q + 1] - o;
+	uint32_t k = budget[q], s = slot[q];
+	if (off[q + 1] <= o || len > 0x7FFFFFFFull || k > 254 || s >= nslots) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; s = 0; }
+	QInfo Q; Q.off = o; Q.len = (uint32_t)len; Q.slot = s; Q.k = (uint16_t)k; Q.P = (uint8_t)min((uint64_t)32, len); Q.cls = 0;
+	qi[q] = Q;
+	atomicAdd(&hist[min(k, 4u)], 1u);
+}
+
+__global__ void k_qtables(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, const uint32_t *__restrict__ Sterm,
+		uint32_t nq, SeedLayout SL, uint32_t *__restrict__ peq, uint32_t *__restrict__ seq, uint32_t *__restrict__ nseed) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t q = i >> 4, c = i & 15;
 	if (q >= nq) return;
 	QInfo Q = qi[q];
-	uint32_t P = Q.P, m = P < 32 ? (1u << (32 - P)) - 1 : 0;
 	const uint8_t *s = codes + Q.off;
+	const uint32_t P = Q.P;
+	uint32_t m = P < 32 ? (1u << (32 - P)) - 1 : 0;
 	for (uint32_t y = 0; y < P; ++y)
-		if (Sterm[s[y] * 16 + c] == 0) m |= 1u << (32 - P + y);
+		if (Sterm[(s[y] & 15) * 16 + c] == 0) m |= 1u << (32 - P + y);
 	peq[i] = m;
+	const uint32_t np = Q.k + 1u, plen = Q.len / np;
+	const bool seed = SL.np && np <= SL.np && plen >= SL.w;
+	uint32_t e = 0;
+	if (seed) for (uint32_t p = 0; p < np; ++p)
+		for (uint32_t j = 0; j < SL.w; ++j)
+			if (Sterm[(s[(p + 1) * plen - SL.w + j] & 15) * 16 + c] == 0) e |= 1u << (p * SL.ws + j);
+	seq[i] = e;
+	if (c == 0) { qi[q].cls = seed; if (seed) atomicAdd(nseed, 1u); }
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase A: bit-parallel prefix filter.  128 threads = 8 tasks x 16 lanes.
+// Diagonal clusters: a tiny sorted set of disjoint intervals (rare path, local memory is fine).
+// ---------------------------------------------------------------------------------------------
+#define CLUS_MAX 4
+struct Clus { int lo[CLUS_MAX + 1], hi[CLUS_MAX + 1]; int n; };
+
+__device__ __noinline__ void clus_add(Clus &C, int lo, int hi) {
+	int tl[CLUS_MAX + 1], th[CLUS_MAX + 1], out = 0; bool placed = false;
+	for (int i = 0; i < C.n; ++i) {
+		if (C.hi[i] + 1 < lo) { tl[out] = C.lo[i]; th[out] = C.hi[i]; ++out; }
+		else if (C.lo[i] > hi + 1) {
+			if (!placed) { tl[out] = lo; th[out] = hi; ++out; placed = true; }
+			tl[out] = C.lo[i]; th[out] = C.hi[i]; ++out;
+		} else { lo = min(lo, C.lo[i]); hi = max(hi, C.hi[i]); }       // overlapping or adjacent: absorb
+	}
+	if (!placed) { tl[out] = lo; th[out] = hi; ++out; }
+	if (out > CLUS_MAX) {                                              // too many: fuse the two closest neighbours
+		int bi = 0, bg = INT32_MAX;
+		for (int i = 0; i + 1 < out; ++i) { int g = tl[i + 1] - th[i]; if (g < bg) { bg = g; bi = i; } }
+		th[bi] = th[bi + 1];
+		for (int i = bi + 1; i + 1 < out; ++i) { tl[i] = tl[i + 1]; th[i] = th[i + 1]; }
+		--out;
+	}
+	for (int i = 0; i < out; ++i) { C.lo[i] = tl[i]; C.hi[i] = th[i]; }
+	C.n = out;
+}
+
+__device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_t lane, Surv *surv, uint32_t surv_cap, uint32_t *counters) {
+	if (!C.n) return;
+	const uint32_t base = atomicAdd(&counters[C_SURV], (uint32_t)C.n);
+	for (int s = 0; s < C.n; ++s) {
+		const uint32_t W = (uint32_t)(C.hi[s] - C.lo[s] + 1);
+		uint32_t scratch = 0;
+		if (W > 64) scratch = atomicAdd(&counters[C_SCRATCH], W);
+		if (base + s < surv_cap) {
+			Surv v; v.task = task; v.lo = C.lo[s]; v.w_lane = (W << 8) | ((s == 0 ? (uint32_t)C.n : 0u) << 4) | lane; v.scratch = scratch;
+			surv[base + s] = v;
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A1: pigeonhole seed filter.  128 threads = 4 warps = 4 runs.
+// ---------------------------------------------------------------------------------------------
+struct SeedArgs {
+	const uint32_t *dbw; const uint64_t *clump_off; const uint32_t *clump_len;
+	const QInfo *qi; const uint32_t *seq; Work W; SeedLayout SL;
+	Surv *surv; uint32_t surv_cap; uint32_t *counters;
+};
+
+#define SEED_WARM 2      // words of warm-up before a scan segment: 16 columns >= w - 1
+
+__global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
+	__shared__ uint32_t sEqAll[4][BG_RUN_MAX * 16];
+	const uint32_t warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	const uint64_t r = (uint64_t)blockIdx.x * 4 + warp;
+	if (r >= A.W.nruns) return;
+	uint32_t c, q0, n;
+	if (!get_run(A.W, r, c, q0, n)) return;
+	uint32_t *sEq = sEqAll[warp];
+	#pragma unroll
+	for (int i = 0; i < 8; ++i) {
+		const uint32_t e = t + 32 * i, q = e >> 4;
+		sEq[e] = q < n ? __ldg(A.seq + (size_t)(q0 + q) * 16 + (e & 15)) : 0u;
+	}
+	__syncwarp();
+	const uint32_t L = A.clump_len[c], nwords = (L + 7) >> 3;
+	const uint32_t lane = t & 15, h = t >> 4;
+	const uint32_t *lanew = A.dbw + A.clump_off[c] * 4 + lane * 4;
+	// this thread's share of the lane: words [w0, w1); granule = words per mask bit
+	const uint32_t wh = (nwords + 1) >> 1;
+	const uint32_t w0 = h * wh, w1 = min(nwords, w0 + wh);
+	const uint32_t g = (wh + 31) >> 5;
+	const uint32_t I = A.SL.I, F = A.SL.F;
+	uint32_t D[BG_RUN_MAX];
+	#pragma unroll
+	for (int q = 0; q < BG_RUN_MAX; ++q) D[q] = 0;
+	uint32_t mask = 0;
+	const uint32_t ws0 = w0 >= SEED_WARM ? w0 - SEED_WARM : 0;
+	uint32_t w = ws0 < w1 ? lane_word(lanew, ws0) : 0;
+	for (uint32_t wi = ws0; wi < w1; ++wi) {
+		const uint32_t cur = w;
+		if (wi + 1 < w1) w = lane_word(lanew, wi + 1);
+		uint32_t H = 0;
+		#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			const uint32_t *e = sEq + ((cur >> (4 * j)) & 15u);
+			#pragma unroll
+			for (int q = 0; q < BG_RUN_MAX; ++q) {
+				D[q] = ((D[q] << 1) | I) & e[q * 16];
+				H |= D[q];
+			}
+		}
+		if ((H & F) && wi >= w0) mask |= 1u << ((wi - w0) / g);
+	}
+	// ---- resolve: which query, which diagonals (rare words only) ----
+	const uint32_t evm = __ballot_sync(0xFFFFFFFFu, mask != 0);
+	uint32_t lanes16 = (evm | (evm >> 16)) & 0xFFFFu;
+	if (!lanes16) return;
+	const uint32_t qi_ = t & 15, hh = t >> 4;
+	QInfo Q; Q.len = 0; Q.k = 0; Q.cls = 0;
+	if (qi_ < n) Q = A.qi[q0 + qi_];
+	const uint32_t plen = Q.len / (Q.k + 1u);
+	const uint32_t *myEq = sEq + qi_ * 16;
+	while (lanes16) {
+		const uint32_t l = __ffs(lanes16) - 1; lanes16 &= lanes16 - 1;
+		const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, mask, l), m1 = __shfl_sync(0xFFFFFFFFu, mask, l + 16);
+		uint32_t mm = hh ? m1 : m0;
+		Clus C; C.n = 0;
+		#pragma unroll
+		for (int s = 0; s <= CLUS_MAX; ++s) { C.lo[s] = 0; C.hi[s] = 0; }
+		if (Q.cls && mm) {
+			const uint32_t *lw = A.dbw + A.clump_off[c] * 4 + l * 4;
+			const uint32_t b0 = hh * wh, b1 = min(nwords, b0 + wh);
+			while (mm) {
+				const uint32_t s = __ffs(mm) - 1;
+				uint32_t e = s; while (e + 1 < 32 && (mm >> (e + 1) & 1)) ++e;       // maximal run of flagged granules
+				mm &= e == 31 ? 0u : ~0u << (e + 1);
+				const uint32_t first = b0 + s * g, last = min(b1, b0 + (e + 1) * g);
+				uint32_t d = 0;
+				for (uint32_t wi = first >= SEED_WARM ? first - SEED_WARM : 0; wi < last; ++wi) {
+					const uint32_t cw = lane_word(lw, wi);
+					for (int j = 0; j < 8; ++j) {
+						d = ((d << 1) | I) & myEq[(cw >> (4 * j)) & 15u];
+						uint32_t f = d & F;
+						while (f) {                                   // a piece ends in this column: one seed diagonal
+							const uint32_t bit = __ffs(f) - 1; f &= f - 1;
+							const int x1 = (int)(wi * 8 + j) + 1, y1 = (int)((bit / A.SL.ws + 1) * plen);
+							const int dg = x1 - y1;
+							clus_add(C, dg - (int)Q.k, dg + (int)Q.k);
+						}
+					}
+				}
+			}
+		}
+		// the two halves of a lane belong to one (task, lane): fold the upper half's clusters into the lower's
+		const int pn = __shfl_down_sync(0xFFFFFFFFu, C.n, 16);
+		#pragma unroll
+		for (int s = 0; s < CLUS_MAX; ++s) {
+			const int plo = __shfl_down_sync(0xFFFFFFFFu, C.lo[s], 16), phi = __shfl_down_sync(0xFFFFFFFFu, C.hi[s], 16);
+			if (hh == 0 && s < pn) clus_add(C, plo, phi);
+		}
+		if (hh == 0) emit_clusters(C, (uint32_t)(r * BG_RUN_MAX + qi_), l, A.surv, A.surv_cap, A.counters);
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase A2: Myers bit-parallel prefix filter.  128 threads = 8 tasks x 16 lanes.
 // ---------------------------------------------------------------------------------------------
 struct FilterArgs {
 	const uint4 *db; const uint64_t *clump_off; const uint32_t *clump_len;
-	const QInfo *qi; const uint32_t *peq; const bg_task *tasks;
-	uint64_t ntasks; uint32_t nq, first_clump, num_clumps;
-	Surv *surv; uint32_t surv_cap; uint32_t *counters;   // [0] survivors, [1] scratch words, [2] hits
-	uint32_t two;        // the constant 2, passed at run time so ptxas keeps IMAD.HI / IMAD.WIDE (FMA pipe)
-	uint32_t c16;        // the constant 16, same reason
+	const QInfo *qi; const uint32_t *peq; Work W;
+	Surv *surv; uint32_t surv_cap; uint32_t *counters;
+	uint32_t c16;        // the constant 16, passed at run time so ptxas keeps IMAD.HI (FMA pipe)
 };
-
-__device__ __forceinline__ void task_of(const FilterArgs &A, uint64_t t, uint32_t &q, uint32_t &c) {
-	if (A.tasks) { bg_task T = A.tasks[t]; q = T.query; c = T.clump; }
-	else { q = (uint32_t)(t % A.nq); c = (uint32_t)(t / A.nq) + A.first_clump; }
-}
 
 // Hyyro's formulation of Myers' bit-vector step; the text character is one reference base.
 // Integer-pipe budget per column (ncu: the kernel is bound by the ALU pipe, LOP3/SHF/ISETP issue
 // at half rate): the seven 3-input logic ops below are irreducible, so everything that can run
 // on the FMA pipe instead is written as a multiply-add: the two shifts are x+x, the nibble
-// extraction is a mul.hi, and the row-P score is kept as two mad.hi accumulators (bit 31 of
-// Ph / Mh) that are only compared once per 8 columns.
-__device__ __forceinline__ uint32_t madhi(uint32_t a, uint32_t b, uint32_t c) {
-	uint32_t d; asm("mad.hi.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
-}
+// extraction is a mul.hi.  The row-P value is not tracked per column: it is popc(Pv) - popc(Mv)
+// (sum of the vertical deltas over the pattern rows), read once per 8 columns.
 __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
 	uint32_t d; asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
 }
@@ -158,26 +351,24 @@ __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
 	uint32_t Ph = Mv | ~(Xh | Pv);                              \
 	uint32_t Mh = Pv & Xh;
 
-template <int V>
 __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	__shared__ uint32_t sPeq[8][16];
 	const uint32_t slot = threadIdx.x >> 4, lane = threadIdx.x & 15;
-	const uint64_t t = (uint64_t)blockIdx.x * 8 + slot;
-	bool valid = t < A.ntasks;
-	uint32_t q = 0, c = 0;
-	if (valid) {
-		task_of(A, t, q, c);
-		c -= A.first_clump;
-		valid = c < A.num_clumps;              // other shards' clumps are skipped
-	}
+	const uint64_t t = (uint64_t)blockIdx.x * 8 + slot;           // task id = run * 16 + query-in-run
+	const uint64_t r = t >> 4; const uint32_t qi_ = (uint32_t)t & 15;
+	bool valid = r < A.W.nruns;
+	uint32_t q = 0, c = 0, q0 = 0, n = 0;
+	if (valid) { valid = get_run(A.W, r, c, q0, n) && qi_ < n; q = q0 + qi_; }
+	QInfo Q; Q.cls = 1; Q.P = 0; Q.k = 0;
+	if (valid) { Q = A.qi[q]; valid = !Q.cls; }                   // seed-eligible queries were handled by k_seed
 	sPeq[slot][lane] = valid ? A.peq[(size_t)q * 16 + lane] : 0;
 	__syncwarp();
 	if (!valid) return;
-	const QInfo Q = A.qi[q];
 	const int P = Q.P, k = Q.k;
 	const uint32_t L = A.clump_len[c];
 	const uint4 *base = A.db + A.clump_off[c] + lane;
 	const char *eq = (const char *)sPeq[slot];
+	const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(eq);
 
 	uint32_t Pv = P < 32 ? ~0u << (32 - P) : ~0u, Mv = 0;
 	uint32_t cP = (uint32_t)P, cM = 0;          // row-P value = cP - cM
@@ -194,53 +385,17 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 			const uint32_t w = ws[wi];
 			const uint32_t Pv0 = Pv, Mv0 = Mv;
 			const int s0 = (int)(cP - cM);
-			if (V == 5) {
-				// as V == 4 but the shared address is formed on the ALU pipe (shift, and-or): no IMAD.HI
-				const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(eq);
-				#pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					const uint32_t sh = j == 0 ? w << 2 : w >> (4 * j - 2);
-					uint32_t Eq;
-					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"((sh & 0x3Cu) | eqs));
-					MYERS_STEP(Eq)
-					Ph += Ph; Mh += Mh;
-					Pv = Mh | ~(Xv | Ph);
-					Mv = Ph & Xv;
-				}
-				cP = (uint32_t)__popc(Pv); cM = (uint32_t)__popc(Mv);
-			} else if (V == 4) {
-				// ALU pipe: only the seven logic ops.  FMA pipe: nibble -> shared address (shl, mul.hi, mad),
-				// the add and the two shifts.  The row-P value is not tracked at all: it is
-				// popc(Pv) - popc(Mv) (sum of the vertical deltas over the pattern rows), read once per word.
-				const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(eq);
-				#pragma unroll
-				for (int j = 0; j < 8; ++j) {
-					const uint32_t code = mulhi(j == 7 ? w : w << (28 - 4 * j), A.c16);
-					uint32_t Eq;
-					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"(code * 4u + eqs));
-					MYERS_STEP(Eq)
-					Ph += Ph; Mh += Mh;
-					Pv = Mh | ~(Xv | Ph);
-					Mv = Ph & Xv;
-				}
-				cP = (uint32_t)__popc(Pv); cM = (uint32_t)__popc(Mv);
-			} else
 			#pragma unroll
 			for (int j = 0; j < 8; ++j) {
-				const uint32_t off = (j == 0 ? w * 4u : mulhi(w, 1u << (34 - 4 * j))) & 0x3Cu;   // code * 4
-				const uint32_t Eq = *(const uint32_t *)(eq + off);
+				const uint32_t code = mulhi(j == 7 ? w : w << (28 - 4 * j), A.c16);
+				uint32_t Eq;
+				asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"(code * 4u + eqs));
 				MYERS_STEP(Eq)
-				if (V == 1) { cP = madhi(Ph, 2u, cP); cM = madhi(Mh, 2u, cM); Ph += Ph; Mh += Mh; }      // ptxas: LEA.HI (ALU)
-				else if (V == 2) { cP = madhi(Ph, A.two, cP); cM = madhi(Mh, A.two, cM); Ph += Ph; Mh += Mh; }  // IMAD.HI (FMA)
-				else {                                               // IMAD.WIDE: shift and bit 31 in one
-					uint64_t p2, m2;
-					asm("mul.wide.u32 %0, %1, %2;" : "=l"(p2) : "r"(Ph), "r"(A.two));
-					asm("mul.wide.u32 %0, %1, %2;" : "=l"(m2) : "r"(Mh), "r"(A.two));
-					Ph = (uint32_t)p2; Mh = (uint32_t)m2; cP += (uint32_t)(p2 >> 32); cM += (uint32_t)(m2 >> 32);
-				}
+				Ph += Ph; Mh += Mh;
 				Pv = Mh | ~(Xv | Ph);                                // row 0 is all zero: no carry-in
 				Mv = Ph & Xv;
 			}
+			cP = (uint32_t)__popc(Pv); cM = (uint32_t)__popc(Mv);
 			// The row-P value moves by at most 1 per column, so inside these 8 columns it cannot
 			// drop below (s0 + s1 - 8) / 2.  Only then is a seed (value <= k) possible: redo the
 			// word column by column from the saved state.
@@ -269,10 +424,10 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	if (lo <= hi) {
 		const uint32_t W = (uint32_t)(hi - lo + 1);
 		uint32_t scratch = 0;
-		if (W > 64) scratch = atomicAdd(&A.counters[1], W);
-		const uint32_t i = atomicAdd(&A.counters[0], 1u);
+		if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+		const uint32_t i = atomicAdd(&A.counters[C_SURV], 1u);
 		if (i < A.surv_cap) {
-			Surv s; s.task = (uint32_t)t; s.lo = lo; s.w_lane = (W << 8) | lane; s.scratch = scratch;
+			Surv s; s.task = (uint32_t)t; s.lo = lo; s.w_lane = (W << 8) | (1u << 4) | lane; s.scratch = scratch;
 			A.surv[i] = s;
 		}
 	}
@@ -283,8 +438,7 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 // ---------------------------------------------------------------------------------------------
 struct ExtendArgs {
 	const uint32_t *dbw; const uint64_t *clump_off; const uint32_t *clump_len;
-	const uint8_t *codes; const QInfo *qi; const bg_task *tasks;
-	uint32_t nq, first_clump;
+	const uint8_t *codes; const QInfo *qi; Work W;
 	const Surv *surv; uint32_t surv_cap; const uint32_t *counters;
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
 	uint32_t *scratch; uint32_t scratch_cap;
@@ -310,18 +464,16 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	__shared__ uint32_t sS[256];
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) sS[i] = A.Sterm[i];
 	__syncthreads();
-	const uint32_t nsurv = min(A.counters[0], A.surv_cap);
+	const uint32_t nsurv = min(A.counters[C_SURV], A.surv_cap);
 	unsigned long long cells = 0;
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsurv; i += gridDim.x * blockDim.x) {
 		const Surv sv = A.surv[i];
-		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 255;
+		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 15;
 		// class dispatch: this instantiation takes bands that fit WMAX but not WMAX/2
 		if (WMAX == 0 ? (W <= 64) : (W > (uint32_t)WMAX || (WMAX > 8 && W <= (uint32_t)WMAX / 2))) continue;
-		uint32_t q, c;
-		if (A.tasks) { bg_task T = A.tasks[sv.task]; q = T.query; c = T.clump; }
-		else { q = sv.task % A.nq; c = sv.task / A.nq + A.first_clump; }
-		c -= A.first_clump;
-		const QInfo Q = A.qi[q];
+		uint32_t c, q0, n;
+		get_run(A.W, sv.task >> 4, c, q0, n);
+		const QInfo Q = A.qi[q0 + (sv.task & 15)];
 		const uint32_t m = Q.len, L = A.clump_len[c];
 		const uint8_t *qs = A.codes + Q.off;
 		const uint32_t *lanew = A.dbw + A.clump_off[c] * 4 + lane * 4;
@@ -352,7 +504,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		uint32_t y = 1;
 		for (; y <= m; ++y) {
 			const int x0 = (int)y + lo;                      // column (1-based) of band cell 0 in row y
-			const uint32_t *Srow = sS + qs[y - 1] * 16;
+			const uint32_t *Srow = sS + (qs[y - 1] & 15) * 16;
 			uint32_t rowmin = KEY_NONE, left = inf;
 			if (WMAX) {
 				// slide the code window by one column
@@ -426,29 +578,78 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase C: keep what the reference keeps.
+// Phase C: keep what the reference keeps.  The clusters of one (task, lane) cover disjoint diagonal
+// ranges, hence disjoint stretches of the last row, in ascending column order: the reference's
+// left-to-right scan (burst.c:826-883) keeps the best (score, shift), numGapR of its first
+// occurrence and the column of its last.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_select(const Surv *__restrict__ surv, const Res *__restrict__ res, const bg_task *__restrict__ tasks,
-		const QInfo *__restrict__ qi, uint32_t nq, const uint32_t *__restrict__ best, uint32_t *counters,
-		uint32_t surv_cap, bg_hit *__restrict__ hits, int mode) {
-	const uint32_t nsurv = min(counters[0], surv_cap);
+__global__ void k_select(const Surv *__restrict__ surv, const Res *__restrict__ res, const QInfo *__restrict__ qi, Work W,
+		const uint32_t *__restrict__ best, uint32_t *counters, uint32_t surv_cap, bg_hit *__restrict__ hits,
+		unsigned long long *__restrict__ keys, int mode) {
+	const uint32_t nsurv = min(counters[C_SURV], surv_cap);
 	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsurv; i += gridDim.x * blockDim.x) {
-		const Res r = res[i];
-		if (!(r.a >> 31)) continue;
 		const Surv sv = surv[i];
-		const uint32_t q = tasks ? tasks[sv.task].query : sv.task % nq;
-		const uint32_t ed = r.a & 255;
-		if (mode == BG_MODE_MIN && ed != best[qi[q].slot]) continue;     // burst.c:4229, 4497
-		const uint32_t j = atomicAdd(&counters[2], 1u);
-		bg_hit h; h.task = sv.task; h.lane = (uint8_t)(sv.w_lane & 255); h.ed = (uint8_t)ed;
-		h.gap_q = (uint8_t)(r.a >> 8); h.gap_r = (uint8_t)(r.a >> 16); h.final_pos = r.b;
+		const uint32_t grp = (sv.w_lane >> 4) & 15;
+		if (!grp) continue;
+		uint32_t bkey = 0xFFFFFFFFu, gr = 0, fp = 0;
+		for (uint32_t s = 0; s < grp && i + s < nsurv; ++s) {
+			const Res r = res[i + s];
+			if (!(r.a >> 31)) continue;
+			const uint32_t key = ((r.a & 255) << 8) | (255 - ((r.a >> 8) & 255));
+			if (key < bkey) { bkey = key; gr = (r.a >> 16) & 255; fp = r.b; }
+			else if (key == bkey) fp = r.b;
+		}
+		if (bkey == 0xFFFFFFFFu) continue;
+		const uint32_t ed = bkey >> 8;
+		uint32_t c, q0, n;
+		get_run(W, sv.task >> 4, c, q0, n);
+		if (mode == BG_MODE_MIN && ed != best[qi[q0 + (sv.task & 15)].slot]) continue;     // burst.c:4229, 4497
+		const uint32_t j = atomicAdd(&counters[C_HITS], 1u);
+		bg_hit h; h.task = sv.task; h.lane = (uint8_t)(sv.w_lane & 15); h.ed = (uint8_t)ed;
+		h.gap_q = (uint8_t)(255 - (bkey & 255)); h.gap_r = (uint8_t)gr; h.final_pos = fp;
 		hits[j] = h;
+		keys[j] = ((unsigned long long)sv.task << 4) | (sv.w_lane & 15);
 	}
 }
+
+__global__ void k_gather_hits(const bg_hit *__restrict__ in, const uint32_t *__restrict__ order, uint32_t n, bg_hit *__restrict__ out) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = in[order[i]];
+}
+__global__ void k_iota(uint32_t *v, uint32_t n) { uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; if (i < n) v[i] = i; }
 
 __global__ void k_init_best(uint32_t *best, const uint16_t *in, uint32_t n) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) best[i] = in ? in[i] : 0xFFFFu;
+}
+
+// run validation (explicit run lists): malformed runs raise the error flag
+__global__ void k_check_runs(const bg_run *__restrict__ runs, uint64_t nruns, uint32_t nq, uint32_t *counters) {
+	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nruns) return;
+	const bg_run R = runs[r];
+	if (!R.nq || R.nq > BG_RUN_MAX || (uint64_t)R.query0 + R.nq > nq) atomicExch(&counters[C_ERR], 0x80000000u | (uint32_t)min(r, (uint64_t)0x7FFFFFFF));
+}
+
+// work statistics: nominal = sum over tasks of 16 * qlen * ClumpLen
+__global__ void k_work_stats(Work W, const QInfo *__restrict__ qi, const uint32_t *__restrict__ clump_len, unsigned long long *out) {
+	unsigned long long tasks = 0, nominal = 0, fcells = 0, scells = 0;
+	for (uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; r < W.nruns; r += (uint64_t)gridDim.x * blockDim.x) {
+		uint32_t c, q0, n;
+		if (!get_run(W, r, c, q0, n)) continue;
+		const unsigned long long L = clump_len[c];
+		for (uint32_t i = 0; i < n; ++i) {
+			const QInfo Q = qi[q0 + i];
+			nominal += 16ull * Q.len * L;
+			if (Q.cls) scells += 16ull * L; else fcells += 16ull * Q.P * L;
+		}
+		tasks += n;
+	}
+	for (int o = 16; o; o >>= 1) {
+		tasks += __shfl_down_sync(0xFFFFFFFFu, tasks, o); nominal += __shfl_down_sync(0xFFFFFFFFu, nominal, o);
+		fcells += __shfl_down_sync(0xFFFFFFFFu, fcells, o); scells += __shfl_down_sync(0xFFFFFFFFu, scells, o);
+	}
+	if ((threadIdx.x & 31) == 0) { atomicAdd(out, tasks); atomicAdd(out + 1, nominal); atomicAdd(out + 2, fcells); atomicAdd(out + 3, scells); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -468,32 +669,44 @@ template <typename T> struct DBuf {
 	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
+
 struct bg_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
+	int seed_filter = 1;
 	// scoring
 	uint8_t S[256];
 	DBuf<uint32_t> d_sterm;
 	// DB
 	DBuf<uint4> d_db; DBuf<uint64_t> d_clump_off; DBuf<uint32_t> d_clump_len;
-	std::vector<uint32_t> clump_len;
 	uint32_t num_clumps = 0, first_clump = 0;
 	// batch
-	DBuf<uint8_t> d_codes; DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq; DBuf<bg_task> d_tasks;
+	DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
+	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_seq; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
-	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits; DBuf<uint32_t> d_scratch;
-	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;
-	std::vector<QInfo> h_qi;
-	uint32_t nq = 0, nslots = 0; uint64_t ntasks = 0; bool have_tasks = false;
+	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
+	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
+	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;   // cells: [0] band, [1..4] work stats
+	uint32_t *h_pinned = nullptr;                                 // 16 x u32 pinned scratch for small readbacks
+	int kind = WORK_NONE;
+	uint32_t nq = 0, nslots = 0, ntiles = 0; uint64_t nruns = 0, ntasks = 0;
+	std::vector<uint32_t> task0;                                  // WORK_TASKS: first task index of each run
+	SeedLayout SL = {0, 0, 0, 0, 0}; uint32_t nseed = 0;          // queries taken by k_seed
 	uint32_t surv_cap = 0;
 	int last_mode = 0; std::vector<uint16_t> last_best_in; bool have_best_in = false;
 	bg_stats stats;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 	uint32_t h_counters[4] = {0, 0, 0, 0};
-	bool ran = false;
-	bool by_runs = false; std::vector<uint32_t> run_key;      // run-list batches: task index -> run * BG_RUN_MAX + i
+	bool ran = false, sorted = false;
 };
+
+static Work work_of(const bg_ctx *c) {
+	Work W; W.runs = c->kind == WORK_ALL ? nullptr : c->d_runs.p; W.nruns = c->nruns; W.nq = c->nq; W.ntiles = c->ntiles;
+	W.first_clump = c->first_clump; W.num_clumps = c->num_clumps;
+	return W;
+}
 
 extern "C" void bg_default_scoring(int z, uint8_t S[256]) {
 	// IUPAC code -> base set (A=1, C=2, G=4, T=8) in the reference's alphabet order
@@ -521,12 +734,11 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	c->sms = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
 	for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
+	CU(cudaMallocHost((void **)&c->h_pinned, 64));
 	memset(&c->stats, 0, sizeof(c->stats));
 	bg_default_scoring(1, c->S);
 	*out = c;
-	int rc = bg_set_scoring(c, c->S);
-	if (rc) { return rc; }
-	return BG_OK;
+	return bg_set_scoring(c, c->S);
 }
 
 extern "C" void bg_free(bg_ctx *c) {
@@ -534,10 +746,13 @@ extern "C" void bg_free(bg_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release();
-	c->d_codes.release(); c->d_qi.release(); c->d_peq.release(); c->d_tasks.release();
+	c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
+	c->d_qi.release(); c->d_peq.release(); c->d_seq.release(); c->d_runs.release();
 	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release();
-	c->d_hits.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
+	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
+	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->h_pinned) cudaFreeHost(c->h_pinned);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 }
@@ -547,6 +762,12 @@ extern "C" int bg_set_stream(bg_ctx *c, void *s) {
 	if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
 	c->stream = (cudaStream_t)s; c->own_stream = false;
 	return BG_OK;
+}
+
+extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
+	if (!c) return fail(BG_EINVAL, "null ctx");
+	if (what == BG_PARAM_SEED_FILTER) { c->seed_filter = value != 0; return BG_OK; }
+	return fail(BG_EINVAL, "bg_set_param: unknown parameter %d", what);
 }
 
 extern "C" int bg_set_scoring(bg_ctx *c, const uint8_t S[256]) {
@@ -571,8 +792,8 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 		in_off[i + 1] = in_off[i] + (uint64_t)((clump_len[i] + 1) / 2) * 16;
 		out_off[i + 1] = out_off[i] + (uint64_t)((clump_len[i] + 31) / 32) * 16;
 	}
-	c->clump_len.assign(clump_len, clump_len + num_clumps);
 	c->num_clumps = num_clumps; c->first_clump = first_clump;
+	c->kind = WORK_NONE;
 	if (c->d_db.need(out_off[num_clumps])) return BG_ENOMEM;
 	if (c->d_clump_off.need(num_clumps + 1) || c->d_clump_len.need(num_clumps)) return BG_ENOMEM;
 	DBuf<uint64_t> d_in_off;
@@ -602,97 +823,148 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 	return BG_OK;
 }
 
-extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *tasks, uint64_t ntasks) {
-	if (!c || !Q) return fail(BG_EINVAL, "bg_batch_upload: null argument");
+// Smallest piece count (<= 4) that covers ~all queries of the batch; 0 = seed filter off.
+static SeedLayout choose_layout(const uint32_t hist[5], uint32_t nq, int enabled) {
+	SeedLayout L = {0, 0, 0, 0, 0};
+	if (!enabled) return L;
+	uint64_t acc = 0; uint32_t np = 0;
+	for (uint32_t p = 0; p < 4; ++p) { acc += hist[p]; if (acc * 20 >= (uint64_t)nq * 19) { np = p + 1; break; } }
+	if (!np) {                                      // most queries need more than 4 pieces: take the ones that fit 4 if they are a fair share
+		if (acc * 4 >= nq) np = 4; else return L;
+	}
+	L.np = np; L.ws = 32 / np; L.w = std::min<uint32_t>(L.ws, 16);
+	for (uint32_t p = 0; p < np; ++p) { L.I |= 1u << (p * L.ws); L.F |= 1u << (p * L.ws + L.w - 1); }
+	return L;
+}
+
+// queries -> device, QInfo + tables
+static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	if (!c->num_clumps) return fail(BG_EINVAL, "bg_batch_upload: no database loaded");
 	if (!Q->nq) return fail(BG_EINVAL, "bg_batch_upload: empty query batch");
-	CU(cudaSetDevice(c->device));
-	c->h_qi.resize(Q->nq);
-	for (uint32_t i = 0; i < Q->nq; ++i) {
-		uint64_t len = Q->offset[i + 1] - Q->offset[i];
-		if (!len || len > 0x7FFFFFFF) return fail(BG_EINVAL, "bg_batch_upload: query %u has length %llu", i, (unsigned long long)len);
-		if (Q->budget[i] > 254) return fail(BG_EINVAL, "bg_batch_upload: budget %u of query %u exceeds 254 (burst.c:3076)", Q->budget[i], i);
-		if (Q->slot[i] >= Q->nslots) return fail(BG_EINVAL, "bg_batch_upload: slot %u of query %u out of range", Q->slot[i], i);
-		QInfo &q = c->h_qi[i];
-		q.off = Q->offset[i]; q.len = (uint32_t)len; q.slot = Q->slot[i]; q.k = Q->budget[i];
-		q.P = (uint16_t)std::min<uint64_t>(32, len);
-	}
-	uint64_t ncodes = Q->offset[Q->nq];
-	if (!tasks) {
-		ntasks = (uint64_t)Q->nq * c->num_clumps;
-	} else {
-		for (uint64_t t = 0; t < ntasks; ++t)
-			if (tasks[t].query >= Q->nq) return fail(BG_EINVAL, "bg_batch_upload: task %llu names query %u of %u", (unsigned long long)t, tasks[t].query, Q->nq);
-	}
-	if (ntasks >= (1ull << 32)) return fail(BG_EINVAL, "bg_batch_upload: %llu tasks in one batch (limit 2^32-1); split the query batch", (unsigned long long)ntasks);
-	if (c->d_codes.need(ncodes + 16) || c->d_qi.need(Q->nq) || c->d_peq.need((size_t)Q->nq * 16) ||
-	    c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) || c->d_counters.need(4) || c->d_cells.need(1)) return BG_ENOMEM;
-	if (tasks && c->d_tasks.need(ntasks)) return BG_ENOMEM;
+	if (!Q->codes || !Q->offset || !Q->budget || !Q->slot) return fail(BG_EINVAL, "bg_batch_upload: null query array");
+	const uint32_t nq = Q->nq;
+	const uint64_t ncodes = Q->offset[nq];
+	if (c->d_codes.need(ncodes + 16) || c->d_qoff.need(nq + 1) || c->d_budget.need(nq) || c->d_slot.need(nq) || c->d_qi.need(nq) ||
+	    c->d_peq.need((size_t)nq * 16) || c->d_seq.need((size_t)nq * 16) || c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) ||
+	    c->d_counters.need(16) || c->d_cells.need(8)) return BG_ENOMEM;
 	CU(cudaMemcpyAsync(c->d_codes.p, Q->codes, ncodes, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemcpyAsync(c->d_qi.p, c->h_qi.data(), Q->nq * sizeof(QInfo), cudaMemcpyHostToDevice, c->stream));
-	if (tasks) CU(cudaMemcpyAsync(c->d_tasks.p, tasks, ntasks * sizeof(bg_task), cudaMemcpyHostToDevice, c->stream));
-	c->nq = Q->nq; c->nslots = Q->nslots; c->ntasks = ntasks; c->have_tasks = tasks != nullptr;
-	// nominal cell count: 16 * qlen * ClumpLen per task
-	uint64_t nominal = 0, fcells = 0;
-	if (tasks) {
-		for (uint64_t t = 0; t < ntasks; ++t) {
-			uint32_t cl = tasks[t].clump - c->first_clump;
-			if (cl >= c->num_clumps) continue;
-			nominal += 16ull * c->h_qi[tasks[t].query].len * c->clump_len[cl];
-			fcells += 16ull * c->h_qi[tasks[t].query].P * c->clump_len[cl];
-		}
-	} else {
-		uint64_t sl = 0, sq = 0, sp = 0;
-		for (uint32_t i = 0; i < c->num_clumps; ++i) sl += c->clump_len[i];
-		for (uint32_t i = 0; i < Q->nq; ++i) { sq += c->h_qi[i].len; sp += c->h_qi[i].P; }
-		nominal = 16ull * sl * sq; fcells = 16ull * sl * sp;
+	CU(cudaMemcpyAsync(c->d_qoff.p, Q->offset, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_budget.p, Q->budget, (size_t)nq * 2, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemcpyAsync(c->d_slot.p, Q->slot, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));           // [0..3] counters, [4..8] piece histogram, [9] seed queries
+	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 4, c->d_counters.p);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	if (c->h_pinned[C_ERR]) {
+		uint32_t q = c->h_pinned[C_ERR] - 1;
+		return fail(BG_EINVAL, "bg_batch_upload: query %u is malformed (length %llu, budget %u (max 254, burst.c:3076), slot %u of %u)", q,
+			(unsigned long long)(Q->offset[q + 1] - Q->offset[q]), Q->budget[q], Q->slot[q], Q->nslots);
 	}
+	c->SL = choose_layout(c->h_pinned + 4, nq, c->seed_filter);
+	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->SL, c->d_peq.p, c->d_seq.p, c->d_counters.p + 9);
+	CU(cudaGetLastError());
+	c->nq = nq; c->nslots = Q->nslots;
+	return BG_OK;
+}
+
+static int finish_upload(bg_ctx *c) {
+	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));     // the caller's host buffers may be reused after this returns
+	if (c->h_pinned[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_batch_upload_runs: run %u is malformed (nq must be 1..%d and query0+nq within the batch)", c->h_pinned[C_ERR] & 0x7FFFFFFF, BG_RUN_MAX); }
+	c->nseed = c->h_pinned[9];
 	memset(&c->stats, 0, sizeof(c->stats));
-	c->stats.tasks = ntasks; c->stats.nominal_cells = nominal; c->stats.filter_cells = fcells;
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
-	uint64_t want = std::min<uint64_t>(ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * Q->nq + ntasks / 8));
+	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
 	want = std::max<uint64_t>(want, 1024);
 	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
-	if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap)) return BG_ENOMEM;
+	if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 	if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
-	k_query_prep<<<(Q->nq * 16 + 255) / 256, 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, Q->nq, c->d_peq.p);
-	CU(cudaGetLastError());
-	CU(cudaStreamSynchronize(c->stream));     // the caller's host buffers may be reused after this returns
-	c->ran = false; c->by_runs = false;
+	c->ran = false; c->sorted = false;
 	return BG_OK;
+}
+
+extern "C" int bg_batch_upload_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns) {
+	if (!c || !Q || !runs) return fail(BG_EINVAL, "bg_batch_upload_runs: null argument");
+	if (nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_batch_upload_runs: %llu runs in one batch (limit 2^28-1); split the query batch", (unsigned long long)nruns);
+	CU(cudaSetDevice(c->device));
+	c->kind = WORK_NONE;
+	int rc = upload_queries(c, Q); if (rc) return rc;
+	if (c->d_runs.need(nruns + 1)) return BG_ENOMEM;
+	CU(cudaMemcpyAsync(c->d_runs.p, runs, nruns * sizeof(bg_run), cudaMemcpyHostToDevice, c->stream));
+	if (nruns) k_check_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, c->stream>>>(c->d_runs.p, nruns, c->nq, c->d_counters.p);
+	CU(cudaGetLastError());
+	c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = nruns * BG_RUN_MAX; c->ntiles = 0;
+	return finish_upload(c);
+}
+
+extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *tasks, uint64_t ntasks) {
+	if (!c || !Q) return fail(BG_EINVAL, "bg_batch_upload: null argument");
+	CU(cudaSetDevice(c->device));
+	c->kind = WORK_NONE;
+	if (!tasks) {                                                 // all-vs-all, reference order clump-major (burst.c:4344, 4365)
+		int rc = upload_queries(c, Q); if (rc) return rc;
+		c->ntiles = (Q->nq + BG_RUN_MAX - 1) / BG_RUN_MAX;
+		c->nruns = (uint64_t)c->ntiles * c->num_clumps;
+		c->ntasks = (uint64_t)Q->nq * c->num_clumps;
+		if (c->ntasks >= (1ull << 32) || c->nruns >= (1ull << 28))
+			return fail(BG_EINVAL, "bg_batch_upload: %llu tasks in one all-vs-all batch (limits 2^32-1 tasks, 2^28-1 clump x 16-query tiles); split the query batch", (unsigned long long)c->ntasks);
+		c->kind = WORK_ALL;
+		return finish_upload(c);
+	}
+	if (ntasks >= (1ull << 32)) return fail(BG_EINVAL, "bg_batch_upload: %llu tasks in one batch (limit 2^32-1); split the query batch", (unsigned long long)ntasks);
+	// coalesce the task list into runs: consecutive tasks on one clump with consecutive query ids
+	std::vector<bg_run> runs; runs.reserve(ntasks / 8 + 16);
+	c->task0.clear(); c->task0.reserve(ntasks / 8 + 16);
+	for (uint64_t t = 0; t < ntasks; ++t) {
+		if (tasks[t].query >= Q->nq) return fail(BG_EINVAL, "bg_batch_upload: task %llu names query %u of %u", (unsigned long long)t, tasks[t].query, Q->nq);
+		if (!runs.empty()) {
+			bg_run &R = runs.back();
+			if (R.clump == tasks[t].clump && R.nq < BG_RUN_MAX && tasks[t].query == R.query0 + R.nq) { ++R.nq; continue; }
+		}
+		runs.push_back(bg_run{tasks[t].clump, tasks[t].query, 1}); c->task0.push_back((uint32_t)t);
+	}
+	if (runs.size() >= (1ull << 28)) return fail(BG_EINVAL, "bg_batch_upload: task list needs %zu runs (limit 2^28-1)", runs.size());
+	int rc = upload_queries(c, Q); if (rc) return rc;
+	if (c->d_runs.need(runs.size() + 1)) return BG_ENOMEM;
+	CU(cudaMemcpyAsync(c->d_runs.p, runs.data(), runs.size() * sizeof(bg_run), cudaMemcpyHostToDevice, c->stream));
+	c->kind = WORK_TASKS; c->nruns = runs.size(); c->ntasks = ntasks; c->ntiles = 0;
+	return finish_upload(c);                                      // synchronises: `runs` may go out of scope
 }
 
 static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	CU(cudaSetDevice(c->device));
 	c->last_mode = mode; c->have_best_in = best_in != nullptr;
 	if (best_in) {
-		c->last_best_in.assign(best_in, best_in + c->nslots);
-		CU(cudaMemcpyAsync(c->d_best16.p, best_in, c->nslots * 2, cudaMemcpyHostToDevice, c->stream));
+		if (best_in != c->last_best_in.data()) c->last_best_in.assign(best_in, best_in + c->nslots);
+		CU(cudaMemcpyAsync(c->d_best16.p, c->last_best_in.data(), c->nslots * 2, cudaMemcpyHostToDevice, c->stream));
 	}
 	k_init_best<<<(c->nslots + 255) / 256, 256, 0, c->stream>>>(c->d_best.p, best_in ? c->d_best16.p : nullptr, c->nslots);
 	CU(cudaMemsetAsync(c->d_counters.p, 0, 16, c->stream));
 	CU(cudaMemsetAsync(c->d_cells.p, 0, 8, c->stream));
 	CU(cudaEventRecord(c->ev[0], c->stream));
-	FilterArgs F;
-	F.db = c->d_db.p; F.clump_off = c->d_clump_off.p; F.clump_len = c->d_clump_len.p; F.qi = c->d_qi.p;
-	F.peq = c->d_peq.p; F.tasks = c->have_tasks ? c->d_tasks.p : nullptr; F.ntasks = c->ntasks; F.nq = c->nq;
-	F.first_clump = c->first_clump; F.num_clumps = c->num_clumps; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap;
-	F.counters = c->d_counters.p; F.two = 2; F.c16 = 16;
-	uint64_t blocks = (c->ntasks + 7) / 8;
-	if (blocks > 0x7FFFFFFFull) return fail(BG_EINVAL, "too many tasks for one launch");
-	if (blocks) {
-		static int variant = getenv("BURST_FILTER_VARIANT") ? atoi(getenv("BURST_FILTER_VARIANT")) : 4;
-		if (variant == 1) k_filter<1><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
-		else if (variant == 4) k_filter<4><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
-		else if (variant == 5) k_filter<5><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
-		else if (variant == 3) k_filter<3><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
-		else k_filter<2><<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+	const Work W = work_of(c);
+	if (c->nruns && c->nseed) {
+		SeedArgs S;
+		S.dbw = (const uint32_t *)c->d_db.p; S.clump_off = c->d_clump_off.p; S.clump_len = c->d_clump_len.p; S.qi = c->d_qi.p;
+		S.seq = c->d_seq.p; S.W = W; S.SL = c->SL; S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
+		const uint64_t blocks = (c->nruns + 3) / 4;
+		k_seed<<<(unsigned)blocks, 128, 0, c->stream>>>(S);
+		CU(cudaGetLastError());
 	}
-	CU(cudaGetLastError());
+	if (c->nruns && c->nseed < c->nq) {
+		FilterArgs F;
+		F.db = c->d_db.p; F.clump_off = c->d_clump_off.p; F.clump_len = c->d_clump_len.p; F.qi = c->d_qi.p;
+		F.peq = c->d_peq.p; F.W = W; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap; F.counters = c->d_counters.p; F.c16 = 16;
+		const uint64_t blocks = c->nruns * 2;                     // 8 task ids per block
+		if (blocks > 0x7FFFFFFFull) return fail(BG_EINVAL, "too many tasks for one launch");
+		k_filter<<<(unsigned)blocks, 128, 0, c->stream>>>(F);
+		CU(cudaGetLastError());
+	}
 	CU(cudaEventRecord(c->ev[1], c->stream));
 	ExtendArgs E;
 	E.dbw = (const uint32_t *)c->d_db.p; E.clump_off = c->d_clump_off.p; E.clump_len = c->d_clump_len.p;
-	E.codes = c->d_codes.p; E.qi = c->d_qi.p; E.tasks = F.tasks; E.nq = c->nq; E.first_clump = c->first_clump;
+	E.codes = c->d_codes.p; E.qi = c->d_qi.p; E.W = W;
 	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.res = c->d_res.p;
 	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
 	E.band_cells = c->d_cells.p; E.mode = mode;
@@ -709,25 +981,25 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 
 static int run_select(bg_ctx *c, int mode) {
 	CU(cudaSetDevice(c->device));
-	k_select<<<(unsigned)c->sms * 4, 256, 0, c->stream>>>(c->d_surv.p, c->d_res.p, c->have_tasks ? c->d_tasks.p : nullptr,
-		c->d_qi.p, c->nq, c->d_best.p, c->d_counters.p, c->surv_cap, c->d_hits.p, mode);
+	k_select<<<(unsigned)c->sms * 4, 256, 0, c->stream>>>(c->d_surv.p, c->d_res.p, c->d_qi.p, work_of(c), c->d_best.p, c->d_counters.p,
+		c->surv_cap, c->d_hits.p, c->d_keys.p, mode);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[3], c->stream));
-	c->ran = true;
+	c->ran = true; c->sorted = false;
 	return BG_OK;
 }
 
 extern "C" int bg_batch_run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
-	if (!c || !c->nq) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
+	if (!c || c->kind == WORK_NONE) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
 	return run_extend(c, mode, best_in);
 }
 extern "C" void *bg_batch_best_device(bg_ctx *c) { return c ? (void *)c->d_best.p : nullptr; }
 extern "C" int bg_batch_run_select(bg_ctx *c, int mode) {
-	if (!c || !c->nq) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
+	if (!c || c->kind == WORK_NONE) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
 	return run_select(c, mode);
 }
 extern "C" int bg_batch_run(bg_ctx *c, int mode, const uint16_t *best_in) {
-	if (!c || !c->nq) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
+	if (!c || c->kind == WORK_NONE) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
 	int rc = run_extend(c, mode, best_in);
 	if (rc) return rc;
 	return run_select(c, mode);
@@ -737,28 +1009,44 @@ extern "C" int bg_batch_run(bg_ctx *c, int mode, const uint16_t *best_in) {
 static int settle(bg_ctx *c) {
 	if (!c->ran) return fail(BG_EINVAL, "no batch has been run");
 	for (int attempt = 0; attempt < 4; ++attempt) {
-		CU(cudaMemcpyAsync(c->h_counters, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		bool grow_s = c->h_counters[0] > c->surv_cap, grow_g = c->h_counters[1] > c->d_scratch.cap;
+		memcpy(c->h_counters, c->h_pinned, 16);
+		bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->d_scratch.cap;
 		if (!grow_s && !grow_g) return BG_OK;
 		if (grow_s) {
-			c->surv_cap = c->h_counters[0] + c->h_counters[0] / 4;
-			if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap)) return BG_ENOMEM;
+			c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
+			if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		}
-		if (grow_g && c->d_scratch.need((size_t)c->h_counters[1] + 1024)) return BG_ENOMEM;
+		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
 		int rc = run_extend(c, c->last_mode, c->have_best_in ? c->last_best_in.data() : nullptr);
 		if (rc) return rc;
 		rc = run_select(c, c->last_mode);
 		if (rc) return rc;
 	}
-	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[0]);
+	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
 }
 
 extern "C" int bg_batch_count(bg_ctx *c, uint64_t *nhits) {
 	if (!c) return fail(BG_EINVAL, "null ctx");
 	CU(cudaSetDevice(c->device));
 	int rc = settle(c); if (rc) return rc;
-	if (nhits) *nhits = c->h_counters[2];
+	if (nhits) *nhits = c->h_counters[C_HITS];
+	return BG_OK;
+}
+
+// hits ordered by (task, lane) on the device: radix sort of 32+4-bit keys, then a gather
+static int sort_hits(bg_ctx *c, uint32_t n) {
+	if (c->sorted || !n) { c->sorted = true; return BG_OK; }
+	if (c->d_keys2.need(n) || c->d_order.need(n) || c->d_order2.need(n) || c->d_hits_sorted.need(n)) return BG_ENOMEM;
+	size_t tmp = 0;
+	CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, 36, c->stream));
+	if (c->d_sort_tmp.need(tmp + 16)) return BG_ENOMEM;
+	k_iota<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_order.p, n);
+	CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, 36, c->stream));
+	k_gather_hits<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_hits.p, c->d_order2.p, n, c->d_hits_sorted.p);
+	CU(cudaGetLastError());
+	c->sorted = true;
 	return BG_OK;
 }
 
@@ -766,10 +1054,11 @@ extern "C" int bg_batch_download(bg_ctx *c, bg_hit *hits, uint64_t cap, uint16_t
 	if (!c) return fail(BG_EINVAL, "null ctx");
 	CU(cudaSetDevice(c->device));
 	int rc = settle(c); if (rc) return rc;
-	uint64_t n = c->h_counters[2];
+	uint64_t n = c->h_counters[C_HITS];
 	if (hits) {
 		if (cap < n) return fail(BG_EINVAL, "bg_batch_download: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
-		CU(cudaMemcpyAsync(hits, c->d_hits.p, n * sizeof(bg_hit), cudaMemcpyDeviceToHost, c->stream));
+		rc = sort_hits(c, (uint32_t)n); if (rc) return rc;
+		if (n) CU(cudaMemcpyAsync(hits, c->d_hits_sorted.p, n * sizeof(bg_hit), cudaMemcpyDeviceToHost, c->stream));
 	}
 	std::vector<uint32_t> b32;
 	if (best_out) {
@@ -778,8 +1067,12 @@ extern "C" int bg_batch_download(bg_ctx *c, bg_hit *hits, uint64_t cap, uint16_t
 	}
 	CU(cudaStreamSynchronize(c->stream));
 	if (best_out) for (uint32_t i = 0; i < c->nslots; ++i) best_out[i] = (uint16_t)std::min<uint32_t>(b32[i], 0xFFFF);
-	if (hits) std::sort(hits, hits + n, [](const bg_hit &a, const bg_hit &b) { return a.task != b.task ? a.task < b.task : a.lane < b.lane; });
-	if (hits && c->by_runs) for (uint64_t i = 0; i < n; ++i) hits[i].task = c->run_key[hits[i].task];
+	// internal task id (run * 16 + i) -> the caller's task index
+	if (hits && c->kind == WORK_TASKS) for (uint64_t i = 0; i < n; ++i) hits[i].task = c->task0[hits[i].task >> 4] + (hits[i].task & 15);
+	else if (hits && c->kind == WORK_ALL) for (uint64_t i = 0; i < n; ++i) {
+		const uint32_t r = hits[i].task >> 4, cl = r / c->ntiles, tile = r % c->ntiles;
+		hits[i].task = cl * c->nq + tile * BG_RUN_MAX + (hits[i].task & 15);
+	}
 	return BG_OK;
 }
 
@@ -787,9 +1080,15 @@ extern "C" int bg_batch_stats(bg_ctx *c, bg_stats *out) {
 	if (!c || !out) return fail(BG_EINVAL, "null argument");
 	CU(cudaSetDevice(c->device));
 	int rc = settle(c); if (rc) return rc;
-	unsigned long long cells = 0;
-	CU(cudaMemcpy(&cells, c->d_cells.p, 8, cudaMemcpyDeviceToHost));
-	c->stats.survivors = c->h_counters[0]; c->stats.hits = c->h_counters[2]; c->stats.band_cells = cells;
+	CU(cudaMemsetAsync(c->d_cells.p + 1, 0, 32, c->stream));
+	if (c->nruns) k_work_stats<<<(unsigned)c->sms * 8, 256, 0, c->stream>>>(work_of(c), c->d_qi.p, c->d_clump_len.p, c->d_cells.p + 1);
+	CU(cudaGetLastError());
+	unsigned long long v[5] = {0, 0, 0, 0, 0};
+	CU(cudaMemcpyAsync(v, c->d_cells.p, 40, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->stats.tasks = v[1]; c->stats.nominal_cells = v[2]; c->stats.filter_cells = v[3]; c->stats.seed_steps = v[4];
+	c->stats.survivors = c->h_counters[C_SURV]; c->stats.hits = c->h_counters[C_HITS]; c->stats.band_cells = v[0];
+	c->stats.seed_queries = c->nseed; c->stats.seed_pieces = c->SL.np; c->stats.seed_piece_len = c->SL.w;
 	cudaEventElapsedTime(&c->stats.ms_filter, c->ev[0], c->ev[1]);
 	cudaEventElapsedTime(&c->stats.ms_extend, c->ev[1], c->ev[2]);
 	cudaEventElapsedTime(&c->stats.ms_select, c->ev[2], c->ev[3]);
@@ -797,11 +1096,8 @@ extern "C" int bg_batch_stats(bg_ctx *c, bg_stats *out) {
 	return BG_OK;
 }
 
-extern "C" int bg_align_batch(bg_ctx *c, const bg_queries *Q, const bg_task *tasks, uint64_t ntasks, int mode,
-		uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
-	if (!hits || !nhits) return fail(BG_EINVAL, "bg_align_batch: null output");
-	int rc = bg_batch_upload(c, Q, tasks, ntasks); if (rc) return rc;
-	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
+static int finish_align(bg_ctx *c, int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
+	int rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
 	uint64_t n = 0;
 	rc = bg_batch_count(c, &n); if (rc) return rc;
 	bg_hit *h = (bg_hit *)malloc((n ? n : 1) * sizeof(bg_hit));
@@ -812,38 +1108,16 @@ extern "C" int bg_align_batch(bg_ctx *c, const bg_queries *Q, const bg_task *tas
 	return BG_OK;
 }
 
-// Run lists (bg_run): expanded to tasks here; hits come back keyed run * BG_RUN_MAX + i.
-static int expand_runs(const bg_queries *Q, const bg_run *runs, uint64_t nruns, std::vector<bg_task> &tasks, std::vector<uint32_t> &key) {
-	if (!Q || !runs) return fail(BG_EINVAL, "bg_batch_upload_runs: null argument");
-	if (nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_batch_upload_runs: %llu runs in one batch (limit 2^28-1)", (unsigned long long)nruns);
-	tasks.clear(); key.clear();
-	for (uint64_t r = 0; r < nruns; ++r) {
-		if (!runs[r].nq || runs[r].nq > BG_RUN_MAX || (uint64_t)runs[r].query0 + runs[r].nq > Q->nq)
-			return fail(BG_EINVAL, "bg_batch_upload_runs: run %llu (query0 %u, nq %u) is malformed", (unsigned long long)r, runs[r].query0, runs[r].nq);
-		for (uint32_t i = 0; i < runs[r].nq; ++i) { tasks.push_back(bg_task{runs[r].query0 + i, runs[r].clump}); key.push_back((uint32_t)(r * BG_RUN_MAX + i)); }
-	}
-	return BG_OK;
-}
-extern "C" int bg_batch_upload_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns) {
-	if (!c) return fail(BG_EINVAL, "null ctx");
-	std::vector<bg_task> tasks;
-	int rc = expand_runs(Q, runs, nruns, tasks, c->run_key); if (rc) return rc;
-	rc = bg_batch_upload(c, Q, tasks.data(), tasks.size());
-	c->by_runs = rc == BG_OK;
-	return rc;
+extern "C" int bg_align_batch(bg_ctx *c, const bg_queries *Q, const bg_task *tasks, uint64_t ntasks, int mode,
+		uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
+	if (!hits || !nhits) return fail(BG_EINVAL, "bg_align_batch: null output");
+	int rc = bg_batch_upload(c, Q, tasks, ntasks); if (rc) return rc;
+	return finish_align(c, mode, best_inout, hits, nhits);
 }
 extern "C" int bg_align_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns, int mode,
 		uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
 	if (!hits || !nhits) return fail(BG_EINVAL, "bg_align_runs: null output");
 	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;
-	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
-	uint64_t n = 0;
-	rc = bg_batch_count(c, &n); if (rc) return rc;
-	bg_hit *h = (bg_hit *)malloc((n ? n : 1) * sizeof(bg_hit));
-	if (!h) return fail(BG_ENOMEM, "malloc hits");
-	rc = bg_batch_download(c, h, n, best_inout);
-	if (rc) { free(h); return rc; }
-	*hits = h; *nhits = n;
-	return BG_OK;
+	return finish_align(c, mode, best_inout, hits, nhits);
 }
 extern "C" void bg_free_hits(bg_hit *h) { free(h); }

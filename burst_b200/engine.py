@@ -16,6 +16,7 @@ TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
 RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
+PARAM_SEED_FILTER = 1
 
 
 class BgQueries(C.Structure):
@@ -25,7 +26,9 @@ class BgQueries(C.Structure):
 
 class BgStats(C.Structure):
     _fields_ = [("tasks", C.c_uint64), ("nominal_cells", C.c_uint64), ("filter_cells", C.c_uint64),
+                ("seed_steps", C.c_uint64),
                 ("survivors", C.c_uint64), ("band_cells", C.c_uint64), ("hits", C.c_uint64),
+                ("seed_queries", C.c_uint32), ("seed_pieces", C.c_uint32), ("seed_piece_len", C.c_uint32),
                 ("ms_filter", C.c_float), ("ms_extend", C.c_float), ("ms_select", C.c_float)]
 
     def asdict(self):
@@ -35,7 +38,7 @@ class BgStats(C.Structure):
 EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scoring", "bg_default_scoring",
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
-           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs"]
+           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param"]
 
 
 def load_library():
@@ -49,6 +52,7 @@ def load_library():
     L.bg_free.argtypes = [C.c_void_p]
     L.bg_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     L.bg_set_scoring.argtypes = [C.c_void_p, C.c_void_p]
+    L.bg_set_param.argtypes = [C.c_void_p, C.c_int, C.c_int]
     L.bg_default_scoring.argtypes = [C.c_int, C.c_void_p]
     L.bg_load_db.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32]
     L.bg_batch_upload.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64]
@@ -101,6 +105,9 @@ class Engine:
     def set_scoring(self, S):
         S = np.ascontiguousarray(S, np.uint8)
         self._check(self.lib.bg_set_scoring(self.ctx, S.ctypes.data))
+
+    def set_seed_filter(self, on):
+        self._check(self.lib.bg_set_param(self.ctx, PARAM_SEED_FILTER, 1 if on else 0))
 
     def load_db(self, packed, clump_len, first_clump=0):
         packed = np.ascontiguousarray(packed, np.uint8)

@@ -241,10 +241,13 @@ def bunch_workload(n_reads, read_len, n_err, db_bytes, clump_len, seed, qbunch=1
     tq = np.repeat(qstart, qcount) + (np.arange(int(qcount.sum())) - np.repeat(np.cumsum(qcount) - qcount, qcount))
     tc = np.repeat(cand, qcount)
     tasks = np.stack([tq, tc], 1).astype(np.uint32)
+    # the same visits as run records {clump, query0, nq}: one per (bunch, candidate clump)
+    runs = np.zeros(len(cand), dtype=np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")]))
+    runs["clump"] = cand; runs["query0"] = qstart; runs["nq"] = qcount
     if budget is None:
         budget = np.full(nq, n_err, np.uint16)
     return dict(packed=packed, clump_off=coff, clump_len=clens, qcodes=qcodes, qoff=qoff, slot=slot,
-                nslots=n_reads, budget=budget, tasks=tasks, cand_off=cand_off, cand=cand, qbunch=qbunch,
+                nslots=n_reads, budget=budget, tasks=tasks, runs=runs, cand_off=cand_off, cand=cand, qbunch=qbunch,
                 true_clump=clump, true_lane=lane, true_start=start, n_reads=n_reads, match=match)
 
 

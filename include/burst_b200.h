@@ -73,10 +73,13 @@ typedef struct {
 typedef struct {
 	uint64_t tasks;             /* (query, clump) pairs evaluated */
 	uint64_t nominal_cells;     /* sum over tasks of 16 * qlen * ClumpLen */
-	uint64_t filter_cells;      /* DP cells covered by the bit-parallel prefix filter */
+	uint64_t filter_cells;      /* DP cells covered by the Myers prefix filter (k_filter) */
+	uint64_t seed_steps;        /* (lane, column) automaton steps of the pigeonhole seed filter (k_seed), per query */
 	uint64_t survivors;         /* (task, lane) pairs handed to the banded pass */
 	uint64_t band_cells;        /* DP cells updated by the banded pass (x3 values each) */
 	uint64_t hits;              /* lanes reported */
+	uint32_t seed_queries;      /* queries of the batch taken by k_seed (the rest go through k_filter) */
+	uint32_t seed_pieces, seed_piece_len;    /* automaton layout chosen for the batch */
 	float ms_filter, ms_extend, ms_select;   /* device time of the last bg_batch_run */
 } bg_stats;
 
@@ -86,6 +89,10 @@ void bg_free(bg_ctx *ctx);
 const char *bg_last_error(void);
 /* Run every kernel and copy of this context on an existing CUDA stream (cudaStream_t). */
 int  bg_set_stream(bg_ctx *ctx, void *cuda_stream);
+
+/* Tuning knobs (results never depend on them). */
+enum { BG_PARAM_SEED_FILTER = 1 };   /* 1 (default): pigeonhole seed filter where the batch allows; 0: Myers prefix filter only */
+int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),
  * S[q*16+r] in {0,1,255}; call before aligning (default: Z=1 table). */

@@ -47,6 +47,7 @@ static void free_batch(bg_ctx *c) {
 }
 void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); free(c->packed); free(c->clump_off); free(c->clump_len); free(c); }
 int bg_set_stream(bg_ctx *c, void *s) { (void)c; (void)s; return BG_OK; }
+int bg_set_param(bg_ctx *c, int what, int value) { (void)c; (void)what; (void)value; return BG_OK; }
 int bg_set_scoring(bg_ctx *c, const uint8_t S[256]) { memcpy(c->S, S, 256); return BG_OK; }
 
 int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clump_len, uint32_t n, uint32_t first) {

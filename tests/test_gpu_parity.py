@@ -37,12 +37,16 @@ def check(eng, oracle, packed, off, clen, reads, budget, tasks=None, mode=0, slo
     else:
         tq, tc = tasks
         gt = np.stack([tq, tc], 1).astype(np.uint32)
-    hits, gbest = eng.align(codes, qoff, budget, gt, mode, slot=slot, nslots=nslots, best=best)
     ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nslots, tq, tc, S, mode, best=best)
-    assert np.array_equal(gbest, obest), "per-slot minima differ"
-    assert len(hits) == len(ohits), (len(hits), len(ohits))
-    assert np.array_equal(hits, ohits), "hits differ: first diff %s" % (
-        next(((tuple(a), tuple(b)) for a, b in zip(hits, ohits) if tuple(a) != tuple(b)), None),)
+    for seed in (True, False):          # both filters: pigeonhole seeds (where the batch allows) and the Myers prefix filter
+        eng.set_seed_filter(seed)
+        hits, gbest = eng.align(codes, qoff, budget, gt, mode, slot=slot, nslots=nslots, best=best)
+        assert np.array_equal(gbest, obest), "per-slot minima differ (seed filter %s)" % seed
+        assert len(hits) == len(ohits), (len(hits), len(ohits), seed)
+        assert np.array_equal(hits, ohits), "hits differ (seed filter %s): first diff %s" % (seed,
+            next(((tuple(a), tuple(b)) for a, b in zip(hits, ohits) if tuple(a) != tuple(b)), None),)
+    eng.set_seed_filter(True)
+    hits, gbest = eng.align(codes, qoff, budget, gt, mode, slot=slot, nslots=nslots, best=best)
     return hits, eng.stats()
 
 
@@ -178,3 +182,102 @@ def test_reference_shard_skips_foreign_clumps(eng, oracle):
     keep = allh[allh["ed"] == gbest[tq[allh["task"]]]]
     keep = keep[np.lexsort((keep["lane"], keep["task"]))]
     assert np.array_equal(keep, full)
+
+
+def test_run_lists_match_task_lists(eng, oracle):
+    """bg_run work lists (one entry per clump visit of a bunch, burst.c:4137-4157) against the same
+    visits written out as tasks for the oracle; hits come back keyed run * 16 + query-in-run."""
+    from burst_b200.engine import RUN_DTYPE, RUN_MAX
+    rng = np.random.default_rng(17)
+    refs = synth.random_refs(16 * 64, 214, rng, jitter=6)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 203, 100, 2, rng, exact_edits=True)
+    codes, qoff = synth.concat_queries(reads)
+    nq = len(reads)
+    budget = np.full(nq, 2, np.uint16)
+    runs, tq, tc, key = [], [], [], []
+    for q0 in range(0, nq, 11):                      # bunches of 11 (last one ragged)
+        n = min(11, nq - q0)
+        cands = sorted({int(origin[q, 0]) for q in range(q0, q0 + n)} | {int(v) for v in rng.integers(0, len(clen), 2)})
+        for c in cands:
+            for i in range(n):
+                tq.append(q0 + i); tc.append(c); key.append(len(runs) * RUN_MAX + i)
+            runs.append((c, q0, n))
+    runs = np.array(runs, dtype=RUN_DTYPE)
+    S = oracle.score_table(1)
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    slot = np.arange(nq, dtype=np.uint32)
+    ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nq, np.array(tq, np.uint32), np.array(tc, np.uint32), S, 0)
+    ohits = ohits.copy(); ohits["task"] = np.array(key, np.uint32)[ohits["task"]]
+    for seed in (True, False):
+        eng.set_seed_filter(seed)
+        hits, best = eng.align(codes, qoff, budget, None, 0, runs=runs)
+        assert np.array_equal(best, obest)
+        assert np.array_equal(hits, ohits), seed
+    eng.set_seed_filter(True)
+    eng.align(codes, qoff, budget, None, 0, runs=runs)
+    st = eng.stats()
+    assert st["seed_queries"] == nq and st["seed_pieces"] == 3 and st["seed_piece_len"] == 10
+    assert len(hits) >= 200
+
+
+def test_repeats_give_several_seed_clusters(eng, oracle):
+    """A read that occurs more than once in one reference lane (tandem / distant repeats, with and without
+    errors) yields several diagonal clusters for one (query, lane); the merged result must be what the
+    reference's left-to-right last-row scan gives (burst.c:826-883): best (score, shift), numGapR of its
+    first occurrence, column of its last."""
+    rng = np.random.default_rng(23)
+    reads, refs = [], []
+    for i in range(48):
+        q = rng.integers(1, 5, 100, dtype=np.uint8)
+        copies = [q.copy() for _ in range(int(rng.integers(2, 5)))]
+        for j, cp in enumerate(copies):
+            ne = int(rng.integers(0, 4))
+            if (i + j) % 3 == 0:
+                ne = 0
+            copies[j] = synth.mutate(cp, ne, rng)
+        parts = []
+        for cp in copies:
+            parts += [rng.integers(1, 5, int(rng.integers(3, 90)), dtype=np.uint8), cp]
+        parts.append(rng.integers(1, 5, 20, dtype=np.uint8))
+        refs.append(np.concatenate(parts).astype(np.uint8))
+        reads.append(q)
+    refs += synth.random_refs(16, 400, rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    for k in (1, 2, 3):
+        hits, st = check(eng, oracle, packed, off, clen, reads, [k] * len(reads), mode=0)
+        assert len(hits) >= 20
+    check(eng, oracle, packed, off, clen, reads, [3] * len(reads), mode=1)
+
+
+def test_mixed_budgets_split_between_filters(eng, oracle):
+    """One batch where some queries fit the seed automaton and others (large budget, short pieces) do not."""
+    rng = np.random.default_rng(29)
+    refs = synth.random_refs(16 * 6, 360, rng, jitter=25)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, budget = [], []
+    for i in range(90):
+        L = int(rng.choice([40, 100, 150, 260]))
+        r, _ = synth.reads_from_clumps(packed, off, clen, 1, L, int(rng.integers(0, 4)), rng)
+        reads.append(r[0]); budget.append(int(rng.choice([0, 1, 2, 3, 3, 3, 8, 13])))
+    hits, st = check(eng, oracle, packed, off, clen, reads, budget, mode=0)
+    assert 0 < st["seed_queries"] < len(reads)
+    check(eng, oracle, packed, off, clen, reads, budget, mode=1)
+
+
+def test_malformed_input_is_an_error_not_a_crash(eng, oracle):
+    from burst_b200.engine import RUN_DTYPE
+    rng = np.random.default_rng(31)
+    refs = synth.random_refs(16, 200, rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    eng.load_db(packed, clen)
+    reads, _ = synth.reads_from_clumps(packed, off, clen, 8, 50, 1, rng)
+    codes, qoff = synth.concat_queries(reads)
+    with pytest.raises(RuntimeError, match="malformed"):
+        eng.align(codes, qoff, np.full(8, 255, np.uint16), None)          # budget above 254
+    with pytest.raises(RuntimeError, match="malformed"):
+        eng.align(codes, qoff, np.full(8, 1, np.uint16), None, runs=np.array([(0, 4, 9)], dtype=RUN_DTYPE))   # runs past the batch
+    with pytest.raises(RuntimeError, match="names query"):
+        eng.align(codes, qoff, np.full(8, 1, np.uint16), np.array([[8, 0]], np.uint32))
+    hits, best = eng.align(codes, qoff, np.full(8, 1, np.uint16), None)    # the context is still usable
+    assert len(hits) >= 8
