@@ -41,11 +41,15 @@ EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scori
            "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param"]
 
 
-def load_library():
-    if not os.path.exists(LIB_PATH):
+def load_library(path=None):
+    """Load the engine.  `path` exists for the CPU test tier only (tests/ point it at the oracle-backed
+    stand-in oracle/_sim/libburst_b200_sim.so to exercise host-side logic without a GPU); the product
+    always loads the CUDA library next to this file and fails loudly when it is missing."""
+    path = path or LIB_PATH
+    if not os.path.exists(path):
         raise RuntimeError("%s is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "(there is no CPU fallback for the DP path)" % LIB_PATH)
-    L = C.CDLL(LIB_PATH)
+                           "(there is no CPU fallback for the DP path)" % path)
+    L = C.CDLL(path)
     L.bg_last_error.restype = C.c_char_p
     L.bg_batch_best_device.restype = C.c_void_p
     L.bg_init.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
@@ -79,8 +83,8 @@ def default_scoring(z=1):
 
 
 class Engine:
-    def __init__(self, device=0, stream=None):
-        self.lib = load_library()
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.lib = load_library(lib_path)
         self.ctx = C.c_void_p()
         self._check(self.lib.bg_init(device, C.byref(self.ctx)))
         if stream is not None:

@@ -27,6 +27,7 @@ struct bg_ctx {
 	uint8_t *codes; uint64_t *qoff; uint16_t *budget; uint32_t *slot; uint32_t nq, nslots;
 	uint32_t *tq, *tc; uint64_t *orig; uint64_t ntasks;
 	uint16_t *best; OracleHit *hits; uint64_t nhits;
+	uint32_t *best32;           /* what bg_batch_best_device() exposes between run_extend and run_select */
 };
 
 static char g_err[256] = "";
@@ -42,7 +43,7 @@ int bg_init(int device, bg_ctx **out) {
 }
 static void free_batch(bg_ctx *c) {
 	free(c->codes); free(c->qoff); free(c->budget); free(c->slot); free(c->tq); free(c->tc); free(c->orig);
-	free(c->best); free(c->hits);
+	free(c->best); free(c->hits); free(c->best32); c->best32 = NULL;
 	c->codes = NULL; c->qoff = NULL; c->budget = NULL; c->slot = NULL; c->tq = c->tc = NULL; c->orig = NULL; c->best = NULL; c->hits = NULL;
 }
 void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); free(c->packed); free(c->clump_off); free(c->clump_len); free(c); }
@@ -116,9 +117,22 @@ static int run(bg_ctx *c, int mode, const uint16_t *best_in) {
 	return BG_OK;
 }
 int bg_batch_run(bg_ctx *c, int mode, const uint16_t *best_in) { return run(c, mode, best_in); }
-int bg_batch_run_extend(bg_ctx *c, int mode, const uint16_t *best_in) { return run(c, mode, best_in); }
-void *bg_batch_best_device(bg_ctx *c) { (void)c; return NULL; }
-int bg_batch_run_select(bg_ctx *c, int mode) { (void)c; (void)mode; return BG_OK; }
+/* split form: extend leaves the local minima in best32 (host memory here); the caller may lower them
+ * (all-reduce MIN across reference shards); select re-derives the hits under the lowered minima */
+int bg_batch_run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
+	run(c, mode, best_in);
+	free(c->best32); c->best32 = malloc(c->nslots * 4 + 4);
+	for (uint32_t i = 0; i < c->nslots; ++i) c->best32[i] = c->best[i];
+	return BG_OK;
+}
+void *bg_batch_best_device(bg_ctx *c) { return c->best32; }
+int bg_batch_run_select(bg_ctx *c, int mode) {
+	uint16_t *in = malloc(c->nslots * 2 + 2);
+	for (uint32_t i = 0; i < c->nslots; ++i) in[i] = (uint16_t)(c->best32[i] > 0xFFFF ? 0xFFFF : c->best32[i]);
+	run(c, mode, in);
+	free(in);
+	return BG_OK;
+}
 int bg_batch_count(bg_ctx *c, uint64_t *n) { if (n) *n = c->nhits; return BG_OK; }
 int bg_batch_download(bg_ctx *c, bg_hit *hits, uint64_t cap, uint16_t *best_out) {
 	if (hits) {
