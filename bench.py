@@ -264,7 +264,7 @@ def main():
                "seed_steps_per_s": st["seed_steps"] * world / (ms_step / 1e3),
                "work": {"tasks": st["tasks"], "survivors": st["survivors"], "hits": st["hits"], "nominal_cells": st["nominal_cells"],
                         "filter_cells": st["filter_cells"], "seed_steps": st["seed_steps"], "seed_queries": st["seed_queries"],
-                        "seed_layout": "%d pieces x %d bases" % (st["seed_pieces"], st["seed_piece_len"]), "band_cells": st["band_cells"], "reads_found": found, "reads_at_planted_lane": planted,
+                        "seed_layout": "probe every %d columns, %d-base windows, %d-word filter per warp" % (st["seed_stride"], st["seed_window"], st["seed_words"]), "band_cells": st["band_cells"], "reads_found": found, "reads_at_planted_lane": planted,
                         "ms_filter": st["ms_filter"], "ms_extend": st["ms_extend"], "ms_select": st["ms_select"]},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                             "kernel": "k_seed" if st["seed_queries"] else "k_filter", "peak_source": how + " (MEASURED_PEAKS.json hbm_gbs, burst figure)",

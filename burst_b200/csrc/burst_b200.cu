@@ -4,14 +4,16 @@
 //   pass 1  aded_mat16L / aded_mat16   burst.c:1003-1204   16-lane banded edit distance
 //   pass 2  reScoreM_mat16             burst.c:713-886     (score, shift, shiftR) + end column
 // and how this file restructures it for the GPU (DESIGN.md section 2 has the full argument):
-//   k_qinfo/k_qtables  per query: budget/length record, Myers match vectors, Shift-And piece tables
-//   k_seed         one warp per RUN (= one clump visit by <= 16 consecutive queries, the reference's
-//                  "unpack the clump once, then loop over the bunch", burst.c:4141-4157).  Pigeonhole:
-//                  an alignment with <= k errors contains one of k+1 disjoint query pieces unchanged.
-//                  All pieces of a query form one 32-bit Shift-And automaton; 16 lanes x 2 column halves
-//                  per warp, the run's 16 automata in registers.  Exact piece matches = seeds ->
+//   k_qinfo/k_qprep/k_qtables  per query: budget/length record, nibble-packed bases, Myers match vectors
+//   k_seed         one warp per chunk of RUNS (run = one clump visit by <= 16 consecutive queries, the
+//                  reference's "unpack the clump once, then loop over the bunch", burst.c:4141-4157).
+//                  Pigeonhole: an alignment with <= k errors leaves one of k+1 disjoint query stretches
+//                  unchanged, so some word-aligned (or half-word-aligned) window of w reference bases
+//                  equals one of `stride` windows at the end of that stretch.  The run's query windows go
+//                  into a blocked Bloom filter in shared memory; the clump is streamed once, one hash
+//                  probe per 8 (or 4) columns per lane; flagged windows are verified exactly -> seeds ->
 //                  disjoint diagonal clusters [d-k, d+k].
-//   k_filter       queries k_seed cannot take (many errors / short pieces): Myers/Hyyro bit-vector
+//   k_filter       queries k_seed cannot take (many errors / short stretches / IUPAC bases): Myers/Hyyro bit-vector
 //                  semi-global DP of the query's first P <= 32 rows; columns with row-P value <= k
 //                  are seeds (every <= k alignment has a <= k prefix); hull of the seed diagonals.
 //   k_extend       one thread per surviving (task, lane, cluster): exact banded DP, carrying the
@@ -133,18 +135,23 @@ __device__ __forceinline__ uint32_t lane_word(const uint32_t *lanew, uint32_t wi
 
 // ---------------------------------------------------------------------------------------------
 // Query prep.
-// k_qinfo: raw (offset, budget, slot) arrays -> QInfo, validation, histogram of pieces needed.
-//   hist[p] (p = 0..4) counts queries needing p+1 pieces (k+1), hist[4] everything above 4.
-// k_qtables: per (query, reference code c)
-//   peq: Myers match vector, bit (32-P+y-1) = 1 iff row y (1-based) matches c (S == 0).  The
-//        pattern is left-aligned so that row P sits in bit 31; the unused low 32-P bits are set for
-//        every code: with Pv = Mv = 0 there they behave as extra copies of the all-zero row 0.
-//   seq: Shift-And table, bit (p*ws + i) = 1 iff base i of piece p matches c; piece p = the LAST w bases
-//        of the p-th of k+1 equal stretches of the query (ending at offset (p+1) * (len / (k+1))): sorted
-//        neighbours of a bunch share their first ~log4(#queries) bases, so a piece taken from the very
-//        start of the query would seed at every bunch-mate's true hit.  All zero when not seed-eligible.
+// k_qinfo:  raw (offset, budget, slot) arrays -> QInfo, validation, histogram of stretch lengths
+//           hist[min(plen, 31)] over queries with k+1 <= SEED_NP_MAX, plen = len / (k+1).
+// k_qprep:  nibble-packed copy of every query (two zero pad words, then 8 bases per word, base i in
+//           nibble i & 7 -- the same nibble order as the DB) at word (off >> 3) + 3 * q, and the class:
+//           cls = 1 (k_seed) iff the seed filter is on, every stretch is long enough for the batch's
+//           window layout and the windows' bases are all plain A/C/G/T; else 0 (k_filter).
+// k_qtables: per (query, reference code c) the Myers match vector
+//   peq: bit (32-P+y-1) = 1 iff row y (1-based) matches c (S == 0).  The pattern is left-aligned so
+//        that row P sits in bit 31; the unused low 32-P bits are set for every code: with Pv = Mv = 0
+//        there they behave as extra copies of the all-zero row 0.
 // ---------------------------------------------------------------------------------------------
-struct SeedLayout { uint32_t np, ws, w, I, F; };   // pieces per word, slot width, piece length, start bits, final bits
+#define SEED_NP_MAX 32
+// stride: reference windows are probed every `stride` columns (8 = word ends, 4 = also half words, 0 = off);
+// w: window length in bases (8..16); hm: mask of the older word's nibbles inside the window;
+// words: Bloom filter words per warp (power of two), shw = 32 - log2(words);
+// amb_add: 0x2222.. flags reference codes >= 6, 0x3333.. codes >= 5 (N matches for free, -y) as "verify by table".
+struct SeedLayout { uint32_t stride, w, hm, words, shw, amb_add; };
 
 __global__ void k_qinfo(const uint64_t *__restrict__ off, const uint16_t *__restrict__ budget, const uint32_t *__restrict__ slot,
 		uint32_t nq, uint32_t nslots, QInfo *__restrict__ qi, uint32_t *__restrict__ hist, uint32_t *__restrict__ counters) {
@@ -155,11 +162,39 @@ __global__ void k_qinfo(const uint64_t *__restrict__ off, const uint16_t *__rest
 	if (off[q + 1] <= o || len > 0x7FFFFFFFull || k > 254 || s >= nslots) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; s = 0; }
 	QInfo Q; Q.off = o; Q.len = (uint32_t)len; Q.slot = s; Q.k = (uint16_t)k; Q.P = (uint8_t)min((uint64_t)32, len); Q.cls = 0;
 	qi[q] = Q;
-	atomicAdd(&hist[min(k, 4u)], 1u);
+	if (k + 1 <= SEED_NP_MAX) atomicAdd(&hist[min((uint32_t)len / (k + 1), 31u)], 1u);
 }
 
-__global__ void k_qtables(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, const uint32_t *__restrict__ Sterm,
-		uint32_t nq, SeedLayout SL, uint32_t *__restrict__ peq, uint32_t *__restrict__ seq, uint32_t *__restrict__ nseed) {
+__global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, uint32_t nq, SeedLayout SL,
+		uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed) {
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	bool seed = false; uint32_t nst = 0;
+	if (q < nq) {
+		const QInfo Q = qi[q];
+		const uint8_t *s = codes + Q.off;
+		uint32_t *W = qnib + (Q.off >> 3) + 3ull * q;
+		W[0] = 0; W[1] = 0;
+		for (uint32_t j = 0; j < Q.len; j += 8) {
+			uint32_t w = 0;
+			#pragma unroll
+			for (int i = 0; i < 8; ++i) if (j + i < Q.len) w |= (uint32_t)(s[j + i] & 15) << (4 * i);
+			W[2 + (j >> 3)] = w;
+		}
+		const uint32_t np = Q.k + 1u, plen = Q.len / np;
+		seed = SL.stride && np <= SEED_NP_MAX && plen >= SL.w + SL.stride - 1;
+		for (uint32_t p = 0; p < np && seed; ++p) {
+			const uint32_t E = (p + 1) * plen;
+			for (uint32_t i = E - (SL.w + SL.stride - 1); i < E; ++i) { const uint32_t c = s[i] & 15; if (c < 1 || c > 4) { seed = false; break; } }
+		}
+		qi[q].cls = seed;
+		if (seed) nst = np;
+	}
+	const uint32_t m = __ballot_sync(0xFFFFFFFFu, seed), tot = __reduce_add_sync(0xFFFFFFFFu, nst);
+	if (m && (threadIdx.x & 31) == 0) { atomicAdd(nseed, (uint32_t)__popc(m)); atomicAdd(nseed + 1, tot); }   // seeded queries, their stretches
+}
+
+__global__ void k_qtables(const uint8_t *__restrict__ codes, const QInfo *__restrict__ qi, const uint32_t *__restrict__ Sterm,
+		uint32_t nq, uint32_t *__restrict__ peq) {
 	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	uint32_t q = i >> 4, c = i & 15;
 	if (q >= nq) return;
@@ -170,14 +205,6 @@ __global__ void k_qtables(const uint8_t *__restrict__ codes, QInfo *__restrict__
 	for (uint32_t y = 0; y < P; ++y)
 		if (Sterm[(s[y] & 15) * 16 + c] == 0) m |= 1u << (32 - P + y);
 	peq[i] = m;
-	const uint32_t np = Q.k + 1u, plen = Q.len / np;
-	const bool seed = SL.np && np <= SL.np && plen >= SL.w;
-	uint32_t e = 0;
-	if (seed) for (uint32_t p = 0; p < np; ++p)
-		for (uint32_t j = 0; j < SL.w; ++j)
-			if (Sterm[(s[(p + 1) * plen - SL.w + j] & 15) * 16 + c] == 0) e |= 1u << (p * SL.ws + j);
-	seq[i] = e;
-	if (c == 0) { qi[q].cls = seed; if (seed) atomicAdd(nseed, 1u); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -222,107 +249,174 @@ __device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------
-// Phase A1: pigeonhole seed filter.  128 threads = 4 warps = 4 runs.
+// Phase A1: pigeonhole seed filter.  128 threads = 4 warps, each warp owns a chunk of consecutive runs.
+//
+// Why a probe every `stride` columns is enough.  Let a query of length m with budget k be cut into k+1
+// stretches of plen = m / (k+1) bases (stretch p ends at query offset E = (p+1) * plen).  An alignment
+// with <= k errors leaves at least one stretch without error: its plen bases sit on ONE diagonal opposite
+// plen consecutive reference columns [a, a + plen).  With plen >= w + stride - 1 those columns contain a
+// window of w columns that ends on a multiple of `stride`; the query bases opposite it are a window of w
+// bases ending at E - j for some 0 <= j < stride.  So: put the `stride` windows ending at E, E-1, ..,
+// E-stride+1 of every stretch into a set, probe the set with the reference window ending at every
+// multiple of `stride`, and every alignment within budget is found, with seed diagonal
+// d = (reference end column) - (E - j); the whole alignment then lies within diagonals [d-k, d+k].
+// The set is a blocked Bloom filter (one 32-bit word, two bits) per warp in shared memory, keyed by the
+// window's nibbles; a set bit is only a candidate, the verification below compares the nibbles.
+// Reference codes that can match a plain base without being equal to it (IUPAC codes, N under -y)
+// bypass the filter: their words are always flagged and verified through the scoring table.
 // ---------------------------------------------------------------------------------------------
 struct SeedArgs {
-	const uint32_t *dbw; const uint64_t *clump_off; const uint32_t *clump_len;
-	const QInfo *qi; const uint32_t *seq; Work W; SeedLayout SL;
+	const uint4 *db; const uint64_t *clump_off; const uint32_t *clump_len;
+	const QInfo *qi; const uint32_t *qnib; Work W; SeedLayout SL;
+	uint64_t nwork; uint32_t chunk;                 // run indices to enumerate, runs per warp
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;
+	uint32_t m16[8];                                // match sets: bit r of half-word q = (S[q][r] == 0)
 };
 
-#define SEED_WARM 2      // words of warm-up before a scan segment: 16 columns >= w - 1
+// work index -> run.  Explicit lists are walked as given (a bunch's clump visits are consecutive and share
+// their queries); the implicit all-vs-all list is walked tile-major for the same reason, while the run id
+// (and with it the task id the host sees) stays clump-major.
+__device__ __forceinline__ bool get_work(const Work &W, uint64_t i, uint64_t &r, uint32_t &c, uint32_t &q0, uint32_t &n) {
+	if (W.runs) r = i;
+	else { const uint64_t tile = i / W.num_clumps, cl = i - tile * W.num_clumps; r = cl * W.ntiles + tile; }
+	return get_run(W, r, c, q0, n);
+}
 
-__global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
-	__shared__ uint32_t sEqAll[4][BG_RUN_MAX * 16];
-	const uint32_t warp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	const uint64_t r = (uint64_t)blockIdx.x * 4 + warp;
-	if (r >= A.W.nruns) return;
-	uint32_t c, q0, n;
-	if (!get_run(A.W, r, c, q0, n)) return;
-	uint32_t *sEq = sEqAll[warp];
-	#pragma unroll
-	for (int i = 0; i < 8; ++i) {
-		const uint32_t e = t + 32 * i, q = e >> 4;
-		sEq[e] = q < n ? __ldg(A.seq + (size_t)(q0 + q) * 16 + (e & 15)) : 0u;
-	}
-	__syncwarp();
-	const uint32_t L = A.clump_len[c], nwords = (L + 7) >> 3;
-	const uint32_t lane = t & 15, h = t >> 4;
-	const uint32_t *lanew = A.dbw + A.clump_off[c] * 4 + lane * 4;
-	// this thread's share of the lane: words [w0, w1); granule = words per mask bit
-	const uint32_t wh = (nwords + 1) >> 1;
-	const uint32_t w0 = h * wh, w1 = min(nwords, w0 + wh);
-	const uint32_t g = (wh + 31) >> 5;
-	const uint32_t I = A.SL.I, F = A.SL.F;
-	uint32_t D[BG_RUN_MAX];
-	#pragma unroll
-	for (int q = 0; q < BG_RUN_MAX; ++q) D[q] = 0;
-	uint32_t mask = 0;
-	const uint32_t ws0 = w0 >= SEED_WARM ? w0 - SEED_WARM : 0;
-	uint32_t w = ws0 < w1 ? lane_word(lanew, ws0) : 0;
-	for (uint32_t wi = ws0; wi < w1; ++wi) {
-		const uint32_t cur = w;
-		if (wi + 1 < w1) w = lane_word(lanew, wi + 1);
-		uint32_t H = 0;
+#define HASH_C1 0x9E3779B1u
+#define HASH_C2 0x85EBCA77u
+__device__ __forceinline__ uint32_t seed_hash(uint32_t newer, uint32_t older_masked) { return newer * HASH_C1 + older_masked * HASH_C2; }
+__device__ __forceinline__ uint32_t bloom_bits(uint32_t h) { return (1u << ((h >> 15) & 31)) | (1u << ((h >> 10) & 31)); }
+__device__ __forceinline__ uint32_t bloom_test(uint32_t word, uint32_t h) { return (word >> ((h >> 15) & 31)) & (word >> ((h >> 10) & 31)) & 1u; }
+__device__ __forceinline__ uint32_t amb_nibbles(uint32_t w, uint32_t add) { return (((w & 0x77777777u) + add) | w) & 0x88888888u; }
+
+// The windows of one query handled by table half hh (stretches hh, hh+2, ..): f(newer 8 bases, older 8 bases, end offset).
+template <int STRIDE, typename F>
+__device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ Wq, uint32_t len, uint32_t k, uint32_t hh, F f) {
+	const uint32_t np = k + 1u, plen = len / np;
+	for (uint32_t p = hh; p < np; p += 2) {
+		const uint32_t E = (p + 1) * plen;
+		const uint32_t wI = (E + 8) >> 3, sh = ((E + 8) & 7) * 4;          // bases [E-8, E) start at padded nibble E+8
+		const uint32_t a = __ldg(Wq + wI - 2), b = __ldg(Wq + wI - 1), c = __ldg(Wq + wI), d = __ldg(Wq + wI + 1);
+		const uint32_t r0 = __funnelshift_r(a, b, sh), r1 = __funnelshift_r(b, c, sh), r2 = __funnelshift_r(c, d, sh);
 		#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			const uint32_t *e = sEq + ((cur >> (4 * j)) & 15u);
-			#pragma unroll
-			for (int q = 0; q < BG_RUN_MAX; ++q) {
-				D[q] = ((D[q] << 1) | I) & e[q * 16];
-				H |= D[q];
+		for (int j = 0; j < STRIDE; ++j) f(__funnelshift_l(r1, r2, 4 * j), __funnelshift_l(r0, r1, 4 * j), E - j);
+	}
+}
+
+// nibble-by-nibble comparison through the match sets (windows holding ambiguous reference codes only)
+__device__ __noinline__ bool window_matches_table(const uint32_t *sM, uint32_t kn, uint32_t ko, uint32_t rn, uint32_t ro, uint32_t w) {
+	for (uint32_t t = 16 - w; t < 16; ++t) {
+		const uint32_t qn = ((t < 8 ? ko >> (4 * t) : kn >> (4 * (t - 8)))) & 15, rr = ((t < 8 ? ro >> (4 * t) : rn >> (4 * (t - 8)))) & 15;
+		if (!((sM[qn] >> rr) & 1)) return false;
+	}
+	return true;
+}
+
+template <int STRIDE>
+__global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
+	extern __shared__ uint32_t smem[];
+	uint32_t *sM = smem;                                                   // 16 match sets
+	const uint32_t warp = threadIdx.x >> 5, t = threadIdx.x & 31;
+	uint32_t *bits = smem + 16 + warp * A.SL.words;
+	if (threadIdx.x < 16) sM[threadIdx.x] = (A.m16[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xFFFFu;
+	__syncthreads();
+	const uint64_t i0 = ((uint64_t)blockIdx.x * 4 + warp) * A.chunk, i1 = min(A.nwork, i0 + A.chunk);
+	const uint32_t lane = t & 15, h = t >> 4;                              // scan role: reference lane, half of its chunks
+	const uint32_t qi_ = t & 15, hh = t >> 4;                              // table role: query of the run, half of its stretches
+	const uint32_t HM = A.SL.hm, SHW = A.SL.shw, ADD = A.SL.amb_add;
+	uint32_t cur_q0 = 0xFFFFFFFFu, cur_n = 0;
+	QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
+	const uint32_t *Wq = A.qnib;
+	bool act = false, anyact = false;
+	for (uint64_t i = i0; i < i1; ++i) {
+		uint64_t r; uint32_t c, q0, n;
+		if (!get_work(A.W, i, r, c, q0, n)) continue;
+		if (q0 != cur_q0 || n != cur_n) {                                  // new bunch: rebuild the window set
+			cur_q0 = q0; cur_n = n;
+			act = false;
+			if (qi_ < n) { Q = A.qi[q0 + qi_]; act = Q.cls != 0; }
+			anyact = __any_sync(0xFFFFFFFFu, act);
+			if (anyact) {
+				for (uint32_t w = t * 4; w < A.SL.words; w += 128) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);
+				__syncwarp();
+				if (act) {
+					Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi_);
+					for_each_window<STRIDE>(Wq, Q.len, Q.k, hh, [&](uint32_t kn, uint32_t ko, uint32_t) {
+						const uint32_t hv = seed_hash(kn, ko & HM);
+						atomicOr(&bits[hv >> SHW], bloom_bits(hv));
+					});
+				}
+				__syncwarp();
 			}
 		}
-		if ((H & F) && wi >= w0) mask |= 1u << ((wi - w0) / g);
-	}
-	// ---- resolve: which query, which diagonals (rare words only) ----
-	const uint32_t evm = __ballot_sync(0xFFFFFFFFu, mask != 0);
-	uint32_t lanes16 = (evm | (evm >> 16)) & 0xFFFFu;
-	if (!lanes16) return;
-	const uint32_t qi_ = t & 15, hh = t >> 4;
-	QInfo Q; Q.len = 0; Q.k = 0; Q.cls = 0;
-	if (qi_ < n) Q = A.qi[q0 + qi_];
-	const uint32_t plen = Q.len / (Q.k + 1u);
-	const uint32_t *myEq = sEq + qi_ * 16;
-	while (lanes16) {
-		const uint32_t l = __ffs(lanes16) - 1; lanes16 &= lanes16 - 1;
-		const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, mask, l), m1 = __shfl_sync(0xFFFFFFFFu, mask, l + 16);
-		uint32_t mm = hh ? m1 : m0;
-		Clus C; C.n = 0;
-		#pragma unroll
-		for (int s = 0; s <= CLUS_MAX; ++s) { C.lo[s] = 0; C.hi[s] = 0; }
-		if (Q.cls && mm) {
-			const uint32_t *lw = A.dbw + A.clump_off[c] * 4 + l * 4;
-			const uint32_t b0 = hh * wh, b1 = min(nwords, b0 + wh);
-			while (mm) {
-				const uint32_t s = __ffs(mm) - 1;
-				uint32_t e = s; while (e + 1 < 32 && (mm >> (e + 1) & 1)) ++e;       // maximal run of flagged granules
-				mm &= e == 31 ? 0u : ~0u << (e + 1);
-				const uint32_t first = b0 + s * g, last = min(b1, b0 + (e + 1) * g);
-				uint32_t d = 0;
-				for (uint32_t wi = first >= SEED_WARM ? first - SEED_WARM : 0; wi < last; ++wi) {
-					const uint32_t cw = lane_word(lw, wi);
-					for (int j = 0; j < 8; ++j) {
-						d = ((d << 1) | I) & myEq[(cw >> (4 * j)) & 15u];
-						uint32_t f = d & F;
-						while (f) {                                   // a piece ends in this column: one seed diagonal
-							const uint32_t bit = __ffs(f) - 1; f &= f - 1;
-							const int x1 = (int)(wi * 8 + j) + 1, y1 = (int)((bit / A.SL.ws + 1) * plen);
-							const int dg = x1 - y1;
-							clus_add(C, dg - (int)Q.k, dg + (int)Q.k);
+		if (!anyact) continue;
+		// ---- scan: this thread streams chunks [c0, c1) of its lane, one probe per `STRIDE` columns ----
+		const uint32_t L = A.clump_len[c], nchunks = (L + 31) >> 5, ch = (nchunks + 1) >> 1;
+		const uint32_t c0 = h * ch, c1 = min(nchunks, c0 + ch);
+		const uint32_t gs = ch <= 8 ? 0u : 32u - __clz((ch * 4 - 1) >> 5);  // 2^gs words per mask bit
+		const uint4 *lp = A.db + A.clump_off[c] + lane;                    // piece (chunk, lane) at lp[chunk * 16]
+		uint32_t prev = 0, prev2 = 0, mask = 0, wl = 0;
+		if (c0 && c0 < c1) { const uint4 pp = __ldg(lp + (size_t)(c0 - 1) * 16); prev = pp.w; prev2 = pp.z; }
+		uint32_t ambp = amb_nibbles(prev, ADD), ambp2 = amb_nibbles(prev2, ADD);
+		uint4 pc = make_uint4(0, 0, 0, 0);
+		if (c0 < c1) pc = __ldg(lp + (size_t)c0 * 16);
+		for (uint32_t ck = c0; ck < c1; ++ck) {
+			const uint4 cw = pc;
+			if (ck + 1 < c1) pc = __ldg(lp + (size_t)(ck + 1) * 16);
+			const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
+			#pragma unroll
+			for (int j = 0; j < 4; ++j) {
+				const uint32_t cur = ws[j];
+				const uint32_t ambc = amb_nibbles(cur, ADD);
+				const uint32_t h8 = seed_hash(cur, prev & HM);
+				uint32_t hit = bloom_test(bits[h8 >> SHW], h8) | ambc | ambp;
+				if (STRIDE == 4) {
+					const uint32_t h4 = seed_hash(__funnelshift_r(prev, cur, 16), __funnelshift_r(prev2, prev, 16) & HM);
+					hit |= bloom_test(bits[h4 >> SHW], h4) | ambp2;
+				}
+				if (hit) mask |= 1u << (wl >> gs);
+				prev2 = prev; prev = cur; ambp2 = ambp; ambp = ambc; ++wl;
+			}
+		}
+		// ---- verify the flagged words (rare): thread = (query, half of its stretches), lane by lane ----
+		const uint32_t evm = __ballot_sync(0xFFFFFFFFu, mask != 0);
+		uint32_t lanes16 = (evm | (evm >> 16)) & 0xFFFFu;
+		while (lanes16) {
+			const uint32_t l = __ffs(lanes16) - 1; lanes16 &= lanes16 - 1;
+			const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, mask, l), m1 = __shfl_sync(0xFFFFFFFFu, mask, l + 16);
+			Clus C; C.n = 0;
+			#pragma unroll
+			for (int s = 0; s <= CLUS_MAX; ++s) { C.lo[s] = 0; C.hi[s] = 0; }
+			const uint32_t *lw = (const uint32_t *)(A.db + A.clump_off[c] + l);
+			for (uint32_t half = 0; half < 2; ++half) {
+				uint32_t mm = half ? m1 : m0;
+				const uint32_t b0 = half * ch * 4, b1 = min(nchunks, (half + 1) * ch) * 4;
+				while (mm) {
+					const uint32_t s = __ffs(mm) - 1; mm &= mm - 1;
+					for (uint32_t wi = b0 + (s << gs); wi < min(b1, b0 + ((s + 1) << gs)); ++wi) {
+						const uint32_t cur = lane_word(lw, wi), pv = wi >= 1 ? lane_word(lw, wi - 1) : 0u, pv2 = wi >= 2 ? lane_word(lw, wi - 2) : 0u;
+						#pragma unroll
+						for (int e = STRIDE; e <= 8; e += STRIDE) {
+							const uint32_t rn = e == 8 ? cur : __funnelshift_r(pv, cur, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
+							const bool amb = (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD)) != 0;
+							if (act) for_each_window<STRIDE>(Wq, Q.len, Q.k, hh, [&](uint32_t kn, uint32_t ko, uint32_t y1) {
+								bool m = kn == rn && (ko & HM) == ro;
+								if (amb && !m) m = window_matches_table(sM, kn, ko, rn, ro, A.SL.w);
+								if (m) { const int dg = (int)(wi * 8 + e) - (int)y1; clus_add(C, dg - (int)Q.k, dg + (int)Q.k); }
+							});
 						}
 					}
 				}
 			}
+			// the two table halves of a query belong to one (task, lane): fold the upper half's clusters into the lower's
+			const int pn = __shfl_down_sync(0xFFFFFFFFu, C.n, 16);
+			#pragma unroll
+			for (int s = 0; s < CLUS_MAX; ++s) {
+				const int plo = __shfl_down_sync(0xFFFFFFFFu, C.lo[s], 16), phi = __shfl_down_sync(0xFFFFFFFFu, C.hi[s], 16);
+				if (hh == 0 && s < pn) clus_add(C, plo, phi);
+			}
+			if (hh == 0) emit_clusters(C, (uint32_t)(r * BG_RUN_MAX + qi_), l, A.surv, A.surv_cap, A.counters);
 		}
-		// the two halves of a lane belong to one (task, lane): fold the upper half's clusters into the lower's
-		const int pn = __shfl_down_sync(0xFFFFFFFFu, C.n, 16);
-		#pragma unroll
-		for (int s = 0; s < CLUS_MAX; ++s) {
-			const int plo = __shfl_down_sync(0xFFFFFFFFu, C.lo[s], 16), phi = __shfl_down_sync(0xFFFFFFFFu, C.hi[s], 16);
-			if (hh == 0 && s < pn) clus_add(C, plo, phi);
-		}
-		if (hh == 0) emit_clusters(C, (uint32_t)(r * BG_RUN_MAX + qi_), l, A.surv, A.surv_cap, A.counters);
 	}
 }
 
@@ -638,11 +732,13 @@ __global__ void k_work_stats(Work W, const QInfo *__restrict__ qi, const uint32_
 		uint32_t c, q0, n;
 		if (!get_run(W, r, c, q0, n)) continue;
 		const unsigned long long L = clump_len[c];
+		bool seeded = false;
 		for (uint32_t i = 0; i < n; ++i) {
 			const QInfo Q = qi[q0 + i];
 			nominal += 16ull * Q.len * L;
-			if (Q.cls) scells += 16ull * L; else fcells += 16ull * Q.P * L;
+			if (Q.cls) seeded = true; else fcells += 16ull * Q.P * L;
 		}
+		if (seeded) scells += 16ull * L;                         // k_seed streams the clump once per run
 		tasks += n;
 	}
 	for (int o = 16; o; o >>= 1) {
@@ -675,7 +771,8 @@ struct bg_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
-	int seed_filter = 1;
+	int seed_filter = 1, seed_chunk = 8, seed_words = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto)
+	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
 	uint8_t S[256];
 	DBuf<uint32_t> d_sterm;
@@ -684,7 +781,7 @@ struct bg_ctx {
 	uint32_t num_clumps = 0, first_clump = 0;
 	// batch
 	DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
-	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_seq; DBuf<bg_run> d_runs;
+	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
 	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
@@ -693,7 +790,7 @@ struct bg_ctx {
 	int kind = WORK_NONE;
 	uint32_t nq = 0, nslots = 0, ntiles = 0; uint64_t nruns = 0, ntasks = 0;
 	std::vector<uint32_t> task0;                                  // WORK_TASKS: first task index of each run
-	SeedLayout SL = {0, 0, 0, 0, 0}; uint32_t nseed = 0;          // queries taken by k_seed
+	SeedLayout SL = {0, 0, 0, 0, 0, 0}; uint32_t nseed = 0;       // queries taken by k_seed
 	uint32_t surv_cap = 0;
 	int last_mode = 0; std::vector<uint16_t> last_best_in; bool have_best_in = false;
 	bg_stats stats;
@@ -734,7 +831,7 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	c->sms = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
 	for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
-	CU(cudaMallocHost((void **)&c->h_pinned, 64));
+	CU(cudaMallocHost((void **)&c->h_pinned, 256));
 	memset(&c->stats, 0, sizeof(c->stats));
 	bg_default_scoring(1, c->S);
 	*out = c;
@@ -747,7 +844,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	cudaStreamSynchronize(c->stream);
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release();
 	c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
-	c->d_qi.release(); c->d_peq.release(); c->d_seq.release(); c->d_runs.release();
+	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
 	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
@@ -767,6 +864,11 @@ extern "C" int bg_set_stream(bg_ctx *c, void *s) {
 extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 	if (!c) return fail(BG_EINVAL, "null ctx");
 	if (what == BG_PARAM_SEED_FILTER) { c->seed_filter = value != 0; return BG_OK; }
+	if (what == BG_PARAM_SEED_CHUNK) { if (value < 1 || value > 4096) return fail(BG_EINVAL, "bg_set_param: seed chunk %d out of range", value); c->seed_chunk = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_WORDS) {
+		if (value && (value < 128 || value > 8192 || (value & (value - 1)))) return fail(BG_EINVAL, "bg_set_param: seed words %d must be 0 or a power of two in 128..8192", value);
+		c->seed_words = value; return BG_OK;
+	}
 	return fail(BG_EINVAL, "bg_set_param: unknown parameter %d", what);
 }
 
@@ -776,6 +878,17 @@ extern "C" int bg_set_scoring(bg_ctx *c, const uint8_t S[256]) {
 	memcpy(c->S, S, 256);
 	uint32_t st[256];
 	for (int i = 0; i < 256; ++i) st[i] = (uint32_t)S[i] << 22;
+	// What the seed filter needs from the table: plain bases match exactly themselves among plain bases;
+	// which other reference codes can match a plain base for free decides what the scan must always verify.
+	c->seed_ok = true; c->amb_add = 0x22222222u;
+	for (int q = 1; q <= 4; ++q) for (int r = 0; r < 16; ++r) {
+		const bool m = S[q * 16 + r] == 0;
+		if (r >= 1 && r <= 4) { if (m != (q == r)) c->seed_ok = false; }
+		else if (m && r == 0) c->seed_ok = false;
+		else if (m && r == 5) c->amb_add = 0x33333333u;
+	}
+	memset(c->m16, 0, sizeof(c->m16));
+	for (int q = 0; q < 16; ++q) for (int r = 0; r < 16; ++r) if (S[q * 16 + r] == 0) c->m16[q >> 1] |= 1u << (16 * (q & 1) + r);
 	if (c->d_sterm.need(256)) return BG_ENOMEM;
 	CU(cudaMemcpyAsync(c->d_sterm.p, st, sizeof(st), cudaMemcpyHostToDevice, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
@@ -823,17 +936,21 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 	return BG_OK;
 }
 
-// Smallest piece count (<= 4) that covers ~all queries of the batch; 0 = seed filter off.
-static SeedLayout choose_layout(const uint32_t hist[5], uint32_t nq, int enabled) {
-	SeedLayout L = {0, 0, 0, 0, 0};
-	if (!enabled) return L;
-	uint64_t acc = 0; uint32_t np = 0;
-	for (uint32_t p = 0; p < 4; ++p) { acc += hist[p]; if (acc * 20 >= (uint64_t)nq * 19) { np = p + 1; break; } }
-	if (!np) {                                      // most queries need more than 4 pieces: take the ones that fit 4 if they are a fair share
-		if (acc * 4 >= nq) np = 4; else return L;
-	}
-	L.np = np; L.ws = 32 / np; L.w = std::min<uint32_t>(L.ws, 16);
-	for (uint32_t p = 0; p < np; ++p) { L.I |= 1u << (p * L.ws); L.F |= 1u << (p * L.ws + L.w - 1); }
+// Window layout for the batch from the histogram of stretch lengths (plen = len / (k+1), capped at 31):
+// the longest window (<= 16 bases) that ~all seedable queries can afford, probing every 8 columns when
+// that still leaves >= 14 bases, else every 4.
+static SeedLayout choose_layout(const bg_ctx *c, const uint32_t hist[32], uint32_t nq) {
+	SeedLayout L = {0, 0, 0, 0, 0, 0};
+	if (!c->seed_filter || !c->seed_ok) return L;
+	uint64_t total = 0;
+	for (uint32_t p = 11; p < 32; ++p) total += hist[p];
+	if (!total || total * 4 < nq) return L;                      // too few queries could use it
+	uint64_t acc = 0; uint32_t P = 11;
+	for (uint32_t p = 31; p >= 11; --p) { acc += hist[p]; if (acc * 20 >= total * 19) { P = p; break; } }
+	const uint32_t w8 = P >= 15 ? std::min<uint32_t>(16, P - 7) : 0, w4 = std::min<uint32_t>(16, P - 3);
+	if (w8 >= 14) { L.stride = 8; L.w = w8; } else { L.stride = 4; L.w = w4; }
+	L.hm = L.w > 8 ? 0xFFFFFFFFu << (4 * (16 - L.w)) : 0u;
+	L.amb_add = c->amb_add;
 	return L;
 }
 
@@ -845,24 +962,25 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	const uint32_t nq = Q->nq;
 	const uint64_t ncodes = Q->offset[nq];
 	if (c->d_codes.need(ncodes + 16) || c->d_qoff.need(nq + 1) || c->d_budget.need(nq) || c->d_slot.need(nq) || c->d_qi.need(nq) ||
-	    c->d_peq.need((size_t)nq * 16) || c->d_seq.need((size_t)nq * 16) || c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) ||
-	    c->d_counters.need(16) || c->d_cells.need(8)) return BG_ENOMEM;
+	    c->d_peq.need((size_t)nq * 16) || c->d_qnib.need(ncodes / 8 + 3ull * nq + 8) || c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) ||
+	    c->d_counters.need(64) || c->d_cells.need(8)) return BG_ENOMEM;
 	CU(cudaMemcpyAsync(c->d_codes.p, Q->codes, ncodes, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->d_qoff.p, Q->offset, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->d_budget.p, Q->budget, (size_t)nq * 2, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->d_slot.p, Q->slot, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
-	CU(cudaMemsetAsync(c->d_counters.p, 0, 64, c->stream));           // [0..3] counters, [4..8] piece histogram, [9] seed queries
-	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 4, c->d_counters.p);
+	CU(cudaMemsetAsync(c->d_counters.p, 0, 256, c->stream));          // [0..3] counters, [9] seed queries, [16..47] stretch-length histogram
+	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
 	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, c->stream));
+	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
 	if (c->h_pinned[C_ERR]) {
 		uint32_t q = c->h_pinned[C_ERR] - 1;
 		return fail(BG_EINVAL, "bg_batch_upload: query %u is malformed (length %llu, budget %u (max 254, burst.c:3076), slot %u of %u)", q,
 			(unsigned long long)(Q->offset[q + 1] - Q->offset[q]), Q->budget[q], Q->slot[q], Q->nslots);
 	}
-	c->SL = choose_layout(c->h_pinned + 4, nq, c->seed_filter);
-	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->SL, c->d_peq.p, c->d_seq.p, c->d_counters.p + 9);
+	c->SL = choose_layout(c, c->h_pinned + 16, nq);
+	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9);
+	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = Q->nslots;
 	return BG_OK;
@@ -873,6 +991,14 @@ static int finish_upload(bg_ctx *c) {
 	CU(cudaStreamSynchronize(c->stream));     // the caller's host buffers may be reused after this returns
 	if (c->h_pinned[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_batch_upload_runs: run %u is malformed (nq must be 1..%d and query0+nq within the batch)", c->h_pinned[C_ERR] & 0x7FFFFFFF, BG_RUN_MAX); }
 	c->nseed = c->h_pinned[9];
+	if (c->nseed) {
+		// Bloom filter size: ~4 words per window of a full run (16 queries x mean stretches x stride)
+		const uint64_t windows = (uint64_t)BG_RUN_MAX * c->SL.stride * ((c->h_pinned[10] + c->nseed - 1) / c->nseed);
+		uint32_t words = 256;
+		while (words < 4096 && words < 4 * windows) words <<= 1;
+		if (c->seed_words) words = (uint32_t)c->seed_words;
+		c->SL.words = words; c->SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --c->SL.shw;
+	}
 	memset(&c->stats, 0, sizeof(c->stats));
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
 	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
@@ -946,10 +1072,19 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	const Work W = work_of(c);
 	if (c->nruns && c->nseed) {
 		SeedArgs S;
-		S.dbw = (const uint32_t *)c->d_db.p; S.clump_off = c->d_clump_off.p; S.clump_len = c->d_clump_len.p; S.qi = c->d_qi.p;
-		S.seq = c->d_seq.p; S.W = W; S.SL = c->SL; S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
-		const uint64_t blocks = (c->nruns + 3) / 4;
-		k_seed<<<(unsigned)blocks, 128, 0, c->stream>>>(S);
+		S.db = c->d_db.p; S.clump_off = c->d_clump_off.p; S.clump_len = c->d_clump_len.p; S.qi = c->d_qi.p;
+		S.qnib = c->d_qnib.p; S.W = W; S.SL = c->SL; S.nwork = c->nruns; S.chunk = (uint32_t)c->seed_chunk;
+		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
+		memcpy(S.m16, c->m16, sizeof(S.m16));
+		const uint64_t warps = (c->nruns + S.chunk - 1) / S.chunk, blocks = (warps + 3) / 4;
+		const size_t smem = (16 + 4 * (size_t)c->SL.words) * sizeof(uint32_t);
+		if (c->SL.stride == 8) {
+			if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_seed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			k_seed<8><<<(unsigned)blocks, 128, smem, c->stream>>>(S);
+		} else {
+			if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_seed<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+			k_seed<4><<<(unsigned)blocks, 128, smem, c->stream>>>(S);
+		}
 		CU(cudaGetLastError());
 	}
 	if (c->nruns && c->nseed < c->nq) {
@@ -1088,7 +1223,7 @@ extern "C" int bg_batch_stats(bg_ctx *c, bg_stats *out) {
 	CU(cudaStreamSynchronize(c->stream));
 	c->stats.tasks = v[1]; c->stats.nominal_cells = v[2]; c->stats.filter_cells = v[3]; c->stats.seed_steps = v[4];
 	c->stats.survivors = c->h_counters[C_SURV]; c->stats.hits = c->h_counters[C_HITS]; c->stats.band_cells = v[0];
-	c->stats.seed_queries = c->nseed; c->stats.seed_pieces = c->SL.np; c->stats.seed_piece_len = c->SL.w;
+	c->stats.seed_queries = c->nseed; c->stats.seed_stride = c->SL.stride; c->stats.seed_window = c->SL.w; c->stats.seed_words = c->SL.words;
 	cudaEventElapsedTime(&c->stats.ms_filter, c->ev[0], c->ev[1]);
 	cudaEventElapsedTime(&c->stats.ms_extend, c->ev[1], c->ev[2]);
 	cudaEventElapsedTime(&c->stats.ms_select, c->ev[2], c->ev[3]);

@@ -16,7 +16,7 @@ TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
 RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
-PARAM_SEED_FILTER = 1
+PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS = 1, 2, 3
 
 
 class BgQueries(C.Structure):
@@ -28,7 +28,7 @@ class BgStats(C.Structure):
     _fields_ = [("tasks", C.c_uint64), ("nominal_cells", C.c_uint64), ("filter_cells", C.c_uint64),
                 ("seed_steps", C.c_uint64),
                 ("survivors", C.c_uint64), ("band_cells", C.c_uint64), ("hits", C.c_uint64),
-                ("seed_queries", C.c_uint32), ("seed_pieces", C.c_uint32), ("seed_piece_len", C.c_uint32),
+                ("seed_queries", C.c_uint32), ("seed_stride", C.c_uint32), ("seed_window", C.c_uint32), ("seed_words", C.c_uint32),
                 ("ms_filter", C.c_float), ("ms_extend", C.c_float), ("ms_select", C.c_float)]
 
     def asdict(self):
@@ -112,6 +112,9 @@ class Engine:
 
     def set_seed_filter(self, on):
         self._check(self.lib.bg_set_param(self.ctx, PARAM_SEED_FILTER, 1 if on else 0))
+
+    def set_param(self, what, value):
+        self._check(self.lib.bg_set_param(self.ctx, what, value))
 
     def load_db(self, packed, clump_len, first_clump=0):
         packed = np.ascontiguousarray(packed, np.uint8)

@@ -74,12 +74,13 @@ typedef struct {
 	uint64_t tasks;             /* (query, clump) pairs evaluated */
 	uint64_t nominal_cells;     /* sum over tasks of 16 * qlen * ClumpLen */
 	uint64_t filter_cells;      /* DP cells covered by the Myers prefix filter (k_filter) */
-	uint64_t seed_steps;        /* (lane, column) automaton steps of the pigeonhole seed filter (k_seed), per query */
+	uint64_t seed_steps;        /* (lane, column) positions streamed by the pigeonhole seed filter (k_seed), once per run */
 	uint64_t survivors;         /* (task, lane) pairs handed to the banded pass */
 	uint64_t band_cells;        /* DP cells updated by the banded pass (x3 values each) */
 	uint64_t hits;              /* lanes reported */
 	uint32_t seed_queries;      /* queries of the batch taken by k_seed (the rest go through k_filter) */
-	uint32_t seed_pieces, seed_piece_len;    /* automaton layout chosen for the batch */
+	uint32_t seed_stride, seed_window;       /* window layout chosen for the batch: probe every `stride` columns, `window` bases */
+	uint32_t seed_words;                     /* words of the per-warp window filter */
 	float ms_filter, ms_extend, ms_select;   /* device time of the last bg_batch_run */
 } bg_stats;
 
@@ -91,7 +92,9 @@ const char *bg_last_error(void);
 int  bg_set_stream(bg_ctx *ctx, void *cuda_stream);
 
 /* Tuning knobs (results never depend on them). */
-enum { BG_PARAM_SEED_FILTER = 1 };   /* 1 (default): pigeonhole seed filter where the batch allows; 0: Myers prefix filter only */
+enum { BG_PARAM_SEED_FILTER = 1,     /* 1 (default): pigeonhole seed filter where the batch allows; 0: Myers prefix filter only */
+       BG_PARAM_SEED_CHUNK  = 2,     /* consecutive runs handled by one warp of the seed filter (default 8) */
+       BG_PARAM_SEED_WORDS  = 3 };   /* 32-bit words of the per-warp window filter, power of two 128..8192 (0 = sized from the batch) */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),
