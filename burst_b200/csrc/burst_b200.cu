@@ -34,6 +34,7 @@
 #include <stdarg.h>
 #include <algorithm>
 #include <vector>
+#include <type_traits>
 #include "burst_b200.h"
 
 // ---------------------------------------------------------------------------------------------
@@ -110,8 +111,9 @@ __device__ __forceinline__ uint32_t viaddmin(uint32_t a, uint32_t b, uint32_t c)
 // ---------------------------------------------------------------------------------------------
 __global__ void k_relayout(const uint8_t *__restrict__ in, const uint64_t *__restrict__ in_off,
 		const uint64_t *__restrict__ out_off, const uint32_t *__restrict__ clump_len,
-		uint4 *__restrict__ out, uint32_t first, uint64_t in_base) {
+		uint4 *__restrict__ out, uint32_t first, uint64_t in_base, uint32_t *__restrict__ meta_words) {
 	uint32_t c = first + blockIdx.x;
+	uint32_t flags = 0;
 	uint32_t L = clump_len[c], nvec = (L + 1) >> 1, npieces = ((L + 31) >> 5) * 16;
 	const uint8_t *src = in + (in_off[c] - in_base);
 	uint4 *dst = out + out_off[c];
@@ -125,7 +127,14 @@ __global__ void k_relayout(const uint8_t *__restrict__ in, const uint64_t *__res
 			w[j >> 2] |= b << (8 * (j & 3));
 		}
 		dst[p] = make_uint4(w[0], w[1], w[2], w[3]);
+		#pragma unroll
+		for (int j = 0; j < 4; ++j) {
+			const uint32_t ge6 = (((w[j] & 0x77777777u) + 0x22222222u) | w[j]) & 0x88888888u, ge5 = (((w[j] & 0x77777777u) + 0x33333333u) | w[j]) & 0x88888888u;
+			if (ge6) flags |= 1u;
+			if (ge5 ^ ge6) flags |= 2u;                                     // a nibble that is >= 5 but not >= 6
+		}
 	}
+	if (flags) atomicOr(&meta_words[(size_t)c * 4 + 3], flags);            // ClumpMeta.flags (k_seed verifies words holding such codes by table)
 }
 
 // word `wi` (8 columns) of one lane: lanew points at the lane's first piece
@@ -146,7 +155,7 @@ __device__ __forceinline__ uint32_t lane_word(const uint32_t *lanew, uint32_t wi
 //        that row P sits in bit 31; the unused low 32-P bits are set for every code: with Pv = Mv = 0
 //        there they behave as extra copies of the all-zero row 0.
 // ---------------------------------------------------------------------------------------------
-#define SEED_NP_MAX 32
+#define SEED_NP_MAX 32                 // stretches per query the seed filter takes: 64 / stride windows per thread in the hash cache
 // stride: reference windows are probed every `stride` columns (8 = word ends, 4 = also half words, 0 = off);
 // w: window length in bases (8..16); hm: mask of the older word's nibbles inside the window;
 // words: Bloom filter words per warp (power of two), shw = 32 - log2(words);
@@ -181,7 +190,7 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 			W[2 + (j >> 3)] = w;
 		}
 		const uint32_t np = Q.k + 1u, plen = Q.len / np;
-		seed = SL.stride && np <= SEED_NP_MAX && plen >= SL.w + SL.stride - 1;
+		seed = SL.stride && np * SL.stride <= 128 && plen >= SL.w + SL.stride - 1;
 		for (uint32_t p = 0; p < np && seed; ++p) {
 			const uint32_t E = (p + 1) * plen;
 			for (uint32_t i = E - (SL.w + SL.stride - 1); i < E; ++i) { const uint32_t c = s[i] & 15; if (c < 1 || c > 4) { seed = false; break; } }
@@ -189,8 +198,8 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 		qi[q].cls = seed;
 		if (seed) nst = np;
 	}
-	const uint32_t m = __ballot_sync(0xFFFFFFFFu, seed), tot = __reduce_add_sync(0xFFFFFFFFu, nst);
-	if (m && (threadIdx.x & 31) == 0) { atomicAdd(nseed, (uint32_t)__popc(m)); atomicAdd(nseed + 1, tot); }   // seeded queries, their stretches
+	const uint32_t m = __ballot_sync(0xFFFFFFFFu, seed), tot = __reduce_add_sync(0xFFFFFFFFu, nst), mx = __reduce_max_sync(0xFFFFFFFFu, nst);
+	if (m && (threadIdx.x & 31) == 0) { atomicAdd(nseed, (uint32_t)__popc(m)); atomicAdd(nseed + 1, tot); atomicMax(nseed + 2, mx); }   // seeded queries, their stretches (sum, max)
 }
 
 __global__ void k_qtables(const uint8_t *__restrict__ codes, const QInfo *__restrict__ qi, const uint32_t *__restrict__ Sterm,
@@ -265,10 +274,13 @@ __device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_
 // Reference codes that can match a plain base without being equal to it (IUPAC codes, N under -y)
 // bypass the filter: their words are always flagged and verified through the scoring table.
 // ---------------------------------------------------------------------------------------------
+// One record per clump for k_seed: a single 16-byte load instead of two dependent ones.
+struct ClumpMeta { uint64_t off; uint32_t len; uint32_t flags; };   // off in uint4 units; flags: 1 = some code >= 6, 2 = some code == 5
 struct SeedArgs {
-	const uint4 *db; const uint64_t *clump_off; const uint32_t *clump_len;
+	const uint4 *db; const ClumpMeta *meta;
 	const QInfo *qi; const uint32_t *qnib; Work W; SeedLayout SL;
 	uint64_t nwork; uint32_t chunk;                 // run indices to enumerate, runs per warp
+	uint32_t wpt, stage;                            // windows per thread kept in the hash cache; bytes per staging buffer (0 = none)
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;
 	uint32_t m16[8];                                // match sets: bit r of half-word q = (S[q][r] == 0)
 };
@@ -285,22 +297,36 @@ __device__ __forceinline__ bool get_work(const Work &W, uint64_t i, uint64_t &r,
 #define HASH_C1 0x9E3779B1u
 #define HASH_C2 0x85EBCA77u
 __device__ __forceinline__ uint32_t seed_hash(uint32_t newer, uint32_t older_masked) { return newer * HASH_C1 + older_masked * HASH_C2; }
-__device__ __forceinline__ uint32_t bloom_bits(uint32_t h) { return (1u << ((h >> 15) & 31)) | (1u << ((h >> 10) & 31)); }
-__device__ __forceinline__ uint32_t bloom_test(uint32_t word, uint32_t h) { return (word >> ((h >> 15) & 31)) & (word >> ((h >> 10) & 31)) & 1u; }
+// blocked Bloom filter: word = top bits of the hash, two bit positions from its low ten bits
+__device__ __forceinline__ uint32_t bloom_bits(uint32_t h) { return (1u << (h & 31)) | (1u << ((h >> 5) & 31)); }
+__device__ __forceinline__ uint32_t bloom_test(uint32_t word, uint32_t h) { return (word >> (h & 31)) & (word >> ((h >> 5) & 31)) & 1u; }
 __device__ __forceinline__ uint32_t amb_nibbles(uint32_t w, uint32_t add) { return (((w & 0x77777777u) + add) | w) & 0x88888888u; }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr)); return v; }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr)); return v; }
 
-// The windows of one query handled by table half hh (stretches hh, hh+2, ..): f(newer 8 bases, older 8 bases, end offset).
-template <int STRIDE, typename F>
-__device__ __forceinline__ void for_each_window(const uint32_t *__restrict__ Wq, uint32_t len, uint32_t k, uint32_t hh, F f) {
-	const uint32_t np = k + 1u, plen = len / np;
-	for (uint32_t p = hh; p < np; p += 2) {
-		const uint32_t E = (p + 1) * plen;
-		const uint32_t wI = (E + 8) >> 3, sh = ((E + 8) & 7) * 4;          // bases [E-8, E) start at padded nibble E+8
-		const uint32_t a = __ldg(Wq + wI - 2), b = __ldg(Wq + wI - 1), c = __ldg(Wq + wI), d = __ldg(Wq + wI + 1);
-		const uint32_t r0 = __funnelshift_r(a, b, sh), r1 = __funnelshift_r(b, c, sh), r2 = __funnelshift_r(c, d, sh);
-		#pragma unroll
-		for (int j = 0; j < STRIDE; ++j) f(__funnelshift_l(r1, r2, 4 * j), __funnelshift_l(r0, r1, 4 * j), E - j);
-	}
+// mbarrier + bulk copy (TMA, 1-D): one elected thread arms the barrier with the byte count and issues the copy
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	asm volatile("{\n\t.reg .pred p;\n\tMB_WAIT:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra MB_DONE;\n\tbra MB_WAIT;\n\tMB_DONE:\n\t}" :: "r"(bar), "r"(parity) : "memory");
+}
+
+// Window (p, j) of a query: stretch p ends at offset E = (p+1) * plen; the window's 16 bases end at E - j.
+// Returns the newer 8 bases, the older 8 (unmasked) and the end offset.
+struct QWin { uint32_t kn, ko, y1; };
+struct QStretch { uint32_t r0, r1, r2, E; };
+__device__ __forceinline__ QStretch stretch_of(const uint32_t *__restrict__ Wq, uint32_t plen, uint32_t p) {
+	QStretch S; S.E = (p + 1) * plen;
+	const uint32_t wI = (S.E + 8) >> 3, sh = ((S.E + 8) & 7) * 4;          // bases [E-8, E) start at padded nibble E+8
+	const uint32_t a = __ldg(Wq + wI - 2), b = __ldg(Wq + wI - 1), c = __ldg(Wq + wI), d = __ldg(Wq + wI + 1);
+	S.r0 = __funnelshift_r(a, b, sh); S.r1 = __funnelshift_r(b, c, sh); S.r2 = __funnelshift_r(c, d, sh);
+	return S;
+}
+__device__ __forceinline__ QWin window_of(const QStretch &S, uint32_t j) {
+	QWin w; w.kn = __funnelshift_l(S.r1, S.r2, 4 * j); w.ko = __funnelshift_l(S.r0, S.r1, 4 * j); w.y1 = S.E - j; return w;
 }
 
 // nibble-by-nibble comparison through the match sets (windows holding ambiguous reference codes only)
@@ -312,110 +338,262 @@ __device__ __noinline__ bool window_matches_table(const uint32_t *sM, uint32_t k
 	return true;
 }
 
-template <int STRIDE>
+// Shared memory of one warp, in 32-bit words (every part a multiple of 4 words):
+//   [0, words)                     Bloom filter
+//   [+0, +32*wpt)                  hash cache: H[i * 32 + t] = hash of window i of thread t
+//   [+0, +2*stage/4)               two staging buffers for clumps (bulk copies)
+//   [+0, +96)                      interval list: 32 x (key u64, hi u32)
+//   [+0, +4)                       two mbarriers
+//   [+0, +4)                       list counter
+__host__ __device__ __forceinline__ uint32_t seed_warp_words(uint32_t words, uint32_t wpt, uint32_t stage) { return words + 32 * wpt + 2 * (stage / 4) + 96 + 4 + 4; }
+
+template <int STRIDE, bool FULLW>   // FULLW: 16-base windows (no mask on the older word)
 __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
-	extern __shared__ uint32_t smem[];
+	extern __shared__ __align__(128) uint32_t smem[];
 	uint32_t *sM = smem;                                                   // 16 match sets
 	const uint32_t warp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	uint32_t *bits = smem + 16 + warp * A.SL.words;
+	uint32_t *wbase = smem + 16 + warp * seed_warp_words(A.SL.words, A.wpt, A.stage);
+	uint32_t *bits = wbase, *H = bits + A.SL.words, *stg = H + 32 * A.wpt, *list = stg + 2 * (A.stage / 4);
+	uint32_t *cnt = list + 100;
+	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits), stg_s = (uint32_t)__cvta_generic_to_shared(stg);
+	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(list + 96);
 	if (threadIdx.x < 16) sM[threadIdx.x] = (A.m16[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xFFFFu;
+	if (t == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); *cnt = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 	__syncthreads();
 	const uint64_t i0 = ((uint64_t)blockIdx.x * 4 + warp) * A.chunk, i1 = min(A.nwork, i0 + A.chunk);
+	if (i0 >= i1) return;
 	const uint32_t lane = t & 15, h = t >> 4;                              // scan role: reference lane, half of its chunks
 	const uint32_t qi_ = t & 15, hh = t >> 4;                              // table role: query of the run, half of its stretches
-	const uint32_t HM = A.SL.hm, SHW = A.SL.shw, ADD = A.SL.amb_add;
-	uint32_t cur_q0 = 0xFFFFFFFFu, cur_n = 0;
+	const uint32_t HM = FULLW ? 0xFFFFFFFFu : A.SL.hm, SHW = A.SL.shw, ADD = A.SL.amb_add, ambsel = ADD == 0x33333333u ? 3u : 1u;
+	uint32_t cur_q0 = 0xFFFFFFFFu, cur_n = 0, mycount = 0, plen = 0;
 	QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
 	const uint32_t *Wq = A.qnib;
 	bool act = false, anyact = false;
-	for (uint64_t i = i0; i < i1; ++i) {
-		uint64_t r; uint32_t c, q0, n;
-		if (!get_work(A.W, i, r, c, q0, n)) continue;
+
+	struct Desc { uint64_t r; uint32_t c, q0, n; bool ok; ClumpMeta M; };
+	auto load_desc = [&](uint64_t i, Desc &D) {
+		D.ok = get_work(A.W, i, D.r, D.c, D.q0, D.n);
+		if (D.ok) { const uint4 m = __ldg((const uint4 *)(A.meta + D.c)); D.M.off = (uint64_t)m.x | ((uint64_t)m.y << 32); D.M.len = m.z; D.M.flags = m.w; }
+	};
+	// bulk copy of a clump into staging buffer b (all lanes call; lane 0 issues)
+	auto stage_issue = [&](const Desc &D, uint32_t b) -> bool {
+		const uint32_t bytes = ((D.M.len + 31) >> 5) * 256;
+		if (!D.ok || bytes > A.stage) return false;
+		__syncwarp();                                                      // everyone is done reading buffer b
+		if (t == 0) { mbar_expect_tx(bar_s + 8 * b, bytes); bulk_g2s(stg_s + b * A.stage, A.db + D.M.off, bytes, bar_s + 8 * b); }
+		return true;
+	};
+	Desc cur, nxt;
+	load_desc(i0, cur);
+	bool cur_staged = stage_issue(cur, 0);
+	uint32_t buf = 0, phase = 0;
+
+	for (uint64_t i = i0; i < i1; ++i, cur = nxt, buf ^= 1) {
+		bool nxt_staged = false; nxt.ok = false;
+		if (i + 1 < i1) { load_desc(i + 1, nxt); nxt_staged = stage_issue(nxt, buf ^ 1); }
+		const bool staged = cur_staged; cur_staged = nxt_staged;
+		if (!cur.ok) continue;
+		const uint32_t q0 = cur.q0, n = cur.n;
 		if (q0 != cur_q0 || n != cur_n) {                                  // new bunch: rebuild the window set
 			cur_q0 = q0; cur_n = n;
-			act = false;
+			act = false; mycount = 0;
 			if (qi_ < n) { Q = A.qi[q0 + qi_]; act = Q.cls != 0; }
 			anyact = __any_sync(0xFFFFFFFFu, act);
 			if (anyact) {
 				for (uint32_t w = t * 4; w < A.SL.words; w += 128) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);
 				__syncwarp();
 				if (act) {
+					const uint32_t np = Q.k + 1u;
+					plen = Q.len / np;
 					Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi_);
-					for_each_window<STRIDE>(Wq, Q.len, Q.k, hh, [&](uint32_t kn, uint32_t ko, uint32_t) {
-						const uint32_t hv = seed_hash(kn, ko & HM);
-						atomicOr(&bits[hv >> SHW], bloom_bits(hv));
-					});
+					for (uint32_t p = hh; p < np; p += 2) {
+						const QStretch S = stretch_of(Wq, plen, p);
+						#pragma unroll
+						for (int j = 0; j < STRIDE; ++j) {
+							const QWin w = window_of(S, j);
+							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
+							atomicOr(&bits[hv >> SHW], bloom_bits(hv));
+							H[((mycount + j) >> 2) * 128 + t * 4 + ((mycount + j) & 3)] = hv;
+						}
+						mycount += STRIDE;
+					}
 				}
 				__syncwarp();
 			}
 		}
+		if (staged) { mbar_wait(bar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
 		if (!anyact) continue;
+
 		// ---- scan: this thread streams chunks [c0, c1) of its lane, one probe per `STRIDE` columns ----
-		const uint32_t L = A.clump_len[c], nchunks = (L + 31) >> 5, ch = (nchunks + 1) >> 1;
+		const uint32_t L = cur.M.len, nchunks = (L + 31) >> 5, ch = (nchunks + 1) >> 1;
 		const uint32_t c0 = h * ch, c1 = min(nchunks, c0 + ch);
-		const uint32_t gs = ch <= 8 ? 0u : 32u - __clz((ch * 4 - 1) >> 5);  // 2^gs words per mask bit
-		const uint4 *lp = A.db + A.clump_off[c] + lane;                    // piece (chunk, lane) at lp[chunk * 16]
-		uint32_t prev = 0, prev2 = 0, mask = 0, wl = 0;
-		if (c0 && c0 < c1) { const uint4 pp = __ldg(lp + (size_t)(c0 - 1) * 16); prev = pp.w; prev2 = pp.z; }
-		uint32_t ambp = amb_nibbles(prev, ADD), ambp2 = amb_nibbles(prev2, ADD);
-		uint4 pc = make_uint4(0, 0, 0, 0);
-		if (c0 < c1) pc = __ldg(lp + (size_t)c0 * 16);
-		for (uint32_t ck = c0; ck < c1; ++ck) {
-			const uint4 cw = pc;
-			if (ck + 1 < c1) pc = __ldg(lp + (size_t)(ck + 1) * 16);
-			const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
-			#pragma unroll
-			for (int j = 0; j < 4; ++j) {
-				const uint32_t cur = ws[j];
-				const uint32_t ambc = amb_nibbles(cur, ADD);
-				const uint32_t h8 = seed_hash(cur, prev & HM);
-				uint32_t hit = bloom_test(bits[h8 >> SHW], h8) | ambc | ambp;
-				if (STRIDE == 4) {
-					const uint32_t h4 = seed_hash(__funnelshift_r(prev, cur, 16), __funnelshift_r(prev2, prev, 16) & HM);
-					hit |= bloom_test(bits[h4 >> SHW], h4) | ambp2;
+		const uint32_t gs = ch <= 8 ? 0u : max(2u, 32u - __clz((ch * 4 - 1) >> 5));   // 2^gs words per mask bit
+		const bool amb_on = (cur.M.flags & ambsel) != 0;
+		const uint4 *gp = A.db + cur.M.off;                                // piece (chunk, lane) at gp[chunk * 16 + lane]
+		const uint32_t sp = stg_s + buf * A.stage;
+		auto piece = [&](uint32_t ck, uint32_t l) -> uint4 { return staged ? lds128(sp + (ck * 16 + l) * 16) : __ldg(gp + (size_t)ck * 16 + l); };
+		auto word_at = [&](uint32_t l, uint32_t wi) -> uint32_t {
+			return staged ? lds32(sp + ((wi >> 2) * 16 + l) * 16 + (wi & 3) * 4) : __ldg((const uint32_t *)(gp + (size_t)(wi >> 2) * 16 + l) + (wi & 3));
+		};
+		uint32_t mask = 0;
+		auto scan = [&](auto staged_c, auto amb_c) {
+			constexpr bool ST = decltype(staged_c)::value, AMB = decltype(amb_c)::value;
+			auto ld = [&](uint32_t ck) -> uint4 { return ST ? lds128(sp + (ck * 16 + lane) * 16) : __ldg(gp + (size_t)ck * 16 + lane); };
+			uint32_t prev = 0, prev2 = 0;
+			if (c0 && c0 < c1) { const uint4 pp = ld(c0 - 1); prev = pp.w; prev2 = pp.z; }
+			uint32_t ambp = AMB ? amb_nibbles(prev, ADD) : 0u, ambp2 = AMB ? amb_nibbles(prev2, ADD) : 0u;
+			uint4 pc = make_uint4(0, 0, 0, 0);
+			if (c0 < c1) pc = ld(c0);
+			for (uint32_t ck = c0; ck < c1; ++ck) {
+				const uint4 cw = pc;
+				if (!ST && ck + 1 < c1) pc = ld(ck + 1);
+				const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
+				uint32_t m4 = 0;
+				#pragma unroll
+				for (int j = 0; j < 4; ++j) {
+					const uint32_t cu = ws[j];
+					const uint32_t h8 = seed_hash(cu, prev & HM);
+					uint32_t hit = bloom_test(lds32(bits_s + ((h8 >> SHW) << 2)), h8);
+					if (STRIDE == 4) {
+						const uint32_t h4 = seed_hash(__funnelshift_r(prev, cu, 16), __funnelshift_r(prev2, prev, 16) & HM);
+						hit |= bloom_test(lds32(bits_s + ((h4 >> SHW) << 2)), h4);
+					}
+					if (AMB) {
+						const uint32_t ambc = amb_nibbles(cu, ADD);
+						if (ambc | ambp | (STRIDE == 4 ? ambp2 : 0u)) hit = 1;
+						ambp2 = ambp; ambp = ambc;
+					}
+					m4 |= hit << j;
+					prev2 = prev; prev = cu;
 				}
-				if (hit) mask |= 1u << (wl >> gs);
-				prev2 = prev; prev = cur; ambp2 = ambp; ambp = ambc; ++wl;
+				if (ST && ck + 1 < c1) pc = ld(ck + 1);
+				const uint32_t rel = (ck - c0) * 4;
+				mask |= (gs ? (uint32_t)(m4 != 0) : m4) << (rel >> gs);
 			}
-		}
-		// ---- verify the flagged words (rare): thread = (query, half of its stretches), lane by lane ----
+		};
+		if (staged) { if (amb_on) scan(std::true_type{}, std::true_type{}); else scan(std::true_type{}, std::false_type{}); }
+		else        { if (amb_on) scan(std::false_type{}, std::true_type{}); else scan(std::false_type{}, std::false_type{}); }
+
+		// ---- verify the flagged words (rare), lane by lane: thread = (query, half of its stretches) ----
 		const uint32_t evm = __ballot_sync(0xFFFFFFFFu, mask != 0);
 		uint32_t lanes16 = (evm | (evm >> 16)) & 0xFFFFu;
 		while (lanes16) {
 			const uint32_t l = __ffs(lanes16) - 1; lanes16 &= lanes16 - 1;
 			const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, mask, l), m1 = __shfl_sync(0xFFFFFFFFu, mask, l + 16);
-			Clus C; C.n = 0;
-			#pragma unroll
-			for (int s = 0; s <= CLUS_MAX; ++s) { C.lo[s] = 0; C.hi[s] = 0; }
-			const uint32_t *lw = (const uint32_t *)(A.db + A.clump_off[c] + l);
+			// this thread's current interval of seed diagonals, and the hull of all of them
+			int clo = 1, chi = 0, hlo = INT32_MAX, hhi = INT32_MIN;
+			auto push = [&](int lo, int hi) {
+				const uint32_t ix = atomicAdd(cnt, 1u);
+				if (ix < 32) { list[ix * 2] = (uint32_t)lo + 0x80000000u; list[ix * 2 + 1] = qi_; list[64 + ix] = (uint32_t)hi; }
+			};
+			auto seed = [&](int dg) {
+				const int lo = dg - (int)Q.k, hi = dg + (int)Q.k;
+				hlo = min(hlo, lo); hhi = max(hhi, hi);
+				if (clo > chi) { clo = lo; chi = hi; }
+				else if (lo <= chi + 1 && hi >= clo - 1) { clo = min(clo, lo); chi = max(chi, hi); }
+				else { push(clo, chi); clo = lo; chi = hi; }
+			};
 			for (uint32_t half = 0; half < 2; ++half) {
 				uint32_t mm = half ? m1 : m0;
 				const uint32_t b0 = half * ch * 4, b1 = min(nchunks, (half + 1) * ch) * 4;
 				while (mm) {
 					const uint32_t s = __ffs(mm) - 1; mm &= mm - 1;
 					for (uint32_t wi = b0 + (s << gs); wi < min(b1, b0 + ((s + 1) << gs)); ++wi) {
-						const uint32_t cur = lane_word(lw, wi), pv = wi >= 1 ? lane_word(lw, wi - 1) : 0u, pv2 = wi >= 2 ? lane_word(lw, wi - 2) : 0u;
+						const uint32_t cu = word_at(l, wi), pv = wi >= 1 ? word_at(l, wi - 1) : 0u, pv2 = (STRIDE == 4 && wi >= 2) ? word_at(l, wi - 2) : 0u;
 						#pragma unroll
 						for (int e = STRIDE; e <= 8; e += STRIDE) {
-							const uint32_t rn = e == 8 ? cur : __funnelshift_r(pv, cur, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
-							const bool amb = (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD)) != 0;
-							if (act) for_each_window<STRIDE>(Wq, Q.len, Q.k, hh, [&](uint32_t kn, uint32_t ko, uint32_t y1) {
-								bool m = kn == rn && (ko & HM) == ro;
-								if (amb && !m) m = window_matches_table(sM, kn, ko, rn, ro, A.SL.w);
-								if (m) { const int dg = (int)(wi * 8 + e) - (int)y1; clus_add(C, dg - (int)Q.k, dg + (int)Q.k); }
-							});
+							const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
+							const int x1 = (int)(wi * 8 + e);
+							if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window, through the table
+								for (uint32_t iw = 0; iw < mycount; ++iw) {
+									const QWin w = window_of(stretch_of(Wq, plen, hh + 2 * (iw / STRIDE)), iw % STRIDE);
+									if (window_matches_table(sM, w.kn, w.ko & HM, rn, ro, A.SL.w)) seed(x1 - (int)w.y1);
+								}
+							} else {
+								const uint32_t hv = seed_hash(rn, ro);
+								for (uint32_t i4 = 0; i4 < mycount; i4 += 4) {
+									const uint4 hq = *(const uint4 *)(H + i4 * 32 + t * 4);
+									if (hq.x != hv && hq.y != hv && hq.z != hv && hq.w != hv) continue;
+									const uint32_t hs[4] = {hq.x, hq.y, hq.z, hq.w};
+									for (uint32_t u = 0; u < 4 && i4 + u < mycount; ++u) if (hs[u] == hv) {
+										const uint32_t iw = i4 + u;
+										const QWin w = window_of(stretch_of(Wq, plen, hh + 2 * (iw / STRIDE)), iw % STRIDE);
+										if (w.kn == rn && (w.ko & HM) == ro) seed(x1 - (int)w.y1);
+									}
+								}
+							}
 						}
 					}
 				}
 			}
-			// the two table halves of a query belong to one (task, lane): fold the upper half's clusters into the lower's
-			const int pn = __shfl_down_sync(0xFFFFFFFFu, C.n, 16);
-			#pragma unroll
-			for (int s = 0; s < CLUS_MAX; ++s) {
-				const int plo = __shfl_down_sync(0xFFFFFFFFu, C.lo[s], 16), phi = __shfl_down_sync(0xFFFFFFFFu, C.hi[s], 16);
-				if (hh == 0 && s < pn) clus_add(C, plo, phi);
+			if (clo <= chi) push(clo, chi);
+			__syncwarp();
+			const uint32_t nl = *cnt;
+			unsigned long long key = ~0ull; uint32_t vhi = 0;
+			if (t < nl) { key = ((unsigned long long)list[t * 2 + 1] << 32) | list[t * 2]; vhi = list[64 + t]; }
+			__syncwarp();
+			if (t == 0) *cnt = 0;
+			__syncwarp();
+			if (!nl) continue;
+			uint32_t emit = 0, grpcnt = 0; int lo = 0, hi = 0, q = 0;
+			if (nl == 1) {                                                     // the usual case: one interval, nothing to merge
+				q = (int)(key >> 32); lo = (int)((uint32_t)key - 0x80000000u); hi = (int)vhi;
+				emit = t == 0; grpcnt = 1;
+			} else if (nl <= 32) {
+				// sort the intervals by (query, lo); a cluster starts where lo exceeds every earlier hi of the query by more than 1
+				{
+					#pragma unroll
+					for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
+						#pragma unroll
+						for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+							const unsigned long long ok = __shfl_xor_sync(0xFFFFFFFFu, key, j2);
+							const uint32_t oh = __shfl_xor_sync(0xFFFFFFFFu, vhi, j2);
+							const bool takemin = ((t & k2) == 0) == ((t & j2) == 0);
+							if (takemin ? ok < key : ok > key) { key = ok; vhi = oh; }
+						}
+					}
+				}
+				const bool valid = t < nl;
+				q = (int)(key >> 32); lo = (int)((uint32_t)key - 0x80000000u); hi = (int)vhi;
+				const int pq = __shfl_up_sync(0xFFFFFFFFu, q, 1);
+				const bool newg = valid && (t == 0 || q != pq);
+				const uint32_t G = __ballot_sync(0xFFFFFFFFu, newg);
+				const uint32_t gstart = valid ? 31u - __clz(G & (0xFFFFFFFFu >> (31 - t))) : 0u;
+				int pm = hi;                                                   // prefix max of hi within the query's segment
+				#pragma unroll
+				for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, pm, o); if (t >= gstart + o) pm = max(pm, v); }
+				const int ppm = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
+				const bool brk = valid && (newg || lo > ppm + 1);
+				const uint32_t B = __ballot_sync(0xFFFFFFFFu, brk);
+				const uint32_t nb = t < 31 ? B & (0xFFFFFFFFu << (t + 1)) : 0u, ng = t < 31 ? G & (0xFFFFFFFFu << (t + 1)) : 0u;
+				const uint32_t ce = nb ? __ffs(nb) - 2 : nl - 1, ge = ng ? __ffs(ng) - 1 : nl;     // last interval of the cluster, end of the group
+				const int chiv = __shfl_sync(0xFFFFFFFFu, pm, ce), ghiv = __shfl_sync(0xFFFFFFFFu, pm, ge - 1);
+				const uint32_t gc = __popc(B & (ge >= 32 ? 0xFFFFFFFFu : (1u << ge) - 1) & (0xFFFFFFFFu << t));
+				const uint32_t mygc = __shfl_sync(0xFFFFFFFFu, gc, gstart);
+				if (brk) {
+					if (mygc <= 15) { emit = 1; hi = chiv; grpcnt = newg ? mygc : 0; }
+					else if (newg) { emit = 1; hi = ghiv; grpcnt = 1; }        // too many clusters for one lane: one hull
+				}
+			} else {
+				// more intervals than the list holds: one hull per (query, lane) from the two halves' hulls
+				const int olo = __shfl_down_sync(0xFFFFFFFFu, hlo, 16), ohi = __shfl_down_sync(0xFFFFFFFFu, hhi, 16);
+				lo = min(hlo, olo); hi = max(hhi, ohi); q = (int)qi_;
+				if (hh == 0 && lo <= hi) { emit = 1; grpcnt = 1; }
 			}
-			if (hh == 0) emit_clusters(C, (uint32_t)(r * BG_RUN_MAX + qi_), l, A.surv, A.surv_cap, A.counters);
+			const uint32_t E = __ballot_sync(0xFFFFFFFFu, emit);
+			if (!E) continue;
+			uint32_t base = 0;
+			if (t == 0) base = atomicAdd(&A.counters[C_SURV], (uint32_t)__popc(E));
+			base = __shfl_sync(0xFFFFFFFFu, base, 0);
+			if (emit) {
+				const uint32_t slot = base + __popc(E & ((1u << t) - 1)), W = (uint32_t)(hi - lo + 1);
+				uint32_t scratch = 0;
+				if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+				if (slot < A.surv_cap) {
+					Surv v; v.task = (uint32_t)(cur.r * BG_RUN_MAX) + (uint32_t)q; v.lo = lo; v.w_lane = (W << 8) | (grpcnt << 4) | l; v.scratch = scratch;
+					A.surv[slot] = v;
+				}
+			}
 		}
 	}
 }
@@ -771,13 +949,15 @@ struct bg_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
-	int seed_filter = 1, seed_chunk = 8, seed_words = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto)
+	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 1;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
+	uint32_t seed_wpt = 0;                                        // windows per thread of the hash cache (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
 	uint8_t S[256];
 	DBuf<uint32_t> d_sterm;
 	// DB
-	DBuf<uint4> d_db; DBuf<uint64_t> d_clump_off; DBuf<uint32_t> d_clump_len;
+	DBuf<uint4> d_db; DBuf<uint64_t> d_clump_off; DBuf<uint32_t> d_clump_len; DBuf<ClumpMeta> d_meta;
+	uint32_t stage_bytes = 0;                                     // k_seed staging buffer: the largest clump, at most 8 KB
 	uint32_t num_clumps = 0, first_clump = 0;
 	// batch
 	DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
@@ -842,7 +1022,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	if (!c) return;
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
-	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release();
+	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
 	c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
 	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
 	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release();
@@ -869,6 +1049,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 		if (value && (value < 128 || value > 8192 || (value & (value - 1)))) return fail(BG_EINVAL, "bg_set_param: seed words %d must be 0 or a power of two in 128..8192", value);
 		c->seed_words = value; return BG_OK;
 	}
+	if (what == BG_PARAM_SEED_STAGE) { c->seed_stage = value != 0; return BG_OK; }
 	return fail(BG_EINVAL, "bg_set_param: unknown parameter %d", what);
 }
 
@@ -908,7 +1089,15 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 	c->num_clumps = num_clumps; c->first_clump = first_clump;
 	c->kind = WORK_NONE;
 	if (c->d_db.need(out_off[num_clumps])) return BG_ENOMEM;
-	if (c->d_clump_off.need(num_clumps + 1) || c->d_clump_len.need(num_clumps)) return BG_ENOMEM;
+	if (c->d_clump_off.need(num_clumps + 1) || c->d_clump_len.need(num_clumps) || c->d_meta.need(num_clumps)) return BG_ENOMEM;
+	{
+		std::vector<ClumpMeta> meta(num_clumps);
+		uint64_t maxb = 0;
+		for (uint32_t i = 0; i < num_clumps; ++i) { meta[i].off = out_off[i]; meta[i].len = clump_len[i]; meta[i].flags = 0; maxb = std::max<uint64_t>(maxb, (out_off[i + 1] - out_off[i]) * 16); }
+		c->stage_bytes = (uint32_t)std::min<uint64_t>(maxb, 8192);
+		CU(cudaMemcpyAsync(c->d_meta.p, meta.data(), (size_t)num_clumps * sizeof(ClumpMeta), cudaMemcpyHostToDevice, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+	}
 	DBuf<uint64_t> d_in_off;
 	if (d_in_off.need(num_clumps + 1)) return BG_ENOMEM;
 	CU(cudaMemcpyAsync(c->d_clump_off.p, out_off.data(), (num_clumps + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -927,7 +1116,7 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 		if (j == i) { stage.release(); d_in_off.release(); return fail(BG_EINVAL, "bg_load_db: clump %u larger than staging", i); }
 		uint64_t bytes = in_off[j] - in_off[i];
 		CU(cudaMemcpyAsync(stage.p, packed + in_off[i], bytes, cudaMemcpyHostToDevice, c->stream));
-		k_relayout<<<j - i, 128, 0, c->stream>>>(stage.p, d_in_off.p, c->d_clump_off.p, c->d_clump_len.p, c->d_db.p, i, in_off[i]);
+		k_relayout<<<j - i, 128, 0, c->stream>>>(stage.p, d_in_off.p, c->d_clump_off.p, c->d_clump_len.p, c->d_db.p, i, in_off[i], (uint32_t *)c->d_meta.p);
 		CU(cudaGetLastError());
 		CU(cudaStreamSynchronize(c->stream));
 		i = j;
@@ -992,12 +1181,13 @@ static int finish_upload(bg_ctx *c) {
 	if (c->h_pinned[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_batch_upload_runs: run %u is malformed (nq must be 1..%d and query0+nq within the batch)", c->h_pinned[C_ERR] & 0x7FFFFFFF, BG_RUN_MAX); }
 	c->nseed = c->h_pinned[9];
 	if (c->nseed) {
-		// Bloom filter size: ~4 words per window of a full run (16 queries x mean stretches x stride)
+		// Bloom filter size: ~2-4 words per window of a full run (16 queries x mean stretches x stride)
 		const uint64_t windows = (uint64_t)BG_RUN_MAX * c->SL.stride * ((c->h_pinned[10] + c->nseed - 1) / c->nseed);
 		uint32_t words = 256;
-		while (words < 4096 && words < 4 * windows) words <<= 1;
+		while (words < 4096 && words < 2 * windows) words <<= 1;
 		if (c->seed_words) words = (uint32_t)c->seed_words;
 		c->SL.words = words; c->SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --c->SL.shw;
+		c->seed_wpt = ((c->h_pinned[11] + 1) / 2) * c->SL.stride;     // a multiple of 4: the cache is read four hashes at a time
 	}
 	memset(&c->stats, 0, sizeof(c->stats));
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
@@ -1072,19 +1262,16 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	const Work W = work_of(c);
 	if (c->nruns && c->nseed) {
 		SeedArgs S;
-		S.db = c->d_db.p; S.clump_off = c->d_clump_off.p; S.clump_len = c->d_clump_len.p; S.qi = c->d_qi.p;
+		S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = c->d_qi.p;
 		S.qnib = c->d_qnib.p; S.W = W; S.SL = c->SL; S.nwork = c->nruns; S.chunk = (uint32_t)c->seed_chunk;
+		S.wpt = c->seed_wpt; S.stage = c->seed_stage ? c->stage_bytes : 0;
 		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 		memcpy(S.m16, c->m16, sizeof(S.m16));
 		const uint64_t warps = (c->nruns + S.chunk - 1) / S.chunk, blocks = (warps + 3) / 4;
-		const size_t smem = (16 + 4 * (size_t)c->SL.words) * sizeof(uint32_t);
-		if (c->SL.stride == 8) {
-			if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_seed<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			k_seed<8><<<(unsigned)blocks, 128, smem, c->stream>>>(S);
-		} else {
-			if (smem > 48 * 1024) CU(cudaFuncSetAttribute(k_seed<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-			k_seed<4><<<(unsigned)blocks, 128, smem, c->stream>>>(S);
-		}
+		const size_t smem = (16 + 4 * (size_t)seed_warp_words(c->SL.words, S.wpt, S.stage)) * sizeof(uint32_t);
+		void (*kern)(SeedArgs) = c->SL.stride == 8 ? (c->SL.w == 16 ? k_seed<8, true> : k_seed<8, false>) : (c->SL.w == 16 ? k_seed<4, true> : k_seed<4, false>);
+		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kern<<<(unsigned)blocks, 128, smem, c->stream>>>(S);
 		CU(cudaGetLastError());
 	}
 	if (c->nruns && c->nseed < c->nq) {

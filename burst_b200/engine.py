@@ -16,7 +16,7 @@ TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
 RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
-PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS = 1, 2, 3
+PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE = 1, 2, 3, 4
 
 
 class BgQueries(C.Structure):

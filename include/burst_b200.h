@@ -94,7 +94,8 @@ int  bg_set_stream(bg_ctx *ctx, void *cuda_stream);
 /* Tuning knobs (results never depend on them). */
 enum { BG_PARAM_SEED_FILTER = 1,     /* 1 (default): pigeonhole seed filter where the batch allows; 0: Myers prefix filter only */
        BG_PARAM_SEED_CHUNK  = 2,     /* consecutive runs handled by one warp of the seed filter (default 8) */
-       BG_PARAM_SEED_WORDS  = 3 };   /* 32-bit words of the per-warp window filter, power of two 128..8192 (0 = sized from the batch) */
+       BG_PARAM_SEED_WORDS  = 3,     /* 32-bit words of the per-warp window filter, power of two 128..8192 (0 = sized from the batch) */
+       BG_PARAM_SEED_STAGE  = 4 };   /* 1 (default): clumps reach the seed filter through bulk copies (TMA) into shared memory; 0: direct loads */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),

@@ -269,22 +269,22 @@ def test_seed_layouts_and_tuning_knobs(eng, oracle):
     """The seed filter's window layouts -- a probe every 8 columns with 16-base windows (100 bp, budget 2),
     every 4 columns with shorter windows (budget 5: stretches of 16 bases) -- under window filters small
     enough to be mostly false positives and odd numbers of runs per warp.  Results never depend on the knobs."""
-    from burst_b200.engine import PARAM_SEED_CHUNK, PARAM_SEED_WORDS
+    from burst_b200.engine import PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE
     rng = np.random.default_rng(37)
     refs = synth.random_refs(16 * 9, 230, rng, jitter=40, iupac_rate=0.002)
     packed, off, clen = synth.pack_clumps(refs)
     try:
         for k, want in ((2, (8, 16)), (3, (8, 16)), (4, (4, 16)), (5, (4, 13)), (6, (4, 11))):
             reads, _ = synth.reads_from_clumps(packed, off, clen, 150, 100, k, rng)
-            for chunk, words in ((8, 0), (1, 128), (5, 256), (64, 4096)):
-                eng.set_param(PARAM_SEED_CHUNK, chunk); eng.set_param(PARAM_SEED_WORDS, words)
+            for chunk, words, stage in ((8, 0, 1), (1, 128, 1), (5, 256, 0), (64, 4096, 1)):
+                eng.set_param(PARAM_SEED_CHUNK, chunk); eng.set_param(PARAM_SEED_WORDS, words); eng.set_param(PARAM_SEED_STAGE, stage)
                 hits, st = check(eng, oracle, packed, off, clen, reads, [k] * len(reads), mode=0)
                 assert (st["seed_stride"], st["seed_window"]) == want, (k, st)
                 assert st["seed_queries"] >= 0.7 * len(reads) and len(hits) >= 100
         eng.set_param(PARAM_SEED_CHUNK, 3); eng.set_param(PARAM_SEED_WORDS, 128)
         check(eng, oracle, packed, off, clen, reads, [6] * len(reads), mode=1)
     finally:
-        eng.set_param(PARAM_SEED_CHUNK, 8); eng.set_param(PARAM_SEED_WORDS, 0)
+        eng.set_param(PARAM_SEED_CHUNK, 8); eng.set_param(PARAM_SEED_WORDS, 0); eng.set_param(PARAM_SEED_STAGE, 1)
 
 
 def test_malformed_input_is_an_error_not_a_crash(eng, oracle):
