@@ -340,12 +340,12 @@ __device__ __noinline__ bool window_matches_table(const uint32_t *sM, uint32_t k
 
 // Shared memory of one warp, in 32-bit words (every part a multiple of 4 words):
 //   [0, words)                     Bloom filter
-//   [+0, +32*wpt)                  hash cache: H[i * 32 + t] = hash of window i of thread t
+//   [+0, +16*wpt)                  tag cache: 16-bit hash tags of each thread's windows, eight per 16-byte group (wpt a multiple of 8)
 //   [+0, +2*stage/4)               two staging buffers for clumps (bulk copies)
 //   [+0, +96)                      interval list: 32 x (key u64, hi u32)
 //   [+0, +4)                       two mbarriers
 //   [+0, +4)                       list counter
-__host__ __device__ __forceinline__ uint32_t seed_warp_words(uint32_t words, uint32_t wpt, uint32_t stage) { return words + 32 * wpt + 2 * (stage / 4) + 96 + 4 + 4; }
+__host__ __device__ __forceinline__ uint32_t seed_warp_words(uint32_t words, uint32_t wpt, uint32_t stage) { return words + 16 * wpt + 2 * (stage / 4) + 96 + 4 + 4; }
 
 template <int STRIDE, bool FULLW>   // FULLW: 16-base windows (no mask on the older word)
 __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 	uint32_t *sM = smem;                                                   // 16 match sets
 	const uint32_t warp = threadIdx.x >> 5, t = threadIdx.x & 31;
 	uint32_t *wbase = smem + 16 + warp * seed_warp_words(A.SL.words, A.wpt, A.stage);
-	uint32_t *bits = wbase, *H = bits + A.SL.words, *stg = H + 32 * A.wpt, *list = stg + 2 * (A.stage / 4);
+	uint32_t *bits = wbase, *H = bits + A.SL.words, *stg = H + 16 * A.wpt, *list = stg + 2 * (A.stage / 4);
 	uint32_t *cnt = list + 100;
 	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits), stg_s = (uint32_t)__cvta_generic_to_shared(stg);
 	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(list + 96);
@@ -413,7 +413,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 							const QWin w = window_of(S, j);
 							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
 							atomicOr(&bits[hv >> SHW], bloom_bits(hv));
-							H[((mycount + j) >> 2) * 128 + t * 4 + ((mycount + j) & 3)] = hv;
+							((uint16_t *)H)[((mycount + j) >> 3) * 256 + t * 8 + ((mycount + j) & 7)] = (uint16_t)(hv >> 16);
 						}
 						mycount += STRIDE;
 					}
@@ -511,12 +511,16 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 								}
 							} else {
 								const uint32_t hv = seed_hash(rn, ro);
-								for (uint32_t i4 = 0; i4 < mycount; i4 += 4) {
-									const uint4 hq = *(const uint4 *)(H + i4 * 32 + t * 4);
-									if (hq.x != hv && hq.y != hv && hq.z != hv && hq.w != hv) continue;
-									const uint32_t hs[4] = {hq.x, hq.y, hq.z, hq.w};
-									for (uint32_t u = 0; u < 4 && i4 + u < mycount; ++u) if (hs[u] == hv) {
-										const uint32_t iw = i4 + u;
+								const uint32_t tag2 = (hv >> 16) * 0x00010001u;                // the window's 16-bit tag in both halves
+								for (uint32_t i8 = 0; i8 < mycount; i8 += 8) {
+									const uint4 hq = *(const uint4 *)(H + i8 * 16 + t * 4);          // eight tags of this thread
+									const uint32_t dx = hq.x ^ tag2, dy = hq.y ^ tag2, dz = hq.z ^ tag2, dw = hq.w ^ tag2;
+									// a zero half-word in any of them?  (v - 0x00010001) & ~v & 0x80008000
+									const uint32_t z = ((dx - 0x00010001u) & ~dx) | ((dy - 0x00010001u) & ~dy) | ((dz - 0x00010001u) & ~dz) | ((dw - 0x00010001u) & ~dw);
+									if (!(z & 0x80008000u)) continue;
+									const uint32_t ds[4] = {dx, dy, dz, dw};
+									for (uint32_t u = 0; u < 8 && i8 + u < mycount; ++u) if (((ds[u >> 1] >> (16 * (u & 1))) & 0xFFFFu) == 0) {
+										const uint32_t iw = i8 + u;
 										const QWin w = window_of(stretch_of(Wq, plen, hh + 2 * (iw / STRIDE)), iw % STRIDE);
 										if (w.kn == rn && (w.ko & HM) == ro) seed(x1 - (int)w.y1);
 									}
@@ -526,7 +530,13 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 					}
 				}
 			}
-			if (clo <= chi) push(clo, chi);
+			{	// the two table halves of a query usually hold the same cluster: fold the upper half's open interval into the lower's
+				const int olo = __shfl_down_sync(0xFFFFFFFFu, clo, 16), ohi = __shfl_down_sync(0xFFFFFFFFu, chi, 16);
+				const bool mine = clo <= chi, theirs = olo <= ohi, join = mine && theirs && olo <= chi + 1 && ohi >= clo - 1;
+				const bool joined = __shfl_up_sync(0xFFFFFFFFu, join, 16);
+				if (hh == 0) { if (join) { clo = min(clo, olo); chi = max(chi, ohi); } if (mine) push(clo, chi); }
+				else if (mine && !joined) push(clo, chi);
+			}
 			__syncwarp();
 			const uint32_t nl = *cnt;
 			unsigned long long key = ~0ull; uint32_t vhi = 0;
@@ -1187,7 +1197,7 @@ static int finish_upload(bg_ctx *c) {
 		while (words < 4096 && words < 2 * windows) words <<= 1;
 		if (c->seed_words) words = (uint32_t)c->seed_words;
 		c->SL.words = words; c->SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --c->SL.shw;
-		c->seed_wpt = ((c->h_pinned[11] + 1) / 2) * c->SL.stride;     // a multiple of 4: the cache is read four hashes at a time
+		c->seed_wpt = (((c->h_pinned[11] + 1) / 2) * c->SL.stride + 7) & ~7u;   // the tag cache is read eight tags at a time
 	}
 	memset(&c->stats, 0, sizeof(c->stats));
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
