@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 // ---------------------------------------------------------------------------------------------
 struct ExtendArgs {
 	const uint32_t *dbw; const uint64_t *clump_off; const uint32_t *clump_len;
-	const uint8_t *codes; const QInfo *qi; Work W;
+	const uint8_t *codes; const uint32_t *qnib; const QInfo *qi; Work W;
 	const Surv *surv; uint32_t surv_cap; const uint32_t *counters;
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
 	uint32_t *scratch; uint32_t scratch_cap;
@@ -741,6 +741,12 @@ __device__ __forceinline__ uint32_t cell(uint32_t diag, uint32_t up, uint32_t le
 	return min(t, inf) & KEY_CLEAR;                          // burst.c:802-803
 }
 
+// Eight consecutive codes of one lane starting at (0-based, possibly negative) column cb, one nibble each;
+// columns outside the clump read as 0 (pad).  Two 32-bit loads; consecutive groups share one.
+__device__ __forceinline__ uint32_t lane_word_or0(const uint32_t *lanew, int wi, int nwords) {
+	return (wi >= 0 && wi < nwords) ? __ldg(lanew + (size_t)(wi >> 2) * 64 + (wi & 3)) : 0u;
+}
+
 template <int WMAX>
 __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	__shared__ uint32_t sS[256];
@@ -755,9 +761,9 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		if (WMAX == 0 ? (W <= 64) : (W > (uint32_t)WMAX || (WMAX > 8 && W <= (uint32_t)WMAX / 2))) continue;
 		uint32_t c, q0, n;
 		get_run(A.W, sv.task >> 4, c, q0, n);
-		const QInfo Q = A.qi[q0 + (sv.task & 15)];
+		const uint32_t qix = q0 + (sv.task & 15);
+		const QInfo Q = A.qi[qix];
 		const uint32_t m = Q.len, L = A.clump_len[c];
-		const uint8_t *qs = A.codes + Q.off;
 		const uint32_t *lanew = A.dbw + A.clump_off[c] * 4 + lane * 4;
 		uint32_t k = Q.k;
 		if (A.mode == BG_MODE_MIN) k = min(k, A.best[Q.slot]);
@@ -766,55 +772,84 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		constexpr int WB = WMAX ? WMAX : 1;
 		const int Wd = WMAX ? WMAX : (int)W;                 // cells per row actually swept
 		uint32_t a[WB];                                      // band, register resident when WMAX > 0
-		uint32_t win[WMAX ? (WMAX + 7) / 8 : 1];             // codes of columns x0 .. x0+WMAX-1, one nibble each
 		uint32_t *g = A.scratch + sv.scratch;                // generic path: band in global scratch
 		if (WMAX == 0 && (uint64_t)sv.scratch + W > A.scratch_cap) { A.res[i].a = 0; continue; }
-
-		// row 0: zero for columns 0..L (burst.c:4052 calloc / 723-725), absent elsewhere
-		if (WMAX) {
-			#pragma unroll
-			for (int d = 0; d < WB; ++d) { const int x = lo + d; a[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
-			#pragma unroll
-			for (int j = 0; j < (WB + 7) / 8; ++j) win[j] = 0;
-			#pragma unroll
-			for (int d = 0; d < WB; ++d) win[d >> 3] |= fetch_code(lanew, (uint32_t)(lo + d - 1), L) << (4 * (d & 7));
-		} else {
-			for (int d = 0; d < Wd; ++d) { const int x = lo + d; g[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
-		}
-
 		bool dead = false;
 		uint32_t y = 1;
-		for (; y <= m; ++y) {
-			const int x0 = (int)y + lo;                      // column (1-based) of band cell 0 in row y
-			const uint32_t *Srow = sS + (qs[y - 1] & 15) * 16;
-			uint32_t rowmin = KEY_NONE, left = inf;
-			if (WMAX) {
-				// slide the code window by one column
-				const uint32_t nc = fetch_code(lanew, (uint32_t)(x0 + WB - 2), L);
+
+		if (WMAX) {
+			// The band slides one column per row, so row y needs exactly one new reference code (column y+lo+WB-1)
+			// and one query code: both are streamed as packed words, one 32-bit load of each per 8 rows
+			// (the query from its nibble-packed copy, the lane from the DB pieces), loaded one group ahead.
+			constexpr int NW = (WB + 7) / 8;
+			uint32_t win[NW];                                // codes of columns x0 .. x0+WB-1, one nibble each
+			const int nwords = (int)((L + 7) >> 3);
+			const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * qix + 2;
+			// row 0: zero for columns 0..L (burst.c:4052 calloc / 723-725), absent elsewhere
+			#pragma unroll
+			for (int d = 0; d < WB; ++d) { const int x = lo + d; a[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
+			// codes of columns lo .. lo+WB-1 (0-based index lo-1 ..): NW unaligned groups of 8
+			int cb = lo - 1;                                 // 0-based column index of the window's first nibble
+			const uint32_t sh = (uint32_t)(cb & 7) * 4;
+			int wi = cb >> 3;                                // arithmetic shift: floor for negative columns too
+			uint32_t w0 = lane_word_or0(lanew, wi, nwords);
+			#pragma unroll
+			for (int j = 0; j < NW; ++j) { const uint32_t w1 = lane_word_or0(lanew, ++wi, nwords); win[j] = __funnelshift_r(w0, w1, sh); w0 = w1; }
+			// w0 = word wi now holds the first codes that enter the window; feed for rows 8g+1..8g+8 = nibbles cb+WB+8g ..
+			uint32_t w1 = lane_word_or0(lanew, ++wi, nwords);
+			uint32_t feed = __funnelshift_r(w0, w1, sh), qw = __ldg(Wq);
+			const uint32_t ngroups = (m + 7) >> 3;
+			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
+				// next group's words (ignored after the last group)
+				w0 = w1; w1 = lane_word_or0(lanew, ++wi, nwords);
+				const uint32_t nfeed = __funnelshift_r(w0, w1, sh), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
 				#pragma unroll
-				for (int j = 0; j < (WB + 7) / 8 - 1; ++j) win[j] = __funnelshift_r(win[j], win[j + 1], 4);
-				win[(WB + 7) / 8 - 1] = (win[(WB + 7) / 8 - 1] >> 4) | (nc << (4 * ((WB - 1) & 7)));
-				if (x0 >= 1 && x0 + WB - 1 <= (int)L) {      // interior row: every cell and predecessor is inside the matrix
+				for (int r = 0; r < 8; ++r) {
+					if (y > m) break;
+					const int x0 = (int)y + lo;              // column (1-based) of band cell 0 in row y
+					const uint32_t *Srow = sS + ((qw >> (4 * r)) & 15) * 16;
+					uint32_t rowmin = KEY_NONE, left = inf;
+					// slide the code window by one column
+					const uint32_t nc = (feed >> (4 * r)) & 15;
 					#pragma unroll
-					for (int d = 0; d < WB; ++d) {
-						const uint32_t st = Srow[(win[d >> 3] >> (4 * (d & 7))) & 15];
-						const uint32_t up = d + 1 < WB ? a[d + 1] : inf;
-						const uint32_t v = cell(a[d], up, left, st, inf);
-						a[d] = v; left = v; rowmin = min(rowmin, v);
+					for (int j = 0; j < NW - 1; ++j) win[j] = __funnelshift_r(win[j], win[j + 1], 4);
+					win[NW - 1] = (win[NW - 1] >> 4) | (nc << (4 * ((WB - 1) & 7)));
+					if (x0 >= 1 && x0 + WB - 1 <= (int)L) {  // interior row: every cell and predecessor is inside the matrix
+						#pragma unroll
+						for (int d = 0; d < WB; ++d) {
+							const uint32_t st = Srow[(win[d >> 3] >> (4 * (d & 7))) & 15];
+							const uint32_t up = d + 1 < WB ? a[d + 1] : inf;
+							const uint32_t v = cell(a[d], up, left, st, inf);
+							a[d] = v; left = v; rowmin = min(rowmin, v);
+						}
+					} else {
+						#pragma unroll
+						for (int d = 0; d < WB; ++d) {
+							const int x = x0 + d;
+							const uint32_t st = Srow[(win[d >> 3] >> (4 * (d & 7))) & 15];
+							const uint32_t up = d + 1 < WB ? a[d + 1] : inf;
+							uint32_t v = cell(a[d], up, left, st, inf);
+							if (x < 0 || x > (int)L) v = inf;
+							else if (x == 0) v = y <= k ? key_col0(y) : inf;
+							a[d] = v; left = v; rowmin = min(rowmin, v);
+						}
 					}
-				} else {
-					#pragma unroll
-					for (int d = 0; d < WB; ++d) {
-						const int x = x0 + d;
-						const uint32_t st = Srow[(win[d >> 3] >> (4 * (d & 7))) & 15];
-						const uint32_t up = d + 1 < WB ? a[d + 1] : inf;
-						uint32_t v = cell(a[d], up, left, st, inf);
-						if (x < 0 || x > (int)L) v = inf;
-						else if (x == 0) v = y <= k ? key_col0(y) : inf;
-						a[d] = v; left = v; rowmin = min(rowmin, v);
-					}
+					if (rowmin >= inf) { dead = true; break; }   // every lane cell > maxED: the reference truncates (burst.c:1062-1065)
+					++y;
 				}
-			} else {
+				if (!dead && (gq & 1) && A.mode == BG_MODE_MIN) {  // every 16 rows: tighten Emac as better hits land (burst.c:4159, 4220)
+					k = min(k, A.best[Q.slot]); inf = (k + 1) << 22;
+				}
+				feed = nfeed; qw = nqw;
+			}
+			if (!dead) y = m + 1;
+		} else {
+			const uint8_t *qs = A.codes + Q.off;
+			for (int d = 0; d < Wd; ++d) { const int x = lo + d; g[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
+			for (; y <= m; ++y) {
+				const int x0 = (int)y + lo;
+				const uint32_t *Srow = sS + (qs[y - 1] & 15) * 16;
+				uint32_t rowmin = KEY_NONE, left = inf;
 				uint32_t diag = g[0];
 				for (int d = 0; d < Wd; ++d) {
 					const int x = x0 + d;
@@ -825,10 +860,8 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					else if (x == 0) v = y <= k ? key_col0(y) : inf;
 					diag = up; g[d] = v; left = v; rowmin = min(rowmin, v);
 				}
-			}
-			if (rowmin >= inf) { dead = true; break; }       // every lane cell > maxED: the reference truncates (burst.c:1062-1065)
-			if ((y & 15) == 0 && A.mode == BG_MODE_MIN) {    // tighten Emac as better hits land (burst.c:4159, 4220)
-				k = min(k, A.best[Q.slot]); inf = (k + 1) << 22;
+				if (rowmin >= inf) { dead = true; break; }
+				if ((y & 15) == 0 && A.mode == BG_MODE_MIN) { k = min(k, A.best[Q.slot]); inf = (k + 1) << 22; }
 			}
 		}
 		cells += (unsigned long long)(dead ? y : m) * (unsigned)Wd;
@@ -1296,11 +1329,11 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	CU(cudaEventRecord(c->ev[1], c->stream));
 	ExtendArgs E;
 	E.dbw = (const uint32_t *)c->d_db.p; E.clump_off = c->d_clump_off.p; E.clump_len = c->d_clump_len.p;
-	E.codes = c->d_codes.p; E.qi = c->d_qi.p; E.W = W;
+	E.codes = c->d_codes.p; E.qnib = c->d_qnib.p; E.qi = c->d_qi.p; E.W = W;
 	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.res = c->d_res.p;
 	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
 	E.band_cells = c->d_cells.p; E.mode = mode;
-	const unsigned g = (unsigned)c->sms * 8;
+	const unsigned g = (unsigned)c->sms * 12;
 	k_extend<8><<<g, 128, 0, c->stream>>>(E);
 	k_extend<16><<<g, 128, 0, c->stream>>>(E);
 	k_extend<32><<<g, 128, 0, c->stream>>>(E);
