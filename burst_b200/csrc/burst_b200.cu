@@ -67,15 +67,17 @@ struct Surv {             // one diagonal cluster of a (task, lane) that survive
 	uint32_t w_lane;      // band width << 8 | clusters-in-group << 4 (first of a group, else 0) | lane
 	uint32_t scratch;     // offset into the global band scratch (generic kernel only)
 };
-struct Res { uint32_t a, b; };   // a = ed | gap_q << 8 | gap_r << 16 | valid << 31 ; b = final_pos
+struct Res { uint32_t a, b, slot; };   // a = ed | gap_q << 8 | gap_r << 16 | valid << 31 ; b = final_pos ; slot of the query
 
 // Where the work list comes from: explicit runs, or all-vs-all tiles (run r = clump r / ntiles,
 // queries 16 * (r % ntiles) ..).
+// q_base / run_base: a slice of a larger batch (pipelined upload) holds queries q_base.. and runs run_base..;
+// run records keep their batch-wide query numbers, task ids carried by survivors and hits are batch-wide.
 struct Work {
-	const bg_run *runs; uint64_t nruns; uint32_t nq, ntiles, first_clump, num_clumps;
+	const bg_run *runs; uint64_t nruns; uint32_t nq, ntiles, first_clump, num_clumps, q_base, run_base;
 };
 __device__ __forceinline__ bool get_run(const Work &W, uint64_t r, uint32_t &c, uint32_t &q0, uint32_t &n) {
-	if (W.runs) { const bg_run R = W.runs[r]; c = R.clump; q0 = R.query0; n = R.nq; }
+	if (W.runs) { const bg_run R = W.runs[r]; c = R.clump; q0 = R.query0 - W.q_base; n = R.nq; }
 	else { c = (uint32_t)(r / W.ntiles) + W.first_clump; q0 = (uint32_t)(r % W.ntiles) * BG_RUN_MAX; n = min((uint32_t)BG_RUN_MAX, W.nq - q0); }
 	c -= W.first_clump;
 	return c < W.num_clumps;                      // other shards' clumps are skipped
@@ -160,22 +162,28 @@ __device__ __forceinline__ uint32_t lane_word(const uint32_t *lanew, uint32_t wi
 // w: window length in bases (8..16); hm: mask of the older word's nibbles inside the window;
 // words: Bloom filter words per warp (power of two), shw = 32 - log2(words);
 // amb_add: 0x2222.. flags reference codes >= 6, 0x3333.. codes >= 5 (N matches for free, -y) as "verify by table".
-struct SeedLayout { uint32_t stride, w, hm, words, shw, amb_add; };
+struct SeedLayout { uint32_t stride, w, hm, words, shw, amb_add, np_max; };   // np_max: most stretches per query the tag cache holds
 
 __global__ void k_qinfo(const uint64_t *__restrict__ off, const uint16_t *__restrict__ budget, const uint32_t *__restrict__ slot,
-		uint32_t nq, uint32_t nslots, QInfo *__restrict__ qi, uint32_t *__restrict__ hist, uint32_t *__restrict__ counters) {
+		uint32_t nq, uint32_t nslots, QInfo *__restrict__ qi, uint32_t *__restrict__ hist, uint32_t *__restrict__ counters, uint64_t base_off) {
+	__shared__ uint32_t sh[32];
+	if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+	__syncthreads();
 	uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-	if (q >= nq) return;
+	if (q < nq) {
 	uint64_t o = off[q], len = off[q + 1] - o;
 	uint32_t k = budget[q], s = slot[q];
-	if (off[q + 1] <= o || len > 0x7FFFFFFFull || k > 254 || s >= nslots) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; s = 0; }
-	QInfo Q; Q.off = o; Q.len = (uint32_t)len; Q.slot = s; Q.k = (uint16_t)k; Q.P = (uint8_t)min((uint64_t)32, len); Q.cls = 0;
+	if (off[q + 1] <= o || o < base_off || len > 0x7FFFFFFFull || k > 254 || s >= nslots) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; s = 0; o = base_off; }
+	QInfo Q; Q.off = o - base_off; Q.len = (uint32_t)len; Q.slot = s; Q.k = (uint16_t)k; Q.P = (uint8_t)min((uint64_t)32, len); Q.cls = 0;
 	qi[q] = Q;
-	if (k + 1 <= SEED_NP_MAX) atomicAdd(&hist[min((uint32_t)len / (k + 1), 31u)], 1u);
+	if (hist && k + 1 <= SEED_NP_MAX) atomicAdd(&sh[min((uint32_t)len / (k + 1), 31u)], 1u);
+	}
+	__syncthreads();
+	if (hist && threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
 __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, uint32_t nq, SeedLayout SL,
-		uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed) {
+		uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed, uint32_t *__restrict__ unseeded) {
 	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
 	bool seed = false; uint32_t nst = 0;
 	if (q < nq) {
@@ -190,7 +198,7 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 			W[2 + (j >> 3)] = w;
 		}
 		const uint32_t np = Q.k + 1u, plen = Q.len / np;
-		seed = SL.stride && np * SL.stride <= 128 && plen >= SL.w + SL.stride - 1;
+		seed = SL.stride && np <= SL.np_max && plen >= SL.w + SL.stride - 1;
 		for (uint32_t p = 0; p < np && seed; ++p) {
 			const uint32_t E = (p + 1) * plen;
 			for (uint32_t i = E - (SL.w + SL.stride - 1); i < E; ++i) { const uint32_t c = s[i] & 15; if (c < 1 || c > 4) { seed = false; break; } }
@@ -200,6 +208,8 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 	}
 	const uint32_t m = __ballot_sync(0xFFFFFFFFu, seed), tot = __reduce_add_sync(0xFFFFFFFFu, nst), mx = __reduce_max_sync(0xFFFFFFFFu, nst);
 	if (m && (threadIdx.x & 31) == 0) { atomicAdd(nseed, (uint32_t)__popc(m)); atomicAdd(nseed + 1, tot); atomicMax(nseed + 2, mx); }   // seeded queries, their stretches (sum, max)
+	const uint32_t u = __ballot_sync(0xFFFFFFFFu, q < nq && !seed);
+	if (unseeded && u && (threadIdx.x & 31) == 0) atomicAdd(unseeded, (uint32_t)__popc(u));
 }
 
 __global__ void k_qtables(const uint8_t *__restrict__ codes, const QInfo *__restrict__ qi, const uint32_t *__restrict__ Sterm,
@@ -208,6 +218,7 @@ __global__ void k_qtables(const uint8_t *__restrict__ codes, const QInfo *__rest
 	uint32_t q = i >> 4, c = i & 15;
 	if (q >= nq) return;
 	QInfo Q = qi[q];
+	if (Q.cls) return;                                       // taken by k_seed: no Myers table needed
 	const uint8_t *s = codes + Q.off;
 	const uint32_t P = Q.P;
 	uint32_t m = P < 32 ? (1u << (32 - P)) - 1 : 0;
@@ -600,7 +611,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 				uint32_t scratch = 0;
 				if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
 				if (slot < A.surv_cap) {
-					Surv v; v.task = (uint32_t)(cur.r * BG_RUN_MAX) + (uint32_t)q; v.lo = lo; v.w_lane = (W << 8) | (grpcnt << 4) | l; v.scratch = scratch;
+					Surv v; v.task = (uint32_t)((cur.r + A.W.run_base) * BG_RUN_MAX) + (uint32_t)q; v.lo = lo; v.w_lane = (W << 8) | (grpcnt << 4) | l; v.scratch = scratch;
 					A.surv[slot] = v;
 				}
 			}
@@ -616,6 +627,7 @@ struct FilterArgs {
 	const QInfo *qi; const uint32_t *peq; Work W;
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;
 	uint32_t c16;        // the constant 16, passed at run time so ptxas keeps IMAD.HI (FMA pipe)
+	const uint32_t *todo; // number of queries k_seed did not take (device; NULL = unknown, run)
 };
 
 // Hyyro's formulation of Myers' bit-vector step; the text character is one reference base.
@@ -635,8 +647,12 @@ __device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
 
 __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	__shared__ uint32_t sPeq[8][16];
+	if (A.todo && *A.todo == 0) return;                           // every query of the batch went to k_seed
 	const uint32_t slot = threadIdx.x >> 4, lane = threadIdx.x & 15;
-	const uint64_t t = (uint64_t)blockIdx.x * 8 + slot;           // task id = run * 16 + query-in-run
+	const uint64_t ngroups = A.W.nruns * 2;                       // 8 task ids per group
+	for (uint64_t grp = blockIdx.x; grp < ngroups; grp += gridDim.x) {
+	__syncwarp();                                                 // the previous group's readers are done with sPeq
+	const uint64_t t = grp * 8 + slot;                            // task id = run * 16 + query-in-run
 	const uint64_t r = t >> 4; const uint32_t qi_ = (uint32_t)t & 15;
 	bool valid = r < A.W.nruns;
 	uint32_t q = 0, c = 0, q0 = 0, n = 0;
@@ -645,7 +661,7 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	if (valid) { Q = A.qi[q]; valid = !Q.cls; }                   // seed-eligible queries were handled by k_seed
 	sPeq[slot][lane] = valid ? A.peq[(size_t)q * 16 + lane] : 0;
 	__syncwarp();
-	if (!valid) return;
+	if (!valid) continue;
 	const int P = Q.P, k = Q.k;
 	const uint32_t L = A.clump_len[c];
 	const uint4 *base = A.db + A.clump_off[c] + lane;
@@ -709,9 +725,10 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 		if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
 		const uint32_t i = atomicAdd(&A.counters[C_SURV], 1u);
 		if (i < A.surv_cap) {
-			Surv s; s.task = (uint32_t)t; s.lo = lo; s.w_lane = (W << 8) | (1u << 4) | lane; s.scratch = scratch;
+			Surv s; s.task = (uint32_t)t + A.W.run_base * BG_RUN_MAX; s.lo = lo; s.w_lane = (W << 8) | (1u << 4) | lane; s.scratch = scratch;
 			A.surv[i] = s;
 		}
+	}
 	}
 }
 
@@ -721,7 +738,7 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 struct ExtendArgs {
 	const uint32_t *dbw; const uint64_t *clump_off; const uint32_t *clump_len;
 	const uint8_t *codes; const uint32_t *qnib; const QInfo *qi; Work W;
-	const Surv *surv; uint32_t surv_cap; const uint32_t *counters;
+	const Surv *surv; uint32_t surv_cap; const uint32_t *counters; const uint32_t *first;   // first: survivors before *first belong to earlier slices
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
 	uint32_t *scratch; uint32_t scratch_cap;
 	unsigned long long *band_cells;
@@ -752,15 +769,15 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	__shared__ uint32_t sS[256];
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) sS[i] = A.Sterm[i];
 	__syncthreads();
-	const uint32_t nsurv = min(A.counters[C_SURV], A.surv_cap);
+	const uint32_t nsurv = min(A.counters[C_SURV], A.surv_cap), first = A.first ? min(*A.first, nsurv) : 0u;
 	unsigned long long cells = 0;
-	for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nsurv; i += gridDim.x * blockDim.x) {
+	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < nsurv; i += gridDim.x * blockDim.x) {
 		const Surv sv = A.surv[i];
 		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 15;
 		// class dispatch: this instantiation takes bands that fit WMAX but not WMAX/2
 		if (WMAX == 0 ? (W <= 64) : (W > (uint32_t)WMAX || (WMAX > 8 && W <= (uint32_t)WMAX / 2))) continue;
 		uint32_t c, q0, n;
-		get_run(A.W, sv.task >> 4, c, q0, n);
+		get_run(A.W, (sv.task >> 4) - A.W.run_base, c, q0, n);
 		const uint32_t qix = q0 + (sv.task & 15);
 		const QInfo Q = A.qi[qix];
 		const uint32_t m = Q.len, L = A.clump_len[c];
@@ -773,7 +790,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		const int Wd = WMAX ? WMAX : (int)W;                 // cells per row actually swept
 		uint32_t a[WB];                                      // band, register resident when WMAX > 0
 		uint32_t *g = A.scratch + sv.scratch;                // generic path: band in global scratch
-		if (WMAX == 0 && (uint64_t)sv.scratch + W > A.scratch_cap) { A.res[i].a = 0; continue; }
+		if (WMAX == 0 && (uint64_t)sv.scratch + W > A.scratch_cap) { Res z; z.a = 0; z.b = 0; z.slot = Q.slot; A.res[i] = z; continue; }
 		bool dead = false;
 		uint32_t y = 1;
 
@@ -886,7 +903,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 				atomicMin(&A.best[Q.slot], ed);
 			}
 		}
-		Res r; r.a = out; r.b = fp;
+		Res r; r.a = out; r.b = fp; r.slot = Q.slot;
 		A.res[i] = r;
 	}
 	if (cells) atomicAdd(A.band_cells, cells);
@@ -898,7 +915,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 // left-to-right scan (burst.c:826-883) keeps the best (score, shift), numGapR of its first
 // occurrence and the column of its last.
 // ---------------------------------------------------------------------------------------------
-__global__ void k_select(const Surv *__restrict__ surv, const Res *__restrict__ res, const QInfo *__restrict__ qi, Work W,
+__global__ void k_select(const Surv *__restrict__ surv, const Res *__restrict__ res,
 		const uint32_t *__restrict__ best, uint32_t *counters, uint32_t surv_cap, bg_hit *__restrict__ hits,
 		unsigned long long *__restrict__ keys, int mode) {
 	const uint32_t nsurv = min(counters[C_SURV], surv_cap);
@@ -916,9 +933,7 @@ __global__ void k_select(const Surv *__restrict__ surv, const Res *__restrict__ 
 		}
 		if (bkey == 0xFFFFFFFFu) continue;
 		const uint32_t ed = bkey >> 8;
-		uint32_t c, q0, n;
-		get_run(W, sv.task >> 4, c, q0, n);
-		if (mode == BG_MODE_MIN && ed != best[qi[q0 + (sv.task & 15)].slot]) continue;     // burst.c:4229, 4497
+		if (mode == BG_MODE_MIN && ed != best[res[i].slot]) continue;     // burst.c:4229, 4497
 		const uint32_t j = atomicAdd(&counters[C_HITS], 1u);
 		bg_hit h; h.task = sv.task; h.lane = (uint8_t)(sv.w_lane & 15); h.ed = (uint8_t)ed;
 		h.gap_q = (uint8_t)(255 - (bkey & 255)); h.gap_r = (uint8_t)gr; h.final_pos = fp;
@@ -939,11 +954,11 @@ __global__ void k_init_best(uint32_t *best, const uint16_t *in, uint32_t n) {
 }
 
 // run validation (explicit run lists): malformed runs raise the error flag
-__global__ void k_check_runs(const bg_run *__restrict__ runs, uint64_t nruns, uint32_t nq, uint32_t *counters) {
+__global__ void k_check_runs(const bg_run *__restrict__ runs, uint64_t nruns, uint32_t q_base, uint32_t nq, uint32_t *counters) {
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
 	if (r >= nruns) return;
 	const bg_run R = runs[r];
-	if (!R.nq || R.nq > BG_RUN_MAX || (uint64_t)R.query0 + R.nq > nq) atomicExch(&counters[C_ERR], 0x80000000u | (uint32_t)min(r, (uint64_t)0x7FFFFFFF));
+	if (!R.nq || R.nq > BG_RUN_MAX || R.query0 < q_base || (uint64_t)R.query0 - q_base + R.nq > nq) atomicExch(&counters[C_ERR], 0x80000000u | (uint32_t)min(r, (uint64_t)0x7FFFFFFF));
 }
 
 // work statistics: nominal = sum over tasks of 16 * qlen * ClumpLen
@@ -988,6 +1003,15 @@ template <typename T> struct DBuf {
 
 enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
 
+// One of two device buffer sets the pipelined one-call path alternates between: while the kernels of one
+// slice run, the next slice's queries and runs are copied in on a second stream.
+struct Slice {
+	DBuf<uint8_t> codes; DBuf<uint64_t> qoff; DBuf<uint16_t> budget; DBuf<uint32_t> slot;
+	DBuf<QInfo> qi; DBuf<uint32_t> peq, qnib; DBuf<bg_run> runs;
+	cudaEvent_t copied = nullptr, computed = nullptr;
+	void release() { codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); peq.release(); qnib.release(); runs.release(); }
+};
+
 struct bg_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr; bool own_stream = false;
@@ -1013,18 +1037,19 @@ struct bg_ctx {
 	int kind = WORK_NONE;
 	uint32_t nq = 0, nslots = 0, ntiles = 0; uint64_t nruns = 0, ntasks = 0;
 	std::vector<uint32_t> task0;                                  // WORK_TASKS: first task index of each run
-	SeedLayout SL = {0, 0, 0, 0, 0, 0}; uint32_t nseed = 0;       // queries taken by k_seed
+	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t nseed = 0;    // queries taken by k_seed
 	uint32_t surv_cap = 0;
 	int last_mode = 0; std::vector<uint16_t> last_best_in; bool have_best_in = false;
 	bg_stats stats;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+	Slice sl[2]; cudaStream_t copy_stream = nullptr; DBuf<uint32_t> d_first; int pipe_slices = 4, pipe_min_runs = 4096, pipe_ratio = 100;   // pipelined one-call path
 	uint32_t h_counters[4] = {0, 0, 0, 0};
 	bool ran = false, sorted = false;
 };
 
 static Work work_of(const bg_ctx *c) {
 	Work W; W.runs = c->kind == WORK_ALL ? nullptr : c->d_runs.p; W.nruns = c->nruns; W.nq = c->nq; W.ntiles = c->ntiles;
-	W.first_clump = c->first_clump; W.num_clumps = c->num_clumps;
+	W.first_clump = c->first_clump; W.num_clumps = c->num_clumps; W.q_base = 0; W.run_base = 0;
 	return W;
 }
 
@@ -1054,6 +1079,8 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	c->sms = prop.multiProcessorCount;
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
 	for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
+	CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+	for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&c->sl[i].copied, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->sl[i].computed, cudaEventDisableTiming)); }
 	CU(cudaMallocHost((void **)&c->h_pinned, 256));
 	memset(&c->stats, 0, sizeof(c->stats));
 	bg_default_scoring(1, c->S);
@@ -1072,6 +1099,9 @@ extern "C" void bg_free(bg_ctx *c) {
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
+	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+	for (int i = 0; i < 2; ++i) { c->sl[i].release(); if (c->sl[i].copied) cudaEventDestroy(c->sl[i].copied); if (c->sl[i].computed) cudaEventDestroy(c->sl[i].computed); }
+	c->d_first.release();
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -1093,6 +1123,9 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 		c->seed_words = value; return BG_OK;
 	}
 	if (what == BG_PARAM_SEED_STAGE) { c->seed_stage = value != 0; return BG_OK; }
+	if (what == BG_PARAM_PIPE_RATIO) { if (value < 10 || value > 100) return fail(BG_EINVAL, "bg_set_param: slice ratio %d out of range 10..100", value); c->pipe_ratio = value; return BG_OK; }
+	if (what == BG_PARAM_PIPE_MIN_RUNS) { if (value < 1) return fail(BG_EINVAL, "bg_set_param: minimum runs per slice %d", value); c->pipe_min_runs = value; return BG_OK; }
+	if (what == BG_PARAM_PIPE_SLICES) { if (value < 0 || value > 64) return fail(BG_EINVAL, "bg_set_param: pipeline slices %d out of range 0..64", value); c->pipe_slices = value; return BG_OK; }
 	return fail(BG_EINVAL, "bg_set_param: unknown parameter %d", what);
 }
 
@@ -1172,7 +1205,7 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 // the longest window (<= 16 bases) that ~all seedable queries can afford, probing every 8 columns when
 // that still leaves >= 14 bases, else every 4.
 static SeedLayout choose_layout(const bg_ctx *c, const uint32_t hist[32], uint32_t nq) {
-	SeedLayout L = {0, 0, 0, 0, 0, 0};
+	SeedLayout L = {0, 0, 0, 0, 0, 0, 0};
 	if (!c->seed_filter || !c->seed_ok) return L;
 	uint64_t total = 0;
 	for (uint32_t p = 11; p < 32; ++p) total += hist[p];
@@ -1182,7 +1215,7 @@ static SeedLayout choose_layout(const bg_ctx *c, const uint32_t hist[32], uint32
 	const uint32_t w8 = P >= 15 ? std::min<uint32_t>(16, P - 7) : 0, w4 = std::min<uint32_t>(16, P - 3);
 	if (w8 >= 14) { L.stride = 8; L.w = w8; } else { L.stride = 4; L.w = w4; }
 	L.hm = L.w > 8 ? 0xFFFFFFFFu << (4 * (16 - L.w)) : 0u;
-	L.amb_add = c->amb_add;
+	L.amb_add = c->amb_add; L.np_max = 128 / L.stride;
 	return L;
 }
 
@@ -1201,7 +1234,7 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	CU(cudaMemcpyAsync(c->d_budget.p, Q->budget, (size_t)nq * 2, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->d_slot.p, Q->slot, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemsetAsync(c->d_counters.p, 0, 256, c->stream));          // [0..3] counters, [9] seed queries, [16..47] stretch-length histogram
-	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
+	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p, 0);
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
@@ -1211,27 +1244,21 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 			(unsigned long long)(Q->offset[q + 1] - Q->offset[q]), Q->budget[q], Q->slot[q], Q->nslots);
 	}
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
-	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9);
+	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = Q->nslots;
 	return BG_OK;
 }
 
+static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &wpt);
+
 static int finish_upload(bg_ctx *c) {
 	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));     // the caller's host buffers may be reused after this returns
 	if (c->h_pinned[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_batch_upload_runs: run %u is malformed (nq must be 1..%d and query0+nq within the batch)", c->h_pinned[C_ERR] & 0x7FFFFFFF, BG_RUN_MAX); }
 	c->nseed = c->h_pinned[9];
-	if (c->nseed) {
-		// Bloom filter size: ~2-4 words per window of a full run (16 queries x mean stretches x stride)
-		const uint64_t windows = (uint64_t)BG_RUN_MAX * c->SL.stride * ((c->h_pinned[10] + c->nseed - 1) / c->nseed);
-		uint32_t words = 256;
-		while (words < 4096 && words < 2 * windows) words <<= 1;
-		if (c->seed_words) words = (uint32_t)c->seed_words;
-		c->SL.words = words; c->SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --c->SL.shw;
-		c->seed_wpt = (((c->h_pinned[11] + 1) / 2) * c->SL.stride + 7) & ~7u;   // the tag cache is read eight tags at a time
-	}
+	if (c->nseed) seed_sizes(c, c->SL, (c->h_pinned[10] + c->nseed - 1) / c->nseed, c->h_pinned[11], c->seed_wpt);
 	memset(&c->stats, 0, sizeof(c->stats));
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
 	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
@@ -1251,7 +1278,7 @@ extern "C" int bg_batch_upload_runs(bg_ctx *c, const bg_queries *Q, const bg_run
 	int rc = upload_queries(c, Q); if (rc) return rc;
 	if (c->d_runs.need(nruns + 1)) return BG_ENOMEM;
 	CU(cudaMemcpyAsync(c->d_runs.p, runs, nruns * sizeof(bg_run), cudaMemcpyHostToDevice, c->stream));
-	if (nruns) k_check_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, c->stream>>>(c->d_runs.p, nruns, c->nq, c->d_counters.p);
+	if (nruns) k_check_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, c->stream>>>(c->d_runs.p, nruns, 0, c->nq, c->d_counters.p);
 	CU(cudaGetLastError());
 	c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = nruns * BG_RUN_MAX; c->ntiles = 0;
 	return finish_upload(c);
@@ -1291,6 +1318,63 @@ extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *ta
 	return finish_upload(c);                                      // synchronises: `runs` may go out of scope
 }
 
+// Device view of one uploaded batch (or one slice of a pipelined one).
+struct BatchDev { const uint8_t *codes; const uint32_t *qnib, *peq; const QInfo *qi; Work W; };
+
+static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &wpt) {
+	// Bloom filter size: ~2-4 words per window of a full run (16 queries x mean stretches x stride)
+	const uint64_t windows = (uint64_t)BG_RUN_MAX * SL.stride * stretches_mean;
+	uint32_t words = 256;
+	while (words < 4096 && words < 2 * windows) words <<= 1;
+	if (c->seed_words) words = (uint32_t)c->seed_words;
+	SL.words = words; SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --SL.shw;
+	wpt = (((stretches_max + 1) / 2) * SL.stride + 7) & ~7u;          // the tag cache is read eight tags at a time
+}
+
+static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t wpt, bool seed, bool filter, const uint32_t *todo) {
+	if (B.W.nruns && seed) {
+		SeedArgs S;
+		S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = B.qi;
+		S.qnib = B.qnib; S.W = B.W; S.SL = SL; S.nwork = B.W.nruns; S.chunk = (uint32_t)c->seed_chunk;
+		S.wpt = wpt; S.stage = c->seed_stage ? c->stage_bytes : 0;
+		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
+		memcpy(S.m16, c->m16, sizeof(S.m16));
+		const uint64_t warps = (B.W.nruns + S.chunk - 1) / S.chunk, blocks = (warps + 3) / 4;
+		const size_t smem = (16 + 4 * (size_t)seed_warp_words(SL.words, S.wpt, S.stage)) * sizeof(uint32_t);
+		void (*kern)(SeedArgs) = SL.stride == 8 ? (SL.w == 16 ? k_seed<8, true> : k_seed<8, false>) : (SL.w == 16 ? k_seed<4, true> : k_seed<4, false>);
+		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		kern<<<(unsigned)blocks, 128, smem, st>>>(S);
+		CU(cudaGetLastError());
+	}
+	if (B.W.nruns && filter) {
+		FilterArgs F;
+		F.db = c->d_db.p; F.clump_off = c->d_clump_off.p; F.clump_len = c->d_clump_len.p; F.qi = B.qi;
+		F.peq = B.peq; F.W = B.W; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap; F.counters = c->d_counters.p; F.c16 = 16;
+		F.todo = todo;
+		const uint64_t blocks = std::min<uint64_t>(B.W.nruns * 2, (uint64_t)c->sms * 16);   // 8 task ids per group, groups strided over a resident grid
+		k_filter<<<(unsigned)blocks, 128, 0, st>>>(F);
+		CU(cudaGetLastError());
+	}
+	return BG_OK;
+}
+
+static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode, const uint32_t *first) {
+	ExtendArgs E;
+	E.dbw = (const uint32_t *)c->d_db.p; E.clump_off = c->d_clump_off.p; E.clump_len = c->d_clump_len.p;
+	E.codes = B.codes; E.qnib = B.qnib; E.qi = B.qi; E.W = B.W;
+	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.first = first; E.res = c->d_res.p;
+	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
+	E.band_cells = c->d_cells.p; E.mode = mode;
+	const unsigned g = (unsigned)c->sms * 12;
+	k_extend<8><<<g, 128, 0, st>>>(E);
+	k_extend<16><<<g, 128, 0, st>>>(E);
+	k_extend<32><<<g, 128, 0, st>>>(E);
+	k_extend<64><<<g, 128, 0, st>>>(E);
+	k_extend<0><<<g, 128, 0, st>>>(E);
+	CU(cudaGetLastError());
+	return BG_OK;
+}
+
 static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	CU(cudaSetDevice(c->device));
 	c->last_mode = mode; c->have_best_in = best_in != nullptr;
@@ -1302,51 +1386,17 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	CU(cudaMemsetAsync(c->d_counters.p, 0, 16, c->stream));
 	CU(cudaMemsetAsync(c->d_cells.p, 0, 8, c->stream));
 	CU(cudaEventRecord(c->ev[0], c->stream));
-	const Work W = work_of(c);
-	if (c->nruns && c->nseed) {
-		SeedArgs S;
-		S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = c->d_qi.p;
-		S.qnib = c->d_qnib.p; S.W = W; S.SL = c->SL; S.nwork = c->nruns; S.chunk = (uint32_t)c->seed_chunk;
-		S.wpt = c->seed_wpt; S.stage = c->seed_stage ? c->stage_bytes : 0;
-		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
-		memcpy(S.m16, c->m16, sizeof(S.m16));
-		const uint64_t warps = (c->nruns + S.chunk - 1) / S.chunk, blocks = (warps + 3) / 4;
-		const size_t smem = (16 + 4 * (size_t)seed_warp_words(c->SL.words, S.wpt, S.stage)) * sizeof(uint32_t);
-		void (*kern)(SeedArgs) = c->SL.stride == 8 ? (c->SL.w == 16 ? k_seed<8, true> : k_seed<8, false>) : (c->SL.w == 16 ? k_seed<4, true> : k_seed<4, false>);
-		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kern<<<(unsigned)blocks, 128, smem, c->stream>>>(S);
-		CU(cudaGetLastError());
-	}
-	if (c->nruns && c->nseed < c->nq) {
-		FilterArgs F;
-		F.db = c->d_db.p; F.clump_off = c->d_clump_off.p; F.clump_len = c->d_clump_len.p; F.qi = c->d_qi.p;
-		F.peq = c->d_peq.p; F.W = W; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap; F.counters = c->d_counters.p; F.c16 = 16;
-		const uint64_t blocks = c->nruns * 2;                     // 8 task ids per block
-		if (blocks > 0x7FFFFFFFull) return fail(BG_EINVAL, "too many tasks for one launch");
-		k_filter<<<(unsigned)blocks, 128, 0, c->stream>>>(F);
-		CU(cudaGetLastError());
-	}
+	BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.peq = c->d_peq.p; B.qi = c->d_qi.p; B.W = work_of(c);
+	int rc = launch_filters(c, c->stream, B, c->SL, c->seed_wpt, c->nseed != 0, c->nseed < c->nq, nullptr); if (rc) return rc;
 	CU(cudaEventRecord(c->ev[1], c->stream));
-	ExtendArgs E;
-	E.dbw = (const uint32_t *)c->d_db.p; E.clump_off = c->d_clump_off.p; E.clump_len = c->d_clump_len.p;
-	E.codes = c->d_codes.p; E.qnib = c->d_qnib.p; E.qi = c->d_qi.p; E.W = W;
-	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.res = c->d_res.p;
-	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
-	E.band_cells = c->d_cells.p; E.mode = mode;
-	const unsigned g = (unsigned)c->sms * 12;
-	k_extend<8><<<g, 128, 0, c->stream>>>(E);
-	k_extend<16><<<g, 128, 0, c->stream>>>(E);
-	k_extend<32><<<g, 128, 0, c->stream>>>(E);
-	k_extend<64><<<g, 128, 0, c->stream>>>(E);
-	k_extend<0><<<g, 128, 0, c->stream>>>(E);
-	CU(cudaGetLastError());
+	rc = launch_extend(c, c->stream, B, mode, nullptr); if (rc) return rc;
 	CU(cudaEventRecord(c->ev[2], c->stream));
 	return BG_OK;
 }
 
 static int run_select(bg_ctx *c, int mode) {
 	CU(cudaSetDevice(c->device));
-	k_select<<<(unsigned)c->sms * 4, 256, 0, c->stream>>>(c->d_surv.p, c->d_res.p, c->d_qi.p, work_of(c), c->d_best.p, c->d_counters.p,
+	k_select<<<(unsigned)c->sms * 4, 256, 0, c->stream>>>(c->d_surv.p, c->d_res.p, c->d_best.p, c->d_counters.p,
 		c->surv_cap, c->d_hits.p, c->d_keys.p, mode);
 	CU(cudaGetLastError());
 	CU(cudaEventRecord(c->ev[3], c->stream));
@@ -1461,6 +1511,163 @@ extern "C" int bg_batch_stats(bg_ctx *c, bg_stats *out) {
 	return BG_OK;
 }
 
+__global__ void k_best16(const uint32_t *__restrict__ best, uint16_t *__restrict__ out, uint32_t n) {
+	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = (uint16_t)min(best[i], 0xFFFFu);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined one-call path (large run-list batches): the batch is cut into slices of consecutive runs;
+// slice i+1's queries and runs travel host -> device on the copy stream while slice i's kernels
+// (query prep, seed filter, banded extend) run on the compute stream.  All slices append to one survivor
+// list and share the per-slot minima, so the selection (which needs the batch-wide minimum of a read and
+// its reverse complement, burst.c:4229/4497) runs once at the end, followed by the hit sort and the
+// device -> host copy.  Results are identical to the single-batch path.
+// ---------------------------------------------------------------------------------------------
+static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns, int mode,
+		uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+	CU(cudaSetDevice(c->device));
+	const uint32_t nq = Q->nq;
+	c->kind = WORK_NONE; c->ran = false;
+	// ---- window layout from a sample of the batch (the device re-checks every query against it) ----
+	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t wpt = 8;
+	{
+		uint32_t hist[32]; memset(hist, 0, sizeof(hist));
+		const uint32_t step = std::max<uint32_t>(1, nq / 8192); uint32_t ns = 0;
+		for (uint32_t q = 0; q < nq; q += step, ++ns) {
+			const uint64_t len = Q->offset[q + 1] - Q->offset[q]; const uint32_t np = Q->budget[q] + 1u;
+			if (np <= SEED_NP_MAX) ++hist[std::min<uint64_t>(len / np, 31)];
+		}
+		SL = choose_layout(c, hist, ns);
+		if (SL.stride) {
+			uint64_t sum = 0, cnt = 0; uint32_t mx = 1;
+			for (uint32_t q = 0; q < nq; q += step) {
+				const uint64_t len = Q->offset[q + 1] - Q->offset[q]; const uint32_t np = Q->budget[q] + 1u;
+				if (np <= SL.np_max && len / np >= SL.w + SL.stride - 1) { sum += np; ++cnt; mx = std::max(mx, np); }
+			}
+			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, wpt);
+			SL.np_max = 2 * (wpt / SL.stride);                   // queries with more stretches than the sample showed go to k_filter
+		}
+	}
+	// ---- batch-wide device state ----
+	const uint64_t ntasks = nruns * BG_RUN_MAX;
+	if (!c->surv_cap) c->surv_cap = 1u << 20;
+	uint64_t want = std::min<uint64_t>(ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * nq + ntasks / 8));
+	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 1024), 0xFFFFFFF0ull);
+	const int nsl = (int)std::min<uint64_t>((uint64_t)c->pipe_slices, std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
+	// slice boundaries: sizes shrink geometrically so that little work is left when the last copy lands
+	std::vector<uint64_t> cut(nsl + 1, 0);
+	{
+		const double ratio = c->pipe_ratio / 100.0; double tot = 0, w = 1, acc = 0;
+		for (int i = 0; i < nsl; ++i, w *= ratio) tot += w;
+		w = 1;
+		for (int i = 0; i < nsl; ++i, w *= ratio) { acc += w; cut[i + 1] = std::min<uint64_t>(nruns, (uint64_t)(nruns * (acc / tot) + 0.5)); }
+		cut[nsl] = nruns;
+	}
+	const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
+	for (int attempt = 0; attempt < 4; ++attempt) {
+		if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
+		if (c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128)) return BG_ENOMEM;
+		cudaStream_t cs = c->stream, ps = c->copy_stream;
+		if (best_inout) CU(cudaMemcpyAsync(c->d_best16.p, best_inout, (size_t)Q->nslots * 2, cudaMemcpyHostToDevice, cs));
+		k_init_best<<<(Q->nslots + 255) / 256, 256, 0, cs>>>(c->d_best.p, best_inout ? c->d_best16.p : nullptr, Q->nslots);
+		CU(cudaMemsetAsync(c->d_counters.p, 0, 256, cs));
+		CU(cudaMemsetAsync(c->d_cells.p, 0, 8, cs));
+		CU(cudaMemsetAsync(c->d_first.p, 0, 128 * 4, cs));        // [0,64) first survivor of each slice, [64,128) its queries left to k_filter
+		CU(cudaEventRecord(c->ev[0], cs));
+		CU(cudaStreamWaitEvent(ps, c->ev[0], 0));                 // copies of this call start after earlier work of the context
+		for (int i = 0; i < nsl; ++i) {
+			const uint64_t ra = cut[i], rb = cut[i + 1];
+			if (ra >= rb) continue;
+			// queries this slice touches
+			uint32_t qa = 0xFFFFFFFFu, qb = 0;
+			for (uint64_t r = ra; r < rb; ++r) {
+				const uint32_t a = runs[r].query0, n = runs[r].nq;
+				if (!n || n > BG_RUN_MAX || (uint64_t)a + n > nq) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); }
+				if (!n || n > BG_RUN_MAX || (uint64_t)a + n > nq)
+					return fail(BG_EINVAL, "bg_align_runs: run %llu is malformed (nq must be 1..%d and query0+nq within the batch)", (unsigned long long)r, BG_RUN_MAX);
+				qa = std::min(qa, a); qb = std::max(qb, a + n);
+			}
+			const uint32_t n = qb - qa; const uint64_t base = Q->offset[qa], bytes = Q->offset[qb] - base;
+			if (Q->offset[qb] < base) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return fail(BG_EINVAL, "bg_align_runs: query offsets are not ascending"); }
+			Slice &S = c->sl[i & 1];
+			if (S.codes.need(bytes + 16) || S.qoff.need((size_t)n + 1) || S.budget.need(n) || S.slot.need(n) || S.qi.need(n) ||
+			    S.peq.need((size_t)n * 16) || S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) return BG_ENOMEM;
+			if (i >= 2) CU(cudaStreamWaitEvent(ps, S.computed, 0));   // the slice two back is done with these buffers
+			CU(cudaMemcpyAsync(S.codes.p, Q->codes + base, bytes, cudaMemcpyHostToDevice, ps));
+			CU(cudaMemcpyAsync(S.qoff.p, Q->offset + qa, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ps));
+			CU(cudaMemcpyAsync(S.budget.p, Q->budget + qa, (size_t)n * 2, cudaMemcpyHostToDevice, ps));
+			CU(cudaMemcpyAsync(S.slot.p, Q->slot + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
+			CU(cudaMemcpyAsync(S.runs.p, runs + ra, (rb - ra) * sizeof(bg_run), cudaMemcpyHostToDevice, ps));
+			CU(cudaEventRecord(S.copied, ps));
+			CU(cudaStreamWaitEvent(cs, S.copied, 0));
+			k_qinfo<<<(n + 255) / 256, 256, 0, cs>>>(S.qoff.p, S.budget.p, S.slot.p, n, Q->nslots, S.qi.p, nullptr, c->d_counters.p, base);
+			k_qprep<<<(n + 127) / 128, 128, 0, cs>>>(S.codes.p, S.qi.p, n, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
+			k_qtables<<<(unsigned)(((uint64_t)n * 16 + 255) / 256), 256, 0, cs>>>(S.codes.p, S.qi.p, c->d_sterm.p, n, S.peq.p);
+			k_check_runs<<<(unsigned)((rb - ra + 255) / 256), 256, 0, cs>>>(S.runs.p, rb - ra, qa, n, c->d_counters.p);
+			CU(cudaMemcpyAsync(c->d_first.p + i, c->d_counters.p + C_SURV, 4, cudaMemcpyDeviceToDevice, cs));
+			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.peq = S.peq.p; B.qi = S.qi.p;
+			B.W.runs = S.runs.p; B.W.nruns = rb - ra; B.W.nq = n; B.W.ntiles = 0; B.W.first_clump = c->first_clump; B.W.num_clumps = c->num_clumps;
+			B.W.q_base = qa; B.W.run_base = (uint32_t)ra;
+			int rc = launch_filters(c, cs, B, SL, wpt, SL.stride != 0, true, c->d_first.p + 64 + i); if (rc) return rc;
+			rc = launch_extend(c, cs, B, mode, c->d_first.p + i); if (rc) return rc;
+			CU(cudaEventRecord(S.computed, cs));
+			if (dbg && rb == nruns) { CU(cudaEventRecord(c->ev[1], ps)); CU(cudaEventRecord(c->ev[2], cs)); }
+		}
+		k_select<<<(unsigned)c->sms * 4, 256, 0, cs>>>(c->d_surv.p, c->d_res.p, c->d_best.p, c->d_counters.p, c->surv_cap, c->d_hits.p, c->d_keys.p, mode);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, cs));
+		CU(cudaStreamSynchronize(cs));
+		CU(cudaStreamSynchronize(ps));
+		memcpy(c->h_counters, c->h_pinned, 16);
+		if (c->h_counters[C_ERR]) return fail(BG_EINVAL, "bg_align_runs: a query or run of the batch is malformed (query lengths >= 1, budgets <= 254 (burst.c:3076), slots < nslots, runs within the batch)");
+		const bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->d_scratch.cap;
+		if (!grow_s && !grow_g) {
+			const uint64_t n = c->h_counters[C_HITS];
+			if (n > cap) { *nhits = n; return fail(BG_EOVERFLOW, "bg_align_runs_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap); }
+			c->sorted = false;
+			int rc = sort_hits(c, (uint32_t)n); if (rc) return rc;
+			if (n) CU(cudaMemcpyAsync(hits, c->d_hits_sorted.p, n * sizeof(bg_hit), cudaMemcpyDeviceToHost, cs));
+			if (best_inout) {
+				k_best16<<<(Q->nslots + 255) / 256, 256, 0, cs>>>(c->d_best.p, c->d_best16.p, Q->nslots);
+				CU(cudaMemcpyAsync(best_inout, c->d_best16.p, (size_t)Q->nslots * 2, cudaMemcpyDeviceToHost, cs));
+			}
+			if (dbg) CU(cudaEventRecord(c->ev[3], cs));
+			CU(cudaStreamSynchronize(cs));
+			if (dbg) {
+				float a = 0, b = 0, d = 0; cudaEventElapsedTime(&a, c->ev[0], c->ev[1]); cudaEventElapsedTime(&b, c->ev[0], c->ev[2]); cudaEventElapsedTime(&d, c->ev[0], c->ev[3]);
+				fprintf(stderr, "[burst_b200] one-call timing: last copy done %.3f ms, last slice computed %.3f ms, hits on host %.3f ms (%d slices)\n", a, b, d, nsl);
+			}
+			*nhits = n;
+			return BG_OK;
+		}
+		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
+		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
+	}
+	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
+}
+
+static bool pipeline_applies(const bg_ctx *c, const bg_queries *Q, uint64_t nruns) {
+	return c->pipe_slices >= 2 && Q && Q->nq && nruns >= 2ull * (uint64_t)c->pipe_min_runs && nruns < (1ull << 28) && c->num_clumps;
+}
+
+extern "C" int bg_align_runs_into(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns, int mode,
+		uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+	if (!c || !Q || !runs || !nhits || (!hits && cap)) return fail(BG_EINVAL, "bg_align_runs_into: null argument");
+	if (pipeline_applies(c, Q, nruns)) {
+		if (!Q->codes || !Q->offset || !Q->budget || !Q->slot) return fail(BG_EINVAL, "bg_align_runs_into: null query array");
+		return align_pipelined(c, Q, runs, nruns, mode, best_inout, hits, cap, nhits);
+	}
+	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;
+	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
+	uint64_t n = 0;
+	rc = bg_batch_count(c, &n); if (rc) return rc;
+	*nhits = n;
+	if (n > cap) return fail(BG_EOVERFLOW, "bg_align_runs_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
+	return bg_batch_download(c, hits, cap, best_inout);
+}
+
 static int finish_align(bg_ctx *c, int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
 	int rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
 	uint64_t n = 0;
@@ -1482,6 +1689,21 @@ extern "C" int bg_align_batch(bg_ctx *c, const bg_queries *Q, const bg_task *tas
 extern "C" int bg_align_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns, int mode,
 		uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {
 	if (!hits || !nhits) return fail(BG_EINVAL, "bg_align_runs: null output");
+	if (pipeline_applies(c, Q, nruns) && runs) {
+		// hits are bounded by the survivors: size the host buffer after a first pass would cost a second one, so take the
+		// one-call path with a generous buffer and shrink it
+		uint64_t cap = std::max<uint64_t>(1024, (uint64_t)Q->nq * 2), n = 0;
+		for (int attempt = 0; attempt < 2; ++attempt) {
+			bg_hit *h = (bg_hit *)malloc(cap * sizeof(bg_hit));
+			if (!h) return fail(BG_ENOMEM, "malloc hits");
+			int rc = bg_align_runs_into(c, Q, runs, nruns, mode, best_inout, h, cap, &n);
+			if (rc == BG_OK) { *hits = h; *nhits = n; return BG_OK; }
+			free(h);
+			if (rc != BG_EOVERFLOW || n <= cap) return rc;
+			cap = n;
+		}
+		return fail(BG_EOVERFLOW, "bg_align_runs: hit buffer kept overflowing");
+	}
 	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;
 	return finish_align(c, mode, best_inout, hits, nhits);
 }

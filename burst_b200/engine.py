@@ -16,7 +16,8 @@ TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
 RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
-PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE = 1, 2, 3, 4
+PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE, PARAM_PIPE_SLICES = 1, 2, 3, 4, 5
+PARAM_PIPE_MIN_RUNS, PARAM_PIPE_RATIO = 6, 7
 
 
 class BgQueries(C.Structure):
@@ -38,7 +39,7 @@ class BgStats(C.Structure):
 EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scoring", "bg_default_scoring",
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
-           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param"]
+           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into"]
 
 
 def load_library(path=None):
@@ -73,6 +74,8 @@ def load_library(path=None):
     L.bg_align_runs.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64, C.c_int,
                                 C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_uint64)]
     L.bg_free_hits.argtypes = [C.c_void_p]
+    L.bg_align_runs_into.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64, C.c_int,
+                                     C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     return L
 
 
@@ -186,6 +189,18 @@ class Engine:
         s = BgStats()
         self._check(self.lib.bg_batch_stats(self.ctx, C.byref(s)))
         return s.asdict()
+
+    def align_runs_into(self, codes, offset, budget, runs, hits_out, best_inout=None, mode=MODE_MIN, slot=None, nslots=0):
+        """One call, caller-owned buffers (bg_align_runs_into): `hits_out` is a HIT_DTYPE array (pinned for full speed),
+        `best_inout` an optional uint16 array of per-slot minima carried in and out.  Returns the number of hits."""
+        q = self._queries(codes, offset, budget, slot, nslots)
+        self._nslots = q.nslots
+        r = np.ascontiguousarray(runs, RUN_DTYPE)
+        nh = C.c_uint64(0)
+        self._check(self.lib.bg_align_runs_into(self.ctx, C.byref(q), r.ctypes.data, len(r), mode,
+                                                None if best_inout is None else best_inout.ctypes.data,
+                                                hits_out.ctypes.data, len(hits_out), C.byref(nh)))
+        return int(nh.value)
 
     # ---- one call, host buffers in, host buffers out ----
     def align(self, codes, offset, budget, tasks, mode=MODE_MIN, slot=None, nslots=0, best=None, runs=None):

@@ -95,7 +95,11 @@ int  bg_set_stream(bg_ctx *ctx, void *cuda_stream);
 enum { BG_PARAM_SEED_FILTER = 1,     /* 1 (default): pigeonhole seed filter where the batch allows; 0: Myers prefix filter only */
        BG_PARAM_SEED_CHUNK  = 2,     /* consecutive runs handled by one warp of the seed filter (default 8) */
        BG_PARAM_SEED_WORDS  = 3,     /* 32-bit words of the per-warp window filter, power of two 128..8192 (0 = sized from the batch) */
-       BG_PARAM_SEED_STAGE  = 4 };   /* 1 (default): clumps reach the seed filter through bulk copies (TMA) into shared memory; 0: direct loads */
+       BG_PARAM_SEED_STAGE  = 4,     /* 1 (default): clumps reach the seed filter through bulk copies (TMA) into shared memory; 0: direct loads */
+       BG_PARAM_PIPE_SLICES = 5 };   /* slices the one-call run-list path cuts a large batch into so that host->device copies overlap the kernels
+                                        (default 4; 0 or 1 = one upload, then run) */
+enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096): lists shorter than two slices take the single-batch path */
+       BG_PARAM_PIPE_RATIO = 7 };    /* size of each slice in percent of the one before (default 100 = equal slices; smaller leaves less work behind the last copy) */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),
@@ -138,6 +142,10 @@ int  bg_align_batch(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint
 int  bg_align_runs(bg_ctx *ctx, const bg_queries *q, const bg_run *runs, uint64_t nruns,
                    int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits);
 void bg_free_hits(bg_hit *hits);
+/* The same with the hits written to a caller-owned buffer of `cap` entries (pinned host memory makes the copy
+ * asynchronous): no allocation per call.  BG_EOVERFLOW with *nhits = the number needed when cap is too small. */
+int  bg_align_runs_into(bg_ctx *ctx, const bg_queries *q, const bg_run *runs, uint64_t nruns,
+                        int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits);
 
 #ifdef __cplusplus
 }

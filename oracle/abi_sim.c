@@ -165,4 +165,12 @@ int bg_align_runs(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t n
 	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;
 	return finish(c, mode, best_inout, hits, nhits);
 }
+int bg_align_runs_into(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint64_t nruns, int mode,
+		uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;
+	run(c, mode, best_inout);
+	*nhits = c->nhits;
+	if (c->nhits > cap) return BG_EOVERFLOW;
+	return bg_batch_download(c, hits, cap, best_inout);
+}
 void bg_free_hits(bg_hit *h) { free(h); }

@@ -221,6 +221,59 @@ def test_run_lists_match_task_lists(eng, oracle):
     assert len(hits) >= 200
 
 
+def test_pipelined_one_call_path(eng, oracle):
+    """bg_align_runs / bg_align_runs_into on a list long enough to be cut into slices (copy of slice i+1 overlapping
+    the kernels of slice i): same hits and minima as the oracle, with reverse-complement-style shared slots whose
+    two strands fall into different slices, running minima carried in, both selection modes, ragged bunches."""
+    from burst_b200.engine import RUN_DTYPE, RUN_MAX, HIT_DTYPE, PARAM_PIPE_MIN_RUNS, PARAM_PIPE_SLICES
+    rng = np.random.default_rng(41)
+    refs = synth.random_refs(16 * 40, 214, rng, jitter=6)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 360, 100, 3, rng)
+    # mix in a few queries the seed filter cannot take (IUPAC base, large budget)
+    for i in range(0, len(reads), 37):
+        reads[i][50] = 5
+    codes, qoff = synth.concat_queries(reads)
+    nq = len(reads)
+    budget = np.full(nq, 3, np.uint16); budget[::53] = 9
+    slot = (np.arange(nq, dtype=np.uint32) * 7) % (nq // 2)          # pairs of queries far apart share a slot
+    nslots = nq // 2
+    runs, tq, tc, key = [], [], [], []
+    for q0 in range(0, nq, 13):
+        n = min(13, nq - q0)
+        cands = sorted({int(origin[q, 0]) for q in range(q0, q0 + n)} | {int(v) for v in rng.integers(0, len(clen), 2)})
+        for c in cands:
+            for i in range(n):
+                tq.append(q0 + i); tc.append(c); key.append(len(runs) * RUN_MAX + i)
+            runs.append((c, q0, n))
+    runs = np.array(runs, dtype=RUN_DTYPE)
+    S = oracle.score_table(1)
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    best_in = np.full(nslots, 0xFFFF, np.uint16); best_in[::5] = 1
+    try:
+        eng.set_param(PARAM_PIPE_MIN_RUNS, 16)
+        for mode in (0, 1):
+            for bi in (None, best_in):
+                ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nslots, np.array(tq, np.uint32), np.array(tc, np.uint32), S, mode, best=bi)
+                ohits = ohits.copy(); ohits["task"] = np.array(key, np.uint32)[ohits["task"]]
+                ohits = ohits[np.lexsort((ohits["lane"], ohits["task"]))]
+                for slices in (8, 3, 0):
+                    eng.set_param(PARAM_PIPE_SLICES, slices)
+                    hits, best = eng.align(codes, qoff, budget, None, mode, slot=slot, nslots=nslots, best=bi, runs=runs)
+                    assert np.array_equal(best, obest), (mode, slices)
+                    assert np.array_equal(hits, ohits), (mode, slices)
+                    buf = np.zeros(len(ohits) + 5, HIT_DTYPE); b2 = np.full(nslots, 0xFFFF, np.uint16) if bi is None else bi.copy()
+                    n = eng.align_runs_into(codes, qoff, budget, runs, buf, b2, mode, slot=slot, nslots=nslots)
+                    assert n == len(ohits) and np.array_equal(buf[:n], ohits) and np.array_equal(b2, obest)
+        with pytest.raises(RuntimeError, match="room for"):
+            eng.align_runs_into(codes, qoff, budget, runs, np.zeros(3, HIT_DTYPE), None, 0, slot=slot, nslots=nslots)
+        bad = runs.copy(); bad["query0"][len(bad) // 2] = nq - 2; bad["nq"][len(bad) // 2] = 5
+        with pytest.raises(RuntimeError, match="malformed"):
+            eng.align(codes, qoff, budget, None, 0, slot=slot, nslots=nslots, runs=bad)
+    finally:
+        eng.set_param(PARAM_PIPE_MIN_RUNS, 4096); eng.set_param(PARAM_PIPE_SLICES, 4)
+
+
 def test_repeats_give_several_seed_clusters(eng, oracle):
     """A read that occurs more than once in one reference lane (tandem / distant repeats, with and without
     errors) yields several diagonal clusters for one (query, lane); the merged result must be what the
