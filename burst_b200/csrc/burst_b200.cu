@@ -182,6 +182,25 @@ __global__ void k_qinfo(const uint64_t *__restrict__ off, const uint16_t *__rest
 	if (hist && threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 
+// BG_Q_PACKED4 input: nibble stream -> one code byte per base.  Thread i writes bases 16i .. 16i+15; `odd` = 1 when the
+// first base of the range sits in the high nibble of packed[0].
+__device__ __forceinline__ unsigned long long spread_nibbles(uint32_t w) {
+	unsigned long long x = w;
+	x = (x | (x << 16)) & 0x0000FFFF0000FFFFull;
+	x = (x | (x << 8)) & 0x00FF00FF00FF00FFull;
+	x = (x | (x << 4)) & 0x0F0F0F0F0F0F0F0Full;
+	return x;
+}
+__global__ void k_unpack4(const uint8_t *__restrict__ packed, uint32_t odd, uint64_t nbases, uint8_t *__restrict__ out) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i * 16 >= nbases) return;
+	const uint2 v = *(const uint2 *)(packed + i * 8);                 // the buffer is padded: reads past the last base stay inside it
+	unsigned long long w = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+	if (odd) w = (w >> 4) | ((unsigned long long)packed[i * 8 + 8] << 60);
+	const unsigned long long lo = spread_nibbles((uint32_t)w), hi = spread_nibbles((uint32_t)(w >> 32));
+	*(uint4 *)(out + i * 16) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+}
+
 __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, uint32_t nq, SeedLayout SL,
 		uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed, uint32_t *__restrict__ unseeded) {
 	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1006,10 +1025,10 @@ enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
 // One of two device buffer sets the pipelined one-call path alternates between: while the kernels of one
 // slice run, the next slice's queries and runs are copied in on a second stream.
 struct Slice {
-	DBuf<uint8_t> codes; DBuf<uint64_t> qoff; DBuf<uint16_t> budget; DBuf<uint32_t> slot;
+	DBuf<uint8_t> packed, codes; DBuf<uint64_t> qoff; DBuf<uint16_t> budget; DBuf<uint32_t> slot;
 	DBuf<QInfo> qi; DBuf<uint32_t> peq, qnib; DBuf<bg_run> runs;
 	cudaEvent_t copied = nullptr, computed = nullptr;
-	void release() { codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); peq.release(); qnib.release(); runs.release(); }
+	void release() { packed.release(); codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); peq.release(); qnib.release(); runs.release(); }
 };
 
 struct bg_ctx {
@@ -1027,7 +1046,7 @@ struct bg_ctx {
 	uint32_t stage_bytes = 0;                                     // k_seed staging buffer: the largest clump, at most 8 KB
 	uint32_t num_clumps = 0, first_clump = 0;
 	// batch
-	DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
+	DBuf<uint8_t> d_packed; DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
 	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
 	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
@@ -1093,7 +1112,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
-	c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
+	c->d_packed.release(); c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
 	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
 	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
@@ -1219,6 +1238,21 @@ static SeedLayout choose_layout(const bg_ctx *c, const uint32_t hist[32], uint32
 	return L;
 }
 
+// Query bases [b0, b1) of the caller's code array -> `codes` on the device (one byte per base), through the
+// nibble-packed staging buffer when the caller's array is BG_Q_PACKED4.
+static int copy_codes(const bg_queries *Q, uint64_t b0, uint64_t b1, DBuf<uint8_t> &packed, DBuf<uint8_t> &codes, cudaStream_t copy, cudaStream_t unpack, cudaEvent_t copied) {
+	const uint64_t n = b1 - b0;
+	if (codes.need(n + 32)) return BG_ENOMEM;
+	if (!(Q->flags & BG_Q_PACKED4)) { CU(cudaMemcpyAsync(codes.p, Q->codes + b0, n, cudaMemcpyHostToDevice, copy)); return BG_OK; }
+	const uint64_t y0 = b0 >> 1, y1 = (b1 + 1) >> 1;
+	if (packed.need(y1 - y0 + 32)) return BG_ENOMEM;
+	CU(cudaMemcpyAsync(packed.p, Q->codes + y0, y1 - y0, cudaMemcpyHostToDevice, copy));
+	if (copy != unpack) { CU(cudaEventRecord(copied, copy)); CU(cudaStreamWaitEvent(unpack, copied, 0)); }
+	if (n) k_unpack4<<<(unsigned)((n + 16 * 256 - 1) / (16 * 256)), 256, 0, unpack>>>(packed.p, (uint32_t)(b0 & 1), n, codes.p);
+	CU(cudaGetLastError());
+	return BG_OK;
+}
+
 // queries -> device, QInfo + tables
 static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	if (!c->num_clumps) return fail(BG_EINVAL, "bg_batch_upload: no database loaded");
@@ -1226,15 +1260,16 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	if (!Q->codes || !Q->offset || !Q->budget || !Q->slot) return fail(BG_EINVAL, "bg_batch_upload: null query array");
 	const uint32_t nq = Q->nq;
 	const uint64_t ncodes = Q->offset[nq];
-	if (c->d_codes.need(ncodes + 16) || c->d_qoff.need(nq + 1) || c->d_budget.need(nq) || c->d_slot.need(nq) || c->d_qi.need(nq) ||
+	if (Q->flags & ~(uint32_t)BG_Q_PACKED4) return fail(BG_EINVAL, "bg_batch_upload: unknown query flags %u", Q->flags);
+	if (c->d_qoff.need(nq + 1) || c->d_budget.need(nq) || c->d_slot.need(nq) || c->d_qi.need(nq) ||
 	    c->d_peq.need((size_t)nq * 16) || c->d_qnib.need(ncodes / 8 + 3ull * nq + 8) || c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) ||
 	    c->d_counters.need(64) || c->d_cells.need(8)) return BG_ENOMEM;
-	CU(cudaMemcpyAsync(c->d_codes.p, Q->codes, ncodes, cudaMemcpyHostToDevice, c->stream));
+	{ int rc = copy_codes(Q, Q->offset[0], ncodes, c->d_packed, c->d_codes, c->stream, c->stream, c->ev[3]); if (rc) return rc; }
 	CU(cudaMemcpyAsync(c->d_qoff.p, Q->offset, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->d_budget.p, Q->budget, (size_t)nq * 2, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemcpyAsync(c->d_slot.p, Q->slot, (size_t)nq * 4, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemsetAsync(c->d_counters.p, 0, 256, c->stream));          // [0..3] counters, [9] seed queries, [16..47] stretch-length histogram
-	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p, 0);
+	k_qinfo<<<(nq + 255) / 256, 256, 0, c->stream>>>(c->d_qoff.p, c->d_budget.p, c->d_slot.p, nq, Q->nslots, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p, Q->offset[0]);
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));
@@ -1592,10 +1627,10 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			const uint32_t n = qb - qa; const uint64_t base = Q->offset[qa], bytes = Q->offset[qb] - base;
 			if (Q->offset[qb] < base) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return fail(BG_EINVAL, "bg_align_runs: query offsets are not ascending"); }
 			Slice &S = c->sl[i & 1];
-			if (S.codes.need(bytes + 16) || S.qoff.need((size_t)n + 1) || S.budget.need(n) || S.slot.need(n) || S.qi.need(n) ||
+			if (S.qoff.need((size_t)n + 1) || S.budget.need(n) || S.slot.need(n) || S.qi.need(n) ||
 			    S.peq.need((size_t)n * 16) || S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) return BG_ENOMEM;
 			if (i >= 2) CU(cudaStreamWaitEvent(ps, S.computed, 0));   // the slice two back is done with these buffers
-			CU(cudaMemcpyAsync(S.codes.p, Q->codes + base, bytes, cudaMemcpyHostToDevice, ps));
+			{ int rc = copy_codes(Q, base, base + bytes, S.packed, S.codes, ps, ps, S.copied); if (rc) return rc; }
 			CU(cudaMemcpyAsync(S.qoff.p, Q->offset + qa, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ps));
 			CU(cudaMemcpyAsync(S.budget.p, Q->budget + qa, (size_t)n * 2, cudaMemcpyHostToDevice, ps));
 			CU(cudaMemcpyAsync(S.slot.p, Q->slot + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
@@ -1657,6 +1692,7 @@ extern "C" int bg_align_runs_into(bg_ctx *c, const bg_queries *Q, const bg_run *
 	if (!c || !Q || !runs || !nhits || (!hits && cap)) return fail(BG_EINVAL, "bg_align_runs_into: null argument");
 	if (pipeline_applies(c, Q, nruns)) {
 		if (!Q->codes || !Q->offset || !Q->budget || !Q->slot) return fail(BG_EINVAL, "bg_align_runs_into: null query array");
+		if (Q->flags & ~(uint32_t)BG_Q_PACKED4) return fail(BG_EINVAL, "bg_align_runs_into: unknown query flags %u", Q->flags);
 		return align_pipelined(c, Q, runs, nruns, mode, best_inout, hits, cap, nhits);
 	}
 	int rc = bg_batch_upload_runs(c, Q, runs, nruns); if (rc) return rc;

@@ -16,13 +16,14 @@ TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
 RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
+Q_PACKED4 = 1
 PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE, PARAM_PIPE_SLICES = 1, 2, 3, 4, 5
 PARAM_PIPE_MIN_RUNS, PARAM_PIPE_RATIO = 6, 7
 
 
 class BgQueries(C.Structure):
     _fields_ = [("codes", C.c_void_p), ("offset", C.c_void_p), ("budget", C.c_void_p),
-                ("slot", C.c_void_p), ("nq", C.c_uint32), ("nslots", C.c_uint32)]
+                ("slot", C.c_void_p), ("nq", C.c_uint32), ("nslots", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class BgStats(C.Structure):
@@ -125,7 +126,20 @@ class Engine:
         self._check(self.lib.bg_load_db(self.ctx, packed.ctypes.data, clump_len.ctypes.data,
                                         len(clump_len), first_clump))
 
+    @staticmethod
+    def pack4(codes):
+        """BG_Q_PACKED4 form of a code array: two bases per byte, even base in the low nibble."""
+        c = np.ascontiguousarray(codes, np.uint8)
+        if len(c) & 1:
+            c = np.concatenate([c, np.zeros(1, np.uint8)])
+        return (c[0::2] | (c[1::2] << 4)).astype(np.uint8)
+
     def _queries(self, codes, offset, budget, slot, nslots):
+        """`codes` is a uint8 code array, or a ("packed4", array) pair holding the nibble-packed form."""
+        flags = 0
+        if isinstance(codes, tuple):
+            assert codes[0] == "packed4"
+            flags, codes = Q_PACKED4, codes[1]
         codes = np.ascontiguousarray(codes, np.uint8)
         offset = np.ascontiguousarray(offset, np.uint64)
         budget = np.ascontiguousarray(budget, np.uint16)
@@ -134,7 +148,7 @@ class Engine:
             slot = np.arange(nq, dtype=np.uint32)
             nslots = nq
         slot = np.ascontiguousarray(slot, np.uint32)
-        q = BgQueries(codes.ctypes.data, offset.ctypes.data, budget.ctypes.data, slot.ctypes.data, nq, nslots)
+        q = BgQueries(codes.ctypes.data, offset.ctypes.data, budget.ctypes.data, slot.ctypes.data, nq, nslots, flags)
         self._keep = [codes, offset, budget, slot]
         return q
 

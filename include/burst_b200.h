@@ -62,12 +62,16 @@ typedef struct { uint32_t task; uint8_t lane, ed, gap_q, gap_r; uint32_t final_p
  * budget[i] = Emac the reference would start query i with (ShrBin.ed, burst.c:3069-3081),
  * slot[i]   = index of the running-minimum cell the query shares with its reverse complement
  *             (Ub->six, burst.c:4158, 4218); slot[i] < nslots. */
+enum { BG_Q_PACKED4 = 1 };  /* bg_queries.flags: `codes` holds two bases per byte (even base in the low nibble, the .edx
+                             * clump convention, burst.c:2810-2824) and offset[] counts bases, so a query may start on
+                             * either nibble of a byte.  Halves the bytes that cross PCIe; results are identical. */
 typedef struct {
 	const uint8_t  *codes;
-	const uint64_t *offset;     /* nq + 1 entries into codes */
+	const uint64_t *offset;     /* nq + 1 entries into codes (in bases) */
 	const uint16_t *budget;     /* nq, each <= 254 */
 	const uint32_t *slot;       /* nq */
 	uint32_t nq, nslots;
+	uint32_t flags;             /* 0, or BG_Q_PACKED4 */
 } bg_queries;
 
 typedef struct {

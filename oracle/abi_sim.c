@@ -67,7 +67,13 @@ static void *dup(const void *p, size_t n) { void *r = malloc(n ? n : 1); memcpy(
 static void set_queries(bg_ctx *c, const bg_queries *Q) {
 	free_batch(c);
 	c->nq = Q->nq; c->nslots = Q->nslots;
-	c->codes = dup(Q->codes, Q->offset[Q->nq]); c->qoff = dup(Q->offset, (Q->nq + 1) * 8);
+	if (Q->flags & BG_Q_PACKED4) {                     /* nibble stream -> one code per byte */
+		uint64_t nb = Q->offset[Q->nq];
+		uint8_t *u = malloc(nb + 1);
+		for (uint64_t i = 0; i < nb; ++i) u[i] = (Q->codes[i >> 1] >> (4 * (i & 1))) & 15;
+		c->codes = u;
+	} else c->codes = dup(Q->codes, Q->offset[Q->nq]);
+	c->qoff = dup(Q->offset, (Q->nq + 1) * 8);
 	c->budget = dup(Q->budget, Q->nq * 2); c->slot = dup(Q->slot, Q->nq * 4);
 }
 

@@ -274,6 +274,46 @@ def test_pipelined_one_call_path(eng, oracle):
         eng.set_param(PARAM_PIPE_MIN_RUNS, 4096); eng.set_param(PARAM_PIPE_SLICES, 4)
 
 
+def test_packed4_queries(eng, oracle):
+    """BG_Q_PACKED4: the same batch given as a nibble stream (odd-length queries, so later ones start on a high nibble),
+    through the resident path, the one-call path and its pipelined form; all-vs-all and run lists."""
+    from burst_b200.engine import Engine, RUN_DTYPE, RUN_MAX, PARAM_PIPE_MIN_RUNS
+    rng = np.random.default_rng(43)
+    refs = synth.random_refs(16 * 10, 230, rng, jitter=30, iupac_rate=0.003)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads = []
+    for i in range(120):
+        r, _ = synth.reads_from_clumps(packed, off, clen, 1, int(rng.integers(60, 131)), 3, rng)
+        reads.append(r[0])
+    codes, qoff = synth.concat_queries(reads)
+    assert any(int(o) & 1 for o in qoff[1:-1])
+    nq = len(reads)
+    budget = np.full(nq, 3, np.uint16)
+    p4 = ("packed4", Engine.pack4(codes))
+    S = oracle.score_table(1)
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    slot = np.arange(nq, dtype=np.uint32)
+    for mode in (0, 1):
+        want_h, want_b = eng.align(codes, qoff, budget, None, mode)                       # byte form, checked against the oracle elsewhere
+        tq = np.tile(np.arange(nq, dtype=np.uint32), len(clen)); tc = np.repeat(np.arange(len(clen), dtype=np.uint32), nq)
+        oh, ob = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nq, tq, tc, S, mode)
+        assert np.array_equal(want_h, oh) and np.array_equal(want_b, ob)
+        h, b = eng.align(p4, qoff, budget, None, mode)
+        assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
+        eng.upload(p4, qoff, budget, None); eng.run(mode); h, b = eng.download()
+        assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
+    runs = np.array([(c, q0, min(16, nq - q0)) for q0 in range(0, nq, 16) for c in range(len(clen))], dtype=RUN_DTYPE)
+    want_h, want_b = eng.align(codes, qoff, budget, None, 0, runs=runs)
+    try:
+        for min_runs in (4096, 8):                                                        # single batch, then slices
+            eng.set_param(PARAM_PIPE_MIN_RUNS, min_runs)
+            h, b = eng.align(p4, qoff, budget, None, 0, runs=runs)
+            assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
+    finally:
+        eng.set_param(PARAM_PIPE_MIN_RUNS, 4096)
+    assert len(want_h) >= 100
+
+
 def test_repeats_give_several_seed_clusters(eng, oracle):
     """A read that occurs more than once in one reference lane (tandem / distant repeats, with and without
     errors) yields several diagonal clusters for one (query, lane); the merged result must be what the
