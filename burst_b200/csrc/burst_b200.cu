@@ -310,7 +310,7 @@ struct SeedArgs {
 	const uint4 *db; const ClumpMeta *meta;
 	const QInfo *qi; const uint32_t *qnib; Work W; SeedLayout SL;
 	uint64_t nwork; uint32_t chunk;                 // run indices to enumerate, runs per warp
-	uint32_t wpt, stage;                            // windows per thread kept in the hash cache; bytes per staging buffer (0 = none)
+	uint32_t npmax, hb, stage;                      // stretches per query the window table holds, its hash buckets; bytes per staging buffer
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;
 	uint32_t m16[8];                                // match sets: bit r of half-word q = (S[q][r] == 0)
 };
@@ -368,115 +368,158 @@ __device__ __noinline__ bool window_matches_table(const uint32_t *sM, uint32_t k
 	return true;
 }
 
-// Shared memory of one warp, in 32-bit words (every part a multiple of 4 words):
-//   [0, words)                     Bloom filter
-//   [+0, +16*wpt)                  tag cache: 16-bit hash tags of each thread's windows, eight per 16-byte group (wpt a multiple of 8)
-//   [+0, +2*stage/4)               two staging buffers for clumps (bulk copies)
-//   [+0, +96)                      interval list: 32 x (key u64, hi u32)
-//   [+0, +4)                       two mbarriers
-//   [+0, +4)                       list counter
-__host__ __device__ __forceinline__ uint32_t seed_warp_words(uint32_t words, uint32_t wpt, uint32_t stage) { return words + 16 * wpt + 2 * (stage / 4) + 96 + 4 + 4; }
+// Shared memory of one GROUP (16 threads = one run at a time), in 32-bit words (every part a multiple of 4 words):
+//   bits   [words]          Bloom filter over the windows of the run's queries
+//   head   [hb]             hash buckets of the window table: entry index + 1, 0 = empty
+//   tag    [ne]             full 32-bit hash of window e = (query * npmax + stretch) * stride + j
+//   next   [ne / 2]         chain links (16 bit)
+//   str    [4 * 16 * npmax] the stretch registers (r0, r1, r2, E) of (query, stretch); E = 0: no such stretch
+//   kq     [16]             budgets of the run's queries
+//   stage  [2 * stage / 4]  two staging buffers for clumps (bulk copies)
+//   mbar   [4]              two mbarriers
+struct SeedSmem { uint32_t bits, head, tag, next, str, kq, stage, mbar, total; };
+__host__ __device__ __forceinline__ SeedSmem seed_smem(uint32_t words, uint32_t hb, uint32_t npmax, uint32_t stride, uint32_t stage) {
+	SeedSmem M; const uint32_t ne = 16 * npmax * stride;
+	M.bits = 0; M.head = M.bits + words; M.tag = M.head + hb; M.next = M.tag + ne; M.str = M.next + ((ne / 2 + 3) & ~3u);
+	M.kq = M.str + 64 * npmax; M.stage = M.kq + 16; M.mbar = M.stage + 2 * (stage / 4); M.total = M.mbar + 4;
+	return M;
+}
+
+// A thread's seeds of one run (it owns one reference lane): a short list, and per query the hull of its
+// seed diagonals for the (rare) case that the list overflows.
+#define SEED_LIST 24
+struct LaneSeeds { uint32_t q[SEED_LIST]; int d[SEED_LIST]; int n; int hlo[16], hhi[16]; };
+
+__device__ __noinline__ void lane_seeds_overflow(LaneSeeds &L, uint32_t qi, int dg) {
+	if (L.n == SEED_LIST) {                                                // first overflow: hulls of what the list holds
+		for (int i = 0; i < 16; ++i) { L.hlo[i] = INT32_MAX; L.hhi[i] = INT32_MIN; }
+		for (int i = 0; i < SEED_LIST; ++i) { L.hlo[L.q[i]] = min(L.hlo[L.q[i]], L.d[i]); L.hhi[L.q[i]] = max(L.hhi[L.q[i]], L.d[i]); }
+		L.n = SEED_LIST + 1;
+	}
+	L.hlo[qi] = min(L.hlo[qi], dg); L.hhi[qi] = max(L.hhi[qi], dg);
+}
+
+// clusters of one (query, lane) from the list -> survivors
+__device__ __noinline__ void lane_seeds_emit(LaneSeeds &L, const uint32_t *kq, uint32_t task0, uint32_t lane, Surv *surv, uint32_t surv_cap, uint32_t *counters) {
+	if (L.n > SEED_LIST) {
+		for (uint32_t qi = 0; qi < 16; ++qi) if (L.hlo[qi] <= L.hhi[qi]) {
+			Clus C; C.n = 1; C.lo[0] = L.hlo[qi] - (int)kq[qi]; C.hi[0] = L.hhi[qi] + (int)kq[qi];
+			emit_clusters(C, task0 + qi, lane, surv, surv_cap, counters);
+		}
+		return;
+	}
+	uint32_t done = 0;
+	for (int i = 0; i < L.n; ++i) {
+		const uint32_t qi = L.q[i];
+		if (done >> qi & 1) continue;
+		done |= 1u << qi;
+		const int k = (int)kq[qi];
+		Clus C; C.n = 0;
+		for (int s = 0; s <= CLUS_MAX; ++s) { C.lo[s] = 0; C.hi[s] = 0; }
+		for (int j = i; j < L.n; ++j) if (L.q[j] == qi) clus_add(C, L.d[j] - k, L.d[j] + k);
+		emit_clusters(C, task0 + qi, lane, surv, surv_cap, counters);
+	}
+}
 
 template <int STRIDE, bool FULLW>   // FULLW: 16-base windows (no mask on the older word)
 __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 	extern __shared__ __align__(128) uint32_t smem[];
 	uint32_t *sM = smem;                                                   // 16 match sets
-	const uint32_t warp = threadIdx.x >> 5, t = threadIdx.x & 31;
-	uint32_t *wbase = smem + 16 + warp * seed_warp_words(A.SL.words, A.wpt, A.stage);
-	uint32_t *bits = wbase, *H = bits + A.SL.words, *stg = H + 16 * A.wpt, *list = stg + 2 * (A.stage / 4);
-	uint32_t *cnt = list + 100;
-	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits), stg_s = (uint32_t)__cvta_generic_to_shared(stg);
-	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(list + 96);
+	const uint32_t grp = threadIdx.x >> 4, l = threadIdx.x & 15;          // group of the block, lane / query index within the group
+	const uint32_t gmask = 0xFFFFu << (threadIdx.x & 16);                  // the group's threads within their warp
+	const SeedSmem M = seed_smem(A.SL.words, A.hb, A.npmax, STRIDE, A.stage);
+	uint32_t *gbase = smem + 16 + grp * M.total;
+	uint32_t *bits = gbase + M.bits, *head = gbase + M.head, *tag = gbase + M.tag, *str = gbase + M.str, *kq = gbase + M.kq;
+	uint16_t *nxt = (uint16_t *)(gbase + M.next);
+	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits), stg_s = (uint32_t)__cvta_generic_to_shared(gbase + M.stage);
+	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(gbase + M.mbar);
 	if (threadIdx.x < 16) sM[threadIdx.x] = (A.m16[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xFFFFu;
-	if (t == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); *cnt = 0; asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+	if (l == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 	__syncthreads();
-	const uint64_t i0 = ((uint64_t)blockIdx.x * 4 + warp) * A.chunk, i1 = min(A.nwork, i0 + A.chunk);
+	const uint64_t gid = (uint64_t)blockIdx.x * (blockDim.x >> 4) + grp;
+	const uint64_t i0 = gid * A.chunk, i1 = min(A.nwork, i0 + A.chunk);
 	if (i0 >= i1) return;
-	const uint32_t lane = t & 15, h = t >> 4;                              // scan role: reference lane, half of its chunks
-	const uint32_t qi_ = t & 15, hh = t >> 4;                              // table role: query of the run, half of its stretches
 	const uint32_t HM = FULLW ? 0xFFFFFFFFu : A.SL.hm, SHW = A.SL.shw, ADD = A.SL.amb_add, ambsel = ADD == 0x33333333u ? 3u : 1u;
-	uint32_t cur_q0 = 0xFFFFFFFFu, cur_n = 0, mycount = 0, plen = 0;
-	QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
-	const uint32_t *Wq = A.qnib;
-	bool act = false, anyact = false;
+	const uint32_t HBM = A.hb - 1, NPM = A.npmax;
+	uint32_t cur_q0 = 0xFFFFFFFFu, cur_n = 0;
+	bool anyact = false;
 
 	struct Desc { uint64_t r; uint32_t c, q0, n; bool ok; ClumpMeta M; };
 	auto load_desc = [&](uint64_t i, Desc &D) {
 		D.ok = get_work(A.W, i, D.r, D.c, D.q0, D.n);
 		if (D.ok) { const uint4 m = __ldg((const uint4 *)(A.meta + D.c)); D.M.off = (uint64_t)m.x | ((uint64_t)m.y << 32); D.M.len = m.z; D.M.flags = m.w; }
 	};
-	// bulk copy of a clump into staging buffer b (all lanes call; lane 0 issues)
+	// bulk copy of a clump into staging buffer b (the whole group calls; its first thread issues)
 	auto stage_issue = [&](const Desc &D, uint32_t b) -> bool {
 		const uint32_t bytes = ((D.M.len + 31) >> 5) * 256;
 		if (!D.ok || bytes > A.stage) return false;
-		__syncwarp();                                                      // everyone is done reading buffer b
-		if (t == 0) { mbar_expect_tx(bar_s + 8 * b, bytes); bulk_g2s(stg_s + b * A.stage, A.db + D.M.off, bytes, bar_s + 8 * b); }
+		__syncwarp(gmask);                                                 // everyone is done reading buffer b
+		if (l == 0) { mbar_expect_tx(bar_s + 8 * b, bytes); bulk_g2s(stg_s + b * A.stage, A.db + D.M.off, bytes, bar_s + 8 * b); }
 		return true;
 	};
-	Desc cur, nxt;
+	Desc cur, nxtd;
 	load_desc(i0, cur);
 	bool cur_staged = stage_issue(cur, 0);
 	uint32_t buf = 0, phase = 0;
 
-	for (uint64_t i = i0; i < i1; ++i, cur = nxt, buf ^= 1) {
-		bool nxt_staged = false; nxt.ok = false;
-		if (i + 1 < i1) { load_desc(i + 1, nxt); nxt_staged = stage_issue(nxt, buf ^ 1); }
+	for (uint64_t i = i0; i < i1; ++i, cur = nxtd, buf ^= 1) {
+		bool nxt_staged = false; nxtd.ok = false;
+		if (i + 1 < i1) { load_desc(i + 1, nxtd); nxt_staged = stage_issue(nxtd, buf ^ 1); }
 		const bool staged = cur_staged; cur_staged = nxt_staged;
 		if (!cur.ok) continue;
 		const uint32_t q0 = cur.q0, n = cur.n;
-		if (q0 != cur_q0 || n != cur_n) {                                  // new bunch: rebuild the window set
+		if (q0 != cur_q0 || n != cur_n) {                                  // new bunch: rebuild the window set; thread l = query l
 			cur_q0 = q0; cur_n = n;
-			act = false; mycount = 0;
-			if (qi_ < n) { Q = A.qi[q0 + qi_]; act = Q.cls != 0; }
-			anyact = __any_sync(0xFFFFFFFFu, act);
+			bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
+			if (l < n) { Q = A.qi[q0 + l]; act = Q.cls != 0; }
+			anyact = __any_sync(gmask, act);
 			if (anyact) {
-				for (uint32_t w = t * 4; w < A.SL.words; w += 128) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);
-				__syncwarp();
-				if (act) {
-					const uint32_t np = Q.k + 1u;
-					plen = Q.len / np;
-					Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi_);
-					for (uint32_t p = hh; p < np; p += 2) {
+				for (uint32_t w = l * 4; w < A.SL.words; w += 64) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);
+				for (uint32_t w = l * 4; w < A.hb; w += 64) *(uint4 *)(head + w) = make_uint4(0, 0, 0, 0);
+				kq[l] = Q.k;
+				__syncwarp(gmask);
+				const uint32_t np = act ? Q.k + 1u : 0u, plen = act ? Q.len / np : 0u;
+				const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + l);
+				for (uint32_t p = 0; p < NPM; ++p) {
+					uint4 rec = make_uint4(0, 0, 0, 0);
+					if (p < np) {
 						const QStretch S = stretch_of(Wq, plen, p);
+						rec = make_uint4(S.r0, S.r1, S.r2, S.E);
 						#pragma unroll
 						for (int j = 0; j < STRIDE; ++j) {
 							const QWin w = window_of(S, j);
-							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
+							const uint32_t hv = seed_hash(w.kn, w.ko & HM), e = (l * NPM + p) * STRIDE + j;
 							atomicOr(&bits[hv >> SHW], bloom_bits(hv));
-							((uint16_t *)H)[((mycount + j) >> 3) * 256 + t * 8 + ((mycount + j) & 7)] = (uint16_t)(hv >> 16);
+							tag[e] = hv;
+							nxt[e] = (uint16_t)atomicExch(&head[(hv >> 10) & HBM], e + 1);
 						}
-						mycount += STRIDE;
 					}
+					*(uint4 *)(str + (l * NPM + p) * 4) = rec;
 				}
-				__syncwarp();
+				__syncwarp(gmask);
 			}
 		}
 		if (staged) { mbar_wait(bar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
 		if (!anyact) continue;
 
-		// ---- scan: this thread streams chunks [c0, c1) of its lane, one probe per `STRIDE` columns ----
-		const uint32_t L = cur.M.len, nchunks = (L + 31) >> 5, ch = (nchunks + 1) >> 1;
-		const uint32_t c0 = h * ch, c1 = min(nchunks, c0 + ch);
-		const uint32_t gs = ch <= 8 ? 0u : max(2u, 32u - __clz((ch * 4 - 1) >> 5));   // 2^gs words per mask bit
+		// ---- scan: this thread streams its lane, one probe per `STRIDE` columns ----
+		const uint32_t L = cur.M.len, nchunks = (L + 31) >> 5;
+		const uint32_t gs = nchunks <= 8 ? 0u : max(2u, 32u - __clz((nchunks * 4 - 1) >> 5));   // 2^gs words per mask bit
 		const bool amb_on = (cur.M.flags & ambsel) != 0;
 		const uint4 *gp = A.db + cur.M.off;                                // piece (chunk, lane) at gp[chunk * 16 + lane]
 		const uint32_t sp = stg_s + buf * A.stage;
-		auto piece = [&](uint32_t ck, uint32_t l) -> uint4 { return staged ? lds128(sp + (ck * 16 + l) * 16) : __ldg(gp + (size_t)ck * 16 + l); };
-		auto word_at = [&](uint32_t l, uint32_t wi) -> uint32_t {
+		auto word_at = [&](uint32_t wi) -> uint32_t {
 			return staged ? lds32(sp + ((wi >> 2) * 16 + l) * 16 + (wi & 3) * 4) : __ldg((const uint32_t *)(gp + (size_t)(wi >> 2) * 16 + l) + (wi & 3));
 		};
 		uint32_t mask = 0;
 		auto scan = [&](auto staged_c, auto amb_c) {
 			constexpr bool ST = decltype(staged_c)::value, AMB = decltype(amb_c)::value;
-			auto ld = [&](uint32_t ck) -> uint4 { return ST ? lds128(sp + (ck * 16 + lane) * 16) : __ldg(gp + (size_t)ck * 16 + lane); };
-			uint32_t prev = 0, prev2 = 0;
-			if (c0 && c0 < c1) { const uint4 pp = ld(c0 - 1); prev = pp.w; prev2 = pp.z; }
-			uint32_t ambp = AMB ? amb_nibbles(prev, ADD) : 0u, ambp2 = AMB ? amb_nibbles(prev2, ADD) : 0u;
-			uint4 pc = make_uint4(0, 0, 0, 0);
-			if (c0 < c1) pc = ld(c0);
-			for (uint32_t ck = c0; ck < c1; ++ck) {
+			auto ld = [&](uint32_t ck) -> uint4 { return ST ? lds128(sp + (ck * 16 + l) * 16) : __ldg(gp + (size_t)ck * 16 + l); };
+			uint32_t prev = 0, prev2 = 0, ambp = 0, ambp2 = 0;
+			uint4 pc = ld(0);
+			for (uint32_t ck = 0; ck < nchunks; ++ck) {
 				const uint4 cw = pc;
-				if (!ST && ck + 1 < c1) pc = ld(ck + 1);
+				if (ck + 1 < nchunks) pc = ld(ck + 1);
 				const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
 				uint32_t m4 = 0;
 				#pragma unroll
@@ -496,143 +539,66 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 					m4 |= hit << j;
 					prev2 = prev; prev = cu;
 				}
-				if (ST && ck + 1 < c1) pc = ld(ck + 1);
-				const uint32_t rel = (ck - c0) * 4;
+				const uint32_t rel = ck * 4;
 				mask |= (gs ? (uint32_t)(m4 != 0) : m4) << (rel >> gs);
 			}
 		};
 		if (staged) { if (amb_on) scan(std::true_type{}, std::true_type{}); else scan(std::true_type{}, std::false_type{}); }
 		else        { if (amb_on) scan(std::false_type{}, std::true_type{}); else scan(std::false_type{}, std::false_type{}); }
 
-		// ---- verify the flagged words (rare), lane by lane: thread = (query, half of its stretches) ----
-		const uint32_t evm = __ballot_sync(0xFFFFFFFFu, mask != 0);
-		uint32_t lanes16 = (evm | (evm >> 16)) & 0xFFFFu;
-		while (lanes16) {
-			const uint32_t l = __ffs(lanes16) - 1; lanes16 &= lanes16 - 1;
-			const uint32_t m0 = __shfl_sync(0xFFFFFFFFu, mask, l), m1 = __shfl_sync(0xFFFFFFFFu, mask, l + 16);
-			// this thread's current interval of seed diagonals, and the hull of all of them
-			int clo = 1, chi = 0, hlo = INT32_MAX, hhi = INT32_MIN;
-			auto push = [&](int lo, int hi) {
-				const uint32_t ix = atomicAdd(cnt, 1u);
-				if (ix < 32) { list[ix * 2] = (uint32_t)lo + 0x80000000u; list[ix * 2 + 1] = qi_; list[64 + ix] = (uint32_t)hi; }
+		// ---- verify this lane's flagged words against the window table; seeds -> clusters -> survivors ----
+		if (mask) {
+			LaneSeeds LS; LS.n = 0;
+			auto seed = [&](uint32_t qi, int dg) {
+				if (LS.n < SEED_LIST) { LS.q[LS.n] = qi; LS.d[LS.n] = dg; ++LS.n; }
+				else lane_seeds_overflow(LS, qi, dg);
 			};
-			auto seed = [&](int dg) {
-				const int lo = dg - (int)Q.k, hi = dg + (int)Q.k;
-				hlo = min(hlo, lo); hhi = max(hhi, hi);
-				if (clo > chi) { clo = lo; chi = hi; }
-				else if (lo <= chi + 1 && hi >= clo - 1) { clo = min(clo, lo); chi = max(chi, hi); }
-				else { push(clo, chi); clo = lo; chi = hi; }
-			};
-			for (uint32_t half = 0; half < 2; ++half) {
-				uint32_t mm = half ? m1 : m0;
-				const uint32_t b0 = half * ch * 4, b1 = min(nchunks, (half + 1) * ch) * 4;
-				while (mm) {
-					const uint32_t s = __ffs(mm) - 1; mm &= mm - 1;
-					for (uint32_t wi = b0 + (s << gs); wi < min(b1, b0 + ((s + 1) << gs)); ++wi) {
-						const uint32_t cu = word_at(l, wi), pv = wi >= 1 ? word_at(l, wi - 1) : 0u, pv2 = (STRIDE == 4 && wi >= 2) ? word_at(l, wi - 2) : 0u;
-						#pragma unroll
-						for (int e = STRIDE; e <= 8; e += STRIDE) {
-							const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
-							const int x1 = (int)(wi * 8 + e);
-							if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window, through the table
-								for (uint32_t iw = 0; iw < mycount; ++iw) {
-									const QWin w = window_of(stretch_of(Wq, plen, hh + 2 * (iw / STRIDE)), iw % STRIDE);
-									if (window_matches_table(sM, w.kn, w.ko & HM, rn, ro, A.SL.w)) seed(x1 - (int)w.y1);
+			const uint32_t nw = nchunks * 4;
+			while (mask) {
+				const uint32_t s = __ffs(mask) - 1; mask &= mask - 1;
+				for (uint32_t wi = s << gs; wi < min(nw, (s + 1) << gs); ++wi) {
+					const uint32_t cu = word_at(wi), pv = wi >= 1 ? word_at(wi - 1) : 0u, pv2 = (STRIDE == 4 && wi >= 2) ? word_at(wi - 2) : 0u;
+					#pragma unroll
+					for (int e = STRIDE; e <= 8; e += STRIDE) {
+						const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
+						const int x1 = (int)(wi * 8 + e);
+						if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the run, through the table
+							for (uint32_t si = 0; si < 16 * NPM; ++si) {
+								const uint4 rec = *(const uint4 *)(str + si * 4);
+								if (!rec.w) continue;
+								QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
+								for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
+									const QWin w = window_of(S, j);
+									if (window_matches_table(sM, w.kn, w.ko & HM, rn, ro, A.SL.w)) seed(si / NPM, x1 - (int)w.y1);
 								}
-							} else {
-								const uint32_t hv = seed_hash(rn, ro);
-								const uint32_t tag2 = (hv >> 16) * 0x00010001u;                // the window's 16-bit tag in both halves
-								for (uint32_t i8 = 0; i8 < mycount; i8 += 8) {
-									const uint4 hq = *(const uint4 *)(H + i8 * 16 + t * 4);          // eight tags of this thread
-									const uint32_t dx = hq.x ^ tag2, dy = hq.y ^ tag2, dz = hq.z ^ tag2, dw = hq.w ^ tag2;
-									// a zero half-word in any of them?  (v - 0x00010001) & ~v & 0x80008000
-									const uint32_t z = ((dx - 0x00010001u) & ~dx) | ((dy - 0x00010001u) & ~dy) | ((dz - 0x00010001u) & ~dz) | ((dw - 0x00010001u) & ~dw);
-									if (!(z & 0x80008000u)) continue;
-									const uint32_t ds[4] = {dx, dy, dz, dw};
-									for (uint32_t u = 0; u < 8 && i8 + u < mycount; ++u) if (((ds[u >> 1] >> (16 * (u & 1))) & 0xFFFFu) == 0) {
-										const uint32_t iw = i8 + u;
-										const QWin w = window_of(stretch_of(Wq, plen, hh + 2 * (iw / STRIDE)), iw % STRIDE);
-										if (w.kn == rn && (w.ko & HM) == ro) seed(x1 - (int)w.y1);
-									}
-								}
+							}
+						} else {
+							const uint32_t hv = seed_hash(rn, ro);
+							for (uint32_t en = head[(hv >> 10) & HBM]; en; en = nxt[en - 1]) {
+								if (tag[en - 1] != hv) continue;
+								const uint32_t si = (en - 1) / STRIDE, j = (en - 1) % STRIDE;
+								const uint4 rec = *(const uint4 *)(str + si * 4);
+								QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
+								const QWin w = window_of(S, j);
+								if (w.kn == rn && (w.ko & HM) == ro) seed(si / NPM, x1 - (int)w.y1);
 							}
 						}
 					}
 				}
 			}
-			{	// the two table halves of a query usually hold the same cluster: fold the upper half's open interval into the lower's
-				const int olo = __shfl_down_sync(0xFFFFFFFFu, clo, 16), ohi = __shfl_down_sync(0xFFFFFFFFu, chi, 16);
-				const bool mine = clo <= chi, theirs = olo <= ohi, join = mine && theirs && olo <= chi + 1 && ohi >= clo - 1;
-				const bool joined = __shfl_up_sync(0xFFFFFFFFu, join, 16);
-				if (hh == 0) { if (join) { clo = min(clo, olo); chi = max(chi, ohi); } if (mine) push(clo, chi); }
-				else if (mine && !joined) push(clo, chi);
-			}
-			__syncwarp();
-			const uint32_t nl = *cnt;
-			unsigned long long key = ~0ull; uint32_t vhi = 0;
-			if (t < nl) { key = ((unsigned long long)list[t * 2 + 1] << 32) | list[t * 2]; vhi = list[64 + t]; }
-			__syncwarp();
-			if (t == 0) *cnt = 0;
-			__syncwarp();
-			if (!nl) continue;
-			uint32_t emit = 0, grpcnt = 0; int lo = 0, hi = 0, q = 0;
-			if (nl == 1) {                                                     // the usual case: one interval, nothing to merge
-				q = (int)(key >> 32); lo = (int)((uint32_t)key - 0x80000000u); hi = (int)vhi;
-				emit = t == 0; grpcnt = 1;
-			} else if (nl <= 32) {
-				// sort the intervals by (query, lo); a cluster starts where lo exceeds every earlier hi of the query by more than 1
-				{
-					#pragma unroll
-					for (uint32_t k2 = 2; k2 <= 32; k2 <<= 1) {
-						#pragma unroll
-						for (uint32_t j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
-							const unsigned long long ok = __shfl_xor_sync(0xFFFFFFFFu, key, j2);
-							const uint32_t oh = __shfl_xor_sync(0xFFFFFFFFu, vhi, j2);
-							const bool takemin = ((t & k2) == 0) == ((t & j2) == 0);
-							if (takemin ? ok < key : ok > key) { key = ok; vhi = oh; }
-						}
-					}
-				}
-				const bool valid = t < nl;
-				q = (int)(key >> 32); lo = (int)((uint32_t)key - 0x80000000u); hi = (int)vhi;
-				const int pq = __shfl_up_sync(0xFFFFFFFFu, q, 1);
-				const bool newg = valid && (t == 0 || q != pq);
-				const uint32_t G = __ballot_sync(0xFFFFFFFFu, newg);
-				const uint32_t gstart = valid ? 31u - __clz(G & (0xFFFFFFFFu >> (31 - t))) : 0u;
-				int pm = hi;                                                   // prefix max of hi within the query's segment
-				#pragma unroll
-				for (int o = 1; o < 32; o <<= 1) { const int v = __shfl_up_sync(0xFFFFFFFFu, pm, o); if (t >= gstart + o) pm = max(pm, v); }
-				const int ppm = __shfl_up_sync(0xFFFFFFFFu, pm, 1);
-				const bool brk = valid && (newg || lo > ppm + 1);
-				const uint32_t B = __ballot_sync(0xFFFFFFFFu, brk);
-				const uint32_t nb = t < 31 ? B & (0xFFFFFFFFu << (t + 1)) : 0u, ng = t < 31 ? G & (0xFFFFFFFFu << (t + 1)) : 0u;
-				const uint32_t ce = nb ? __ffs(nb) - 2 : nl - 1, ge = ng ? __ffs(ng) - 1 : nl;     // last interval of the cluster, end of the group
-				const int chiv = __shfl_sync(0xFFFFFFFFu, pm, ce), ghiv = __shfl_sync(0xFFFFFFFFu, pm, ge - 1);
-				const uint32_t gc = __popc(B & (ge >= 32 ? 0xFFFFFFFFu : (1u << ge) - 1) & (0xFFFFFFFFu << t));
-				const uint32_t mygc = __shfl_sync(0xFFFFFFFFu, gc, gstart);
-				if (brk) {
-					if (mygc <= 15) { emit = 1; hi = chiv; grpcnt = newg ? mygc : 0; }
-					else if (newg) { emit = 1; hi = ghiv; grpcnt = 1; }        // too many clusters for one lane: one hull
-				}
-			} else {
-				// more intervals than the list holds: one hull per (query, lane) from the two halves' hulls
-				const int olo = __shfl_down_sync(0xFFFFFFFFu, hlo, 16), ohi = __shfl_down_sync(0xFFFFFFFFu, hhi, 16);
-				lo = min(hlo, olo); hi = max(hhi, ohi); q = (int)qi_;
-				if (hh == 0 && lo <= hi) { emit = 1; grpcnt = 1; }
-			}
-			const uint32_t E = __ballot_sync(0xFFFFFFFFu, emit);
-			if (!E) continue;
-			uint32_t base = 0;
-			if (t == 0) base = atomicAdd(&A.counters[C_SURV], (uint32_t)__popc(E));
-			base = __shfl_sync(0xFFFFFFFFu, base, 0);
-			if (emit) {
-				const uint32_t slot = base + __popc(E & ((1u << t) - 1)), W = (uint32_t)(hi - lo + 1);
-				uint32_t scratch = 0;
-				if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
-				if (slot < A.surv_cap) {
-					Surv v; v.task = (uint32_t)((cur.r + A.W.run_base) * BG_RUN_MAX) + (uint32_t)q; v.lo = lo; v.w_lane = (W << 8) | (grpcnt << 4) | l; v.scratch = scratch;
-					A.surv[slot] = v;
-				}
+			if (LS.n) {
+				const uint32_t task0 = (uint32_t)((cur.r + A.W.run_base) * BG_RUN_MAX);
+				bool simple = LS.n <= SEED_LIST;                               // usual case: one query, one cluster
+				int dlo = LS.d[0], dhi = LS.d[0];
+				if (simple) for (int z = 1; z < LS.n; ++z) { simple = simple && LS.q[z] == LS.q[0]; dlo = min(dlo, LS.d[z]); dhi = max(dhi, LS.d[z]); }
+				const int k0 = (int)kq[LS.q[0] & 15];
+				if (simple && dhi - dlo <= 2 * k0 + 1) {
+					const uint32_t W = (uint32_t)(dhi - dlo + 2 * k0 + 1);
+					const uint32_t slot = atomicAdd(&A.counters[C_SURV], 1u);
+					uint32_t scratch = 0;
+					if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+					if (slot < A.surv_cap) { Surv v; v.task = task0 + LS.q[0]; v.lo = dlo - k0; v.w_lane = (W << 8) | (1u << 4) | l; v.scratch = scratch; A.surv[slot] = v; }
+				} else lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters);
 			}
 		}
 	}
@@ -1036,7 +1002,7 @@ struct bg_ctx {
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 1;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
-	uint32_t seed_wpt = 0;                                        // windows per thread of the hash cache (from the batch)
+	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
 	uint8_t S[256];
@@ -1286,14 +1252,14 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	return BG_OK;
 }
 
-static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &wpt);
+static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &npmax);
 
 static int finish_upload(bg_ctx *c) {
 	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, c->stream));
 	CU(cudaStreamSynchronize(c->stream));     // the caller's host buffers may be reused after this returns
 	if (c->h_pinned[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_batch_upload_runs: run %u is malformed (nq must be 1..%d and query0+nq within the batch)", c->h_pinned[C_ERR] & 0x7FFFFFFF, BG_RUN_MAX); }
 	c->nseed = c->h_pinned[9];
-	if (c->nseed) seed_sizes(c, c->SL, (c->h_pinned[10] + c->nseed - 1) / c->nseed, c->h_pinned[11], c->seed_wpt);
+	if (c->nseed) seed_sizes(c, c->SL, (c->h_pinned[10] + c->nseed - 1) / c->nseed, c->h_pinned[11], c->seed_npmax);
 	memset(&c->stats, 0, sizeof(c->stats));
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
 	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
@@ -1356,29 +1322,33 @@ extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *ta
 // Device view of one uploaded batch (or one slice of a pipelined one).
 struct BatchDev { const uint8_t *codes; const uint32_t *qnib, *peq; const QInfo *qi; Work W; };
 
-static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &wpt) {
+static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &npmax) {
 	// Bloom filter size: ~2-4 words per window of a full run (16 queries x mean stretches x stride)
 	const uint64_t windows = (uint64_t)BG_RUN_MAX * SL.stride * stretches_mean;
 	uint32_t words = 256;
 	while (words < 4096 && words < 2 * windows) words <<= 1;
 	if (c->seed_words) words = (uint32_t)c->seed_words;
 	SL.words = words; SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --SL.shw;
-	wpt = (((stretches_max + 1) / 2) * SL.stride + 7) & ~7u;          // the tag cache is read eight tags at a time
+	npmax = std::min<uint32_t>(std::max<uint32_t>(stretches_max, 1), 128 / SL.stride);   // window table rows per query
 }
 
-static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t wpt, bool seed, bool filter, const uint32_t *todo) {
+static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t npmax, bool seed, bool filter, const uint32_t *todo) {
 	if (B.W.nruns && seed) {
 		SeedArgs S;
 		S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = B.qi;
 		S.qnib = B.qnib; S.W = B.W; S.SL = SL; S.nwork = B.W.nruns; S.chunk = (uint32_t)c->seed_chunk;
-		S.wpt = wpt; S.stage = c->seed_stage ? c->stage_bytes : 0;
+		S.npmax = npmax; S.stage = c->seed_stage ? c->stage_bytes : 0;
+		S.hb = 64; while (S.hb < 16 * npmax * SL.stride) S.hb <<= 1;
 		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 		memcpy(S.m16, c->m16, sizeof(S.m16));
-		const uint64_t warps = (B.W.nruns + S.chunk - 1) / S.chunk, blocks = (warps + 3) / 4;
-		const size_t smem = (16 + 4 * (size_t)seed_warp_words(SL.words, S.wpt, S.stage)) * sizeof(uint32_t);
+		const uint32_t gwords = seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage).total;
+		uint32_t gpb = 8;                                         // groups (runs in flight) per block: as many as leave room for two blocks per SM
+		while (gpb > 2 && (16 + (size_t)gpb * gwords) * 4 > 110 * 1024) gpb >>= 1;
+		const uint64_t groups = (B.W.nruns + S.chunk - 1) / S.chunk, blocks = (groups + gpb - 1) / gpb;
+		const size_t smem = (16 + (size_t)gpb * gwords) * sizeof(uint32_t);
 		void (*kern)(SeedArgs) = SL.stride == 8 ? (SL.w == 16 ? k_seed<8, true> : k_seed<8, false>) : (SL.w == 16 ? k_seed<4, true> : k_seed<4, false>);
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		kern<<<(unsigned)blocks, 128, smem, st>>>(S);
+		kern<<<(unsigned)blocks, gpb * 16, smem, st>>>(S);
 		CU(cudaGetLastError());
 	}
 	if (B.W.nruns && filter) {
@@ -1422,7 +1392,7 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	CU(cudaMemsetAsync(c->d_cells.p, 0, 8, c->stream));
 	CU(cudaEventRecord(c->ev[0], c->stream));
 	BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.peq = c->d_peq.p; B.qi = c->d_qi.p; B.W = work_of(c);
-	int rc = launch_filters(c, c->stream, B, c->SL, c->seed_wpt, c->nseed != 0, c->nseed < c->nq, nullptr); if (rc) return rc;
+	int rc = launch_filters(c, c->stream, B, c->SL, c->seed_npmax, c->nseed != 0, c->nseed < c->nq, nullptr); if (rc) return rc;
 	CU(cudaEventRecord(c->ev[1], c->stream));
 	rc = launch_extend(c, c->stream, B, mode, nullptr); if (rc) return rc;
 	CU(cudaEventRecord(c->ev[2], c->stream));
@@ -1565,7 +1535,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 	const uint32_t nq = Q->nq;
 	c->kind = WORK_NONE; c->ran = false;
 	// ---- window layout from a sample of the batch (the device re-checks every query against it) ----
-	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t wpt = 8;
+	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t npmax = 1;
 	{
 		uint32_t hist[32]; memset(hist, 0, sizeof(hist));
 		const uint32_t step = std::max<uint32_t>(1, nq / 8192); uint32_t ns = 0;
@@ -1580,8 +1550,8 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 				const uint64_t len = Q->offset[q + 1] - Q->offset[q]; const uint32_t np = Q->budget[q] + 1u;
 				if (np <= SL.np_max && len / np >= SL.w + SL.stride - 1) { sum += np; ++cnt; mx = std::max(mx, np); }
 			}
-			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, wpt);
-			SL.np_max = 2 * (wpt / SL.stride);                   // queries with more stretches than the sample showed go to k_filter
+			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, npmax);
+			SL.np_max = npmax;                                   // queries with more stretches than the sample showed go to k_filter
 		}
 	}
 	// ---- batch-wide device state ----
@@ -1645,7 +1615,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.peq = S.peq.p; B.qi = S.qi.p;
 			B.W.runs = S.runs.p; B.W.nruns = rb - ra; B.W.nq = n; B.W.ntiles = 0; B.W.first_clump = c->first_clump; B.W.num_clumps = c->num_clumps;
 			B.W.q_base = qa; B.W.run_base = (uint32_t)ra;
-			int rc = launch_filters(c, cs, B, SL, wpt, SL.stride != 0, true, c->d_first.p + 64 + i); if (rc) return rc;
+			int rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64 + i); if (rc) return rc;
 			rc = launch_extend(c, cs, B, mode, c->d_first.p + i); if (rc) return rc;
 			CU(cudaEventRecord(S.computed, cs));
 			if (dbg && rb == nruns) { CU(cudaEventRecord(c->ev[1], ps)); CU(cudaEventRecord(c->ev[2], cs)); }
