@@ -201,26 +201,55 @@ __global__ void k_unpack4(const uint8_t *__restrict__ packed, uint32_t odd, uint
 	*(uint4 *)(out + i * 16) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
 }
 
+// eight code bytes (two aligned-shifted words) -> eight nibbles
+__device__ __forceinline__ uint32_t pack_nibbles(uint32_t b0, uint32_t b1) {
+	unsigned long long x = ((unsigned long long)b0 | ((unsigned long long)b1 << 32)) & 0x0F0F0F0F0F0F0F0Full;
+	x = (x | (x >> 4)) & 0x00FF00FF00FF00FFull;
+	x = (x | (x >> 8)) & 0x0000FFFF0000FFFFull;
+	x = (x | (x >> 16));
+	return (uint32_t)x;
+}
+
 __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, uint32_t nq, SeedLayout SL,
 		uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed, uint32_t *__restrict__ unseeded) {
 	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
 	bool seed = false; uint32_t nst = 0;
 	if (q < nq) {
 		const QInfo Q = qi[q];
-		const uint8_t *s = codes + Q.off;
+		// the code bytes through aligned 32-bit loads (`codes` is 256-byte aligned and padded), shifted into place
+		const uint32_t *a = (const uint32_t *)(codes + (Q.off & ~3ull));
+		const uint32_t sh = (uint32_t)(Q.off & 3) * 8;
 		uint32_t *W = qnib + (Q.off >> 3) + 3ull * q;
 		W[0] = 0; W[1] = 0;
-		for (uint32_t j = 0; j < Q.len; j += 8) {
-			uint32_t w = 0;
-			#pragma unroll
-			for (int i = 0; i < 8; ++i) if (j + i < Q.len) w |= (uint32_t)(s[j + i] & 15) << (4 * i);
+		uint32_t w0 = a[0], w1 = a[1];
+		for (uint32_t j = 0, k = 0; j < Q.len; j += 8, k += 2) {
+			const uint32_t w2 = a[k + 2];
+			const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);
+			w0 = w2; w1 = a[k + 3];
+			uint32_t w = pack_nibbles(b0, b1);
+			if (j + 8 > Q.len) w &= (1u << (4 * (Q.len - j))) - 1u;
 			W[2 + (j >> 3)] = w;
 		}
 		const uint32_t np = Q.k + 1u, plen = Q.len / np;
 		seed = SL.stride && np <= SL.np_max && plen >= SL.w + SL.stride - 1;
+		// every base the windows cover must be a plain A/C/G/T (codes 1..4): checked on the packed words just written
+		const uint32_t span = SL.w + SL.stride - 1;
 		for (uint32_t p = 0; p < np && seed; ++p) {
-			const uint32_t E = (p + 1) * plen;
-			for (uint32_t i = E - (SL.w + SL.stride - 1); i < E; ++i) { const uint32_t c = s[i] & 15; if (c < 1 || c > 4) { seed = false; break; } }
+			const uint32_t E = (p + 1) * plen, B = E - span;
+			for (uint32_t wi = B >> 3; wi <= (E - 1) >> 3; ++wi) {
+				const uint32_t w = W[2 + wi];
+				uint32_t bad = ((((w & 0x77777777u) + 0x33333333u) | w) | ((w - 0x11111111u) & ~w)) & 0x88888888u;   // nibble >= 5, or 0 (or just above a 0)
+				const uint32_t lo = wi * 8 < B ? B - wi * 8 : 0u, hi = wi * 8 + 8 > E ? E - wi * 8 : 8u;            // nibbles [lo, hi) of this word are inside
+				uint32_t keep = hi == 8 ? 0xFFFFFFFFu : (1u << (4 * hi)) - 1u;
+				keep &= ~((1u << (4 * lo)) - 1u);
+				// a zero nibble raises the flag of the nibbles above it as well; those are inside the region or beyond its end, where a
+				// spurious flag could only come from a zero below, itself inside the word -- so test from the region start upward
+				bad &= keep;
+				if (bad) {                                                     // confirm nibble by nibble (rare)
+					for (uint32_t i = lo; i < hi; ++i) { const uint32_t c = (w >> (4 * i)) & 15; if (c < 1 || c > 4) { seed = false; break; } }
+					if (!seed) break;
+				}
+			}
 		}
 		qi[q].cls = seed;
 		if (seed) nst = np;
@@ -368,20 +397,23 @@ __device__ __noinline__ bool window_matches_table(const uint32_t *sM, uint32_t k
 	return true;
 }
 
-// Shared memory of one GROUP (16 threads = one run at a time), in 32-bit words (every part a multiple of 4 words):
-//   bits   [words]          Bloom filter over the windows of the run's queries
+// Shared memory of one block, in 32-bit words (every part a multiple of 4 words).  A block walks its runs in rounds
+// of G (= groups per block, 16 threads each, one run per group); the runs of a round that belong to one bunch share
+// ONE window table, built by the whole block:
+//   sM     [16]             match sets of the scoring table
+//   bits   [words]          Bloom filter over the windows of the bunch's queries
 //   head   [hb]             hash buckets of the window table: entry index + 1, 0 = empty
 //   tag    [ne]             full 32-bit hash of window e = (query * npmax + stretch) * stride + j
 //   next   [ne / 2]         chain links (16 bit)
 //   str    [4 * 16 * npmax] the stretch registers (r0, r1, r2, E) of (query, stretch); E = 0: no such stretch
-//   kq     [16]             budgets of the run's queries
-//   stage  [2 * stage / 4]  two staging buffers for clumps (bulk copies)
-//   mbar   [4]              two mbarriers
-struct SeedSmem { uint32_t bits, head, tag, next, str, kq, stage, mbar, total; };
-__host__ __device__ __forceinline__ SeedSmem seed_smem(uint32_t words, uint32_t hb, uint32_t npmax, uint32_t stride, uint32_t stage) {
+//   kq     [16]             budgets of the bunch's queries
+//   keys   [16]             (query0, nq) of the run each group holds in this round
+//   per group: stage [2 * stage / 4] two staging buffers for clumps (bulk copies), mbar [4] two mbarriers
+struct SeedSmem { uint32_t bits, head, tag, next, str, kq, keys, groups, gwords, total; };
+__host__ __device__ __forceinline__ SeedSmem seed_smem(uint32_t words, uint32_t hb, uint32_t npmax, uint32_t stride, uint32_t stage, uint32_t G) {
 	SeedSmem M; const uint32_t ne = 16 * npmax * stride;
-	M.bits = 0; M.head = M.bits + words; M.tag = M.head + hb; M.next = M.tag + ne; M.str = M.next + ((ne / 2 + 3) & ~3u);
-	M.kq = M.str + 64 * npmax; M.stage = M.kq + 16; M.mbar = M.stage + 2 * (stage / 4); M.total = M.mbar + 4;
+	M.bits = 16; M.head = M.bits + words; M.tag = M.head + hb; M.next = M.tag + ne; M.str = M.next + ((ne / 2 + 3) & ~3u);
+	M.kq = M.str + 64 * npmax; M.keys = M.kq + 16; M.groups = M.keys + 16; M.gwords = 2 * (stage / 4) + 4; M.total = M.groups + G * M.gwords;
 	return M;
 }
 
@@ -424,29 +456,27 @@ __device__ __noinline__ void lane_seeds_emit(LaneSeeds &L, const uint32_t *kq, u
 template <int STRIDE, bool FULLW>   // FULLW: 16-base windows (no mask on the older word)
 __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 	extern __shared__ __align__(128) uint32_t smem[];
-	uint32_t *sM = smem;                                                   // 16 match sets
-	const uint32_t grp = threadIdx.x >> 4, l = threadIdx.x & 15;          // group of the block, lane / query index within the group
+	const uint32_t G = blockDim.x >> 4;                                    // groups of the block = runs per round
+	const uint32_t grp = threadIdx.x >> 4, l = threadIdx.x & 15;          // group, reference lane within the run
 	const uint32_t gmask = 0xFFFFu << (threadIdx.x & 16);                  // the group's threads within their warp
-	const SeedSmem M = seed_smem(A.SL.words, A.hb, A.npmax, STRIDE, A.stage);
-	uint32_t *gbase = smem + 16 + grp * M.total;
-	uint32_t *bits = gbase + M.bits, *head = gbase + M.head, *tag = gbase + M.tag, *str = gbase + M.str, *kq = gbase + M.kq;
-	uint16_t *nxt = (uint16_t *)(gbase + M.next);
-	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits), stg_s = (uint32_t)__cvta_generic_to_shared(gbase + M.stage);
-	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(gbase + M.mbar);
+	const SeedSmem M = seed_smem(A.SL.words, A.hb, A.npmax, STRIDE, A.stage, G);
+	uint32_t *sM = smem, *bits = smem + M.bits, *head = smem + M.head, *tag = smem + M.tag, *str = smem + M.str, *kq = smem + M.kq;
+	uint16_t *nxt = (uint16_t *)(smem + M.next);
+	unsigned long long *keys = (unsigned long long *)(smem + M.keys);
+	uint32_t *gbase = smem + M.groups + grp * M.gwords;
+	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits), stg_s = (uint32_t)__cvta_generic_to_shared(gbase);
+	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(gbase + 2 * (A.stage / 4));
 	if (threadIdx.x < 16) sM[threadIdx.x] = (A.m16[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xFFFFu;
 	if (l == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 	__syncthreads();
-	const uint64_t gid = (uint64_t)blockIdx.x * (blockDim.x >> 4) + grp;
-	const uint64_t i0 = gid * A.chunk, i1 = min(A.nwork, i0 + A.chunk);
-	if (i0 >= i1) return;
+	const uint64_t b0 = (uint64_t)blockIdx.x * G * A.chunk;               // the block's runs: b0 .. b0 + G * chunk
 	const uint32_t HM = FULLW ? 0xFFFFFFFFu : A.SL.hm, SHW = A.SL.shw, ADD = A.SL.amb_add, ambsel = ADD == 0x33333333u ? 3u : 1u;
 	const uint32_t HBM = A.hb - 1, NPM = A.npmax;
-	uint32_t cur_q0 = 0xFFFFFFFFu, cur_n = 0;
-	bool anyact = false;
+	const unsigned long long NOKEY = ~0ull;
 
 	struct Desc { uint64_t r; uint32_t c, q0, n; bool ok; ClumpMeta M; };
 	auto load_desc = [&](uint64_t i, Desc &D) {
-		D.ok = get_work(A.W, i, D.r, D.c, D.q0, D.n);
+		D.ok = i < A.nwork && get_work(A.W, i, D.r, D.c, D.q0, D.n);
 		if (D.ok) { const uint4 m = __ldg((const uint4 *)(A.meta + D.c)); D.M.off = (uint64_t)m.x | ((uint64_t)m.y << 32); D.M.len = m.z; D.M.flags = m.w; }
 	};
 	// bulk copy of a clump into staging buffer b (the whole group calls; its first thread issues)
@@ -458,50 +488,54 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 		return true;
 	};
 	Desc cur, nxtd;
-	load_desc(i0, cur);
+	load_desc(b0 + grp, cur);
 	bool cur_staged = stage_issue(cur, 0);
 	uint32_t buf = 0, phase = 0;
 
-	for (uint64_t i = i0; i < i1; ++i, cur = nxtd, buf ^= 1) {
+	for (uint32_t round = 0; round < A.chunk; ++round, cur = nxtd, buf ^= 1) {
+		if (b0 + (uint64_t)round * G >= A.nwork) break;                    // block-uniform
 		bool nxt_staged = false; nxtd.ok = false;
-		if (i + 1 < i1) { load_desc(i + 1, nxtd); nxt_staged = stage_issue(nxtd, buf ^ 1); }
+		if (round + 1 < A.chunk) { load_desc(b0 + (uint64_t)(round + 1) * G + grp, nxtd); nxt_staged = stage_issue(nxtd, buf ^ 1); }
 		const bool staged = cur_staged; cur_staged = nxt_staged;
-		if (!cur.ok) continue;
-		const uint32_t q0 = cur.q0, n = cur.n;
-		if (q0 != cur_q0 || n != cur_n) {                                  // new bunch: rebuild the window set; thread l = query l
-			cur_q0 = q0; cur_n = n;
+		const unsigned long long mykey = cur.ok ? ((unsigned long long)cur.q0 << 8) | cur.n : NOKEY;
+		if (l == 0) keys[grp] = mykey;
+		__syncthreads();                                                   // keys published; the previous round is done with the table
+		uint32_t processed = 0;
+		for (uint32_t g = 0; g < G; ++g) if (keys[g] == NOKEY) processed |= 1u << g;
+		if (processed == (1u << G) - 1) __syncthreads();                   // nothing to do this round: keep the next round's keys behind a barrier all the same
+		while (processed != (1u << G) - 1) {
+			// ---- the first pending bunch of the round: every run of it is scanned against one table ----
+			const unsigned long long K = keys[__ffs(~processed) - 1];
+			for (uint32_t g = 0; g < G; ++g) if (keys[g] == K) processed |= 1u << g;
+			const bool active = mykey == K;
+			const uint32_t q0 = (uint32_t)(K >> 8), n = (uint32_t)(K & 255);
+			// build: thread = (query t & 15, window phase t >> 4)
+			for (uint32_t w = threadIdx.x * 4; w < A.SL.words + A.hb; w += blockDim.x * 4) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);   // bits and head are adjacent
+			const uint32_t qi = threadIdx.x & 15, sub = threadIdx.x >> 4;
 			bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
-			if (l < n) { Q = A.qi[q0 + l]; act = Q.cls != 0; }
-			anyact = __any_sync(gmask, act);
-			if (anyact) {
-				for (uint32_t w = l * 4; w < A.SL.words; w += 64) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);
-				for (uint32_t w = l * 4; w < A.hb; w += 64) *(uint4 *)(head + w) = make_uint4(0, 0, 0, 0);
-				kq[l] = Q.k;
-				__syncwarp(gmask);
+			if (qi < n) { Q = A.qi[q0 + qi]; act = Q.cls != 0; }
+			if (sub == 0) kq[qi] = Q.k;
+			__syncthreads();
+			{
 				const uint32_t np = act ? Q.k + 1u : 0u, plen = act ? Q.len / np : 0u;
-				const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + l);
-				for (uint32_t p = 0; p < NPM; ++p) {
-					uint4 rec = make_uint4(0, 0, 0, 0);
+				const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi);
+				for (uint32_t wn = sub; wn < NPM * STRIDE; wn += G) {
+					const uint32_t p = wn / STRIDE, j = wn % STRIDE;
 					if (p < np) {
 						const QStretch S = stretch_of(Wq, plen, p);
-						rec = make_uint4(S.r0, S.r1, S.r2, S.E);
-						#pragma unroll
-						for (int j = 0; j < STRIDE; ++j) {
-							const QWin w = window_of(S, j);
-							const uint32_t hv = seed_hash(w.kn, w.ko & HM), e = (l * NPM + p) * STRIDE + j;
-							atomicOr(&bits[hv >> SHW], bloom_bits(hv));
-							tag[e] = hv;
-							nxt[e] = (uint16_t)atomicExch(&head[(hv >> 10) & HBM], e + 1);
-						}
-					}
-					*(uint4 *)(str + (l * NPM + p) * 4) = rec;
+						const QWin w = window_of(S, j);
+						const uint32_t hv = seed_hash(w.kn, w.ko & HM), e = (qi * NPM + p) * STRIDE + j;
+						atomicOr(&bits[hv >> SHW], bloom_bits(hv));
+						tag[e] = hv;
+						nxt[e] = (uint16_t)atomicExch(&head[(hv >> 10) & HBM], e + 1);
+						if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(S.r0, S.r1, S.r2, S.E);
+					} else if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(0, 0, 0, 0);
 				}
-				__syncwarp(gmask);
 			}
-		}
-		if (staged) { mbar_wait(bar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
-		if (!anyact) continue;
-
+			const bool anyact = __syncthreads_or(act);
+			if (active) {
+				if (staged) { mbar_wait(bar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
+				if (anyact) {
 		// ---- scan: this thread streams its lane, one probe per `STRIDE` columns ----
 		const uint32_t L = cur.M.len, nchunks = (L + 31) >> 5;
 		const uint32_t gs = nchunks <= 8 ? 0u : max(2u, 32u - __clz((nchunks * 4 - 1) >> 5));   // 2^gs words per mask bit
@@ -549,9 +583,9 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 		// ---- verify this lane's flagged words against the window table; seeds -> clusters -> survivors ----
 		if (mask) {
 			LaneSeeds LS; LS.n = 0;
-			auto seed = [&](uint32_t qi, int dg) {
-				if (LS.n < SEED_LIST) { LS.q[LS.n] = qi; LS.d[LS.n] = dg; ++LS.n; }
-				else lane_seeds_overflow(LS, qi, dg);
+			auto seed = [&](uint32_t sq, int dg) {
+				if (LS.n < SEED_LIST) { LS.q[LS.n] = sq; LS.d[LS.n] = dg; ++LS.n; }
+				else lane_seeds_overflow(LS, sq, dg);
 			};
 			const uint32_t nw = nchunks * 4;
 			while (mask) {
@@ -562,7 +596,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 					for (int e = STRIDE; e <= 8; e += STRIDE) {
 						const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
 						const int x1 = (int)(wi * 8 + e);
-						if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the run, through the table
+						if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the bunch, through the table
 							for (uint32_t si = 0; si < 16 * NPM; ++si) {
 								const uint4 rec = *(const uint4 *)(str + si * 4);
 								if (!rec.w) continue;
@@ -600,6 +634,10 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 					if (slot < A.surv_cap) { Surv v; v.task = task0 + LS.q[0]; v.lo = dlo - k0; v.w_lane = (W << 8) | (1u << 4) | l; v.scratch = scratch; A.surv[slot] = v; }
 				} else lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters);
 			}
+		}
+				}
+			}
+			__syncthreads();                                               // the table is free for the next bunch of the round
 		}
 	}
 }
@@ -1323,10 +1361,11 @@ extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *ta
 struct BatchDev { const uint8_t *codes; const uint32_t *qnib, *peq; const QInfo *qi; Work W; };
 
 static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &npmax) {
-	// Bloom filter size: ~2-4 words per window of a full run (16 queries x mean stretches x stride)
+	// Bloom filter size: 1-2 words per window of a full bunch (16 queries x mean stretches x stride): a false positive
+	// costs the owning thread one hash-table probe, a larger filter costs occupancy (measured: profiles/)
 	const uint64_t windows = (uint64_t)BG_RUN_MAX * SL.stride * stretches_mean;
 	uint32_t words = 256;
-	while (words < 4096 && words < 2 * windows) words <<= 1;
+	while (words < 4096 && words < windows) words <<= 1;
 	if (c->seed_words) words = (uint32_t)c->seed_words;
 	SL.words = words; SL.shw = 32; for (uint32_t w = words; w > 1; w >>= 1) --SL.shw;
 	npmax = std::min<uint32_t>(std::max<uint32_t>(stretches_max, 1), 128 / SL.stride);   // window table rows per query
@@ -1341,11 +1380,16 @@ static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const S
 		S.hb = 64; while (S.hb < 16 * npmax * SL.stride) S.hb <<= 1;
 		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 		memcpy(S.m16, c->m16, sizeof(S.m16));
-		const uint32_t gwords = seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage).total;
-		uint32_t gpb = 8;                                         // groups (runs in flight) per block: as many as leave room for two blocks per SM
-		while (gpb > 2 && (16 + (size_t)gpb * gwords) * 4 > 110 * 1024) gpb >>= 1;
-		const uint64_t groups = (B.W.nruns + S.chunk - 1) / S.chunk, blocks = (groups + gpb - 1) / gpb;
-		const size_t smem = (16 + (size_t)gpb * gwords) * sizeof(uint32_t);
+		// groups (runs per round) per block: the count that keeps the most runs in flight per SM
+		uint32_t gpb = 8, best_inflight = 0;
+		for (uint32_t g = 8; g >= 2; g >>= 1) {
+			const size_t b = (size_t)seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage, g).total * 4 + 1024;
+			const uint32_t inflight = (uint32_t)std::min<size_t>(220 * 1024 / b, 2048 / (g * 16)) * g;
+			if (inflight > best_inflight) { best_inflight = inflight; gpb = g; }
+		}
+		if (!best_inflight) return fail(BG_EINVAL, "seed filter tables do not fit shared memory (words %u, stretches %u)", SL.words, npmax);
+		const uint64_t per_block = (uint64_t)gpb * S.chunk, blocks = (B.W.nruns + per_block - 1) / per_block;
+		const size_t smem = (size_t)seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage, gpb).total * sizeof(uint32_t);
 		void (*kern)(SeedArgs) = SL.stride == 8 ? (SL.w == 16 ? k_seed<8, true> : k_seed<8, false>) : (SL.w == 16 ? k_seed<4, true> : k_seed<4, false>);
 		if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		kern<<<(unsigned)blocks, gpb * 16, smem, st>>>(S);
