@@ -380,23 +380,6 @@ def test_seed_layouts_and_tuning_knobs(eng, oracle):
         eng.set_param(PARAM_SEED_CHUNK, 8); eng.set_param(PARAM_SEED_WORDS, 0); eng.set_param(PARAM_SEED_STAGE, 0)
 
 
-@pytest.mark.xfail(strict=False, reason="known issue (DESIGN.md section 4): with bulk-copy (TMA) staging of clumps in k_seed an intermittent "
-                   "mismatch / fault shows up in some builds; neither memcheck nor racecheck explains it yet, so staging is off by default")
-def test_seed_filter_with_tma_staging(eng, oracle):
-    """BG_PARAM_SEED_STAGE = 1: clumps reach the seed filter through cp.async.bulk + mbarrier, one run ahead."""
-    from burst_b200.engine import PARAM_SEED_STAGE
-    rng = np.random.default_rng(47)
-    refs = synth.random_refs(16 * 9, 230, rng, jitter=40)
-    packed, off, clen = synth.pack_clumps(refs)
-    reads, _ = synth.reads_from_clumps(packed, off, clen, 150, 100, 2, rng)
-    try:
-        eng.set_param(PARAM_SEED_STAGE, 1)
-        hits, st = check(eng, oracle, packed, off, clen, reads, [2] * len(reads), mode=0)
-        assert len(hits) >= 100
-    finally:
-        eng.set_param(PARAM_SEED_STAGE, 0)
-
-
 def test_malformed_input_is_an_error_not_a_crash(eng, oracle):
     from burst_b200.engine import RUN_DTYPE
     rng = np.random.default_rng(31)
@@ -413,3 +396,21 @@ def test_malformed_input_is_an_error_not_a_crash(eng, oracle):
         eng.align(codes, qoff, np.full(8, 1, np.uint16), np.array([[8, 0]], np.uint32))
     hits, best = eng.align(codes, qoff, np.full(8, 1, np.uint16), None)    # the context is still usable
     assert len(hits) >= 8
+
+
+# Keep this test LAST in the GPU tier: a device fault would leave the CUDA context of the test process unusable.
+@pytest.mark.xfail(strict=False, reason="known issue (DESIGN.md section 4): with bulk-copy (TMA) staging of clumps in k_seed an intermittent "
+                   "mismatch / fault shows up in some builds; neither memcheck nor racecheck explains it yet, so staging is off by default")
+def test_seed_filter_with_tma_staging(eng, oracle):
+    """BG_PARAM_SEED_STAGE = 1: clumps reach the seed filter through cp.async.bulk + mbarrier, one run ahead."""
+    from burst_b200.engine import PARAM_SEED_STAGE
+    rng = np.random.default_rng(47)
+    refs = synth.random_refs(16 * 9, 230, rng, jitter=40)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, _ = synth.reads_from_clumps(packed, off, clen, 150, 100, 2, rng)
+    try:
+        eng.set_param(PARAM_SEED_STAGE, 1)
+        hits, st = check(eng, oracle, packed, off, clen, reads, [2] * len(reads), mode=0)
+        assert len(hits) >= 100
+    finally:
+        eng.set_param(PARAM_SEED_STAGE, 0)
