@@ -61,14 +61,11 @@ struct QInfo {            // one query of the batch
 	uint8_t  P;           // rows covered by the Myers prefix filter = min(32, len)
 	uint8_t  cls;         // 1: handled by k_seed (piece automaton), 0: by k_filter (Myers)
 };
-struct Surv {             // one diagonal cluster of a (task, lane) that survived the filter (32 bytes)
+struct Surv {             // one diagonal cluster of a (task, lane) that survived the filter
 	uint32_t task;        // run * 16 + query-in-run (batch-wide)
 	int32_t  lo;          // lowest diagonal (x - y) of the band
 	uint32_t w_lane;      // band width << 8 | clusters-in-group << 4 (first of a group, else 0) | lane
 	uint32_t scratch;     // offset into the global band scratch (generic kernel only)
-	uint32_t clump;       // clump index on this device
-	uint32_t qix;         // query index within the uploaded batch / slice
-	uint32_t pad0, pad1;
 };
 struct Res { uint32_t a, b, slot; };   // a = ed | gap_q << 8 | gap_r << 16 | valid << 31 ; b = final_pos ; slot of the query
 
@@ -305,7 +302,7 @@ __device__ __noinline__ void clus_add(Clus &C, int lo, int hi) {
 	C.n = out;
 }
 
-__device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_t lane, uint32_t clump, uint32_t qix, Surv *surv, uint32_t surv_cap, uint32_t *counters) {
+__device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_t lane, Surv *surv, uint32_t surv_cap, uint32_t *counters) {
 	if (!C.n) return;
 	const uint32_t base = atomicAdd(&counters[C_SURV], (uint32_t)C.n);
 	for (int s = 0; s < C.n; ++s) {
@@ -314,7 +311,6 @@ __device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_
 		if (W > 64) scratch = atomicAdd(&counters[C_SCRATCH], W);
 		if (base + s < surv_cap) {
 			Surv v; v.task = task; v.lo = C.lo[s]; v.w_lane = (W << 8) | ((s == 0 ? (uint32_t)C.n : 0u) << 4) | lane; v.scratch = scratch;
-			v.clump = clump; v.qix = qix; v.pad0 = 0; v.pad1 = 0;
 			surv[base + s] = v;
 		}
 	}
@@ -436,11 +432,11 @@ __device__ __noinline__ void lane_seeds_overflow(LaneSeeds &L, uint32_t qi, int 
 }
 
 // clusters of one (query, lane) from the list -> survivors
-__device__ __noinline__ void lane_seeds_emit(LaneSeeds &L, const uint32_t *kq, uint32_t task0, uint32_t lane, uint32_t clump, uint32_t qix0, Surv *surv, uint32_t surv_cap, uint32_t *counters) {
+__device__ __noinline__ void lane_seeds_emit(LaneSeeds &L, const uint32_t *kq, uint32_t task0, uint32_t lane, Surv *surv, uint32_t surv_cap, uint32_t *counters) {
 	if (L.n > SEED_LIST) {
 		for (uint32_t qi = 0; qi < 16; ++qi) if (L.hlo[qi] <= L.hhi[qi]) {
 			Clus C; C.n = 1; C.lo[0] = L.hlo[qi] - (int)kq[qi]; C.hi[0] = L.hhi[qi] + (int)kq[qi];
-			emit_clusters(C, task0 + qi, lane, clump, qix0 + qi, surv, surv_cap, counters);
+			emit_clusters(C, task0 + qi, lane, surv, surv_cap, counters);
 		}
 		return;
 	}
@@ -453,7 +449,7 @@ __device__ __noinline__ void lane_seeds_emit(LaneSeeds &L, const uint32_t *kq, u
 		Clus C; C.n = 0;
 		for (int s = 0; s <= CLUS_MAX; ++s) { C.lo[s] = 0; C.hi[s] = 0; }
 		for (int j = i; j < L.n; ++j) if (L.q[j] == qi) clus_add(C, L.d[j] - k, L.d[j] + k);
-		emit_clusters(C, task0 + qi, lane, clump, qix0 + qi, surv, surv_cap, counters);
+		emit_clusters(C, task0 + qi, lane, surv, surv_cap, counters);
 	}
 }
 
@@ -635,8 +631,8 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 					const uint32_t slot = atomicAdd(&A.counters[C_SURV], 1u);
 					uint32_t scratch = 0;
 					if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
-					if (slot < A.surv_cap) { Surv v; v.task = task0 + LS.q[0]; v.lo = dlo - k0; v.w_lane = (W << 8) | (1u << 4) | l; v.scratch = scratch; v.clump = cur.c; v.qix = q0 + LS.q[0]; v.pad0 = 0; v.pad1 = 0; A.surv[slot] = v; }
-				} else lane_seeds_emit(LS, kq, task0, l, cur.c, q0, A.surv, A.surv_cap, A.counters);
+					if (slot < A.surv_cap) { Surv v; v.task = task0 + LS.q[0]; v.lo = dlo - k0; v.w_lane = (W << 8) | (1u << 4) | l; v.scratch = scratch; A.surv[slot] = v; }
+				} else lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters);
 			}
 		}
 				}
@@ -753,7 +749,6 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 		const uint32_t i = atomicAdd(&A.counters[C_SURV], 1u);
 		if (i < A.surv_cap) {
 			Surv s; s.task = (uint32_t)t + A.W.run_base * BG_RUN_MAX; s.lo = lo; s.w_lane = (W << 8) | (1u << 4) | lane; s.scratch = scratch;
-			s.clump = c; s.qix = q; s.pad0 = 0; s.pad1 = 0;
 			A.surv[i] = s;
 		}
 	}
@@ -804,8 +799,10 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 15;
 		// class dispatch: this instantiation takes bands that fit WMAX but not WMAX/2
 		if (WMAX == 0 ? (W <= 64) : (W > (uint32_t)WMAX || (WMAX > 8 && W <= (uint32_t)WMAX / 2))) continue;
-		const uint32_t qix = sv.qix;
-		const uint4 cm = __ldg((const uint4 *)(A.meta + sv.clump));      // clump record and query record: two independent loads
+		uint32_t c, q0, n;
+		get_run(A.W, (sv.task >> 4) - A.W.run_base, c, q0, n);
+		const uint32_t qix = q0 + (sv.task & 15);
+		const uint4 cm = __ldg((const uint4 *)(A.meta + c));              // clump record: one 16-byte load
 		const QInfo Q = A.qi[qix];
 		const uint32_t m = Q.len, L = cm.z;
 		const uint32_t *lanew = A.dbw + ((uint64_t)cm.x | ((uint64_t)cm.y << 32)) * 4 + lane * 4;
@@ -1043,7 +1040,7 @@ struct bg_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
-	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
+	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 1;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
