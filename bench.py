@@ -48,6 +48,9 @@ def parse():
     return ap.parse_args()
 
 
+DPX_PEAK = 571.6e9 * 32      # VIADDMNMX.U32 thread-instructions/s, measured (profiles/r1d_pipe_microbench.txt)
+
+
 def peaks():
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
@@ -179,6 +182,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the DP path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"              # keep rank 0's stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from burst_b200.engine import Engine, MODE_MIN, RUN_DTYPE
 
@@ -302,6 +307,10 @@ def main():
                             "peak_source": "of " + how + " (MEASURED_PEAKS.json hbm_gbs, burst figure; fallback = 6650 GB/s of B200_PROFILING.md)",
                             "achieved_per_task_8d": alg_bytes_8d / (filt_ms / 1e3) / 1e9,
                             "note": "achieved = bytes one pass must move (clump once per run + queries once + survivors) / CUDA-event time of the k_seed launch; the kernel streams each clump once for the <=16 queries of a bunch, so SURVEY 8(d)'s per-(query, clump) byte count (achieved_per_task_8d) exceeds what is physically read; the kernel is latency/issue bound, not HBM bound (profiles/)"},
+               "integer_roofline": {"kernel": "k_extend (5 band classes)", "kernel_ms": st["ms_extend"],
+                                    "dpx_thread_inst_per_s": 2.0 * st["band_cells"] / (st["ms_extend"] / 1e3),
+                                    "dpx_peak_thread_inst_per_s": DPX_PEAK, "frac": 2.0 * st["band_cells"] / (st["ms_extend"] / 1e3) / DPX_PEAK,
+                                    "note": "2 VIADDMNMX per band cell (select-with-tie-break of the packed pass-2 key); peak = VIADDMNMX.U32 issue rate measured on this pool's B200 by burst_b200/csrc/tools/pipe_microbench (profiles/r1d_pipe_microbench.txt: 571.6 G warp-inst/s at 1965 MHz, half the 4-per-clock issue rate: it shares the ALU pipe with the ~5 LOP3/SHF/VIMNMX each cell also needs)"},
                "clocks": clocks, "workload_gen_s": w["gen_s"]}
         if not args.no_cpu_baseline and world == 1:
             cb, _ = cpu_reference(args, w)

@@ -4,6 +4,7 @@ the set of reported (task, lane) pairs and the per-slot minima."""
 import numpy as np
 import pytest
 from burst_b200 import synth
+from burst_b200.engine import default_scoring
 
 pytestmark = pytest.mark.gpu
 
@@ -396,6 +397,42 @@ def test_malformed_input_is_an_error_not_a_crash(eng, oracle):
         eng.align(codes, qoff, np.full(8, 1, np.uint16), np.array([[8, 0]], np.uint32))
     hits, best = eng.align(codes, qoff, np.full(8, 1, np.uint16), None)    # the context is still usable
     assert len(hits) >= 8
+
+
+def test_bench_shape_at_scale(eng):
+    """configs[1] shape at a size the oracle cannot check cell by cell (120 k reads = 240 k strands in 15 k bunches, 128 MB
+    DB, ~120 k runs) through size-independent properties: every read is reported exactly at the lane it was cut from with
+    at most its planted number of edits; the one-call path (pipelined, byte and nibble-packed input) returns byte-identical
+    hits and minima to the resident path; both staging modes and the Myers filter agree."""
+    from burst_b200.engine import Engine, RUN_DTYPE, HIT_DTYPE, PARAM_SEED_STAGE, PARAM_PIPE_MIN_RUNS
+    w = synth.bunch_workload(120_000, 100, 2, 128 << 20, 214, seed=20261017)
+    runs = np.ascontiguousarray(w["runs"], RUN_DTYPE)
+    eng.set_scoring(default_scoring(1)); eng.load_db(w["packed"], w["clump_len"])
+    eng.upload_runs(w["qcodes"], w["qoff"], w["budget"], runs, slot=w["slot"], nslots=w["nslots"])
+    eng.run(0); hits, best = eng.download()
+    assert int((best <= 2).sum()) == w["n_reads"]
+    tq = runs["query0"][hits["task"] >> 4] + (hits["task"] & 15); tc = runs["clump"][hits["task"] >> 4]
+    rd = w["slot"][tq]
+    ok = (tc == w["true_clump"][rd]) & (hits["lane"] == w["true_lane"][rd]) & (hits["ed"] <= 2)
+    assert len(np.unique(rd[ok])) == w["n_reads"]
+    assert np.all(np.diff((hits["task"].astype(np.int64) << 4) | hits["lane"]) > 0)          # sorted by (task, lane), no duplicates
+    buf = np.zeros(len(hits) + 16, HIT_DTYPE)
+    try:
+        for codes in (w["qcodes"], ("packed4", Engine.pack4(w["qcodes"]))):
+            for stage in (1, 0):
+                eng.set_param(PARAM_SEED_STAGE, stage)
+                b2 = np.full(w["nslots"], 0xFFFF, np.uint16)
+                n = eng.align_runs_into(codes, w["qoff"], w["budget"], runs, buf, b2, 0, slot=w["slot"], nslots=w["nslots"])
+                assert n == len(hits) and np.array_equal(buf[:n], hits) and np.array_equal(b2, best)
+        eng.set_seed_filter(False)                                                          # Myers prefix filter on a tenth of the list
+        sub = runs[: len(runs) // 10]
+        nqs = int(sub["query0"][-1] + sub["nq"][-1])
+        h1, b1 = eng.align(w["qcodes"][: int(w["qoff"][nqs])], w["qoff"][: nqs + 1], w["budget"][:nqs], None, 0, slot=w["slot"][:nqs], nslots=w["nslots"], runs=sub)
+        eng.set_seed_filter(True)
+        h2, b2 = eng.align(w["qcodes"][: int(w["qoff"][nqs])], w["qoff"][: nqs + 1], w["budget"][:nqs], None, 0, slot=w["slot"][:nqs], nslots=w["nslots"], runs=sub)
+        assert np.array_equal(h1, h2) and np.array_equal(b1, b2) and len(h1) > 1000
+    finally:
+        eng.set_seed_filter(True); eng.set_param(PARAM_SEED_STAGE, 1)
 
 
 def test_seed_filter_with_direct_loads(eng, oracle):
