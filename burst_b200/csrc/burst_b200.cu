@@ -1066,7 +1066,7 @@ struct bg_ctx {
 	int last_mode = 0; std::vector<uint16_t> last_best_in; bool have_best_in = false;
 	bg_stats stats;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	Slice sl[2]; cudaStream_t copy_stream = nullptr; DBuf<uint32_t> d_first; int pipe_slices = 4, pipe_min_runs = 4096, pipe_ratio = 100;   // pipelined one-call path
+	Slice sl[2]; cudaStream_t copy_stream = nullptr; DBuf<uint32_t> d_first; int pipe_slices = 4, pipe_min_runs = 4096, pipe_ratio = 0;   // pipelined one-call path
 	uint32_t h_counters[4] = {0, 0, 0, 0};
 	bool ran = false, sorted = false;
 };
@@ -1152,7 +1152,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 		c->seed_words = value; return BG_OK;
 	}
 	if (what == BG_PARAM_SEED_STAGE) { c->seed_stage = value != 0; return BG_OK; }
-	if (what == BG_PARAM_PIPE_RATIO) { if (value < 10 || value > 100) return fail(BG_EINVAL, "bg_set_param: slice ratio %d out of range 10..100", value); c->pipe_ratio = value; return BG_OK; }
+	if (what == BG_PARAM_PIPE_RATIO) { if (value && (value < 10 || value > 300)) return fail(BG_EINVAL, "bg_set_param: slice ratio %d must be 0 (auto) or 10..300", value); c->pipe_ratio = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_MIN_RUNS) { if (value < 1) return fail(BG_EINVAL, "bg_set_param: minimum runs per slice %d", value); c->pipe_min_runs = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_SLICES) { if (value < 0 || value > 64) return fail(BG_EINVAL, "bg_set_param: pipeline slices %d out of range 0..64", value); c->pipe_slices = value; return BG_OK; }
 	return fail(BG_EINVAL, "bg_set_param: unknown parameter %d", what);
@@ -1613,7 +1613,9 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 	// slice boundaries: sizes shrink geometrically so that little work is left when the last copy lands
 	std::vector<uint64_t> cut(nsl + 1, 0);
 	{
-		const double ratio = c->pipe_ratio / 100.0; double tot = 0, w = 1, acc = 0;
+		// growing slices when the kernels are the longer leg (nibble-packed reads: first copy short, copies hide behind the kernels),
+		// equal slices when the copies are (one byte per base)
+		const double ratio = (c->pipe_ratio ? c->pipe_ratio : ((Q->flags & BG_Q_PACKED4) ? 140 : 100)) / 100.0; double tot = 0, w = 1, acc = 0;
 		for (int i = 0; i < nsl; ++i, w *= ratio) tot += w;
 		w = 1;
 		for (int i = 0; i < nsl; ++i, w *= ratio) { acc += w; cut[i + 1] = std::min<uint64_t>(nruns, (uint64_t)(nruns * (acc / tot) + 0.5)); }

@@ -104,7 +104,8 @@ enum { BG_PARAM_SEED_FILTER = 1,     /* 1 (default): pigeonhole seed filter wher
        BG_PARAM_PIPE_SLICES = 5 };   /* slices the one-call run-list path cuts a large batch into so that host->device copies overlap the kernels
                                         (default 4; 0 or 1 = one upload, then run) */
 enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096): lists shorter than two slices take the single-batch path */
-       BG_PARAM_PIPE_RATIO = 7 };    /* size of each slice in percent of the one before (default 100 = equal slices; smaller leaves less work behind the last copy) */
+       BG_PARAM_PIPE_RATIO = 7 };    /* size of each slice in percent of the one before; 0 (default) = 100 for byte codes (copy-bound), 140 for
+                                        BG_Q_PACKED4 (kernel-bound: a short first copy, later copies hide behind the kernels) */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),

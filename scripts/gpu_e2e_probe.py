@@ -25,7 +25,12 @@ for it in range(3):
     eng.run(MODE_MIN); n = eng.count(); t2 = time.perf_counter()
     hits, best = eng.download(); t3 = time.perf_counter()
     print("resident: upload %.2f ms  run+count %.2f ms  download %.2f ms  (hits %d)" % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, n), flush=True)
-for slices, ratio in ((4, 100), (4, 100), (5, 65), (6, 65), (6, 50), (8, 70), (5, 80), (0, 65)):
+PACK = ("packed4", pin(Engine.pack4(w["qcodes"]))[0]) if os.environ.get("PACKED") else None
+_keep = PACK
+if PACK is not None:
+    pp, kk = pin(Engine.pack4(w["qcodes"])); PACK = ("packed4", pp)
+    pc = PACK
+for slices, ratio in ((4, 100), (4, 100), (4, 120), (5, 120), (5, 130), (6, 120), (4, 140), (3, 130), (5, 100)):
     eng.set_param(PARAM_PIPE_SLICES, slices); eng.set_param(PARAM_PIPE_RATIO, ratio)
     ts = []
     for it in range(4):
