@@ -453,6 +453,13 @@ __device__ __noinline__ void lane_seeds_emit(LaneSeeds &L, const uint32_t *kq, u
 	}
 }
 
+// Block-wide barrier for k_seed.  The two 16-thread groups of a warp take different paths between barriers (one scans and
+// emits, the other may not), and bar.sync is an ALIGNED barrier: every thread of a warp has to execute it together.  Leaving
+// the reconvergence to the compiler made the kernel fault or lose seeds depending on unrelated code changes
+// (profiles/r1d_known_issue.txt); the explicit __syncwarp() makes the warp whole again before it arrives.
+__device__ __forceinline__ void block_barrier() { __syncwarp(); __syncthreads(); }
+__device__ __forceinline__ bool block_barrier_or(bool p) { __syncwarp(); return __syncthreads_or(p) != 0; }
+
 template <int STRIDE, bool FULLW>   // FULLW: 16-base windows (no mask on the older word)
 __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 	extern __shared__ __align__(128) uint32_t smem[];
@@ -499,10 +506,10 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 		const bool staged = cur_staged; cur_staged = nxt_staged;
 		const unsigned long long mykey = cur.ok ? ((unsigned long long)cur.q0 << 8) | cur.n : NOKEY;
 		if (l == 0) keys[grp] = mykey;
-		__syncthreads();                                                   // keys published; the previous round is done with the table
+		block_barrier();                                                   // keys published; the previous round is done with the table
 		uint32_t processed = 0;
 		for (uint32_t g = 0; g < G; ++g) if (keys[g] == NOKEY) processed |= 1u << g;
-		if (processed == (1u << G) - 1) __syncthreads();                   // nothing to do this round: keep the next round's keys behind a barrier all the same
+		if (processed == (1u << G) - 1) block_barrier();                   // nothing to do this round: keep the next round's keys behind a barrier all the same
 		while (processed != (1u << G) - 1) {
 			// ---- the first pending bunch of the round: every run of it is scanned against one table ----
 			const unsigned long long K = keys[__ffs(~processed) - 1];
@@ -515,7 +522,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 			bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
 			if (qi < n) { Q = A.qi[q0 + qi]; act = Q.cls != 0; }
 			if (sub == 0) kq[qi] = Q.k;
-			__syncthreads();
+			block_barrier();
 			{
 				const uint32_t np = act ? Q.k + 1u : 0u, plen = act ? Q.len / np : 0u;
 				const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi);
@@ -532,7 +539,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 					} else if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(0, 0, 0, 0);
 				}
 			}
-			const bool anyact = __syncthreads_or(act);
+			const bool anyact = block_barrier_or(act);
 			if (active) {
 				if (staged) { mbar_wait(bar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
 				if (anyact) {
@@ -637,7 +644,7 @@ __global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
 		}
 				}
 			}
-			__syncthreads();                                               // the table is free for the next bunch of the round
+			block_barrier();                                               // the table is free for the next bunch of the round
 		}
 	}
 }
