@@ -461,7 +461,7 @@ __device__ __forceinline__ void block_barrier() { __syncwarp(); __syncthreads();
 __device__ __forceinline__ bool block_barrier_or(bool p) { __syncwarp(); return __syncthreads_or(p) != 0; }
 
 template <int STRIDE, bool FULLW>   // FULLW: 16-base windows (no mask on the older word)
-__global__ void __launch_bounds__(128) k_seed(SeedArgs A) {
+__global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 	extern __shared__ __align__(128) uint32_t smem[];
 	const uint32_t G = blockDim.x >> 4;                                    // groups of the block = runs per round
 	const uint32_t grp = threadIdx.x >> 4, l = threadIdx.x & 15;          // group, reference lane within the run
@@ -847,7 +847,9 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			uint32_t w1 = lane_word_or0(lanew, ++wi, nwords);
 			uint32_t feed = __funnelshift_r(w0, w1, sh), qw = __ldg(Wq);
 			const uint32_t ngroups = (m + 7) >> 3;
+			uint32_t bpre = k;                               // the slot's running minimum, fetched 16 rows before it is applied
 			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
+				if (!(gq & 1) && A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + Q.slot);
 				// next group's words (ignored after the last group)
 				w0 = w1; w1 = lane_word_or0(lanew, ++wi, nwords);
 				const uint32_t nfeed = __funnelshift_r(w0, w1, sh), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
@@ -885,8 +887,8 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					if (rowmin >= inf) { dead = true; break; }   // every lane cell > maxED: the reference truncates (burst.c:1062-1065)
 					++y;
 				}
-				if (!dead && (gq & 1) && A.mode == BG_MODE_MIN) {  // every 16 rows: tighten Emac as better hits land (burst.c:4159, 4220)
-					k = min(k, A.best[Q.slot]); inf = (k + 1) << 22;
+				if (!dead && (gq & 1) && A.mode == BG_MODE_MIN) {  // every 16 rows: tighten Emac as better hits land (burst.c:4159, 4220);
+					k = min(k, bpre); inf = (k + 1) << 22;         // a value read 16 rows ago is only less tight, never wrong
 				}
 				feed = nfeed; qw = nqw;
 			}
@@ -1047,7 +1049,8 @@ struct bg_ctx {
 	int device = 0;
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
-	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 1;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
+	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
+	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
@@ -1159,6 +1162,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 		c->seed_words = value; return BG_OK;
 	}
 	if (what == BG_PARAM_SEED_STAGE) { c->seed_stage = value != 0; return BG_OK; }
+	if (what == BG_PARAM_SEED_GROUPS) { if (value != 0 && value != 2 && value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed groups %d must be 0, 2, 4 or 8", value); c->seed_groups = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_RATIO) { if (value && (value < 10 || value > 300)) return fail(BG_EINVAL, "bg_set_param: slice ratio %d must be 0 (auto) or 10..300", value); c->pipe_ratio = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_MIN_RUNS) { if (value < 1) return fail(BG_EINVAL, "bg_set_param: minimum runs per slice %d", value); c->pipe_min_runs = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_SLICES) { if (value < 0 || value > 64) return fail(BG_EINVAL, "bg_set_param: pipeline slices %d out of range 0..64", value); c->pipe_slices = value; return BG_OK; }
@@ -1394,13 +1398,13 @@ static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const S
 		S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 		memcpy(S.m16, c->m16, sizeof(S.m16));
 		// groups (runs per round) per block: the count that keeps the most runs in flight per SM
-		uint32_t gpb = 8, best_inflight = 0;
-		for (uint32_t g = 8; g >= 2; g >>= 1) {
-			const size_t b = (size_t)seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage, g).total * 4 + 1024;
-			const uint32_t inflight = (uint32_t)std::min<size_t>(220 * 1024 / b, 2048 / (g * 16)) * g;
-			if (inflight > best_inflight) { best_inflight = inflight; gpb = g; }
-		}
-		if (!best_inflight) return fail(BG_EINVAL, "seed filter tables do not fit shared memory (words %u, stretches %u)", SL.words, npmax);
+		// a block stalls as a whole on its barriers and table builds, so small blocks (4 groups = 2 warps) hide latency best
+		// (measured, profiles/): 4 unless that leaves fewer than two blocks per SM
+		uint32_t gpb = 4;
+		while (gpb > 2 && (size_t)seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage, gpb).total * 4 > 110 * 1024) gpb >>= 1;
+		if (c->seed_groups) gpb = (uint32_t)c->seed_groups;
+		if ((size_t)seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage, gpb).total * 4 > 220 * 1024)
+			return fail(BG_EINVAL, "seed filter tables do not fit shared memory (words %u, stretches %u)", SL.words, npmax);
 		const uint64_t per_block = (uint64_t)gpb * S.chunk, blocks = (B.W.nruns + per_block - 1) / per_block;
 		const size_t smem = (size_t)seed_smem(SL.words, S.hb, npmax, SL.stride, S.stage, gpb).total * sizeof(uint32_t);
 		void (*kern)(SeedArgs) = SL.stride == 8 ? (SL.w == 16 ? k_seed<8, true> : k_seed<8, false>) : (SL.w == 16 ? k_seed<4, true> : k_seed<4, false>);

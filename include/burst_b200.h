@@ -99,10 +99,11 @@ int  bg_set_stream(bg_ctx *ctx, void *cuda_stream);
 enum { BG_PARAM_SEED_FILTER = 1,     /* 1 (default): pigeonhole seed filter where the batch allows; 0: Myers prefix filter only */
        BG_PARAM_SEED_CHUNK  = 2,     /* consecutive runs handled by one warp of the seed filter (default 8) */
        BG_PARAM_SEED_WORDS  = 3,     /* 32-bit words of the per-warp window filter, power of two 128..8192 (0 = sized from the batch) */
-       BG_PARAM_SEED_STAGE  = 4,     /* 1 (default): clumps reach the seed filter through bulk copies (TMA, cp.async.bulk + mbarrier) into shared
-                                        memory, one run ahead; 0: direct 128-bit loads */
+       BG_PARAM_SEED_STAGE  = 4,     /* 1: clumps reach the seed filter through bulk copies (TMA, cp.async.bulk + mbarrier) into shared memory,
+                                        one run ahead; 0 (default): direct 128-bit loads, which leave room for more resident blocks */
        BG_PARAM_PIPE_SLICES = 5 };   /* slices the one-call run-list path cuts a large batch into so that host->device copies overlap the kernels
                                         (default 4; 0 or 1 = one upload, then run) */
+enum { BG_PARAM_SEED_GROUPS = 8 };   /* 16-thread groups (runs per round) per block of the seed filter: 2, 4 or 8; 0 (default) = 4 when the tables allow */
 enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096): lists shorter than two slices take the single-batch path */
        BG_PARAM_PIPE_RATIO = 7 };    /* size of each slice in percent of the one before; 0 (default) = 100 for byte codes (copy-bound), 140 for
                                         BG_Q_PACKED4 (kernel-bound: a short first copy, later copies hide behind the kernels) */

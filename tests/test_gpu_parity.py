@@ -370,7 +370,7 @@ def test_seed_layouts_and_tuning_knobs(eng, oracle):
     try:
         for k, want in ((2, (8, 16)), (3, (8, 16)), (4, (4, 16)), (5, (4, 13)), (6, (4, 11))):
             reads, _ = synth.reads_from_clumps(packed, off, clen, 150, 100, k, rng)
-            for chunk, words, stage in ((8, 0, 1), (1, 128, 1), (5, 256, 0), (64, 4096, 1)):
+            for chunk, words, stage in ((8, 0, 0), (1, 128, 1), (5, 256, 0), (64, 4096, 1)):
                 eng.set_param(PARAM_SEED_CHUNK, chunk); eng.set_param(PARAM_SEED_WORDS, words); eng.set_param(PARAM_SEED_STAGE, stage)
                 hits, st = check(eng, oracle, packed, off, clen, reads, [k] * len(reads), mode=0)
                 assert (st["seed_stride"], st["seed_window"]) == want, (k, st)
@@ -378,7 +378,7 @@ def test_seed_layouts_and_tuning_knobs(eng, oracle):
         eng.set_param(PARAM_SEED_CHUNK, 3); eng.set_param(PARAM_SEED_WORDS, 128)
         check(eng, oracle, packed, off, clen, reads, [6] * len(reads), mode=1)
     finally:
-        eng.set_param(PARAM_SEED_CHUNK, 8); eng.set_param(PARAM_SEED_WORDS, 0); eng.set_param(PARAM_SEED_STAGE, 1)
+        eng.set_param(PARAM_SEED_CHUNK, 8); eng.set_param(PARAM_SEED_WORDS, 0); eng.set_param(PARAM_SEED_STAGE, 0)
 
 
 def test_malformed_input_is_an_error_not_a_crash(eng, oracle):
@@ -432,20 +432,21 @@ def test_bench_shape_at_scale(eng):
         h2, b2 = eng.align(w["qcodes"][: int(w["qoff"][nqs])], w["qoff"][: nqs + 1], w["budget"][:nqs], None, 0, slot=w["slot"][:nqs], nslots=w["nslots"], runs=sub)
         assert np.array_equal(h1, h2) and np.array_equal(b1, b2) and len(h1) > 1000
     finally:
-        eng.set_seed_filter(True); eng.set_param(PARAM_SEED_STAGE, 1)
+        eng.set_seed_filter(True); eng.set_param(PARAM_SEED_STAGE, 0)
 
 
-def test_seed_filter_with_direct_loads(eng, oracle):
-    """BG_PARAM_SEED_STAGE = 0: clumps reach the seed filter through plain 128-bit loads instead of the default
-    cp.async.bulk (TMA) + mbarrier staging, one run ahead.  Same results."""
-    from burst_b200.engine import PARAM_SEED_STAGE
+def test_seed_filter_with_tma_staging(eng, oracle):
+    """BG_PARAM_SEED_STAGE = 1: clumps reach the seed filter through cp.async.bulk (TMA) + mbarrier staging, one run ahead,
+    instead of the default direct 128-bit loads; 8, 4 and 2 groups per block.  Same results."""
+    from burst_b200.engine import PARAM_SEED_STAGE, PARAM_SEED_GROUPS
     rng = np.random.default_rng(47)
     refs = synth.random_refs(16 * 9, 230, rng, jitter=40)
     packed, off, clen = synth.pack_clumps(refs)
     reads, _ = synth.reads_from_clumps(packed, off, clen, 150, 100, 2, rng)
     try:
-        eng.set_param(PARAM_SEED_STAGE, 0)
-        hits, st = check(eng, oracle, packed, off, clen, reads, [2] * len(reads), mode=0)
-        assert len(hits) >= 100
+        for stage, groups in ((1, 0), (1, 8), (0, 8), (1, 2), (0, 2)):
+            eng.set_param(PARAM_SEED_STAGE, stage); eng.set_param(PARAM_SEED_GROUPS, groups)
+            hits, st = check(eng, oracle, packed, off, clen, reads, [2] * len(reads), mode=0)
+            assert len(hits) >= 100
     finally:
-        eng.set_param(PARAM_SEED_STAGE, 1)
+        eng.set_param(PARAM_SEED_STAGE, 0); eng.set_param(PARAM_SEED_GROUPS, 0)
