@@ -850,9 +850,8 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			uint32_t bpre = k;                               // the slot's running minimum, fetched 16 rows before it is applied
 			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
 				if (!(gq & 1) && A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + Q.slot);
-				// next group's words (ignored after the last group)
-				w0 = w1; w1 = lane_word_or0(lanew, ++wi, nwords);
-				const uint32_t nfeed = __funnelshift_r(w0, w1, sh), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
+				// next group's words: issued here, first touched after the 8 rows below (ignored after the last group)
+				const uint32_t wn = lane_word_or0(lanew, ++wi, nwords), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
 				#pragma unroll
 				for (int r = 0; r < 8; ++r) {
 					if (y > m) break;
@@ -890,7 +889,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 				if (!dead && (gq & 1) && A.mode == BG_MODE_MIN) {  // every 16 rows: tighten Emac as better hits land (burst.c:4159, 4220);
 					k = min(k, bpre); inf = (k + 1) << 22;         // a value read 16 rows ago is only less tight, never wrong
 				}
-				feed = nfeed; qw = nqw;
+				w0 = w1; w1 = wn; feed = __funnelshift_r(w0, w1, sh); qw = nqw;
 			}
 			if (!dead) y = m + 1;
 		} else {
