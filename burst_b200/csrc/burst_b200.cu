@@ -847,9 +847,11 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			uint32_t w1 = lane_word_or0(lanew, ++wi, nwords);
 			uint32_t feed = __funnelshift_r(w0, w1, sh), qw = __ldg(Wq);
 			const uint32_t ngroups = (m + 7) >> 3;
-			uint32_t bpre = k;                               // the slot's running minimum, fetched 16 rows before it is applied
+			uint32_t bpre = k;                               // the slot's running minimum, fetched one group (8 rows) before it is applied
 			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
-				if (!(gq & 1) && A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + Q.slot);
+				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
+				k = min(k, bpre); inf = (k + 1) << 22;
+				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + Q.slot);
 				// next group's words: issued here, first touched after the 8 rows below (ignored after the last group)
 				const uint32_t wn = lane_word_or0(lanew, ++wi, nwords), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
 				#pragma unroll
@@ -885,9 +887,6 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					}
 					if (rowmin >= inf) { dead = true; break; }   // every lane cell > maxED: the reference truncates (burst.c:1062-1065)
 					++y;
-				}
-				if (!dead && (gq & 1) && A.mode == BG_MODE_MIN) {  // every 16 rows: tighten Emac as better hits land (burst.c:4159, 4220);
-					k = min(k, bpre); inf = (k + 1) << 22;         // a value read 16 rows ago is only less tight, never wrong
 				}
 				w0 = w1; w1 = wn; feed = __funnelshift_r(w0, w1, sh); qw = nqw;
 			}
