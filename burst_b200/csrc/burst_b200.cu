@@ -1034,8 +1034,9 @@ template <typename T> struct DBuf {
 
 enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
 
-// One of two device buffer sets the pipelined one-call path alternates between: while the kernels of one
-// slice run, the next slice's queries and runs are copied in on a second stream.
+// One of the device buffer sets the pipelined one-call path cycles through: while the kernels of one slice run, the
+// next slices' queries and runs are copied in on a second stream (three sets: the copies never wait for the kernels).
+#define NSLICEBUF 3
 struct Slice {
 	DBuf<uint8_t> packed, codes; DBuf<uint64_t> qoff; DBuf<uint16_t> budget; DBuf<uint32_t> slot;
 	DBuf<QInfo> qi; DBuf<uint32_t> peq, qnib; DBuf<bg_run> runs;
@@ -1074,7 +1075,7 @@ struct bg_ctx {
 	int last_mode = 0; std::vector<uint16_t> last_best_in; bool have_best_in = false;
 	bg_stats stats;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-	Slice sl[2]; cudaStream_t copy_stream = nullptr; DBuf<uint32_t> d_first; int pipe_slices = 4, pipe_min_runs = 4096, pipe_ratio = 0;   // pipelined one-call path
+	Slice sl[NSLICEBUF]; cudaStream_t copy_stream = nullptr; DBuf<uint32_t> d_first; int pipe_slices = 4, pipe_min_runs = 4096, pipe_ratio = 0;   // pipelined one-call path
 	uint32_t h_counters[4] = {0, 0, 0, 0};
 	bool ran = false, sorted = false;
 };
@@ -1112,7 +1113,7 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)); c->own_stream = true;
 	for (int i = 0; i < 4; ++i) CU(cudaEventCreate(&c->ev[i]));
 	CU(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
-	for (int i = 0; i < 2; ++i) { CU(cudaEventCreateWithFlags(&c->sl[i].copied, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->sl[i].computed, cudaEventDisableTiming)); }
+	for (int i = 0; i < NSLICEBUF; ++i) { CU(cudaEventCreateWithFlags(&c->sl[i].copied, cudaEventDisableTiming)); CU(cudaEventCreateWithFlags(&c->sl[i].computed, cudaEventDisableTiming)); }
 	CU(cudaMallocHost((void **)&c->h_pinned, 256));
 	memset(&c->stats, 0, sizeof(c->stats));
 	// tuning knobs may also come from the environment (the drop-in binary has no flags for them)
@@ -1137,7 +1138,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
 	if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-	for (int i = 0; i < 2; ++i) { c->sl[i].release(); if (c->sl[i].copied) cudaEventDestroy(c->sl[i].copied); if (c->sl[i].computed) cudaEventDestroy(c->sl[i].computed); }
+	for (int i = 0; i < NSLICEBUF; ++i) { c->sl[i].release(); if (c->sl[i].copied) cudaEventDestroy(c->sl[i].copied); if (c->sl[i].computed) cudaEventDestroy(c->sl[i].computed); }
 	c->d_first.release();
 	if (c->h_pinned) cudaFreeHost(c->h_pinned);
 	if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -1657,10 +1658,10 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			}
 			const uint32_t n = qb - qa; const uint64_t base = Q->offset[qa], bytes = Q->offset[qb] - base;
 			if (Q->offset[qb] < base) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return fail(BG_EINVAL, "bg_align_runs: query offsets are not ascending"); }
-			Slice &S = c->sl[i & 1];
+			Slice &S = c->sl[i % NSLICEBUF];
 			if (S.qoff.need((size_t)n + 1) || S.budget.need(n) || S.slot.need(n) || S.qi.need(n) ||
 			    S.peq.need((size_t)n * 16) || S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) return BG_ENOMEM;
-			if (i >= 2) CU(cudaStreamWaitEvent(ps, S.computed, 0));   // the slice two back is done with these buffers
+			if (i >= NSLICEBUF) CU(cudaStreamWaitEvent(ps, S.computed, 0));   // the slice that used these buffers last is done with them
 			{ int rc = copy_codes(Q, base, base + bytes, S.packed, S.codes, ps, ps, S.copied); if (rc) return rc; }
 			CU(cudaMemcpyAsync(S.qoff.p, Q->offset + qa, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ps));
 			CU(cudaMemcpyAsync(S.budget.p, Q->budget + qa, (size_t)n * 2, cudaMemcpyHostToDevice, ps));

@@ -30,7 +30,7 @@ _keep = PACK
 if PACK is not None:
     pp, kk = pin(Engine.pack4(w["qcodes"])); PACK = ("packed4", pp)
     pc = PACK
-for slices, ratio in ((4, 100), (4, 100), (4, 120), (5, 120), (5, 130), (6, 120), (4, 140), (3, 130), (5, 100)):
+for slices, ratio in ((4, 140), (4, 140), (4, 100), (4, 120), (5, 110), (3, 120), (6, 100), (8, 100), (5, 130)):
     eng.set_param(PARAM_PIPE_SLICES, slices); eng.set_param(PARAM_PIPE_RATIO, ratio)
     ts = []
     for it in range(4):
