@@ -101,6 +101,28 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Best effort: run this rank on the CPUs of the NUMA node its GPU hangs off, so that first-touch places the pinned
+    host buffers there and N ranks do not funnel their host->device copies through one socket.  Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        addr = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % addr).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def build_workload(args, rank):
     from burst_b200 import synth
     t0 = time.time()
@@ -161,7 +183,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     config = {"workload": "configs[1]: %d x %d bp reads (exactly %d edits, LLsim model, fwd+rc strands) per GPU vs %d MB synthetic .edx-layout DB (%d-column clumps), -i 0.98 budget %d, BEST-style min selection, task list = reference bunch driver (QBUNCH 16 x bunch candidates)" % (
         args.reads, args.read_len, args.edits, args.db_mb, args.clump_len, args.edits),
-        "reads_per_gpu": args.reads, "db_mb": args.db_mb, "sharding": "queries (DB replicated), no data-path collective",
+        "reads_per_gpu": args.reads, "db_mb": args.db_mb, "sharding": "queries (DB replicated), no data-path collective", "numa_node_rank0": None,
         "l2": "inputs (DB %d MB + tasks) exceed the 126 MB L2; no explicit flush" % args.db_mb}
 
     if args.impl == "reference":
@@ -181,11 +203,13 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the DP path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)             # host buffers (pinned) and the calling thread next to the GPU's PCIe root
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
             os.environ["NCCL_DEBUG"] = "WARN"              # keep rank 0's stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from burst_b200.engine import Engine, MODE_MIN, RUN_DTYPE
+    config["numa_node_rank0"] = numa
 
     w = build_workload(args, rank)
     stream = torch.cuda.Stream()
