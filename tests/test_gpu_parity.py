@@ -266,6 +266,13 @@ def test_pipelined_one_call_path(eng, oracle):
                     buf = np.zeros(len(ohits) + 5, HIT_DTYPE); b2 = np.full(nslots, 0xFFFF, np.uint16) if bi is None else bi.copy()
                     n = eng.align_runs_into(codes, qoff, budget, runs, buf, b2, mode, slot=slot, nslots=nslots)
                     assert n == len(ohits) and np.array_equal(buf[:n], ohits) and np.array_equal(b2, obest)
+        # a list in no particular order: every slice then spans (almost) the whole query array -- slower, same answers
+        shuf = runs[rng.permutation(len(runs))]
+        eng.set_param(PARAM_PIPE_SLICES, 0)
+        want_h, want_b = eng.align(codes, qoff, budget, None, 0, slot=slot, nslots=nslots, runs=shuf)
+        eng.set_param(PARAM_PIPE_SLICES, 4)
+        got_h, got_b = eng.align(codes, qoff, budget, None, 0, slot=slot, nslots=nslots, runs=shuf)
+        assert np.array_equal(got_h, want_h) and np.array_equal(got_b, want_b) and len(got_h) > 100
         with pytest.raises(RuntimeError, match="room for"):
             eng.align_runs_into(codes, qoff, budget, runs, np.zeros(3, HIT_DTYPE), None, 0, slot=slot, nslots=nslots)
         bad = runs.copy(); bad["query0"][len(bad) // 2] = nq - 2; bad["nq"][len(bad) // 2] = 5
