@@ -5,14 +5,15 @@
 //   pass 2  reScoreM_mat16             burst.c:713-886     (score, shift, shiftR) + end column
 // and how this file restructures it for the GPU (DESIGN.md section 2 has the full argument):
 //   k_qinfo/k_qprep/k_qtables  per query: budget/length record, nibble-packed bases, Myers match vectors
-//   k_seed         one warp per chunk of RUNS (run = one clump visit by <= 16 consecutive queries, the
-//                  reference's "unpack the clump once, then loop over the bunch", burst.c:4141-4157).
-//                  Pigeonhole: an alignment with <= k errors leaves one of k+1 disjoint query stretches
-//                  unchanged, so some word-aligned (or half-word-aligned) window of w reference bases
-//                  equals one of `stride` windows at the end of that stretch.  The run's query windows go
-//                  into a blocked Bloom filter in shared memory; the clump is streamed once, one hash
-//                  probe per 8 (or 4) columns per lane; flagged windows are verified exactly -> seeds ->
-//                  disjoint diagonal clusters [d-k, d+k].
+//   k_seed         a block walks its RUNS (run = one clump visit by <= 16 consecutive queries, the reference's
+//                  "unpack the clump once, then loop over the bunch", burst.c:4141-4157) in rounds, one run per group
+//                  of 16 threads, one thread per reference lane.  Pigeonhole: an alignment with <= k errors leaves
+//                  one of k+1 disjoint query stretches unchanged, so some word-aligned (or half-word-aligned) window
+//                  of w reference bases equals one of `stride` windows at the end of that stretch.  The bunch's
+//                  query windows go into a blocked Bloom filter + hash table in shared memory (built once per bunch,
+//                  shared by its runs); each lane is streamed once, one hash probe per 8 (or 4) columns; a thread
+//                  verifies its own Bloom hits exactly through the table -> seeds -> disjoint diagonal clusters
+//                  [d-k, d+k].  Clumps arrive by 128-bit loads or, optionally, 1-D TMA bulk copies + mbarriers.
 //   k_filter       queries k_seed cannot take (many errors / short stretches / IUPAC bases): Myers/Hyyro bit-vector
 //                  semi-global DP of the query's first P <= 32 rows; columns with row-P value <= k
 //                  are seeds (every <= k alignment has a <= k prefix); hull of the seed diagonals.
