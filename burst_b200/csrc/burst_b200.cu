@@ -558,10 +558,11 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 			constexpr bool ST = decltype(staged_c)::value, AMB = decltype(amb_c)::value;
 			auto ld = [&](uint32_t ck) -> uint4 { return ST ? lds128(sp + (ck * 16 + l) * 16) : __ldg(gp + (size_t)ck * 16 + l); };
 			uint32_t prev = 0, prev2 = 0, ambp = 0, ambp2 = 0;
-			uint4 pc = ld(0);
+			uint4 pc = ld(0), pn = nchunks > 1 ? ld(1) : make_uint4(0, 0, 0, 0);   // two chunks (64 columns) in flight
 			for (uint32_t ck = 0; ck < nchunks; ++ck) {
 				const uint4 cw = pc;
-				if (ck + 1 < nchunks) pc = ld(ck + 1);
+				pc = pn;
+				if (ck + 2 < nchunks) pn = ld(ck + 2);
 				const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
 				uint32_t m4 = 0;
 				#pragma unroll
