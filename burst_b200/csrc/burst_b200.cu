@@ -481,6 +481,8 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 	const uint32_t HM = FULLW ? 0xFFFFFFFFu : A.SL.hm, SHW = A.SL.shw, ADD = A.SL.amb_add, ambsel = ADD == 0x33333333u ? 3u : 1u;
 	const uint32_t HBM = A.hb - 1, NPM = A.npmax;
 	const unsigned long long NOKEY = ~0ull;
+	unsigned long long tableK = NOKEY;                                     // the bunch the shared window table was built for (block-uniform)
+	bool table_any = false;                                               // ... and whether any of its queries is seeded
 
 	struct Desc { uint64_t r; uint32_t c, q0, n; bool ok; ClumpMeta M; };
 	auto load_desc = [&](uint64_t i, Desc &D) {
@@ -517,30 +519,34 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 			for (uint32_t g = 0; g < G; ++g) if (keys[g] == K) processed |= 1u << g;
 			const bool active = mykey == K;
 			const uint32_t q0 = (uint32_t)(K >> 8), n = (uint32_t)(K & 255);
-			// build: thread = (query t & 15, window phase t >> 4)
-			for (uint32_t w = threadIdx.x * 4; w < A.SL.words + A.hb; w += blockDim.x * 4) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);   // bits and head are adjacent
-			const uint32_t qi = threadIdx.x & 15, sub = threadIdx.x >> 4;
-			bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
-			if (qi < n) { Q = A.qi[q0 + qi]; act = Q.cls != 0; }
-			if (sub == 0) kq[qi] = Q.k;
-			block_barrier();
-			{
-				const uint32_t np = act ? Q.k + 1u : 0u, plen = act ? Q.len / np : 0u;
-				const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi);
-				for (uint32_t wn = sub; wn < NPM * STRIDE; wn += G) {
-					const uint32_t p = wn / STRIDE, j = wn % STRIDE;
-					if (p < np) {
-						const QStretch S = stretch_of(Wq, plen, p);
-						const QWin w = window_of(S, j);
-						const uint32_t hv = seed_hash(w.kn, w.ko & HM), e = (qi * NPM + p) * STRIDE + j;
-						atomicOr(&bits[hv >> SHW], bloom_bits(hv));
-						tag[e] = hv;
-						nxt[e] = (uint16_t)atomicExch(&head[(hv >> 10) & HBM], e + 1);
-						if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(S.r0, S.r1, S.r2, S.E);
-					} else if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(0, 0, 0, 0);
+			if (K != tableK) {                                             // (a bunch with more runs than a round keeps its table)
+				// build: thread = (query t & 15, window phase t >> 4)
+				for (uint32_t w = threadIdx.x * 4; w < A.SL.words + A.hb; w += blockDim.x * 4) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);   // bits and head are adjacent
+				const uint32_t qi = threadIdx.x & 15, sub = threadIdx.x >> 4;
+				bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
+				if (qi < n) { Q = A.qi[q0 + qi]; act = Q.cls != 0; }
+				if (sub == 0) kq[qi] = Q.k;
+				block_barrier();
+				{
+					const uint32_t np = act ? Q.k + 1u : 0u, plen = act ? Q.len / np : 0u;
+					const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (q0 + qi);
+					for (uint32_t wn = sub; wn < NPM * STRIDE; wn += G) {
+						const uint32_t p = wn / STRIDE, j = wn % STRIDE;
+						if (p < np) {
+							const QStretch S = stretch_of(Wq, plen, p);
+							const QWin w = window_of(S, j);
+							const uint32_t hv = seed_hash(w.kn, w.ko & HM), e = (qi * NPM + p) * STRIDE + j;
+							atomicOr(&bits[hv >> SHW], bloom_bits(hv));
+							tag[e] = hv;
+							nxt[e] = (uint16_t)atomicExch(&head[(hv >> 10) & HBM], e + 1);
+							if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(S.r0, S.r1, S.r2, S.E);
+						} else if (j == 0) *(uint4 *)(str + (qi * NPM + p) * 4) = make_uint4(0, 0, 0, 0);
+					}
 				}
+				table_any = block_barrier_or(act);
+				tableK = K;
 			}
-			const bool anyact = block_barrier_or(act);
+			const bool anyact = table_any;
 			if (active) {
 				if (staged) { mbar_wait(bar_s + 8 * buf, (phase >> buf) & 1u); phase ^= 1u << buf; }
 				if (anyact) {
