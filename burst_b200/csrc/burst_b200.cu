@@ -60,7 +60,7 @@ struct QInfo {            // one query of the batch
 	uint32_t slot;
 	uint16_t k;           // budget (Emac)
 	uint8_t  P;           // rows covered by the Myers prefix filter = min(32, len)
-	uint8_t  cls;         // 1: handled by k_seed (piece automaton), 0: by k_filter (Myers)
+	uint8_t  cls;         // bit 0: handled by k_seed (else by k_filter, Myers); bit 1: every base is a plain A/C/G/T
 };
 struct Surv {             // one diagonal cluster of a (task, lane) that survived the filter
 	uint32_t task;        // run * 16 + query-in-run (batch-wide)
@@ -211,10 +211,16 @@ __device__ __forceinline__ uint32_t pack_nibbles(uint32_t b0, uint32_t b1) {
 	return (uint32_t)x;
 }
 
+// nibbles of w that are not a plain base (codes 1..4): bit 3 of the nibble set
+__device__ __forceinline__ uint32_t nonplain_nibbles(uint32_t w) {
+	const uint32_t a = w & 0x77777777u;
+	return (~(a + 0x77777777u) | (a + 0x33333333u) | w) & 0x88888888u;
+}
+
 __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ qi, uint32_t nq, SeedLayout SL,
 		uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed, uint32_t *__restrict__ unseeded) {
 	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
-	bool seed = false; uint32_t nst = 0;
+	bool seed = false; uint32_t nst = 0, notplain = 0;
 	if (q < nq) {
 		const QInfo Q = qi[q];
 		// the code bytes through aligned 32-bit loads (`codes` is 256-byte aligned and padded), shifted into place
@@ -228,7 +234,8 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 			const uint32_t b0 = __funnelshift_r(w0, w1, sh), b1 = __funnelshift_r(w1, w2, sh);
 			w0 = w2; w1 = a[k + 3];
 			uint32_t w = pack_nibbles(b0, b1);
-			if (j + 8 > Q.len) w &= (1u << (4 * (Q.len - j))) - 1u;
+			if (j + 8 > Q.len) { w &= (1u << (4 * (Q.len - j))) - 1u; notplain |= nonplain_nibbles(w | (0x11111111u << (4 * (Q.len - j)))); }
+			else notplain |= nonplain_nibbles(w);
 			W[2 + (j >> 3)] = w;
 		}
 		const uint32_t np = Q.k + 1u, plen = Q.len / np;
@@ -252,7 +259,7 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 				}
 			}
 		}
-		qi[q].cls = seed;
+		qi[q].cls = (uint8_t)((seed ? 1u : 0u) | (notplain ? 0u : 2u));
 		if (seed) nst = np;
 	}
 	const uint32_t m = __ballot_sync(0xFFFFFFFFu, seed), tot = __reduce_add_sync(0xFFFFFFFFu, nst), mx = __reduce_max_sync(0xFFFFFFFFu, nst);
@@ -267,7 +274,7 @@ __global__ void k_qtables(const uint8_t *__restrict__ codes, const QInfo *__rest
 	uint32_t q = i >> 4, c = i & 15;
 	if (q >= nq) return;
 	QInfo Q = qi[q];
-	if (Q.cls) return;                                       // taken by k_seed: no Myers table needed
+	if (Q.cls & 1) return;                                   // taken by k_seed: no Myers table needed
 	const uint8_t *s = codes + Q.off;
 	const uint32_t P = Q.P;
 	uint32_t m = P < 32 ? (1u << (32 - P)) - 1 : 0;
@@ -524,7 +531,7 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 				for (uint32_t w = threadIdx.x * 4; w < A.SL.words + A.hb; w += blockDim.x * 4) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);   // bits and head are adjacent
 				const uint32_t qi = threadIdx.x & 15, sub = threadIdx.x >> 4;
 				bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
-				if (qi < n) { Q = A.qi[q0 + qi]; act = Q.cls != 0; }
+				if (qi < n) { Q = A.qi[q0 + qi]; act = (Q.cls & 1) != 0; }
 				if (sub == 0) kq[qi] = Q.k;
 				block_barrier();
 				{
@@ -658,6 +665,283 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// Phase A1, warp form (the default).  The same pigeonhole filter as k_seed above, reorganised so that
+// nothing in the steady state waits on a block-wide barrier:
+//   * a WARP owns a bunch (the <= 16 queries that share a candidate list, burst.c:4077-4157): its window
+//     set lives in the warp's private slice of shared memory -- a one-bit-per-window bitmap (the scan
+//     filter) and an open-addressing table of window ids (the exact verification) -- built by the 32
+//     lanes together and kept for every clump visit (run) of the bunch; only __syncwarp() orders it;
+//   * the two half-warps scan two runs of the bunch at a time, a thread per reference lane; the clump
+//     words of the NEXT item are in flight in a second register buffer while the current one is probed
+//     (ping-pong, no copies), and the run records + clump records of a whole segment (<= 32 runs) are
+//     fetched by one coalesced load per lane before the first of them is needed;
+//   * a probe is seven instructions: two multiply-adds (hash of the 16-base window), shift + address,
+//     one shared load, and two funnel shifts that test the bit and append it to the hit mask;
+//   * survivors of the usual kind (one query, one diagonal cluster) leave through one atomicAdd per warp.
+// Work is cut into chunks of `chunk` consecutive runs, chunks are dealt to warps round-robin; a bunch is
+// scanned by the warp whose chunk holds its first run (bunches longer than SEEDW_SPLIT runs are split), so
+// a bunch's table is built once.
+// ---------------------------------------------------------------------------------------------
+#define SEEDW_WARPS 4
+#define SEEDW_SPLIT 256
+struct SeedWArgs {
+	const uint4 *db; const ClumpMeta *meta;
+	const QInfo *qi; const uint32_t *qnib; Work W; SeedLayout SL;
+	uint64_t nwork; uint32_t chunk;                 // run indices to enumerate, runs per chunk
+	uint32_t npmax, lbits, hslots;                  // stretches per query in the table; log2 of the bitmap bits; table slots (power of two)
+	Surv *surv; uint32_t surv_cap; uint32_t *counters;
+	uint32_t m16[8];
+};
+// per-warp shared memory in words: bitmap | slots | stretch records | budgets
+__host__ __device__ __forceinline__ uint32_t seedw_warp_words(uint32_t lbits, uint32_t hslots, uint32_t npmax) {
+	return (1u << (lbits - 5)) + hslots + 64 * npmax + 16;
+}
+
+template <int STRIDE, bool FULLW, int NCH>
+__global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(SeedWArgs A) {
+	extern __shared__ __align__(16) uint32_t smem[];
+	constexpr uint32_t FULL = 0xFFFFFFFFu;
+	constexpr int NW = NCH * 4;                                           // words (of 8 columns) per item
+	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l = lane & 15;
+	const uint32_t BW = 1u << (A.lbits - 5), HSM = A.hslots - 1, NPM = A.npmax;
+	uint32_t *sM = smem;
+	uint32_t *bits = smem + 16 + warp * seedw_warp_words(A.lbits, A.hslots, NPM), *slots = bits + BW, *str = slots + A.hslots, *kq = str + 64 * NPM;
+	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits);
+	if (threadIdx.x < 16) sM[threadIdx.x] = (A.m16[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xFFFFu;
+	__syncthreads();
+	const uint32_t HM = FULLW ? FULL : A.SL.hm, SHB = 32 - (A.lbits - 5), ADD = A.SL.amb_add, ambsel = ADD == 0x33333333u ? 3u : 1u;
+	const unsigned long long NOKEY = ~0ull;
+	unsigned long long tableK = NOKEY; bool table_any = false;            // the bunch the warp's table holds; whether any of its queries is seeded
+	const uint64_t nchunk = (A.nwork + A.chunk - 1) / A.chunk;
+	LaneSeeds LS; LS.n = 0;                                                // local memory; touched only by lanes that see several queries or far-apart seeds
+
+	auto key_of = [&](uint64_t i) -> unsigned long long {                  // (query0, nq) of work item i
+		uint64_t r; uint32_t c, q0, n; get_work(A.W, i, r, c, q0, n);
+		return ((unsigned long long)q0 << 8) | n;
+	};
+
+	for (uint64_t ch = (uint64_t)blockIdx.x * SEEDW_WARPS + warp; ch < nchunk; ch += (uint64_t)gridDim.x * SEEDW_WARPS) {
+		uint64_t i = ch * A.chunk;
+		const uint64_t cend = min(A.nwork, i + A.chunk);
+		// ---- runs at the head of the chunk that continue a bunch begun in an earlier chunk belong to that chunk's warp ----
+		if (i % SEEDW_SPLIT) {
+			unsigned long long kprev = key_of(i - 1);
+			for (;;) {
+				const uint64_t me = i + lane;
+				const unsigned long long k = me < cend ? key_of(me) : NOKEY;
+				unsigned long long pk = __shfl_up_sync(FULL, k, 1);
+				if (lane == 0) pk = kprev;
+				const uint32_t b = __ballot_sync(FULL, k != pk || me % SEEDW_SPLIT == 0 || me >= cend);
+				if (b) { i += __ffs(b) - 1; break; }
+				kprev = __shfl_sync(FULL, k, 31); i += 32;
+			}
+			if (i >= cend) continue;
+		}
+		// ---- segments: <= 32 consecutive runs of one bunch ----
+		for (;;) {
+			uint64_t d_r = 0; uint32_t d_c = 0, q0 = 0, n = 0; bool d_ok = false;
+			unsigned long long k = NOKEY;
+			if (i + lane < A.nwork) { d_ok = get_work(A.W, i + lane, d_r, d_c, q0, n); k = ((unsigned long long)q0 << 8) | n; }
+			const unsigned long long K = __shfl_sync(FULL, k, 0);
+			const uint32_t lim = (uint32_t)min((uint64_t)32, min(A.nwork - i, (uint64_t)SEEDW_SPLIT - i % SEEDW_SPLIT));
+			const uint32_t same = __ballot_sync(FULL, k == K && lane < lim);
+			const uint32_t seglen = same == FULL ? 32u : (uint32_t)__ffs(~same) - 1u;        // >= 1
+			d_ok = d_ok && lane < seglen;
+			uint4 d_m = make_uint4(0, 0, 0, 0);
+			if (d_ok) d_m = __ldg((const uint4 *)(A.meta + d_c));              // clump record of this lane's run: offset (uint4 units), length, flags
+			const uint32_t d_r32 = (uint32_t)d_r;
+
+			// ---- the bunch's window set ----
+			if (K != tableK) {
+				const uint32_t bq0 = (uint32_t)(K >> 8), bn = (uint32_t)(K & 255);
+				for (uint32_t w = lane * 4; w < BW + A.hslots; w += 128) *(uint4 *)(bits + w) = make_uint4(0, 0, 0, 0);   // bitmap and slots are adjacent
+				bool act = false; QInfo Q; Q.len = 0; Q.k = 0; Q.off = 0;
+				if (l < bn) { Q = A.qi[bq0 + l]; act = (Q.cls & 1) != 0; }           // both half-warps read the same 16 records
+				if (half == 0) kq[l] = Q.k;
+				__syncwarp();
+				const uint32_t np = act ? Q.k + 1u : 0u, plen = act ? Q.len / np : 0u;
+				const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (bq0 + l);
+				for (uint32_t p = half; p < NPM; p += 2) {                     // thread = (query l, stretches of its half's parity)
+					const uint32_t si = l * NPM + p;
+					if (p < np) {
+						const QStretch S = stretch_of(Wq, plen, p);
+						*(uint4 *)(str + si * 4) = make_uint4(S.r0, S.r1, S.r2, S.E);
+						#pragma unroll
+						for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
+							const QWin w = window_of(S, j);
+							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
+							atomicOr(&bits[hv >> SHB], 0x80000000u >> (hv & 31));
+							uint32_t s = (hv >> 4) & HSM;
+							while (atomicCAS(&slots[s], 0u, si * STRIDE + j + 1u) != 0u) s = (s + 1) & HSM;
+						}
+					} else *(uint4 *)(str + si * 4) = make_uint4(0, 0, 0, 0);
+				}
+				table_any = __any_sync(FULL, act);
+				tableK = K;
+				__syncwarp();
+			}
+
+			if (table_any && __any_sync(FULL, d_ok)) {
+				// ---- scan: each half-warp walks every other run of the segment; item = NCH chunks (32 columns each) of a run ----
+				struct RunD { uint64_t off; uint32_t len, flags, r; bool valid; };
+				auto fetch = [&](uint32_t t) -> RunD {                        // record of run t of the segment, from the lane that holds it
+					const uint32_t src = min(t, 31u);
+					RunD D;
+					D.off = (uint64_t)__shfl_sync(FULL, d_m.x, src) | ((uint64_t)__shfl_sync(FULL, d_m.y, src) << 32);
+					D.len = __shfl_sync(FULL, d_m.z, src); D.flags = __shfl_sync(FULL, d_m.w, src); D.r = __shfl_sync(FULL, d_r32, src);
+					D.valid = __shfl_sync(FULL, (uint32_t)d_ok, src) != 0 && t < seglen;
+					return D;
+				};
+				auto issue = [&](uint4 (&buf)[NCH], const RunD &D, uint32_t g) {
+					const uint32_t nchunks = (D.len + 31) >> 5;
+					const uint4 *gp = A.db + D.off + l;
+					#pragma unroll
+					for (int c = 0; c < NCH; ++c) {
+						const uint32_t ck = g * NCH + c;
+						buf[c] = (D.valid && ck < nchunks) ? __ldg(gp + (size_t)ck * 16) : make_uint4(0, 0, 0, 0);
+					}
+				};
+				uint32_t ct = half, cg = 0;                                    // current run (index in the segment) and item within it
+				RunD C = fetch(ct);
+				uint32_t prev = 0, prev2 = 0, ambp = 0, ambp2 = 0;             // scan state carried from item to item of a run
+				uint32_t sn = 0, sq = 0; int dlo = 0, dhi = 0;                 // seeds of the current run: 0 none, 1 one query + a narrow hull (registers), 2 list (LS)
+				bool more = true;
+
+				auto seed = [&](uint32_t q, int dg) {
+					if (sn == 0) { sn = 1; sq = q; dlo = dhi = dg; return; }
+					if (sn == 1) {
+						const int nlo = min(dlo, dg), nhi = max(dhi, dg);
+						if (q == sq && nhi - nlo <= 2 * (int)kq[q] + 1) { dlo = nlo; dhi = nhi; return; }
+						// the hull so far is one cluster [dlo-k, dhi+k]: its two ends stand for it in the list
+						LS.q[0] = LS.q[1] = sq; LS.d[0] = dlo; LS.d[1] = dhi; LS.n = 2; sn = 2;
+					}
+					if (LS.n < SEED_LIST) { LS.q[LS.n] = q; LS.d[LS.n] = dg; ++LS.n; }
+					else lane_seeds_overflow(LS, q, dg);
+				};
+
+				auto step = [&](uint4 (&cur)[NCH], uint4 (&nxt)[NCH]) {
+					// ---- the item after this one: load it now, probe it in the next step ----
+					const uint32_t ngroups = C.valid ? (((C.len + 31) >> 5) + NCH - 1) / NCH : 1u;
+					const bool lastg = cg + 1 >= ngroups;
+					const uint32_t nt = lastg ? ct + 2 : ct, ng = lastg ? 0u : cg + 1;
+					const RunD F = fetch(nt);
+					const RunD N = lastg ? F : C;
+					issue(nxt, N, ng);
+					bool emit = false; Surv ev; ev.task = 0; ev.lo = 0; ev.w_lane = 0; ev.scratch = 0;
+					if (C.valid) {
+						const uint32_t nchunks = (C.len + 31) >> 5;
+						const bool amb_on = (C.flags & ambsel) != 0;
+						if (cg == 0) { prev = prev2 = ambp = ambp2 = 0; }
+						uint32_t m8 = 0, m4 = 0;
+						auto scan = [&](auto amb_c) {
+							constexpr bool AMB = decltype(amb_c)::value;
+							#pragma unroll
+							for (int c = 0; c < NCH; ++c) {
+								const uint32_t ws[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
+								#pragma unroll
+								for (int j = 0; j < 4; ++j) {
+									const uint32_t cu = ws[j];
+									const uint32_t h8 = seed_hash(cu, prev & HM);
+									uint32_t t8 = __funnelshift_l(0u, lds32(bits_s + ((h8 >> SHB) << 2)), h8);     // the window's bit -> bit 31
+									uint32_t t4 = 0;
+									if (STRIDE == 4) {
+										const uint32_t h4 = seed_hash(__funnelshift_r(prev, cu, 16), __funnelshift_r(prev2, prev, 16) & HM);
+										t4 = __funnelshift_l(0u, lds32(bits_s + ((h4 >> SHB) << 2)), h4);
+									}
+									if (AMB) {
+										const uint32_t ambc = amb_nibbles(cu, ADD);
+										if (ambc | ambp) t8 = 0x80000000u;
+										if (ambc | ambp | ambp2) t4 = 0x80000000u;
+										ambp2 = ambp; ambp = ambc;
+									}
+									m8 = __funnelshift_l(t8, m8, 1);                       // word w of the item -> bit NW-1-w
+									if (STRIDE == 4) m4 = __funnelshift_l(t4, m4, 1);
+									prev2 = prev; prev = cu;
+								}
+							}
+						};
+						if (amb_on) scan(std::true_type{}); else scan(std::false_type{});
+						const uint32_t nvalid = min((uint32_t)NW, nchunks * 4 - cg * NW);
+						const uint32_t vm = nvalid >= 32 ? FULL : (((1u << nvalid) - 1u) << (NW - nvalid));
+						m8 &= vm; m4 &= vm;
+						// ---- verify this lane's flagged words against the window table; seeds -> clusters ----
+						if (m8 | m4) {
+							const uint4 *gp = A.db + C.off;
+							auto word_at = [&](uint32_t wi) -> uint32_t { return __ldg((const uint32_t *)(gp + (size_t)(wi >> 2) * 16 + l) + (wi & 3)); };
+							auto verify = [&](uint32_t wi, int e) {
+								const uint32_t cu = word_at(wi), pv = wi >= 1 ? word_at(wi - 1) : 0u, pv2 = (e == 4 && wi >= 2) ? word_at(wi - 2) : 0u;
+								const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
+								const int x1 = (int)(wi * 8 + e);
+								if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the bunch, through the table
+									for (uint32_t si = 0; si < 16 * NPM; ++si) {
+										const uint4 rec = *(const uint4 *)(str + si * 4);
+										if (!rec.w) continue;
+										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
+										for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
+											const QWin w = window_of(S, j);
+											if (window_matches_table(sM, w.kn, w.ko & HM, rn, ro, A.SL.w)) seed(si / NPM, x1 - (int)w.y1);
+										}
+									}
+								} else {
+									const uint32_t hv = seed_hash(rn, ro);
+									for (uint32_t s = (hv >> 4) & HSM;; s = (s + 1) & HSM) {
+										const uint32_t en = slots[s];
+										if (!en) break;
+										const uint32_t si = (en - 1) / STRIDE, j = (en - 1) % STRIDE;
+										const uint4 rec = *(const uint4 *)(str + si * 4);
+										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
+										const QWin w = window_of(S, j);
+										if (w.kn == rn && (w.ko & HM) == ro) seed(si / NPM, x1 - (int)w.y1);
+									}
+								}
+							};
+							while (m8 | m4) {                                          // in column order: the half-word window of a word comes before its full-word window
+								const uint32_t b = 31 - __clz(m8 | m4), bit = 1u << b, wi = cg * NW + (NW - 1 - b);
+								if (STRIDE == 4 && (m4 & bit)) verify(wi, 4);
+								if (m8 & bit) verify(wi, 8);
+								m8 &= ~bit; m4 &= ~bit;
+							}
+						}
+						// ---- end of the run: its seeds leave as survivors ----
+						if (lastg && sn) {
+							const uint32_t task0 = (C.r + A.W.run_base) * BG_RUN_MAX;
+							if (sn == 1) {
+								const int k0 = (int)kq[sq];
+								const uint32_t W = (uint32_t)(dhi - dlo + 2 * k0 + 1);
+								emit = true; ev.task = task0 + sq; ev.lo = dlo - k0; ev.w_lane = (W << 8) | (1u << 4) | l;
+								if (W > 64) ev.scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+							} else lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters);
+							sn = 0;
+						}
+					}
+					const uint32_t em = __ballot_sync(FULL, emit);
+					if (em) {
+						uint32_t base = 0;
+						if (lane == (uint32_t)__ffs(em) - 1) base = atomicAdd(&A.counters[C_SURV], (uint32_t)__popc(em));
+						base = __shfl_sync(FULL, base, __ffs(em) - 1);
+						const uint32_t pos = base + __popc(em & ((1u << lane) - 1u));
+						if (emit && pos < A.surv_cap) A.surv[pos] = ev;
+					}
+					ct = nt; cg = ng; C = N;
+					more = __any_sync(FULL, ct < seglen);
+				};
+
+				uint4 bufA[NCH], bufB[NCH];
+				issue(bufA, C, 0);
+				for (;;) {
+					step(bufA, bufB); if (!more) break;
+					step(bufB, bufA); if (!more) break;
+				}
+			}
+
+			i += seglen;
+			if (i >= A.nwork) break;
+			if (i >= cend && (i % SEEDW_SPLIT == 0 || key_of(i) != K)) break;  // past the chunk: go on only while the bunch does
+		}
+	}
+}
+
+// ---------------------------------------------------------------------------------------------
 // Phase A2: Myers bit-parallel prefix filter.  128 threads = 8 tasks x 16 lanes.
 // ---------------------------------------------------------------------------------------------
 struct FilterArgs {
@@ -696,7 +980,7 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	uint32_t q = 0, c = 0, q0 = 0, n = 0;
 	if (valid) { valid = get_run(A.W, r, c, q0, n) && qi_ < n; q = q0 + qi_; }
 	QInfo Q; Q.cls = 1; Q.P = 0; Q.k = 0;
-	if (valid) { Q = A.qi[q]; valid = !Q.cls; }                   // seed-eligible queries were handled by k_seed
+	if (valid) { Q = A.qi[q]; valid = !(Q.cls & 1); }                   // seed-eligible queries were handled by k_seed
 	sPeq[slot][lane] = valid ? A.peq[(size_t)q * 16 + lane] : 0;
 	__syncwarp();
 	if (!valid) continue;
@@ -776,7 +1060,8 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 struct ExtendArgs {
 	const uint32_t *dbw; const ClumpMeta *meta;
 	const uint8_t *codes; const uint32_t *qnib; const QInfo *qi; Work W;
-	const Surv *surv; uint32_t surv_cap; const uint32_t *counters; const uint32_t *first;   // first: survivors before *first belong to earlier slices
+	const Surv *surv; uint32_t surv_cap; const uint32_t *counters;
+	const uint32_t *cls, *order;                         // survivors of this launch binned by band class (k_bin_*)
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
 	uint32_t *scratch; uint32_t scratch_cap;
 	unsigned long long *band_cells;
@@ -802,18 +1087,62 @@ __device__ __forceinline__ uint32_t lane_word_or0(const uint32_t *lanew, int wi,
 	return (wi >= 0 && wi < nwords) ? __ldg(lanew + (size_t)(wi >> 2) * 64 + (wi & 3)) : 0u;
 }
 
+// Band classes: a survivor goes to the narrowest register band that holds its cluster (W = hull of the seed
+// diagonals + 2k); above 64 the band lives in global scratch.  Survivors are binned by class before the sweep
+// (k_bin_*), so that a warp's 32 threads run the same instantiation on 32 survivors.
+#define NCLASS 9
+__host__ __device__ __forceinline__ constexpr int class_width(int c) { return c == 0 ? 5 : c == 1 ? 8 : c == 2 ? 12 : c == 3 ? 16 : c == 4 ? 24 : c == 5 ? 32 : c == 6 ? 48 : c == 7 ? 64 : 0; }
+__device__ __forceinline__ uint32_t class_of(uint32_t W) { return W <= 5 ? 0u : W <= 8 ? 1u : W <= 12 ? 2u : W <= 16 ? 3u : W <= 24 ? 4u : W <= 32 ? 5u : W <= 48 ? 6u : W <= 64 ? 7u : 8u; }
+// cls: [0, NCLASS) counts, [16, 16+NCLASS) first position in `order`, [32, 32+NCLASS) fill cursors
+__global__ void k_bin_count(const Surv *__restrict__ surv, const uint32_t *__restrict__ counters, uint32_t surv_cap, const uint32_t *__restrict__ firstp, uint32_t *__restrict__ cls) {
+	__shared__ uint32_t sh[NCLASS];
+	if (threadIdx.x < NCLASS) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t nsurv = min(counters[C_SURV], surv_cap), first = firstp ? min(*firstp, nsurv) : 0u;
+	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < nsurv; i += gridDim.x * blockDim.x) atomicAdd(&sh[class_of(surv[i].w_lane >> 8)], 1u);
+	__syncthreads();
+	if (threadIdx.x < NCLASS && sh[threadIdx.x]) atomicAdd(&cls[threadIdx.x], sh[threadIdx.x]);
+}
+__global__ void k_bin_offsets(const uint32_t *__restrict__ counters, uint32_t surv_cap, const uint32_t *__restrict__ firstp, uint32_t *__restrict__ cls) {
+	if (threadIdx.x) return;
+	const uint32_t nsurv = min(counters[C_SURV], surv_cap);
+	uint32_t o = firstp ? min(*firstp, nsurv) : 0u;
+	for (int c = 0; c < NCLASS; ++c) { cls[16 + c] = o; cls[32 + c] = 0; o += cls[c]; }
+}
+__global__ void k_bin_scatter(const Surv *__restrict__ surv, const uint32_t *__restrict__ counters, uint32_t surv_cap, const uint32_t *__restrict__ firstp,
+		uint32_t *__restrict__ cls, uint32_t *__restrict__ order) {
+	const uint32_t nsurv = min(counters[C_SURV], surv_cap), first = firstp ? min(*firstp, nsurv) : 0u;
+	const uint32_t lane = threadIdx.x & 31;
+	for (uint32_t i0 = first + (blockIdx.x * blockDim.x + threadIdx.x - lane); i0 < nsurv; i0 += gridDim.x * blockDim.x) {
+		const uint32_t i = i0 + lane;
+		const uint32_t c = i < nsurv ? class_of(surv[i].w_lane >> 8) : 0xFFu;
+		// one atomic per class present in the warp; positions inside a class keep the survivor order
+		for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, i < nsurv); todo;) {
+			const uint32_t lead = __ffs(todo) - 1, cc = __shfl_sync(0xFFFFFFFFu, c, lead);
+			const uint32_t same = __ballot_sync(0xFFFFFFFFu, c == cc);
+			uint32_t base = 0;
+			if (lane == lead) base = atomicAdd(&cls[32 + cc], (uint32_t)__popc(same));
+			base = __shfl_sync(0xFFFFFFFFu, base, lead);
+			if (c == cc) order[cls[16 + cc] + base + __popc(same & ((1u << lane) - 1u))] = i;
+			todo &= ~same;
+		}
+	}
+}
+
+
 template <int WMAX>
 __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	__shared__ uint32_t sS[256];
+	constexpr int CLS = WMAX == 5 ? 0 : WMAX == 8 ? 1 : WMAX == 12 ? 2 : WMAX == 16 ? 3 : WMAX == 24 ? 4 : WMAX == 32 ? 5 : WMAX == 48 ? 6 : WMAX == 64 ? 7 : 8;
+	const uint32_t begin = A.cls[16 + CLS], count = A.cls[CLS];
+	if (!count) return;
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) sS[i] = A.Sterm[i];
 	__syncthreads();
-	const uint32_t nsurv = min(A.counters[C_SURV], A.surv_cap), first = A.first ? min(*A.first, nsurv) : 0u;
 	unsigned long long cells = 0;
-	for (uint32_t i = first + blockIdx.x * blockDim.x + threadIdx.x; i < nsurv; i += gridDim.x * blockDim.x) {
+	for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
+		const uint32_t i = A.order[begin + p];
 		const Surv sv = A.surv[i];
 		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 15;
-		// class dispatch: this instantiation takes bands that fit WMAX but not WMAX/2
-		if (WMAX == 0 ? (W <= 64) : (W > (uint32_t)WMAX || (WMAX > 8 && W <= (uint32_t)WMAX / 2))) continue;
 		uint32_t c, q0, n;
 		get_run(A.W, (sv.task >> 4) - A.W.run_base, c, q0, n);
 		const uint32_t qix = q0 + (sv.task & 15);
@@ -838,6 +1167,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			// and one query code: both are streamed as packed words, one 32-bit load of each per 8 rows
 			// (the query from its nibble-packed copy, the lane from the DB pieces), loaded one group ahead.
 			constexpr int NW = (WB + 7) / 8;
+			constexpr uint32_t TOPMASK = (WB & 7) ? (1u << (4 * (WB & 7))) - 1u : 0xFFFFFFFFu;   // nibbles of the last window word inside the band
 			uint32_t win[NW];                                // codes of columns x0 .. x0+WB-1, one nibble each
 			const int nwords = (int)((L + 7) >> 3);
 			const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * qix + 2;
@@ -851,17 +1181,63 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			uint32_t w0 = lane_word_or0(lanew, wi, nwords);
 			#pragma unroll
 			for (int j = 0; j < NW; ++j) { const uint32_t w1 = lane_word_or0(lanew, ++wi, nwords); win[j] = __funnelshift_r(w0, w1, sh); w0 = w1; }
-			// w0 = word wi now holds the first codes that enter the window; feed for rows 8g+1..8g+8 = nibbles cb+WB+8g ..
+			// the codes that enter the window in rows 8g+1 .. 8g+8 are nibbles cb+WB+8g .. : the word pair (w0, w1) shifted by sh2
+			constexpr int EXTRA = (NW * 8 - WB);             // nibbles of the last window word beyond the band: they are the first to enter
+			const uint32_t sh2 = (uint32_t)((cb + WB) & 7) * 4;
+			if (EXTRA) { wi = (cb + WB) >> 3; w0 = lane_word_or0(lanew, wi, nwords); }
+			win[NW - 1] &= TOPMASK;
 			uint32_t w1 = lane_word_or0(lanew, ++wi, nwords);
-			uint32_t feed = __funnelshift_r(w0, w1, sh), qw = __ldg(Wq);
+			uint32_t feed = __funnelshift_r(w0, w1, sh2), qw = __ldg(Wq);
 			const uint32_t ngroups = (m + 7) >> 3;
 			uint32_t bpre = k;                               // the slot's running minimum, fetched one group (8 rows) before it is applied
+			// Fast rows: query and reference codes all plain bases, band inside the matrix, short query.  Then the substitution cost is
+			// "the nibbles differ" (one XOR per row, no table), and cells above the budget need no clamp: they can never win or tie a
+			// cell within it, and with m + WB < 480 no field of the key can overflow.
+			const bool fastok = WMAX <= 32 && (Q.cls & 2) && m + WB + 8 < 480;
+			int badrows = 0;                                 // rows during which the window may still hold a code that is not a plain base
+			#pragma unroll
+			for (int j = 0; j < NW; ++j) if (nonplain_nibbles(win[j] | (j == NW - 1 ? ~TOPMASK & 0x11111111u : 0u))) badrows = WB;
 			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
 				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
 				k = min(k, bpre); inf = (k + 1) << 22;
 				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + Q.slot);
 				// next group's words: issued here, first touched after the 8 rows below (ignored after the last group)
 				const uint32_t wn = lane_word_or0(lanew, ++wi, nwords), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
+				const int x0g = (int)y + lo;                 // column (1-based) of band cell 0 in the first row of the group
+				if (nonplain_nibbles(feed)) badrows = WB + 8;
+				const bool fast = fastok && badrows == 0 && y + 7 <= m && x0g >= 1 && x0g + 7 + WB - 1 <= (int)L;
+				badrows = max(0, badrows - 8);
+				if (fast) {
+					#pragma unroll
+					for (int r = 0; r < 8; ++r) {
+						const uint32_t qb = ((qw >> (4 * r)) & 15) * 0x11111111u;
+						const uint32_t nc = (feed >> (4 * r)) & 15;
+						#pragma unroll
+						for (int j = 0; j < NW - 1; ++j) win[j] = __funnelshift_r(win[j], win[j + 1], 4);
+						win[NW - 1] = (win[NW - 1] >> 4) | (nc << (4 * ((WB - 1) & 7)));
+						uint32_t left = inf;
+						#pragma unroll
+						for (int j = 0; j < NW; ++j) {
+							const uint32_t x = win[j] ^ qb;
+							const uint32_t nz = (((x & 0x77777777u) + 0x77777777u) | x) & 0x88888888u, nzh = nz >> 16;   // bit 4d+3: cell d mismatches
+							#pragma unroll
+							for (int dd = 0; dd < 8; ++dd) {
+								const int d = j * 8 + dd;
+								if (d >= WB) break;
+								const uint32_t st = dd < 5 ? (nz & (8u << (4 * dd))) * (1u << (19 - 4 * dd)) : (nzh & (8u << (4 * (dd - 4)))) * (1u << (19 - 4 * (dd - 4)));
+								const uint32_t up = d + 1 < WB ? a[d + 1] : inf;
+								uint32_t t = viaddmin(up, KEY_UP, a[d] + st);
+								t = viaddmin(left, KEY_LEFT, t) & KEY_CLEAR;
+								a[d] = t; left = t;
+							}
+						}
+					}
+					uint32_t rowmin = KEY_NONE;
+					#pragma unroll
+					for (int d = 0; d < WB; ++d) rowmin = min(rowmin, a[d]);
+					y += 8;
+					if (rowmin >= inf) { dead = true; y -= 1; }
+				} else {
 				#pragma unroll
 				for (int r = 0; r < 8; ++r) {
 					if (y > m) break;
@@ -896,7 +1272,8 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					if (rowmin >= inf) { dead = true; break; }   // every lane cell > maxED: the reference truncates (burst.c:1062-1065)
 					++y;
 				}
-				w0 = w1; w1 = wn; feed = __funnelshift_r(w0, w1, sh); qw = nqw;
+				}
+				w0 = w1; w1 = wn; feed = __funnelshift_r(w0, w1, sh2); qw = nqw;
 			}
 			if (!dead) y = m + 1;
 		} else {
@@ -934,7 +1311,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			};
 			if (WMAX) {
 				#pragma unroll
-				for (int d = 0; d < WB; ++d) scan(d, a[d]);
+				for (int d = 0; d < WB; ++d) if (d < (int)W) scan(d, a[d]);      // the cluster's own diagonals only: beyond them the sweep may see part of a neighbouring cluster's band
 			} else for (int d = 0; d < Wd; ++d) scan(d, g[d]);
 			const uint32_t ed = bk >> 11, sh = 2047u - (bk & 2047u);
 			if (bk != (KEY_NONE >> 11) && ed <= k) {
@@ -1011,7 +1388,7 @@ __global__ void k_work_stats(Work W, const QInfo *__restrict__ qi, const uint32_
 		for (uint32_t i = 0; i < n; ++i) {
 			const QInfo Q = qi[q0 + i];
 			nominal += 16ull * Q.len * L;
-			if (Q.cls) seeded = true; else fcells += 16ull * Q.P * L;
+			if (Q.cls & 1) seeded = true; else fcells += 16ull * Q.P * L;
 		}
 		if (seeded) scells += 16ull * L;                         // k_seed streams the clump once per run
 		tasks += n;
@@ -1058,6 +1435,7 @@ struct bg_ctx {
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
 	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
+	int seed_impl = 1, seed_nch = 8, seed_lbits = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
@@ -1071,6 +1449,7 @@ struct bg_ctx {
 	DBuf<uint8_t> d_packed; DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
 	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
+	DBuf<uint32_t> d_cls, d_sorder;                               // band-class bins of the survivors (k_bin_*)
 	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
 	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;   // cells: [0] band, [1..4] work stats
@@ -1129,6 +1508,9 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	if (const char *e = getenv("BURST_B200_SEED_FILTER")) c->seed_filter = atoi(e) != 0;
 	if (const char *e = getenv("BURST_B200_SEED_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 4096) c->seed_chunk = v; }
 	if (const char *e = getenv("BURST_B200_PIPE_SLICES")) { const int v = atoi(e); if (v >= 0 && v <= 64) c->pipe_slices = v; }
+	if (const char *e = getenv("BURST_B200_SEED_IMPL")) c->seed_impl = atoi(e) != 0;
+	if (const char *e = getenv("BURST_B200_SEED_NCH")) { const int v = atoi(e); if (v == 4 || v == 8) c->seed_nch = v; }
+	if (const char *e = getenv("BURST_B200_SEED_LBITS")) { const int v = atoi(e); if (v == 0 || (v >= 10 && v <= 20)) c->seed_lbits = v; }
 	bg_default_scoring(1, c->S);
 	*out = c;
 	return bg_set_scoring(c, c->S);
@@ -1141,7 +1523,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
 	c->d_packed.release(); c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
 	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
-	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release();
+	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_cls.release(); c->d_sorder.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -1170,6 +1552,9 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 	}
 	if (what == BG_PARAM_SEED_STAGE) { c->seed_stage = value != 0; return BG_OK; }
 	if (what == BG_PARAM_SEED_GROUPS) { if (value != 0 && value != 2 && value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed groups %d must be 0, 2, 4 or 8", value); c->seed_groups = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_IMPL) { c->seed_impl = value != 0; return BG_OK; }
+	if (what == BG_PARAM_SEED_NCH) { if (value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed buffer chunks %d must be 4 or 8", value); c->seed_nch = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_LBITS) { if (value && (value < 10 || value > 20)) return fail(BG_EINVAL, "bg_set_param: seed bitmap 2^%d bits out of range (0 = auto, 10..20)", value); c->seed_lbits = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_RATIO) { if (value && (value < 10 || value > 300)) return fail(BG_EINVAL, "bg_set_param: slice ratio %d must be 0 (auto) or 10..300", value); c->pipe_ratio = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_MIN_RUNS) { if (value < 1) return fail(BG_EINVAL, "bg_set_param: minimum runs per slice %d", value); c->pipe_min_runs = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_SLICES) { if (value < 0 || value > 64) return fail(BG_EINVAL, "bg_set_param: pipeline slices %d out of range 0..64", value); c->pipe_slices = value; return BG_OK; }
@@ -1327,7 +1712,7 @@ static int finish_upload(bg_ctx *c) {
 	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
 	want = std::max<uint64_t>(want, 1024);
 	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
-	if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+	if (c->d_surv.need(c->surv_cap) || c->d_sorder.need(c->surv_cap) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 	if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
 	c->ran = false; c->sorted = false;
 	return BG_OK;
@@ -1395,8 +1780,41 @@ static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint3
 	npmax = std::min<uint32_t>(std::max<uint32_t>(stretches_max, 1), 128 / SL.stride);   // window table rows per query
 }
 
+// the warp form of the seed filter: table sizes from the batch, grid = what is resident at once
+static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t npmax) {
+	SeedWArgs S;
+	S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = B.qi; S.qnib = B.qnib; S.W = B.W; S.SL = SL; S.nwork = B.W.nruns;
+	uint32_t chunk = 1; while (chunk * 2 <= (uint32_t)c->seed_chunk * 4 && chunk < SEEDW_SPLIT) chunk <<= 1;   // a power of two that divides SEEDW_SPLIT
+	S.chunk = chunk; S.npmax = npmax;
+	const uint32_t ne = BG_RUN_MAX * npmax * SL.stride;                 // most windows a bunch can hold
+	S.hslots = 64; while (S.hslots < 2 * ne) S.hslots <<= 1;
+	// bitmap: ~128 bits per window of a typical full bunch (SL.words was sized as 1-2 words per such window), so that a false
+	// positive -- one table probe by the owning thread -- stays below one per run
+	uint32_t lbits = 12; while (lbits < 17 && (1u << lbits) < 64u * SL.words) ++lbits;
+	if (c->seed_lbits) lbits = (uint32_t)c->seed_lbits;
+	while (lbits > 10 && (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax)) * 4 > 200 * 1024) --lbits;
+	S.lbits = lbits;
+	const size_t smem = (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax)) * sizeof(uint32_t);
+	if (smem > 220 * 1024) return fail(BG_EINVAL, "seed filter tables do not fit shared memory (stretches %u, stride %u)", npmax, SL.stride);
+	S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
+	memcpy(S.m16, c->m16, sizeof(S.m16));
+	void (*kern)(SeedWArgs);
+	if (c->seed_nch == 4) kern = SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, 4> : k_seedw<8, false, 4>) : (SL.w == 16 ? k_seedw<4, true, 4> : k_seedw<4, false, 4>);
+	else kern = SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, 8> : k_seedw<8, false, 8>) : (SL.w == 16 ? k_seedw<4, true, 8> : k_seedw<4, false, 8>);
+	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+	int bps = 0;
+	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SEEDW_WARPS * 32, smem));
+	if (bps < 1) bps = 1;
+	const uint64_t nchunk = (S.nwork + chunk - 1) / chunk;
+	const uint64_t blocks = std::min<uint64_t>((nchunk + SEEDW_WARPS - 1) / SEEDW_WARPS, (uint64_t)c->sms * bps);
+	kern<<<(unsigned)blocks, SEEDW_WARPS * 32, smem, st>>>(S);
+	CU(cudaGetLastError());
+	return BG_OK;
+}
+
 static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t npmax, bool seed, bool filter, const uint32_t *todo) {
-	if (B.W.nruns && seed) {
+	if (B.W.nruns && seed && c->seed_impl) { int rc = launch_seedw(c, st, B, SL, npmax); if (rc) return rc; }
+	else if (B.W.nruns && seed) {
 		SeedArgs S;
 		S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = B.qi;
 		S.qnib = B.qnib; S.W = B.W; S.SL = SL; S.nwork = B.W.nruns; S.chunk = (uint32_t)c->seed_chunk;
@@ -1432,18 +1850,27 @@ static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const S
 }
 
 static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode, const uint32_t *first) {
+	// survivors of this launch ([*first, count)) binned by band class, then one sweep per class over its own range
+	CU(cudaMemsetAsync(c->d_cls.p, 0, 64 * sizeof(uint32_t), st));
+	k_bin_count<<<(unsigned)c->sms * 4, 256, 0, st>>>(c->d_surv.p, c->d_counters.p, c->surv_cap, first, c->d_cls.p);
+	k_bin_offsets<<<1, 32, 0, st>>>(c->d_counters.p, c->surv_cap, first, c->d_cls.p);
+	k_bin_scatter<<<(unsigned)c->sms * 4, 256, 0, st>>>(c->d_surv.p, c->d_counters.p, c->surv_cap, first, c->d_cls.p, c->d_sorder.p);
 	ExtendArgs E;
 	E.dbw = (const uint32_t *)c->d_db.p; E.meta = c->d_meta.p;
 	E.codes = B.codes; E.qnib = B.qnib; E.qi = B.qi; E.W = B.W;
-	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.first = first; E.res = c->d_res.p;
+	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.cls = c->d_cls.p; E.order = c->d_sorder.p; E.res = c->d_res.p;
 	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
 	E.band_cells = c->d_cells.p; E.mode = mode;
 	const unsigned g = (unsigned)c->sms * 12;
+	k_extend<5><<<g, 128, 0, st>>>(E);
 	k_extend<8><<<g, 128, 0, st>>>(E);
+	k_extend<12><<<g, 128, 0, st>>>(E);
 	k_extend<16><<<g, 128, 0, st>>>(E);
+	k_extend<24><<<g, 128, 0, st>>>(E);
 	k_extend<32><<<g, 128, 0, st>>>(E);
-	k_extend<64><<<g, 128, 0, st>>>(E);
-	k_extend<0><<<g, 128, 0, st>>>(E);
+	k_extend<48><<<g / 2, 128, 0, st>>>(E);
+	k_extend<64><<<g / 2, 128, 0, st>>>(E);
+	k_extend<0><<<g / 2, 128, 0, st>>>(E);
 	CU(cudaGetLastError());
 	return BG_OK;
 }
@@ -1504,7 +1931,7 @@ static int settle(bg_ctx *c) {
 		if (!grow_s && !grow_g) return BG_OK;
 		if (grow_s) {
 			c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
-			if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+			if (c->d_surv.need(c->surv_cap) || c->d_sorder.need(c->surv_cap) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		}
 		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
 		int rc = run_extend(c, c->last_mode, c->have_best_in ? c->last_best_in.data() : nullptr);
@@ -1641,7 +2068,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 	}
 	const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
 	for (int attempt = 0; attempt < 4; ++attempt) {
-		if (c->d_surv.need(c->surv_cap) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+		if (c->d_surv.need(c->surv_cap) || c->d_sorder.need(c->surv_cap) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
 		if (c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128)) return BG_ENOMEM;
 		cudaStream_t cs = c->stream, ps = c->copy_stream;

@@ -19,6 +19,7 @@ MODE_MIN, MODE_ALL = 0, 1
 Q_PACKED4 = 1
 PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE, PARAM_PIPE_SLICES = 1, 2, 3, 4, 5
 PARAM_PIPE_MIN_RUNS, PARAM_PIPE_RATIO, PARAM_SEED_GROUPS = 6, 7, 8
+PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS = 9, 10, 11
 
 
 class BgQueries(C.Structure):

@@ -107,6 +107,9 @@ enum { BG_PARAM_SEED_GROUPS = 8 };   /* 16-thread groups (runs per round) per bl
 enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096): lists shorter than two slices take the single-batch path */
        BG_PARAM_PIPE_RATIO = 7 };    /* size of each slice in percent of the one before; 0 (default) = 100 for byte codes (copy-bound), 140 for
                                         BG_Q_PACKED4 (kernel-bound: a short first copy, later copies hide behind the kernels) */
+enum { BG_PARAM_SEED_IMPL = 9,       /* 1 (default): warp-per-bunch seed filter (private window table, no block barriers); 0: the block form */
+       BG_PARAM_SEED_NCH = 10,       /* 32-column chunks per register buffer of the warp form: 8 (default) or 4 */
+       BG_PARAM_SEED_LBITS = 11 };   /* log2 of the bits in a warp's window bitmap, 10..20 (0 = sized from the batch) */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),

@@ -1,0 +1,120 @@
+"""GPU parity at the shapes of BASELINE.json configs[2] and configs[3] (scaled so that the scalar oracle finishes in
+seconds), through the C ABI, for both seed-filter forms and the Myers prefix filter.
+
+  C3  amplicon: 292 bp reads, -i 0.97 (budget 9), references in a mutation tree so that the lanes of a clump are
+      near-identical (most visited lanes seed, many tie), sorted strands in bunches of 16, >= 30 clump visits per
+      query, MIN and ALL selection.                                         burst.c:4136-4284, BASELINE.md section 2
+  C4  150 bp reads, -i 0.98 (budget 3), the DB cut into two reference shards whose per-slot minima are combined by
+      MIN before the selection (the rule of burst.c:4490-4519).
+"""
+import numpy as np
+import pytest
+from burst_b200 import synth
+from burst_b200.engine import RUN_DTYPE, PARAM_SEED_IMPL, PARAM_SEED_NCH
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from burst_b200.engine import Engine
+    e = Engine(0)
+    yield e
+    e.close()
+
+
+def amplicon_case(seed, n_refs=16 * 36, n_reads=48, read_len=292, ref_len=700):
+    rng = np.random.default_rng(seed)
+    refs = synth.mutation_tree_refs(rng, n_refs, ref_len, levels=(0.25, 0.10, 0.05, 0.006))   # 9 leaves per genus, a few edits apart
+    # the reference sorts references so that similar ones share clumps; a lexicographic sort does that for a mutation tree
+    refs.sort(key=lambda r: r.tobytes())
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, src = synth.amplicon_reads(refs, n_reads, read_len, 5, rng, start=60, jitter=5, dup_rate=0.0)
+    # forward + reverse complement strands, sorted (burst.c:3087-3109, 3181-3184)
+    strands = []; sread = []
+    for i, r in enumerate(reads):
+        strands += [r, synth.RC_TABLE[r[::-1]]]; sread += [i, i]
+    codes, qoff = synth.concat_queries(strands)
+    order = synth.sort_strands(codes, qoff)
+    strands = [strands[i] for i in order]; slot = np.array([sread[i] for i in order], np.uint32)
+    return rng, refs, packed, off, clen, strands, slot, len(reads)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_c3_amplicon_shape(eng, oracle, mode):
+    rng, refs, packed, off, clen, strands, slot, nslots = amplicon_case(2026 + mode)
+    codes, qoff = synth.concat_queries(strands)
+    nq = len(strands)
+    budget = np.array([oracle.budget(0.97, len(s)) for s in strands], np.uint16)
+    assert int(budget.max()) == 9
+    nclumps = len(clen)
+    # every bunch visits 32 clumps: a window of the sorted DB around a random point (near-identical families are adjacent)
+    def cands(b, q0, n):
+        c0 = int(rng.integers(0, nclumps - 32))
+        v = np.arange(c0, c0 + 32); rng.shuffle(v)
+        return v
+    runs, tq, tc, key = synth.bunch_runs(nq, 16, cands)
+    S = oracle.score_table(1)
+    ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nslots, tq, tc, S, mode)
+    ohits = ohits.copy(); ohits["task"] = key[ohits["task"]]
+    ohits = ohits[np.lexsort((ohits["lane"], ohits["task"]))]
+    assert len(ohits) > (60 if mode == 0 else 200)                        # families: many lanes within budget / tied
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    try:
+        for impl, nch, seedf in ((1, 8, True), (1, 4, True), (0, 8, True), (1, 8, False)):
+            eng.set_param(PARAM_SEED_IMPL, impl); eng.set_param(PARAM_SEED_NCH, nch); eng.set_seed_filter(seedf)
+            hits, best = eng.align(codes, qoff, budget, None, mode, slot=slot, nslots=nslots, runs=runs.astype(RUN_DTYPE))
+            assert np.array_equal(best, obest), (impl, nch, seedf)
+            assert len(hits) == len(ohits) and np.array_equal(hits, ohits), (impl, nch, seedf, len(hits), len(ohits))
+    finally:
+        eng.set_param(PARAM_SEED_IMPL, 1); eng.set_param(PARAM_SEED_NCH, 8); eng.set_seed_filter(True)
+    st = eng.stats()
+    assert st["seed_queries"] == nq and st["seed_stride"] == 8
+
+
+def test_c4_shape_two_reference_shards(eng, oracle):
+    rng = np.random.default_rng(404)
+    refs = synth.random_refs(16 * 48, 306, rng, jitter=4)
+    # a few references repeated in the other half of the DB, so that both shards hold hits of one read
+    for i in range(0, 16 * 24, 29):
+        refs[16 * 24 + i] = synth.mutate(refs[i], int(rng.integers(0, 3)), rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 220, 150, 3, rng, rc_rate=0.0)
+    codes, qoff = synth.concat_queries(reads)
+    nq = len(reads)
+    budget = np.array([oracle.budget(0.98, len(r)) for r in reads], np.uint16)
+    assert int(budget.max()) == 3
+    nclumps = len(clen)
+    def cands(b, q0, n):
+        own = {int(origin[q, 0]) for q in range(q0, q0 + n)}
+        twin = {(c + 24) % nclumps for c in own}
+        return sorted(own | twin | {int(v) for v in rng.integers(0, nclumps, 3)})
+    runs, tq, tc, key = synth.bunch_runs(nq, 16, cands)
+    runs = runs.astype(RUN_DTYPE)
+    S = oracle.score_table(1)
+    slot = np.arange(nq, dtype=np.uint32)
+    ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, slot, nq, tq, tc, S, 0)
+    ohits = ohits.copy(); ohits["task"] = key[ohits["task"]]
+    ohits = ohits[np.lexsort((ohits["lane"], ohits["task"]))]
+    eng.set_scoring(S)
+    eng.load_db(packed, clen)
+    hits, best = eng.align(codes, qoff, budget, None, 0, runs=runs)
+    assert np.array_equal(best, obest) and np.array_equal(hits, ohits)
+    # two shards: extend on each, MIN of the minima, then select against the combined minima
+    half = nclumps // 2
+    parts, bests = [], []
+    for lo, hi in ((0, half), (half, nclumps)):
+        end = int(off[hi]) if hi < nclumps else len(packed)
+        eng.load_db(packed[int(off[lo]):end], clen[lo:hi], first_clump=lo)
+        eng.upload_runs(codes, qoff, budget, runs)
+        eng.run_extend(0); eng.run_select(1)
+        h, b = eng.download()
+        parts.append(h); bests.append(b)
+    gbest = np.minimum(bests[0], bests[1])
+    assert np.array_equal(gbest, obest)
+    allh = np.concatenate(parts)
+    q_of = runs["query0"][allh["task"] >> 4] + (allh["task"] & 15)
+    keep = allh[allh["ed"] == gbest[q_of]]
+    keep = keep[np.lexsort((keep["lane"], keep["task"]))]
+    assert np.array_equal(keep, ohits)
+    assert len(set(np.nonzero(bests[0] != 0xFFFF)[0]) & set(np.nonzero(bests[1] != 0xFFFF)[0])) > 0   # some reads hit in both shards
