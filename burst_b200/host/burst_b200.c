@@ -35,7 +35,7 @@ static Mode RUNMODE = CAPITALIST;
 static float THRES = 0.97f;
 static int Z = 1, DO_ACCEL = 0, DO_HEUR = 0, TAXA_NCBI = 0, SCOUR_N = 0;
 static uint32_t TAXACUT = 10, LATENCY = 16;
-static long REBASE_AMT = 500; static int REBASE = 0;
+static long REBASE_AMT = 500, DB_QLEN = 500; static int REBASE = 0, ACX_N = 12;   /* ACX_N: word length of the accelerator -d writes (a compile-time constant of the reference binary, burst.c:96-98) */
 static float TAXLEVELS_STRICT[] = {.65f, .75f, .78f, .82f, .86f, .94f, .98f, .995f},
              TAXLEVELS_LENIENT[] = {.55f, .70f, .75f, .80f, .84f, .93f, .97f, .985f},   /* burst.c:264-266 */
              *TAXLEVELS = TAXLEVELS_LENIENT;
@@ -463,6 +463,188 @@ static void ambig_words(uint64_t *W, uint64_t *wix, const char *s, uint32_t j, u
 	else for (int i = 0; i < AMBIG_N[(uint8_t)s[ix] & 15]; ++i) ambig_words(W, wix, s, j, w << 2 | AMBIG_B[(uint8_t)s[ix] & 15][i], ix + 1);
 }
 
+/* =============================================================================================
+ * Database creation (-d): FASTA -> .edx (+ .acx with -a).  SURVEY.md 8(f) #3.
+ * The byte layouts are the reference's (dump_edb burst.c:2758-2839, make_accelerator 3501-3530), so
+ * either binary loads the files.  The way references are cut and grouped is NOT the reference's
+ * duplicate-guided shearing / clustering (burst.c:1852-2686): it is the plain shear of its QUICK
+ * branch (burst.c:2115-2143: windows of shear + ov bases every `shear` bases, ov = qLen / id) followed
+ * by the length / lexicographic ordering of load_fasta_refs.  Clump composition changes the amount
+ * of work, never the alignments found.
+ * ============================================================================================= */
+static int cmp_strp(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
+
+typedef struct { uint8_t *yn; uint32_t *cache, n; uint64_t cap; int N; uint32_t mask; } WordSet;   /* distinct words of one clump */
+static void ws_add(WordSet *S, uint32_t w) {
+	if (S->yn[w >> 3] & (1u << (w & 7))) return;
+	S->yn[w >> 3] |= (uint8_t)(1u << (w & 7));
+	if (S->n == S->cap) { S->cap *= 2; S->cache = xrealloc(S->cache, S->cap * 4); }
+	S->cache[S->n++] = w;
+}
+static void ws_ambig(WordSet *S, const char *s, uint32_t w, int ix) {      /* every plain variant of an ambiguous window (burst.c:3285-3292) */
+	if (ix == S->N) ws_add(S, w);
+	else for (int i = 0; i < AMBIG_N[(uint8_t)s[ix] & 15]; ++i) ws_ambig(S, s, w << 2 | AMBIG_B[(uint8_t)s[ix] & 15][i], ix + 1);
+}
+/* words of one clump's lanes into S; returns 1 if the clump is "bad" (too many ambiguous variants: always visited instead, burst.c:3349-3356) */
+static int clump_words(WordSet *S, char **Seq, const uint32_t *Len, const uint32_t *ix, uint32_t nlanes, int skipAmbig) {
+	const int N = S->N; const uint32_t AMBIG = 4 + (uint32_t)Z;
+	const uint64_t fullSize = N > 14 ? INT32_MAX : (1u << 24);
+	S->n = 0;
+	uint64_t Tsum = 0; uint16_t doAmbig = 0;
+	if (!skipAmbig) for (uint32_t z = 0; z < nlanes; ++z) {
+		uint32_t len = Len[ix[z]], Asum = 0; const char *s = Seq[ix[z]];
+		if (len < (uint32_t)N) continue;
+		for (uint32_t j = 0; j < len; ++j) {
+			if (j >= (uint32_t)N - 1) { uint64_t v = 1; for (uint32_t a = 0; a < Asum && v < fullSize; ++a) v *= Z ? 3 : 4; Tsum += v; if ((uint8_t)s[j - (N - 1)] > AMBIG) --Asum; }
+			if ((uint8_t)s[j] > AMBIG) ++Asum, doAmbig |= (uint16_t)(1u << z);
+			if (Tsum >= fullSize) return 1;
+		}
+	}
+	for (uint32_t z = 0; z < nlanes; ++z) {
+		uint32_t len = Len[ix[z]]; const char *s = Seq[ix[z]];
+		if (len < (uint32_t)N) continue;
+		if (skipAmbig || Z) {                                            /* windows holding an N (any ambiguous base with -sa) are not indexed */
+			for (uint32_t j = 0; j + N <= len; ++j) {
+				int k = 0;
+				for (; k < N; ++k) if (skipAmbig ? (uint8_t)s[j + k] >= 5 : s[j + k] == 5) break;
+				if (k < N) { j += k; continue; }
+				ws_ambig(S, s + j, 0, 0);
+			}
+		} else if (doAmbig >> z & 1) for (uint32_t j = 0; j + N <= len; ++j) ws_ambig(S, s + j, 0, 0);
+		else {
+			uint32_t w = 0;
+			for (uint32_t j = 0; j < len; ++j) { w = (w << 2 | (uint32_t)(s[j] - 1)) & S->mask; if (j + 1 >= (uint32_t)N) ws_add(S, w); }
+		}
+	}
+	return 0;
+}
+
+static void make_db(const char *ref_FN, const char *edx_FN, const char *acx_FN, long dbQLen, int N, int skipAmbig) {
+	char **Head, **Seq; uint32_t *Len;
+	uint32_t origR = read_fasta_refs(ref_FN, &Head, &Seq, &Len);
+	printf("Parsed %u references.\n", origR);
+	if (!origR) { fputs("ERROR: no references found.\n", stderr); exit(1); }
+	for (uint32_t i = 0; i < origR; ++i) { if (!Seq[i]) Seq[i] = xcalloc(17, 1); translate(Seq[i], Len[i]); }
+	if (!REBASE) dbQLen = 0;                                              /* burst.c:5121 */
+	/* ---- shear (burst.c:1853-1856, 2115-2143) ---- */
+	uint32_t totR = origR, *Start = NULL, *Src = NULL, maxLenR = 0;
+	char **SSeq = Seq; uint32_t *SLen = Len;
+	if (REBASE) {
+		uint32_t minShear = (uint32_t)(dbQLen / THRES), shear = minShear > (uint32_t)REBASE_AMT ? minShear : (uint32_t)REBASE_AMT, ov = minShear;
+		printf("\nInitiating database shearing procedure [shear %u, ov %u].\n", shear, ov);
+		uint64_t n = 0;
+		for (uint32_t i = 0; i < origR; ++i) { long unit = (long)Len[i] - (long)ov; if (unit <= 0) unit = 1; n += (uint64_t)(unit / shear + (unit % shear != 0)); }
+		if (n >= UINT32_MAX) { fputs("ERROR: too many shears\n", stderr); exit(4); }
+		totR = (uint32_t)n;
+		Start = xmalloc((size_t)totR * 4); Src = xmalloc((size_t)totR * 4);
+		SSeq = xmalloc((size_t)totR * sizeof(*SSeq)); SLen = xmalloc((size_t)totR * 4);
+		uint32_t x = 0;
+		for (uint32_t i = 0; i < origR; ++i) {
+			long unit = (long)Len[i] - (long)ov; if (unit <= 0) unit = 1;
+			for (long j = 0; j < unit; j += shear) {
+				Src[x] = i; Start[x] = (uint32_t)j; SSeq[x] = Seq[i] + j;
+				uint32_t l = Len[i] - (uint32_t)j; SLen[x] = l > shear + ov ? shear + ov : l; ++x;
+			}
+		}
+		printf("Shorn refs: %u, rebased clumps: %u\n", totR, totR / 16 + (totR % 16 != 0));
+	}
+	/* ---- order: length pods of LATENCY bases, lexicographic inside (as load_fasta_refs) ---- */
+	Tux *T = xmalloc((size_t)totR * sizeof(*T));
+	for (uint32_t i = 0; i < totR; ++i) T[i] = (Tux){SSeq[i], SLen[i], i};
+	qsort(T, totR, sizeof(*T), cmp_tux_len);
+	maxLenR = T[totR - 1].len;
+	uint32_t prev = 0, curTol = T[0].len;
+	for (uint32_t i = 1; i <= totR; ++i) if (i == totR || T[i].len > curTol + LATENCY) {
+		if (i - prev > 1) qsort(T + prev, i - prev, sizeof(*T), cmp_tux_seq);
+		if (i < totR) curTol = T[i].len;
+		prev = i;
+	}
+	Refs R; memset(&R, 0, sizeof(R));
+	R.totR = R.origTotR = totR; R.maxLenR = maxLenR;
+	R.RefIxSrt = xmalloc(((size_t)totR + 1) * 4);
+	for (uint32_t i = 0; i < totR; ++i) R.RefIxSrt[i] = T[i].ix;
+	free(T);
+	pack_clumps(&R, SSeq, SLen);
+	printf("There are %u references and hence %u clumps\n", totR, R.numRclumps);
+	/* ---- .edx (burst.c:2758-2839) ---- */
+	FILE *out = fopen(edx_FN, "wb");
+	if (!out) { fprintf(stderr, "ERROR: Cannot open output: %s\n", edx_FN); exit(2); }
+	setvbuf(out, 0, _IOFBF, 1 << 22);
+	puts("Writing database...");
+	fputc(1 << 7 | REBASE << 6 | 3, out);
+	/* unique sorted headers, NUL-separated; RefMap[shear] = index of its header */
+	char **hs = xmalloc((size_t)origR * sizeof(*hs)); uint32_t *hmap = xmalloc((size_t)origR * 4);
+	uint32_t *hix = xmalloc((size_t)origR * 4);
+	for (uint32_t i = 0; i < origR; ++i) hs[i] = Head[i];
+	qsort(hs, origR, sizeof(*hs), cmp_strp);
+	uint32_t nheads = 0; uint64_t totRefHeadLen = 0;
+	for (uint32_t i = 0; i < origR; ++i) if (!i || strcmp(hs[i], hs[nheads - 1])) { hs[nheads++] = hs[i]; totRefHeadLen += strlen(hs[i]) + 1; }
+	for (uint32_t i = 0; i < origR; ++i) {                                /* binary search of each original header */
+		uint32_t lo = 0, hi = nheads;
+		while (lo + 1 < hi) { uint32_t mid = (lo + hi) / 2; if (strcmp(hs[mid], Head[i]) <= 0) lo = mid; else hi = mid; }
+		hmap[i] = lo;
+	}
+	(void)hix;
+	uint32_t shearHdr = (uint32_t)(dbQLen / THRES);
+	fwrite(&totRefHeadLen, 8, 1, out); fwrite(&shearHdr, 4, 1, out); fwrite(&totR, 4, 1, out); fwrite(&totR, 4, 1, out);
+	fwrite(&R.numRclumps, 4, 1, out); fwrite(&maxLenR, 4, 1, out);
+	for (uint32_t i = 0; i < nheads; ++i) fwrite(hs[i], 1, strlen(hs[i]) + 1, out);
+	fwrite(&nheads, 4, 1, out);
+	for (uint32_t i = 0; i < totR; ++i) { uint32_t m = hmap[Src ? Src[i] : i]; fwrite(&m, 4, 1, out); }       /* RefMap */
+	if (REBASE) fwrite(Start, 4, totR, out);                              /* RefStart */
+	fwrite(R.RefIxSrt, 4, totR, out);                                     /* TmpRIX: lane slot -> sheared reference (no de-duplication here) */
+	fwrite(R.ClumpLen, 4, R.numRclumps, out);
+	fwrite(R.packed, 1, R.packedBytes, out);
+	fclose(out);
+	puts("Database written.");
+	/* ---- .acx (burst.c:3304-3532) ---- */
+	if (acx_FN) {
+		printf("Generating accelerator '%s'\n", acx_FN);
+		if (Z) fprintf(stderr, "Note: N-penalized accelerator not usable for unpenalized alignment\n");
+		const uint64_t nk = 1ull << (2 * N);
+		uint32_t *Lens = xcalloc(nk, 4);
+		WordSet S = {xcalloc(nk >> 3, 1), xmalloc((1u << 16) * 4), 0, 1u << 16, N, N == 16 ? 0xFFFFFFFFu : (uint32_t)(nk - 1)};
+		uint32_t *Bad = xmalloc(((size_t)R.numRclumps + 1) * 4), badSz = 0;
+		uint8_t *isBad = xcalloc(R.numRclumps + 1, 1);
+		uint64_t total = 0;
+		for (uint32_t c = 0; c < R.numRclumps; ++c) {                      /* pass 1: posting-list lengths */
+			uint32_t nl = MIN(VECSZ, totR - c * VECSZ);
+			if (clump_words(&S, SSeq, SLen, R.RefIxSrt + (size_t)c * VECSZ, nl, skipAmbig)) { isBad[c] = 1; Bad[badSz++] = c; }
+			else for (uint32_t k = 0; k < S.n; ++k) ++Lens[S.cache[k]];
+			for (uint32_t k = 0; k < S.n; ++k) S.yn[S.cache[k] >> 3] = 0;
+			total += isBad[c] ? 0 : S.n;
+		}
+		printf("Total accelerants stored: %" PRIu64 " (%u bad)\n", total, badSz);
+		uint64_t *off = xmalloc((nk + 1) * 8); off[0] = 0;
+		for (uint64_t i = 0; i < nk; ++i) off[i + 1] = off[i] + Lens[i];
+		uint32_t *post = xmalloc((total + 1) * 4), *fill = xcalloc(nk, 4);
+		for (uint32_t c = 0; c < R.numRclumps; ++c) {                      /* pass 2: postings, ascending clump id per word */
+			if (isBad[c]) continue;
+			uint32_t nl = MIN(VECSZ, totR - c * VECSZ);
+			clump_words(&S, SSeq, SLen, R.RefIxSrt + (size_t)c * VECSZ, nl, skipAmbig);
+			for (uint32_t k = 0; k < S.n; ++k) { uint32_t w = S.cache[k]; post[off[w] + fill[w]++] = c; S.yn[w >> 3] = 0; }
+		}
+		FILE *ax = fopen(acx_FN, "wb");
+		if (!ax) { fprintf(stderr, "Cannot write accelerator '%s'\n", acx_FN); exit(1); }
+		setvbuf(ax, 0, _IOFBF, 1 << 22);
+		if (R.numRclumps > 16777214) { fputs("ERROR: acc error M16\n", stderr); exit(101); }
+		int big = R.numRclumps > 1048574;
+		fputc(1 << 7 | Z << 6 | (big ? 1 : 0), ax);
+		fwrite(&badSz, 4, 1, ax);
+		fwrite(Lens, 4, nk, ax);
+		fprintf(stderr, " --> [Re-Accel] Writing %s format acx...\n", big ? "LARGE" : "SMALL");
+		if (big) for (uint64_t i = 0; i < total; ++i) fwrite(post + i, 3, 1, ax);
+		else for (uint64_t w = 0; w < nk; ++w) for (uint64_t p = off[w]; p < off[w + 1]; p += 2) {
+			uint64_t bay = post[p];
+			if (p + 1 < off[w + 1]) { bay |= (uint64_t)post[p + 1] << 20; fwrite(&bay, 1, 5, ax); }
+			else fwrite(&bay, 1, 3, ax);
+		}
+		fwrite(Bad, 4, badSz, ax);
+		fclose(ax);
+		printf("Wrote accelerator (DB%d).\n", N);
+	}
+}
+
 typedef struct { bg_task *t; uint64_t n, cap; } TaskVec;
 static void task_push(TaskVec *T, uint32_t q, uint32_t c) {
 	if (T->n == T->cap) { T->cap = T->cap ? T->cap * 2 : (1 << 16); T->t = xrealloc(T->t, T->cap * sizeof(bg_task)); }
@@ -865,7 +1047,7 @@ static void usage(void) {
 	puts("--mode (-m) BEST | ALLPATHS | CAPITALIST [default] | FORAGE");
 	puts("--id (-i) <decimal> [0.97], --threads (-t) <int> (accepted, unused), --skipambig (-sa), --heuristic (-hr)");
 	puts("--gpu <int>: CUDA device to use [0];  --noprogress");
-	puts("Database creation (-d) is not part of this build: create .edx/.acx with the reference burst binary.");
+	puts("--makedb (-d) [DNA|RNA|QUICK] [qLen]: write -o <edx> (and -a <acx>, word length --acx-n 12|15 [12]) from -r <fasta>; -s [len] shears");
 	exit(1);
 }
 static int is_edx(const char *fn) {                                  /* burst.c:4894-4901 */
@@ -878,7 +1060,7 @@ static int is_edx(const char *fn) {                                  /* burst.c:
 
 int main(int argc, char *argv[]) {
 	Queries Q; memset(&Q, 0, sizeof(Q));
-	Refs R; char *ref_FN = 0, *query_FN = 0, *output_FN = 0, *xcel_FN = 0, *tax_FN = 0; int taxasuppress = 0;
+	Refs R; char *ref_FN = 0, *query_FN = 0, *output_FN = 0, *xcel_FN = 0, *tax_FN = 0; int taxasuppress = 0, makedb = 0;
 	printf("This is BURST [" VER "]\n");
 	if (argc < 2) usage();
 #define NEEDARG(msg) if (++i == argc || argv[i][0] == '-') { puts("ERROR: " msg); exit(1); }
@@ -902,7 +1084,20 @@ int main(int argc, char *argv[]) {
 			else { printf("Unsupported run mode '%s'\n", argv[i]); exit(1); }
 			printf(" --> Setting run mode to %s\n", argv[i]);
 		}
-		else if (OPT("--makedb", "-d")) { fputs("ERROR: database creation (-d) is not part of this build; make the .edx/.acx with the reference burst binary.\n", stderr); exit(1); }
+		else if (OPT("--makedb", "-d")) {                                  /* burst.c:4969-4985 */
+			makedb = 1; const char *dbsel = "QUICK";
+			if (i + 1 != argc && argv[i + 1][0] != '-' && !atol(argv[i + 1])) {
+				++i;
+				if (strcmp(argv[i], "DNA") && strcmp(argv[i], "RNA") && strcmp(argv[i], "QUICK")) { printf("Unsupported makedb mode '%s'\n", argv[i]); exit(1); }
+				dbsel = argv[i];
+			}
+			if (i + 1 != argc && argv[i + 1][0] != '-') {
+				DB_QLEN = atol(argv[++i]);
+				if (DB_QLEN <= 0) { fprintf(stderr, "ERROR: bad max query length '%s'\n", argv[i]); exit(1); }
+			}
+			printf(" --> Creating %s database (assuming max query length %ld)\n", dbsel, DB_QLEN);
+		}
+		else if (!strcmp(argv[i], "--acx-n")) { NEEDARG("--acx-n requires 12 or 15") ACX_N = atoi(argv[i]); if (ACX_N != 12 && ACX_N != 15) { fputs("ERROR: --acx-n must be 12 or 15\n", stderr); exit(1); } }
 		else if (OPT("--accelerator", "-a")) { NEEDARG("--accelerator requires filename argument") xcel_FN = argv[i]; DO_ACCEL = 1; printf(" --> Using accelerator file %s\n", xcel_FN); }
 		else if (OPT("--taxacut", "-bc")) {
 			NEEDARG("--taxacut requires numeric argument")
@@ -934,6 +1129,13 @@ int main(int argc, char *argv[]) {
 		else if (OPT("--cache", "-c") || OPT("--latency", "-l") || OPT("--clustradius", "-cr") || OPT("--dbpartition", "-dp")) { NEEDARG("option requires integer argument") }
 		else if (OPT("--help", "-h")) usage();
 		else { printf("ERROR: Unrecognized command-line option: %s\n", argv[i]); puts("See help by running with just '-h'"); exit(1); }
+	}
+	if (makedb) {                                                       /* burst.c:5118-5134: no GPU involved */
+		if (!ref_FN || !output_FN) { puts("ERROR: -r and -o are required"); exit(1); }
+		if (is_edx(ref_FN)) { fputs("ERROR: DBs can't make DBs.\n", stderr); exit(1); }
+		init_char2num();
+		make_db(ref_FN, output_FN, xcel_FN, DB_QLEN, ACX_N, Q.skipAmbig);
+		return 0;
 	}
 	if (!ref_FN || !query_FN || !output_FN) { puts("ERROR: -r, -q and -o are required"); exit(1); }
 	FILE *output = fopen(output_FN, "wb");

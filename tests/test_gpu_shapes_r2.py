@@ -68,6 +68,7 @@ def test_c3_amplicon_shape(eng, oracle, mode):
             assert len(hits) == len(ohits) and np.array_equal(hits, ohits), (impl, nch, seedf, len(hits), len(ohits))
     finally:
         eng.set_param(PARAM_SEED_IMPL, 1); eng.set_param(PARAM_SEED_NCH, 8); eng.set_seed_filter(True)
+    eng.align(codes, qoff, budget, None, mode, slot=slot, nslots=nslots, runs=runs.astype(RUN_DTYPE))
     st = eng.stats()
     assert st["seed_queries"] == nq and st["seed_stride"] == 8
 
