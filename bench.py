@@ -8,7 +8,8 @@ reference simulator's model, embalmlets/LLsim.c) against a 2 GB synthetic .edx-l
 = what the reference's accelerated driver enumerates (bunches of 16 sorted strands x the bunch's
 candidate clumps, burst.c:4077-4157).
 
-  value     whole-job reads/s with queries, tasks and DB resident in HBM (kernels only)
+  value     whole-job reads/s with queries, tasks and DB resident in HBM (kernels only: k_init_best, k_seedw, k_bin_count/offsets/scatter,
+            k_extend x 9 band classes, k_select = 15 launches per step)
   e2e       the same through bg_align_batch(): pinned host buffers in, hits in host memory out
   roofline  dominant kernel (k_seed) algorithmic bytes / its CUDA-event time vs measured HBM peak
             -- the kernel is integer-ALU bound, see "alu" and DESIGN.md
@@ -48,6 +49,7 @@ def parse():
     return ap.parse_args()
 
 
+PARITY_SAMPLE_MOD = 64        # the CPU reference also records the kept lanes of every 64th read, for the bench-size parity check
 DPX_PEAK = 571.6e9 * 32      # VIADDMNMX.U32 thread-instructions/s, measured (profiles/r1d_pipe_microbench.txt)
 
 
@@ -135,6 +137,7 @@ def cpu_reference(args, w, steps=1, warmup=0):
     """The reference's kernels on the host cores over a bounded sample of the same task list."""
     from oracle import pyoracle
     threads = os.cpu_count() or 1
+    refout = None
     qb = w["qbunch"]
     nb_all = (len(w["qoff"]) - 1 + qb - 1) // qb
     if pyoracle.Reference.available():
@@ -148,10 +151,11 @@ def cpu_reference(args, w, steps=1, warmup=0):
         times = []
         for it in range(warmup + steps):
             t0 = time.perf_counter()
-            r = pyoracle.reference_run_bunches(ref, w, nb, threads)
+            r = pyoracle.reference_run_bunches(ref, w, nb, threads, sample_mod=PARITY_SAMPLE_MOD)
             if it >= warmup:
                 times.append(time.perf_counter() - t0)
         nq = r["nq"]
+        refout = r
         found = int((r["ed"][np.unique(w["slot"][:nq])] <= args.edits).sum())
         desc = "reference kernels aded_mat16L+reScoreM_mat16 (burst.c) in the reference's bunch loop, first %d of %d bunches = %d strands (%d pass-1 calls, %d truncated, %d pass-2), %d threads" % (
             nb, nb_all, nq, r["calls"], r["truncated"], r["rescore"], threads)
@@ -173,7 +177,30 @@ def cpu_reference(args, w, steps=1, warmup=0):
     dt = float(np.mean(times))
     reads = nq / 2.0
     return {"value": reads / dt, "unit": "reads/s", "cores": threads, "kind": kind, "sample": desc,
-            "seconds_per_step": dt, "reads_in_sample": reads}, dt
+            "seconds_per_step": dt, "reads_in_sample": reads}, dt, refout
+
+
+def parity_vs_reference(w, runs, hits, best, refout):
+    """The GPU's results against what the reference's own kernels produced on the same bunches (bench-size parity):
+    per-slot minima of every slot whose strands were all inside the CPU sample, and -- for the sampled slots (slot % PARITY_SAMPLE_MOD
+    == 0) -- the kept lanes with their (ed, numGapQ, numGapR, finalPos), as sets keyed by (query, clump, lane)."""
+    nq = refout["nq"]
+    inside = np.ones(w["nslots"], bool)
+    inside[w["slot"][nq:]] = False                                   # a slot with a strand beyond the sample saw fewer visits on the CPU
+    inside &= np.bincount(w["slot"][:nq], minlength=w["nslots"]) > 0
+    minima_equal = bool(np.array_equal(best[inside], refout["best"][inside]))
+    tq = runs["query0"][hits["task"] >> 4] + (hits["task"] & 15); tc = runs["clump"][hits["task"] >> 4]
+    sl = w["slot"][tq]
+    sel = inside[sl] & (sl % PARITY_SAMPLE_MOD == 0)
+    g = np.zeros(int(sel.sum()), refout["hits"].dtype)
+    g["query"] = tq[sel]; g["clump"] = tc[sel]
+    for f in ("lane", "ed", "gap_q", "gap_r", "final_pos"):
+        g[f] = hits[f][sel]
+    g = g[np.lexsort((g["lane"], g["clump"], g["query"]))]
+    rh = refout["hits"]; rh = rh[inside[w["slot"][rh["query"]]]]
+    return {"minima_equal": minima_equal, "slots_compared": int(inside.sum()), "slots_with_hit": int((refout["best"][inside] != 0xFFFF).sum()),
+            "hits_equal": bool(len(g) == len(rh) and np.array_equal(g, rh)), "hits_compared": int(len(rh)), "sample": "slot %% %d == 0" % PARITY_SAMPLE_MOD,
+            "against": "reference kernels (oracle/_ref/libburstref.so) over the same bunches, %d of %d" % (refout["nb"], (len(w["qoff"]) - 1 + w["qbunch"] - 1) // w["qbunch"])}
 
 
 def main():
@@ -190,7 +217,7 @@ def main():
         if rank != 0:
             return
         w = build_workload(args, 0)
-        cb, dt = cpu_reference(args, w, steps=max(1, args.steps), warmup=min(args.warmup, 1))
+        cb, dt, _ = cpu_reference(args, w, steps=max(1, args.steps), warmup=min(args.warmup, 1))
         out = {"impl": "reference", "metric": "reads_per_sec", "value": cb["value"], "unit": "reads/s", "n_gpus": args.gpus,
                "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config, "cpu_baseline": cb,
@@ -318,7 +345,7 @@ def main():
                        "call": "bg_align_runs_into(), reads as BG_Q_PACKED4 (two bases per byte) in pinned host memory, hits + minima into pinned host buffers",
                        "byte_codes": {"value": total_reads / (e2e_bytes_ms / 1e3 / args.steps), "h2d_bytes_per_step": int(h2d_bytes_form), "ms_per_step": e2e_bytes_ms / args.steps,
                                       "call": "the same call with one code byte per base"}},
-               "gpu_launches": 8 * args.steps,
+               "gpu_launches": 15 * args.steps,
                "dp_gcups_nominal": st["nominal_cells"] * world / (ms_step / 1e3) / 1e9,
                "dp_gcups_executed": (st["filter_cells"] + st["band_cells"]) * world / (ms_step / 1e3) / 1e9,
                "seed_steps_per_s": st["seed_steps"] * world / (ms_step / 1e3),
@@ -337,8 +364,10 @@ def main():
                                     "note": "2 VIADDMNMX per band cell (select-with-tie-break of the packed pass-2 key); peak = VIADDMNMX.U32 issue rate measured on this pool's B200 by burst_b200/csrc/tools/pipe_microbench (profiles/r1d_pipe_microbench.txt: 571.6 G warp-inst/s at 1965 MHz, half the 4-per-clock issue rate: it shares the ALU pipe with the ~5 LOP3/SHF/VIMNMX each cell also needs)"},
                "clocks": clocks, "workload_gen_s": w["gen_s"]}
         if not args.no_cpu_baseline and world == 1:
-            cb, _ = cpu_reference(args, w)
+            cb, _, refout = cpu_reference(args, w)
             out["cpu_baseline"] = cb
+            if refout is not None:
+                out["parity"] = parity_vs_reference(w, runs, hits, best, refout)
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

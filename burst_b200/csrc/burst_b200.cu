@@ -668,15 +668,19 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 // Phase A1, warp form (the default).  The same pigeonhole filter as k_seed above, reorganised so that
 // nothing in the steady state waits on a block-wide barrier:
 //   * a WARP owns a bunch (the <= 16 queries that share a candidate list, burst.c:4077-4157): its window
-//     set lives in the warp's private slice of shared memory -- a one-bit-per-window bitmap (the scan
-//     filter) and an open-addressing table of window ids (the exact verification) -- built by the 32
-//     lanes together and kept for every clump visit (run) of the bunch; only __syncwarp() orders it;
-//   * the two half-warps scan two runs of the bunch at a time, a thread per reference lane; the clump
-//     words of the NEXT item are in flight in a second register buffer while the current one is probed
-//     (ping-pong, no copies), and the run records + clump records of a whole segment (<= 32 runs) are
-//     fetched by one coalesced load per lane before the first of them is needed;
-//   * a probe is seven instructions: two multiply-adds (hash of the 16-base window), shift + address,
-//     one shared load, and two funnel shifts that test the bit and append it to the hit mask;
+//     set lives in the warp's private slice of shared memory -- a blocked two-bit Bloom filter (the scan
+//     filter) and chained buckets of window ids (the exact verification; one atomicExch per insertion)
+//     -- built by the 32 lanes together and kept for every clump visit (run) of the bunch; only
+//     __syncwarp() orders it;
+//   * the two half-warps scan two runs of the bunch at a time, a thread per reference lane.  Clumps come
+//     through TMA: the first lane of a half-warp issues ONE bulk copy (cp.async.bulk, <= NCH * 256 bytes)
+//     of the next item into the half-warp's second staging buffer and arms its mbarrier, then everyone
+//     probes the current buffer (128-bit conflict-free shared loads); the exact verification of a hit
+//     re-reads its words from the same buffer, never from global memory.  The run records + clump records
+//     of a whole segment (<= 32 runs) are fetched by one coalesced load per lane before the first is needed;
+//   * a probe is ten instructions: two multiply-adds (hash of the 16-base window), shift + address,
+//     one shared load, three shifts + an AND that test the two bits, one funnel shift that appends the
+//     result to the hit mask;
 //   * survivors of the usual kind (one query, one diagonal cluster) leave through one atomicAdd per warp.
 // Work is cut into chunks of `chunk` consecutive runs, chunks are dealt to warps round-robin; a bunch is
 // scanned by the warp whose chunk holds its first run (bunches longer than SEEDW_SPLIT runs are split), so
@@ -692,23 +696,41 @@ struct SeedWArgs {
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;
 	uint32_t m16[8];
 };
-// per-warp shared memory in words: bitmap | slots | stretch records | budgets
-__host__ __device__ __forceinline__ uint32_t seedw_warp_words(uint32_t lbits, uint32_t hslots, uint32_t npmax) {
-	return (1u << (lbits - 5)) + hslots + 64 * npmax + 16;
+// per-warp shared memory in words: filter | bucket heads | chain links (16 bit) | stretch records | budgets | 4 staging buffers (2 per half-warp) |
+// 4 mbarriers | 32 survivors waiting to leave.  hslots = buckets (power of two), ne = windows the table can hold = 16 * npmax * stride
+__host__ __device__ __forceinline__ uint32_t seedw_warp_words(uint32_t lbits, uint32_t hslots, uint32_t npmax, uint32_t stride, uint32_t nch) {
+	return (1u << (lbits - 5)) + hslots + ((8 * npmax * stride + 3) & ~3u) + 64 * npmax + 16 + 4 * nch * 64 + 8 + 128;
 }
 
 template <int STRIDE, bool FULLW, int NCH>
-__global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(SeedWArgs A) {
+__global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 	extern __shared__ __align__(16) uint32_t smem[];
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
 	constexpr int NW = NCH * 4;                                           // words (of 8 columns) per item
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l = lane & 15;
 	const uint32_t BW = 1u << (A.lbits - 5), HSM = A.hslots - 1, NPM = A.npmax;
 	uint32_t *sM = smem;
-	uint32_t *bits = smem + 16 + warp * seedw_warp_words(A.lbits, A.hslots, NPM), *slots = bits + BW, *str = slots + A.hslots, *kq = str + 64 * NPM;
+	uint32_t *bits = smem + 16 + warp * seedw_warp_words(A.lbits, A.hslots, NPM, STRIDE, NCH), *slots = bits + BW;   // slots: bucket heads, entry + 1 (0 = empty)
+	uint16_t *nxt = (uint16_t *)(slots + A.hslots);                        // chain links
+	uint32_t *str = slots + A.hslots + ((8 * NPM * STRIDE + 3) & ~3u), *kq = str + 64 * NPM;
+	constexpr uint32_t ITEM = NCH * 256;                                   // bytes of one staging buffer
+	uint32_t *stage0 = kq + 16;                                            // this warp's staging: half h uses buffers 2h, 2h+1
 	const uint32_t bits_s = (uint32_t)__cvta_generic_to_shared(bits);
+	const uint32_t stg_s = (uint32_t)__cvta_generic_to_shared(stage0) + half * 2 * ITEM;
+	const uint32_t bar_s = (uint32_t)__cvta_generic_to_shared(stage0 + 4 * NCH * 64) + half * 16;
 	if (threadIdx.x < 16) sM[threadIdx.x] = (A.m16[threadIdx.x >> 1] >> (16 * (threadIdx.x & 1))) & 0xFFFFu;
+	if (l == 0) { mbar_init(bar_s, 1); mbar_init(bar_s + 8, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 	__syncthreads();
+	uint32_t cb = 0, phase = 0;                                            // staging buffer that holds the current item (warp-uniform); per-buffer mbarrier parity
+	uint4 *sbuf = (uint4 *)(stage0 + 4 * NCH * 64 + 8); uint32_t scount = 0;   // survivors collected by the warp; they leave 32 at a time through one atomicAdd
+	auto flush = [&]() {
+		uint32_t base = 0;
+		if (lane == 0) base = atomicAdd(&A.counters[C_SURV], scount);
+		base = __shfl_sync(FULL, base, 0);
+		if (lane < scount && base + lane < A.surv_cap) ((uint4 *)A.surv)[base + lane] = sbuf[lane];
+		scount = 0;
+		__syncwarp();
+	};
 	const uint32_t HM = FULLW ? FULL : A.SL.hm, SHB = 32 - (A.lbits - 5), ADD = A.SL.amb_add, ambsel = ADD == 0x33333333u ? 3u : 1u;
 	const unsigned long long NOKEY = ~0ull;
 	unsigned long long tableK = NOKEY; bool table_any = false;            // the bunch the warp's table holds; whether any of its queries is seeded
@@ -770,9 +792,9 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 						for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
 							const QWin w = window_of(S, j);
 							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
-							atomicOr(&bits[hv >> SHB], 0x80000000u >> (hv & 31));
-							uint32_t s = (hv >> 4) & HSM;
-							while (atomicCAS(&slots[s], 0u, si * STRIDE + j + 1u) != 0u) s = (s + 1) & HSM;
+							atomicOr(&bits[hv >> SHB], (0x80000000u >> (hv & 31)) | (0x80000000u >> ((hv >> 5) & 31)));
+							const uint32_t e = si * STRIDE + j;
+							nxt[e] = (uint16_t)atomicExch(&slots[(hv >> 10) & HSM], e + 1u);
 						}
 					} else *(uint4 *)(str + si * 4) = make_uint4(0, 0, 0, 0);
 				}
@@ -792,18 +814,18 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 					D.valid = __shfl_sync(FULL, (uint32_t)d_ok, src) != 0 && t < seglen;
 					return D;
 				};
-				auto issue = [&](uint4 (&buf)[NCH], const RunD &D, uint32_t g) {
-					const uint32_t nchunks = (D.len + 31) >> 5;
-					const uint4 *gp = A.db + D.off + l;
-					#pragma unroll
-					for (int c = 0; c < NCH; ++c) {
-						const uint32_t ck = g * NCH + c;
-						buf[c] = (D.valid && ck < nchunks) ? __ldg(gp + (size_t)ck * 16) : make_uint4(0, 0, 0, 0);
+				// bulk copy of item g of run D into staging buffer b of this half-warp (its first lane issues; the others only wait later)
+				auto stage = [&](const RunD &D, uint32_t g, uint32_t b) {
+					if (D.valid && l == 0) {
+						const uint32_t nchunks = (D.len + 31) >> 5, bytes = min((uint32_t)NCH, nchunks - g * NCH) * 256u;
+						mbar_expect_tx(bar_s + 8 * b, bytes);
+						bulk_g2s(stg_s + b * ITEM, A.db + D.off + (size_t)g * NCH * 16, bytes, bar_s + 8 * b);
 					}
 				};
 				uint32_t ct = half, cg = 0;                                    // current run (index in the segment) and item within it
 				RunD C = fetch(ct);
 				uint32_t prev = 0, prev2 = 0, ambp = 0, ambp2 = 0;             // scan state carried from item to item of a run
+				uint32_t iprev = 0, iprev2 = 0;                                // the two words before the current item (for verifying its first words)
 				uint32_t sn = 0, sq = 0; int dlo = 0, dhi = 0;                 // seeds of the current run: 0 none, 1 one query + a narrow hull (registers), 2 list (LS)
 				bool more = true;
 
@@ -819,34 +841,41 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 					else lane_seeds_overflow(LS, q, dg);
 				};
 
-				auto step = [&](uint4 (&cur)[NCH], uint4 (&nxt)[NCH]) {
+				auto step = [&]() {
 					// ---- the item after this one: load it now, probe it in the next step ----
 					const uint32_t ngroups = C.valid ? (((C.len + 31) >> 5) + NCH - 1) / NCH : 1u;
 					const bool lastg = cg + 1 >= ngroups;
 					const uint32_t nt = lastg ? ct + 2 : ct, ng = lastg ? 0u : cg + 1;
 					const RunD F = fetch(nt);
 					const RunD N = lastg ? F : C;
-					issue(nxt, N, ng);
+					__syncwarp();                                              // everyone is done with the other buffer (read in the previous step)
+					stage(N, ng, cb ^ 1);
 					bool emit = false; Surv ev; ev.task = 0; ev.lo = 0; ev.w_lane = 0; ev.scratch = 0;
 					if (C.valid) {
 						const uint32_t nchunks = (C.len + 31) >> 5;
 						const bool amb_on = (C.flags & ambsel) != 0;
 						if (cg == 0) { prev = prev2 = ambp = ambp2 = 0; }
+						iprev = prev; iprev2 = prev2;
+						const uint32_t sb = stg_s + cb * ITEM + l * 16;              // this lane's pieces: chunk c at sb + c * 256
+						mbar_wait(bar_s + 8 * cb, (phase >> cb) & 1u); phase ^= 1u << cb;
 						uint32_t m8 = 0, m4 = 0;
 						auto scan = [&](auto amb_c) {
 							constexpr bool AMB = decltype(amb_c)::value;
 							#pragma unroll
 							for (int c = 0; c < NCH; ++c) {
-								const uint32_t ws[4] = {cur[c].x, cur[c].y, cur[c].z, cur[c].w};
+								const uint4 cw = lds128(sb + c * 256);
+								const uint32_t ws[4] = {cw.x, cw.y, cw.z, cw.w};
 								#pragma unroll
 								for (int j = 0; j < 4; ++j) {
 									const uint32_t cu = ws[j];
 									const uint32_t h8 = seed_hash(cu, prev & HM);
-									uint32_t t8 = __funnelshift_l(0u, lds32(bits_s + ((h8 >> SHB) << 2)), h8);     // the window's bit -> bit 31
+									const uint32_t f8 = lds32(bits_s + ((h8 >> SHB) << 2));
+									uint32_t t8 = __funnelshift_l(0u, f8, h8) & __funnelshift_l(0u, f8, h8 >> 5);    // both bits of the window -> bit 31
 									uint32_t t4 = 0;
 									if (STRIDE == 4) {
 										const uint32_t h4 = seed_hash(__funnelshift_r(prev, cu, 16), __funnelshift_r(prev2, prev, 16) & HM);
-										t4 = __funnelshift_l(0u, lds32(bits_s + ((h4 >> SHB) << 2)), h4);
+										const uint32_t f4 = lds32(bits_s + ((h4 >> SHB) << 2));
+										t4 = __funnelshift_l(0u, f4, h4) & __funnelshift_l(0u, f4, h4 >> 5);
 									}
 									if (AMB) {
 										const uint32_t ambc = amb_nibbles(cu, ADD);
@@ -866,10 +895,11 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 						m8 &= vm; m4 &= vm;
 						// ---- verify this lane's flagged words against the window table; seeds -> clusters ----
 						if (m8 | m4) {
-							const uint4 *gp = A.db + C.off;
-							auto word_at = [&](uint32_t wi) -> uint32_t { return __ldg((const uint32_t *)(gp + (size_t)(wi >> 2) * 16 + l) + (wi & 3)); };
+							// word wl of the item (wl = -1, -2: the words before it), from the staging buffer
+							auto word_at = [&](int wl) -> uint32_t { return wl >= 0 ? lds32(sb + (uint32_t)(wl >> 2) * 256 + (uint32_t)(wl & 3) * 4) : (wl == -1 ? iprev : iprev2); };
 							auto verify = [&](uint32_t wi, int e) {
-								const uint32_t cu = word_at(wi), pv = wi >= 1 ? word_at(wi - 1) : 0u, pv2 = (e == 4 && wi >= 2) ? word_at(wi - 2) : 0u;
+								const int wl = (int)(wi - cg * NW);
+								const uint32_t cu = word_at(wl), pv = word_at(wl - 1), pv2 = e == 4 ? word_at(wl - 2) : 0u;
 								const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
 								const int x1 = (int)(wi * 8 + e);
 								if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the bunch, through the table
@@ -884,9 +914,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 									}
 								} else {
 									const uint32_t hv = seed_hash(rn, ro);
-									for (uint32_t s = (hv >> 4) & HSM;; s = (s + 1) & HSM) {
-										const uint32_t en = slots[s];
-										if (!en) break;
+									for (uint32_t en = slots[(hv >> 10) & HSM]; en; en = nxt[en - 1]) {
 										const uint32_t si = (en - 1) / STRIDE, j = (en - 1) % STRIDE;
 										const uint4 rec = *(const uint4 *)(str + si * 4);
 										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
@@ -916,22 +944,18 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 					}
 					const uint32_t em = __ballot_sync(FULL, emit);
 					if (em) {
-						uint32_t base = 0;
-						if (lane == (uint32_t)__ffs(em) - 1) base = atomicAdd(&A.counters[C_SURV], (uint32_t)__popc(em));
-						base = __shfl_sync(FULL, base, __ffs(em) - 1);
-						const uint32_t pos = base + __popc(em & ((1u << lane) - 1u));
-						if (emit && pos < A.surv_cap) A.surv[pos] = ev;
+						if (scount + __popc(em) > 32) flush();
+						if (emit) sbuf[scount + __popc(em & ((1u << lane) - 1u))] = make_uint4(ev.task, (uint32_t)ev.lo, ev.w_lane, ev.scratch);
+						scount += __popc(em);
+						__syncwarp();
 					}
-					ct = nt; cg = ng; C = N;
+					ct = nt; cg = ng; C = N; cb ^= 1;
 					more = __any_sync(FULL, ct < seglen);
 				};
 
-				uint4 bufA[NCH], bufB[NCH];
-				issue(bufA, C, 0);
-				for (;;) {
-					step(bufA, bufB); if (!more) break;
-					step(bufB, bufA); if (!more) break;
-				}
+				__syncwarp();
+				stage(C, 0, cb);
+				while (more) step();
 			}
 
 			i += seglen;
@@ -939,6 +963,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, NCH == 8 ? 4 : 5) k_seedw(Se
 			if (i >= cend && (i % SEEDW_SPLIT == 0 || key_of(i) != K)) break;  // past the chunk: go on only while the bunch does
 		}
 	}
+	if (scount) flush();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1061,7 +1086,7 @@ struct ExtendArgs {
 	const uint32_t *dbw; const ClumpMeta *meta;
 	const uint8_t *codes; const uint32_t *qnib; const QInfo *qi; Work W;
 	const Surv *surv; uint32_t surv_cap; const uint32_t *counters;
-	const uint32_t *cls, *order;                         // survivors of this launch binned by band class (k_bin_*)
+	const uint32_t *cls; const uint4 *xs;                // survivors of this launch binned by band class, as expanded records (k_bin_*)
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
 	uint32_t *scratch; uint32_t scratch_cap;
 	unsigned long long *band_cells;
@@ -1109,13 +1134,24 @@ __global__ void k_bin_offsets(const uint32_t *__restrict__ counters, uint32_t su
 	uint32_t o = firstp ? min(*firstp, nsurv) : 0u;
 	for (int c = 0; c < NCLASS; ++c) { cls[16 + c] = o; cls[32 + c] = 0; o += cls[c]; }
 }
+// One record per survivor, in class order, holding everything the sweep needs: the survivor itself plus what the chain
+// survivor -> run -> (query record, clump record) resolves to.  This kernel has a thread per survivor and nothing to compute, so the
+// chain's latency hides behind its parallelism; k_extend then starts from ONE coalesced 48-byte read.
+struct XSurv {
+	uint32_t task; int32_t lo; uint32_t w_lane, scratch;      // the survivor
+	uint32_t coff_lo, coff_hi, L, qw;                           // clump: offset in uint4 units, length; query: word index of its packed bases in qnib
+	uint32_t m, slot, k_flags, index;                           // query length, slot, budget | plain << 16; index of the survivor in the list
+};
 __global__ void k_bin_scatter(const Surv *__restrict__ surv, const uint32_t *__restrict__ counters, uint32_t surv_cap, const uint32_t *__restrict__ firstp,
-		uint32_t *__restrict__ cls, uint32_t *__restrict__ order) {
+		uint32_t *__restrict__ cls, uint4 *__restrict__ xs, Work W, const QInfo *__restrict__ qi, const ClumpMeta *__restrict__ meta) {
 	const uint32_t nsurv = min(counters[C_SURV], surv_cap), first = firstp ? min(*firstp, nsurv) : 0u;
 	const uint32_t lane = threadIdx.x & 31;
 	for (uint32_t i0 = first + (blockIdx.x * blockDim.x + threadIdx.x - lane); i0 < nsurv; i0 += gridDim.x * blockDim.x) {
 		const uint32_t i = i0 + lane;
-		const uint32_t c = i < nsurv ? class_of(surv[i].w_lane >> 8) : 0xFFu;
+		Surv sv; sv.task = 0; sv.lo = 0; sv.w_lane = 0; sv.scratch = 0;
+		if (i < nsurv) sv = surv[i];
+		const uint32_t c = i < nsurv ? class_of(sv.w_lane >> 8) : 0xFFu;
+		uint32_t pos = 0;
 		// one atomic per class present in the warp; positions inside a class keep the survivor order
 		for (uint32_t todo = __ballot_sync(0xFFFFFFFFu, i < nsurv); todo;) {
 			const uint32_t lead = __ffs(todo) - 1, cc = __shfl_sync(0xFFFFFFFFu, c, lead);
@@ -1123,12 +1159,21 @@ __global__ void k_bin_scatter(const Surv *__restrict__ surv, const uint32_t *__r
 			uint32_t base = 0;
 			if (lane == lead) base = atomicAdd(&cls[32 + cc], (uint32_t)__popc(same));
 			base = __shfl_sync(0xFFFFFFFFu, base, lead);
-			if (c == cc) order[cls[16 + cc] + base + __popc(same & ((1u << lane) - 1u))] = i;
+			if (c == cc) pos = cls[16 + cc] + base + __popc(same & ((1u << lane) - 1u));
 			todo &= ~same;
+		}
+		if (i < nsurv) {
+			uint32_t cl, q0, n;
+			get_run(W, (sv.task >> 4) - W.run_base, cl, q0, n);
+			const uint32_t qix = q0 + (sv.task & 15);
+			const uint4 cm = __ldg((const uint4 *)(meta + cl));
+			const QInfo Q = qi[qix];
+			xs[(size_t)pos * 3] = make_uint4(sv.task, (uint32_t)sv.lo, sv.w_lane, sv.scratch);
+			xs[(size_t)pos * 3 + 1] = make_uint4(cm.x, cm.y, cm.z, (uint32_t)((Q.off >> 3) + 3ull * qix + 2));
+			xs[(size_t)pos * 3 + 2] = make_uint4(Q.len, Q.slot, (uint32_t)Q.k | ((Q.cls & 2u) << 15), i);
 		}
 	}
 }
-
 
 template <int WMAX>
 __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
@@ -1140,25 +1185,22 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	__syncthreads();
 	unsigned long long cells = 0;
 	for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
-		const uint32_t i = A.order[begin + p];
-		const Surv sv = A.surv[i];
+		const uint4 x0 = __ldg(A.xs + (size_t)(begin + p) * 3), x1 = __ldg(A.xs + (size_t)(begin + p) * 3 + 1), x2 = __ldg(A.xs + (size_t)(begin + p) * 3 + 2);
+		Surv sv; sv.task = x0.x; sv.lo = (int32_t)x0.y; sv.w_lane = x0.z; sv.scratch = x0.w;
+		const uint32_t i = x2.w;
 		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 15;
-		uint32_t c, q0, n;
-		get_run(A.W, (sv.task >> 4) - A.W.run_base, c, q0, n);
-		const uint32_t qix = q0 + (sv.task & 15);
-		const uint4 cm = __ldg((const uint4 *)(A.meta + c));              // clump record: one 16-byte load
-		const QInfo Q = A.qi[qix];
-		const uint32_t m = Q.len, L = cm.z;
-		const uint32_t *lanew = A.dbw + ((uint64_t)cm.x | ((uint64_t)cm.y << 32)) * 4 + lane * 4;
-		uint32_t k = Q.k;
-		if (A.mode == BG_MODE_MIN) k = min(k, A.best[Q.slot]);
+		const uint32_t m = x2.x, L = x1.z, slot = x2.y;
+		const bool plain = (x2.z >> 16) & 1u;
+		const uint32_t *lanew = A.dbw + ((uint64_t)x1.x | ((uint64_t)x1.y << 32)) * 4 + lane * 4;
+		uint32_t k = x2.z & 0xFFFFu;
+		if (A.mode == BG_MODE_MIN) k = min(k, A.best[slot]);
 		uint32_t inf = (k + 1) << 22;
 		const int lo = sv.lo;
 		constexpr int WB = WMAX ? WMAX : 1;
 		const int Wd = WMAX ? WMAX : (int)W;                 // cells per row actually swept
 		uint32_t a[WB];                                      // band, register resident when WMAX > 0
 		uint32_t *g = A.scratch + sv.scratch;                // generic path: band in global scratch
-		if (WMAX == 0 && (uint64_t)sv.scratch + W > A.scratch_cap) { Res z; z.a = 0; z.b = 0; z.slot = Q.slot; A.res[i] = z; continue; }
+		if (WMAX == 0 && (uint64_t)sv.scratch + W > A.scratch_cap) { Res z; z.a = 0; z.b = 0; z.slot = slot; A.res[i] = z; continue; }
 		bool dead = false;
 		uint32_t y = 1;
 
@@ -1170,7 +1212,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			constexpr uint32_t TOPMASK = (WB & 7) ? (1u << (4 * (WB & 7))) - 1u : 0xFFFFFFFFu;   // nibbles of the last window word inside the band
 			uint32_t win[NW];                                // codes of columns x0 .. x0+WB-1, one nibble each
 			const int nwords = (int)((L + 7) >> 3);
-			const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * qix + 2;
+			const uint32_t *Wq = A.qnib + x1.w;
 			// row 0: zero for columns 0..L (burst.c:4052 calloc / 723-725), absent elsewhere
 			#pragma unroll
 			for (int d = 0; d < WB; ++d) { const int x = lo + d; a[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
@@ -1186,23 +1228,35 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			const uint32_t sh2 = (uint32_t)((cb + WB) & 7) * 4;
 			if (EXTRA) { wi = (cb + WB) >> 3; w0 = lane_word_or0(lanew, wi, nwords); }
 			win[NW - 1] &= TOPMASK;
-			uint32_t w1 = lane_word_or0(lanew, ++wi, nwords);
-			uint32_t feed = __funnelshift_r(w0, w1, sh2), qw = __ldg(Wq);
+			// Group g (rows 8g+1 .. 8g+8) needs the reference words wbase+g, wbase+g+1 and the query word g.  They are kept in small rings and
+			// fetched D+1 groups ahead: the sweep of a group is ~70 instructions, far less than a DRAM round trip.
+			constexpr int D = 4;
+			const int wbase = wi;
+			uint32_t R[D + 1], Qw[D], RN[D], QN[D];
 			const uint32_t ngroups = (m + 7) >> 3;
+			#pragma unroll
+			for (int u = 0; u <= D; ++u) R[u] = u == 0 ? w0 : lane_word_or0(lanew, wbase + u, nwords);
+			#pragma unroll
+			for (int u = 0; u < D; ++u) { Qw[u] = (uint32_t)u < ngroups ? __ldg(Wq + u) : 0u; RN[u] = 0; QN[u] = 0; }
 			uint32_t bpre = k;                               // the slot's running minimum, fetched one group (8 rows) before it is applied
 			// Fast rows: query and reference codes all plain bases, band inside the matrix, short query.  Then the substitution cost is
 			// "the nibbles differ" (one XOR per row, no table), and cells above the budget need no clamp: they can never win or tie a
 			// cell within it, and with m + WB < 480 no field of the key can overflow.
-			const bool fastok = WMAX <= 32 && (Q.cls & 2) && m + WB + 8 < 480;
+			const bool fastok = WMAX <= 32 && plain && m + WB + 8 < 480;
 			int badrows = 0;                                 // rows during which the window may still hold a code that is not a plain base
 			#pragma unroll
 			for (int j = 0; j < NW; ++j) if (nonplain_nibbles(win[j] | (j == NW - 1 ? ~TOPMASK & 0x11111111u : 0u))) badrows = WB;
-			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
+			for (uint32_t gq0 = 0; gq0 < ngroups && !dead; gq0 += D) {
+			#pragma unroll
+			for (int u = 0; u < D; ++u) {
+				const uint32_t gq = gq0 + u;
+				if (gq >= ngroups || dead) break;
 				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
 				k = min(k, bpre); inf = (k + 1) << 22;
-				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + Q.slot);
-				// next group's words: issued here, first touched after the 8 rows below (ignored after the last group)
-				const uint32_t wn = lane_word_or0(lanew, ++wi, nwords), nqw = gq + 1 < ngroups ? __ldg(Wq + gq + 1) : 0u;
+				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + slot);
+				// the words this ring slot will hold in the next round: issued here, first touched D groups later
+				RN[u] = lane_word_or0(lanew, wbase + (int)gq0 + D + 1 + u, nwords); QN[u] = gq0 + D + u < ngroups ? __ldg(Wq + gq0 + D + u) : 0u;
+				const uint32_t feed = __funnelshift_r(R[u], R[u + 1], sh2), qw = Qw[u];
 				const int x0g = (int)y + lo;                 // column (1-based) of band cell 0 in the first row of the group
 				if (nonplain_nibbles(feed)) badrows = WB + 8;
 				const bool fast = fastok && badrows == 0 && y + 7 <= m && x0g >= 1 && x0g + 7 + WB - 1 <= (int)L;
@@ -1273,11 +1327,16 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					++y;
 				}
 				}
-				w0 = w1; w1 = wn; feed = __funnelshift_r(w0, w1, sh2); qw = nqw;
+			}
+			R[0] = R[D];
+			#pragma unroll
+			for (int u = 0; u < D; ++u) { R[u + 1] = RN[u]; Qw[u] = QN[u]; }
 			}
 			if (!dead) y = m + 1;
 		} else {
-			const uint8_t *qs = A.codes + Q.off;
+			uint32_t c_, q0_, n_;
+			get_run(A.W, (sv.task >> 4) - A.W.run_base, c_, q0_, n_);
+			const uint8_t *qs = A.codes + A.qi[q0_ + (sv.task & 15)].off;
 			for (int d = 0; d < Wd; ++d) { const int x = lo + d; g[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
 			for (; y <= m; ++y) {
 				const int x0 = (int)y + lo;
@@ -1294,7 +1353,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					diag = up; g[d] = v; left = v; rowmin = min(rowmin, v);
 				}
 				if (rowmin >= inf) { dead = true; break; }
-				if ((y & 15) == 0 && A.mode == BG_MODE_MIN) { k = min(k, A.best[Q.slot]); inf = (k + 1) << 22; }
+				if ((y & 15) == 0 && A.mode == BG_MODE_MIN) { k = min(k, A.best[slot]); inf = (k + 1) << 22; }
 			}
 		}
 		cells += (unsigned long long)(dead ? y : m) * (unsigned)Wd;
@@ -1316,10 +1375,10 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			const uint32_t ed = bk >> 11, sh = 2047u - (bk & 2047u);
 			if (bk != (KEY_NONE >> 11) && ed <= k) {
 				out = ed | (sh << 8) | (bshr << 16) | (1u << 31);
-				atomicMin(&A.best[Q.slot], ed);
+				atomicMin(&A.best[slot], ed);
 			}
 		}
-		Res r; r.a = out; r.b = fp; r.slot = Q.slot;
+		Res r; r.a = out; r.b = fp; r.slot = slot;
 		A.res[i] = r;
 	}
 	if (cells) atomicAdd(A.band_cells, cells);
@@ -1449,7 +1508,7 @@ struct bg_ctx {
 	DBuf<uint8_t> d_packed; DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
 	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
-	DBuf<uint32_t> d_cls, d_sorder;                               // band-class bins of the survivors (k_bin_*)
+	DBuf<uint32_t> d_cls; DBuf<uint4> d_xs;                       // band-class bins of the survivors, expanded records (k_bin_*)
 	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
 	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;   // cells: [0] band, [1..4] work stats
@@ -1523,7 +1582,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
 	c->d_packed.release(); c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
 	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
-	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_cls.release(); c->d_sorder.release();
+	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_cls.release(); c->d_xs.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -1712,7 +1771,7 @@ static int finish_upload(bg_ctx *c) {
 	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
 	want = std::max<uint64_t>(want, 1024);
 	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
-	if (c->d_surv.need(c->surv_cap) || c->d_sorder.need(c->surv_cap) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+	if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 	if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
 	c->ran = false; c->sorted = false;
 	return BG_OK;
@@ -1787,14 +1846,14 @@ static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const See
 	uint32_t chunk = 1; while (chunk * 2 <= (uint32_t)c->seed_chunk * 4 && chunk < SEEDW_SPLIT) chunk <<= 1;   // a power of two that divides SEEDW_SPLIT
 	S.chunk = chunk; S.npmax = npmax;
 	const uint32_t ne = BG_RUN_MAX * npmax * SL.stride;                 // most windows a bunch can hold
-	S.hslots = 64; while (S.hslots < 2 * ne) S.hslots <<= 1;
-	// bitmap: ~128 bits per window of a typical full bunch (SL.words was sized as 1-2 words per such window), so that a false
-	// positive -- one table probe by the owning thread -- stays below one per run
+	S.hslots = 64; while (S.hslots < ne) S.hslots <<= 1;                 // buckets of the chained window table
+	// filter: two bits per window in one 32-bit word; ~64 bits per window of a typical full bunch (SL.words was sized as 1-2 words per
+	// such window) keep false positives -- one bucket probe by the owning thread -- well below one per run
 	uint32_t lbits = 12; while (lbits < 17 && (1u << lbits) < 64u * SL.words) ++lbits;
 	if (c->seed_lbits) lbits = (uint32_t)c->seed_lbits;
-	while (lbits > 10 && (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax)) * 4 > 200 * 1024) --lbits;
+	while (lbits > 10 && (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * 4 > 200 * 1024) --lbits;
 	S.lbits = lbits;
-	const size_t smem = (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax)) * sizeof(uint32_t);
+	const size_t smem = (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * sizeof(uint32_t);
 	if (smem > 220 * 1024) return fail(BG_EINVAL, "seed filter tables do not fit shared memory (stretches %u, stride %u)", npmax, SL.stride);
 	S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 	memcpy(S.m16, c->m16, sizeof(S.m16));
@@ -1854,11 +1913,11 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 	CU(cudaMemsetAsync(c->d_cls.p, 0, 64 * sizeof(uint32_t), st));
 	k_bin_count<<<(unsigned)c->sms * 4, 256, 0, st>>>(c->d_surv.p, c->d_counters.p, c->surv_cap, first, c->d_cls.p);
 	k_bin_offsets<<<1, 32, 0, st>>>(c->d_counters.p, c->surv_cap, first, c->d_cls.p);
-	k_bin_scatter<<<(unsigned)c->sms * 4, 256, 0, st>>>(c->d_surv.p, c->d_counters.p, c->surv_cap, first, c->d_cls.p, c->d_sorder.p);
+	k_bin_scatter<<<(unsigned)c->sms * 8, 256, 0, st>>>(c->d_surv.p, c->d_counters.p, c->surv_cap, first, c->d_cls.p, c->d_xs.p, B.W, B.qi, c->d_meta.p);
 	ExtendArgs E;
 	E.dbw = (const uint32_t *)c->d_db.p; E.meta = c->d_meta.p;
 	E.codes = B.codes; E.qnib = B.qnib; E.qi = B.qi; E.W = B.W;
-	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.cls = c->d_cls.p; E.order = c->d_sorder.p; E.res = c->d_res.p;
+	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.cls = c->d_cls.p; E.xs = c->d_xs.p; E.res = c->d_res.p;
 	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
 	E.band_cells = c->d_cells.p; E.mode = mode;
 	const unsigned g = (unsigned)c->sms * 12;
@@ -1931,7 +1990,7 @@ static int settle(bg_ctx *c) {
 		if (!grow_s && !grow_g) return BG_OK;
 		if (grow_s) {
 			c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
-			if (c->d_surv.need(c->surv_cap) || c->d_sorder.need(c->surv_cap) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+			if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		}
 		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
 		int rc = run_extend(c, c->last_mode, c->have_best_in ? c->last_best_in.data() : nullptr);
@@ -2068,7 +2127,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 	}
 	const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
 	for (int attempt = 0; attempt < 4; ++attempt) {
-		if (c->d_surv.need(c->surv_cap) || c->d_sorder.need(c->surv_cap) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+		if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
 		if (c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128)) return BG_ENOMEM;
 		cudaStream_t cs = c->stream, ps = c->copy_stream;

@@ -156,8 +156,13 @@ def nul_terminated(qcodes, qoff):
     return out, noff, lens.astype(np.uint32)
 
 
-def reference_run_bunches(ref, w, nbunches=None, threads=1):
-    """Drive Reference (libburstref.so) over the first nbunches bunches of a synth.bunch_workload."""
+SHIMHIT_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4"), ("lane", "u1"), ("ed", "u1"), ("gap_q", "u1"), ("gap_r", "u1"), ("final_pos", "<u4")])
+
+
+def reference_run_bunches(ref, w, nbunches=None, threads=1, sample_mod=0):
+    """Drive Reference (libburstref.so) over the first nbunches bunches of a synth.bunch_workload.
+    With sample_mod, also returns under "hits" the lanes the reference keeps (ed == final minimum of the slot) for the
+    queries whose slot % sample_mod == 0, sorted by (query, clump, lane)."""
     qb = w["qbunch"]
     nq_all = len(w["qoff"]) - 1
     nb_all = (nq_all + qb - 1) // qb
@@ -167,7 +172,9 @@ def reference_run_bunches(ref, w, nbunches=None, threads=1):
     ed = np.full(w["nslots"], 0, np.uint16)
     ed[w["slot"][:nq]] = w["budget"][:nq]          # ShrBins[].ed starts at the budget (burst.c:3076)
     budget0 = ed.copy()
-    nres = C.c_uint64(0); nhits = C.c_uint64(0); ninst = C.c_uint64(0)
+    nres = C.c_uint64(0); nhits = C.c_uint64(0); ninst = C.c_uint64(0); nrec = C.c_uint64(0)
+    found = np.zeros(w["nslots"], np.uint8)
+    rec = np.zeros((nq // max(sample_mod, 1)) * 8 + 1024 if sample_mod else 1, SHIMHIT_DTYPE)
     L = ref.lib
     L.refshim_run_bunches.restype = C.c_uint64
     calls = L.refshim_run_bunches(
@@ -176,6 +183,12 @@ def reference_run_bunches(ref, w, nbunches=None, threads=1):
         _p(qc), _p(noff), _p(lens), _p(np.ascontiguousarray(w["slot"][:nq], np.uint32)), _p(ed),
         C.c_uint64(nq), C.c_uint32(qb), _p(np.ascontiguousarray(w["cand_off"][:nb + 1], np.uint64)),
         _p(np.ascontiguousarray(w["cand"], np.uint32)), C.c_int(threads),
-        C.byref(nres), C.byref(nhits), C.byref(ninst))
+        C.byref(nres), C.byref(nhits), C.byref(ninst),
+        _p(found), C.c_uint32(sample_mod), _p(rec), C.c_uint64(len(rec)), C.byref(nrec))
+    assert nrec.value <= len(rec), "sample record buffer too small"
+    best = np.where(found != 0, ed, 0xFFFF).astype(np.uint16)         # the ABI's convention: 0xFFFF = no lane within budget
+    rec = rec[:nrec.value]
+    rec = rec[rec["ed"] == best[w["slot"][rec["query"]]]]
+    rec = rec[np.lexsort((rec["lane"], rec["clump"], rec["query"]))]
     return dict(calls=int(calls), rescore=int(nres.value), lanes=int(nhits.value), truncated=int(ninst.value),
-                ed=ed, budget0=budget0, nq=nq, nb=nb)
+                ed=ed, best=best, found=found, hits=rec, budget0=budget0, nq=nq, nb=nb)

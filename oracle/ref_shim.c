@@ -175,13 +175,19 @@ uint64_t refshim_run_tasks(const uint8_t *packed, const uint64_t *clump_off, con
  * The per-query k-mer-count skip (burst.c:4163-4168) is not applied: the caller expands exactly
  * the same (query, clump) pairs for the GPU arm.  ed_slot is shared and unsynchronised, as
  * ShrBins[].ed is in the reference.  Returns the number of pass-1 calls. */
+/* found_slot[s] = 1 once any lane of slot s reached its running minimum (ed_slot starts at the budget, so the minimum
+ * alone cannot tell "no hit" from "hit at the budget").  With sample_mod != 0 every lane the reference would push as a
+ * ResultPod (burst.c:4228-4238) for a query whose slot % sample_mod == 0 is also written to rec[] (query, clump, lane,
+ * ed, numGapQ, numGapR, finalPos): the caller keeps those whose ed equals the slot's final minimum (burst.c:4497-4517). */
+typedef struct { uint32_t query, clump; uint8_t lane, ed, gap_q, gap_r; uint32_t final_pos; } ShimHit;
 __attribute__((visibility("default")))
 uint64_t refshim_run_bunches(const uint8_t *packed, const uint64_t *clump_off, const uint32_t *clump_len,
 		uint32_t max_clump_len, const char *qcodes, const uint64_t *qoff, const uint32_t *qlen,
 		const uint32_t *slot, uint16_t *ed_slot, uint64_t nq, uint32_t qbunch,
 		const uint64_t *cand_off, const uint32_t *cand, int threads,
-		uint64_t *n_rescore, uint64_t *n_hits, uint64_t *n_instant) {
-	uint64_t calls = 0, resc = 0, hits = 0, instant = 0;
+		uint64_t *n_rescore, uint64_t *n_hits, uint64_t *n_instant,
+		uint8_t *found_slot, uint32_t sample_mod, ShimHit *rec, uint64_t rec_cap, uint64_t *n_rec) {
+	uint64_t calls = 0, resc = 0, hits = 0, instant = 0, nrec = 0;
 	uint32_t maxq = 0;
 	for (uint64_t q = 0; q < nq; ++q) if (qlen[q] > maxq) maxq = qlen[q];
 	int savedCache = cacheSz;
@@ -243,6 +249,13 @@ uint64_t refshim_run_bunches(const uint8_t *packed, const uint64_t *clump_off, c
 							S->ShiftsBX, min, 0, &MPK);
 						++resc;
 						for (int l = 0; l < 16; ++l) hits += m.u8[l] <= min;
+						if (found_slot) found_slot[slot[j]] = 1;
+						if (sample_mod && slot[j] % sample_mod == 0) for (int l = 0; l < 16; ++l) if (m.u8[l] <= min) {
+							uint64_t ix;
+							#pragma omp atomic capture
+							ix = nrec++;
+							if (ix < rec_cap) rec[ix] = (ShimHit){(uint32_t)j, ri, (uint8_t)l, m.u8[l], MPK.numGapQ[l], MPK.numGapR[l], MPK.finalPos[l]};
+						}
 					}
 				}
 			}
@@ -253,5 +266,6 @@ uint64_t refshim_run_bunches(const uint8_t *packed, const uint64_t *clump_off, c
 	free(Div);
 	cacheSz = savedCache;
 	*n_rescore = resc; *n_hits = hits; *n_instant = instant;
+	if (n_rec) *n_rec = nrec;
 	return calls;
 }
