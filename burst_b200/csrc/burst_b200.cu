@@ -697,12 +697,12 @@ struct SeedWArgs {
 	uint32_t m16[8];
 };
 // per-warp shared memory in words: filter | bucket heads | chain links (16 bit) | stretch records | budgets | 4 staging buffers (2 per half-warp) |
-// 4 mbarriers | 32 survivors waiting to leave.  hslots = buckets (power of two), ne = windows the table can hold = 16 * npmax * stride
+// 4 mbarriers | 32 survivors waiting to leave | 64 flagged words waiting for verification.  hslots = buckets (power of two), ne = windows the table can hold = 16 * npmax * stride
 __host__ __device__ __forceinline__ uint32_t seedw_warp_words(uint32_t lbits, uint32_t hslots, uint32_t npmax, uint32_t stride, uint32_t nch) {
-	return (1u << (lbits - 5)) + hslots + ((8 * npmax * stride + 3) & ~3u) + 64 * npmax + 16 + 4 * nch * 64 + 8 + 128;
+	return (1u << (lbits - 5)) + hslots + ((8 * npmax * stride + 3) & ~3u) + 64 * npmax + 16 + 4 * nch * 64 + 8 + 128 + 64;
 }
 
-template <int STRIDE, bool FULLW, int NCH>
+template <int STRIDE, bool FULLW, int NCH, int FB>   // FB: bits per window in the filter (1 or 2)
 __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 	extern __shared__ __align__(16) uint32_t smem[];
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -723,6 +723,9 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 	__syncthreads();
 	uint32_t cb = 0, phase = 0;                                            // staging buffer that holds the current item (warp-uniform); per-buffer mbarrier parity
 	uint4 *sbuf = (uint4 *)(stage0 + 4 * NCH * 64 + 8); uint32_t scount = 0;   // survivors collected by the warp; they leave 32 at a time through one atomicAdd
+	uint32_t *hq = stage0 + 4 * NCH * 64 + 8 + 128;                        // flagged words waiting for verification: owner lane << 8 | half-word window << 7 | word of the item
+	constexpr uint32_t HQ = 64;
+	const uint32_t stgw_s = (uint32_t)__cvta_generic_to_shared(stage0);   // staging of the whole warp (a helper lane reads the owner's buffer)
 	auto flush = [&]() {
 		uint32_t base = 0;
 		if (lane == 0) base = atomicAdd(&A.counters[C_SURV], scount);
@@ -792,7 +795,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 						for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
 							const QWin w = window_of(S, j);
 							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
-							atomicOr(&bits[hv >> SHB], (0x80000000u >> (hv & 31)) | (0x80000000u >> ((hv >> 5) & 31)));
+							atomicOr(&bits[hv >> SHB], (0x80000000u >> (hv & 31)) | (FB == 2 ? 0x80000000u >> ((hv >> 5) & 31) : 0u));
 							const uint32_t e = si * STRIDE + j;
 							nxt[e] = (uint16_t)atomicExch(&slots[(hv >> 10) & HSM], e + 1u);
 						}
@@ -851,14 +854,14 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 					__syncwarp();                                              // everyone is done with the other buffer (read in the previous step)
 					stage(N, ng, cb ^ 1);
 					bool emit = false; Surv ev; ev.task = 0; ev.lo = 0; ev.w_lane = 0; ev.scratch = 0;
+					uint32_t m8 = 0, m4 = 0;                                   // flagged words of this lane's item: word w -> bit NW-1-w
+					const bool amb_on = C.valid && (C.flags & ambsel) != 0;
 					if (C.valid) {
 						const uint32_t nchunks = (C.len + 31) >> 5;
-						const bool amb_on = (C.flags & ambsel) != 0;
 						if (cg == 0) { prev = prev2 = ambp = ambp2 = 0; }
 						iprev = prev; iprev2 = prev2;
 						const uint32_t sb = stg_s + cb * ITEM + l * 16;              // this lane's pieces: chunk c at sb + c * 256
 						mbar_wait(bar_s + 8 * cb, (phase >> cb) & 1u); phase ^= 1u << cb;
-						uint32_t m8 = 0, m4 = 0;
 						auto scan = [&](auto amb_c) {
 							constexpr bool AMB = decltype(amb_c)::value;
 							#pragma unroll
@@ -870,12 +873,14 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 									const uint32_t cu = ws[j];
 									const uint32_t h8 = seed_hash(cu, prev & HM);
 									const uint32_t f8 = lds32(bits_s + ((h8 >> SHB) << 2));
-									uint32_t t8 = __funnelshift_l(0u, f8, h8) & __funnelshift_l(0u, f8, h8 >> 5);    // both bits of the window -> bit 31
+									uint32_t t8 = __funnelshift_l(0u, f8, h8);                                    // the window's bit(s) -> bit 31
+									if (FB == 2) t8 &= __funnelshift_l(0u, f8, h8 >> 5);
 									uint32_t t4 = 0;
 									if (STRIDE == 4) {
 										const uint32_t h4 = seed_hash(__funnelshift_r(prev, cu, 16), __funnelshift_r(prev2, prev, 16) & HM);
 										const uint32_t f4 = lds32(bits_s + ((h4 >> SHB) << 2));
-										t4 = __funnelshift_l(0u, f4, h4) & __funnelshift_l(0u, f4, h4 >> 5);
+										t4 = __funnelshift_l(0u, f4, h4);
+										if (FB == 2) t4 &= __funnelshift_l(0u, f4, h4 >> 5);
 									}
 									if (AMB) {
 										const uint32_t ambc = amb_nibbles(cu, ADD);
@@ -893,16 +898,22 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 						const uint32_t nvalid = min((uint32_t)NW, nchunks * 4 - cg * NW);
 						const uint32_t vm = nvalid >= 32 ? FULL : (((1u << nvalid) - 1u) << (NW - nvalid));
 						m8 &= vm; m4 &= vm;
-						// ---- verify this lane's flagged words against the window table; seeds -> clusters ----
-						if (m8 | m4) {
-							// word wl of the item (wl = -1, -2: the words before it), from the staging buffer
+					}
+					// ---- verification of the flagged words against the window table; seeds -> clusters ----
+					// A flagged word is rare per lane (a false positive of the filter, or the one or two windows of a true alignment), so a lane
+					// that verified its own would keep the other 31 waiting.  Instead the flagged words of the whole warp go into a queue in
+					// shared memory and are verified 32 at a time, one per HELPER lane (the owner's words are in its staging buffer, readable by
+					// anyone); a match returns to its owner by shuffle.
+					if (__any_sync(FULL, (m8 | m4) != 0u)) {
+						const uint32_t sb = stg_s + cb * ITEM + l * 16;
+						if (amb_on && (m8 | m4)) {                                 // clumps holding IUPAC codes: the owner compares its windows through the scoring table itself (rare)
 							auto word_at = [&](int wl) -> uint32_t { return wl >= 0 ? lds32(sb + (uint32_t)(wl >> 2) * 256 + (uint32_t)(wl & 3) * 4) : (wl == -1 ? iprev : iprev2); };
 							auto verify = [&](uint32_t wi, int e) {
 								const int wl = (int)(wi - cg * NW);
 								const uint32_t cu = word_at(wl), pv = word_at(wl - 1), pv2 = e == 4 ? word_at(wl - 2) : 0u;
 								const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
 								const int x1 = (int)(wi * 8 + e);
-								if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the bunch, through the table
+								if (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD)) {
 									for (uint32_t si = 0; si < 16 * NPM; ++si) {
 										const uint4 rec = *(const uint4 *)(str + si * 4);
 										if (!rec.w) continue;
@@ -923,13 +934,69 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 									}
 								}
 							};
-							while (m8 | m4) {                                          // in column order: the half-word window of a word comes before its full-word window
+							while (m8 | m4) {
 								const uint32_t b = 31 - __clz(m8 | m4), bit = 1u << b, wi = cg * NW + (NW - 1 - b);
 								if (STRIDE == 4 && (m4 & bit)) verify(wi, 4);
 								if (m8 & bit) verify(wi, 8);
 								m8 &= ~bit; m4 &= ~bit;
 							}
 						}
+						while (__any_sync(FULL, (m8 | m4) != 0u)) {
+							// ---- enqueue: all flagged words if they fit, else the first two of every lane (the rest in the next pass) ----
+							const uint32_t mine = (uint32_t)(__popc(m8) + __popc(m4));
+							const uint32_t cnt = __reduce_add_sync(FULL, mine) <= HQ ? mine : min(mine, HQ / 32);
+							uint32_t off = cnt;
+							#pragma unroll
+							for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, off, d); if (lane >= (uint32_t)d) off += t; }
+							const uint32_t total = __shfl_sync(FULL, off, 31), maxcnt = __reduce_max_sync(FULL, cnt);
+							off -= cnt;
+							for (uint32_t j = 0; j < cnt; ++j) {
+								const uint32_t b = 31 - __clz(m8 | m4), bit = 1u << b;
+								const bool four = STRIDE == 4 && (m4 & bit);           // the half-word window of a word comes before its full-word window
+								hq[off + j] = (lane << 8) | (four ? 128u : 0u) | (uint32_t)(NW - 1 - b);
+								if (four) m4 &= ~bit; else m8 &= ~bit;
+							}
+							__syncwarp();
+							for (uint32_t base = 0; base < total; base += 32) {
+								// ---- helper: one queue entry per lane ----
+								const bool have = base + lane < total;
+								const uint32_t ent = have ? hq[base + lane] : 0u, owner = ent >> 8, wl = ent & 127u;
+								const bool four = (ent & 128u) != 0;
+								const uint32_t o_cg = __shfl_sync(FULL, cg, owner), o_ip = __shfl_sync(FULL, iprev, owner), o_ip2 = __shfl_sync(FULL, iprev2, owner);
+								uint32_t en = 0, rn = 0, ro = 0; int x1 = 0;
+								if (have) {
+									const uint32_t osb = stgw_s + (owner >> 4) * 2 * ITEM + cb * ITEM + (owner & 15) * 16;
+									auto word = [&](int w) -> uint32_t { return w >= 0 ? lds32(osb + (uint32_t)(w >> 2) * 256 + (uint32_t)(w & 3) * 4) : (w == -1 ? o_ip : o_ip2); };
+									const uint32_t cu = word((int)wl), pv = word((int)wl - 1), pv2 = four ? word((int)wl - 2) : 0u;
+									rn = four ? __funnelshift_r(pv, cu, 16) : cu; ro = (four ? __funnelshift_r(pv2, pv, 16) : pv) & HM;
+									x1 = (int)((o_cg * NW + wl) * 8 + (four ? 4 : 8));
+									en = slots[(seed_hash(rn, ro) >> 10) & HSM];
+								}
+								for (;;) {                                               // the next matching window of every entry (usually there is at most one)
+									bool found = false; uint32_t mq = 0; int mdg = 0;
+									while (en && !found) {
+										const uint32_t si = (en - 1) / STRIDE, j = (en - 1) % STRIDE;
+										const uint4 rec = *(const uint4 *)(str + si * 4);
+										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
+										const QWin w = window_of(S, j);
+										if (w.kn == rn && (w.ko & HM) == ro) { found = true; mq = si / NPM; mdg = x1 - (int)w.y1; }
+										en = nxt[en - 1];
+									}
+									if (!__any_sync(FULL, found)) break;
+									// ---- back to the owners: lane o's entries sit at queue positions off .. off + cnt - 1 ----
+									for (uint32_t j = 0; j < maxcnt; ++j) {
+										const int src = (int)(off + j) - (int)base;
+										const uint32_t sl = (uint32_t)min(max(src, 0), 31);
+										const uint32_t gf = __shfl_sync(FULL, (uint32_t)found, sl), gq = __shfl_sync(FULL, mq, sl);
+										const int gd = __shfl_sync(FULL, mdg, sl);
+										if (j < cnt && src >= 0 && src < 32 && gf) seed(gq, gd);
+									}
+								}
+							}
+							__syncwarp();
+						}
+					}
+					if (C.valid) {
 						// ---- end of the run: its seeds leave as survivors ----
 						if (lastg && sn) {
 							const uint32_t task0 = (C.r + A.W.run_base) * BG_RUN_MAX;
@@ -1494,7 +1561,8 @@ struct bg_ctx {
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
 	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
-	int seed_impl = 1, seed_nch = 8, seed_lbits = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
+	int seed_impl = 1, seed_nch = 8, seed_lbits = 0, seed_fb = 1;   // seed_fb: filter bits per window (1 or 2)
+	int _pad0 = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
@@ -1569,6 +1637,7 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	if (const char *e = getenv("BURST_B200_PIPE_SLICES")) { const int v = atoi(e); if (v >= 0 && v <= 64) c->pipe_slices = v; }
 	if (const char *e = getenv("BURST_B200_SEED_IMPL")) c->seed_impl = atoi(e) != 0;
 	if (const char *e = getenv("BURST_B200_SEED_NCH")) { const int v = atoi(e); if (v == 4 || v == 8) c->seed_nch = v; }
+	if (const char *e = getenv("BURST_B200_SEED_FB")) { const int v = atoi(e); if (v == 1 || v == 2) c->seed_fb = v; }
 	if (const char *e = getenv("BURST_B200_SEED_LBITS")) { const int v = atoi(e); if (v == 0 || (v >= 10 && v <= 20)) c->seed_lbits = v; }
 	bg_default_scoring(1, c->S);
 	*out = c;
@@ -1594,6 +1663,13 @@ extern "C" void bg_free(bg_ctx *c) {
 	delete c;
 }
 
+extern "C" void *bg_host_alloc(uint64_t bytes) {
+	void *p = nullptr;
+	if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocPortable) != cudaSuccess) { (void)cudaGetLastError(); fail(BG_ENOMEM, "cudaHostAlloc(%llu bytes) failed", (unsigned long long)bytes); return nullptr; }
+	return p;
+}
+extern "C" void bg_host_free(void *p) { if (p) cudaFreeHost(p); }
+
 extern "C" int bg_set_stream(bg_ctx *c, void *s) {
 	if (!c) return fail(BG_EINVAL, "null ctx");
 	if (c->own_stream && c->stream) { cudaStreamSynchronize(c->stream); cudaStreamDestroy(c->stream); }
@@ -1613,6 +1689,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 	if (what == BG_PARAM_SEED_GROUPS) { if (value != 0 && value != 2 && value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed groups %d must be 0, 2, 4 or 8", value); c->seed_groups = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_IMPL) { c->seed_impl = value != 0; return BG_OK; }
 	if (what == BG_PARAM_SEED_NCH) { if (value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed buffer chunks %d must be 4 or 8", value); c->seed_nch = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_FB) { if (value != 1 && value != 2) return fail(BG_EINVAL, "bg_set_param: filter bits per window %d must be 1 or 2", value); c->seed_fb = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_LBITS) { if (value && (value < 10 || value > 20)) return fail(BG_EINVAL, "bg_set_param: seed bitmap 2^%d bits out of range (0 = auto, 10..20)", value); c->seed_lbits = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_RATIO) { if (value && (value < 10 || value > 300)) return fail(BG_EINVAL, "bg_set_param: slice ratio %d must be 0 (auto) or 10..300", value); c->pipe_ratio = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_MIN_RUNS) { if (value < 1) return fail(BG_EINVAL, "bg_set_param: minimum runs per slice %d", value); c->pipe_min_runs = value; return BG_OK; }
@@ -1858,8 +1935,10 @@ static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const See
 	S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 	memcpy(S.m16, c->m16, sizeof(S.m16));
 	void (*kern)(SeedWArgs);
-	if (c->seed_nch == 4) kern = SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, 4> : k_seedw<8, false, 4>) : (SL.w == 16 ? k_seedw<4, true, 4> : k_seedw<4, false, 4>);
-	else kern = SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, 8> : k_seedw<8, false, 8>) : (SL.w == 16 ? k_seedw<4, true, 8> : k_seedw<4, false, 8>);
+	#define SEEDW_PICK(NCH, FB) (SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, NCH, FB> : k_seedw<8, false, NCH, FB>) : (SL.w == 16 ? k_seedw<4, true, NCH, FB> : k_seedw<4, false, NCH, FB>))
+	if (c->seed_nch == 4) kern = c->seed_fb == 2 ? SEEDW_PICK(4, 2) : SEEDW_PICK(4, 1);
+	else kern = c->seed_fb == 2 ? SEEDW_PICK(8, 2) : SEEDW_PICK(8, 1);
+	#undef SEEDW_PICK
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int bps = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SEEDW_WARPS * 32, smem));

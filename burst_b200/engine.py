@@ -19,7 +19,7 @@ MODE_MIN, MODE_ALL = 0, 1
 Q_PACKED4 = 1
 PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE, PARAM_PIPE_SLICES = 1, 2, 3, 4, 5
 PARAM_PIPE_MIN_RUNS, PARAM_PIPE_RATIO, PARAM_SEED_GROUPS = 6, 7, 8
-PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS = 9, 10, 11
+PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB = 9, 10, 11, 12
 
 
 class BgQueries(C.Structure):
@@ -41,7 +41,8 @@ class BgStats(C.Structure):
 EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scoring", "bg_default_scoring",
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
-           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into"]
+           "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into",
+           "bg_host_alloc", "bg_host_free"]
 
 
 def load_library(path=None):

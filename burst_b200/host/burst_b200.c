@@ -22,6 +22,9 @@
 #include <string.h>
 #include <inttypes.h>
 #include <time.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include "burst_b200.h"
 
 #define VER "v1.0-b200"
@@ -39,7 +42,7 @@ static long REBASE_AMT = 500, DB_QLEN = 500; static int REBASE = 0, ACX_N = 12; 
 static float TAXLEVELS_STRICT[] = {.65f, .75f, .78f, .82f, .86f, .94f, .98f, .995f},
              TAXLEVELS_LENIENT[] = {.55f, .70f, .75f, .80f, .84f, .93f, .97f, .985f},   /* burst.c:264-266 */
              *TAXLEVELS = TAXLEVELS_LENIENT;
-static int QUIET = 0, GPU_DEVICE = 0, THREADS = 1;
+static int QUIET = 0, GPU_DEVICE = 0, NGPU = 1, THREADS = 1;
 
 static uint8_t CHAR2NUM[256];
 static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};   /* burst.c:168 */
@@ -645,135 +648,256 @@ static void make_db(const char *ref_FN, const char *edx_FN, const char *acx_FN, 
 	}
 }
 
-typedef struct { bg_task *t; uint64_t n, cap; } TaskVec;
-static void task_push(TaskVec *T, uint32_t q, uint32_t c) {
-	if (T->n == T->cap) { T->cap = T->cap ? T->cap * 2 : (1 << 16); T->t = xrealloc(T->t, T->cap * sizeof(bg_task)); }
-	T->t[T->n].query = q; T->t[T->n++].clump = c;
+/* =============================================================================================
+ * Accelerated search (burst.c:4018-4316).  Bunches of QBUNCH sorted queries share one candidate list
+ * (burst.c:4085-4133); a bunch visits its candidates by descending k-mer count, then the always-visited
+ * BadList, and inside a clump its queries in order (burst.c:4136-4168).  Here the visits of many bunches
+ * form one BATCH: the (bunch, clump) visits become bg_run records in exactly that order -- so hits sorted
+ * by run index are in the reference's -t 1 discovery order -- the reads of the batch are nibble-packed
+ * into page-locked memory, and one bg_align_runs_into() call does the rest on the GPU.
+ *   * candidate generation runs on all host threads (-t), one bunch per task, into per-thread arenas that
+ *     are stitched together in bunch order;
+ *   * batches are dealt to the GPUs (--gpus N, one engine context each, database replicated) in waves:
+ *     while the GPUs work on wave w the host threads generate wave w+1; every GPU carries its own per-read
+ *     running minima (ShrBins[].ed), merged by MIN at the end exactly like the reference's thread pods
+ *     (burst.c:4497-4517) -- a read's forward and reverse-complement strands may sit in different batches;
+ *   * the per-query skip (burst.c:4163-4168: count <= len - (ed+1) N) is kept exactly: a visit is cut into
+ *     the maximal runs of consecutive queries that pass it.
+ * ============================================================================================= */
+typedef struct { bg_run *r; uint64_t n, cap; } RunVec;
+static void run_push(RunVec *V, uint32_t clump, uint32_t q0, uint32_t nq) {
+	if (V->n == V->cap) { V->cap = V->cap ? V->cap * 2 : (1 << 14); V->r = xrealloc(V->r, V->cap * sizeof(bg_run)); }
+	V->r[V->n].clump = clump; V->r[V->n].query0 = q0; V->r[V->n++].nq = nq;
+}
+typedef struct {                       /* per host thread */
+	uint16_t *Hash; uint32_t *Cache; Split *Cand; uint64_t *W, wcap; RunVec runs;
+} GenScratch;
+typedef struct { uint32_t tid; uint64_t off, n; } BunchRuns;   /* where a bunch's runs sit: thread arena, offset, count */
+typedef struct {
+	uint64_t qa, qb, nbunch;           /* UniBins [qa, qb), bunches */
+	BunchRuns *br;                     /* per bunch */
+	bg_run *runs; uint64_t nruns, runcap;
+	uint8_t *codes; uint64_t *off; uint16_t *bud; uint32_t *slot; uint64_t cap_codes, cap_q;   /* page-locked */
+	bg_hit *hits; uint64_t hitcap;
+} Batch;
+
+/* candidates of one bunch [z, bound) -> runs appended to S->runs; query numbers are relative to qa */
+static void gen_bunch(const Queries *Q, const Acx *A, uint32_t numRclumps, GenScratch *S, uint64_t z, uint64_t bound, uint64_t qa) {
+	const uint32_t N = (uint32_t)SCOUR_N;
+	uint64_t wix = 0; uint64_t *W = S->W;
+	uint32_t min_mmatch = UINT32_MAX, mm[16];
+	for (uint64_t j = z; j < bound; ++j) {                                /* burst.c:4085-4114 */
+		const UniBin *u = Q->UniBins + j; const ShrBin *sb = Q->ShrBins + u->six;
+		uint32_t len = sb->len, err = sb->ed, kload = err * N + N, mmatch = kload < len ? len - kload : 0;
+		uint32_t heur = DO_HEUR ? (len >> 4) + 1u : 0;
+		if (mmatch < heur) mmatch = heur;
+		if (mmatch < min_mmatch) min_mmatch = mmatch;
+		mm[j - z] = kload < len ? len - kload : 1;                        /* the per-query skip threshold, burst.c:4163-4164 */
+		const char *s = u->seq;
+		uint64_t need = wix + (uint64_t)len * (j >= Q->QBins[0] ? 1 : 1024) + 16;
+		if (need > S->wcap) { while (S->wcap < need) S->wcap *= 2; W = S->W = xrealloc(S->W, S->wcap * 8); }
+		if (j >= Q->QBins[0]) {                                           /* unambiguous: rolling 2-bit words */
+			uint32_t mask = N == 16 ? 0xFFFFFFFFu : (1u << (2 * N)) - 1, w = 0;
+			for (uint32_t k = 0; k < len; ++k) {
+				w = (w << 2 | (uint32_t)(s[k] - 1)) & mask;
+				if (k + 1 >= N) W[wix++] = (uint64_t)w << 32 | (uint32_t)(j - z);
+			}
+		} else for (uint32_t k = 0; k + N <= len; ++k) {                  /* ambiguous: every variant of every window */
+			if (Z) { uint32_t p = k, e = k + N; for (; p < e; ++p) if (s[p] == 5) break; if (p < e) { k = p; continue; } }
+			uint64_t variants = 1;
+			for (uint32_t p = k; p < k + N; ++p) variants *= AMBIG_N[(uint8_t)s[p] & 15];
+			if (wix + variants + 16 > S->wcap) { while (S->wcap < wix + variants + 16) S->wcap *= 2; W = S->W = xrealloc(S->W, S->wcap * 8); }
+			ambig_words(W, &wix, s + k, (uint32_t)(j - z), 0, 0);
+		}
+	}
+	qsort(W, wix, 8, cmp_u64);                                            /* burst.c:4118 */
+	/* burst.c:3238-3282: each distinct word adds its largest per-query multiplicity to every clump it lists */
+	uint16_t *Hash = S->Hash; uint32_t *Cache = S->Cache, cix = 0;
+	for (uint64_t i = 0; i < wix;) {
+		uint32_t v = (uint32_t)(W[i] >> 32), mx = 0; uint64_t e = i;
+		while (e < wix && (uint32_t)(W[e] >> 32) == v) { uint64_t r = e; while (r < wix && W[r] == W[e]) ++r; if (r - e > mx) mx = (uint32_t)(r - e); e = r; }
+		const uint8_t *p = A->post + A->off[v], *end = A->post + A->off[(uint64_t)v + 1];
+#define BUMP(px) do { uint32_t px_ = (px); if (px_ < numRclumps) { if (!Hash[px_]) Cache[cix++] = px_; uint32_t nv_ = mx + Hash[px_]; Hash[px_] = (uint16_t)(nv_ > 65535 ? 65535 : nv_); } } while (0)
+		if (A->big) for (; p < end; p += 3) { uint32_t px; memcpy(&px, p, 4); BUMP(px & 0xFFFFFF); }
+		else for (; p < end; p += 5) {
+			uint64_t PX; memcpy(&PX, p, 8);
+			BUMP((uint32_t)(PX & 0xFFFFF));
+			if (p + 3 >= end) break;
+			BUMP((uint32_t)((PX >> 20) & 0xFFFFF));
+		}
+		i = e;
+	}
+	Split *Cand = S->Cand; uint32_t nref = 0;
+	for (uint32_t i = 0; i < cix; ++i) { uint16_t *h = Hash + Cache[i]; if (*h > min_mmatch) Cand[nref++] = (Split){Cache[i], *h}; *h = 0; }
+	if (nref > 24) qsort(Cand, nref, sizeof(*Cand), cmp_refcount);        /* burst.c:4038-4046 */
+	else for (uint32_t i = 1, j; i < nref; ++i) {
+		Split key = Cand[i];
+		for (j = i; j && Cand[j - 1].i < key.i; --j);
+		memmove(Cand + j + 1, Cand + j, sizeof(*Cand) * (i - j)); Cand[j] = key;
+	}
+	const uint32_t nb = (uint32_t)(bound - z), q0 = (uint32_t)(z - qa);
+	for (uint32_t i = 0; i < nref; ++i) {                                 /* burst.c:4137-4168 */
+		uint32_t a = 0;
+		while (a < nb) {
+			while (a < nb && !(Cand[i].i > mm[a])) ++a;
+			uint32_t b = a;
+			while (b < nb && Cand[i].i > mm[b]) ++b;
+			if (b > a) run_push(&S->runs, Cand[i].v, q0 + a, b - a);
+			a = b;
+		}
+	}
+	if (!Q->skipAmbig) for (uint32_t i = 0; i < A->nbad; ++i) if (A->bad[i] < numRclumps) run_push(&S->runs, A->bad[i], q0, nb);
 }
 
-/* Accelerated search (burst.c:4018-4316).  Bunches of QBUNCH sorted queries share one candidate
- * list; tasks are emitted in the reference's loop order (bunch; candidates by descending k-mer
- * count, then the always-visited BadList; queries of the bunch), so hits sorted by task index are
- * in discovery order.  The per-query skip uses the starting budget (the reference's running Emac
- * is never larger), which can only add visits whose lanes are later discarded as non-minimal. */
-static void accel_search(bg_ctx *ctx, Queries *Q, Refs *R, Acx *A, PodList *Pods, int mode, int threads) {
+static void batch_room(Batch *B, uint64_t nq, uint64_t ncodes, uint64_t nruns) {
+	if (nq + 1 > B->cap_q) {
+		bg_host_free(B->off); bg_host_free(B->bud); bg_host_free(B->slot);
+		B->cap_q = nq + nq / 8 + 64;
+		B->off = bg_host_alloc(B->cap_q * 8); B->bud = bg_host_alloc(B->cap_q * 2); B->slot = bg_host_alloc(B->cap_q * 4);
+	}
+	if (ncodes / 2 + 64 > B->cap_codes) { bg_host_free(B->codes); B->cap_codes = ncodes / 2 + ncodes / 16 + 256; B->codes = bg_host_alloc(B->cap_codes); }
+	if (nruns + 1 > B->runcap) { bg_host_free(B->runs); B->runcap = nruns + nruns / 8 + 64; B->runs = bg_host_alloc(B->runcap * sizeof(bg_run)); }
+	if (!B->off || !B->bud || !B->slot || !B->codes || !B->runs) { fputs("OOM: page-locked batch buffers\n", stderr); exit(3); }
+}
+
+/* queries of the batch -> nibble-packed codes (two bases per byte, even base low: BG_Q_PACKED4), offsets in bases */
+static void batch_pack_queries(const Queries *Q, Batch *B) {
+	uint64_t nq = B->qb - B->qa, tot = 0;
+	for (uint64_t j = 0; j < nq; ++j) { B->off[j] = tot; tot += Q->ShrBins[Q->UniBins[B->qa + j].six].len; }
+	B->off[nq] = tot;
+	memset(B->codes, 0, tot / 2 + 16);
+	#pragma omp parallel for schedule(static, 4096) num_threads(THREADS)
+	for (uint64_t j = 0; j < nq; ++j) {
+		const UniBin *u = Q->UniBins + B->qa + j; const ShrBin *sb = Q->ShrBins + u->six;
+		B->bud[j] = sb->ed; B->slot[j] = (uint32_t)u->six;
+		uint64_t o = B->off[j]; const char *s = u->seq; uint32_t len = sb->len, k = 0;
+		/* the first and last nibble of a query may share a byte with its neighbours (handled by another thread): atomic OR there */
+		if ((o & 1) && len) { __atomic_fetch_or(&B->codes[o >> 1], (uint8_t)((s[0] & 15) << 4), __ATOMIC_RELAXED); k = 1; }
+		for (; k + 1 < len; k += 2) B->codes[(o + k) >> 1] = (uint8_t)((s[k] & 15) | ((s[k + 1] & 15) << 4));
+		if (k < len) __atomic_fetch_or(&B->codes[(o + k) >> 1], (uint8_t)(s[k] & 15), __ATOMIC_RELAXED);
+	}
+}
+
+static void accel_search(bg_ctx **ctxs, int ngpu, Queries *Q, Refs *R, Acx *A, PodList *Pods, int mode, int threads) {
 	uint64_t nAcc = Q->QBins[1], newUniqQ = Q->newUniqQ;
 	if (!nAcc) return;
 	uint64_t QBUNCH = newUniqQ / ((uint64_t)threads * 128);
 	if (QBUNCH > 16) QBUNCH = 16;
 	if (!QBUNCH) QBUNCH = 1;
 	printf("Setting QBUNCH to %" PRIu64 "\nUsing ACCELERATOR to align %" PRIu64 " unique queries...\n", QBUNCH, nAcc);
-	uint32_t N = (uint32_t)SCOUR_N, numRclumps = R->numRclumps;
-	uint16_t *Hash = xcalloc(numRclumps, sizeof(*Hash));
-	uint32_t *Cache = xmalloc(((uint64_t)numRclumps + 1) * 4);
-	Split *Cand = xmalloc(((uint64_t)numRclumps + 1) * sizeof(*Cand));
-	uint64_t wcap = 1 << 16, *W = xmalloc(wcap * 8);
-	uint16_t *best = xmalloc(Q->numUniqQ * sizeof(*best));
-	for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[i] = 0xFFFF;
-	PodList *SPods = xcalloc(newUniqQ, sizeof(*SPods));                 /* per strand, folded below (4299-4312) */
-	TaskVec T = {0};
-	const uint64_t TASK_FLUSH = 1ull << 24;
-	uint64_t batch_q0 = 0;                                              /* first query (UniBins index) of the open batch */
-
-	for (uint64_t z = 0;; z += QBUNCH) {                              /* ends through `last` below */
-		int last = z >= nAcc;
-		if (last || T.n >= TASK_FLUSH) {                                /* ---- run the open batch [batch_q0, z) ---- */
-			uint64_t qa = batch_q0, qb = last ? nAcc : z, nq = qb - qa;
-			if (nq && T.n) {
-				uint64_t *off = xmalloc((nq + 1) * 8), tot = 0;
-				uint16_t *bud = xmalloc(nq * 2); uint32_t *slot = xmalloc(nq * 4);
-				for (uint64_t j = 0; j < nq; ++j) { off[j] = tot; tot += Q->ShrBins[Q->UniBins[qa + j].six].len; }
-				off[nq] = tot;
-				uint8_t *codes = xmalloc(tot + 16);
-				for (uint64_t j = 0; j < nq; ++j) {
-					UniBin *u = Q->UniBins + qa + j; ShrBin *sb = Q->ShrBins + u->six;
-					memcpy(codes + off[j], u->seq, sb->len); bud[j] = sb->ed; slot[j] = (uint32_t)u->six;
-				}
-				bg_queries bq = {codes, off, bud, slot, (uint32_t)nq, (uint32_t)Q->numUniqQ};
-				bg_hit *hits = NULL; uint64_t nh = 0;
-				int rc = bg_align_batch(ctx, &bq, T.t, T.n, mode, best, &hits, &nh);
-				if (rc) die_gpu("bg_align_batch", rc);
-				for (uint64_t h = 0; h < nh; ++h) {
-					bg_task t = T.t[hits[h].task];
-					UniBin *u = Q->UniBins + qa + t.query; ShrBin *sb = Q->ShrBins + u->six;
-					uint32_t refIx = t.clump * VECSZ + hits[h].lane;
-					if (refIx >= R->totR) continue;                         /* burst.c:4229 */
-					Pod p = {identity(hits[h].ed, sb->len, hits[h].gap_q), refIx, hits[h].final_pos, hits[h].gap_r, hits[h].gap_q, hits[h].ed, u->rc};
-					pod_push(SPods + u->six + (u->rc ? Q->numUniqQ : 0), p);
-				}
-				bg_free_hits(hits); free(off); free(bud); free(slot); free(codes);
-			}
-			T.n = 0; batch_q0 = z;
-			if (!QUIET) printf("\rSearch Progress: [%3.2f%%]", 100.0 * (double)MIN(z, nAcc) / (double)nAcc);
-			if (last) break;
-		}
-		uint64_t bound = MIN(z + QBUNCH, nAcc), wix = 0;
-		uint32_t min_mmatch = UINT32_MAX, mm[16];
-		for (uint64_t j = z; j < bound; ++j) {                          /* burst.c:4085-4114 */
-			UniBin *u = Q->UniBins + j; ShrBin *sb = Q->ShrBins + u->six;
-			uint32_t len = sb->len, err = sb->ed, kload = err * N + N, mmatch = kload < len ? len - kload : 0;
-			uint32_t heur = DO_HEUR ? (len >> 4) + 1u : 0;
-			if (mmatch < heur) mmatch = heur;
-			if (mmatch < min_mmatch) min_mmatch = mmatch;
-			mm[j - z] = kload < len ? len - kload : 1;                    /* the per-query skip threshold, burst.c:4163-4164 */
-			const char *s = u->seq;
-			uint64_t need = wix + (uint64_t)len * (j >= Q->QBins[0] ? 1 : 1024) + 16;
-			if (need > wcap) { while (wcap < need) wcap *= 2; W = xrealloc(W, wcap * 8); }
-			if (j >= Q->QBins[0]) {                                       /* unambiguous: rolling 2-bit words */
-				uint32_t mask = N == 16 ? 0xFFFFFFFFu : (1u << (2 * N)) - 1, w = 0;
-				for (uint32_t k = 0; k < len; ++k) {
-					w = (w << 2 | (uint32_t)(s[k] - 1)) & mask;
-					if (k + 1 >= N) W[wix++] = (uint64_t)w << 32 | (uint32_t)(j - z);
-				}
-			} else for (uint32_t k = 0; k + N <= len; ++k) {              /* ambiguous: every variant of every window */
-				if (Z) { uint32_t p = k, e = k + N; for (; p < e; ++p) if (s[p] == 5) break; if (p < e) { k = p; continue; } }
-				uint64_t variants = 1;
-				for (uint32_t p = k; p < k + N; ++p) variants *= AMBIG_N[(uint8_t)s[p] & 15];
-				if (wix + variants + 16 > wcap) { while (wcap < wix + variants + 16) wcap *= 2; W = xrealloc(W, wcap * 8); }
-				ambig_words(W, &wix, s + k, (uint32_t)(j - z), 0, 0);
-			}
-		}
-		qsort(W, wix, 8, cmp_u64);                                      /* burst.c:4118 */
-		/* burst.c:3238-3282: each distinct word adds its largest per-query multiplicity to every clump it lists */
-		uint32_t cix = 0;
-		for (uint64_t i = 0; i < wix;) {
-			uint32_t v = (uint32_t)(W[i] >> 32), mx = 0; uint64_t e = i;
-			while (e < wix && (uint32_t)(W[e] >> 32) == v) { uint64_t r = e; while (r < wix && W[r] == W[e]) ++r; if (r - e > mx) mx = (uint32_t)(r - e); e = r; }
-			const uint8_t *p = A->post + A->off[v], *end = A->post + A->off[(uint64_t)v + 1];
-#define BUMP(px) do { uint32_t px_ = (px); if (px_ < numRclumps) { if (!Hash[px_]) Cache[cix++] = px_; uint32_t nv_ = mx + Hash[px_]; Hash[px_] = (uint16_t)(nv_ > 65535 ? 65535 : nv_); } } while (0)
-			if (A->big) for (; p < end; p += 3) { uint32_t px; memcpy(&px, p, 4); BUMP(px & 0xFFFFFF); }
-			else for (; p < end; p += 5) {
-				uint64_t PX; memcpy(&PX, p, 8);
-				BUMP((uint32_t)(PX & 0xFFFFF));
-				if (p + 3 >= end) break;
-				BUMP((uint32_t)((PX >> 20) & 0xFFFFF));
-			}
-			i = e;
-		}
-		uint32_t nref = 0;
-		for (uint32_t i = 0; i < cix; ++i) { uint16_t *h = Hash + Cache[i]; if (*h > min_mmatch) Cand[nref++] = (Split){Cache[i], *h}; *h = 0; }
-		if (nref > 24) qsort(Cand, nref, sizeof(*Cand), cmp_refcount);  /* burst.c:4038-4046 */
-		else for (uint32_t i = 1, j; i < nref; ++i) {
-			Split key = Cand[i];
-			for (j = i; j && Cand[j - 1].i < key.i; --j);
-			memmove(Cand + j + 1, Cand + j, sizeof(*Cand) * (i - j)); Cand[j] = key;
-		}
-		for (uint32_t i = 0; i < nref; ++i) for (uint64_t j = z; j < bound; ++j)       /* burst.c:4137-4168 */
-			if (Cand[i].i > mm[j - z]) task_push(&T, (uint32_t)(j - batch_q0), Cand[i].v);
-		if (!Q->skipAmbig) for (uint32_t i = 0; i < A->nbad; ++i) for (uint64_t j = z; j < bound; ++j)
-			if (A->bad[i] < numRclumps) task_push(&T, (uint32_t)(j - batch_q0), A->bad[i]);
+	const uint32_t numRclumps = R->numRclumps;
+	const uint64_t nbunch = (nAcc + QBUNCH - 1) / QBUNCH;
+	/* bunches per batch: enough batches to keep every GPU busy and the generation a wave ahead, at most ~1 M queries each */
+	uint64_t bpb = (nbunch + (uint64_t)ngpu * 4 - 1) / ((uint64_t)ngpu * 4);
+	if (bpb < 2048) bpb = 2048;
+	if (bpb > 65536) bpb = 65536;
+	const uint64_t nbatch = (nbunch + bpb - 1) / bpb;
+	int nthr = threads < 1 ? 1 : threads;
+#ifdef _OPENMP
+	if (nthr < ngpu) nthr = ngpu;
+#else
+	nthr = 1;
+#endif
+	GenScratch *GS = xcalloc((size_t)nthr, sizeof(*GS));
+	for (int t = 0; t < nthr; ++t) {
+		GS[t].Hash = xcalloc(numRclumps, sizeof(uint16_t)); GS[t].Cache = xmalloc(((uint64_t)numRclumps + 1) * 4);
+		GS[t].Cand = xmalloc(((uint64_t)numRclumps + 1) * sizeof(Split)); GS[t].wcap = 1 << 16; GS[t].W = xmalloc(GS[t].wcap * 8);
 	}
+	uint16_t **best = xmalloc((size_t)ngpu * sizeof(*best));
+	for (int g = 0; g < ngpu; ++g) { best[g] = xmalloc(Q->numUniqQ * sizeof(uint16_t)); for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[g][i] = 0xFFFF; }
+	PodList *SPods = xcalloc(newUniqQ, sizeof(*SPods));                 /* per strand, folded below (4299-4312) */
+	Batch *BT = xcalloc((size_t)ngpu * 2, sizeof(*BT));                  /* two waves of ngpu batches */
+	int failed = 0, fail_rc = 0;
+	double t_gen = 0, t_gpu = 0;
+
+	const uint64_t nwaves = (nbatch + (uint64_t)ngpu - 1) / (uint64_t)ngpu;
+	for (uint64_t wave = 0; wave <= nwaves; ++wave) {
+		/* this pass: the GPUs align wave-1 (if any) while the whole team generates the candidates of `wave` (if any) */
+		const uint64_t wb0 = MIN(nbunch, wave * (uint64_t)ngpu * bpb), wb1 = MIN(nbunch, (wave + 1) * (uint64_t)ngpu * bpb);   /* bunches of this wave */
+		Batch *Gen = BT + (wave & 1) * (uint64_t)ngpu, *Run = BT + ((wave + 1) & 1) * (uint64_t)ngpu;
+		for (int g = 0; g < ngpu; ++g) {
+			Batch *B = Gen + g; uint64_t b0 = MIN(nbunch, wb0 + (uint64_t)g * bpb), b1 = MIN(nbunch, b0 + bpb);
+			B->nbunch = b1 - b0; B->qa = b0 * QBUNCH; B->qb = MIN(nAcc, b1 * QBUNCH);
+			if (B->nbunch) B->br = xrealloc(B->br, B->nbunch * sizeof(BunchRuns));
+		}
+		for (int t = 0; t < nthr; ++t) GS[t].runs.n = 0;
+		double t0 = now();
+		#pragma omp parallel num_threads(nthr)
+		{
+			if (wave > 0) {
+				#pragma omp for schedule(static, 1) nowait
+				for (int g = 0; g < ngpu; ++g) {
+					Batch *B = Run + g;
+					if (!B->nbunch || failed) continue;
+					uint64_t nq = B->qb - B->qa;
+					bg_queries bq = {B->codes, B->off, B->bud, B->slot, (uint32_t)nq, (uint32_t)Q->numUniqQ, BG_Q_PACKED4};
+					uint64_t nh = 0; int rc;
+					if (!B->hits) { B->hitcap = nq * 2 + 1024; B->hits = bg_host_alloc(B->hitcap * sizeof(bg_hit)); }
+					rc = B->nruns ? bg_align_runs_into(ctxs[g], &bq, B->runs, B->nruns, mode, best[g], B->hits, B->hitcap, &nh) : BG_OK;
+					if (rc == BG_EOVERFLOW && nh > B->hitcap) {            /* more hits than room: grow and redo the batch */
+						bg_host_free(B->hits); B->hitcap = nh + nh / 8; B->hits = bg_host_alloc(B->hitcap * sizeof(bg_hit));
+						rc = bg_align_runs_into(ctxs[g], &bq, B->runs, B->nruns, mode, best[g], B->hits, B->hitcap, &nh);
+					}
+					if (rc) {
+						#pragma omp critical
+						{ failed = 1; fail_rc = rc; fprintf(stderr, "ERROR: GPU engine failed in bg_align_runs_into: %s\n", bg_last_error()); }
+						continue;
+					}
+					for (uint64_t h = 0; h < nh; ++h) {
+						const bg_run *r = B->runs + (B->hits[h].task >> 4);
+						const UniBin *u = Q->UniBins + B->qa + r->query0 + (B->hits[h].task & 15); const ShrBin *sb = Q->ShrBins + u->six;
+						uint32_t refIx = r->clump * VECSZ + B->hits[h].lane;
+						if (refIx >= R->totR) continue;                     /* burst.c:4229 */
+						Pod p = {identity(B->hits[h].ed, sb->len, B->hits[h].gap_q), refIx, B->hits[h].final_pos, B->hits[h].gap_r, B->hits[h].gap_q, B->hits[h].ed, u->rc};
+						pod_push(SPods + u->six + (u->rc ? Q->numUniqQ : 0), p);
+					}
+				}
+			}
+			/* no barrier up to here: the threads not driving a GPU start on the bunches at once, the others join when their call returns */
+			#pragma omp for schedule(dynamic, 16)
+			for (uint64_t b = wb0; b < wb1; ++b) {
+				int tid = 0;
+#ifdef _OPENMP
+				tid = omp_get_thread_num();
+#endif
+				GenScratch *S = GS + tid; Batch *B = Gen + (b - wb0) / bpb; uint64_t before = S->runs.n;
+				gen_bunch(Q, A, numRclumps, S, b * QBUNCH, MIN(nAcc, (b + 1) * QBUNCH), B->qa);
+				B->br[(b - wb0) % bpb] = (BunchRuns){(uint32_t)tid, before, S->runs.n - before};
+			}
+		}
+		if (failed) exit(fail_rc == BG_ENOMEM ? 3 : 4);
+		double t1 = now();
+		/* stitch the wave's runs together in bunch order and pack its reads (page-locked buffers) */
+		for (int g = 0; g < ngpu; ++g) {
+			Batch *B = Gen + g;
+			if (!B->nbunch) continue;
+			uint64_t tot = 0, nc = 0, o = 0;
+			for (uint64_t b = 0; b < B->nbunch; ++b) tot += B->br[b].n;
+			for (uint64_t j = B->qa; j < B->qb; ++j) nc += Q->ShrBins[Q->UniBins[j].six].len;
+			batch_room(B, B->qb - B->qa, nc, tot);
+			for (uint64_t b = 0; b < B->nbunch; ++b) { memcpy(B->runs + o, GS[B->br[b].tid].runs.r + B->br[b].off, B->br[b].n * sizeof(bg_run)); o += B->br[b].n; }
+			B->nruns = tot;
+			batch_pack_queries(Q, B);
+		}
+		t_gen += now() - t1; t_gpu += t1 - t0;
+		if (!QUIET) printf("\rSearch Progress: [%3.2f%%]", 100.0 * (double)MIN(wave, nwaves) / (double)(nwaves ? nwaves : 1));
+	}
+	printf(" --> [Accel] %" PRIu64 " batches on %d GPU(s): align + candidate generation %.3f s, stitch + pack %.3f s\n", nbatch, ngpu, t_gpu, t_gen);
 	if (!QUIET) printf("\rSearch Progress: [100.00%%]\n");
-	/* fold strands: forward list, then reverse-complement list (burst.c:4299-4312); lists are push-front */
+	/* per-read minima over all GPUs (burst.c:4497-4517), then fold strands: forward list, then reverse-complement list (4299-4312) */
+	for (int g = 1; g < ngpu; ++g) for (uint64_t i = 0; i < Q->numUniqQ; ++i) if (best[g][i] < best[0][i]) best[0][i] = best[g][i];
 	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
 		PodList *F = SPods + i, *Rc = Q->rc ? SPods + Q->numUniqQ + i : NULL;
 		/* Pods[] is kept in discovery order and read backwards; "fwd list then rc list" read backwards is
 		 * rc pods (discovery order) followed by fwd pods (discovery order) */
-		if (Rc) for (uint32_t k = 0; k < Rc->n; ++k) if (mode != BG_MODE_MIN || Rc->p[k].mismatches <= best[i]) pod_push(Pods + i, Rc->p[k]);
-		for (uint32_t k = 0; k < F->n; ++k) if (mode != BG_MODE_MIN || F->p[k].mismatches <= best[i]) pod_push(Pods + i, F->p[k]);
+		if (Rc) for (uint32_t k = 0; k < Rc->n; ++k) if (mode != BG_MODE_MIN || Rc->p[k].mismatches <= best[0][i]) pod_push(Pods + i, Rc->p[k]);
+		for (uint32_t k = 0; k < F->n; ++k) if (mode != BG_MODE_MIN || F->p[k].mismatches <= best[0][i]) pod_push(Pods + i, F->p[k]);
 		free(F->p); if (Rc) free(Rc->p);
 	}
-	free(SPods); free(best); free(Hash); free(Cache); free(Cand); free(W); free(T.t);
+	for (int t = 0; t < nthr; ++t) { free(GS[t].Hash); free(GS[t].Cache); free(GS[t].Cand); free(GS[t].W); free(GS[t].runs.r); }
+	for (int b = 0; b < ngpu * 2; ++b) { Batch *B = BT + b; free(B->br); bg_host_free(B->runs); bg_host_free(B->codes); bg_host_free(B->off); bg_host_free(B->bud); bg_host_free(B->slot); bg_host_free(B->hits); }
+	for (int g = 0; g < ngpu; ++g) free(best[g]);
+	free(best); free(GS); free(BT); free(SPods);
 }
 
 /* =============================================================================================
@@ -1045,8 +1169,8 @@ static void usage(void) {
 	puts("--forwardreverse (-fr), --whitespace (-w), --nwildcard (-y), --npenalize (-n)");
 	puts("--taxonomy (-b) <name>, --taxacut (-bc) <num>, --taxa_ncbi (-bn), --taxasuppress (-bs) [STRICT]");
 	puts("--mode (-m) BEST | ALLPATHS | CAPITALIST [default] | FORAGE");
-	puts("--id (-i) <decimal> [0.97], --threads (-t) <int> (accepted, unused), --skipambig (-sa), --heuristic (-hr)");
-	puts("--gpu <int>: CUDA device to use [0];  --noprogress");
+	puts("--id (-i) <decimal> [0.97], --threads (-t) <int> (host threads for candidate generation), --skipambig (-sa), --heuristic (-hr)");
+	puts("--gpu <int>: first CUDA device to use [0];  --gpus <int>: number of devices (queries are sharded, DB replicated) [1];  --noprogress");
 	puts("--makedb (-d) [DNA|RNA|QUICK] [qLen]: write -o <edx> (and -a <acx>, word length --acx-n 12|15 [12]) from -r <fasta>; -s [len] shears");
 	exit(1);
 }
@@ -1120,11 +1244,12 @@ int main(int argc, char *argv[]) {
 			if (THRES < 0.01f) THRES = 0.01f;
 			printf(" --> Setting identity threshold to %f\n", THRES);
 		}
-		else if (OPT("--threads", "-t")) { NEEDARG("--threads requires integer argument") THREADS = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1; printf(" --> Setting threads to %d (bunch size only; the DP runs on the GPU)\n", THREADS); }
+		else if (OPT("--threads", "-t")) { NEEDARG("--threads requires integer argument") THREADS = atoi(argv[i]) > 0 ? atoi(argv[i]) : 1; printf(" --> Setting threads to %d (bunch size and host-side candidate generation; the DP runs on the GPU)\n", THREADS); }
 		else if (OPT("--shear", "-s")) { REBASE = 1; if (i + 1 != argc && argv[i + 1][0] != '-') REBASE_AMT = atol(argv[++i]); if (!REBASE_AMT) REBASE = 0; }
 		else if (OPT("--heuristic", "-hr")) { DO_HEUR = 1; printf(" --> WARNING: Heuristic mode set; optimality not guaranteed at low ids\n"); }
 		else if (!strcmp(argv[i], "--noprogress")) { QUIET = 1; printf(" --> Surpressing progress indicator\n"); }
 		else if (!strcmp(argv[i], "--gpu")) { NEEDARG("--gpu requires integer argument") GPU_DEVICE = atoi(argv[i]); }
+		else if (!strcmp(argv[i], "--gpus")) { NEEDARG("--gpus requires integer argument") NGPU = atoi(argv[i]); if (NGPU < 1 || NGPU > 64) { fputs("ERROR: --gpus must be 1..64\n", stderr); exit(1); } }
 		else if (OPT("--fingerprint", "-f") || OPT("--prepass", "-p") || OPT("--unique", "-u")) { fprintf(stderr, "ERROR: %s selects a heuristic/legacy path that this build does not provide (see DESIGN.md, out of scope)\n", argv[i]); exit(1); }
 		else if (OPT("--cache", "-c") || OPT("--latency", "-l") || OPT("--clustradius", "-cr") || OPT("--dbpartition", "-dp")) { NEEDARG("option requires integer argument") }
 		else if (OPT("--help", "-h")) usage();
@@ -1145,12 +1270,14 @@ int main(int argc, char *argv[]) {
 	init_char2num();
 
 	/* the engine first: without a CUDA device there is nothing this program can do */
-	bg_ctx *ctx = NULL;
-	int rc = bg_init(GPU_DEVICE, &ctx);
-	if (rc) { fprintf(stderr, "ERROR: cannot start the GPU engine: %s\n", bg_last_error()); exit(3); }
+	bg_ctx *ctxs[64]; int rc;
 	uint8_t S[256]; bg_default_scoring(Z, S);
-	if ((rc = bg_set_scoring(ctx, S))) die_gpu("bg_set_scoring", rc);
-
+	for (int g = 0; g < NGPU; ++g) {                                     /* --gpus N: devices GPU_DEVICE .. GPU_DEVICE+N-1, one context each */
+		ctxs[g] = NULL;
+		if ((rc = bg_init(GPU_DEVICE + g, &ctxs[g]))) { fprintf(stderr, "ERROR: cannot start the GPU engine: %s\n", bg_last_error()); exit(3); }
+		if ((rc = bg_set_scoring(ctxs[g], S))) die_gpu("bg_set_scoring", rc);
+	}
+	bg_ctx *ctx = ctxs[0];
 	Acx A; memset(&A, 0, sizeof(A));
 	if (DO_ACCEL) load_acx(xcel_FN, &A);
 	int usedb = is_edx(ref_FN);
@@ -1163,11 +1290,11 @@ int main(int argc, char *argv[]) {
 		if (!DO_HEUR) exit(1);
 		fputs("!!! WARNING: Error overridden by use of heuristic mode!\n", stderr);
 	}
-	if ((rc = bg_load_db(ctx, R.packed, R.ClumpLen, R.numRclumps, 0))) die_gpu("bg_load_db", rc);
+	for (int g = 0; g < NGPU; ++g) if ((rc = bg_load_db(ctxs[g], R.packed, R.ClumpLen, R.numRclumps, 0))) die_gpu("bg_load_db", rc);   /* queries are sharded, the database is replicated */
 
 	PodList *Pods = xcalloc(Q.numUniqQ, sizeof(*Pods));
 	int mode = RUNMODE == FORAGE ? BG_MODE_ALL : BG_MODE_MIN;
-	if (DO_ACCEL) accel_search(ctx, &Q, &R, &A, Pods, mode, THREADS);
+	if (DO_ACCEL) accel_search(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS);
 	/* queries the accelerator cannot vouch for (or all of them without -a) go all-vs-all, burst.c:4320-4323 */
 	uint64_t firstQ = DO_ACCEL ? Q.QBins[1] : 0;
 	if (firstQ != Q.newUniqQ && !(DO_ACCEL && Q.skipAmbig)) search_all_vs_all(ctx, &Q, &R, firstQ, Pods, mode);
@@ -1178,7 +1305,7 @@ int main(int argc, char *argv[]) {
 	else if (RUNMODE == FORAGE) report_allpaths_or_forage(&P, Pods, 1);
 	else report_capitalist(&P, Pods);
 	fclose(output);
-	bg_free(ctx);
+	for (int g = 0; g < NGPU; ++g) bg_free(ctxs[g]);
 	printf("\nAlignment time: %f seconds\n", now() - start);
 	return 0;
 }

@@ -109,8 +109,14 @@ enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096)
                                         BG_Q_PACKED4 (kernel-bound: a short first copy, later copies hide behind the kernels) */
 enum { BG_PARAM_SEED_IMPL = 9,       /* 1 (default): warp-per-bunch seed filter (private window table, no block barriers); 0: the block form */
        BG_PARAM_SEED_NCH = 10,       /* 32-column chunks per register buffer of the warp form: 8 (default) or 4 */
-       BG_PARAM_SEED_LBITS = 11 };   /* log2 of the bits in a warp's window bitmap, 10..20 (0 = sized from the batch) */
+       BG_PARAM_SEED_LBITS = 11,     /* log2 of the bits in a warp's window filter, 10..20 (0 = sized from the batch) */
+       BG_PARAM_SEED_FB = 12 };      /* bits set per window in that filter: 1 (default) or 2 */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
+
+/* Page-locked host memory for the arrays handed to bg_align_runs_into() (queries, runs, hit buffer): makes the library's
+ * host<->device copies asynchronous, so that they overlap its kernels.  bg_host_free(NULL) is a no-op. */
+void *bg_host_alloc(uint64_t bytes);
+void  bg_host_free(void *p);
 
 /* ---- scoring: the 16x16 table the reference builds in setScore() (burst.c:1309-1328),
  * S[q*16+r] in {0,1,255}; call before aligning (default: Z=1 table). */

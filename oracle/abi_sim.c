@@ -47,6 +47,8 @@ static void free_batch(bg_ctx *c) {
 	c->codes = NULL; c->qoff = NULL; c->budget = NULL; c->slot = NULL; c->tq = c->tc = NULL; c->orig = NULL; c->best = NULL; c->hits = NULL;
 }
 void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); free(c->packed); free(c->clump_off); free(c->clump_len); free(c); }
+void *bg_host_alloc(uint64_t bytes) { return malloc(bytes ? bytes : 1); }
+void bg_host_free(void *p) { free(p); }
 int bg_set_stream(bg_ctx *c, void *s) { (void)c; (void)s; return BG_OK; }
 int bg_set_param(bg_ctx *c, int what, int value) { (void)c; (void)what; (void)value; return BG_OK; }
 int bg_set_scoring(bg_ctx *c, const uint8_t S[256]) { memcpy(c->S, S, 256); return BG_OK; }

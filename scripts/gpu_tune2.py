@@ -1,17 +1,17 @@
 #!/usr/bin/env python
 """Round-2 kernel-only timings of the bench workload under the seed-filter knobs (runs on the GPU box).
-usage: python scripts/gpu_tune2.py [--reads N] [--db-mb M] [--settings impl:nch:lbits:chunk,...]
+usage: python scripts/gpu_tune2.py [--reads N] [--db-mb M] [--settings impl:nch:lbits:chunk:fb,...]
 One line per setting: ms_filter / ms_extend / ms_select, and whether hits + minima equal the first setting's."""
 import argparse, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from burst_b200 import synth
-from burst_b200.engine import (Engine, MODE_MIN, RUN_DTYPE, PARAM_SEED_CHUNK, PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS)
+from burst_b200.engine import (Engine, MODE_MIN, RUN_DTYPE, PARAM_SEED_CHUNK, PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=1_000_000)
 ap.add_argument("--db-mb", type=int, default=2048)
-ap.add_argument("--settings", default="0:8:0:8,1:8:0:8,1:4:0:8,1:8:15:8,1:8:17:8,1:8:0:4,1:8:0:16,1:8:0:64,1:4:15:8")
+ap.add_argument("--settings", default="0:8:0:8:1,1:8:0:8:1,1:8:0:8:2,1:4:0:8:1,1:8:16:8:1,1:8:14:8:2,1:8:0:16:1")
 a = ap.parse_args()
 w = synth.bunch_workload(a.reads, 100, 2, a.db_mb << 20, 214, seed=20261017)
 eng = Engine(0)
@@ -19,8 +19,8 @@ eng.load_db(w["packed"], w["clump_len"])
 runs = np.ascontiguousarray(w["runs"], RUN_DTYPE)
 ref = None
 for s in a.settings.split(","):
-    impl, nch, lbits, chunk = [int(x) for x in s.split(":")]
-    eng.set_param(PARAM_SEED_IMPL, impl); eng.set_param(PARAM_SEED_NCH, nch); eng.set_param(PARAM_SEED_LBITS, lbits); eng.set_param(PARAM_SEED_CHUNK, chunk)
+    impl, nch, lbits, chunk, fb = [int(x) for x in s.split(":")]
+    eng.set_param(PARAM_SEED_IMPL, impl); eng.set_param(PARAM_SEED_NCH, nch); eng.set_param(PARAM_SEED_LBITS, lbits); eng.set_param(PARAM_SEED_CHUNK, chunk); eng.set_param(PARAM_SEED_FB, fb)
     eng.upload_runs(w["qcodes"], w["qoff"], w["budget"], runs, slot=w["slot"], nslots=w["nslots"])
     best = None
     for it in range(4):
@@ -32,5 +32,5 @@ for s in a.settings.split(","):
         ref = (hits, mins); same = "reference"
     else:
         same = "same" if (len(hits) == len(ref[0]) and np.array_equal(hits, ref[0]) and np.array_equal(mins, ref[1])) else "DIFFERENT (%d vs %d hits)" % (len(hits), len(ref[0]))
-    print("impl %d nch %d lbits %2d chunk %3d : filter %.3f ms  extend %.3f ms  select %.3f ms  survivors %d hits %d  [%s]" % (
-        impl, nch, lbits, chunk, best["ms_filter"], best["ms_extend"], best["ms_select"], best["survivors"], best["hits"], same), flush=True)
+    print("impl %d nch %d lbits %2d chunk %3d fb %d : filter %.3f ms  extend %.3f ms  select %.3f ms  survivors %d hits %d  [%s]" % (
+        impl, nch, lbits, chunk, fb, best["ms_filter"], best["ms_extend"], best["ms_select"], best["survivors"], best["hits"], same), flush=True)

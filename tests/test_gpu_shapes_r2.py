@@ -10,7 +10,7 @@ seconds), through the C ABI, for both seed-filter forms and the Myers prefix fil
 import numpy as np
 import pytest
 from burst_b200 import synth
-from burst_b200.engine import RUN_DTYPE, PARAM_SEED_IMPL, PARAM_SEED_NCH
+from burst_b200.engine import RUN_DTYPE, PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_FB
 
 pytestmark = pytest.mark.gpu
 
@@ -61,13 +61,13 @@ def test_c3_amplicon_shape(eng, oracle, mode):
     assert len(ohits) > (60 if mode == 0 else 200)                        # families: many lanes within budget / tied
     eng.set_scoring(S); eng.load_db(packed, clen)
     try:
-        for impl, nch, seedf in ((1, 8, True), (1, 4, True), (0, 8, True), (1, 8, False)):
-            eng.set_param(PARAM_SEED_IMPL, impl); eng.set_param(PARAM_SEED_NCH, nch); eng.set_seed_filter(seedf)
+        for impl, nch, fb, seedf in ((1, 8, 1, True), (1, 4, 2, True), (1, 8, 2, True), (0, 8, 1, True), (1, 8, 1, False)):
+            eng.set_param(PARAM_SEED_IMPL, impl); eng.set_param(PARAM_SEED_NCH, nch); eng.set_param(PARAM_SEED_FB, fb); eng.set_seed_filter(seedf)
             hits, best = eng.align(codes, qoff, budget, None, mode, slot=slot, nslots=nslots, runs=runs.astype(RUN_DTYPE))
-            assert np.array_equal(best, obest), (impl, nch, seedf)
-            assert len(hits) == len(ohits) and np.array_equal(hits, ohits), (impl, nch, seedf, len(hits), len(ohits))
+            assert np.array_equal(best, obest), (impl, nch, fb, seedf)
+            assert len(hits) == len(ohits) and np.array_equal(hits, ohits), (impl, nch, fb, seedf, len(hits), len(ohits))
     finally:
-        eng.set_param(PARAM_SEED_IMPL, 1); eng.set_param(PARAM_SEED_NCH, 8); eng.set_seed_filter(True)
+        eng.set_param(PARAM_SEED_IMPL, 1); eng.set_param(PARAM_SEED_NCH, 8); eng.set_param(PARAM_SEED_FB, 1); eng.set_seed_filter(True)
     eng.align(codes, qoff, budget, None, mode, slot=slot, nslots=nslots, runs=runs.astype(RUN_DTYPE))
     st = eng.stats()
     assert st["seed_queries"] == nq and st["seed_stride"] == 8
