@@ -28,6 +28,7 @@
 // every cell > maxED is treated as absent there too (burst.c:1053-1054, 802-803).
 #include <cuda_runtime.h>
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -697,9 +698,9 @@ struct SeedWArgs {
 	uint32_t m16[8];
 };
 // per-warp shared memory in words: filter | bucket heads | chain links (16 bit) | stretch records | budgets | 4 staging buffers (2 per half-warp) |
-// 4 mbarriers | 32 survivors waiting to leave | 64 flagged words waiting for verification.  hslots = buckets (power of two), ne = windows the table can hold = 16 * npmax * stride
+// 4 mbarriers | 32 survivors waiting to leave | 64 flagged words waiting for verification | per-lane seed records | queue fill.  hslots = buckets (power of two), ne = windows the table can hold = 16 * npmax * stride
 __host__ __device__ __forceinline__ uint32_t seedw_warp_words(uint32_t lbits, uint32_t hslots, uint32_t npmax, uint32_t stride, uint32_t nch) {
-	return (1u << (lbits - 5)) + hslots + ((8 * npmax * stride + 3) & ~3u) + 64 * npmax + 16 + 4 * nch * 64 + 8 + 128 + 64;
+	return (1u << (lbits - 5)) + hslots + ((8 * npmax * stride + 3) & ~3u) + 64 * npmax + 16 + 4 * nch * 64 + 8 + 128 + 64 + 128 + 4;
 }
 
 template <int STRIDE, bool FULLW, int NCH, int FB>   // FB: bits per window in the filter (1 or 2)
@@ -725,6 +726,8 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 	uint4 *sbuf = (uint4 *)(stage0 + 4 * NCH * 64 + 8); uint32_t scount = 0;   // survivors collected by the warp; they leave 32 at a time through one atomicAdd
 	uint32_t *hq = stage0 + 4 * NCH * 64 + 8 + 128;                        // flagged words waiting for verification: owner lane << 8 | half-word window << 7 | word of the item
 	constexpr uint32_t HQ = 64;
+	uint32_t *ost = hq + HQ, *hqn = ost + 128;                             // per lane: {query, lowest, highest seed diagonal, conflict flag} of its current run; queue fill
+	constexpr uint32_t NOQ = 0xFFFFFFFFu;
 	const uint32_t stgw_s = (uint32_t)__cvta_generic_to_shared(stage0);   // staging of the whole warp (a helper lane reads the owner's buffer)
 	auto flush = [&]() {
 		uint32_t base = 0;
@@ -829,16 +832,14 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 				RunD C = fetch(ct);
 				uint32_t prev = 0, prev2 = 0, ambp = 0, ambp2 = 0;             // scan state carried from item to item of a run
 				uint32_t iprev = 0, iprev2 = 0;                                // the two words before the current item (for verifying its first words)
-				uint32_t sn = 0, sq = 0; int dlo = 0, dhi = 0;                 // seeds of the current run: 0 none, 1 one query + a narrow hull (registers), 2 list (LS)
+				uint32_t sn = 0; bool serial = false;                          // seeds of the current run: sn 0 = in the lane's shared-memory record (one query, a hull), 2 = list (LS); serial: the lane verifies its own words
 				bool more = true;
 
-				auto seed = [&](uint32_t q, int dg) {
-					if (sn == 0) { sn = 1; sq = q; dlo = dhi = dg; return; }
-					if (sn == 1) {
-						const int nlo = min(dlo, dg), nhi = max(dhi, dg);
-						if (q == sq && nhi - nlo <= 2 * (int)kq[q] + 1) { dlo = nlo; dhi = nhi; return; }
-						// the hull so far is one cluster [dlo-k, dhi+k]: its two ends stand for it in the list
-						LS.q[0] = LS.q[1] = sq; LS.d[0] = dlo; LS.d[1] = dhi; LS.n = 2; sn = 2;
+				auto seed = [&](uint32_t q, int dg) {                          // list form (lanes that see several queries, IUPAC clumps)
+					if (sn == 0) {                                             // what the helpers gathered so far is one cluster: its two ends stand for it in the list
+						const uint32_t q0 = ost[lane * 4];
+						LS.n = 0; sn = 2;
+						if (q0 != NOQ) { LS.q[0] = LS.q[1] = q0; LS.d[0] = (int)ost[lane * 4 + 1]; LS.d[1] = (int)ost[lane * 4 + 2]; LS.n = 2; }
 					}
 					if (LS.n < SEED_LIST) { LS.q[LS.n] = q; LS.d[LS.n] = dg; ++LS.n; }
 					else lane_seeds_overflow(LS, q, dg);
@@ -858,7 +859,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 					const bool amb_on = C.valid && (C.flags & ambsel) != 0;
 					if (C.valid) {
 						const uint32_t nchunks = (C.len + 31) >> 5;
-						if (cg == 0) { prev = prev2 = ambp = ambp2 = 0; }
+						if (cg == 0) { prev = prev2 = ambp = ambp2 = 0; sn = 0; serial = amb_on; *(uint4 *)(ost + lane * 4) = make_uint4(NOQ, 0x7FFFFFFFu, 0x80000000u, 0u); }
 						iprev = prev; iprev2 = prev2;
 						const uint32_t sb = stg_s + cb * ITEM + l * 16;              // this lane's pieces: chunk c at sb + c * 256
 						mbar_wait(bar_s + 8 * cb, (phase >> cb) & 1u); phase ^= 1u << cb;
@@ -906,14 +907,15 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 					// anyone); a match returns to its owner by shuffle.
 					if (__any_sync(FULL, (m8 | m4) != 0u)) {
 						const uint32_t sb = stg_s + cb * ITEM + l * 16;
-						if (amb_on && (m8 | m4)) {                                 // clumps holding IUPAC codes: the owner compares its windows through the scoring table itself (rare)
+						// the owner's own (serial) verification: IUPAC clumps, lanes with seeds of several queries, a full queue
+						auto own = [&](uint32_t o8, uint32_t o4) {
 							auto word_at = [&](int wl) -> uint32_t { return wl >= 0 ? lds32(sb + (uint32_t)(wl >> 2) * 256 + (uint32_t)(wl & 3) * 4) : (wl == -1 ? iprev : iprev2); };
 							auto verify = [&](uint32_t wi, int e) {
 								const int wl = (int)(wi - cg * NW);
 								const uint32_t cu = word_at(wl), pv = word_at(wl - 1), pv2 = e == 4 ? word_at(wl - 2) : 0u;
 								const uint32_t rn = e == 8 ? cu : __funnelshift_r(pv, cu, 16), ro = (e == 8 ? pv : __funnelshift_r(pv2, pv, 16)) & HM;
 								const int x1 = (int)(wi * 8 + e);
-								if (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD)) {
+								if (amb_on && (amb_nibbles(rn, ADD) | amb_nibbles(ro, ADD))) {       // IUPAC codes in the window: every window of the bunch, through the table
 									for (uint32_t si = 0; si < 16 * NPM; ++si) {
 										const uint4 rec = *(const uint4 *)(str + si * 4);
 										if (!rec.w) continue;
@@ -934,79 +936,73 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 									}
 								}
 							};
-							while (m8 | m4) {
-								const uint32_t b = 31 - __clz(m8 | m4), bit = 1u << b, wi = cg * NW + (NW - 1 - b);
-								if (STRIDE == 4 && (m4 & bit)) verify(wi, 4);
-								if (m8 & bit) verify(wi, 8);
-								m8 &= ~bit; m4 &= ~bit;
+							while (o8 | o4) {
+								const uint32_t b = 31 - __clz(o8 | o4), bit = 1u << b, wi = cg * NW + (NW - 1 - b);
+								if (STRIDE == 4 && (o4 & bit)) verify(wi, 4);
+								if (o8 & bit) verify(wi, 8);
+								o8 &= ~bit; o4 &= ~bit;
 							}
-						}
-						while (__any_sync(FULL, (m8 | m4) != 0u)) {
-							// ---- enqueue: all flagged words if they fit, else the first two of every lane (the rest in the next pass) ----
-							const uint32_t mine = (uint32_t)(__popc(m8) + __popc(m4));
-							const uint32_t cnt = __reduce_add_sync(FULL, mine) <= HQ ? mine : min(mine, HQ / 32);
-							uint32_t off = cnt;
-							#pragma unroll
-							for (int d = 1; d < 32; d <<= 1) { const uint32_t t = __shfl_up_sync(FULL, off, d); if (lane >= (uint32_t)d) off += t; }
-							const uint32_t total = __shfl_sync(FULL, off, 31), maxcnt = __reduce_max_sync(FULL, cnt);
-							off -= cnt;
-							for (uint32_t j = 0; j < cnt; ++j) {
+						};
+						const uint32_t s8 = m8, s4 = m4;                           // kept: a lane whose helpers report a second query redoes the item itself
+						if (serial) { own(m8, m4); m8 = m4 = 0; }
+						uint32_t cnt = (uint32_t)(__popc(m8) + __popc(m4));
+						if (__reduce_add_sync(FULL, cnt) > HQ) { own(m8, m4); m8 = m4 = 0; cnt = 0; }       // more flagged words than the queue holds (rare): everyone its own
+						if (__any_sync(FULL, cnt != 0u)) {
+							// ---- enqueue ----
+							if (lane == 0) *hqn = 0;
+							__syncwarp();
+							uint32_t pos = cnt ? atomicAdd(hqn, cnt) : 0u;
+							while (m8 | m4) {
 								const uint32_t b = 31 - __clz(m8 | m4), bit = 1u << b;
 								const bool four = STRIDE == 4 && (m4 & bit);           // the half-word window of a word comes before its full-word window
-								hq[off + j] = (lane << 8) | (four ? 128u : 0u) | (uint32_t)(NW - 1 - b);
+								hq[pos++] = (lane << 8) | (four ? 128u : 0u) | (uint32_t)(NW - 1 - b);
 								if (four) m4 &= ~bit; else m8 &= ~bit;
 							}
 							__syncwarp();
+							const uint32_t total = *hqn;
+							// ---- helpers: one queue entry per lane and round; a match goes into the owner's record ----
 							for (uint32_t base = 0; base < total; base += 32) {
-								// ---- helper: one queue entry per lane ----
 								const bool have = base + lane < total;
 								const uint32_t ent = have ? hq[base + lane] : 0u, owner = ent >> 8, wl = ent & 127u;
 								const bool four = (ent & 128u) != 0;
 								const uint32_t o_cg = __shfl_sync(FULL, cg, owner), o_ip = __shfl_sync(FULL, iprev, owner), o_ip2 = __shfl_sync(FULL, iprev2, owner);
-								uint32_t en = 0, rn = 0, ro = 0; int x1 = 0;
 								if (have) {
 									const uint32_t osb = stgw_s + (owner >> 4) * 2 * ITEM + cb * ITEM + (owner & 15) * 16;
 									auto word = [&](int w) -> uint32_t { return w >= 0 ? lds32(osb + (uint32_t)(w >> 2) * 256 + (uint32_t)(w & 3) * 4) : (w == -1 ? o_ip : o_ip2); };
 									const uint32_t cu = word((int)wl), pv = word((int)wl - 1), pv2 = four ? word((int)wl - 2) : 0u;
-									rn = four ? __funnelshift_r(pv, cu, 16) : cu; ro = (four ? __funnelshift_r(pv2, pv, 16) : pv) & HM;
-									x1 = (int)((o_cg * NW + wl) * 8 + (four ? 4 : 8));
-									en = slots[(seed_hash(rn, ro) >> 10) & HSM];
-								}
-								for (;;) {                                               // the next matching window of every entry (usually there is at most one)
-									bool found = false; uint32_t mq = 0; int mdg = 0;
-									while (en && !found) {
+									const uint32_t rn = four ? __funnelshift_r(pv, cu, 16) : cu, ro = (four ? __funnelshift_r(pv2, pv, 16) : pv) & HM;
+									const int x1 = (int)((o_cg * NW + wl) * 8 + (four ? 4 : 8));
+									for (uint32_t en = slots[(seed_hash(rn, ro) >> 10) & HSM]; en; en = nxt[en - 1]) {
 										const uint32_t si = (en - 1) / STRIDE, j = (en - 1) % STRIDE;
 										const uint4 rec = *(const uint4 *)(str + si * 4);
 										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
 										const QWin w = window_of(S, j);
-										if (w.kn == rn && (w.ko & HM) == ro) { found = true; mq = si / NPM; mdg = x1 - (int)w.y1; }
-										en = nxt[en - 1];
-									}
-									if (!__any_sync(FULL, found)) break;
-									// ---- back to the owners: lane o's entries sit at queue positions off .. off + cnt - 1 ----
-									for (uint32_t j = 0; j < maxcnt; ++j) {
-										const int src = (int)(off + j) - (int)base;
-										const uint32_t sl = (uint32_t)min(max(src, 0), 31);
-										const uint32_t gf = __shfl_sync(FULL, (uint32_t)found, sl), gq = __shfl_sync(FULL, mq, sl);
-										const int gd = __shfl_sync(FULL, mdg, sl);
-										if (j < cnt && src >= 0 && src < 32 && gf) seed(gq, gd);
+										if (w.kn == rn && (w.ko & HM) == ro) {
+											const uint32_t q = si / NPM, was = atomicCAS(&ost[owner * 4], NOQ, q);
+											if (was == NOQ || was == q) { atomicMin((int *)&ost[owner * 4 + 1], x1 - (int)w.y1); atomicMax((int *)&ost[owner * 4 + 2], x1 - (int)w.y1); }
+											else ost[owner * 4 + 3] = 1u;                    // a second query on this lane: the owner takes over
+										}
 									}
 								}
 							}
 							__syncwarp();
+							if (ost[lane * 4 + 3]) { ost[lane * 4 + 3] = 0u; serial = true; own(s8, s4); }
 						}
 					}
 					if (C.valid) {
 						// ---- end of the run: its seeds leave as survivors ----
-						if (lastg && sn) {
+						if (lastg) {
 							const uint32_t task0 = (C.r + A.W.run_base) * BG_RUN_MAX;
-							if (sn == 1) {
-								const int k0 = (int)kq[sq];
-								const uint32_t W = (uint32_t)(dhi - dlo + 2 * k0 + 1);
-								emit = true; ev.task = task0 + sq; ev.lo = dlo - k0; ev.w_lane = (W << 8) | (1u << 4) | l;
-								if (W > 64) ev.scratch = atomicAdd(&A.counters[C_SCRATCH], W);
-							} else lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters);
-							sn = 0;
+							if (sn == 2) { lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters); sn = 0; }
+							else {
+								const uint4 st = *(const uint4 *)(ost + lane * 4);
+								if (st.x != NOQ) {
+									const int k0 = (int)kq[st.x], dlo = (int)st.y, dhi = (int)st.z;
+									const uint32_t W = (uint32_t)(dhi - dlo + 2 * k0 + 1);
+									emit = true; ev.task = task0 + st.x; ev.lo = dlo - k0; ev.w_lane = (W << 8) | (1u << 4) | l;
+									if (W > 64) ev.scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+								}
+							}
 						}
 					}
 					const uint32_t em = __ballot_sync(FULL, emit);
@@ -1305,7 +1301,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			for (int u = 0; u <= D; ++u) R[u] = u == 0 ? w0 : lane_word_or0(lanew, wbase + u, nwords);
 			#pragma unroll
 			for (int u = 0; u < D; ++u) { Qw[u] = (uint32_t)u < ngroups ? __ldg(Wq + u) : 0u; RN[u] = 0; QN[u] = 0; }
-			uint32_t bpre = k;                               // the slot's running minimum, fetched one group (8 rows) before it is applied
+			uint32_t bpre = k;                               // the slot's running minimum, fetched one round (4 groups) before it is applied
 			// Fast rows: query and reference codes all plain bases, band inside the matrix, short query.  Then the substitution cost is
 			// "the nibbles differ" (one XOR per row, no table), and cells above the budget need no clamp: they can never win or tie a
 			// cell within it, and with m + WB < 480 no field of the key can overflow.
@@ -1314,13 +1310,13 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			#pragma unroll
 			for (int j = 0; j < NW; ++j) if (nonplain_nibbles(win[j] | (j == NW - 1 ? ~TOPMASK & 0x11111111u : 0u))) badrows = WB;
 			for (uint32_t gq0 = 0; gq0 < ngroups && !dead; gq0 += D) {
+			// tighten Emac as better hits land (burst.c:4159, 4220): a value read a round (32 rows) ago is only less tight, never wrong
+			k = min(k, bpre); inf = (k + 1) << 22;
+			if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + slot);
 			#pragma unroll
 			for (int u = 0; u < D; ++u) {
 				const uint32_t gq = gq0 + u;
 				if (gq >= ngroups || dead) break;
-				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
-				k = min(k, bpre); inf = (k + 1) << 22;
-				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + slot);
 				// the words this ring slot will hold in the next round: issued here, first touched D groups later
 				RN[u] = lane_word_or0(lanew, wbase + (int)gq0 + D + 1 + u, nwords); QN[u] = gq0 + D + u < ngroups ? __ldg(Wq + gq0 + D + u) : 0u;
 				const uint32_t feed = __funnelshift_r(R[u], R[u + 1], sh2), qw = Qw[u];
@@ -1495,6 +1491,83 @@ __global__ void k_init_best(uint32_t *best, const uint16_t *in, uint32_t n) {
 	if (i < n) best[i] = in ? in[i] : 0xFFFFu;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Compact strand batches (bg_align_bunches_into): every READ crosses the bus once, 2 or 4 bits per base; the device
+// derives both strands (burst.c:3087-3109 builds the reverse-complement copies on the host), the per-strand records
+// and the run list from the bunch -> candidate lists the reference's driver works with (burst.c:4085-4157).
+// ---------------------------------------------------------------------------------------------
+__constant__ uint8_t c_rvt[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};       // burst.c:168
+// lengths: per read (u16 -> u64) and per strand, the latter rounded up to 16 so that every strand's codes start 16-byte aligned
+__global__ void k_compact_len(const uint16_t *__restrict__ rlen, uint32_t nreads, const uint32_t *__restrict__ strand, uint32_t nq,
+		unsigned long long *__restrict__ rl64, unsigned long long *__restrict__ sl64, uint32_t *__restrict__ counters) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i <= nreads) rl64[i] = i < nreads ? rlen[i] : 0;
+	if (i <= nq) {
+		unsigned long long v = 0;
+		if (i < nq) {
+			const uint32_t r = strand[i] & 0x7FFFFFFFu;
+			if (r >= nreads) atomicExch(&counters[C_ERR], i + 1);
+			else v = ((unsigned long long)rlen[r] + 15ull) & ~15ull;
+		}
+		sl64[i] = v;
+	}
+}
+// codes of every strand (one byte per base, 16-byte aligned start): 8 threads per strand, 16 bases per thread and step
+__global__ void k_compact_codes(const uint8_t *__restrict__ reads, uint32_t flags, const unsigned long long *__restrict__ roff, const uint16_t *__restrict__ rlen,
+		const uint32_t *__restrict__ strand, const unsigned long long *__restrict__ qoff, uint32_t nq, uint32_t nreads, uint8_t *__restrict__ codes) {
+	const uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 3, sub = threadIdx.x & 7;
+	if (q >= nq) return;
+	const uint32_t sv = strand[q], r = sv & 0x7FFFFFFFu; const bool rc = sv >> 31;
+	if (r >= nreads) return;
+	const uint32_t len = rlen[r];
+	const unsigned long long ro = roff[r], qo = qoff[q];
+	const bool two = (flags & BG_R_PACKED2) != 0;
+	for (uint32_t b0 = sub * 16; b0 < len; b0 += 128) {
+		uint32_t w[4] = {0, 0, 0, 0};
+		#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			const uint32_t pos = b0 + i;
+			if (pos < len) {
+				const unsigned long long x = ro + (rc ? len - 1 - pos : pos);
+				uint32_t code = two ? ((__ldg(reads + (x >> 2)) >> (2 * (x & 3))) & 3u) + 1u : (__ldg(reads + (x >> 1)) >> (4 * (x & 1))) & 15u;
+				if (rc) code = c_rvt[code];
+				w[i >> 2] |= code << (8 * (i & 3));
+			}
+		}
+		*(uint4 *)(codes + qo + b0) = make_uint4(w[0], w[1], w[2], w[3]);
+	}
+}
+// the strand records (as k_qinfo) and the histogram of stretch lengths
+__global__ void k_compact_qinfo(const unsigned long long *__restrict__ qoff, const uint16_t *__restrict__ rlen, const uint16_t *__restrict__ rbudget,
+		const uint32_t *__restrict__ strand, uint32_t nq, uint32_t nreads, QInfo *__restrict__ qi, uint32_t *__restrict__ hist, uint32_t *__restrict__ counters) {
+	__shared__ uint32_t sh[32];
+	if (threadIdx.x < 32) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+	if (q < nq) {
+		uint32_t r = strand[q] & 0x7FFFFFFFu, len = 1, k = 0;
+		if (r >= nreads) { atomicExch(&counters[C_ERR], q + 1); r = 0; }
+		else { len = rlen[r]; k = rbudget[r]; if (!len || k > 254) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; } }
+		QInfo Q; Q.off = qoff[q]; Q.len = len; Q.slot = r; Q.k = (uint16_t)k; Q.P = (uint8_t)min(32u, len); Q.cls = 0;
+		qi[q] = Q;
+		if (k + 1 <= SEED_NP_MAX) atomicAdd(&sh[min(len / (k + 1), 31u)], 1u);
+	}
+	__syncthreads();
+	if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
+}
+// bunch -> candidate lists into runs: run r = candidate r of the bunch that owns it (cand_off), all queries of the bunch
+__global__ void k_compact_runs(const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t nbunch, uint32_t nruns, uint32_t qbunch, uint32_t nq,
+		bg_run *__restrict__ runs, uint32_t *__restrict__ counters) {
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r >= nruns) return;
+	uint32_t lo = 0, hi = nbunch;                                          // last bunch b with cand_off[b] <= r
+	while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(cand_off + mid) <= r) lo = mid; else hi = mid; }
+	const unsigned long long q0 = (unsigned long long)lo * qbunch;
+	bg_run R; R.clump = cand[r]; R.query0 = (uint32_t)min(q0, (unsigned long long)nq); R.nq = q0 < nq ? (uint32_t)min((unsigned long long)qbunch, nq - q0) : 0u;
+	if (!R.nq || __ldg(cand_off + lo) > r || __ldg(cand_off + lo + 1) <= r) { atomicExch(&counters[C_ERR], 0x80000000u | r); R.nq = 1; R.query0 = 0; }
+	runs[r] = R;
+}
+
 // run validation (explicit run lists): malformed runs raise the error flag
 __global__ void k_check_runs(const bg_run *__restrict__ runs, uint64_t nruns, uint32_t q_base, uint32_t nq, uint32_t *counters) {
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1576,6 +1649,7 @@ struct bg_ctx {
 	DBuf<uint8_t> d_packed; DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
 	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
+	DBuf<uint16_t> d_rlen, d_rbud; DBuf<uint32_t> d_strand, d_candoff, d_cand; DBuf<unsigned long long> d_rl64, d_sl64, d_roff;   // compact strand batches
 	DBuf<uint32_t> d_cls; DBuf<uint4> d_xs;                       // band-class bins of the survivors, expanded records (k_bin_*)
 	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
@@ -1651,7 +1725,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
 	c->d_packed.release(); c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
 	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
-	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_cls.release(); c->d_xs.release();
+	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_cls.release(); c->d_xs.release(); c->d_rlen.release(); c->d_rbud.release(); c->d_strand.release(); c->d_candoff.release(); c->d_cand.release(); c->d_rl64.release(); c->d_sl64.release(); c->d_roff.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -2306,6 +2380,72 @@ extern "C" int bg_align_runs_into(bg_ctx *c, const bg_queries *Q, const bg_run *
 	rc = bg_batch_count(c, &n); if (rc) return rc;
 	*nhits = n;
 	if (n > cap) return fail(BG_EOVERFLOW, "bg_align_runs_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
+	return bg_batch_download(c, hits, cap, best_inout);
+}
+
+extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, const uint32_t *cand_off, const uint32_t *cand, uint32_t nbunch,
+		int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+	if (!c || !R || !cand_off || !cand || !nhits || (!hits && cap)) return fail(BG_EINVAL, "bg_align_bunches_into: null argument");
+	if (!c->num_clumps) return fail(BG_EINVAL, "bg_align_bunches_into: no database loaded");
+	if (!R->reads || !R->len || !R->budget || !R->strand || !R->nreads || !R->nq) return fail(BG_EINVAL, "bg_align_bunches_into: null or empty read arrays");
+	if (R->flags != BG_R_PACKED4 && R->flags != BG_R_PACKED2) return fail(BG_EINVAL, "bg_align_bunches_into: flags must be BG_R_PACKED4 or BG_R_PACKED2");
+	if (!qbunch || qbunch > BG_RUN_MAX) return fail(BG_EINVAL, "bg_align_bunches_into: bunch size %u (must be 1..%d)", qbunch, BG_RUN_MAX);
+	if ((uint64_t)nbunch * qbunch < R->nq || (uint64_t)(nbunch - 1) * qbunch >= R->nq) return fail(BG_EINVAL, "bg_align_bunches_into: %u bunches of %u do not cover %u strands", nbunch, qbunch, R->nq);
+	const uint64_t nruns = cand_off[nbunch];
+	if (cand_off[0] != 0 || nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_align_bunches_into: candidate offsets must start at 0 and end below 2^28");
+	CU(cudaSetDevice(c->device));
+	c->kind = WORK_NONE;
+	const uint32_t nq = R->nq, nr = R->nreads;
+	cudaStream_t st = c->stream;
+	// ---- host -> device: the packed reads, two u16 per read, one u32 per strand, the bunch lists ----
+	uint64_t nbases_max = (uint64_t)nr * 65535ull;                      // bound only; the exact totals come from the scans below
+	(void)nbases_max;
+	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_runs.need(nruns + 1) || c->d_cand.need(nruns + 1) ||
+	    c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) || c->d_qoff.need((size_t)nq + 1) ||
+	    c->d_qi.need(nq) || c->d_peq.need((size_t)nq * 16) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8)) return BG_ENOMEM;
+	CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_strand.p, R->strand, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, st));
+	if (nruns) CU(cudaMemcpyAsync(c->d_cand.p, cand, nruns * 4, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(c->d_counters.p, 0, 256, st));
+	// ---- offsets: reads in the packed stream (bases), strands in the code array (16-byte aligned starts) ----
+	k_compact_len<<<(std::max(nr, nq) + 256) / 256, 256, 0, st>>>(c->d_rlen.p, nr, c->d_strand.p, nq, c->d_rl64.p, c->d_sl64.p, c->d_counters.p);
+	size_t tmp1 = 0, tmp2 = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
+	if (c->d_sort_tmp.need(std::max(tmp1, tmp2) + 16)) return BG_ENOMEM;
+	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
+	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
+	unsigned long long tot[2] = {0, 0};
+	CU(cudaMemcpyAsync(&tot[0], c->d_roff.p + nr, 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(&tot[1], c->d_qoff.p + nq, 8, cudaMemcpyDeviceToHost, st));
+	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_align_bunches_into: strand %u names read %u of %u", c->h_pinned[C_ERR] - 1, R->strand[c->h_pinned[C_ERR] - 1] & 0x7FFFFFFFu, nr);
+	const uint64_t rbytes = R->flags == BG_R_PACKED2 ? (tot[0] + 3) / 4 : (tot[0] + 1) / 2, ncodes = tot[1];
+	if (c->d_packed.need(rbytes + 32) || c->d_codes.need(ncodes + 32) || c->d_qnib.need(ncodes / 8 + 3ull * nq + 8)) return BG_ENOMEM;
+	CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, st));
+	// ---- strands: codes, records, window layout, packed copies, Myers tables; runs from the bunch lists ----
+	k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, st>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
+	k_compact_qinfo<<<(nq + 255) / 256, 256, 0, st>>>((const unsigned long long *)c->d_qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, nq, nr, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
+	if (nruns) k_compact_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, st>>>(c->d_candoff.p, c->d_cand.p, nbunch, (uint32_t)nruns, qbunch, nq, c->d_runs.p, c->d_counters.p);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_align_bunches_into: malformed batch (read lengths >= 1, budgets <= 254 (burst.c:3076), ascending candidate offsets)");
+	c->SL = choose_layout(c, c->h_pinned + 16, nq);
+	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
+	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, st>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
+	CU(cudaGetLastError());
+	c->nq = nq; c->nslots = nr;
+	c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = nruns * BG_RUN_MAX; c->ntiles = 0;
+	int rc = finish_upload(c); if (rc) return rc;
+	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
+	uint64_t n = 0;
+	rc = bg_batch_count(c, &n); if (rc) return rc;
+	*nhits = n;
+	if (n > cap) return fail(BG_EOVERFLOW, "bg_align_bunches_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
 	return bg_batch_download(c, hits, cap, best_inout);
 }
 

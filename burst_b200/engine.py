@@ -17,6 +17,7 @@ RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
 MODE_MIN, MODE_ALL = 0, 1
 Q_PACKED4 = 1
+R_PACKED4, R_PACKED2 = 1, 2
 PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE, PARAM_PIPE_SLICES = 1, 2, 3, 4, 5
 PARAM_PIPE_MIN_RUNS, PARAM_PIPE_RATIO, PARAM_SEED_GROUPS = 6, 7, 8
 PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB = 9, 10, 11, 12
@@ -25,6 +26,11 @@ PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB = 9, 10, 11, 12
 class BgQueries(C.Structure):
     _fields_ = [("codes", C.c_void_p), ("offset", C.c_void_p), ("budget", C.c_void_p),
                 ("slot", C.c_void_p), ("nq", C.c_uint32), ("nslots", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class BgReads(C.Structure):
+    _fields_ = [("reads", C.c_void_p), ("len", C.c_void_p), ("budget", C.c_void_p), ("strand", C.c_void_p),
+                ("nreads", C.c_uint32), ("nq", C.c_uint32), ("flags", C.c_uint32)]
 
 
 class BgStats(C.Structure):
@@ -42,7 +48,7 @@ EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scori
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
            "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into",
-           "bg_host_alloc", "bg_host_free"]
+           "bg_host_alloc", "bg_host_free", "bg_align_bunches_into"]
 
 
 def load_library(path=None):
@@ -79,6 +85,11 @@ def load_library(path=None):
     L.bg_free_hits.argtypes = [C.c_void_p]
     L.bg_align_runs_into.argtypes = [C.c_void_p, C.POINTER(BgQueries), C.c_void_p, C.c_uint64, C.c_int,
                                      C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.bg_align_bunches_into.argtypes = [C.c_void_p, C.POINTER(BgReads), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
+                                        C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    L.bg_host_alloc.restype = C.c_void_p
+    L.bg_host_alloc.argtypes = [C.c_uint64]
+    L.bg_host_free.argtypes = [C.c_void_p]
     return L
 
 
@@ -135,6 +146,31 @@ class Engine:
         if len(c) & 1:
             c = np.concatenate([c, np.zeros(1, np.uint8)])
         return (c[0::2] | (c[1::2] << 4)).astype(np.uint8)
+
+    @staticmethod
+    def pack2(codes):
+        """BG_R_PACKED2 form of a code array holding only A/C/G/T (1..4): code - 1, four bases per byte, first base in the low bits."""
+        c = np.ascontiguousarray(codes, np.uint8)
+        assert c.min() >= 1 and c.max() <= 4, "2-bit packing takes plain bases only"
+        c = c - 1
+        pad = (-len(c)) % 4
+        if pad:
+            c = np.concatenate([c, np.zeros(pad, np.uint8)])
+        c = c.reshape(-1, 4)
+        return (c[:, 0] | (c[:, 1] << 2) | (c[:, 2] << 4) | (c[:, 3] << 6)).astype(np.uint8)
+
+    def align_bunches_into(self, reads, rlen, rbudget, strand, qbunch, cand_off, cand, hits_out, best_inout=None, mode=MODE_MIN, packed2=False):
+        """bg_align_bunches_into: `reads` is the packed stream (pack2 / pack4 of the concatenated read codes), `strand` the sorted
+        strands (read | rc << 31), (cand_off, cand) the bunch -> candidate lists.  Returns the number of hits."""
+        rlen = np.ascontiguousarray(rlen, np.uint16); rbudget = np.ascontiguousarray(rbudget, np.uint16)
+        strand = np.ascontiguousarray(strand, np.uint32); cand_off = np.ascontiguousarray(cand_off, np.uint32); cand = np.ascontiguousarray(cand, np.uint32)
+        reads = np.ascontiguousarray(reads, np.uint8)
+        R = BgReads(reads.ctypes.data, rlen.ctypes.data, rbudget.ctypes.data, strand.ctypes.data, len(rlen), len(strand), R_PACKED2 if packed2 else R_PACKED4)
+        self._nslots = len(rlen)
+        nh = C.c_uint64(0)
+        self._check(self.lib.bg_align_bunches_into(self.ctx, C.byref(R), qbunch, cand_off.ctypes.data, cand.ctypes.data, len(cand_off) - 1, mode,
+                                                   None if best_inout is None else best_inout.ctypes.data, hits_out.ctypes.data, len(hits_out), C.byref(nh)))
+        return int(nh.value)
 
     def _queries(self, codes, offset, budget, slot, nslots):
         """`codes` is a uint8 code array, or a ("packed4", array) pair holding the nibble-packed form."""

@@ -324,3 +324,32 @@ def bunch_runs(order_len, qbunch, cands_of_bunch):
             runs.append((int(c), q0, n))
     runs = np.array(runs, dtype=np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")]))
     return runs, np.array(tq, np.uint32), np.array(tc, np.uint32), np.array(key, np.uint32)
+
+
+def strand_batch(reads, budgets, qbunch, cands_of_bunch, rng=None):
+    """The compact strand form (bg_align_bunches_into) of a read set and the equivalent general form.
+    reads: list of code arrays; budgets: per read.  Strands = every read and its reverse complement, sorted as the
+    reference sorts them (burst.c:3181-3184).  cands_of_bunch(b, strand_reads, strand_rc) -> candidate clumps of bunch b.
+    Returns dict(rlen, rbudget, strand, cand_off, cand, rcodes [concatenated read codes], and the general form:
+    qcodes, qoff, budget, slot, runs, tq, tc, key)."""
+    n = len(reads)
+    strands, sread, src = [], [], []
+    for i, r in enumerate(reads):
+        strands += [r, RC_TABLE[r[::-1]]]; sread += [i, i]; src += [0, 1]
+    codes, off = concat_queries(strands)
+    order = sort_strands(codes, off)
+    strands = [strands[i] for i in order]
+    sread = np.array([sread[i] for i in order], np.uint32); src = np.array([src[i] for i in order], np.uint32)
+    nq = len(strands)
+    cand_off = [0]; cand = []
+    for b, q0 in enumerate(range(0, nq, qbunch)):
+        cs = list(cands_of_bunch(b, sread[q0:q0 + qbunch], src[q0:q0 + qbunch]))
+        cand += [int(c) for c in cs]; cand_off.append(len(cand))
+    cand_off = np.array(cand_off, np.uint32); cand = np.array(cand, np.uint32)
+    it = iter(range(len(cand_off) - 1))
+    runs, tq, tc, key = bunch_runs(nq, qbunch, lambda b, q0, m: cand[cand_off[b]:cand_off[b + 1]])
+    qcodes, qoff = concat_queries(strands)
+    rcodes, _ = concat_queries(reads)
+    return dict(rlen=np.array([len(r) for r in reads], np.uint16), rbudget=np.asarray(budgets, np.uint16), strand=(sread | (src << 31)).astype(np.uint32),
+                cand_off=cand_off, cand=cand, rcodes=rcodes, qcodes=qcodes, qoff=qoff, budget=np.asarray(budgets, np.uint16)[sread], slot=sread,
+                runs=runs, tq=tq, tc=tc, key=key, nreads=n)

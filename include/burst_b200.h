@@ -151,6 +151,24 @@ int  bg_batch_count(bg_ctx *ctx, uint64_t *nhits);
 int  bg_batch_download(bg_ctx *ctx, bg_hit *hits, uint64_t cap, uint16_t *best_out);
 int  bg_batch_stats(bg_ctx *ctx, bg_stats *out);
 
+/* ---- compact strand batches: the form of the accelerated path with -fr (burst.c:3087-3109, 4077-4157) that moves the fewest bytes.
+ * Every READ crosses the bus once, 4 or 2 bits per base; the device derives both strands.  The queries of the batch are the
+ * STRANDS in the order the host sorted them (UniBins order): strand[q] = read index | (1 << 31 if reverse complement); the slot of
+ * a strand (its running minimum, shared by both strands, burst.c:4218) is its read index, so best_inout has nreads entries.
+ * Work comes as the reference's bunch -> candidate lists: bunch b = strands b*qbunch .. (+qbunch), its candidates
+ * cand[cand_off[b] .. cand_off[b+1]) in visiting order.  Run r of the batch = candidate r; hits carry task = r * BG_RUN_MAX + (strand - b*qbunch). */
+enum { BG_R_PACKED4 = 1,    /* reads: concatenated code nibbles, base i of the stream in nibble i & 1 of byte i >> 1 (low first) */
+       BG_R_PACKED2 = 2 };  /* reads: A C G T only, code - 1 in bits 2(i & 3) .. of byte i >> 2 */
+typedef struct {
+	const uint8_t  *reads;      /* packed stream of all reads, back to back (no per-read alignment) */
+	const uint16_t *len;        /* nreads lengths in bases (>= 1) */
+	const uint16_t *budget;     /* nreads budgets (ShrBins[].ed, <= 254) */
+	const uint32_t *strand;     /* nq strands in sorted order */
+	uint32_t nreads, nq, flags; /* flags: BG_R_PACKED4 or BG_R_PACKED2 */
+} bg_reads;
+int  bg_align_bunches_into(bg_ctx *ctx, const bg_reads *reads, uint32_t qbunch, const uint32_t *cand_off, const uint32_t *cand, uint32_t nbunch,
+                           int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits);
+
 /* ---- the one-call form the host driver uses: upload + run + download.  *hits is
  * malloc()ed by the library (free with bg_free_hits). */
 int  bg_align_batch(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint64_t ntasks,

@@ -182,3 +182,39 @@ int bg_align_runs_into(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint6
 	return bg_batch_download(c, hits, cap, best_inout);
 }
 void bg_free_hits(bg_hit *h) { free(h); }
+
+/* compact strand batches: expanded on the host into the general form (strands as byte codes, runs from the bunch lists) */
+int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, const uint32_t *cand_off, const uint32_t *cand, uint32_t nbunch,
+		int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+	static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};
+	uint64_t *roff = malloc(((size_t)R->nreads + 1) * 8), *qoff = malloc(((size_t)R->nq + 1) * 8);
+	roff[0] = 0;
+	for (uint32_t r = 0; r < R->nreads; ++r) roff[r + 1] = roff[r] + R->len[r];
+	qoff[0] = 0;
+	for (uint32_t q = 0; q < R->nq; ++q) {
+		uint32_t r = R->strand[q] & 0x7FFFFFFFu;
+		if (r >= R->nreads) { snprintf(g_err, sizeof(g_err), "bg_align_bunches_into: strand %u names read %u of %u", q, r, R->nreads); free(roff); free(qoff); return BG_EINVAL; }
+		qoff[q + 1] = qoff[q] + R->len[r];
+	}
+	uint8_t *codes = malloc(qoff[R->nq] + 1);
+	uint16_t *bud = malloc((size_t)R->nq * 2); uint32_t *slot = malloc((size_t)R->nq * 4);
+	for (uint32_t q = 0; q < R->nq; ++q) {
+		uint32_t r = R->strand[q] & 0x7FFFFFFFu, len = R->len[r]; int rc = R->strand[q] >> 31;
+		bud[q] = R->budget[r]; slot[q] = r;
+		for (uint32_t i = 0; i < len; ++i) {
+			uint64_t x = roff[r] + (rc ? len - 1 - i : i);
+			uint8_t code = R->flags == BG_R_PACKED2 ? (uint8_t)(((R->reads[x >> 2] >> (2 * (x & 3))) & 3) + 1) : (uint8_t)((R->reads[x >> 1] >> (4 * (x & 1))) & 15);
+			codes[qoff[q] + i] = rc ? RVT[code] : code;
+		}
+	}
+	uint64_t nruns = cand_off[nbunch];
+	bg_run *runs = malloc((nruns + 1) * sizeof(bg_run));
+	for (uint32_t b = 0; b < nbunch; ++b) for (uint64_t r = cand_off[b]; r < cand_off[b + 1]; ++r) {
+		uint64_t q0 = (uint64_t)b * qbunch;
+		runs[r].clump = cand[r]; runs[r].query0 = (uint32_t)q0; runs[r].nq = (uint32_t)(R->nq - q0 < qbunch ? R->nq - q0 : qbunch);
+	}
+	bg_queries Q = {codes, qoff, bud, slot, R->nq, R->nreads, 0};
+	int rc = bg_align_runs_into(c, &Q, runs, nruns, mode, best_inout, hits, cap, nhits);
+	free(roff); free(qoff); free(codes); free(bud); free(slot); free(runs);
+	return rc;
+}

@@ -60,3 +60,25 @@ def test_pack4_layout():
     from burst_b200.engine import Engine
     c = np.array([1, 2, 3, 4, 15], np.uint8)
     assert Engine.pack4(c).tolist() == [0x21, 0x43, 0x0F]
+
+
+def test_compact_strand_batches(sim):
+    """bg_align_bunches_into: reads sent once (2 or 4 bits per base), strands + bunch lists -> the same hits and minima as the
+    general form (strands as byte codes, runs written out)."""
+    from burst_b200 import synth
+    from burst_b200.engine import Engine, HIT_DTYPE
+    rng = np.random.default_rng(12)
+    refs = synth.random_refs(16 * 8, 230, rng, jitter=10)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 37, 100, 2, rng, rc_rate=0.5)
+    reads = [r[:int(rng.integers(80, 101))] for r in reads]                       # ragged lengths
+    B = synth.strand_batch(reads, [2] * len(reads), 8, lambda b, rd, rc: sorted({int(origin[r, 0]) for r in rd} | {0, len(clen) - 1}))
+    sim.load_db(packed, clen)
+    for mode in (0, 1):
+        want_h, want_b = sim.align(B["qcodes"], B["qoff"], B["budget"], None, mode, slot=B["slot"], nslots=B["nreads"], runs=B["runs"])
+        assert len(want_h) >= 30
+        for packed2 in (False, True):
+            stream = Engine.pack2(B["rcodes"]) if packed2 else Engine.pack4(B["rcodes"])
+            buf = np.zeros(len(want_h) + 2, HIT_DTYPE); b2 = np.full(B["nreads"], 0xFFFF, np.uint16)
+            n = sim.align_bunches_into(stream, B["rlen"], B["rbudget"], B["strand"], 8, B["cand_off"], B["cand"], buf, b2, mode, packed2=packed2)
+            assert n == len(want_h) and np.array_equal(buf[:n], want_h) and np.array_equal(b2, want_b), (mode, packed2)

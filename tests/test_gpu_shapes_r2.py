@@ -119,3 +119,32 @@ def test_c4_shape_two_reference_shards(eng, oracle):
     keep = keep[np.lexsort((keep["lane"], keep["task"]))]
     assert np.array_equal(keep, ohits)
     assert len(set(np.nonzero(bests[0] != 0xFFFF)[0]) & set(np.nonzero(bests[1] != 0xFFFF)[0])) > 0   # some reads hit in both shards
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_compact_strand_batches_match_the_oracle(eng, oracle, mode):
+    """bg_align_bunches_into (reads sent once at 2 / 4 bits per base, strands derived on the device, runs from the bunch lists)
+    against the oracle on the written-out form; IUPAC reads included in the 4-bit case."""
+    from burst_b200.engine import Engine, HIT_DTYPE
+    rng = np.random.default_rng(77 + mode)
+    refs = synth.random_refs(16 * 24, 214, rng, jitter=8)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 301, 100, 2, rng, rc_rate=0.5)
+    reads = [r[:int(rng.integers(70, 101))] for r in reads]
+    S = oracle.score_table(1)
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    for packed2 in (True, False):
+        if not packed2:
+            for i in range(0, len(reads), 23):
+                reads[i] = reads[i].copy(); reads[i][len(reads[i]) // 2] = 5              # an N: those strands go to the Myers filter
+        budgets = [oracle.budget(0.98, len(r)) for r in reads]
+        B = synth.strand_batch(reads, budgets, 16, lambda b, rd, rc: sorted({int(origin[r, 0]) for r in rd} | {int(v) for v in rng.integers(0, len(clen), 2)}))
+        ohits, obest = oracle.run_tasks(packed, off, clen, B["qcodes"], B["qoff"], B["budget"], B["slot"], B["nreads"], B["tq"], B["tc"], S, mode)
+        ohits = ohits.copy(); ohits["task"] = B["key"][ohits["task"]]
+        ohits = ohits[np.lexsort((ohits["lane"], ohits["task"]))]
+        stream = Engine.pack2(B["rcodes"]) if packed2 else Engine.pack4(B["rcodes"])
+        buf = np.zeros(len(ohits) + 8, HIT_DTYPE); b2 = np.full(B["nreads"], 0xFFFF, np.uint16)
+        n = eng.align_bunches_into(stream, B["rlen"], B["rbudget"], B["strand"], 16, B["cand_off"], B["cand"], buf, b2, mode, packed2=packed2)
+        assert n == len(ohits) and np.array_equal(buf[:n], ohits), (mode, packed2, n, len(ohits))
+        assert np.array_equal(b2, obest)
+        assert n > 250
