@@ -909,6 +909,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 						const uint32_t sb = stg_s + cb * ITEM + l * 16;
 						// the owner's own (serial) verification: IUPAC clumps, lanes with seeds of several queries, a full queue
 						auto own = [&](uint32_t o8, uint32_t o4) {
+							if (o8 | o4) serial = true;                               // its seeds now live in the list: later items of the run must go there too
 							auto word_at = [&](int wl) -> uint32_t { return wl >= 0 ? lds32(sb + (uint32_t)(wl >> 2) * 256 + (uint32_t)(wl & 3) * 4) : (wl == -1 ? iprev : iprev2); };
 							auto verify = [&](uint32_t wi, int e) {
 								const int wl = (int)(wi - cg * NW);
@@ -1310,13 +1311,13 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			#pragma unroll
 			for (int j = 0; j < NW; ++j) if (nonplain_nibbles(win[j] | (j == NW - 1 ? ~TOPMASK & 0x11111111u : 0u))) badrows = WB;
 			for (uint32_t gq0 = 0; gq0 < ngroups && !dead; gq0 += D) {
-			// tighten Emac as better hits land (burst.c:4159, 4220): a value read a round (32 rows) ago is only less tight, never wrong
-			k = min(k, bpre); inf = (k + 1) << 22;
-			if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + slot);
 			#pragma unroll
 			for (int u = 0; u < D; ++u) {
 				const uint32_t gq = gq0 + u;
 				if (gq >= ngroups || dead) break;
+				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
+				k = min(k, bpre); inf = (k + 1) << 22;
+				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + slot);
 				// the words this ring slot will hold in the next round: issued here, first touched D groups later
 				RN[u] = lane_word_or0(lanew, wbase + (int)gq0 + D + 1 + u, nwords); QN[u] = gq0 + D + u < ngroups ? __ldg(Wq + gq0 + D + u) : 0u;
 				const uint32_t feed = __funnelshift_r(R[u], R[u + 1], sh2), qw = Qw[u];
