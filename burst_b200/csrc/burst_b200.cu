@@ -980,8 +980,12 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 										const QWin w = window_of(S, j);
 										if (w.kn == rn && (w.ko & HM) == ro) {
 											const uint32_t q = si / NPM, was = atomicCAS(&ost[owner * 4], NOQ, q);
-											if (was == NOQ || was == q) { atomicMin((int *)&ost[owner * 4 + 1], x1 - (int)w.y1); atomicMax((int *)&ost[owner * 4 + 2], x1 - (int)w.y1); }
-											else ost[owner * 4 + 3] = 1u;                    // a second query on this lane: the owner takes over
+											const int dg = x1 - (int)w.y1, reach = 2 * (int)kq[q] + 1;
+											// one query, seeds within reach of each other = one cluster: it stays in the record; anything else (a second query, a
+											// far diagonal = a second cluster of the lane) goes to the owner, who keeps a proper list
+											if (was == NOQ || (was == q && dg - (int)ost[owner * 4 + 1] <= reach && (int)ost[owner * 4 + 2] - dg <= reach)) {
+												atomicMin((int *)&ost[owner * 4 + 1], dg); atomicMax((int *)&ost[owner * 4 + 2], dg);
+											} else ost[owner * 4 + 3] = 1u;
 										}
 									}
 								}
@@ -1146,11 +1150,13 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 // ---------------------------------------------------------------------------------------------
 // Phase B: exact banded DP with the pass-2 triple.
 // ---------------------------------------------------------------------------------------------
+#define NCLASS 9
 struct ExtendArgs {
 	const uint32_t *dbw; const ClumpMeta *meta;
 	const uint8_t *codes; const uint32_t *qnib; const QInfo *qi; Work W;
 	const Surv *surv; uint32_t surv_cap; const uint32_t *counters;
 	const uint32_t *cls; const uint4 *xs;                // survivors of this launch binned by band class, as expanded records (k_bin_*)
+	uint32_t np_stage[NCLASS], qp_stage;                 // staging slot per thread and class: reference pieces, query word quads (uint4 each; 0 = read global memory)
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
 	uint32_t *scratch; uint32_t scratch_cap;
 	unsigned long long *band_cells;
@@ -1179,7 +1185,6 @@ __device__ __forceinline__ uint32_t lane_word_or0(const uint32_t *lanew, int wi,
 // Band classes: a survivor goes to the narrowest register band that holds its cluster (W = hull of the seed
 // diagonals + 2k); above 64 the band lives in global scratch.  Survivors are binned by class before the sweep
 // (k_bin_*), so that a warp's 32 threads run the same instantiation on 32 survivors.
-#define NCLASS 9
 __host__ __device__ __forceinline__ constexpr int class_width(int c) { return c == 0 ? 5 : c == 1 ? 8 : c == 2 ? 12 : c == 3 ? 16 : c == 4 ? 24 : c == 5 ? 32 : c == 6 ? 48 : c == 7 ? 64 : 0; }
 __device__ __forceinline__ uint32_t class_of(uint32_t W) { return W <= 5 ? 0u : W <= 8 ? 1u : W <= 12 ? 2u : W <= 16 ? 3u : W <= 24 ? 4u : W <= 32 ? 5u : W <= 48 ? 6u : W <= 64 ? 7u : 8u; }
 // cls: [0, NCLASS) counts, [16, 16+NCLASS) first position in `order`, [32, 32+NCLASS) fill cursors
@@ -1239,17 +1244,65 @@ __global__ void k_bin_scatter(const Surv *__restrict__ surv, const uint32_t *__r
 	}
 }
 
+// cp.async (LDGSTS): 16 bytes global -> shared without a register round trip; groups complete in order
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+
+// The sweep of one survivor is ~100 warp instructions, a DRAM round trip is several thousand cycles: a thread that fetched its words when
+// it needed them would idle almost all the time.  So every thread runs a three-deep pipeline over ITS survivors (p, p+S, p+2S, ..):
+// the 48-byte record of survivor p+2S is loading into registers while the reference pieces and packed query words of survivor p+S
+// travel into the thread's second staging slot in shared memory (cp.async), while survivor p is swept out of the first slot.
 template <int WMAX>
 __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	__shared__ uint32_t sS[256];
+	extern __shared__ __align__(16) uint4 xstage[];
 	constexpr int CLS = WMAX == 5 ? 0 : WMAX == 8 ? 1 : WMAX == 12 ? 2 : WMAX == 16 ? 3 : WMAX == 24 ? 4 : WMAX == 32 ? 5 : WMAX == 48 ? 6 : WMAX == 64 ? 7 : 8;
 	const uint32_t begin = A.cls[16 + CLS], count = A.cls[CLS];
 	if (!count) return;
 	for (int i = threadIdx.x; i < 256; i += blockDim.x) sS[i] = A.Sterm[i];
 	__syncthreads();
 	unsigned long long cells = 0;
-	for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
-		const uint4 x0 = __ldg(A.xs + (size_t)(begin + p) * 3), x1 = __ldg(A.xs + (size_t)(begin + p) * 3 + 1), x2 = __ldg(A.xs + (size_t)(begin + p) * 3 + 2);
+	constexpr int WBS = WMAX ? WMAX : 1;
+	const uint32_t NPS = WMAX ? A.np_stage[CLS] : 0u, QPS = NPS ? A.qp_stage : 0u, SLOT = NPS + QPS;       // uint4 per staging slot: reference pieces, query words
+	const uint32_t slot_s = (uint32_t)__cvta_generic_to_shared(xstage) + threadIdx.x * 2 * SLOT * 16;
+	const uint32_t S = gridDim.x * blockDim.x;
+	struct Staged { int c0w, c1w; uint32_t qsh; bool on; };                // staged reference words [c0w, c1w), query words start qsh words into the slot
+	auto load_x = [&](uint32_t p, uint4 (&X)[3]) { X[0] = __ldg(A.xs + (size_t)(begin + p) * 3); X[1] = __ldg(A.xs + (size_t)(begin + p) * 3 + 1); X[2] = __ldg(A.xs + (size_t)(begin + p) * 3 + 2); };
+	auto stage = [&](const uint4 (&X)[3], uint32_t b) -> Staged {
+		Staged T; T.c0w = 0; T.c1w = 0; T.qsh = X[1].w & 3u; T.on = false;
+		if (!SLOT) return T;
+		const int lo = (int)X[0].y, L = (int)X[1].z, m = (int)X[2].x;
+		const int fc = max(lo - 1, 0), lc = min(lo - 1 + m + WBS + 16, L - 1);         // columns (0-based) the sweep can touch
+		const int c0 = fc >> 5, np = lc >= fc ? (lc >> 5) - c0 + 1 : 0;
+		const uint32_t nq4 = (T.qsh + (uint32_t)((m + 7) >> 3) + 3u) >> 2;
+		if ((uint32_t)np > NPS || nq4 > QPS) return T;                                  // does not fit the slot: this survivor reads global memory directly
+		const uint32_t *src = A.dbw + ((uint64_t)X[1].x | ((uint64_t)X[1].y << 32)) * 4 + (X[0].z & 15u) * 4 + (size_t)c0 * 64;
+		const uint32_t dst = slot_s + b * SLOT * 16;
+		for (int j = 0; j < np; ++j) cp_async16(dst + j * 16, src + (size_t)j * 64);
+		const uint32_t *qsrc = A.qnib + (X[1].w & ~3u);
+		for (uint32_t j = 0; j < nq4; ++j) cp_async16(dst + (NPS + j) * 16, qsrc + j * 4);
+		T.c0w = c0 * 4; T.c1w = (c0 + np) * 4; T.on = true;
+		return T;
+	};
+	uint32_t p = blockIdx.x * blockDim.x + threadIdx.x, buf = 0;
+	uint4 X0[3], X1[3], X2[3];
+	bool v0 = p < count, v1 = v0 && p + S < count;
+	Staged T0, T1; T0.on = T1.on = false; T0.c0w = T0.c1w = T1.c0w = T1.c1w = 0; T0.qsh = T1.qsh = 0;
+	if (v0) { load_x(p, X0); T0 = stage(X0, 0); }
+	cp_async_commit();
+	if (v1) load_x(p + S, X1);
+	for (; v0; p += S, buf ^= 1) {
+		if (v1) T1 = stage(X1, buf ^ 1);
+		cp_async_commit();
+		const bool v2 = v1 && p + 2 * S < count;
+		if (v2) load_x(p + 2 * S, X2);
+		cp_async_wait1();                                                  // everything but the newest group has landed: this survivor's slot is ready
+		const uint4 x0 = X0[0], x1 = X0[1], x2 = X0[2];
+		const Staged T = T0;
+		const uint32_t ref_s = slot_s + buf * SLOT * 16, q_s = ref_s + NPS * 16 + T.qsh * 4;
+		// rotate the pipeline registers now: the body below ends in `continue` on some paths
+		X0[0] = X1[0]; X0[1] = X1[1]; X0[2] = X1[2]; X1[0] = X2[0]; X1[1] = X2[1]; X1[2] = X2[2]; T0 = T1; v0 = v1; v1 = v2;
 		Surv sv; sv.task = x0.x; sv.lo = (int32_t)x0.y; sv.w_lane = x0.z; sv.scratch = x0.w;
 		const uint32_t i = x2.w;
 		const uint32_t W = sv.w_lane >> 8, lane = sv.w_lane & 15;
@@ -1270,13 +1323,19 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 
 		if (WMAX) {
 			// The band slides one column per row, so row y needs exactly one new reference code (column y+lo+WB-1)
-			// and one query code: both are streamed as packed words, one 32-bit load of each per 8 rows
-			// (the query from its nibble-packed copy, the lane from the DB pieces), loaded one group ahead.
+			// and one query code: both are streamed as packed words, one 32-bit read of each per 8 rows
+			// (the query from its nibble-packed copy, the lane from the DB pieces), out of the staging slot.
 			constexpr int NW = (WB + 7) / 8;
 			constexpr uint32_t TOPMASK = (WB & 7) ? (1u << (4 * (WB & 7))) - 1u : 0xFFFFFFFFu;   // nibbles of the last window word inside the band
 			uint32_t win[NW];                                // codes of columns x0 .. x0+WB-1, one nibble each
 			const int nwords = (int)((L + 7) >> 3);
 			const uint32_t *Wq = A.qnib + x1.w;
+			// word wi of the lane (0 outside the clump) / packed word g of the query
+			auto refw = [&](int wi) -> uint32_t {
+				if (T.on) return (wi >= T.c0w && wi < T.c1w) ? lds32(ref_s + (uint32_t)(wi - T.c0w) * 4) : 0u;
+				return lane_word_or0(lanew, wi, nwords);
+			};
+			auto qwd = [&](uint32_t gg) -> uint32_t { return T.on ? lds32(q_s + gg * 4) : __ldg(Wq + gg); };
 			// row 0: zero for columns 0..L (burst.c:4052 calloc / 723-725), absent elsewhere
 			#pragma unroll
 			for (int d = 0; d < WB; ++d) { const int x = lo + d; a[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
@@ -1284,25 +1343,17 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			int cb = lo - 1;                                 // 0-based column index of the window's first nibble
 			const uint32_t sh = (uint32_t)(cb & 7) * 4;
 			int wi = cb >> 3;                                // arithmetic shift: floor for negative columns too
-			uint32_t w0 = lane_word_or0(lanew, wi, nwords);
+			uint32_t w0 = refw(wi);
 			#pragma unroll
-			for (int j = 0; j < NW; ++j) { const uint32_t w1 = lane_word_or0(lanew, ++wi, nwords); win[j] = __funnelshift_r(w0, w1, sh); w0 = w1; }
+			for (int j = 0; j < NW; ++j) { const uint32_t w1 = refw(++wi); win[j] = __funnelshift_r(w0, w1, sh); w0 = w1; }
 			// the codes that enter the window in rows 8g+1 .. 8g+8 are nibbles cb+WB+8g .. : the word pair (w0, w1) shifted by sh2
 			constexpr int EXTRA = (NW * 8 - WB);             // nibbles of the last window word beyond the band: they are the first to enter
 			const uint32_t sh2 = (uint32_t)((cb + WB) & 7) * 4;
-			if (EXTRA) { wi = (cb + WB) >> 3; w0 = lane_word_or0(lanew, wi, nwords); }
+			if (EXTRA) { wi = (cb + WB) >> 3; w0 = refw(wi); }
 			win[NW - 1] &= TOPMASK;
-			// Group g (rows 8g+1 .. 8g+8) needs the reference words wbase+g, wbase+g+1 and the query word g.  They are kept in small rings and
-			// fetched D+1 groups ahead: the sweep of a group is ~70 instructions, far less than a DRAM round trip.
-			constexpr int D = 4;
-			const int wbase = wi;
-			uint32_t R[D + 1], Qw[D], RN[D], QN[D];
+			const int wbase = wi;                            // group g (rows 8g+1 .. 8g+8) needs the reference words wbase+g, wbase+g+1 and the query word g
 			const uint32_t ngroups = (m + 7) >> 3;
-			#pragma unroll
-			for (int u = 0; u <= D; ++u) R[u] = u == 0 ? w0 : lane_word_or0(lanew, wbase + u, nwords);
-			#pragma unroll
-			for (int u = 0; u < D; ++u) { Qw[u] = (uint32_t)u < ngroups ? __ldg(Wq + u) : 0u; RN[u] = 0; QN[u] = 0; }
-			uint32_t bpre = k;                               // the slot's running minimum, fetched one round (4 groups) before it is applied
+			uint32_t bpre = k;                               // the slot's running minimum, fetched one group (8 rows) before it is applied
 			// Fast rows: query and reference codes all plain bases, band inside the matrix, short query.  Then the substitution cost is
 			// "the nibbles differ" (one XOR per row, no table), and cells above the budget need no clamp: they can never win or tie a
 			// cell within it, and with m + WB < 480 no field of the key can overflow.
@@ -1310,17 +1361,13 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			int badrows = 0;                                 // rows during which the window may still hold a code that is not a plain base
 			#pragma unroll
 			for (int j = 0; j < NW; ++j) if (nonplain_nibbles(win[j] | (j == NW - 1 ? ~TOPMASK & 0x11111111u : 0u))) badrows = WB;
-			for (uint32_t gq0 = 0; gq0 < ngroups && !dead; gq0 += D) {
-			#pragma unroll
-			for (int u = 0; u < D; ++u) {
-				const uint32_t gq = gq0 + u;
-				if (gq >= ngroups || dead) break;
+			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
 				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
 				k = min(k, bpre); inf = (k + 1) << 22;
-				if (A.mode == BG_MODE_MIN) bpre = __ldcg(A.best + slot);
-				// the words this ring slot will hold in the next round: issued here, first touched D groups later
-				RN[u] = lane_word_or0(lanew, wbase + (int)gq0 + D + 1 + u, nwords); QN[u] = gq0 + D + u < ngroups ? __ldg(Wq + gq0 + D + u) : 0u;
-				const uint32_t feed = __funnelshift_r(R[u], R[u + 1], sh2), qw = Qw[u];
+				if (A.mode == BG_MODE_MIN && (gq & 3) == 0) bpre = __ldcg(A.best + slot);
+				const uint32_t w1 = refw(wbase + (int)gq + 1);
+				const uint32_t feed = __funnelshift_r(w0, w1, sh2), qw = qwd(gq);
+				w0 = w1;
 				const int x0g = (int)y + lo;                 // column (1-based) of band cell 0 in the first row of the group
 				if (nonplain_nibbles(feed)) badrows = WB + 8;
 				const bool fast = fastok && badrows == 0 && y + 7 <= m && x0g >= 1 && x0g + 7 + WB - 1 <= (int)L;
@@ -1391,10 +1438,6 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 					++y;
 				}
 				}
-			}
-			R[0] = R[D];
-			#pragma unroll
-			for (int u = 0; u < D; ++u) { R[u + 1] = RN[u]; Qw[u] = QN[u]; }
 			}
 			if (!dead) y = m + 1;
 		} else {
@@ -1637,6 +1680,7 @@ struct bg_ctx {
 	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
 	int seed_impl = 1, seed_nch = 8, seed_lbits = 0, seed_fb = 1;   // seed_fb: filter bits per window (1 or 2)
 	int _pad0 = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
+	uint32_t mstage = 0;                                          // longest query the k_extend staging slots are sized for (from the batch's lengths)
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
 	bool seed_ok = true; uint32_t amb_add = 0x22222222u, m16[8];   // derived from the scoring table
 	// scoring
@@ -1878,6 +1922,9 @@ static int copy_codes(const bg_queries *Q, uint64_t b0, uint64_t b1, DBuf<uint8_
 }
 
 // queries -> device, QInfo + tables
+// query length the k_extend staging slots are sized for, from the longest of a sample of the batch (a longer query still works: it reads global memory)
+static uint32_t stage_len(uint64_t sampled_max) { return (uint32_t)std::min<uint64_t>(2048, ((sampled_max + 31) & ~31ull) + 32); }
+
 static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	if (!c->num_clumps) return fail(BG_EINVAL, "bg_batch_upload: no database loaded");
 	if (!Q->nq) return fail(BG_EINVAL, "bg_batch_upload: empty query batch");
@@ -1903,6 +1950,7 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 			(unsigned long long)(Q->offset[q + 1] - Q->offset[q]), Q->budget[q], Q->slot[q], Q->nslots);
 	}
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
+	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nq / 8192); for (uint32_t q = 0; q < nq; q += stp) mx = std::max<uint64_t>(mx, Q->offset[q + 1] - Q->offset[q]); c->mstage = stage_len(mx); }
 	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
 	CU(cudaGetLastError());
@@ -2074,16 +2122,22 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.cls = c->d_cls.p; E.xs = c->d_xs.p; E.res = c->d_res.p;
 	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
 	E.band_cells = c->d_cells.p; E.mode = mode;
-	const unsigned g = (unsigned)c->sms * 12;
-	k_extend<5><<<g, 128, 0, st>>>(E);
-	k_extend<8><<<g, 128, 0, st>>>(E);
-	k_extend<12><<<g, 128, 0, st>>>(E);
-	k_extend<16><<<g, 128, 0, st>>>(E);
-	k_extend<24><<<g, 128, 0, st>>>(E);
-	k_extend<32><<<g, 128, 0, st>>>(E);
-	k_extend<48><<<g / 2, 128, 0, st>>>(E);
-	k_extend<64><<<g / 2, 128, 0, st>>>(E);
-	k_extend<0><<<g / 2, 128, 0, st>>>(E);
+	// staging slot of a thread: the reference pieces and packed query words of one survivor of up to `mstage` bases (longer ones read
+	// global memory directly); two slots per thread, 128 threads per block
+	const uint32_t ms = c->mstage ? c->mstage : 128;
+	E.qp_stage = ((ms + 7) / 8 + 3 + 3) / 4;
+	size_t smem[NCLASS]; unsigned grid[NCLASS];
+	for (int k = 0; k < NCLASS; ++k) {
+		const int wb = class_width(k);
+		E.np_stage[k] = wb ? (ms + wb + 17 + 31) / 32 + 1 : 0;
+		smem[k] = wb ? (size_t)128 * 2 * (E.np_stage[k] + E.qp_stage) * 16 : 0;
+		if (smem[k] > 100 * 1024) { E.np_stage[k] = 0; smem[k] = 0; }            // too long for staging: direct reads
+		grid[k] = (unsigned)c->sms * (wb && wb <= 32 ? 12 : 6);
+	}
+	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 48 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K])); \
+		k_extend<WM><<<grid[K], 128, smem[K], st>>>(E); } while (0)
+	EXT_LAUNCH(5, 0); EXT_LAUNCH(8, 1); EXT_LAUNCH(12, 2); EXT_LAUNCH(16, 3); EXT_LAUNCH(24, 4); EXT_LAUNCH(32, 5); EXT_LAUNCH(48, 6); EXT_LAUNCH(64, 7); EXT_LAUNCH(0, 8);
+	#undef EXT_LAUNCH
 	CU(cudaGetLastError());
 	return BG_OK;
 }
@@ -2246,11 +2300,13 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t npmax = 1;
 	{
 		uint32_t hist[32]; memset(hist, 0, sizeof(hist));
-		const uint32_t step = std::max<uint32_t>(1, nq / 8192); uint32_t ns = 0;
+		const uint32_t step = std::max<uint32_t>(1, nq / 8192); uint32_t ns = 0; uint64_t mxlen = 0;
 		for (uint32_t q = 0; q < nq; q += step, ++ns) {
 			const uint64_t len = Q->offset[q + 1] - Q->offset[q]; const uint32_t np = Q->budget[q] + 1u;
 			if (np <= SEED_NP_MAX) ++hist[std::min<uint64_t>(len / np, 31)];
+			mxlen = std::max(mxlen, len);
 		}
+		c->mstage = stage_len(mxlen);
 		SL = choose_layout(c, hist, ns);
 		if (SL.stride) {
 			uint64_t sum = 0, cnt = 0; uint32_t mx = 1;
@@ -2436,6 +2492,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	CU(cudaStreamSynchronize(st));
 	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_align_bunches_into: malformed batch (read lengths >= 1, budgets <= 254 (burst.c:3076), ascending candidate offsets)");
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
+	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nr / 8192); for (uint32_t r = 0; r < nr; r += stp) mx = std::max<uint64_t>(mx, R->len[r]); c->mstage = stage_len(mx); }
 	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, st>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
 	CU(cudaGetLastError());
