@@ -983,7 +983,8 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 											const int dg = x1 - (int)w.y1, reach = 2 * (int)kq[q] + 1;
 											// one query, seeds within reach of each other = one cluster: it stays in the record; anything else (a second query, a
 											// far diagonal = a second cluster of the lane) goes to the owner, who keeps a proper list
-											if (was == NOQ || (was == q && dg - (int)ost[owner * 4 + 1] <= reach && (int)ost[owner * 4 + 2] - dg <= reach)) {
+											const int clo = (int)ost[owner * 4 + 1], chi = (int)ost[owner * 4 + 2];       // (still at their initial values if the lane's first match is being recorded right now)
+											if (was == NOQ || (was == q && (clo == 0x7FFFFFFF || dg - clo <= reach) && (chi == (int)0x80000000 || chi - dg <= reach))) {
 												atomicMin((int *)&ost[owner * 4 + 1], dg); atomicMax((int *)&ost[owner * 4 + 2], dg);
 											} else ost[owner * 4 + 3] = 1u;
 										}
@@ -1248,6 +1249,7 @@ __global__ void k_bin_scatter(const Surv *__restrict__ surv, const uint32_t *__r
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(dst), "l"(src) : "memory"); }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // The sweep of one survivor is ~100 warp instructions, a DRAM round trip is several thousand cycles: a thread that fetched its words when
 // it needed them would idle almost all the time.  So every thread runs a three-deep pipeline over ITS survivors (p, p+S, p+2S, ..):
@@ -1297,7 +1299,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		cp_async_commit();
 		const bool v2 = v1 && p + 2 * S < count;
 		if (v2) load_x(p + 2 * S, X2);
-		cp_async_wait1();                                                  // everything but the newest group has landed: this survivor's slot is ready
+		if (v1) cp_async_wait1(); else cp_async_wait0();                   // everything but the group just issued has landed: this survivor's slot is ready (an empty newest group completes at once and does not count)
 		const uint4 x0 = X0[0], x1 = X0[1], x2 = X0[2];
 		const Staged T = T0;
 		const uint32_t ref_s = slot_s + buf * SLOT * 16, q_s = ref_s + NPS * 16 + T.qsh * 4;

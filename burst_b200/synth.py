@@ -246,9 +246,12 @@ def bunch_workload(n_reads, read_len, n_err, db_bytes, clump_len, seed, qbunch=1
     runs["clump"] = cand; runs["query0"] = qstart; runs["nq"] = qcount
     if budget is None:
         budget = np.full(nq, n_err, np.uint16)
+    # the compact form of the same batch (bg_align_bunches_into): reads as sequenced, strand = read | rc << 31 in sorted order
+    strand = (sread[order].astype(np.uint32) | ((order >= n_reads).astype(np.uint32) << 31)).astype(np.uint32)
     return dict(packed=packed, clump_off=coff, clump_len=clens, qcodes=qcodes, qoff=qoff, slot=slot,
                 nslots=n_reads, budget=budget, tasks=tasks, runs=runs, cand_off=cand_off, cand=cand, qbunch=qbunch,
-                true_clump=clump, true_lane=lane, true_start=start, n_reads=n_reads, match=match)
+                true_clump=clump, true_lane=lane, true_start=start, n_reads=n_reads, match=match,
+                rcodes=codes, rlen=lens.astype(np.uint16), strand=strand)
 
 
 def random_clumps_fast(nclumps, clump_len, rng):
