@@ -46,7 +46,12 @@ def parse():
     ap.add_argument("--clump-len", type=int, default=214)
     ap.add_argument("--cpu-sample-bunches", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    return ap.parse_args()
+    ap.add_argument("--config", default="c2", choices=["c2", "target"],
+                    help="c2 (default, the headline): BASELINE.json configs[1], 1 M reads vs a 2 GB DB; target: north_star's 10 M x 100 bp vs a 31.5 GB .edx on one B200")
+    a = ap.parse_args()
+    if a.config == "target":
+        a.reads, a.db_mb = 10_000_000, 32256
+    return a
 
 
 PARITY_SAMPLE_MOD = 64        # the CPU reference also records the kept lanes of every 64th read, for the bench-size parity check
@@ -208,7 +213,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": "configs[1]: %d x %d bp reads (exactly %d edits, LLsim model, fwd+rc strands) per GPU vs %d MB synthetic .edx-layout DB (%d-column clumps), -i 0.98 budget %d, BEST-style min selection, task list = reference bunch driver (QBUNCH 16 x bunch candidates)" % (
+    config = {"workload": ("north_star target: " if args.config == "target" else "configs[1]: ") + "%d x %d bp reads (exactly %d edits, LLsim model, fwd+rc strands) per GPU vs %d MB synthetic .edx-layout DB (%d-column clumps), -i 0.98 budget %d, BEST-style min selection, task list = reference bunch driver (QBUNCH 16 x bunch candidates)" % (
         args.reads, args.read_len, args.edits, args.db_mb, args.clump_len, args.edits),
         "reads_per_gpu": args.reads, "db_mb": args.db_mb, "sharding": "queries (DB replicated), no data-path collective", "numa_node_rank0": None,
         "l2": "inputs (DB %d MB + tasks) exceed the 126 MB L2; no explicit flush" % args.db_mb}

@@ -952,6 +952,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 							// ---- enqueue ----
 							if (lane == 0) *hqn = 0;
 							__syncwarp();
+							const uint4 before = *(const uint4 *)(ost + lane * 4);
 							uint32_t pos = cnt ? atomicAdd(hqn, cnt) : 0u;
 							while (m8 | m4) {
 								const uint32_t b = 31 - __clz(m8 | m4), bit = 1u << b;
@@ -980,19 +981,24 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 										const QWin w = window_of(S, j);
 										if (w.kn == rn && (w.ko & HM) == ro) {
 											const uint32_t q = si / NPM, was = atomicCAS(&ost[owner * 4], NOQ, q);
-											const int dg = x1 - (int)w.y1, reach = 2 * (int)kq[q] + 1;
-											// one query, seeds within reach of each other = one cluster: it stays in the record; anything else (a second query, a
-											// far diagonal = a second cluster of the lane) goes to the owner, who keeps a proper list
-											const int clo = (int)ost[owner * 4 + 1], chi = (int)ost[owner * 4 + 2];       // (still at their initial values if the lane's first match is being recorded right now)
-											if (was == NOQ || (was == q && (clo == 0x7FFFFFFF || dg - clo <= reach) && (chi == (int)0x80000000 || chi - dg <= reach))) {
-												atomicMin((int *)&ost[owner * 4 + 1], dg); atomicMax((int *)&ost[owner * 4 + 2], dg);
-											} else ost[owner * 4 + 3] = 1u;
+											const int dg = x1 - (int)w.y1;
+											if (was == NOQ || was == q) { atomicMin((int *)&ost[owner * 4 + 1], dg); atomicMax((int *)&ost[owner * 4 + 2], dg); }
+											else ost[owner * 4 + 3] = 1u;                    // a second query on this lane: the owner takes over
 										}
 									}
 								}
 							}
 							__syncwarp();
-							if (ost[lane * 4 + 3]) { ost[lane * 4 + 3] = 0u; serial = true; own(s8, s4); }
+							// A record stays ONE cluster of ONE query: if the helpers met a second query, or seeds of this item lie out of reach
+							// (2k+1 diagonals) of the cluster, the owner puts the record back as it was before the item and redoes the item itself,
+							// into a proper list (far seeds = separate clusters, each its own narrow band in k_extend)
+							if (cnt) {
+								const uint4 now = *(const uint4 *)(ost + lane * 4);
+								if (now.w || (now.x != NOQ && (int)now.z - (int)now.y > 2 * (int)kq[now.x] + 1)) {
+									*(uint4 *)(ost + lane * 4) = before;
+									own(s8, s4);
+								}
+							}
 						}
 					}
 					if (C.valid) {
@@ -1706,7 +1712,7 @@ struct bg_ctx {
 	uint32_t nq = 0, nslots = 0, ntiles = 0; uint64_t nruns = 0, ntasks = 0;
 	std::vector<uint32_t> task0;                                  // WORK_TASKS: first task index of each run
 	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t nseed = 0;    // queries taken by k_seed
-	uint32_t surv_cap = 0;
+	uint32_t surv_cap = 0; bool surv_cap_forced = false;
 	int last_mode = 0; std::vector<uint16_t> last_best_in; bool have_best_in = false;
 	bg_stats stats;
 	cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -1972,6 +1978,7 @@ static int finish_upload(bg_ctx *c) {
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
 	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
 	want = std::max<uint64_t>(want, 1024);
+	if (c->surv_cap_forced) { want = c->surv_cap; c->surv_cap_forced = false; }      // (bg_set_surv_cap: the next batch starts from exactly that size)
 	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
 	if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 	if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
@@ -2127,13 +2134,14 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 	// staging slot of a thread: the reference pieces and packed query words of one survivor of up to `mstage` bases (longer ones read
 	// global memory directly); two slots per thread, 128 threads per block
 	const uint32_t ms = c->mstage ? c->mstage : 128;
+	static const bool no_stage = getenv("BURST_B200_EXT_STAGE") && atoi(getenv("BURST_B200_EXT_STAGE")) == 0;   // debugging: sweep straight out of global memory
 	E.qp_stage = ((ms + 7) / 8 + 3 + 3) / 4;
 	size_t smem[NCLASS]; unsigned grid[NCLASS];
 	for (int k = 0; k < NCLASS; ++k) {
 		const int wb = class_width(k);
 		E.np_stage[k] = wb ? (ms + wb + 17 + 31) / 32 + 1 : 0;
 		smem[k] = wb ? (size_t)128 * 2 * (E.np_stage[k] + E.qp_stage) * 16 : 0;
-		if (smem[k] > 100 * 1024) { E.np_stage[k] = 0; smem[k] = 0; }            // too long for staging: direct reads
+		if (smem[k] > 100 * 1024 || no_stage) { E.np_stage[k] = 0; smem[k] = 0; }            // too long for staging: direct reads
 		grid[k] = (unsigned)c->sms * (wb && wb <= 32 ? 12 : 6);
 	}
 	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 48 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K])); \
@@ -2173,11 +2181,32 @@ static int run_select(bg_ctx *c, int mode) {
 	return BG_OK;
 }
 
+// The split form hands the per-slot minima to an external all-reduce before the selection: they must be final when this returns.
+// A survivor list (or band scratch) that overflowed would leave them computed from a truncated list, so the overflow is settled
+// HERE -- grow, redo filter + extend -- and not at download time as in the one-call form.
 extern "C" int bg_batch_run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	if (!c || c->kind == WORK_NONE) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
-	return run_extend(c, mode, best_in);
+	for (int attempt = 0; attempt < 5; ++attempt) {
+		int rc = run_extend(c, mode, best_in); if (rc) return rc;
+		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		const bool grow_s = c->h_pinned[C_SURV] > c->surv_cap, grow_g = c->h_pinned[C_SCRATCH] > c->d_scratch.cap;
+		if (!grow_s && !grow_g) return BG_OK;
+		if (grow_s) {
+			c->surv_cap = c->h_pinned[C_SURV] + c->h_pinned[C_SURV] / 4;
+			if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+		}
+		if (grow_g && c->d_scratch.need((size_t)c->h_pinned[C_SCRATCH] + 1024)) return BG_ENOMEM;
+	}
+	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_pinned[C_SURV]);
 }
 extern "C" void *bg_batch_best_device(bg_ctx *c) { return c ? (void *)c->d_best.p : nullptr; }
+extern "C" void *bg_stream(bg_ctx *c) { return c ? (void *)c->stream : nullptr; }
+extern "C" int bg_set_surv_cap(bg_ctx *c, uint32_t cap) {              // tests: start from a tiny survivor list to exercise the grow-and-redo paths
+	if (!c || cap < 16) return fail(BG_EINVAL, "bg_set_surv_cap: null ctx or cap < 16");
+	c->d_surv.release(); c->surv_cap = cap; c->surv_cap_forced = true;
+	return BG_OK;
+}
 extern "C" int bg_batch_run_select(bg_ctx *c, int mode) {
 	if (!c || c->kind == WORK_NONE) return fail(BG_EINVAL, "bg_batch_run: no batch uploaded");
 	return run_select(c, mode);

@@ -48,7 +48,7 @@ EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scori
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
            "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into",
-           "bg_host_alloc", "bg_host_free", "bg_align_bunches_into"]
+           "bg_host_alloc", "bg_host_free", "bg_align_bunches_into", "bg_stream", "bg_set_surv_cap"]
 
 
 def load_library(path=None):
@@ -88,6 +88,9 @@ def load_library(path=None):
     L.bg_align_bunches_into.argtypes = [C.c_void_p, C.POINTER(BgReads), C.c_uint32, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int,
                                         C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.bg_host_alloc.restype = C.c_void_p
+    L.bg_stream.restype = C.c_void_p
+    L.bg_stream.argtypes = [C.c_void_p]
+    L.bg_set_surv_cap.argtypes = [C.c_void_p, C.c_uint32]
     L.bg_host_alloc.argtypes = [C.c_uint64]
     L.bg_host_free.argtypes = [C.c_void_p]
     return L
@@ -218,6 +221,9 @@ class Engine:
     def run_extend(self, mode=MODE_MIN, best_in=None):
         b = None if best_in is None else np.ascontiguousarray(best_in, np.uint16)
         self._check(self.lib.bg_batch_run_extend(self.ctx, mode, None if b is None else b.ctypes.data))
+
+    def set_surv_cap(self, cap):
+        self._check(self.lib.bg_set_surv_cap(self.ctx, cap))
 
     def best_device_ptr(self):
         return self.lib.bg_batch_best_device(self.ctx)

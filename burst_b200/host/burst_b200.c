@@ -26,6 +26,10 @@
 #include <omp.h>
 #endif
 #include "burst_b200.h"
+#ifdef BURST_NCCL
+#include <cuda_runtime_api.h>
+#include <nccl.h>
+#endif
 
 #define VER "v1.0-b200"
 #define VECSZ 16
@@ -42,7 +46,7 @@ static long REBASE_AMT = 500, DB_QLEN = 500; static int REBASE = 0, ACX_N = 12; 
 static float TAXLEVELS_STRICT[] = {.65f, .75f, .78f, .82f, .86f, .94f, .98f, .995f},
              TAXLEVELS_LENIENT[] = {.55f, .70f, .75f, .80f, .84f, .93f, .97f, .985f},   /* burst.c:264-266 */
              *TAXLEVELS = TAXLEVELS_LENIENT;
-static int QUIET = 0, GPU_DEVICE = 0, NGPU = 1, THREADS = 1;
+static int QUIET = 0, GPU_DEVICE = 0, NGPU = 1, THREADS = 1, SHARD_REFS = 0;
 
 static uint8_t CHAR2NUM[256];
 static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};   /* burst.c:168 */
@@ -900,6 +904,139 @@ static void accel_search(bg_ctx **ctxs, int ngpu, Queries *Q, Refs *R, Acx *A, P
 	free(best); free(GS); free(BT); free(SPods);
 }
 
+#ifdef BURST_NCCL
+/* =============================================================================================
+ * Reference sharding (--shard-refs): the .edx does not fit one GPU, so GPU g holds the clump range
+ * [lo_g, hi_g); every GPU sees every batch and skips the runs of foreign clumps.  Per batch: filter + extend on every
+ * GPU, then ONE collective -- ncclAllReduce(MIN) over the per-read minima (uint32 x numUniqQ, on each engine's own
+ * stream, no host synchronisation in between) -- then the selection against the combined minima: exactly the rule by
+ * which the reference merges its thread pods (burst.c:4490-4519).  FORAGE keeps every lane within budget and needs no
+ * collective.  One host thread per GPU; the all-reduce is NCCL over NVLink.
+ * ============================================================================================= */
+static int cmp_hit(const void *a, const void *b) {
+	const bg_hit *A = a, *B = b;
+	if (A->task != B->task) return A->task < B->task ? -1 : 1;
+	return (int)A->lane - (int)B->lane;
+}
+static void accel_search_sharded(bg_ctx **ctxs, int ngpu, Queries *Q, Refs *R, Acx *A, PodList *Pods, int mode, int threads) {
+	uint64_t nAcc = Q->QBins[1], newUniqQ = Q->newUniqQ;
+	if (!nAcc) return;
+	uint64_t QBUNCH = newUniqQ / ((uint64_t)threads * 128);
+	if (QBUNCH > 16) QBUNCH = 16;
+	if (!QBUNCH) QBUNCH = 1;
+	printf("Setting QBUNCH to %" PRIu64 "\nUsing ACCELERATOR to align %" PRIu64 " unique queries on %d reference shards...\n", QBUNCH, nAcc, ngpu);
+	ncclComm_t comms[64]; int devs[64];
+	for (int g = 0; g < ngpu; ++g) devs[g] = GPU_DEVICE + g;
+	if (ncclCommInitAll(comms, ngpu, devs) != ncclSuccess) { fputs("ERROR: ncclCommInitAll failed\n", stderr); exit(4); }
+	const uint32_t numRclumps = R->numRclumps;
+	const uint64_t nbunch = (nAcc + QBUNCH - 1) / QBUNCH;
+	uint64_t bpb = 65536;
+	const uint64_t nbatch = (nbunch + bpb - 1) / bpb;
+	int nthr = threads < ngpu ? ngpu : threads;
+	GenScratch *GS = xcalloc((size_t)nthr, sizeof(*GS));
+	for (int t = 0; t < nthr; ++t) {
+		GS[t].Hash = xcalloc(numRclumps, sizeof(uint16_t)); GS[t].Cache = xmalloc(((uint64_t)numRclumps + 1) * 4);
+		GS[t].Cand = xmalloc(((uint64_t)numRclumps + 1) * sizeof(Split)); GS[t].wcap = 1 << 16; GS[t].W = xmalloc(GS[t].wcap * 8);
+	}
+	uint16_t *best = xmalloc(Q->numUniqQ * sizeof(*best));
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[i] = 0xFFFF;
+	PodList *SPods = xcalloc(newUniqQ, sizeof(*SPods));
+	Batch B; memset(&B, 0, sizeof(B));
+	bg_hit **H = xcalloc((size_t)ngpu, sizeof(*H)); uint64_t *NH = xcalloc((size_t)ngpu, sizeof(*NH));
+	int failed = 0; double t_all = 0, t_gen = 0;
+	for (uint64_t bi = 0; bi < nbatch; ++bi) {
+		uint64_t b0 = bi * bpb, b1 = MIN(nbunch, b0 + bpb);
+		B.nbunch = b1 - b0; B.qa = b0 * QBUNCH; B.qb = MIN(nAcc, b1 * QBUNCH);
+		B.br = xrealloc(B.br, B.nbunch * sizeof(BunchRuns));
+		for (int t = 0; t < nthr; ++t) GS[t].runs.n = 0;
+		double t0 = now();
+		#pragma omp parallel for schedule(dynamic, 16) num_threads(nthr)
+		for (uint64_t b = b0; b < b1; ++b) {
+			int tid = 0;
+#ifdef _OPENMP
+			tid = omp_get_thread_num();
+#endif
+			GenScratch *S = GS + tid; uint64_t before = S->runs.n;
+			gen_bunch(Q, A, numRclumps, S, b * QBUNCH, MIN(nAcc, (b + 1) * QBUNCH), B.qa);
+			B.br[b - b0] = (BunchRuns){(uint32_t)tid, before, S->runs.n - before};
+		}
+		uint64_t tot = 0, nc = 0, o = 0;
+		for (uint64_t b = 0; b < B.nbunch; ++b) tot += B.br[b].n;
+		for (uint64_t j = B.qa; j < B.qb; ++j) nc += Q->ShrBins[Q->UniBins[j].six].len;
+		batch_room(&B, B.qb - B.qa, nc, tot);
+		for (uint64_t b = 0; b < B.nbunch; ++b) { memcpy(B.runs + o, GS[B.br[b].tid].runs.r + B.br[b].off, B.br[b].n * sizeof(bg_run)); o += B.br[b].n; }
+		B.nruns = tot;
+		batch_pack_queries(Q, &B);
+		double t1 = now(); t_gen += t1 - t0;
+		uint64_t nq = B.qb - B.qa;
+		bg_queries bq = {B.codes, B.off, B.bud, B.slot, (uint32_t)nq, (uint32_t)Q->numUniqQ, BG_Q_PACKED4};
+		uint16_t *best_out = xmalloc(Q->numUniqQ * sizeof(*best_out));
+		#pragma omp parallel num_threads(ngpu)
+		{
+			int g = 0;
+#ifdef _OPENMP
+			g = omp_get_thread_num();
+#endif
+			int rc = B.nruns ? bg_batch_upload_runs(ctxs[g], &bq, B.runs, B.nruns) : BG_OK;
+			if (!rc && B.nruns) rc = bg_batch_run_extend(ctxs[g], mode, best);
+			if (rc) {
+				#pragma omp critical
+				{ failed = rc; fprintf(stderr, "ERROR: GPU engine failed on shard %d: %s\n", g, bg_last_error()); }
+			}
+			#pragma omp barrier
+			if (!failed && B.nruns) {
+				if (mode == BG_MODE_MIN && ncclAllReduce(bg_batch_best_device(ctxs[g]), bg_batch_best_device(ctxs[g]), Q->numUniqQ, ncclUint32, ncclMin, comms[g], (cudaStream_t)bg_stream(ctxs[g])) != ncclSuccess) {
+					#pragma omp critical
+					{ failed = 4; fprintf(stderr, "ERROR: ncclAllReduce failed on shard %d\n", g); }
+				}
+				uint64_t n = 0;
+				if (!failed) rc = bg_batch_run_select(ctxs[g], mode);
+				if (!failed && !rc) rc = bg_batch_count(ctxs[g], &n);
+				if (!failed && !rc) { H[g] = xrealloc(H[g], (n + 1) * sizeof(bg_hit)); rc = bg_batch_download(ctxs[g], H[g], n, g == 0 ? best_out : NULL); NH[g] = n; }
+				if (rc) {
+					#pragma omp critical
+					{ failed = rc; fprintf(stderr, "ERROR: GPU engine failed on shard %d: %s\n", g, bg_last_error()); }
+				}
+			} else NH[g] = 0;
+		}
+		if (failed) exit(failed == BG_ENOMEM ? 3 : 4);
+		if (B.nruns) {
+			if (mode == BG_MODE_MIN) memcpy(best, best_out, Q->numUniqQ * sizeof(*best));
+			else for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[i] = MIN(best[i], best_out[i]);
+			uint64_t nh = 0;
+			for (int g = 0; g < ngpu; ++g) nh += NH[g];
+			bg_hit *all = xmalloc((nh + 1) * sizeof(bg_hit)); nh = 0;
+			for (int g = 0; g < ngpu; ++g) { memcpy(all + nh, H[g], NH[g] * sizeof(bg_hit)); nh += NH[g]; }
+			qsort(all, nh, sizeof(bg_hit), cmp_hit);                       /* a run lives on one shard only: (task, lane) order = discovery order */
+			for (uint64_t h = 0; h < nh; ++h) {
+				const bg_run *r = B.runs + (all[h].task >> 4);
+				const UniBin *u = Q->UniBins + B.qa + r->query0 + (all[h].task & 15); const ShrBin *sb = Q->ShrBins + u->six;
+				uint32_t refIx = r->clump * VECSZ + all[h].lane;
+				if (refIx >= R->totR) continue;
+				Pod p = {identity(all[h].ed, sb->len, all[h].gap_q), refIx, all[h].final_pos, all[h].gap_r, all[h].gap_q, all[h].ed, u->rc};
+				pod_push(SPods + u->six + (u->rc ? Q->numUniqQ : 0), p);
+			}
+			free(all);
+		}
+		free(best_out);
+		t_all += now() - t1;
+		if (!QUIET) printf("\rSearch Progress: [%3.2f%%]", 100.0 * (double)(bi + 1) / (double)nbatch);
+	}
+	if (!QUIET) printf("\rSearch Progress: [100.00%%]\n");
+	printf(" --> [Accel] %" PRIu64 " batches on %d reference shards: candidate generation %.3f s, align + all-reduce(MIN) + select %.3f s\n", nbatch, ngpu, t_gen, t_all);
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *F = SPods + i, *Rc = Q->rc ? SPods + Q->numUniqQ + i : NULL;
+		if (Rc) for (uint32_t k = 0; k < Rc->n; ++k) if (mode != BG_MODE_MIN || Rc->p[k].mismatches <= best[i]) pod_push(Pods + i, Rc->p[k]);
+		for (uint32_t k = 0; k < F->n; ++k) if (mode != BG_MODE_MIN || F->p[k].mismatches <= best[i]) pod_push(Pods + i, F->p[k]);
+		free(F->p); if (Rc) free(Rc->p);
+	}
+	for (int t = 0; t < nthr; ++t) { free(GS[t].Hash); free(GS[t].Cache); free(GS[t].Cand); free(GS[t].W); free(GS[t].runs.r); }
+	for (int g = 0; g < ngpu; ++g) { free(H[g]); ncclCommDestroy(comms[g]); }
+	free(B.br); bg_host_free(B.runs); bg_host_free(B.codes); bg_host_free(B.off); bg_host_free(B.bud); bg_host_free(B.slot);
+	free(H); free(NH); free(best); free(GS); free(SPods);
+}
+#endif
+
 /* =============================================================================================
  * Search: all-vs-all (no accelerator, and the accelerator's left-over bin), burst.c:4318-4520.
  * Discovery order per query slot there is (clump, query, lane) ascending; the engine returns
@@ -1249,6 +1386,7 @@ int main(int argc, char *argv[]) {
 		else if (OPT("--heuristic", "-hr")) { DO_HEUR = 1; printf(" --> WARNING: Heuristic mode set; optimality not guaranteed at low ids\n"); }
 		else if (!strcmp(argv[i], "--noprogress")) { QUIET = 1; printf(" --> Surpressing progress indicator\n"); }
 		else if (!strcmp(argv[i], "--gpu")) { NEEDARG("--gpu requires integer argument") GPU_DEVICE = atoi(argv[i]); }
+		else if (!strcmp(argv[i], "--shard-refs")) { SHARD_REFS = 1; printf(" --> Sharding the reference database over the GPUs (all-reduce MIN on the per-read minima)\n"); }
 		else if (!strcmp(argv[i], "--gpus")) { NEEDARG("--gpus requires integer argument") NGPU = atoi(argv[i]); if (NGPU < 1 || NGPU > 64) { fputs("ERROR: --gpus must be 1..64\n", stderr); exit(1); } }
 		else if (OPT("--fingerprint", "-f") || OPT("--prepass", "-p") || OPT("--unique", "-u")) { fprintf(stderr, "ERROR: %s selects a heuristic/legacy path that this build does not provide (see DESIGN.md, out of scope)\n", argv[i]); exit(1); }
 		else if (OPT("--cache", "-c") || OPT("--latency", "-l") || OPT("--clustradius", "-cr") || OPT("--dbpartition", "-dp")) { NEEDARG("option requires integer argument") }
@@ -1290,14 +1428,39 @@ int main(int argc, char *argv[]) {
 		if (!DO_HEUR) exit(1);
 		fputs("!!! WARNING: Error overridden by use of heuristic mode!\n", stderr);
 	}
+	if (SHARD_REFS && NGPU > 1) {                                        /* contiguous clump ranges of about equal bytes, one per GPU */
+#ifndef BURST_NCCL
+		fputs("ERROR: this build has no NCCL: --shard-refs is unavailable\n", stderr); exit(1);
+#endif
+		if (!DO_ACCEL) { fputs("ERROR: --shard-refs needs an accelerator (-a)\n", stderr); exit(1); }
+		uint64_t *boff = xmalloc(((size_t)R.numRclumps + 1) * 8); boff[0] = 0;
+		for (uint32_t i = 0; i < R.numRclumps; ++i) boff[i + 1] = boff[i] + (uint64_t)((R.ClumpLen[i] + 1) / 2) * 16;
+		uint32_t lo = 0;
+		for (int g = 0; g < NGPU; ++g) {
+			uint32_t hi = lo;
+			uint64_t want = boff[R.numRclumps] / (uint64_t)NGPU * (uint64_t)(g + 1);
+			while (hi < R.numRclumps && (g == NGPU - 1 || boff[hi] < want)) ++hi;
+			if (hi == lo) { fputs("ERROR: more GPUs than clumps\n", stderr); exit(1); }
+			printf(" --> shard %d: clumps [%u, %u), %.1f MB\n", g, lo, hi, (double)(boff[hi] - boff[lo]) / 1e6);
+			if ((rc = bg_load_db(ctxs[g], R.packed + boff[lo], R.ClumpLen + lo, hi - lo, lo))) die_gpu("bg_load_db", rc);
+			lo = hi;
+		}
+		free(boff);
+	} else
 	for (int g = 0; g < NGPU; ++g) if ((rc = bg_load_db(ctxs[g], R.packed, R.ClumpLen, R.numRclumps, 0))) die_gpu("bg_load_db", rc);   /* queries are sharded, the database is replicated */
 
 	PodList *Pods = xcalloc(Q.numUniqQ, sizeof(*Pods));
 	int mode = RUNMODE == FORAGE ? BG_MODE_ALL : BG_MODE_MIN;
+#ifdef BURST_NCCL
+	if (DO_ACCEL && SHARD_REFS && NGPU > 1) accel_search_sharded(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS); else
+#endif
 	if (DO_ACCEL) accel_search(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS);
 	/* queries the accelerator cannot vouch for (or all of them without -a) go all-vs-all, burst.c:4320-4323 */
 	uint64_t firstQ = DO_ACCEL ? Q.QBins[1] : 0;
-	if (firstQ != Q.newUniqQ && !(DO_ACCEL && Q.skipAmbig)) search_all_vs_all(ctx, &Q, &R, firstQ, Pods, mode);
+	if (firstQ != Q.newUniqQ && !(DO_ACCEL && Q.skipAmbig)) {
+		if (SHARD_REFS && NGPU > 1) { fputs("ERROR: some queries need the all-vs-all search, which --shard-refs does not cover; use -sa to skip them\n", stderr); exit(1); }
+		search_all_vs_all(ctx, &Q, &R, firstQ, Pods, mode);
+	}
 	printf("Search complete. Consolidating results...\n");
 	Rep P = {output, &Q, &R, taxasuppress};
 	if (RUNMODE == BEST) report_best(&P, Pods);

@@ -144,6 +144,11 @@ int  bg_batch_run(bg_ctx *ctx, int mode, const uint16_t *best_in);
  * all-reduce(MIN) over the device array bg_batch_best_device() (nslots x uint32), then select. */
 int  bg_batch_run_extend(bg_ctx *ctx, int mode, const uint16_t *best_in);
 void *bg_batch_best_device(bg_ctx *ctx);
+/* The CUDA stream (cudaStream_t) the context's kernels run on: enqueue the all-reduce there and no host synchronisation is needed
+ * between bg_batch_run_extend, the all-reduce and bg_batch_run_select. */
+void *bg_stream(bg_ctx *ctx);
+/* Test hook: the next batch starts with a survivor list of exactly `cap` entries (the engine grows it and redoes the work on overflow). */
+int  bg_set_surv_cap(bg_ctx *ctx, uint32_t cap);
 int  bg_batch_run_select(bg_ctx *ctx, int mode);
 /* Device -> host: number of hits, then the hits sorted by (task, lane), and the per-slot
  * minima (0xFFFF = no lane within budget).  Either output pointer may be NULL. */

@@ -134,6 +134,8 @@ int bg_batch_run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	return BG_OK;
 }
 void *bg_batch_best_device(bg_ctx *c) { return c->best32; }
+void *bg_stream(bg_ctx *c) { (void)c; return 0; }
+int bg_set_surv_cap(bg_ctx *c, uint32_t cap) { (void)c; (void)cap; return BG_OK; }
 int bg_batch_run_select(bg_ctx *c, int mode) {
 	uint16_t *in = malloc(c->nslots * 2 + 2);
 	for (uint32_t i = 0; i < c->nslots; ++i) in[i] = (uint16_t)(c->best32[i] > 0xFFFF ? 0xFFFF : c->best32[i]);

@@ -7,6 +7,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_s
 python scripts/ncu_summary.py full /tmp/r2_seed.ncu-rep > gpurun_out/r2_ncu_seed.txt 2>&1
 python scripts/ncu_lines.py /tmp/r2_seed.ncu-rep 250000 0.003 > gpurun_out/r2_lines_seed.txt 2>&1
 ncu -i /tmp/r2_seed.ncu-rep --page raw --csv > gpurun_out/r2_raw_seed.csv 2>/dev/null
+python scripts/ncu_sass_top.py /tmp/r2_seed.ncu-rep 14 > gpurun_out/r2_sass_seed.txt 2>&1
 head -12 gpurun_out/r2_ncu_seed.txt
 if [ -z "$SEED_ONLY" ]; then
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_extend' -s ${EXT_SKIP:-9} -c 1 -o /tmp/r2_extend -f \
@@ -14,6 +15,7 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_e
 python scripts/ncu_summary.py full /tmp/r2_extend.ncu-rep > gpurun_out/r2_ncu_extend.txt 2>&1
 python scripts/ncu_lines.py /tmp/r2_extend.ncu-rep 250000 0.003 > gpurun_out/r2_lines_extend.txt 2>&1
 ncu -i /tmp/r2_extend.ncu-rep --page raw --csv > gpurun_out/r2_raw_extend.csv 2>/dev/null
+python scripts/ncu_sass_top.py /tmp/r2_extend.ncu-rep 14 > gpurun_out/r2_sass_extend.txt 2>&1
 head -12 gpurun_out/r2_ncu_extend.txt
 fi
 if [ -n "$LAUNCHES" ]; then
