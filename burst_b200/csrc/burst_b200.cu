@@ -2144,10 +2144,26 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 		if (smem[k] > 100 * 1024 || no_stage) { E.np_stage[k] = 0; smem[k] = 0; }            // too long for staging: direct reads
 		grid[k] = (unsigned)c->sms * (wb && wb <= 32 ? 12 : 6);
 	}
-	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 48 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K])); \
+	{	// a thread prefetches its NEXT survivor while it sweeps the current one: launch what is resident at once, no more
+		int occ[NCLASS] = {0};
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], k_extend<5>, 128, smem[0]); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], k_extend<8>, 128, smem[1]);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], k_extend<12>, 128, smem[2]); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], k_extend<16>, 128, smem[3]);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[4], k_extend<24>, 128, smem[4]); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[5], k_extend<32>, 128, smem[5]);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[6], k_extend<48>, 128, smem[6]); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[7], k_extend<64>, 128, smem[7]);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[8], k_extend<0>, 128, smem[8]);
+		for (int k = 0; k < NCLASS; ++k) if (occ[k] > 0) grid[k] = std::min<unsigned>(grid[k], (unsigned)c->sms * (unsigned)occ[k]);
+		(void)cudaGetLastError();
+	}
+	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 32 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K]));   /* (the kernel also has 1 KB of static shared memory) */ \
 		k_extend<WM><<<grid[K], 128, smem[K], st>>>(E); } while (0)
 	EXT_LAUNCH(5, 0); EXT_LAUNCH(8, 1); EXT_LAUNCH(12, 2); EXT_LAUNCH(16, 3); EXT_LAUNCH(24, 4); EXT_LAUNCH(32, 5); EXT_LAUNCH(48, 6); EXT_LAUNCH(64, 7); EXT_LAUNCH(0, 8);
 	#undef EXT_LAUNCH
+	if (getenv("BURST_B200_DEBUG")) {                                   // class sizes, staging slots and the launch status of the sweep
+		uint32_t h[64]; cudaError_t e1 = cudaStreamSynchronize(st); cudaMemcpy(h, c->d_cls.p, sizeof(h), cudaMemcpyDeviceToHost);
+		fprintf(stderr, "[burst_b200] extend: mstage %u qp %u sync=%s last=%s |", ms, E.qp_stage, cudaGetErrorString(e1), cudaGetErrorString(cudaPeekAtLastError()));
+		for (int k = 0; k < NCLASS; ++k) fprintf(stderr, " c%d[n=%u np=%u smem=%zu]", k, h[k], E.np_stage[k], smem[k]);
+		fprintf(stderr, "\n");
+	}
 	CU(cudaGetLastError());
 	return BG_OK;
 }

@@ -10,7 +10,9 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     g = np.load(os.path.join(ROOT, "tests", "golden", "kernels_z%d.npz" % z))
     eng = Engine(0); eng.set_scoring(default_scoring(z))
     bad = 0
-    for i in range(len(g["clen"])):
+    only = [int(x) for x in os.environ.get("ONLY", "").split(",") if x]
+    for i in (only or range(len(g["clen"]))):
+        if only: os.environ["BURST_B200_DEBUG"] = "1"
         packed = g["packed"][g["packed_off"][i]:g["packed_off"][i + 1]]
         q = g["q"][g["q_off"][i]:g["q_off"][i + 1]]
         emac, rm = int(g["emac"][i]), int(g["min"][i])
@@ -24,6 +26,6 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
                     i, len(q), int(g["clen"][i]), emac, want, int(best[0]), st["survivors"], st["seed_queries"], st["seed_stride"], st["seed_window"], st["band_cells"]))
     print("  z=%d: %d of %d vectors wrong" % (z, bad, len(g["clen"])))
 else:
-    for env in ({}, {"BURST_B200_EXT_STAGE": "0"}, {"BURST_B200_SEED_IMPL": "0"}, {"BURST_B200_SEED_FILTER": "0"}, {"BURST_B200_SEED_FILTER": "0", "BURST_B200_EXT_STAGE": "0"}):
+    for env in ({"ONLY": "2,3"}, {"BURST_B200_EXT_STAGE": "0", "ONLY": "2,3"}):
         print("settings", env, flush=True)
         subprocess.run([sys.executable, __file__, "child", "0"], env=dict(os.environ, **env))
