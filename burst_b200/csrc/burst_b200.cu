@@ -2498,60 +2498,104 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	const uint64_t nruns = cand_off[nbunch];
 	if (cand_off[0] != 0 || nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_align_bunches_into: candidate offsets must start at 0 and end below 2^28");
 	CU(cudaSetDevice(c->device));
-	c->kind = WORK_NONE;
+	c->kind = WORK_NONE; c->ran = false;
 	const uint32_t nq = R->nq, nr = R->nreads;
-	cudaStream_t st = c->stream;
-	// ---- host -> device: the packed reads, two u16 per read, one u32 per strand, the bunch lists ----
-	uint64_t nbases_max = (uint64_t)nr * 65535ull;                      // bound only; the exact totals come from the scans below
-	(void)nbases_max;
+	cudaStream_t cs = c->stream, ps = c->copy_stream;
+	// ---- one pass over the read lengths on the host: bytes of the packed stream, the longest read (bounds every device buffer, so that
+	//      nothing has to come back from the device before the end), and a sample for the window layout (as the run-list path does) ----
+	uint64_t total = 0; uint32_t maxlen = 0;
+	for (uint32_t r = 0; r < nr; ++r) { total += R->len[r]; maxlen = std::max<uint32_t>(maxlen, R->len[r]); }
+	const uint64_t rbytes = R->flags == BG_R_PACKED2 ? (total + 3) / 4 : (total + 1) / 2, ncodes_max = (uint64_t)nq * (((uint64_t)maxlen + 15) & ~15ull);
+	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t npmax = 1;
+	{
+		uint32_t hist[32]; memset(hist, 0, sizeof(hist));
+		const uint32_t step = std::max<uint32_t>(1, nr / 8192); uint32_t ns = 0;
+		for (uint32_t r = 0; r < nr; r += step, ++ns) { const uint32_t np = R->budget[r] + 1u; if (np <= SEED_NP_MAX) ++hist[std::min<uint32_t>(R->len[r] / np, 31)]; }
+		SL = choose_layout(c, hist, ns);
+		if (SL.stride) {
+			uint64_t sum = 0, cnt = 0; uint32_t mx = 1;
+			for (uint32_t r = 0; r < nr; r += step) { const uint32_t np = R->budget[r] + 1u; if (np <= SL.np_max && R->len[r] / np >= SL.w + SL.stride - 1) { sum += np; ++cnt; mx = std::max(mx, np); } }
+			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, npmax);
+			SL.np_max = npmax;                                       // reads with more stretches than the sample showed go to k_filter
+		}
+		c->mstage = stage_len(maxlen);
+	}
 	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_runs.need(nruns + 1) || c->d_cand.need(nruns + 1) ||
 	    c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) || c->d_qoff.need((size_t)nq + 1) ||
-	    c->d_qi.need(nq) || c->d_peq.need((size_t)nq * 16) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8)) return BG_ENOMEM;
-	CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(c->d_strand.p, R->strand, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
-	CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, st));
-	if (nruns) CU(cudaMemcpyAsync(c->d_cand.p, cand, nruns * 4, cudaMemcpyHostToDevice, st));
-	CU(cudaMemsetAsync(c->d_counters.p, 0, 256, st));
-	// ---- offsets: reads in the packed stream (bases), strands in the code array (16-byte aligned starts) ----
-	k_compact_len<<<(std::max(nr, nq) + 256) / 256, 256, 0, st>>>(c->d_rlen.p, nr, c->d_strand.p, nq, c->d_rl64.p, c->d_sl64.p, c->d_counters.p);
+	    c->d_qi.need(nq) || c->d_peq.need((size_t)nq * 16) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128) ||
+	    c->d_packed.need(rbytes + 32) || c->d_codes.need(ncodes_max + 32) || c->d_qnib.need(ncodes_max / 8 + 3ull * nq + 8)) return BG_ENOMEM;
 	size_t tmp1 = 0, tmp2 = 0;
-	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
-	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, cs));
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, cs));
 	if (c->d_sort_tmp.need(std::max(tmp1, tmp2) + 16)) return BG_ENOMEM;
-	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
-	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
-	unsigned long long tot[2] = {0, 0};
-	CU(cudaMemcpyAsync(&tot[0], c->d_roff.p + nr, 8, cudaMemcpyDeviceToHost, st));
-	CU(cudaMemcpyAsync(&tot[1], c->d_qoff.p + nq, 8, cudaMemcpyDeviceToHost, st));
-	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_align_bunches_into: strand %u names read %u of %u", c->h_pinned[C_ERR] - 1, R->strand[c->h_pinned[C_ERR] - 1] & 0x7FFFFFFFu, nr);
-	const uint64_t rbytes = R->flags == BG_R_PACKED2 ? (tot[0] + 3) / 4 : (tot[0] + 1) / 2, ncodes = tot[1];
-	if (c->d_packed.need(rbytes + 32) || c->d_codes.need(ncodes + 32) || c->d_qnib.need(ncodes / 8 + 3ull * nq + 8)) return BG_ENOMEM;
-	CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, st));
-	// ---- strands: codes, records, window layout, packed copies, Myers tables; runs from the bunch lists ----
-	k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, st>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
-	k_compact_qinfo<<<(nq + 255) / 256, 256, 0, st>>>((const unsigned long long *)c->d_qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, nq, nr, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
-	if (nruns) k_compact_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, st>>>(c->d_candoff.p, c->d_cand.p, nbunch, (uint32_t)nruns, qbunch, nq, c->d_runs.p, c->d_counters.p);
-	CU(cudaGetLastError());
-	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, st));
-	CU(cudaStreamSynchronize(st));
-	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_align_bunches_into: malformed batch (read lengths >= 1, budgets <= 254 (burst.c:3076), ascending candidate offsets)");
-	c->SL = choose_layout(c, c->h_pinned + 16, nq);
-	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nr / 8192); for (uint32_t r = 0; r < nr; r += stp) mx = std::max<uint64_t>(mx, R->len[r]); c->mstage = stage_len(mx); }
-	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
-	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, st>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
-	CU(cudaGetLastError());
-	c->nq = nq; c->nslots = nr;
-	c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = nruns * BG_RUN_MAX; c->ntiles = 0;
-	int rc = finish_upload(c); if (rc) return rc;
-	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
-	uint64_t n = 0;
-	rc = bg_batch_count(c, &n); if (rc) return rc;
-	*nhits = n;
-	if (n > cap) return fail(BG_EOVERFLOW, "bg_align_bunches_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
-	return bg_batch_download(c, hits, cap, best_inout);
+	const uint64_t ntasks = nruns * BG_RUN_MAX;
+	if (!c->surv_cap) c->surv_cap = 1u << 20;
+	{ uint64_t want = std::min<uint64_t>(ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * nq + ntasks / 8)); want = std::max<uint64_t>(want, 1024);
+	  if (c->surv_cap_forced) { want = c->surv_cap; c->surv_cap_forced = false; }
+	  if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull); }
+	for (int attempt = 0; attempt < 4; ++attempt) {
+		if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
+		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
+		// ---- host -> device: the small arrays on the compute stream, the packed reads on the copy stream (they are first needed by
+		//      k_compact_codes; the length scans, strand records and runs are built while they travel) ----
+		CU(cudaEventRecord(c->ev[0], cs));
+		CU(cudaStreamWaitEvent(ps, c->ev[0], 0));                 // (the previous call is done with d_packed)
+		CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, ps));
+		CU(cudaEventRecord(c->sl[0].copied, ps));
+		CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
+		CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
+		CU(cudaMemcpyAsync(c->d_strand.p, R->strand, (size_t)nq * 4, cudaMemcpyHostToDevice, cs));
+		CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, cs));
+		if (nruns) CU(cudaMemcpyAsync(c->d_cand.p, cand, nruns * 4, cudaMemcpyHostToDevice, cs));
+		if (best_inout) CU(cudaMemcpyAsync(c->d_best16.p, best_inout, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
+		k_init_best<<<(nr + 255) / 256, 256, 0, cs>>>(c->d_best.p, best_inout ? c->d_best16.p : nullptr, nr);
+		CU(cudaMemsetAsync(c->d_counters.p, 0, 256, cs));
+		CU(cudaMemsetAsync(c->d_cells.p, 0, 8, cs));
+		CU(cudaMemsetAsync(c->d_first.p, 0, 128 * 4, cs));
+		k_compact_len<<<(std::max(nr, nq) + 256) / 256, 256, 0, cs>>>(c->d_rlen.p, nr, c->d_strand.p, nq, c->d_rl64.p, c->d_sl64.p, c->d_counters.p);
+		CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, cs));
+		CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, cs));
+		k_compact_qinfo<<<(nq + 255) / 256, 256, 0, cs>>>((const unsigned long long *)c->d_qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, nq, nr, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
+		if (nruns) k_compact_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, cs>>>(c->d_candoff.p, c->d_cand.p, nbunch, (uint32_t)nruns, qbunch, nq, c->d_runs.p, c->d_counters.p);
+		CU(cudaStreamWaitEvent(cs, c->sl[0].copied, 0));
+		k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, cs>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
+		k_qprep<<<(nq + 127) / 128, 128, 0, cs>>>(c->d_codes.p, c->d_qi.p, nq, SL, c->d_qnib.p, c->d_counters.p + 9, c->d_first.p + 64);
+		k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, cs>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
+		CU(cudaGetLastError());
+		c->nq = nq; c->nslots = nr; c->SL = SL; c->seed_npmax = npmax;
+		c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = ntasks; c->ntiles = 0;
+		BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.peq = c->d_peq.p; B.qi = c->d_qi.p; B.W = work_of(c);
+		CU(cudaEventRecord(c->ev[0], cs));
+		int rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64); if (rc) return rc;
+		CU(cudaEventRecord(c->ev[1], cs));
+		rc = launch_extend(c, cs, B, mode, nullptr); if (rc) return rc;
+		CU(cudaEventRecord(c->ev[2], cs));
+		k_select<<<(unsigned)c->sms * 4, 256, 0, cs>>>(c->d_surv.p, c->d_res.p, c->d_best.p, c->d_counters.p, c->surv_cap, c->d_hits.p, c->d_keys.p, mode);
+		CU(cudaGetLastError());
+		CU(cudaEventRecord(c->ev[3], cs));
+		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, cs));
+		CU(cudaStreamSynchronize(cs));
+		memcpy(c->h_counters, c->h_pinned, 16);
+		c->nseed = c->h_pinned[9]; c->last_mode = mode; c->have_best_in = false; c->ran = true; c->sorted = false;
+		if (c->h_counters[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_align_bunches_into: malformed batch (strands must name reads < nreads, read lengths >= 1, budgets <= 254 (burst.c:3076), ascending candidate offsets)"); }
+		const bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->d_scratch.cap;
+		if (!grow_s && !grow_g) {
+			const uint64_t n = c->h_counters[C_HITS];
+			*nhits = n;
+			if (n > cap) return fail(BG_EOVERFLOW, "bg_align_bunches_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
+			rc = sort_hits(c, (uint32_t)n); if (rc) return rc;
+			if (n) CU(cudaMemcpyAsync(hits, c->d_hits_sorted.p, n * sizeof(bg_hit), cudaMemcpyDeviceToHost, cs));
+			if (best_inout) {
+				k_best16<<<(nr + 255) / 256, 256, 0, cs>>>(c->d_best.p, c->d_best16.p, nr);
+				CU(cudaMemcpyAsync(best_inout, c->d_best16.p, (size_t)nr * 2, cudaMemcpyDeviceToHost, cs));
+			}
+			CU(cudaStreamSynchronize(cs));
+			return BG_OK;
+		}
+		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
+		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
+	}
+	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
 }
 
 static int finish_align(bg_ctx *c, int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {

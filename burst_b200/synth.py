@@ -271,3 +271,95 @@ def random_clumps_fast(nclumps, clump_len, rng):
         packed.reshape(nclumps, nv, 16)[:, -1, :] &= 15
     off = np.arange(nclumps, dtype=np.uint64) * np.uint64(nv * 16)
     return packed, off, np.full(nclumps, clump_len, np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------
+# Amplicon-shaped inputs (BASELINE.json configs[2]): references in a mutation tree, so that the lanes of a
+# clump are near-identical and most of them tie; reads cut from a (jittered) fixed start of their reference.
+# ---------------------------------------------------------------------------------------------
+
+def mutation_tree_refs(rng, n_refs, length, levels=(0.25, 0.10, 0.05, 0.03), fanout=(4, 4, 4)):
+    """n_refs references of ~`length` bases: a root sequence, `fanout[0]` phyla at levels[0] divergence from it,
+    families under them at levels[1], genera at levels[2], and leaves at levels[3] from their genus
+    (25 % / 10 % / 5 % / 3 %).  Substitutions only above the leaves, any edit at the leaves."""
+    def diverge(seq, frac, subs_only):
+        s = seq.copy()
+        n = int(round(frac * len(s)))
+        if subs_only:
+            pos = rng.choice(len(s), n, replace=False)
+            s[pos] = (s[pos] - 1 + rng.integers(1, 4, n)) % 4 + 1
+            return s.astype(np.uint8)
+        return mutate(s, n, rng, p_sub=0.8, p_ins=0.1)
+    root = rng.integers(1, 5, length, dtype=np.uint8)
+    nodes = [root]
+    for lv, fo in zip(levels[:-1], fanout):
+        nodes = [diverge(p, lv, True) for p in nodes for _ in range(fo)]
+    out = []
+    per = (n_refs + len(nodes) - 1) // len(nodes)
+    for g in nodes:
+        for _ in range(per):
+            if len(out) < n_refs:
+                out.append(diverge(g, levels[-1] * rng.random(), False))
+    return out
+
+
+def amplicon_reads(refs, n, read_len, max_edits, rng, start=40, jitter=5, dup_rate=0.0):
+    """n reads of read_len bases starting within `jitter` of `start` on a random reference, 0..max_edits edits;
+    a fraction dup_rate repeats an earlier read exactly (amplicon data is full of duplicates)."""
+    reads, src = [], np.zeros(n, np.int64)
+    for i in range(n):
+        if reads and rng.random() < dup_rate:
+            j = int(rng.integers(0, len(reads)))
+            reads.append(reads[j].copy()); src[i] = src[j]
+            continue
+        while True:
+            r = int(rng.integers(0, len(refs)))
+            if len(refs[r]) >= start + jitter + read_len:
+                break
+        o = start + int(rng.integers(-jitter, jitter + 1))
+        reads.append(mutate(refs[r][o:o + read_len], int(rng.integers(0, max_edits + 1)), rng))
+        src[i] = r
+    return reads, src
+
+
+def bunch_runs(order_len, qbunch, cands_of_bunch):
+    """Run records {clump, query0, nq} and the equivalent (query, clump) task list + hit keys for bunches of `qbunch`
+    consecutive queries; cands_of_bunch(b, q0, n) -> iterable of clump ids in visiting order."""
+    runs, tq, tc, key = [], [], [], []
+    for b, q0 in enumerate(range(0, order_len, qbunch)):
+        n = min(qbunch, order_len - q0)
+        for c in cands_of_bunch(b, q0, n):
+            for i in range(n):
+                tq.append(q0 + i); tc.append(int(c)); key.append(len(runs) * 16 + i)
+            runs.append((int(c), q0, n))
+    runs = np.array(runs, dtype=np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")]))
+    return runs, np.array(tq, np.uint32), np.array(tc, np.uint32), np.array(key, np.uint32)
+
+
+def strand_batch(reads, budgets, qbunch, cands_of_bunch, rng=None):
+    """The compact strand form (bg_align_bunches_into) of a read set and the equivalent general form.
+    reads: list of code arrays; budgets: per read.  Strands = every read and its reverse complement, sorted as the
+    reference sorts them (burst.c:3181-3184).  cands_of_bunch(b, strand_reads, strand_rc) -> candidate clumps of bunch b.
+    Returns dict(rlen, rbudget, strand, cand_off, cand, rcodes [concatenated read codes], and the general form:
+    qcodes, qoff, budget, slot, runs, tq, tc, key)."""
+    n = len(reads)
+    strands, sread, src = [], [], []
+    for i, r in enumerate(reads):
+        strands += [r, RC_TABLE[r[::-1]]]; sread += [i, i]; src += [0, 1]
+    codes, off = concat_queries(strands)
+    order = sort_strands(codes, off)
+    strands = [strands[i] for i in order]
+    sread = np.array([sread[i] for i in order], np.uint32); src = np.array([src[i] for i in order], np.uint32)
+    nq = len(strands)
+    cand_off = [0]; cand = []
+    for b, q0 in enumerate(range(0, nq, qbunch)):
+        cs = list(cands_of_bunch(b, sread[q0:q0 + qbunch], src[q0:q0 + qbunch]))
+        cand += [int(c) for c in cs]; cand_off.append(len(cand))
+    cand_off = np.array(cand_off, np.uint32); cand = np.array(cand, np.uint32)
+    it = iter(range(len(cand_off) - 1))
+    runs, tq, tc, key = bunch_runs(nq, qbunch, lambda b, q0, m: cand[cand_off[b]:cand_off[b + 1]])
+    qcodes, qoff = concat_queries(strands)
+    rcodes, _ = concat_queries(reads)
+    return dict(rlen=np.array([len(r) for r in reads], np.uint16), rbudget=np.asarray(budgets, np.uint16), strand=(sread | (src << 31)).astype(np.uint32),
+                cand_off=cand_off, cand=cand, rcodes=rcodes, qcodes=qcodes, qoff=qoff, budget=np.asarray(budgets, np.uint16)[sread], slot=sread,
+                runs=runs, tq=tq, tc=tc, key=key, nreads=n)
