@@ -2538,6 +2538,9 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
 		// ---- host -> device: the small arrays on the compute stream, the packed reads on the copy stream (they are first needed by
 		//      k_compact_codes; the length scans, strand records and runs are built while they travel) ----
+		const double hstart = (double)clock() / CLOCKS_PER_SEC;
+		static cudaEvent_t te0 = nullptr;
+		if (getenv("BURST_B200_TIMING")) { if (!te0) cudaEventCreate(&te0); cudaEventRecord(te0, cs); }
 		CU(cudaEventRecord(c->ev[0], cs));
 		CU(cudaStreamWaitEvent(ps, c->ev[0], 0));                 // (the previous call is done with d_packed)
 		CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, ps));
@@ -2566,6 +2569,11 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = ntasks; c->ntiles = 0;
 		BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.peq = c->d_peq.p; B.qi = c->d_qi.p; B.W = work_of(c);
 		CU(cudaEventRecord(c->ev[0], cs));
+		const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
+		static cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
+		if (dbg && !te[1]) for (int i = 1; i < 4; ++i) cudaEventCreate(&te[i]);
+		te[0] = te0;
+		const double h0 = dbg ? (double)clock() / CLOCKS_PER_SEC : 0;
 		int rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64); if (rc) return rc;
 		CU(cudaEventRecord(c->ev[1], cs));
 		rc = launch_extend(c, cs, B, mode, nullptr); if (rc) return rc;
@@ -2583,13 +2591,22 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			const uint64_t n = c->h_counters[C_HITS];
 			*nhits = n;
 			if (n > cap) return fail(BG_EOVERFLOW, "bg_align_bunches_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
+			if (dbg) cudaEventRecord(te[1], cs);
 			rc = sort_hits(c, (uint32_t)n); if (rc) return rc;
+			if (dbg) cudaEventRecord(te[2], cs);
 			if (n) CU(cudaMemcpyAsync(hits, c->d_hits_sorted.p, n * sizeof(bg_hit), cudaMemcpyDeviceToHost, cs));
 			if (best_inout) {
 				k_best16<<<(nr + 255) / 256, 256, 0, cs>>>(c->d_best.p, c->d_best16.p, nr);
 				CU(cudaMemcpyAsync(best_inout, c->d_best16.p, (size_t)nr * 2, cudaMemcpyDeviceToHost, cs));
 			}
+			if (dbg) cudaEventRecord(te[3], cs);
 			CU(cudaStreamSynchronize(cs));
+			if (dbg) {
+				float a = 0, b = 0, d = 0, e = 0, f = 0, g = 0; 
+				cudaEventElapsedTime(&a, te[0], c->ev[0]); cudaEventElapsedTime(&b, c->ev[0], c->ev[1]); cudaEventElapsedTime(&d, c->ev[1], c->ev[2]); cudaEventElapsedTime(&e, c->ev[2], te[1]);
+				cudaEventElapsedTime(&f, te[1], te[2]); cudaEventElapsedTime(&g, te[2], te[3]);
+				fprintf(stderr, "[burst_b200] compact call: copies+prep %.3f ms, filter %.3f, extend %.3f, select+counters sync %.3f, sort %.3f, D2H %.3f (host launch time before filters %.3f ms)\n", a, b, d, e, f, g, (h0 - hstart) * 1e3);
+			}
 			return BG_OK;
 		}
 		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
