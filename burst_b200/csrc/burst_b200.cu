@@ -1550,19 +1550,21 @@ __global__ void k_init_best(uint32_t *best, const uint16_t *in, uint32_t n) {
 // ---------------------------------------------------------------------------------------------
 __constant__ uint8_t c_rvt[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};       // burst.c:168
 // lengths: per read (u16 -> u64) and per strand, the latter rounded up to 16 so that every strand's codes start 16-byte aligned
-__global__ void k_compact_len(const uint16_t *__restrict__ rlen, uint32_t nreads, const uint32_t *__restrict__ strand, uint32_t nq,
-		unsigned long long *__restrict__ rl64, unsigned long long *__restrict__ sl64, uint32_t *__restrict__ counters) {
+__global__ void k_compact_rlen(const uint16_t *__restrict__ rlen, uint32_t nreads, unsigned long long *__restrict__ rl64) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i <= nreads) rl64[i] = i < nreads ? rlen[i] : 0;
-	if (i <= nq) {
-		unsigned long long v = 0;
-		if (i < nq) {
-			const uint32_t r = strand[i] & 0x7FFFFFFFu;
-			if (r >= nreads) atomicExch(&counters[C_ERR], i + 1);
-			else v = ((unsigned long long)rlen[r] + 15ull) & ~15ull;
-		}
-		sl64[i] = v;
+}
+__global__ void k_compact_slen(const uint16_t *__restrict__ rlen, uint32_t nreads, const uint32_t *__restrict__ strand, uint32_t nq,
+		unsigned long long *__restrict__ sl64, uint32_t *__restrict__ counters) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > nq) return;
+	unsigned long long v = 0;
+	if (i < nq) {
+		const uint32_t r = strand[i] & 0x7FFFFFFFu;
+		if (r >= nreads) atomicExch(&counters[C_ERR], i + 1);
+		else v = ((unsigned long long)rlen[r] + 15ull) & ~15ull;
 	}
+	sl64[i] = v;
 }
 // codes of every strand (one byte per base, 16-byte aligned start): 8 threads per strand, 16 bases per thread and step
 __global__ void k_compact_codes(const uint8_t *__restrict__ reads, uint32_t flags, const unsigned long long *__restrict__ roff, const uint16_t *__restrict__ rlen,
@@ -1607,17 +1609,18 @@ __global__ void k_compact_qinfo(const unsigned long long *__restrict__ qoff, con
 	__syncthreads();
 	if (threadIdx.x < 32 && sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
-// bunch -> candidate lists into runs: run r = candidate r of the bunch that owns it (cand_off), all queries of the bunch
-__global__ void k_compact_runs(const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t nbunch, uint32_t nruns, uint32_t qbunch, uint32_t nq,
+// bunch -> candidate lists into runs: run r = candidate r of the bunch that owns it (cand_off), all queries of the bunch; runs r0 .. r0+count-1
+__global__ void k_compact_runs(const uint32_t *__restrict__ cand_off, const uint32_t *__restrict__ cand, uint32_t nbunch, uint32_t r0, uint32_t count, uint32_t qbunch, uint32_t nq,
 		bg_run *__restrict__ runs, uint32_t *__restrict__ counters) {
-	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
-	if (r >= nruns) return;
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= count) return;
+	const uint32_t r = r0 + i;
 	uint32_t lo = 0, hi = nbunch;                                          // last bunch b with cand_off[b] <= r
 	while (lo + 1 < hi) { const uint32_t mid = (lo + hi) >> 1; if (__ldg(cand_off + mid) <= r) lo = mid; else hi = mid; }
 	const unsigned long long q0 = (unsigned long long)lo * qbunch;
 	bg_run R; R.clump = cand[r]; R.query0 = (uint32_t)min(q0, (unsigned long long)nq); R.nq = q0 < nq ? (uint32_t)min((unsigned long long)qbunch, nq - q0) : 0u;
-	if (!R.nq || __ldg(cand_off + lo) > r || __ldg(cand_off + lo + 1) <= r) { atomicExch(&counters[C_ERR], 0x80000000u | r); R.nq = 1; R.query0 = 0; }
-	runs[r] = R;
+	if (!R.nq || __ldg(cand_off + lo) > r || __ldg(cand_off + lo + 1) <= r) { atomicExch(&counters[C_ERR], 0x80000000u | r); R.nq = 1; R.query0 = min(R.query0, nq - 1); }
+	runs[i] = R;
 }
 
 // run validation (explicit run lists): malformed runs raise the error flag
@@ -1675,9 +1678,9 @@ enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
 #define NSLICEBUF 3
 struct Slice {
 	DBuf<uint8_t> packed, codes; DBuf<uint64_t> qoff; DBuf<uint16_t> budget; DBuf<uint32_t> slot;
-	DBuf<QInfo> qi; DBuf<uint32_t> peq, qnib; DBuf<bg_run> runs;
+	DBuf<QInfo> qi; DBuf<uint32_t> peq, qnib; DBuf<bg_run> runs; DBuf<unsigned long long> sl64;
 	cudaEvent_t copied = nullptr, computed = nullptr;
-	void release() { packed.release(); codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); peq.release(); qnib.release(); runs.release(); }
+	void release() { sl64.release(); packed.release(); codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); peq.release(); qnib.release(); runs.release(); }
 };
 
 struct bg_ctx {
@@ -2536,48 +2539,76 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	for (int attempt = 0; attempt < 4; ++attempt) {
 		if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
-		// ---- host -> device: the small arrays on the compute stream, the packed reads on the copy stream (they are first needed by
-		//      k_compact_codes; the length scans, strand records and runs are built while they travel) ----
+		// ---- host -> device on the copy stream: the reads and their lengths/budgets first, then the strands and candidates slice by slice;
+		//      the kernels of slice i (strand records, codes, runs, seed filter, banded sweep) run while slice i+1 travels ----
 		const double hstart = (double)clock() / CLOCKS_PER_SEC;
 		static cudaEvent_t te0 = nullptr;
-		if (getenv("BURST_B200_TIMING")) { if (!te0) cudaEventCreate(&te0); cudaEventRecord(te0, cs); }
-		CU(cudaEventRecord(c->ev[0], cs));
-		CU(cudaStreamWaitEvent(ps, c->ev[0], 0));                 // (the previous call is done with d_packed)
-		CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, ps));
-		CU(cudaEventRecord(c->sl[0].copied, ps));
-		CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
-		CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
-		CU(cudaMemcpyAsync(c->d_strand.p, R->strand, (size_t)nq * 4, cudaMemcpyHostToDevice, cs));
-		CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, cs));
-		if (nruns) CU(cudaMemcpyAsync(c->d_cand.p, cand, nruns * 4, cudaMemcpyHostToDevice, cs));
+		const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
+		static cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
+		if (dbg && !te0) { cudaEventCreate(&te0); for (int i = 1; i < 4; ++i) cudaEventCreate(&te[i]); }
+		te[0] = te0;
+		if (dbg) cudaEventRecord(te0, cs);
 		if (best_inout) CU(cudaMemcpyAsync(c->d_best16.p, best_inout, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
 		k_init_best<<<(nr + 255) / 256, 256, 0, cs>>>(c->d_best.p, best_inout ? c->d_best16.p : nullptr, nr);
 		CU(cudaMemsetAsync(c->d_counters.p, 0, 256, cs));
 		CU(cudaMemsetAsync(c->d_cells.p, 0, 8, cs));
 		CU(cudaMemsetAsync(c->d_first.p, 0, 128 * 4, cs));
-		k_compact_len<<<(std::max(nr, nq) + 256) / 256, 256, 0, cs>>>(c->d_rlen.p, nr, c->d_strand.p, nq, c->d_rl64.p, c->d_sl64.p, c->d_counters.p);
+		CU(cudaEventRecord(c->ev[0], cs));
+		CU(cudaStreamWaitEvent(ps, c->ev[0], 0));                 // (the previous call is done with the buffers)
+		CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
+		CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
+		CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, ps));
+		CU(cudaEventRecord(c->sl[1].copied, ps));
+		CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, ps));
+		CU(cudaEventRecord(c->sl[0].copied, ps));
+		CU(cudaStreamWaitEvent(cs, c->sl[1].copied, 0));
+		k_compact_rlen<<<(nr + 256) / 256, 256, 0, cs>>>(c->d_rlen.p, nr, c->d_rl64.p);
 		CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, cs));
-		CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, cs));
-		k_compact_qinfo<<<(nq + 255) / 256, 256, 0, cs>>>((const unsigned long long *)c->d_qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, nq, nr, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
-		if (nruns) k_compact_runs<<<(unsigned)((nruns + 255) / 256), 256, 0, cs>>>(c->d_candoff.p, c->d_cand.p, nbunch, (uint32_t)nruns, qbunch, nq, c->d_runs.p, c->d_counters.p);
-		CU(cudaStreamWaitEvent(cs, c->sl[0].copied, 0));
-		k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, cs>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
-		k_qprep<<<(nq + 127) / 128, 128, 0, cs>>>(c->d_codes.p, c->d_qi.p, nq, SL, c->d_qnib.p, c->d_counters.p + 9, c->d_first.p + 64);
-		k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, cs>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
-		CU(cudaGetLastError());
 		c->nq = nq; c->nslots = nr; c->SL = SL; c->seed_npmax = npmax;
 		c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = ntasks; c->ntiles = 0;
-		BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.peq = c->d_peq.p; B.qi = c->d_qi.p; B.W = work_of(c);
-		CU(cudaEventRecord(c->ev[0], cs));
-		const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
-		static cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
-		if (dbg && !te[1]) for (int i = 1; i < 4; ++i) cudaEventCreate(&te[i]);
-		te[0] = te0;
-		const double h0 = dbg ? (double)clock() / CLOCKS_PER_SEC : 0;
-		int rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64); if (rc) return rc;
-		CU(cudaEventRecord(c->ev[1], cs));
-		rc = launch_extend(c, cs, B, mode, nullptr); if (rc) return rc;
-		CU(cudaEventRecord(c->ev[2], cs));
+		// slices of whole bunches, growing (the first one short so that the kernels start early)
+		const int nsl = (int)std::min<uint64_t>((uint64_t)std::max(1, c->pipe_slices), std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
+		std::vector<uint32_t> cut(nsl + 1, 0);
+		{ double tot = 0, w = 1, acc = 0; const double ratio = 1.4;
+		  for (int i = 0; i < nsl; ++i, w *= ratio) tot += w;
+		  w = 1;
+		  for (int i = 0; i < nsl; ++i, w *= ratio) { acc += w; cut[i + 1] = (uint32_t)std::min<uint64_t>(nbunch, (uint64_t)(nbunch * (acc / tot) + 0.5)); }
+		  cut[nsl] = nbunch; }
+		int rc = BG_OK;
+		for (int i = 0; i < nsl; ++i) {
+			const uint32_t ba = cut[i], bb = cut[i + 1];
+			if (ba >= bb) continue;
+			const uint32_t qa = (uint32_t)std::min<uint64_t>(nq, (uint64_t)ba * qbunch), qb = (uint32_t)std::min<uint64_t>(nq, (uint64_t)bb * qbunch), n = qb - qa;
+			const uint32_t ra = cand_off[ba], rb = cand_off[bb];
+			if (rb < ra || rb > nruns) { cudaStreamSynchronize(ps); cudaStreamSynchronize(cs); return fail(BG_EINVAL, "bg_align_bunches_into: candidate offsets are not ascending"); }
+			if (!n) continue;
+			Slice &S = c->sl[i % NSLICEBUF];
+			const uint64_t scodes = (uint64_t)n * (((uint64_t)maxlen + 15) & ~15ull);
+			if (S.sl64.need((size_t)n + 1) || S.qoff.need((size_t)n + 1) || S.qi.need(n) || S.peq.need((size_t)n * 16) || S.codes.need(scodes + 32) || S.qnib.need(scodes / 8 + 3ull * n + 8) || S.runs.need((size_t)(rb - ra) + 1)) {
+				cudaStreamSynchronize(ps); cudaStreamSynchronize(cs); return BG_ENOMEM;
+			}
+			CU(cudaMemcpyAsync(c->d_strand.p + qa, R->strand + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
+			if (rb > ra) CU(cudaMemcpyAsync(c->d_cand.p + ra, cand + ra, (size_t)(rb - ra) * 4, cudaMemcpyHostToDevice, ps));
+			CU(cudaEventRecord(S.computed, ps));                     // (used here as "slice i is on the device")
+			CU(cudaStreamWaitEvent(cs, S.computed, 0));
+			k_compact_slen<<<(n + 256) / 256, 256, 0, cs>>>(c->d_rlen.p, nr, c->d_strand.p + qa, n, S.sl64.p, c->d_counters.p);
+			CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, S.sl64.p, (unsigned long long *)S.qoff.p, (int)n + 1, cs));
+			k_compact_qinfo<<<(n + 255) / 256, 256, 0, cs>>>((const unsigned long long *)S.qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p + qa, n, nr, S.qi.p, c->d_counters.p + 16, c->d_counters.p);
+			if (rb > ra) k_compact_runs<<<(unsigned)((rb - ra + 255) / 256), 256, 0, cs>>>(c->d_candoff.p, c->d_cand.p, nbunch, ra, rb - ra, qbunch, nq, S.runs.p, c->d_counters.p);
+			if (i == 0) CU(cudaStreamWaitEvent(cs, c->sl[0].copied, 0));   // the packed reads
+			k_compact_codes<<<(unsigned)(((uint64_t)n * 8 + 255) / 256), 256, 0, cs>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p + qa, (const unsigned long long *)S.qoff.p, n, nr, S.codes.p);
+			k_qprep<<<(n + 127) / 128, 128, 0, cs>>>(S.codes.p, S.qi.p, n, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
+			k_qtables<<<(unsigned)(((uint64_t)n * 16 + 255) / 256), 256, 0, cs>>>(S.codes.p, S.qi.p, c->d_sterm.p, n, S.peq.p);
+			CU(cudaMemcpyAsync(c->d_first.p + i, c->d_counters.p + C_SURV, 4, cudaMemcpyDeviceToDevice, cs));
+			CU(cudaGetLastError());
+			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.peq = S.peq.p; B.qi = S.qi.p;
+			B.W.runs = S.runs.p; B.W.nruns = rb - ra; B.W.nq = n; B.W.ntiles = 0; B.W.first_clump = c->first_clump; B.W.num_clumps = c->num_clumps;
+			B.W.q_base = qa; B.W.run_base = ra;
+			if (i == 0) CU(cudaEventRecord(c->ev[0], cs));
+			rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64 + i); if (rc) return rc;
+			rc = launch_extend(c, cs, B, mode, c->d_first.p + i); if (rc) return rc;
+		}
+		CU(cudaEventRecord(c->ev[1], cs)); CU(cudaEventRecord(c->ev[2], cs));
 		k_select<<<(unsigned)c->sms * 4, 256, 0, cs>>>(c->d_surv.p, c->d_res.p, c->d_best.p, c->d_counters.p, c->surv_cap, c->d_hits.p, c->d_keys.p, mode);
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(c->ev[3], cs));
@@ -2605,8 +2636,10 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 				float a = 0, b = 0, d = 0, e = 0, f = 0, g = 0; 
 				cudaEventElapsedTime(&a, te[0], c->ev[0]); cudaEventElapsedTime(&b, c->ev[0], c->ev[1]); cudaEventElapsedTime(&d, c->ev[1], c->ev[2]); cudaEventElapsedTime(&e, c->ev[2], te[1]);
 				cudaEventElapsedTime(&f, te[1], te[2]); cudaEventElapsedTime(&g, te[2], te[3]);
-				fprintf(stderr, "[burst_b200] compact call: copies+prep %.3f ms, filter %.3f, extend %.3f, select+counters sync %.3f, sort %.3f, D2H %.3f (host launch time before filters %.3f ms)\n", a, b, d, e, f, g, (h0 - hstart) * 1e3);
+				(void)d;
+				fprintf(stderr, "[burst_b200] compact call: until the first filter launch %.3f ms, all slices (prep + filter + extend, copies behind them) %.3f, select + counters %.3f, sort %.3f, D2H %.3f (host time to enqueue everything %.3f ms)\n", a, b, e, f, g, ((double)clock() / CLOCKS_PER_SEC - hstart) * 1e3);
 			}
+			c->kind = WORK_NONE; c->ran = false;                    // the per-slice buffers are not a resident batch: nothing to re-run or to take statistics of
 			return BG_OK;
 		}
 		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
