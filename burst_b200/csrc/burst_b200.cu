@@ -2567,7 +2567,10 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		c->nq = nq; c->nslots = nr; c->SL = SL; c->seed_npmax = npmax;
 		c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = ntasks; c->ntiles = 0;
 		// slices of whole bunches, growing (the first one short so that the kernels start early)
-		const int nsl = (int)std::min<uint64_t>((uint64_t)std::max(1, c->pipe_slices), std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
+		// (measured, profiles/: one slice is fastest on the bench workload -- the per-slice launches and kernel tails cost more than the
+		//  ~0.8 ms of copies they hide; BURST_B200_COMPACT_SLICES cuts the batch for hosts with slower links)
+		static const int want_slices = getenv("BURST_B200_COMPACT_SLICES") ? std::max(1, std::min(32, atoi(getenv("BURST_B200_COMPACT_SLICES")))) : 1;
+		const int nsl = (int)std::min<uint64_t>((uint64_t)want_slices, std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
 		std::vector<uint32_t> cut(nsl + 1, 0);
 		{ double tot = 0, w = 1, acc = 0; const double ratio = 1.4;
 		  for (int i = 0; i < nsl; ++i, w *= ratio) tot += w;
