@@ -446,11 +446,27 @@ static void load_acx(const char *fn, Acx *A) {
 		uint32_t *Lens = xmalloc(nk * 4);
 		fseeko(in, 5, SEEK_SET); rd(Lens, 4, nk, in);
 		uint64_t bytes = 0;
+		#pragma omp parallel for reduction(+:bytes) schedule(static)
 		for (uint64_t i = 0; i < nk; ++i) bytes += A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3;
 		if (5 + nk * 4 + bytes + (uint64_t)szBL * 4 == fsz) {
 			found = 1; SCOUR_N = n; A->nk = nk;
 			A->off = xmalloc((nk + 1) * 8); A->off[0] = 0;
-			for (uint64_t i = 0; i < nk; ++i) A->off[i + 1] = A->off[i] + (A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3);
+			{	/* prefix sums in parallel: per-block totals, then each block from its base */
+				enum { NB = 256 }; uint64_t base[NB + 1]; const uint64_t per = (nk + NB - 1) / NB;
+				#pragma omp parallel for schedule(static)
+				for (int b = 0; b < NB; ++b) {
+					uint64_t t = 0, lo = (uint64_t)b * per, hi = MIN(nk, lo + per);
+					for (uint64_t i = lo; i < hi; ++i) t += A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3;
+					base[b + 1] = t;
+				}
+				base[0] = 0;
+				for (int b = 0; b < NB; ++b) base[b + 1] += base[b];
+				#pragma omp parallel for schedule(static)
+				for (int b = 0; b < NB; ++b) {
+					uint64_t t = base[b], lo = (uint64_t)b * per, hi = MIN(nk, lo + per);
+					for (uint64_t i = lo; i < hi; ++i) { t += A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3; A->off[i + 1] = t; }
+				}
+			}
 			A->post = xmalloc(bytes + 16); rd(A->post, 1, bytes, in); memset(A->post + bytes, 0, 16);
 			A->bad = xmalloc((uint64_t)szBL * 4 + 4); rd(A->bad, 4, szBL, in); A->nbad = szBL;
 		}
@@ -1404,7 +1420,8 @@ int main(int argc, char *argv[]) {
 	FILE *output = fopen(output_FN, "wb");
 	if (!output) { fprintf(stderr, "ERROR: Cannot open output: %s\n", output_FN); exit(2); }
 	setvbuf(output, 0, _IOFBF, 1 << 22);
-	double start = now();
+	double start = now(), tph = start;
+#define PHASE(name) do { double t_ = now(); printf(" --> [time] %-28s %8.3f s\n", name, t_ - tph); tph = t_; } while (0)
 	init_char2num();
 
 	/* the engine first: without a CUDA device there is nothing this program can do */
@@ -1416,12 +1433,15 @@ int main(int argc, char *argv[]) {
 		if ((rc = bg_set_scoring(ctxs[g], S))) die_gpu("bg_set_scoring", rc);
 	}
 	bg_ctx *ctx = ctxs[0];
+	PHASE("GPU engine start");
 	Acx A; memset(&A, 0, sizeof(A));
-	if (DO_ACCEL) load_acx(xcel_FN, &A);
+	if (DO_ACCEL) { load_acx(xcel_FN, &A); PHASE("accelerator load"); }
 	int usedb = is_edx(ref_FN);
 	if (usedb) { puts("\nEDB database provided. Parsing..."); load_edx(ref_FN, &R); }
+	PHASE("database load");
 	if (tax_FN) load_taxonomy(tax_FN);
 	load_queries(query_FN, &Q);
+	PHASE("query parse/sort");
 	if (!usedb) load_fasta_refs(ref_FN, &R);
 	else if (R.shear && (uint32_t)(Q.maxLenQ / THRES) > R.shear) {
 		fputs("ERROR: DB incompatible with selected queries/identity.\n", stderr);
@@ -1449,6 +1469,7 @@ int main(int argc, char *argv[]) {
 	} else
 	for (int g = 0; g < NGPU; ++g) if ((rc = bg_load_db(ctxs[g], R.packed, R.ClumpLen, R.numRclumps, 0))) die_gpu("bg_load_db", rc);   /* queries are sharded, the database is replicated */
 
+	PHASE("database to GPU");
 	PodList *Pods = xcalloc(Q.numUniqQ, sizeof(*Pods));
 	int mode = RUNMODE == FORAGE ? BG_MODE_ALL : BG_MODE_MIN;
 #ifdef BURST_NCCL
@@ -1461,6 +1482,7 @@ int main(int argc, char *argv[]) {
 		if (SHARD_REFS && NGPU > 1) { fputs("ERROR: some queries need the all-vs-all search, which --shard-refs does not cover; use -sa to skip them\n", stderr); exit(1); }
 		search_all_vs_all(ctx, &Q, &R, firstQ, Pods, mode);
 	}
+	PHASE("search");
 	printf("Search complete. Consolidating results...\n");
 	Rep P = {output, &Q, &R, taxasuppress};
 	if (RUNMODE == BEST) report_best(&P, Pods);
@@ -1468,6 +1490,7 @@ int main(int argc, char *argv[]) {
 	else if (RUNMODE == FORAGE) report_allpaths_or_forage(&P, Pods, 1);
 	else report_capitalist(&P, Pods);
 	fclose(output);
+	PHASE("report");
 	for (int g = 0; g < NGPU; ++g) bg_free(ctxs[g]);
 	printf("\nAlignment time: %f seconds\n", now() - start);
 	return 0;

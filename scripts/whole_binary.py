@@ -131,7 +131,7 @@ def main():
            "edx_bytes": os.path.getsize(os.path.join(d, "db.edx")), "acx_bytes": os.path.getsize(os.path.join(d, "db.acx")), "flags": " ".join(common)}
     t_ours, so = run([ours] + common + ["-o", "ours.b6", "-t", str(args.threads), "--gpus", str(args.gpus)], d)
     out["ours_wall_s"] = round(t_ours, 2); out["ours_reads_per_s"] = round(args.reads / t_ours)
-    out["ours_stdout_tail"] = [l for l in so.splitlines() if "Accel" in l or "Alignment time" in l or "Search" in l][-4:]
+    out["ours_stdout_tail"] = [l.strip() for l in so.splitlines() if "[Accel]" in l or "Alignment time" in l or "[time]" in l][-12:]
     rows = sorted(open(os.path.join(d, "ours.b6"), "rb").read().splitlines())
     out["rows"] = len(rows)
     if not args.skip_reference and os.path.exists(ref):
