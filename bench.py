@@ -238,8 +238,16 @@ def main():
     numa = bind_to_gpu_numa_node(torch, local)             # host buffers (pinned) and the calling thread next to the GPU's PCIe root
     if world > 1:
         if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"              # keep rank 0's stdout to the one JSON line
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            os.environ["NCCL_DEBUG"] = "WARN"
+        # keep rank 0's stdout to the one JSON line: NCCL writes its version banner to fd 1 when the communicator is created
+        sys.stdout.flush()
+        saved = os.dup(1); os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush(); os.dup2(saved, 1); os.close(saved)
     from burst_b200.engine import Engine, MODE_MIN, RUN_DTYPE
     config["numa_node_rank0"] = numa
 
