@@ -1623,6 +1623,205 @@ __global__ void k_compact_runs(const uint32_t *__restrict__ cand_off, const uint
 	runs[i] = R;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Candidate generation on the device (burst.c:4085-4133 with postScour20/24, 3238-3282).
+// One block per bunch of <= 16 strands, in the reference's steps:
+//   words    every N-mer of every query -> (word, query) pairs                              burst.c:4097-4105
+//   sort     by (word, query)                                                               burst.c:4118
+//   count    each distinct word adds its largest per-query multiplicity to every clump of its posting list; the clumps touched
+//            are remembered in first-touch order (words ascending, postings in list order)   burst.c:3238-3282
+//   pick     clumps whose count exceeds the bunch's smallest threshold len - (ed+1) N, ordered by descending count (stable: ties keep
+//            first-touch order, as iSort / qsort do)                                        burst.c:4120-4130, 4038-4046
+//   emit     one run per candidate and maximal range of queries whose own threshold it passes, then the always-visited BadList
+//                                                                                            burst.c:4137-4168, 4281-4283
+// The per-clump counters are a dense array in global memory per resident block (the reference's Hash[] / Cache[] per thread), cleared
+// through the touched list.  Queries must be plain A/C/G/T (the reference expands ambiguous bases into every variant, burst.c:4106-4113;
+// such batches stay on the host path).
+// ---------------------------------------------------------------------------------------------
+struct CandArgs {
+	const QInfo *qi; const uint32_t *qnib; uint32_t nq, qbunch, nbunch;
+	const unsigned long long *acx_off; const uint8_t *post; int big, N; uint32_t num_clumps;
+	const uint32_t *bad; uint32_t nbad; int heur, skip_bad;
+	uint32_t *cnt, *first, *cache;              // per resident block: num_clumps counters, first-touch keys, touched list
+	bg_run *runs; uint32_t runs_cap; uint32_t *counters;   // counters[C_RUNS] = runs emitted (keeps counting past the capacity)
+	uint32_t pmax, cmax;                         // capacity of the pair array / candidate list in shared memory (powers of two)
+};
+enum { C_RUNS = 5 };
+
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long *a, uint32_t n) {   // n a power of two, whole block
+	for (uint32_t k = 2; k <= n; k <<= 1)
+		for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+			for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) {
+				const uint32_t l = i ^ j;
+				if (l > i) {
+					const unsigned long long x = a[i], y = a[l];
+					if (((i & k) == 0) == (x > y)) { a[i] = y; a[l] = x; }
+				}
+			}
+			__syncthreads();
+		}
+}
+__device__ __forceinline__ uint32_t posting_at(const uint8_t *p, uint32_t e, int big) {
+	if (big) { const uint8_t *q = p + (size_t)e * 3; return (uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16); }
+	const uint8_t *q = p + (size_t)(e >> 1) * 5;
+	if (!(e & 1)) return ((uint32_t)q[0] | ((uint32_t)q[1] << 8) | ((uint32_t)q[2] << 16)) & 0xFFFFFu;
+	return (((uint32_t)q[2] >> 4) | ((uint32_t)q[3] << 4) | ((uint32_t)q[4] << 12)) & 0xFFFFFu;
+}
+
+__global__ void __launch_bounds__(128) k_candgen(CandArgs A) {
+	extern __shared__ __align__(16) unsigned long long csm[];
+	unsigned long long *pairs = csm;                       // pmax: (word << 5 | query), later reused for the candidate keys
+	__shared__ uint32_t s_len[16], s_mm[16], s_off[17], s_np, s_ncache, s_ncand, s_minmm, s_base, s_nq, s_nlong, s_tot;
+	__shared__ uint32_t s_long[128];                        // heads whose posting lists are long: walked by whole warps
+	const uint32_t N = (uint32_t)A.N;
+	uint32_t *cnt = A.cnt + (size_t)blockIdx.x * A.num_clumps, *first = A.first + (size_t)blockIdx.x * A.num_clumps, *cache = A.cache + (size_t)blockIdx.x * A.num_clumps;
+	uint32_t *candp = (uint32_t *)(csm + A.pmax);          // cmax clump ids, parallel to the candidate keys
+	for (uint32_t b = blockIdx.x; b < A.nbunch; b += gridDim.x) {
+		const uint32_t z = b * A.qbunch, nb = min(A.qbunch, A.nq - z);
+		if (threadIdx.x == 0) { s_np = 0; s_ncache = 0; s_ncand = 0; s_minmm = 0xFFFFFFFFu; s_nq = nb; s_nlong = 0; }
+		__syncthreads();
+		if (threadIdx.x < nb) {                                // thresholds (burst.c:4091-4095, 4163-4164)
+			const QInfo Q = A.qi[z + threadIdx.x];
+			const uint32_t len = Q.len, kload = (uint32_t)Q.k * N + N;
+			uint32_t mmatch = kload < len ? len - kload : 0;
+			const uint32_t heur = A.heur ? (len >> 4) + 1u : 0u;
+			if (mmatch < heur) mmatch = heur;
+			atomicMin(&s_minmm, mmatch);
+			s_mm[threadIdx.x] = kload < len ? len - kload : 1;
+			s_len[threadIdx.x] = len;
+		}
+		__syncthreads();
+		// ---- words ----
+		if (threadIdx.x == 0) {
+			uint32_t t = 0;
+			for (uint32_t j = 0; j < nb; ++j) { s_off[j] = t; t += s_len[j] >= N ? s_len[j] - N + 1 : 0; }
+			s_off[nb] = t;
+			if (t > A.pmax) { atomicExch(&A.counters[C_ERR], 0x20000000u | b); t = 0; for (uint32_t j = 0; j <= nb; ++j) s_off[j] = 0; }   // queries longer than the pair array was sized for
+			s_np = t;
+		}
+		__syncthreads();
+		for (uint32_t j = 0; j < nb; ++j) {
+			const QInfo Q = A.qi[z + j];
+			const uint32_t *Wq = A.qnib + (Q.off >> 3) + 3ull * (z + j) + 2;
+			const uint32_t base = s_off[j], nw = s_off[j + 1] - base;
+			for (uint32_t p = threadIdx.x; p < nw; p += blockDim.x) {
+				unsigned long long w = 0;
+				for (uint32_t t = 0; t < N; ++t) { const uint32_t x = p + t; w = (w << 2) | (((Wq[x >> 3] >> (4 * (x & 7))) & 15u) - 1u); }
+				pairs[base + p] = (w << 5) | j;
+			}
+		}
+		__syncthreads();
+		const uint32_t np = s_np;
+		uint32_t n2 = 2; while (n2 < np) n2 <<= 1;
+		for (uint32_t i = np + threadIdx.x; i < n2; i += blockDim.x) pairs[i] = ~0ull;
+		__syncthreads();
+		bitonic_sort_u64(pairs, n2);
+		// ---- count: thread i owns the distinct word that starts at i ----
+		for (uint32_t i0 = 0; i0 < np; i0 += blockDim.x) {
+			const uint32_t i = i0 + threadIdx.x;
+			if (i < np) {
+				const unsigned long long w = pairs[i] >> 5;
+				if (i == 0 || (pairs[i - 1] >> 5) != w) {
+					uint32_t mx = 0, e = i;
+					while (e < np && (pairs[e] >> 5) == w) { uint32_t r = e; while (r < np && pairs[r] == pairs[e]) ++r; mx = max(mx, r - e); e = r; }
+					const unsigned long long o0 = A.acx_off[w], o1 = A.acx_off[w + 1];
+					const uint32_t L = A.big ? (uint32_t)((o1 - o0) / 3) : (uint32_t)(((o1 - o0) / 5) * 2 + ((o1 - o0) % 5 ? 1 : 0));
+					if (L > 64) { const uint32_t s = atomicAdd(&s_nlong, 1u); if (s < 128) s_long[s] = i | (mx << 16); else {
+						const uint8_t *pp = A.post + o0;                  // (queue full: walk it alone)
+						for (uint32_t t = 0; t < L; ++t) { const uint32_t c = posting_at(pp, t, A.big); if (c < A.num_clumps) { if (atomicAdd(&cnt[c], mx) == 0) cache[atomicAdd(&s_ncache, 1u)] = c; atomicMin(&first[c], (i << 19) | min(t, 0x7FFFFu)); } }
+					} }
+					else {
+						const uint8_t *pp = A.post + o0;
+						for (uint32_t t = 0; t < L; ++t) { const uint32_t c = posting_at(pp, t, A.big); if (c < A.num_clumps) { if (atomicAdd(&cnt[c], mx) == 0) cache[atomicAdd(&s_ncache, 1u)] = c; atomicMin(&first[c], (i << 19) | min(t, 0x7FFFFu)); } }
+					}
+				}
+			}
+			__syncthreads();
+			// long posting lists of this round: a warp each
+			const uint32_t nl = min(s_nlong, 128u);
+			for (uint32_t s = threadIdx.x >> 5; s < nl; s += blockDim.x >> 5) {
+				const uint32_t i = s_long[s] & 0xFFFFu, mx = s_long[s] >> 16;
+				const unsigned long long w = pairs[i] >> 5, o0 = A.acx_off[w], o1 = A.acx_off[w + 1];
+				const uint32_t L = A.big ? (uint32_t)((o1 - o0) / 3) : (uint32_t)(((o1 - o0) / 5) * 2 + ((o1 - o0) % 5 ? 1 : 0));
+				const uint8_t *pp = A.post + o0;
+				for (uint32_t t = threadIdx.x & 31; t < L; t += 32) { const uint32_t c = posting_at(pp, t, A.big); if (c < A.num_clumps) { if (atomicAdd(&cnt[c], mx) == 0) cache[atomicAdd(&s_ncache, 1u)] = c; atomicMin(&first[c], (i << 19) | min(t, 0x7FFFFu)); } }
+			}
+			__syncthreads();
+			if (threadIdx.x == 0) s_nlong = 0;
+			__syncthreads();
+		}
+		// ---- pick: candidates sorted by (count descending, first touch ascending); the key carries the slot of the clump id ----
+		const uint32_t ncache = s_ncache, minmm = s_minmm;
+		unsigned long long *ckey = pairs;                       // (the pairs are done with)
+		__syncthreads();
+		for (uint32_t i = threadIdx.x; i < ncache; i += blockDim.x) {
+			const uint32_t c = cache[i], v = min(cnt[c], 65535u), f = first[c];
+			cnt[c] = 0; first[c] = 0xFFFFFFFFu;
+			if (v > minmm) {
+				const uint32_t s = atomicAdd(&s_ncand, 1u);
+				if (s < A.cmax) { candp[s] = c; ckey[s] = ((unsigned long long)(65535u - v) << 48) | ((unsigned long long)f << 16) | s; }
+				else atomicExch(&A.counters[C_ERR], 0x40000000u | b);    // more candidates than the list holds: reported, the call fails (raise cmax)
+			}
+		}
+		__syncthreads();
+		const uint32_t ncand = min(s_ncand, A.cmax);
+		uint32_t c2 = 2; while (c2 < ncand) c2 <<= 1;
+		for (uint32_t i = ncand + threadIdx.x; i < c2; i += blockDim.x) ckey[i] = ~0ull;
+		__syncthreads();
+		if (ncand > 1) bitonic_sort_u64(ckey, c2);
+		// ---- emit: per candidate the maximal ranges of queries whose own threshold it passes (burst.c:4163-4168), then the BadList ----
+		uint32_t *nsr = candp + A.cmax;                          // sub-runs per candidate, then their exclusive prefix
+		for (uint32_t s = threadIdx.x; s < ncand; s += blockDim.x) {
+			const uint32_t v = 65535u - (uint32_t)(ckey[s] >> 48);
+			uint32_t r = 0; bool in = false;
+			for (uint32_t j = 0; j < nb; ++j) { const bool p = v > s_mm[j]; r += p && !in; in = p; }
+			nsr[s] = r;
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			uint32_t t = 0;
+			for (uint32_t s = 0; s < ncand; ++s) { const uint32_t r = nsr[s]; nsr[s] = t; t += r; }
+			const uint32_t tot = t + (A.skip_bad ? 0u : A.nbad);
+			s_tot = t;
+			s_base = tot ? atomicAdd(&A.counters[C_RUNS], tot) : 0u;
+		}
+		__syncthreads();
+		const uint32_t base = s_base;
+		for (uint32_t s = threadIdx.x; s < ncand; s += blockDim.x) {
+			const uint32_t v = 65535u - (uint32_t)(ckey[s] >> 48), clump = candp[(uint32_t)ckey[s] & 0xFFFFu];
+			uint32_t o = base + nsr[s], a0 = 0;
+			while (a0 < nb) {
+				while (a0 < nb && !(v > s_mm[a0])) ++a0;
+				uint32_t b0 = a0;
+				while (b0 < nb && v > s_mm[b0]) ++b0;
+				if (b0 > a0) { if (o < A.runs_cap) { bg_run R; R.clump = clump; R.query0 = z + a0; R.nq = b0 - a0; A.runs[o] = R; } ++o; }
+				a0 = b0;
+			}
+		}
+		if (!A.skip_bad) for (uint32_t s = threadIdx.x; s < A.nbad; s += blockDim.x) {
+			const uint32_t o = base + s_tot + s;
+			if (o < A.runs_cap) { bg_run R; R.clump = A.bad[s]; R.query0 = z; R.nq = nb; A.runs[o] = R; }           // (ids outside the loaded clump range are skipped by every kernel)
+		}
+		__syncthreads();
+	}
+}
+
+// hits of a device-generated run list -> (strand, clump) form
+__global__ void k_xhits(const bg_hit *__restrict__ in, const bg_run *__restrict__ runs, uint32_t n, bg_xhit *__restrict__ out) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	const bg_hit h = in[i]; const bg_run R = runs[h.task >> 4];
+	bg_xhit x; x.query = R.query0 + (h.task & 15); x.clump = R.clump; x.lane = h.lane; x.ed = h.ed; x.gap_q = h.gap_q; x.gap_r = h.gap_r; x.final_pos = h.final_pos;
+	out[i] = x;
+}
+// bytes of every posting list from the on-disk lengths (burst.c:3504-3527)
+__global__ void k_acx_sizes(const uint32_t *__restrict__ lens, unsigned long long nk, int big, unsigned long long *__restrict__ out) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i > nk) return;
+	const uint32_t L = i < nk ? lens[i] : 0u;
+	out[i] = big ? (unsigned long long)L * 3 : (unsigned long long)(L / 2u) * 5 + (L & 1u) * 3;
+}
+
 // run validation (explicit run lists): malformed runs raise the error flag
 __global__ void k_check_runs(const bg_run *__restrict__ runs, uint64_t nruns, uint32_t q_base, uint32_t nq, uint32_t *counters) {
 	uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1705,6 +1904,8 @@ struct bg_ctx {
 	DBuf<uint8_t> d_packed; DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
 	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
+	DBuf<unsigned long long> d_acx_off; DBuf<uint8_t> d_post; DBuf<uint32_t> d_bad, d_cg_cnt, d_cg_first, d_cg_cache; DBuf<bg_xhit> d_xhits;   // accelerator on the device, candidate-generation scratch
+	int acx_n = 0, acx_big = 0; uint32_t acx_nbad = 0, acx_clumps = 0, cg_blocks = 0; uint32_t runs_cap = 0;
 	DBuf<uint16_t> d_rlen, d_rbud; DBuf<uint32_t> d_strand, d_candoff, d_cand; DBuf<unsigned long long> d_rl64, d_sl64, d_roff;   // compact strand batches
 	DBuf<uint32_t> d_cls; DBuf<uint4> d_xs;                       // band-class bins of the survivors, expanded records (k_bin_*)
 	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
@@ -1781,7 +1982,8 @@ extern "C" void bg_free(bg_ctx *c) {
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
 	c->d_packed.release(); c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
 	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
-	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_cls.release(); c->d_xs.release(); c->d_rlen.release(); c->d_rbud.release(); c->d_strand.release(); c->d_candoff.release(); c->d_cand.release(); c->d_rl64.release(); c->d_sl64.release(); c->d_roff.release();
+	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_acx_off.release(); c->d_post.release(); c->d_bad.release(); c->d_cg_cnt.release(); c->d_cg_first.release(); c->d_cg_cache.release(); c->d_xhits.release();
+	c->d_cls.release(); c->d_xs.release(); c->d_rlen.release(); c->d_rbud.release(); c->d_strand.release(); c->d_candoff.release(); c->d_cand.release(); c->d_rl64.release(); c->d_sl64.release(); c->d_roff.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
 	c->d_keys.release(); c->d_keys2.release(); c->d_order.release(); c->d_order2.release(); c->d_sort_tmp.release();
 	for (int i = 0; i < 4; ++i) if (c->ev[i]) cudaEventDestroy(c->ev[i]);
@@ -2649,6 +2851,146 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
 	}
 	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
+}
+
+extern "C" int bg_load_acx(bg_ctx *c, const uint32_t *lens, const uint8_t *postings, uint64_t post_bytes, int word_len, int big, const uint32_t *bad, uint32_t nbad) {
+	if (!c || !lens || (!postings && post_bytes) || (!bad && nbad)) return fail(BG_EINVAL, "bg_load_acx: null argument");
+	if (word_len != 12 && word_len != 15) return fail(BG_EINVAL, "bg_load_acx: word length %d (must be 12 or 15)", word_len);
+	if (!c->num_clumps) return fail(BG_EINVAL, "bg_load_acx: load the database first");
+	CU(cudaSetDevice(c->device));
+	const unsigned long long nk = 1ull << (2 * word_len);
+	c->acx_n = 0;
+	if (c->d_acx_off.need(nk + 1) || c->d_post.need(post_bytes + 32) || c->d_bad.need((size_t)nbad + 1)) return BG_ENOMEM;
+	{	// lengths -> byte sizes -> offsets, through a bounded staging buffer
+		const unsigned long long SLAB = 64ull << 20;                   // entries per piece
+		DBuf<uint32_t> stage; if (stage.need(std::min(nk, SLAB))) return BG_ENOMEM;
+		for (unsigned long long a = 0; a < nk; a += SLAB) {
+			const unsigned long long n = std::min(SLAB, nk - a);
+			CU(cudaMemcpyAsync(stage.p, lens + a, n * 4, cudaMemcpyHostToDevice, c->stream));
+			k_acx_sizes<<<(unsigned)((n + 255) / 256), 256, 0, c->stream>>>(stage.p, n, big, c->d_acx_off.p + a);   // (writes n + 1 entries; the last is overwritten by the next piece)
+			CU(cudaStreamSynchronize(c->stream));
+		}
+		CU(cudaMemsetAsync(c->d_acx_off.p + nk, 0, 8, c->stream));
+		size_t tmp = 0;
+		CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp, c->d_acx_off.p, c->d_acx_off.p, (int)(nk + 1), c->stream));
+		if (c->d_sort_tmp.need(tmp + 16)) { stage.release(); return BG_ENOMEM; }
+		CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp, c->d_acx_off.p, c->d_acx_off.p, (int)(nk + 1), c->stream));
+		unsigned long long total = 0;
+		CU(cudaMemcpyAsync(&total, c->d_acx_off.p + nk, 8, cudaMemcpyDeviceToHost, c->stream));
+		CU(cudaStreamSynchronize(c->stream));
+		stage.release();
+		if (total != post_bytes) return fail(BG_EINVAL, "bg_load_acx: the lengths describe %llu bytes of postings, %llu given", total, (unsigned long long)post_bytes);
+	}
+	if (post_bytes) CU(cudaMemcpyAsync(c->d_post.p, postings, post_bytes, cudaMemcpyHostToDevice, c->stream));
+	CU(cudaMemsetAsync(c->d_post.p + post_bytes, 0, 32, c->stream));
+	if (nbad) CU(cudaMemcpyAsync(c->d_bad.p, bad, (size_t)nbad * 4, cudaMemcpyHostToDevice, c->stream));
+	// per-clump counters of the resident candidate-generation blocks (the accelerator names clumps of the whole database)
+	c->acx_clumps = c->first_clump + c->num_clumps;
+	uint32_t blocks = (uint32_t)c->sms * 4;
+	while (blocks > (uint32_t)c->sms && (size_t)blocks * c->acx_clumps * 12 > (4ull << 30)) blocks -= (uint32_t)c->sms;
+	c->cg_blocks = blocks;
+	const size_t ne = (size_t)blocks * c->acx_clumps;
+	if (c->d_cg_cnt.need(ne) || c->d_cg_first.need(ne) || c->d_cg_cache.need(ne)) return BG_ENOMEM;
+	CU(cudaMemsetAsync(c->d_cg_cnt.p, 0, ne * 4, c->stream));
+	CU(cudaMemsetAsync(c->d_cg_first.p, 0xFF, ne * 4, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	c->acx_n = word_len; c->acx_big = big; c->acx_nbad = nbad;
+	return BG_OK;
+}
+
+extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, int heuristic, int skip_bad, int mode,
+		uint16_t *best_inout, bg_xhit *hits, uint64_t cap, uint64_t *nhits) {
+	if (!c || !R || !nhits || (!hits && cap)) return fail(BG_EINVAL, "bg_search_bunches_into: null argument");
+	if (!c->acx_n) return fail(BG_EINVAL, "bg_search_bunches_into: no accelerator loaded (bg_load_acx)");
+	if (!R->reads || !R->len || !R->budget || !R->strand || !R->nreads || !R->nq) return fail(BG_EINVAL, "bg_search_bunches_into: null or empty read arrays");
+	if (R->flags != BG_R_PACKED2) return fail(BG_EINVAL, "bg_search_bunches_into: reads must be BG_R_PACKED2 (plain bases)");
+	if (!qbunch || qbunch > BG_RUN_MAX) return fail(BG_EINVAL, "bg_search_bunches_into: bunch size %u (must be 1..%d)", qbunch, BG_RUN_MAX);
+	CU(cudaSetDevice(c->device));
+	c->kind = WORK_NONE; c->ran = false;
+	const uint32_t nq = R->nq, nr = R->nreads, nbunch = (nq + qbunch - 1) / qbunch;
+	cudaStream_t st = c->stream;
+	uint64_t total = 0; uint32_t maxlen = 0;
+	for (uint32_t r = 0; r < nr; ++r) { total += R->len[r]; maxlen = std::max<uint32_t>(maxlen, R->len[r]); }
+	const uint64_t rbytes = (total + 3) / 4, ncodes_max = (uint64_t)nq * (((uint64_t)maxlen + 15) & ~15ull);
+	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) ||
+	    c->d_qoff.need((size_t)nq + 1) || c->d_qi.need(nq) || c->d_peq.need((size_t)nq * 16) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8) ||
+	    c->d_packed.need(rbytes + 32) || c->d_codes.need(ncodes_max + 32) || c->d_qnib.need(ncodes_max / 8 + 3ull * nq + 8)) return BG_ENOMEM;
+	size_t tmp1 = 0, tmp2 = 0;
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
+	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
+	if (c->d_sort_tmp.need(std::max(tmp1, tmp2) + 16)) return BG_ENOMEM;
+	// ---- strands on the device (as bg_align_bunches_into) ----
+	CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_strand.p, R->strand, (size_t)nq * 4, cudaMemcpyHostToDevice, st));
+	CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, st));
+	CU(cudaMemsetAsync(c->d_counters.p, 0, 256, st));
+	k_compact_rlen<<<(nr + 256) / 256, 256, 0, st>>>(c->d_rlen.p, nr, c->d_rl64.p);
+	k_compact_slen<<<(nq + 256) / 256, 256, 0, st>>>(c->d_rlen.p, nr, c->d_strand.p, nq, c->d_sl64.p, c->d_counters.p);
+	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
+	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
+	k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, st>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
+	k_compact_qinfo<<<(nq + 255) / 256, 256, 0, st>>>((const unsigned long long *)c->d_qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, nq, nr, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
+	CU(cudaGetLastError());
+	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, st));
+	CU(cudaStreamSynchronize(st));
+	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_search_bunches_into: malformed batch (strands must name reads < nreads, read lengths >= 1, budgets <= 254)");
+	c->SL = choose_layout(c, c->h_pinned + 16, nq);
+	c->mstage = stage_len(maxlen);
+	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
+	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, st>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
+	CU(cudaGetLastError());
+	c->nq = nq; c->nslots = nr;
+	// ---- candidates -> runs on the device ----
+	CandArgs G;
+	G.qi = c->d_qi.p; G.qnib = c->d_qnib.p; G.nq = nq; G.qbunch = qbunch; G.nbunch = nbunch;
+	G.acx_off = c->d_acx_off.p; G.post = c->d_post.p; G.big = c->acx_big; G.N = c->acx_n; G.num_clumps = c->acx_clumps;
+	G.bad = c->d_bad.p; G.nbad = c->acx_nbad; G.heur = heuristic; G.skip_bad = skip_bad;
+	G.cnt = c->d_cg_cnt.p; G.first = c->d_cg_first.p; G.cache = c->d_cg_cache.p; G.counters = c->d_counters.p;
+	{ const uint32_t words = maxlen >= (uint32_t)c->acx_n ? maxlen - c->acx_n + 1 : 1; uint32_t pm = 1024; while (pm < qbunch * words) pm <<= 1;
+	  if (pm > 8192) return fail(BG_EINVAL, "bg_search_bunches_into: reads of %u bases need %u (word, query) pairs per bunch, the device path holds 8192", maxlen, qbunch * words);
+	  G.pmax = pm; G.cmax = std::min<uint32_t>(pm, 4096); }
+	const size_t cg_smem = (size_t)G.pmax * 8 + (size_t)G.cmax * 8;
+	if (cg_smem > 48 * 1024) CU(cudaFuncSetAttribute(k_candgen, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cg_smem));
+	if (!c->runs_cap) c->runs_cap = 1u << 20;
+	c->runs_cap = (uint32_t)std::min<uint64_t>((1ull << 28) - 2, std::max<uint64_t>(c->runs_cap, (uint64_t)nbunch * (12 + (skip_bad ? 0 : c->acx_nbad))));
+	uint64_t nruns = 0;
+	for (int attempt = 0; attempt < 3; ++attempt) {
+		if (c->d_runs.need((size_t)c->runs_cap + 1)) return BG_ENOMEM;
+		G.runs = c->d_runs.p; G.runs_cap = c->runs_cap;
+		CU(cudaMemsetAsync(c->d_counters.p + C_RUNS, 0, 4, st));
+		k_candgen<<<std::min<uint32_t>(nbunch, c->cg_blocks), 128, cg_smem, st>>>(G);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		if (c->h_pinned[C_ERR]) return fail(BG_EOVERFLOW, "bg_search_bunches_into: a bunch has more candidates or words than the device tables hold (flag %#x); use the host candidate lists for this batch", c->h_pinned[C_ERR]);
+		nruns = c->h_pinned[C_RUNS];
+		if (nruns <= c->runs_cap) break;
+		if (nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_search_bunches_into: %llu runs in one batch (limit 2^28-1); use smaller batches", (unsigned long long)nruns);
+		c->runs_cap = (uint32_t)(nruns + nruns / 8);
+	}
+	if (nruns > c->runs_cap) return fail(BG_EOVERFLOW, "bg_search_bunches_into: run list kept overflowing");
+	c->kind = WORK_RUNS; c->nruns = nruns; c->ntasks = nruns * BG_RUN_MAX; c->ntiles = 0;
+	CU(cudaMemsetAsync(c->d_counters.p, 0, 32, st));                   // (k_qprep's statistics at [9..11] stay)
+	int rc = finish_upload(c); if (rc) return rc;
+	rc = bg_batch_run(c, mode, best_inout); if (rc) return rc;
+	uint64_t n = 0;
+	rc = bg_batch_count(c, &n); if (rc) return rc;
+	*nhits = n;
+	if (n > cap) return fail(BG_EOVERFLOW, "bg_search_bunches_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap);
+	rc = sort_hits(c, (uint32_t)n); if (rc) return rc;
+	if (n) {
+		if (c->d_xhits.need(n)) return BG_ENOMEM;
+		k_xhits<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(c->d_hits_sorted.p, c->d_runs.p, (uint32_t)n, c->d_xhits.p);
+		CU(cudaGetLastError());
+		CU(cudaMemcpyAsync(hits, c->d_xhits.p, n * sizeof(bg_xhit), cudaMemcpyDeviceToHost, st));
+	}
+	if (best_inout) {
+		k_best16<<<(nr + 255) / 256, 256, 0, st>>>(c->d_best.p, c->d_best16.p, nr);
+		CU(cudaMemcpyAsync(best_inout, c->d_best16.p, (size_t)nr * 2, cudaMemcpyDeviceToHost, st));
+	}
+	CU(cudaStreamSynchronize(st));
+	return BG_OK;
 }
 
 static int finish_align(bg_ctx *c, int mode, uint16_t *best_inout, bg_hit **hits, uint64_t *nhits) {

@@ -12,6 +12,8 @@ LIB_PATH = os.path.join(HERE, "libburst_b200.so")
 
 HIT_DTYPE = np.dtype([("task", "<u4"), ("lane", "u1"), ("ed", "u1"), ("gap_q", "u1"),
                       ("gap_r", "u1"), ("final_pos", "<u4")])
+XHIT_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4"), ("lane", "u1"), ("ed", "u1"), ("gap_q", "u1"),
+                       ("gap_r", "u1"), ("final_pos", "<u4")])
 TASK_DTYPE = np.dtype([("query", "<u4"), ("clump", "<u4")])
 RUN_DTYPE = np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")])
 RUN_MAX = 16
@@ -48,7 +50,8 @@ EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scori
            "bg_load_db", "bg_batch_upload", "bg_batch_run", "bg_batch_run_extend", "bg_batch_best_device",
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
            "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into",
-           "bg_host_alloc", "bg_host_free", "bg_align_bunches_into", "bg_stream", "bg_set_surv_cap"]
+           "bg_host_alloc", "bg_host_free", "bg_align_bunches_into", "bg_stream", "bg_set_surv_cap",
+           "bg_load_acx", "bg_search_bunches_into"]
 
 
 def load_library(path=None):
@@ -92,6 +95,9 @@ def load_library(path=None):
     L.bg_stream.argtypes = [C.c_void_p]
     L.bg_set_surv_cap.argtypes = [C.c_void_p, C.c_uint32]
     L.bg_host_alloc.argtypes = [C.c_uint64]
+    L.bg_load_acx.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int, C.c_void_p, C.c_uint32]
+    L.bg_search_bunches_into.argtypes = [C.c_void_p, C.POINTER(BgReads), C.c_uint32, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.bg_host_free.argtypes = [C.c_void_p]
     return L
 
@@ -173,6 +179,25 @@ class Engine:
         nh = C.c_uint64(0)
         self._check(self.lib.bg_align_bunches_into(self.ctx, C.byref(R), qbunch, cand_off.ctypes.data, cand.ctypes.data, len(cand_off) - 1, mode,
                                                    None if best_inout is None else best_inout.ctypes.data, hits_out.ctypes.data, len(hits_out), C.byref(nh)))
+        return int(nh.value)
+
+    def load_acx(self, lens, postings, word_len, big, bad):
+        """bg_load_acx: the k-mer accelerator in its on-disk form (per-word posting counts, packed postings, BadList)."""
+        lens = np.ascontiguousarray(lens, np.uint32); postings = np.ascontiguousarray(postings, np.uint8); bad = np.ascontiguousarray(bad, np.uint32)
+        assert len(lens) == 1 << (2 * word_len)
+        self._check(self.lib.bg_load_acx(self.ctx, lens.ctypes.data, postings.ctypes.data, C.c_uint64(len(postings)), word_len, int(big), bad.ctypes.data, len(bad)))
+
+    def search_bunches_into(self, reads, rlen, rbudget, strand, qbunch, hits_out, best_inout=None, mode=MODE_MIN, heuristic=False, skip_bad=False):
+        """bg_search_bunches_into: candidates from the loaded accelerator on the device, then the alignment; `reads` = pack2 of the read
+        codes, `hits_out` an XHIT_DTYPE array.  Returns the number of hits."""
+        rlen = np.ascontiguousarray(rlen, np.uint16); rbudget = np.ascontiguousarray(rbudget, np.uint16)
+        strand = np.ascontiguousarray(strand, np.uint32); reads = np.ascontiguousarray(reads, np.uint8)
+        assert hits_out.dtype == XHIT_DTYPE
+        R = BgReads(reads.ctypes.data, rlen.ctypes.data, rbudget.ctypes.data, strand.ctypes.data, len(rlen), len(strand), R_PACKED2)
+        self._nslots = len(rlen)
+        nh = C.c_uint64(0)
+        self._check(self.lib.bg_search_bunches_into(self.ctx, C.byref(R), qbunch, int(heuristic), int(skip_bad), mode,
+                                                    None if best_inout is None else best_inout.ctypes.data, hits_out.ctypes.data, C.c_uint64(len(hits_out)), C.byref(nh)))
         return int(nh.value)
 
     def _queries(self, codes, offset, budget, slot, nslots):

@@ -46,7 +46,7 @@ static long REBASE_AMT = 500, DB_QLEN = 500; static int REBASE = 0, ACX_N = 12; 
 static float TAXLEVELS_STRICT[] = {.65f, .75f, .78f, .82f, .86f, .94f, .98f, .995f},
              TAXLEVELS_LENIENT[] = {.55f, .70f, .75f, .80f, .84f, .93f, .97f, .985f},   /* burst.c:264-266 */
              *TAXLEVELS = TAXLEVELS_LENIENT;
-static int QUIET = 0, GPU_DEVICE = 0, NGPU = 1, THREADS = 1, SHARD_REFS = 0;
+static int QUIET = 0, GPU_DEVICE = 0, NGPU = 1, THREADS = 1, SHARD_REFS = 0, DEVICE_CAND = 0;
 
 static uint8_t CHAR2NUM[256];
 static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};   /* burst.c:168 */
@@ -425,7 +425,7 @@ static void die_gpu(const char *what, int rc) {
  * 4085-4133).  The file does not record N (12 or 15, a compile-time constant of the reference
  * binary, burst.c:96-98); it is inferred from the file size.
  * ============================================================================================= */
-typedef struct { uint64_t *off; uint8_t *post; uint32_t *bad, nbad; int big; uint64_t nk; } Acx;
+typedef struct { uint64_t *off; uint8_t *post; uint32_t *bad, nbad; int big; uint64_t nk; uint32_t *lens; uint64_t post_bytes; } Acx;
 static const uint8_t AMBIG_N[16] = {0, 1, 1, 1, 1, 4, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3};
 static const uint8_t AMBIG_B[16][4] = {{0}, {0}, {1}, {2}, {3}, {0, 1, 2, 3}, {2, 3}, {0, 1}, {0, 2}, {1, 3}, {1, 2}, {0, 3},
 	{1, 2, 3}, {0, 1, 2}, {0, 1, 3}, {0, 2, 3}};                              /* burst.c:1372-1375 */
@@ -469,6 +469,8 @@ static void load_acx(const char *fn, Acx *A) {
 			}
 			A->post = xmalloc(bytes + 16); rd(A->post, 1, bytes, in); memset(A->post + bytes, 0, 16);
 			A->bad = xmalloc((uint64_t)szBL * 4 + 4); rd(A->bad, 4, szBL, in); A->nbad = szBL;
+			A->post_bytes = bytes;
+			if (DEVICE_CAND) { A->lens = Lens; Lens = NULL; }                  /* bg_load_acx takes the on-disk form */
 		}
 		free(Lens);
 	}
@@ -918,6 +920,128 @@ static void accel_search(bg_ctx **ctxs, int ngpu, Queries *Q, Refs *R, Acx *A, P
 	for (int b = 0; b < ngpu * 2; ++b) { Batch *B = BT + b; free(B->br); bg_host_free(B->runs); bg_host_free(B->codes); bg_host_free(B->off); bg_host_free(B->bud); bg_host_free(B->slot); bg_host_free(B->hits); }
 	for (int g = 0; g < ngpu; ++g) free(best[g]);
 	free(best); free(GS); free(BT); free(SPods);
+}
+
+/* =============================================================================================
+ * --device-candidates: the accelerator lives on the GPU (bg_load_acx) and a batch is just its reads at 2 bits
+ * per base plus one word per strand; the candidates of every bunch are counted, ranked and cut into runs by the device
+ * (bg_search_bunches_into), which returns hits that name strand and clump.  Same bunches, same candidate rule; among clumps of EQUAL
+ * count the device keeps first-touch order, which is the reference's order for lists of <= 24 clumps (its insertion sort) and for
+ * longer lists whatever the C library's qsort leaves (burst.c:4038-4046) -- so BEST/CAPITALIST may pick a different one of several
+ * equally good references there; ALLPATHS and FORAGE rows are the same set.  Queries with ambiguous bases need every variant of
+ * every window (burst.c:3232-3236): when the accelerated bin holds any, the host lists are used instead.
+ * ============================================================================================= */
+typedef struct {
+	uint64_t qa, qb; uint32_t nreads;
+	uint8_t *reads; uint16_t *len, *bud, *best; uint32_t *strand; uint64_t *roff; uint64_t *six;      /* page-locked: reads/len/bud/strand/best */
+	const char **src; uint8_t *srcrc; uint64_t cap_r, cap_q, nh;
+	bg_xhit *hits; uint64_t hitcap;
+} DevBatch;
+static void accel_search_device(bg_ctx **ctxs, int ngpu, Queries *Q, Refs *R, Acx *A, PodList *Pods, int mode, int threads) {
+	uint64_t nAcc = Q->QBins[1], newUniqQ = Q->newUniqQ;
+	if (!nAcc) return;
+	uint64_t QBUNCH = newUniqQ / ((uint64_t)threads * 128);
+	if (QBUNCH > 16) QBUNCH = 16;
+	if (!QBUNCH) QBUNCH = 1;
+	printf("Setting QBUNCH to %" PRIu64 "\nUsing ACCELERATOR (on the GPU) to align %" PRIu64 " unique queries...\n", QBUNCH, nAcc);
+	double t0 = now();
+	for (int g = 0; g < ngpu; ++g) { int rc = bg_load_acx(ctxs[g], A->lens, A->post, A->post_bytes, SCOUR_N, A->big, A->bad, A->nbad); if (rc) die_gpu("bg_load_acx", rc); }
+	free(A->lens); A->lens = NULL;
+	double t_load = now() - t0;
+	const uint64_t nbunch = (nAcc + QBUNCH - 1) / QBUNCH;
+	uint64_t bpb = (nbunch + (uint64_t)ngpu * 4 - 1) / ((uint64_t)ngpu * 4);
+	if (bpb < 2048) bpb = 2048;
+	if (bpb > 65536) bpb = 65536;
+	const uint64_t nbatch = (nbunch + bpb - 1) / bpb;
+	uint16_t *best = xmalloc(Q->numUniqQ * sizeof(*best));
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) best[i] = 0xFFFF;
+	uint32_t *lid = xmalloc(Q->numUniqQ * 4), *stamp = xcalloc(Q->numUniqQ, 4);
+	PodList *SPods = xcalloc(newUniqQ, sizeof(*SPods));
+	DevBatch *BT = xcalloc((size_t)ngpu, sizeof(*BT));
+	double t_pack = 0, t_gpu = 0;
+	for (uint64_t w0 = 0; w0 < nbatch; w0 += (uint64_t)ngpu) {
+		double ta = now();
+		int nb_wave = (int)MIN((uint64_t)ngpu, nbatch - w0);
+		for (int g = 0; g < nb_wave; ++g) {                               /* the batch's distinct reads, in order of first appearance */
+			DevBatch *B = BT + g; uint64_t b0 = (w0 + (uint64_t)g) * bpb, b1 = MIN(nbunch, b0 + bpb);
+			B->qa = b0 * QBUNCH; B->qb = MIN(nAcc, b1 * QBUNCH);
+			uint64_t nq = B->qb - B->qa;
+			if (nq + 1 > B->cap_q) {
+				bg_host_free(B->strand); bg_host_free(B->len); bg_host_free(B->bud); bg_host_free(B->best); free(B->roff); free(B->six); free(B->src); free(B->srcrc);
+				B->cap_q = nq + nq / 8 + 64;
+				B->strand = bg_host_alloc(B->cap_q * 4); B->len = bg_host_alloc(B->cap_q * 2); B->bud = bg_host_alloc(B->cap_q * 2); B->best = bg_host_alloc(B->cap_q * 2);
+				B->roff = xmalloc((B->cap_q + 1) * 8); B->six = xmalloc(B->cap_q * 8); B->src = xmalloc(B->cap_q * sizeof(*B->src)); B->srcrc = xmalloc(B->cap_q);
+				if (!B->strand || !B->len || !B->bud || !B->best) { fputs("OOM: page-locked batch buffers\n", stderr); exit(3); }
+			}
+			const uint32_t epoch = (uint32_t)(w0 + (uint64_t)g) + 1; uint32_t nr = 0; uint64_t tot = 0;
+			for (uint64_t j = 0; j < nq; ++j) {
+				const UniBin *u = Q->UniBins + B->qa + j; const ShrBin *sb = Q->ShrBins + u->six;
+				if (stamp[u->six] != epoch) {
+					stamp[u->six] = epoch; lid[u->six] = nr;
+					B->len[nr] = (uint16_t)sb->len; B->bud[nr] = sb->ed; B->best[nr] = best[u->six]; B->six[nr] = u->six; B->src[nr] = u->seq; B->srcrc[nr] = u->rc;
+					B->roff[nr] = tot; tot += sb->len; ++nr;
+				}
+				B->strand[j] = lid[u->six] | (u->rc ? 0x80000000u : 0u);
+			}
+			B->roff[nr] = tot; B->nreads = nr;
+			if (tot / 4 + 64 > B->cap_r) { bg_host_free(B->reads); B->cap_r = tot / 4 + tot / 32 + 256; B->reads = bg_host_alloc(B->cap_r); if (!B->reads) { fputs("OOM: page-locked batch buffers\n", stderr); exit(3); } }
+			memset(B->reads, 0, tot / 4 + 16);
+			#pragma omp parallel for schedule(static, 4096) num_threads(threads < 1 ? 1 : threads)
+			for (uint32_t r = 0; r < nr; ++r) {                              /* forward read at 2 bits per base; a read first met through its reverse complement is turned back */
+				const char *sq = B->src[r]; const uint32_t len = B->len[r]; const int rcs = B->srcrc[r]; uint64_t o = B->roff[r];
+				for (uint32_t k = 0; k < len; ++k, ++o) {
+					const uint8_t code = rcs ? (uint8_t)(5 - sq[len - 1 - k]) : (uint8_t)sq[k];
+					const uint8_t bits = (uint8_t)(((code - 1) & 3) << (2 * (o & 3)));
+					if (k < 4 || k + 4 >= len) __atomic_fetch_or(&B->reads[o >> 2], bits, __ATOMIC_RELAXED); else B->reads[o >> 2] |= bits;
+				}
+			}
+		}
+		double tb = now(); t_pack += tb - ta;
+		int failed = 0;
+		#pragma omp parallel for schedule(static, 1) num_threads(nb_wave)
+		for (int g = 0; g < nb_wave; ++g) {
+			DevBatch *B = BT + g; uint64_t nq = B->qb - B->qa, nh = 0;
+			bg_reads br = {B->reads, B->len, B->bud, B->strand, B->nreads, (uint32_t)nq, BG_R_PACKED2};
+			if (!B->hits) { B->hitcap = nq * 2 + 1024; B->hits = bg_host_alloc(B->hitcap * sizeof(bg_xhit)); }
+			int rc = bg_search_bunches_into(ctxs[g], &br, (uint32_t)QBUNCH, DO_HEUR, Q->skipAmbig, mode, B->best, B->hits, B->hitcap, &nh);
+			if (rc == BG_EOVERFLOW && nh > B->hitcap) {
+				bg_host_free(B->hits); B->hitcap = nh + nh / 8; B->hits = bg_host_alloc(B->hitcap * sizeof(bg_xhit));
+				for (uint32_t r = 0; r < B->nreads; ++r) B->best[r] = best[B->six[r]];
+				rc = bg_search_bunches_into(ctxs[g], &br, (uint32_t)QBUNCH, DO_HEUR, Q->skipAmbig, mode, B->best, B->hits, B->hitcap, &nh);
+			}
+			if (rc) {
+				#pragma omp critical
+				{ failed = rc; fprintf(stderr, "ERROR: GPU engine failed in bg_search_bunches_into: %s\n", bg_last_error()); }
+				continue;
+			}
+			B->nh = nh;
+		}
+		if (failed) exit(failed == BG_ENOMEM ? 3 : 4);
+		for (int g = 0; g < nb_wave; ++g) {                               /* fold in batch order: per strand the hits arrive in visiting order */
+			DevBatch *B = BT + g;
+			for (uint32_t r = 0; r < B->nreads; ++r) if (B->best[r] < best[B->six[r]]) best[B->six[r]] = B->best[r];
+			for (uint64_t h = 0; h < B->nh; ++h) {
+				const bg_xhit *x = B->hits + h;
+				const UniBin *u = Q->UniBins + B->qa + x->query; const ShrBin *sb = Q->ShrBins + u->six;
+				uint32_t refIx = x->clump * VECSZ + x->lane;
+				if (refIx >= R->totR) continue;                                 /* burst.c:4229 */
+				Pod p = {identity(x->ed, sb->len, x->gap_q), refIx, x->final_pos, x->gap_r, x->gap_q, x->ed, u->rc};
+				pod_push(SPods + u->six + (u->rc ? Q->numUniqQ : 0), p);
+			}
+		}
+		t_gpu += now() - tb;
+		if (!QUIET) printf("\rSearch Progress: [%3.2f%%]", 100.0 * (double)MIN(w0 + (uint64_t)ngpu, nbatch) / (double)nbatch);
+	}
+	if (!QUIET) printf("\rSearch Progress: [100.00%%]\n");
+	printf(" --> [Accel] %" PRIu64 " batches on %d GPU(s), candidates on the device: accelerator upload %.3f s, read packing %.3f s, search + fold %.3f s\n", nbatch, ngpu, t_load, t_pack, t_gpu);
+	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+		PodList *F = SPods + i, *Rc = Q->rc ? SPods + Q->numUniqQ + i : NULL;
+		if (Rc) for (uint32_t k = 0; k < Rc->n; ++k) if (mode != BG_MODE_MIN || Rc->p[k].mismatches <= best[i]) pod_push(Pods + i, Rc->p[k]);
+		for (uint32_t k = 0; k < F->n; ++k) if (mode != BG_MODE_MIN || F->p[k].mismatches <= best[i]) pod_push(Pods + i, F->p[k]);
+		free(F->p); if (Rc) free(Rc->p);
+	}
+	for (int g = 0; g < ngpu; ++g) { DevBatch *B = BT + g; bg_host_free(B->reads); bg_host_free(B->strand); bg_host_free(B->len); bg_host_free(B->bud); bg_host_free(B->best); bg_host_free(B->hits); free(B->roff); free(B->six); free(B->src); free(B->srcrc); }
+	free(BT); free(best); free(lid); free(stamp); free(SPods);
 }
 
 #ifdef BURST_NCCL
@@ -1403,6 +1527,7 @@ int main(int argc, char *argv[]) {
 		else if (!strcmp(argv[i], "--noprogress")) { QUIET = 1; printf(" --> Surpressing progress indicator\n"); }
 		else if (!strcmp(argv[i], "--gpu")) { NEEDARG("--gpu requires integer argument") GPU_DEVICE = atoi(argv[i]); }
 		else if (!strcmp(argv[i], "--shard-refs")) { SHARD_REFS = 1; printf(" --> Sharding the reference database over the GPUs (all-reduce MIN on the per-read minima)\n"); }
+		else if (!strcmp(argv[i], "--device-candidates")) { DEVICE_CAND = 1; printf(" --> Candidate generation on the GPU (accelerator resident in device memory)\n"); }
 		else if (!strcmp(argv[i], "--gpus")) { NEEDARG("--gpus requires integer argument") NGPU = atoi(argv[i]); if (NGPU < 1 || NGPU > 64) { fputs("ERROR: --gpus must be 1..64\n", stderr); exit(1); } }
 		else if (OPT("--fingerprint", "-f") || OPT("--prepass", "-p") || OPT("--unique", "-u")) { fprintf(stderr, "ERROR: %s selects a heuristic/legacy path that this build does not provide (see DESIGN.md, out of scope)\n", argv[i]); exit(1); }
 		else if (OPT("--cache", "-c") || OPT("--latency", "-l") || OPT("--clustradius", "-cr") || OPT("--dbpartition", "-dp")) { NEEDARG("option requires integer argument") }
@@ -1475,7 +1600,11 @@ int main(int argc, char *argv[]) {
 #ifdef BURST_NCCL
 	if (DO_ACCEL && SHARD_REFS && NGPU > 1) accel_search_sharded(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS); else
 #endif
-	if (DO_ACCEL) accel_search(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS);
+	if (DO_ACCEL && DEVICE_CAND && Q.QBins[0] == 0 && Q.maxLenQ <= 512 + (uint32_t)SCOUR_N - 1) accel_search_device(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS);
+	else if (DO_ACCEL) {
+		if (DEVICE_CAND) printf(" --> [Accel] --device-candidates not used: %s\n", Q.QBins[0] ? "queries with ambiguous bases need the host's variant expansion" : "queries longer than the device word tables hold");
+		accel_search(ctxs, NGPU, &Q, &R, &A, Pods, mode, THREADS);
+	}
 	/* queries the accelerator cannot vouch for (or all of them without -a) go all-vs-all, burst.c:4320-4323 */
 	uint64_t firstQ = DO_ACCEL ? Q.QBins[1] : 0;
 	if (firstQ != Q.newUniqQ && !(DO_ACCEL && Q.skipAmbig)) {

@@ -363,3 +363,98 @@ def strand_batch(reads, budgets, qbunch, cands_of_bunch, rng=None):
     return dict(rlen=np.array([len(r) for r in reads], np.uint16), rbudget=np.asarray(budgets, np.uint16), strand=(sread | (src << 31)).astype(np.uint32),
                 cand_off=cand_off, cand=cand, rcodes=rcodes, qcodes=qcodes, qoff=qoff, budget=np.asarray(budgets, np.uint16)[sread], slot=sread,
                 runs=runs, tq=tq, tc=tc, key=key, nreads=n)
+
+
+def build_acx(refs, N, bad=(), big=False):
+    """A k-mer accelerator over `refs` (16 per clump) in the .acx form (burst.c:3504-3530): for every N-mer of plain bases the ascending
+    list of clumps holding it; clumps in `bad` are left out of the lists and named in the BadList instead.  Returns (lens uint32 [4^N],
+    postings uint8 [small format: two 20-bit ids in 5 bytes, an odd last one in 3; big: 3 bytes each], bad uint32, lists dict word -> ids)."""
+    bad = sorted(int(b) for b in bad)
+    pairs = []
+    for c in range((len(refs) + 15) // 16):
+        if c in bad:
+            continue
+        ws = []
+        for r in refs[c * 16:c * 16 + 16]:
+            r = np.asarray(r, np.int64)
+            if len(r) < N:
+                continue
+            ok = (r >= 1) & (r <= 4)
+            w = np.zeros(len(r) - N + 1, np.int64); good = np.ones(len(r) - N + 1, bool)
+            for t in range(N):
+                w = (w << 2) | ((r[t:len(r) - N + 1 + t] - 1) & 3); good &= ok[t:len(r) - N + 1 + t]
+            ws.append(w[good])
+        if ws:
+            u = np.unique(np.concatenate(ws))
+            pairs.append(np.stack([u, np.full(len(u), c, np.int64)], 1))
+    pairs = np.concatenate(pairs) if pairs else np.zeros((0, 2), np.int64)
+    pairs = pairs[np.lexsort((pairs[:, 1], pairs[:, 0]))]
+    lens = np.bincount(pairs[:, 0], minlength=1 << (2 * N)).astype(np.uint32)
+    words, starts = np.unique(pairs[:, 0], return_index=True)
+    ends = list(starts[1:]) + [len(pairs)]
+    out = bytearray(); lists = {}
+    for w, a, b in zip(words, starts, ends):
+        ids = pairs[a:b, 1]
+        lists[int(w)] = ids
+        if big:
+            for i in ids:
+                out += int(i).to_bytes(3, "little")
+        else:
+            for k in range(0, len(ids) - 1, 2):
+                out += (int(ids[k]) | (int(ids[k + 1]) << 20)).to_bytes(5, "little")
+            if len(ids) & 1:
+                out += int(ids[-1]).to_bytes(3, "little")
+    return lens, np.frombuffer(bytes(out), np.uint8), np.array(bad, np.uint32), lists
+
+
+def acx_runs(strands, budgets, qbunch, N, lists, bad, nclumps, heuristic=False, skip_bad=False):
+    """The reference's candidate rule for bunches of `qbunch` sorted strands (burst.c:4085-4168), restated: every distinct word of the
+    bunch adds its largest per-query multiplicity to each clump of its list; clumps whose count exceeds the bunch threshold are visited
+    by descending count (equal counts: first touched first), each by the maximal ranges of queries whose own threshold it exceeds; then
+    the BadList.  Returns the runs as a list of (clump, query0, nq)."""
+    runs = []
+    for z in range(0, len(strands), qbunch):
+        nb = min(qbunch, len(strands) - z)
+        mm, minmm, mult = [], 1 << 62, {}
+        for j in range(nb):
+            s = np.asarray(strands[z + j], np.int64); ln = len(s); kload = int(budgets[z + j]) * N + N
+            m = ln - kload if kload < ln else 0
+            if heuristic:
+                m = max(m, (ln >> 4) + 1)
+            minmm = min(minmm, m)
+            mm.append(ln - kload if kload < ln else 1)
+            per = {}
+            for k in range(0, ln - N + 1):
+                w = 0
+                for t in range(N):
+                    w = (w << 2) | (int(s[k + t]) - 1)
+                per[w] = per.get(w, 0) + 1
+            for w, n in per.items():
+                mult[w] = max(mult.get(w, 0), n)
+        count, order = {}, []
+        for w in sorted(mult):
+            for c in lists.get(w, ()):
+                c = int(c)
+                if c >= nclumps:
+                    continue
+                if c not in count:
+                    count[c] = 0; order.append(c)
+                count[c] += mult[w]
+        cands = [(min(count[c], 65535), i, c) for i, c in enumerate(order) if min(count[c], 65535) > minmm]
+        cands.sort(key=lambda t: (-t[0], t[1]))
+        for v, _, c in cands:
+            a = 0
+            while a < nb:
+                while a < nb and not v > mm[a]:
+                    a += 1
+                b = a
+                while b < nb and v > mm[b]:
+                    b += 1
+                if b > a:
+                    runs.append((c, z + a, b - a))
+                a = b
+        if not skip_bad:
+            for c in bad:
+                if int(c) < nclumps:
+                    runs.append((int(c), z, nb))
+    return runs

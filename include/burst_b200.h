@@ -174,6 +174,21 @@ typedef struct {
 int  bg_align_bunches_into(bg_ctx *ctx, const bg_reads *reads, uint32_t qbunch, const uint32_t *cand_off, const uint32_t *cand, uint32_t nbunch,
                            int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits);
 
+/* ---- candidate generation on the device (the .acx lookup of burst.c:4085-4133): load the accelerator once, then hand over strand
+ * batches WITHOUT candidate lists.  lens: the 4^word_len posting-list lengths as stored in the file (burst.c:3504-3506); postings: the
+ * packed lists that follow them (small format: two 20-bit clump ids in 5 bytes, an odd last one in 3; big: 3 bytes each, burst.c:3512-3527);
+ * bad: the always-visited clumps (burst.c:3530). */
+int  bg_load_acx(bg_ctx *ctx, const uint32_t *lens, const uint8_t *postings, uint64_t post_bytes, int word_len, int big,
+                 const uint32_t *bad, uint32_t nbad);
+/* A hit of a device-generated run list: the strand (index into reads->strand) and clump instead of a task number. */
+typedef struct { uint32_t query, clump; uint8_t lane, ed, gap_q, gap_r; uint32_t final_pos; } bg_xhit;
+/* Strand batch in, hits out: candidates per bunch of `qbunch` strands exactly as the reference picks and orders them (count above the
+ * bunch threshold, descending count, ties in first-touch order; per-query skip; BadList unless skip_bad), then the alignment.  Reads must
+ * be BG_R_PACKED2 (plain bases: the reference expands ambiguous query bases into all variants, which stays a host job).  Hits arrive
+ * grouped by bunch, inside a bunch in the reference's visiting order (candidate, query, lane). */
+int  bg_search_bunches_into(bg_ctx *ctx, const bg_reads *reads, uint32_t qbunch, int heuristic, int skip_bad, int mode,
+                            uint16_t *best_inout, bg_xhit *hits, uint64_t cap, uint64_t *nhits);
+
 /* ---- the one-call form the host driver uses: upload + run + download.  *hits is
  * malloc()ed by the library (free with bg_free_hits). */
 int  bg_align_batch(bg_ctx *ctx, const bg_queries *q, const bg_task *tasks, uint64_t ntasks,

@@ -28,6 +28,7 @@ struct bg_ctx {
 	uint32_t *tq, *tc; uint64_t *orig; uint64_t ntasks;
 	uint16_t *best; OracleHit *hits; uint64_t nhits;
 	uint32_t *best32;           /* what bg_batch_best_device() exposes between run_extend and run_select */
+	uint64_t *acx_off; uint8_t *acx_post; uint32_t *acx_bad, acx_nbad; int acx_n, acx_big;
 };
 
 static char g_err[256] = "";
@@ -46,7 +47,7 @@ static void free_batch(bg_ctx *c) {
 	free(c->best); free(c->hits); free(c->best32); c->best32 = NULL;
 	c->codes = NULL; c->qoff = NULL; c->budget = NULL; c->slot = NULL; c->tq = c->tc = NULL; c->orig = NULL; c->best = NULL; c->hits = NULL;
 }
-void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); free(c->packed); free(c->clump_off); free(c->clump_len); free(c); }
+void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); free(c->packed); free(c->clump_off); free(c->clump_len); free(c->acx_off); free(c->acx_post); free(c->acx_bad); free(c); }
 void *bg_host_alloc(uint64_t bytes) { return malloc(bytes ? bytes : 1); }
 void bg_host_free(void *p) { free(p); }
 int bg_set_stream(bg_ctx *c, void *s) { (void)c; (void)s; return BG_OK; }
@@ -186,16 +187,18 @@ int bg_align_runs_into(bg_ctx *c, const bg_queries *Q, const bg_run *runs, uint6
 void bg_free_hits(bg_hit *h) { free(h); }
 
 /* compact strand batches: expanded on the host into the general form (strands as byte codes, runs from the bunch lists) */
-int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, const uint32_t *cand_off, const uint32_t *cand, uint32_t nbunch,
-		int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+typedef struct { uint64_t *qoff; uint8_t *codes; uint16_t *bud; uint32_t *slot; } Expanded;
+static void expanded_free(Expanded *E) { free(E->qoff); free(E->codes); free(E->bud); free(E->slot); }
+static int expand_strands(const bg_reads *R, Expanded *E, const char *who) {
 	static const uint8_t RVT[16] = {0, 4, 3, 2, 1, 5, 7, 6, 9, 8, 10, 11, 13, 12, 15, 14};
+	memset(E, 0, sizeof(*E));
 	uint64_t *roff = malloc(((size_t)R->nreads + 1) * 8), *qoff = malloc(((size_t)R->nq + 1) * 8);
 	roff[0] = 0;
 	for (uint32_t r = 0; r < R->nreads; ++r) roff[r + 1] = roff[r] + R->len[r];
 	qoff[0] = 0;
 	for (uint32_t q = 0; q < R->nq; ++q) {
 		uint32_t r = R->strand[q] & 0x7FFFFFFFu;
-		if (r >= R->nreads) { snprintf(g_err, sizeof(g_err), "bg_align_bunches_into: strand %u names read %u of %u", q, r, R->nreads); free(roff); free(qoff); return BG_EINVAL; }
+		if (r >= R->nreads) { snprintf(g_err, sizeof(g_err), "%s: strand %u names read %u of %u", who, q, r, R->nreads); free(roff); free(qoff); return BG_EINVAL; }
 		qoff[q + 1] = qoff[q] + R->len[r];
 	}
 	uint8_t *codes = malloc(qoff[R->nq] + 1);
@@ -209,14 +212,122 @@ int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, const u
 			codes[qoff[q] + i] = rc ? RVT[code] : code;
 		}
 	}
+	free(roff);
+	E->qoff = qoff; E->codes = codes; E->bud = bud; E->slot = slot;
+	return BG_OK;
+}
+int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, const uint32_t *cand_off, const uint32_t *cand, uint32_t nbunch,
+		int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits) {
+	Expanded E;
+	int rc = expand_strands(R, &E, "bg_align_bunches_into"); if (rc) return rc;
 	uint64_t nruns = cand_off[nbunch];
 	bg_run *runs = malloc((nruns + 1) * sizeof(bg_run));
 	for (uint32_t b = 0; b < nbunch; ++b) for (uint64_t r = cand_off[b]; r < cand_off[b + 1]; ++r) {
 		uint64_t q0 = (uint64_t)b * qbunch;
 		runs[r].clump = cand[r]; runs[r].query0 = (uint32_t)q0; runs[r].nq = (uint32_t)(R->nq - q0 < qbunch ? R->nq - q0 : qbunch);
 	}
-	bg_queries Q = {codes, qoff, bud, slot, R->nq, R->nreads, 0};
-	int rc = bg_align_runs_into(c, &Q, runs, nruns, mode, best_inout, hits, cap, nhits);
-	free(roff); free(qoff); free(codes); free(bud); free(slot); free(runs);
+	bg_queries Q = {E.codes, E.qoff, E.bud, E.slot, R->nq, R->nreads, 0};
+	rc = bg_align_runs_into(c, &Q, runs, nruns, mode, best_inout, hits, cap, nhits);
+	expanded_free(&E); free(runs);
+	return rc;
+}
+
+/* ---- the accelerator on the "device": the candidate rule of burst.c:4085-4168 restated on the CPU (what k_candgen must reproduce);
+ * the order among equal counts is first touch (words ascending, posting order), i.e. a STABLE sort by descending count ---- */
+int bg_load_acx(bg_ctx *c, const uint32_t *lens, const uint8_t *postings, uint64_t post_bytes, int word_len, int big, const uint32_t *bad, uint32_t nbad) {
+	if (word_len != 12 && word_len != 15) { snprintf(g_err, sizeof(g_err), "bg_load_acx: word length %d (must be 12 or 15)", word_len); return BG_EINVAL; }
+	if (!c->num_clumps) { snprintf(g_err, sizeof(g_err), "bg_load_acx: load the database first"); return BG_EINVAL; }
+	uint64_t nk = 1ull << (2 * word_len);
+	free(c->acx_off); free(c->acx_post); free(c->acx_bad);
+	c->acx_off = malloc((nk + 1) * 8); c->acx_off[0] = 0;
+	for (uint64_t i = 0; i < nk; ++i) c->acx_off[i + 1] = c->acx_off[i] + (big ? (uint64_t)lens[i] * 3 : (uint64_t)(lens[i] / 2) * 5 + (lens[i] & 1) * 3);
+	if (c->acx_off[nk] != post_bytes) { snprintf(g_err, sizeof(g_err), "bg_load_acx: the lengths describe %llu bytes of postings, %llu given", (unsigned long long)c->acx_off[nk], (unsigned long long)post_bytes); return BG_EINVAL; }
+	c->acx_post = malloc(post_bytes + 8); memcpy(c->acx_post, postings, post_bytes); memset(c->acx_post + post_bytes, 0, 8);
+	c->acx_bad = dup(bad, (size_t)nbad * 4); c->acx_nbad = nbad; c->acx_n = word_len; c->acx_big = big;
+	return BG_OK;
+}
+static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }
+typedef struct { uint32_t clump, count, order; } SimCand;
+static int cmp_cand(const void *a, const void *b) { const SimCand *A = a, *B = b; if (A->count != B->count) return A->count > B->count ? -1 : 1; return A->order < B->order ? -1 : A->order > B->order; }
+int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbunch, int heuristic, int skip_bad, int mode,
+		uint16_t *best_inout, bg_xhit *hits, uint64_t cap, uint64_t *nhits) {
+	if (!c->acx_n) { snprintf(g_err, sizeof(g_err), "bg_search_bunches_into: no accelerator loaded (bg_load_acx)"); return BG_EINVAL; }
+	if (R->flags != BG_R_PACKED2) { snprintf(g_err, sizeof(g_err), "bg_search_bunches_into: reads must be BG_R_PACKED2 (plain bases)"); return BG_EINVAL; }
+	if (!qbunch || qbunch > BG_RUN_MAX) { snprintf(g_err, sizeof(g_err), "bg_search_bunches_into: bunch size %u", qbunch); return BG_EINVAL; }
+	Expanded E;
+	int rc = expand_strands(R, &E, "bg_search_bunches_into"); if (rc) return rc;
+	const uint32_t N = (uint32_t)c->acx_n, nclumps = c->first_clump + c->num_clumps;
+	uint32_t *count = calloc(nclumps, 4), *touched = malloc(((size_t)nclumps + 1) * 4);
+	SimCand *cand = malloc(((size_t)nclumps + 1) * sizeof(*cand));
+	uint64_t wcap = 1 << 16, *W = malloc(wcap * 8);
+	bg_run *runs = NULL; uint64_t nruns = 0, rcap = 0;
+	for (uint64_t z = 0; z < R->nq; z += qbunch) {
+		const uint32_t nb = (uint32_t)(R->nq - z < qbunch ? R->nq - z : qbunch);
+		uint32_t mm[BG_RUN_MAX], minmm = UINT32_MAX; uint64_t nw = 0;
+		for (uint32_t j = 0; j < nb; ++j) {
+			const uint32_t len = (uint32_t)(E.qoff[z + j + 1] - E.qoff[z + j]), kload = (uint32_t)E.bud[z + j] * N + N;
+			uint32_t mmatch = kload < len ? len - kload : 0, heur = heuristic ? (len >> 4) + 1u : 0u;
+			if (mmatch < heur) mmatch = heur;
+			if (mmatch < minmm) minmm = mmatch;
+			mm[j] = kload < len ? len - kload : 1;
+			if (nw + len + 1 > wcap) { while (wcap < nw + len + 1) wcap *= 2; W = realloc(W, wcap * 8); }
+			const uint8_t *s = E.codes + E.qoff[z + j];
+			for (uint32_t k = 0; k + N <= len; ++k) {
+				uint64_t w = 0;
+				for (uint32_t t = 0; t < N; ++t) w = w << 2 | (uint64_t)(s[k + t] - 1);
+				W[nw++] = w << 32 | j;
+			}
+		}
+		qsort(W, nw, 8, cmp_u64);
+		uint32_t ntouched = 0;
+		for (uint64_t i = 0; i < nw;) {
+			const uint32_t v = (uint32_t)(W[i] >> 32); uint32_t mx = 0; uint64_t e = i;
+			while (e < nw && (uint32_t)(W[e] >> 32) == v) { uint64_t r = e; while (r < nw && W[r] == W[e]) ++r; if (r - e > mx) mx = (uint32_t)(r - e); e = r; }
+			const uint8_t *p = c->acx_post + c->acx_off[v], *end = c->acx_post + c->acx_off[(uint64_t)v + 1];
+			while (p < end) {
+				uint32_t ids[2], n = 0;
+				if (c->acx_big) { ids[n++] = (uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16; p += 3; }
+				else {
+					ids[n++] = ((uint32_t)p[0] | (uint32_t)p[1] << 8 | (uint32_t)p[2] << 16) & 0xFFFFF;
+					if (end - p >= 5) { ids[n++] = ((uint32_t)p[2] >> 4 | (uint32_t)p[3] << 4 | (uint32_t)p[4] << 12) & 0xFFFFF; p += 5; } else p += 3;
+				}
+				for (uint32_t t = 0; t < n; ++t) if (ids[t] < nclumps) { if (!count[ids[t]]) touched[ntouched++] = ids[t]; count[ids[t]] += mx; }
+			}
+			i = e;
+		}
+		uint32_t ncand = 0;
+		for (uint32_t i = 0; i < ntouched; ++i) {
+			uint32_t v = count[touched[i]]; if (v > 65535) v = 65535; count[touched[i]] = 0;
+			if (v > minmm) { cand[ncand].clump = touched[i]; cand[ncand].count = v; cand[ncand].order = ncand; ++ncand; }
+		}
+		qsort(cand, ncand, sizeof(*cand), cmp_cand);
+		const uint64_t need = nruns + (uint64_t)ncand * nb + c->acx_nbad + 1;
+		if (need > rcap) { rcap = need * 2; runs = realloc(runs, rcap * sizeof(bg_run)); }
+		for (uint32_t i = 0; i < ncand; ++i) {
+			uint32_t a = 0;
+			while (a < nb) {
+				while (a < nb && !(cand[i].count > mm[a])) ++a;
+				uint32_t b = a;
+				while (b < nb && cand[i].count > mm[b]) ++b;
+				if (b > a) { runs[nruns].clump = cand[i].clump; runs[nruns].query0 = (uint32_t)z + a; runs[nruns++].nq = b - a; }
+				a = b;
+			}
+		}
+		if (!skip_bad) for (uint32_t i = 0; i < c->acx_nbad; ++i) if (c->acx_bad[i] < nclumps) { runs[nruns].clump = c->acx_bad[i]; runs[nruns].query0 = (uint32_t)z; runs[nruns++].nq = nb; }
+	}
+	free(count); free(touched); free(cand); free(W);
+	bg_queries Q = {E.codes, E.qoff, E.bud, E.slot, R->nq, R->nreads, 0};
+	bg_hit *h = NULL; uint64_t n = 0;
+	rc = nruns ? bg_align_runs(c, &Q, runs, nruns, mode, best_inout, &h, &n) : BG_OK;
+	if (!rc) {
+		*nhits = n;
+		if (n > cap) { snprintf(g_err, sizeof(g_err), "bg_search_bunches_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap); rc = BG_EOVERFLOW; }
+		else for (uint64_t i = 0; i < n; ++i) {
+			const bg_run *r = runs + (h[i].task >> 4);
+			bg_xhit x = {r->query0 + (h[i].task & 15), r->clump, h[i].lane, h[i].ed, h[i].gap_q, h[i].gap_r, h[i].final_pos};
+			hits[i] = x;
+		}
+	}
+	bg_free_hits(h); expanded_free(&E); free(runs);
 	return rc;
 }

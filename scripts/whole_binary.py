@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--dir", default="/tmp/wb")
     ap.add_argument("--skip-reference", action="store_true")
     ap.add_argument("--ours", default=None, help="binary under test (default burst_b200/host/burst-b200)")
+    ap.add_argument("--ours-extra", default="", help="extra flags for the binary under test, e.g. --device-candidates")
     ap.add_argument("--acx-n", type=int, default=0, help="override the accelerator word length (12 or 15)")
     args = ap.parse_args()
     d = os.path.join(args.dir, args.shape); os.makedirs(d, exist_ok=True)
@@ -129,7 +130,8 @@ def main():
     common = ["-r", "db.edx", "-a", "db.acx", "-q", "reads.fa", "-m", P["mode"], "-i", P["ident"], "--noprogress"] + P["extra"]
     out = {"shape": args.shape, "mbp": args.mbp, "reads": args.reads, "threads": args.threads, "gpus": args.gpus, "generate_s": round(gen_s, 1), "makedb_s": round(mk, 1),
            "edx_bytes": os.path.getsize(os.path.join(d, "db.edx")), "acx_bytes": os.path.getsize(os.path.join(d, "db.acx")), "flags": " ".join(common)}
-    t_ours, so = run([ours] + common + ["-o", "ours.b6", "-t", str(args.threads), "--gpus", str(args.gpus)], d)
+    t_ours, so = run([ours] + common + ["-o", "ours.b6", "-t", str(args.threads), "--gpus", str(args.gpus)] + args.ours_extra.split(), d)
+    out["ours_extra"] = args.ours_extra
     out["ours_wall_s"] = round(t_ours, 2); out["ours_reads_per_s"] = round(args.reads / t_ours)
     out["ours_stdout_tail"] = [l.strip() for l in so.splitlines() if "[Accel]" in l or "Alignment time" in l or "[time]" in l][-12:]
     rows = sorted(open(os.path.join(d, "ours.b6"), "rb").read().splitlines())

@@ -43,6 +43,20 @@ CASES = sorted(os.listdir(os.path.join(GOLD, "cli")))
 
 @pytest.mark.parametrize("case", CASES)
 def test_cli_matches_reference_b6(case, tmp_path):
+    cli_case(case, tmp_path, [])
+
+
+@pytest.mark.parametrize("case", [c for c in CASES if c.startswith("acx_")])
+def test_cli_device_candidates_matches_reference_b6(case, tmp_path):
+    """--device-candidates: the accelerator on the GPU (bg_load_acx + bg_search_bunches_into, k_candgen); cases whose accelerated bin
+    holds ambiguous queries fall back to the host lists by design and must say so"""
+    out = cli_case(case, tmp_path, ["--device-candidates"])
+    assert ("candidates on the device" in out) or ("--device-candidates not used" in out) or ("Using ACCELERATOR" not in out)
+    if case in ("acx_allpaths_fr", "acx_best"):
+        assert "candidates on the device" in out
+
+
+def cli_case(case, tmp_path, extra):
     d = os.path.join(GOLD, "cli", case)
     meta = json.load(open(os.path.join(d, "case.json")))
     out = str(tmp_path / "out.b6")
@@ -53,10 +67,11 @@ def test_cli_matches_reference_b6(case, tmp_path):
         with gzip.open(os.path.join(d, "db.acx.gz"), "rb") as fi, open(acx, "wb") as fo:
             shutil.copyfileobj(fi, fo)
         args[args.index("db.acx")] = acx
-    r = subprocess.run([BIN] + args + ["--noprogress"], cwd=d, capture_output=True, text=True)
+    r = subprocess.run([BIN] + args + ["--noprogress"] + extra, cwd=d, capture_output=True, text=True)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     got = sorted(open(out).read().splitlines())
     want = sorted(open(os.path.join(d, "expected.b6")).read().splitlines())
     assert len(got) == len(want), (len(got), len(want))
     diff = [(a, b) for a, b in zip(got, want) if a != b]
     assert not diff, "%d rows differ, first: %s" % (len(diff), diff[0])
+    return r.stdout

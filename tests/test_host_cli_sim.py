@@ -50,6 +50,14 @@ def test_host_logic_matches_reference_b6(sim, case, tmp_path):
     assert not diff, "%d rows differ, first: %s" % (len(diff), diff[0])
 
 
+@pytest.mark.parametrize("case", ["acx_allpaths_fr", "acx_best", "acx_capitalist_tax_iupac"])
+def test_device_candidate_driver_matches_reference_b6(sim, case, tmp_path):
+    """--device-candidates: the host side of the path (distinct reads of a batch at 2 bits per base, strand words, hits that name
+    strand and clump) over the stand-in's CPU statement of the candidate rule; the third case must fall back to the host lists"""
+    got, want = run_case(sim, case, tmp_path, extra=["--device-candidates"])
+    assert got == want
+
+
 @pytest.mark.parametrize("threads", ["7", "64"])
 def test_bunch_size_does_not_change_rows(sim, tmp_path, threads):
     """-t only changes QBUNCH (burst.c:4019-4021), never the reported rows."""
