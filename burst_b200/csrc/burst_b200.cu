@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 						for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
 							const QWin w = window_of(S, j);
 							const uint32_t hv = seed_hash(w.kn, w.ko & HM);
-							atomicOr(&bits[hv >> SHB], (0x80000000u >> (hv & 31)) | (FB == 2 ? 0x80000000u >> ((hv >> 5) & 31) : 0u));
+							atomicOr(&bits[hv >> SHB], (0x80000000u >> (hv & 31)) | (FB >= 2 ? 0x80000000u >> ((hv >> 5) & 31) : 0u) | (FB >= 3 ? 0x80000000u >> ((hv >> 10) & 31) : 0u));
 							const uint32_t e = si * STRIDE + j;
 							nxt[e] = (uint16_t)atomicExch(&slots[(hv >> 10) & HSM], e + 1u);
 						}
@@ -875,13 +875,15 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 									const uint32_t h8 = seed_hash(cu, prev & HM);
 									const uint32_t f8 = lds32(bits_s + ((h8 >> SHB) << 2));
 									uint32_t t8 = __funnelshift_l(0u, f8, h8);                                    // the window's bit(s) -> bit 31
-									if (FB == 2) t8 &= __funnelshift_l(0u, f8, h8 >> 5);
+									if (FB >= 2) t8 &= __funnelshift_l(0u, f8, h8 >> 5);
+									if (FB >= 3) t8 &= __funnelshift_l(0u, f8, h8 >> 10);
 									uint32_t t4 = 0;
 									if (STRIDE == 4) {
 										const uint32_t h4 = seed_hash(__funnelshift_r(prev, cu, 16), __funnelshift_r(prev2, prev, 16) & HM);
 										const uint32_t f4 = lds32(bits_s + ((h4 >> SHB) << 2));
 										t4 = __funnelshift_l(0u, f4, h4);
-										if (FB == 2) t4 &= __funnelshift_l(0u, f4, h4 >> 5);
+										if (FB >= 2) t4 &= __funnelshift_l(0u, f4, h4 >> 5);
+										if (FB >= 3) t4 &= __funnelshift_l(0u, f4, h4 >> 10);
 									}
 									if (AMB) {
 										const uint32_t ambc = amb_nibbles(cu, ADD);
@@ -1888,7 +1890,7 @@ struct bg_ctx {
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
 	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
-	int seed_impl = 1, seed_nch = 8, seed_lbits = 0, seed_fb = 1;   // seed_fb: filter bits per window (1 or 2)
+	int seed_impl = 1, seed_nch = 8, seed_lbits = 0, seed_fb = 2, seed_hslots = 0;   // seed_fb: filter bits per window (1 or 2)
 	int _pad0 = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
 	uint32_t mstage = 0;                                          // longest query the k_extend staging slots are sized for (from the batch's lengths)
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
@@ -2021,6 +2023,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 	if (what == BG_PARAM_SEED_GROUPS) { if (value != 0 && value != 2 && value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed groups %d must be 0, 2, 4 or 8", value); c->seed_groups = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_IMPL) { c->seed_impl = value != 0; return BG_OK; }
 	if (what == BG_PARAM_SEED_NCH) { if (value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed buffer chunks %d must be 4 or 8", value); c->seed_nch = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_HSLOTS) { if (value && (value < 64 || value > 4096 || (value & (value - 1)))) return fail(BG_EINVAL, "bg_set_param: %d window-table buckets (must be 0 or a power of two 64..4096)", value); c->seed_hslots = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_FB) { if (value != 1 && value != 2) return fail(BG_EINVAL, "bg_set_param: filter bits per window %d must be 1 or 2", value); c->seed_fb = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_LBITS) { if (value && (value < 10 || value > 20)) return fail(BG_EINVAL, "bg_set_param: seed bitmap 2^%d bits out of range (0 = auto, 10..20)", value); c->seed_lbits = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_RATIO) { if (value && (value < 10 || value > 300)) return fail(BG_EINVAL, "bg_set_param: slice ratio %d must be 0 (auto) or 10..300", value); c->pipe_ratio = value; return BG_OK; }
@@ -2257,15 +2260,21 @@ static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint3
 static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t npmax) {
 	SeedWArgs S;
 	S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = B.qi; S.qnib = B.qnib; S.W = B.W; S.SL = SL; S.nwork = B.W.nruns;
-	uint32_t chunk = 1; while (chunk * 2 <= (uint32_t)c->seed_chunk * 4 && chunk < SEEDW_SPLIT) chunk <<= 1;   // a power of two that divides SEEDW_SPLIT
+	uint32_t chunk = 1; while (chunk * 2 <= (uint32_t)c->seed_chunk * 8 && chunk < SEEDW_SPLIT) chunk <<= 1;   // a power of two that divides SEEDW_SPLIT (default 64 runs)
 	S.chunk = chunk; S.npmax = npmax;
 	const uint32_t ne = BG_RUN_MAX * npmax * SL.stride;                 // most windows a bunch can hold
-	S.hslots = 64; while (S.hslots < ne) S.hslots <<= 1;                 // buckets of the chained window table
-	// filter: two bits per window in one 32-bit word; ~64 bits per window of a typical full bunch (SL.words was sized as 1-2 words per
-	// such window) keep false positives -- one bucket probe by the owning thread -- well below one per run
+	// buckets of the chained window table: about 2/3 of the windows a full bunch can hold (chains of 1-2; more buckets cost shared memory)
+	S.hslots = 64; while (S.hslots * 3 < ne * 2) S.hslots <<= 1;
+	if (c->seed_hslots) S.hslots = (uint32_t)c->seed_hslots;
+	// filter: FB bits per window inside one 32-bit word.  Start from ~64 bits per window of a typical full bunch, then give up one
+	// power of two when that lets one more block live on an SM (measured on the bench shape: 2 bits in 2^14 at 4 blocks/SM beats
+	// 1 bit in 2^15 at 3 blocks/SM by 7 %, profiles/r2_tune_seedw.txt); a false positive costs one bucket probe
+	auto smem_of = [&](uint32_t lb) { return (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lb, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * sizeof(uint32_t); };
+	auto blocks_of = [&](uint32_t lb) { return std::min<size_t>(4, (size_t)(227 * 1024) / (smem_of(lb) + 1024)); };
 	uint32_t lbits = 12; while (lbits < 17 && (1u << lbits) < 64u * SL.words) ++lbits;
 	if (c->seed_lbits) lbits = (uint32_t)c->seed_lbits;
-	while (lbits > 10 && (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * 4 > 200 * 1024) --lbits;
+	else if (lbits > 12 && (1u << (lbits - 1)) >= 32u * ne && blocks_of(lbits - 1) > blocks_of(lbits)) --lbits;
+	while (lbits > 10 && smem_of(lbits) > 200 * 1024) --lbits;
 	S.lbits = lbits;
 	const size_t smem = (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * sizeof(uint32_t);
 	if (smem > 220 * 1024) return fail(BG_EINVAL, "seed filter tables do not fit shared memory (stretches %u, stride %u)", npmax, SL.stride);
@@ -2280,6 +2289,7 @@ static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const See
 	int bps = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SEEDW_WARPS * 32, smem));
 	if (bps < 1) bps = 1;
+	if (getenv("BURST_B200_DEBUG")) fprintf(stderr, "[k_seedw] lbits %u hslots %u nch %d smem %zu B/block, %d blocks/SM\n", lbits, S.hslots, c->seed_nch, smem, bps);
 	const uint64_t nchunk = (S.nwork + chunk - 1) / chunk;
 	const uint64_t blocks = std::min<uint64_t>((nchunk + SEEDW_WARPS - 1) / SEEDW_WARPS, (uint64_t)c->sms * bps);
 	kern<<<(unsigned)blocks, SEEDW_WARPS * 32, smem, st>>>(S);

@@ -110,7 +110,8 @@ enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096)
 enum { BG_PARAM_SEED_IMPL = 9,       /* 1 (default): warp-per-bunch seed filter (private window table, no block barriers); 0: the block form */
        BG_PARAM_SEED_NCH = 10,       /* 32-column chunks per register buffer of the warp form: 8 (default) or 4 */
        BG_PARAM_SEED_LBITS = 11,     /* log2 of the bits in a warp's window filter, 10..20 (0 = sized from the batch) */
-       BG_PARAM_SEED_FB = 12 };      /* bits set per window in that filter: 1 (default) or 2 */
+       BG_PARAM_SEED_FB = 12,        /* bits set per window in that filter: 2 (default) or 1 */
+       BG_PARAM_SEED_HSLOTS = 13 };  /* buckets of a warp's chained window table, a power of two 64..4096 (0 = sized from the batch) */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* Page-locked host memory for the arrays handed to bg_align_runs_into() (queries, runs, hit buffer): makes the library's
