@@ -356,7 +356,7 @@ def main():
 
     if rank == 0:
         peak, how = peaks()
-        # Algorithmic bytes of one k_seed launch: what the batched formulation must move at least once --
+        # Algorithmic bytes of one k_seedw launch: what the batched formulation must move at least once --
         # per clump visit of a bunch (run): the clump (8 B per column), its 16 B record and the 12 B run; per query: its 24 B
         # record and packed bases (len/2); 16 B per survivor written.  SURVEY 8(d)'s per-task figure (8*ClumpLen+len+16 per
         # (query, clump) pair) counts the clump once per query of the bunch, i.e. ~16x what one pass over it moves; it is
@@ -367,10 +367,10 @@ def main():
         filt_ms = st["ms_filter"]
         achieved = alg_bytes / (filt_ms / 1e3) / 1e9
         traffic = None
-        try:    # dram__bytes_read.sum + dram__bytes_write.sum of one k_seed launch of THIS workload, from the committed ncu pass
+        try:    # dram__bytes_read.sum + dram__bytes_write.sum of one k_seedw launch of THIS workload, from the committed ncu pass
             tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
             if tr["reads"] == args.reads and tr["db_mb"] == args.db_mb and tr["read_len"] == args.read_len:
-                traffic = tr["k_seed_dram_bytes_per_launch"]
+                traffic = tr["k_seedw_dram_bytes_per_launch"]
         except Exception:
             pass
         out = {"metric": "reads_per_sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -391,11 +391,11 @@ def main():
                         "seed_layout": "probe every %d columns, %d-base windows, %d-word filter per warp" % (st["seed_stride"], st["seed_window"], st["seed_words"]), "band_cells": st["band_cells"], "reads_found": found, "reads_at_planted_lane": planted,
                         "ms_filter": st["ms_filter"], "ms_extend": st["ms_extend"], "ms_select": st["ms_select"]},
                "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                            "kernel": "k_seed" if st["seed_queries"] else "k_filter", "kernel_ms": filt_ms, "algorithmic_bytes_per_launch": alg_bytes,
+                            "kernel": "k_seedw" if st["seed_queries"] else "k_filter", "kernel_ms": filt_ms, "algorithmic_bytes_per_launch": alg_bytes,
                             "peak_source": "of " + how + " (MEASURED_PEAKS.json hbm_gbs, burst figure; fallback = 6650 GB/s of B200_PROFILING.md)",
                             "achieved_per_task_8d": alg_bytes_8d / (filt_ms / 1e3) / 1e9,
-                            "note": "achieved = bytes one pass must move (clump once per run + queries once + survivors) / CUDA-event time of the k_seed launch; the kernel streams each clump once for the <=16 queries of a bunch, so SURVEY 8(d)'s per-(query, clump) byte count (achieved_per_task_8d) exceeds what is physically read; the kernel is latency/issue bound, not HBM bound (profiles/)"},
-               "integer_roofline": {"kernel": "k_extend (5 band classes)", "kernel_ms": st["ms_extend"],
+                            "note": "achieved = bytes one pass must move (clump once per run + queries once + survivors) / CUDA-event time of the k_seedw launch; the kernel streams each clump once for the <=16 queries of a bunch, so SURVEY 8(d)'s per-(query, clump) byte count (achieved_per_task_8d) exceeds what is physically read; the kernel is latency/issue bound, not HBM bound (profiles/)"},
+               "integer_roofline": {"kernel": "k_extend (9 band classes, one binned survivor list)", "kernel_ms": st["ms_extend"],
                                     "dpx_thread_inst_per_s": 2.0 * st["band_cells"] / (st["ms_extend"] / 1e3),
                                     "dpx_peak_thread_inst_per_s": DPX_PEAK, "frac": 2.0 * st["band_cells"] / (st["ms_extend"] / 1e3) / DPX_PEAK,
                                     "note": "2 VIADDMNMX per band cell (select-with-tie-break of the packed pass-2 key); peak = VIADDMNMX.U32 issue rate measured on this pool's B200 by burst_b200/csrc/tools/pipe_microbench (profiles/r1d_pipe_microbench.txt: 571.6 G warp-inst/s at 1965 MHz, half the 4-per-clock issue rate: it shares the ALU pipe with the ~5 LOP3/SHF/VIMNMX each cell also needs)"},

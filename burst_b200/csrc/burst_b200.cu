@@ -1303,6 +1303,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 	cp_async_commit();
 	if (v1) load_x(p + S, X1);
 	for (; v0; p += S, buf ^= 1) {
+		const uint32_t kbest = A.mode == BG_MODE_MIN ? __ldcg(A.best + X0[2].y) : 0xFFFFFFFFu;   // the slot's running minimum: asked for before the staging work below, used after it
 		if (v1) T1 = stage(X1, buf ^ 1);
 		cp_async_commit();
 		const bool v2 = v1 && p + 2 * S < count;
@@ -1320,7 +1321,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		const bool plain = (x2.z >> 16) & 1u;
 		const uint32_t *lanew = A.dbw + ((uint64_t)x1.x | ((uint64_t)x1.y << 32)) * 4 + lane * 4;
 		uint32_t k = x2.z & 0xFFFFu;
-		if (A.mode == BG_MODE_MIN) k = min(k, A.best[slot]);
+		k = min(k, kbest);
 		uint32_t inf = (k + 1) << 22;
 		const int lo = sv.lo;
 		constexpr int WB = WMAX ? WMAX : 1;
@@ -1371,12 +1372,21 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			int badrows = 0;                                 // rows during which the window may still hold a code that is not a plain base
 			#pragma unroll
 			for (int j = 0; j < NW; ++j) if (nonplain_nibbles(win[j] | (j == NW - 1 ? ~TOPMASK & 0x11111111u : 0u))) badrows = WB;
+#ifndef EXT_NO_PREFETCH
+			uint32_t w1n = refw(wbase + 1), qwn = qwd(0);
+#endif
 			for (uint32_t gq = 0; gq < ngroups && !dead; ++gq) {
 				// tighten Emac as better hits land (burst.c:4159, 4220): a value read 8 rows ago is only less tight, never wrong
 				k = min(k, bpre); inf = (k + 1) << 22;
 				if (A.mode == BG_MODE_MIN && (gq & 3) == 0) bpre = __ldcg(A.best + slot);
+#ifndef EXT_NO_PREFETCH
+				const uint32_t w1 = w1n, qw = qwn;
+				if (gq + 1 < ngroups) { w1n = refw(wbase + (int)gq + 2); qwn = qwd(gq + 1); }   // next group's words: their latency hides behind this group's rows
+				const uint32_t feed = __funnelshift_r(w0, w1, sh2);
+#else
 				const uint32_t w1 = refw(wbase + (int)gq + 1);
 				const uint32_t feed = __funnelshift_r(w0, w1, sh2), qw = qwd(gq);
+#endif
 				w0 = w1;
 				const int x0g = (int)y + lo;                 // column (1-based) of band cell 0 in the first row of the group
 				if (nonplain_nibbles(feed)) badrows = WB + 8;
@@ -2139,7 +2149,10 @@ static int copy_codes(const bg_queries *Q, uint64_t b0, uint64_t b1, DBuf<uint8_
 
 // queries -> device, QInfo + tables
 // query length the k_extend staging slots are sized for, from the longest of a sample of the batch (a longer query still works: it reads global memory)
-static uint32_t stage_len(uint64_t sampled_max) { return (uint32_t)std::min<uint64_t>(2048, ((sampled_max + 31) & ~31ull) + 32); }
+static uint32_t stage_len(uint64_t sampled_max) {
+	static const int pad = getenv("BURST_B200_STAGE_PAD") ? atoi(getenv("BURST_B200_STAGE_PAD")) : 0;
+	return (uint32_t)std::min<uint64_t>(2048, ((sampled_max + 7) & ~7ull) + (uint64_t)pad);
+}
 
 static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	if (!c->num_clumps) return fail(BG_EINVAL, "bg_batch_upload: no database loaded");
@@ -2366,7 +2379,11 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[4], k_extend<24>, 128, smem[4]); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[5], k_extend<32>, 128, smem[5]);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[6], k_extend<48>, 128, smem[6]); cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[7], k_extend<64>, 128, smem[7]);
 		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[8], k_extend<0>, 128, smem[8]);
-		for (int k = 0; k < NCLASS; ++k) if (occ[k] > 0) grid[k] = std::min<unsigned>(grid[k], (unsigned)c->sms * (unsigned)occ[k]);
+		// resident blocks per SM: three (12 warps) measured fastest on the bench shape -- 0.495 ms against 0.52 / 0.55 ms at four / five
+		// (profiles/r2_ab_extend.txt): each thread keeps more survivors in its private pipeline and the unrolled band rows of
+		// twelve warps still fit the instruction cache
+		static const int bps_cap = getenv("BURST_B200_EXT_BPS") ? atoi(getenv("BURST_B200_EXT_BPS")) : 3;
+		for (int k = 0; k < NCLASS; ++k) if (occ[k] > 0) grid[k] = std::min<unsigned>(grid[k], (unsigned)c->sms * (unsigned)(bps_cap > 0 ? std::min(bps_cap, occ[k]) : occ[k]));
 		(void)cudaGetLastError();
 	}
 	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 32 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K]));   /* (the kernel also has 1 KB of static shared memory) */ \

@@ -12,9 +12,10 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=1_000_000)
 ap.add_argument("--db-mb", type=int, default=2048)
 ap.add_argument("--settings", default="0:8:0:8:1,1:8:0:8:1,1:8:0:8:2,1:4:0:8:1,1:8:16:8:1,1:8:14:8:2,1:8:0:16:1")
+ap.add_argument("--lib", default=None, help="engine library to load instead of burst_b200/libburst_b200.so (A/B builds)")
 a = ap.parse_args()
 w = synth.bunch_workload(a.reads, 100, 2, a.db_mb << 20, 214, seed=20261017)
-eng = Engine(0)
+eng = Engine(0, lib_path=a.lib)
 eng.load_db(w["packed"], w["clump_len"])
 runs = np.ascontiguousarray(w["runs"], RUN_DTYPE)
 ref = None
