@@ -11,7 +11,7 @@ candidate clumps, burst.c:4077-4157).
   value     whole-job reads/s with queries, tasks and DB resident in HBM (kernels only: k_init_best, k_seedw, k_bin_count/offsets/scatter,
             k_extend x 9 band classes, k_select = 15 launches per step)
   e2e       the same through bg_align_bunches_into(): pinned host buffers in (reads once, 2 bits per base), hits in pinned host memory out
-  roofline  dominant kernel (k_seed) algorithmic bytes / its CUDA-event time vs measured HBM peak
+  roofline  dominant kernel (k_seedw) algorithmic bytes / its CUDA-event time vs measured HBM peak
             -- the kernel is integer-ALU bound, see "alu" and DESIGN.md
   cpu_baseline / --impl reference
             the reference's own aded_mat16L + reScoreM_mat16 (oracle/_ref/libburstref.so, built
@@ -46,11 +46,15 @@ def parse():
     ap.add_argument("--clump-len", type=int, default=214)
     ap.add_argument("--cpu-sample-bunches", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--config", default="c2", choices=["c2", "target"],
-                    help="c2 (default, the headline): BASELINE.json configs[1], 1 M reads vs a 2 GB DB; target: north_star's 10 M x 100 bp vs a 31.5 GB .edx on one B200")
+    ap.add_argument("--config", default="c2", choices=["c2", "target", "c3"],
+                    help="c2 (default, the headline): BASELINE.json configs[1], 1 M reads vs a 2 GB DB; target: north_star's 10 M x 100 bp vs a 31.5 GB .edx on one B200; "
+                         "c3: configs[2] shape, 200 k x 292 bp amplicon reads (0-5 substitutions, budget 9) vs a 70 MB mutation-tree DB of 1400-base references, ~60 clump visits per strand")
     a = ap.parse_args()
+    a.budget = a.edits; a.probe_bunches = 256
     if a.config == "target":
         a.reads, a.db_mb = 10_000_000, 32256
+    if a.config == "c3":
+        a.reads, a.db_mb, a.read_len, a.edits, a.clump_len, a.budget, a.probe_bunches = 200_000, 70, 292, 5, 1400, 9, 16
     return a
 
 
@@ -133,7 +137,10 @@ def bind_to_gpu_numa_node(torch, local):
 def build_workload(args, rank):
     from burst_b200 import synth
     t0 = time.time()
-    w = synth.bunch_workload(args.reads, args.read_len, args.edits, args.db_mb << 20, args.clump_len, seed=20261017 + rank)
+    if args.config == "c3":
+        w = synth.amplicon_workload(args.reads, args.read_len, args.edits, args.db_mb << 20, args.clump_len, seed=20261017 + rank, budget=args.budget, halo=7)
+    else:
+        w = synth.bunch_workload(args.reads, args.read_len, args.edits, args.db_mb << 20, args.clump_len, seed=20261017 + rank)
     w["gen_s"] = time.time() - t0
     return w
 
@@ -150,7 +157,7 @@ def cpu_reference(args, w, steps=1, warmup=0):
         kind = "reference"
         nb = args.cpu_sample_bunches
         if not nb:
-            probe = min(nb_all, 256 * threads)
+            probe = min(nb_all, args.probe_bunches * threads)
             t0 = time.perf_counter(); pyoracle.reference_run_bunches(ref, w, probe, threads); dt = time.perf_counter() - t0
             nb = int(min(nb_all, max(probe, probe * 4.0 / max(dt, 1e-3))))     # ~4 s per step
         times = []
@@ -161,7 +168,7 @@ def cpu_reference(args, w, steps=1, warmup=0):
                 times.append(time.perf_counter() - t0)
         nq = r["nq"]
         refout = r
-        found = int((r["ed"][np.unique(w["slot"][:nq])] <= args.edits).sum())
+        found = int((r["ed"][np.unique(w["slot"][:nq])] <= args.budget).sum())
         desc = "reference kernels aded_mat16L+reScoreM_mat16 (burst.c) in the reference's bunch loop, first %d of %d bunches = %d strands (%d pass-1 calls, %d truncated, %d pass-2), %d threads" % (
             nb, nb_all, nq, r["calls"], r["truncated"], r["rescore"], threads)
     else:
@@ -213,10 +220,16 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    config = {"workload": ("north_star target: " if args.config == "target" else "configs[1]: ") + "%d x %d bp reads (exactly %d edits, LLsim model, fwd+rc strands) per GPU vs %d MB synthetic .edx-layout DB (%d-column clumps), -i 0.98 budget %d, BEST-style min selection, task list = reference bunch driver (QBUNCH 16 x bunch candidates)" % (
-        args.reads, args.read_len, args.edits, args.db_mb, args.clump_len, args.edits),
+    if args.config == "c3":
+        wl = "configs[2] shape: %d x %d bp amplicon reads (0-%d substitutions, fwd+rc strands) per GPU vs %d MB synthetic mutation-tree DB (%d-column clumps of near-identical references), -i 0.97 budget %d, min selection, task list = reference bunch driver (QBUNCH 16 x ~60 candidate clumps per bunch)" % (
+            args.reads, args.read_len, args.edits, args.db_mb, args.clump_len, args.budget)
+    else:
+        wl = ("north_star target: " if args.config == "target" else "configs[1]: ") + "%d x %d bp reads (exactly %d edits, LLsim model, fwd+rc strands) per GPU vs %d MB synthetic .edx-layout DB (%d-column clumps), -i 0.98 budget %d, BEST-style min selection, task list = reference bunch driver (QBUNCH 16 x bunch candidates)" % (
+            args.reads, args.read_len, args.edits, args.db_mb, args.clump_len, args.edits)
+    config = {"workload": wl,
         "reads_per_gpu": args.reads, "db_mb": args.db_mb, "sharding": "queries (DB replicated), no data-path collective", "numa_node_rank0": None,
-        "l2": "inputs (DB %d MB + tasks) exceed the 126 MB L2; no explicit flush" % args.db_mb}
+        "l2": ("inputs (DB %d MB + tasks) exceed the 126 MB L2; no explicit flush" % args.db_mb) if args.db_mb > 126 else
+              ("the %d MB DB fits the 126 MB L2 (as the reference's amplicon databases do); queries + runs + survivors of a step exceed it; no explicit flush" % args.db_mb)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -289,7 +302,7 @@ def main():
     nhits = eng.count()
     st = eng.stats()
     hits, best = eng.download()
-    found = int((best[:w["n_reads"]] <= args.edits).sum())
+    found = int((best[:w["n_reads"]] <= args.budget).sum())
     # planted-read check: every read must be reported at the lane it was cut from
     tq = runs["query0"][hits["task"] >> 4] + (hits["task"] & 15); tc = runs["clump"][hits["task"] >> 4]
     rd = w["slot"][tq]

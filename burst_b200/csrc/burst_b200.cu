@@ -4,7 +4,7 @@
 //   pass 1  aded_mat16L / aded_mat16   burst.c:1003-1204   16-lane banded edit distance
 //   pass 2  reScoreM_mat16             burst.c:713-886     (score, shift, shiftR) + end column
 // and how this file restructures it for the GPU (DESIGN.md section 2 has the full argument):
-//   k_qinfo/k_qprep/k_qtables  per query: budget/length record, nibble-packed bases, Myers match vectors
+//   k_qinfo/k_qprep            per query: budget/length record, nibble-packed bases (k_filter builds its Myers match vectors itself)
 //   k_seed         a block walks its RUNS (run = one clump visit by <= 16 consecutive queries, the reference's
 //                  "unpack the clump once, then loop over the bunch", burst.c:4141-4157) in rounds, one run per group
 //                  of 16 threads, one thread per reference lane.  Pigeonhole: an alignment with <= k errors leaves
@@ -55,12 +55,21 @@ extern "C" const char *bg_last_error(void) { return g_err; }
 // ---------------------------------------------------------------------------------------------
 // device-side data
 // ---------------------------------------------------------------------------------------------
+// Prefix rows of the Myers filter, coded in one byte: up to 32 rows = one word holding exactly that many; else 32 + NW for NW in
+// {2, 4, 8, 16, 32} words of 32 rows.  NW grows with the budget (about 4 k rows) as long as the query is that long.
+__host__ __device__ __forceinline__ uint32_t filt_words(uint32_t P) { return P <= 32 ? 1u : P - 32u; }
+__host__ __device__ __forceinline__ uint32_t filt_rows(uint32_t P) { return P <= 32 ? P : (P - 32u) * 32u; }
+__host__ __device__ __forceinline__ uint8_t filt_code(uint64_t len, uint32_t k) {
+	uint32_t nw = 1; const uint32_t want = (k + 7) / 8;
+	while (nw < 32 && nw < want && (uint64_t)nw * 64 <= len) nw <<= 1;
+	return (uint8_t)(nw == 1 ? (len < 32 ? len : 32) : 32 + nw);
+}
 struct QInfo {            // one query of the batch
 	uint64_t off;         // into codes
 	uint32_t len;
 	uint32_t slot;
 	uint16_t k;           // budget (Emac)
-	uint8_t  P;           // rows covered by the Myers prefix filter = min(32, len)
+	uint8_t  P;           // rows covered by the Myers prefix filter, coded (filt_code)
 	uint8_t  cls;         // bit 0: handled by k_seed (else by k_filter, Myers); bit 1: every base is a plain A/C/G/T
 };
 struct Surv {             // one diagonal cluster of a (task, lane) that survived the filter
@@ -154,10 +163,6 @@ __device__ __forceinline__ uint32_t lane_word(const uint32_t *lanew, uint32_t wi
 //           nibble i & 7 -- the same nibble order as the DB) at word (off >> 3) + 3 * q, and the class:
 //           cls = 1 (k_seed) iff the seed filter is on, every stretch is long enough for the batch's
 //           window layout and the windows' bases are all plain A/C/G/T; else 0 (k_filter).
-// k_qtables: per (query, reference code c) the Myers match vector
-//   peq: bit (32-P+y-1) = 1 iff row y (1-based) matches c (S == 0).  The pattern is left-aligned so
-//        that row P sits in bit 31; the unused low 32-P bits are set for every code: with Pv = Mv = 0
-//        there they behave as extra copies of the all-zero row 0.
 // ---------------------------------------------------------------------------------------------
 #define SEED_NP_MAX 32                 // stretches per query the seed filter takes: 64 / stride windows per thread in the hash cache
 // stride: reference windows are probed every `stride` columns (8 = word ends, 4 = also half words, 0 = off);
@@ -176,7 +181,7 @@ __global__ void k_qinfo(const uint64_t *__restrict__ off, const uint16_t *__rest
 	uint64_t o = off[q], len = off[q + 1] - o;
 	uint32_t k = budget[q], s = slot[q];
 	if (off[q + 1] <= o || o < base_off || len > 0x7FFFFFFFull || k > 254 || s >= nslots) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; s = 0; o = base_off; }
-	QInfo Q; Q.off = o - base_off; Q.len = (uint32_t)len; Q.slot = s; Q.k = (uint16_t)k; Q.P = (uint8_t)min((uint64_t)32, len); Q.cls = 0;
+	QInfo Q; Q.off = o - base_off; Q.len = (uint32_t)len; Q.slot = s; Q.k = (uint16_t)k; Q.P = filt_code(len, k); Q.cls = 0;
 	qi[q] = Q;
 	if (hist && k + 1 <= SEED_NP_MAX) atomicAdd(&sh[min((uint32_t)len / (k + 1), 31u)], 1u);
 	}
@@ -269,21 +274,6 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 	if (unseeded && u && (threadIdx.x & 31) == 0) atomicAdd(unseeded, (uint32_t)__popc(u));
 }
 
-__global__ void k_qtables(const uint8_t *__restrict__ codes, const QInfo *__restrict__ qi, const uint32_t *__restrict__ Sterm,
-		uint32_t nq, uint32_t *__restrict__ peq) {
-	uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	uint32_t q = i >> 4, c = i & 15;
-	if (q >= nq) return;
-	QInfo Q = qi[q];
-	if (Q.cls & 1) return;                                   // taken by k_seed: no Myers table needed
-	const uint8_t *s = codes + Q.off;
-	const uint32_t P = Q.P;
-	uint32_t m = P < 32 ? (1u << (32 - P)) - 1 : 0;
-	for (uint32_t y = 0; y < P; ++y)
-		if (Sterm[(s[y] & 15) * 16 + c] == 0) m |= 1u << (32 - P + y);
-	peq[i] = m;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Diagonal clusters: a tiny sorted set of disjoint intervals (rare path, local memory is fine).
 // ---------------------------------------------------------------------------------------------
@@ -317,7 +307,7 @@ __device__ __noinline__ void emit_clusters(const Clus &C, uint32_t task, uint32_
 	for (int s = 0; s < C.n; ++s) {
 		const uint32_t W = (uint32_t)(C.hi[s] - C.lo[s] + 1);
 		uint32_t scratch = 0;
-		if (W > 64) scratch = atomicAdd(&counters[C_SCRATCH], W);
+		if (W > 64) atomicMax(&counters[C_SCRATCH], W);
 		if (base + s < surv_cap) {
 			Surv v; v.task = task; v.lo = C.lo[s]; v.w_lane = (W << 8) | ((s == 0 ? (uint32_t)C.n : 0u) << 4) | lane; v.scratch = scratch;
 			surv[base + s] = v;
@@ -653,7 +643,7 @@ __global__ void __launch_bounds__(128, 8) k_seed(SeedArgs A) {
 					const uint32_t W = (uint32_t)(dhi - dlo + 2 * k0 + 1);
 					const uint32_t slot = atomicAdd(&A.counters[C_SURV], 1u);
 					uint32_t scratch = 0;
-					if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+					if (W > 64) atomicMax(&A.counters[C_SCRATCH], W);
 					if (slot < A.surv_cap) { Surv v; v.task = task0 + LS.q[0]; v.lo = dlo - k0; v.w_lane = (W << 8) | (1u << 4) | l; v.scratch = scratch; A.surv[slot] = v; }
 				} else lane_seeds_emit(LS, kq, task0, l, A.surv, A.surv_cap, A.counters);
 			}
@@ -1014,7 +1004,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 									const int k0 = (int)kq[st.x], dlo = (int)st.y, dhi = (int)st.z;
 									const uint32_t W = (uint32_t)(dhi - dlo + 2 * k0 + 1);
 									emit = true; ev.task = task0 + st.x; ev.lo = dlo - k0; ev.w_lane = (W << 8) | (1u << 4) | l;
-									if (W > 64) ev.scratch = atomicAdd(&A.counters[C_SCRATCH], W);
+									if (W > 64) atomicMax(&A.counters[C_SCRATCH], W);
 								}
 							}
 						}
@@ -1048,29 +1038,25 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 // ---------------------------------------------------------------------------------------------
 struct FilterArgs {
 	const uint4 *db; const uint64_t *clump_off; const uint32_t *clump_len;
-	const QInfo *qi; const uint32_t *peq; Work W;
+	const QInfo *qi; const uint8_t *codes; const uint32_t *Sterm; Work W;
 	Surv *surv; uint32_t surv_cap; uint32_t *counters;
 	uint32_t c16;        // the constant 16, passed at run time so ptxas keeps IMAD.HI (FMA pipe)
 	const uint32_t *todo; // number of queries k_seed did not take (device; NULL = unknown, run)
 };
 
-// Hyyro's formulation of Myers' bit-vector step; the text character is one reference base.
-// Integer-pipe budget per column (ncu: the kernel is bound by the ALU pipe, LOP3/SHF/ISETP issue
-// at half rate): the seven 3-input logic ops below are irreducible, so everything that can run
-// on the FMA pipe instead is written as a multiply-add: the two shifts are x+x, the nibble
-// extraction is a mul.hi.  The row-P value is not tracked per column: it is popc(Pv) - popc(Mv)
-// (sum of the vertical deltas over the pattern rows), read once per 8 columns.
-__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {
+// Hyyro's block formulation of Myers' bit-vector algorithm over the first P rows of the query, NW words of 32 rows: the carry of
+// the addition and the shifted horizontal deltas pass from one word to the next as (hp, hm); the last word's pair is the change of
+// the row-P value from one column to the next.  P is chosen per query (filt_code): about four times its budget, so that a
+// prefix within budget is rare by chance -- with 32 rows a budget of 15 is met almost everywhere and the filter passes everything.
+// Seed columns (row-P value <= k) give diagonals x - P; consecutive ones merge into clusters [d - k, d + k] (at most CLUS_MAX per
+// lane, the closest fused beyond that), each cluster one survivor -- not one hull over the whole clump, which on the long
+// references of a sheared genome database would be a band as wide as the clump.
+__device__ __forceinline__ uint32_t mulhi(uint32_t a, uint32_t b) {      // nibble extraction on the FMA pipe (the ALU pipe is the kernel's bound)
 	uint32_t d; asm("mul.hi.u32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b)); return d;
 }
-#define MYERS_STEP(Eq)                                          \
-	const uint32_t Xv = (Eq) | Mv;                              \
-	const uint32_t Xh = ((((Eq) & Pv) + Pv) ^ Pv) | (Eq);       \
-	uint32_t Ph = Mv | ~(Xh | Pv);                              \
-	uint32_t Mh = Pv & Xh;
-
+template <int NW>
 __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
-	__shared__ uint32_t sPeq[8][16];
+	__shared__ uint32_t sPeq[8][NW][16];
 	if (A.todo && *A.todo == 0) return;                           // every query of the batch went to k_seed
 	const uint32_t slot = threadIdx.x >> 4, lane = threadIdx.x & 15;
 	const uint64_t ngroups = A.W.nruns * 2;                       // 8 task ids per group
@@ -1081,78 +1067,78 @@ __global__ void __launch_bounds__(128) k_filter(FilterArgs A) {
 	bool valid = r < A.W.nruns;
 	uint32_t q = 0, c = 0, q0 = 0, n = 0;
 	if (valid) { valid = get_run(A.W, r, c, q0, n) && qi_ < n; q = q0 + qi_; }
-	QInfo Q; Q.cls = 1; Q.P = 0; Q.k = 0;
-	if (valid) { Q = A.qi[q]; valid = !(Q.cls & 1); }                   // seed-eligible queries were handled by k_seed
-	sPeq[slot][lane] = valid ? A.peq[(size_t)q * 16 + lane] : 0;
+	QInfo Q; Q.cls = 1; Q.P = 0; Q.k = 0; Q.off = 0;
+	if (valid) { Q = A.qi[q]; valid = !(Q.cls & 1) && filt_words(Q.P) == (uint32_t)NW; }   // seed-eligible queries were handled by k_seed; other prefix lengths by the other instances
+	const int P = (int)filt_rows(Q.P), k = Q.k;
+	const int sh = NW == 1 ? 32 - P : 0;                           // a prefix shorter than a word sits in its top bits
+	{	// the match masks of reference code `lane` against the prefix rows (0 = the scoring table says the pair costs nothing)
+		const uint8_t *qs = A.codes + Q.off;
+		#pragma unroll 1
+		for (int w = 0; w < NW; ++w) {
+			uint32_t m = 0;
+			if (valid) {
+				if (NW == 1 && P < 32) m = (1u << sh) - 1u;
+				const int rows = min(32, P - 32 * w);
+				for (int y = 0; y < rows; ++y) if (A.Sterm[(qs[32 * w + y] & 15) * 16 + lane] == 0) m |= 1u << (y + sh);
+			}
+			sPeq[slot][w][lane] = m;
+		}
+	}
 	__syncwarp();
 	if (!valid) continue;
-	const int P = Q.P, k = Q.k;
 	const uint32_t L = A.clump_len[c];
 	const uint4 *base = A.db + A.clump_off[c] + lane;
-	const char *eq = (const char *)sPeq[slot];
-	const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(eq);
+	const uint32_t eqs = (uint32_t)__cvta_generic_to_shared(&sPeq[slot][0][0]);
 
-	uint32_t Pv = P < 32 ? ~0u << (32 - P) : ~0u, Mv = 0;
-	uint32_t cP = (uint32_t)P, cM = 0;          // row-P value = cP - cM
-	int lo = INT32_MAX, hi = INT32_MIN;
+	uint32_t Pv[NW], Mv[NW];
+	#pragma unroll
+	for (int w = 0; w < NW; ++w) { Pv[w] = ~0u; Mv[w] = 0; }
+	if (NW == 1 && P < 32) Pv[0] = ~0u << (32 - P);
+	int score = P;                                                 // row-P value of the column before the first
+	int clo = 0, chi = INT32_MIN; bool open = false; Clus C; C.n = 0;
 	const uint32_t nwords = (L + 7) >> 3;
 	uint4 w4 = base[0];
 	for (uint32_t wi0 = 0; wi0 < nwords; wi0 += 4) {
 		uint4 nx = w4;
 		if (wi0 + 4 < nwords) nx = base[(size_t)((wi0 >> 2) + 1) * 16];
 		const uint32_t ws[4] = {w4.x, w4.y, w4.z, w4.w};
-		#pragma unroll
+		#pragma unroll 1
 		for (int wi = 0; wi < 4; ++wi) {
 			if (wi0 + wi >= nwords) break;
 			const uint32_t w = ws[wi];
-			const uint32_t Pv0 = Pv, Mv0 = Mv;
-			const int s0 = (int)(cP - cM);
 			#pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				const uint32_t code = mulhi(j == 7 ? w : w << (28 - 4 * j), A.c16);
-				uint32_t Eq;
-				asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"(code * 4u + eqs));
-				MYERS_STEP(Eq)
-				Ph += Ph; Mh += Mh;
-				Pv = Mh | ~(Xv | Ph);                                // row 0 is all zero: no carry-in
-				Mv = Ph & Xv;
-			}
-			cP = (uint32_t)__popc(Pv); cM = (uint32_t)__popc(Mv);
-			// The row-P value moves by at most 1 per column, so inside these 8 columns it cannot
-			// drop below (s0 + s1 - 8) / 2.  Only then is a seed (value <= k) possible: redo the
-			// word column by column from the saved state.
-			const int s1 = (int)(cP - cM);
-			if (s0 + s1 - 8 <= 2 * k) {
-				uint32_t pv = Pv0, mv = Mv0; int score = s0;
-				#pragma unroll 1
-				for (int j = 0; j < 8; ++j) {
-					const uint32_t Eq = *(const uint32_t *)(eq + (((w >> (4 * j)) & 15u) << 2));
-					const uint32_t xv = Eq | mv;
-					const uint32_t xh = (((Eq & pv) + pv) ^ pv) | Eq;
-					uint32_t ph = mv | ~(xh | pv), mh = pv & xh;
-					score += (int)(ph >> 31) - (int)(mh >> 31);
-					ph <<= 1; mh <<= 1;
-					pv = mh | ~(xv | ph); mv = ph & xv;
+				uint32_t hp = 0, hm = 0;                                 // row 0 is all zero: nothing enters the first word
+				#pragma unroll
+				for (int b = 0; b < NW; ++b) {
+					uint32_t Eq;
+					asm volatile("ld.shared.u32 %0, [%1];" : "=r"(Eq) : "r"(eqs + (uint32_t)b * 64u + code * 4u));
+					const uint32_t Xv = Eq | Mv[b];
+					Eq |= hm;
+					const uint32_t Xh = (((Eq & Pv[b]) + Pv[b]) ^ Pv[b]) | Eq;
+					uint32_t Ph = Mv[b] | ~(Xh | Pv[b]), Mh = Pv[b] & Xh;
+					const uint32_t hpo = Ph >> 31, hmo = Mh >> 31;
+					Ph = (Ph << 1) | hp; Mh = (Mh << 1) | hm;
+					Pv[b] = Mh | ~(Xv | Ph);
+					Mv[b] = Ph & Xv;
+					hp = hpo; hm = hmo;
+				}
+				score += (int)hp - (int)hm;
+				if (score <= k) {                                        // seed: D[P][x] <= k
 					const int x = (int)((wi0 + wi) * 8 + j) + 1;
-					if (score <= k && x <= (int)L) {                 // seed: D[P][x] <= k
+					if (x <= (int)L) {
 						const int d = x - P;
-						lo = min(lo, d - k); hi = max(hi, d + k);
+						if (open && d - k <= chi + 1) chi = d + k;
+						else { if (open) clus_add(C, clo, chi); clo = d - k; chi = d + k; open = true; }
 					}
 				}
 			}
 		}
 		w4 = nx;
 	}
-	if (lo <= hi) {
-		const uint32_t W = (uint32_t)(hi - lo + 1);
-		uint32_t scratch = 0;
-		if (W > 64) scratch = atomicAdd(&A.counters[C_SCRATCH], W);
-		const uint32_t i = atomicAdd(&A.counters[C_SURV], 1u);
-		if (i < A.surv_cap) {
-			Surv s; s.task = (uint32_t)t + A.W.run_base * BG_RUN_MAX; s.lo = lo; s.w_lane = (W << 8) | (1u << 4) | lane; s.scratch = scratch;
-			A.surv[i] = s;
-		}
-	}
+	if (open) clus_add(C, clo, chi);
+	emit_clusters(C, (uint32_t)t + A.W.run_base * BG_RUN_MAX, lane, A.surv, A.surv_cap, A.counters);
 	}
 }
 
@@ -1167,7 +1153,7 @@ struct ExtendArgs {
 	const uint32_t *cls; const uint4 *xs;                // survivors of this launch binned by band class, as expanded records (k_bin_*)
 	uint32_t np_stage[NCLASS], qp_stage;                 // staging slot per thread and class: reference pieces, query word quads (uint4 each; 0 = read global memory)
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
-	uint32_t *scratch; uint32_t scratch_cap;
+	uint32_t *scratch; uint32_t scratch_w;           // generic bands (wider than 64): scratch_w cells per thread of the generic launch, cell d of thread t at scratch[d * threads + t]
 	unsigned long long *band_cells;
 	int mode;
 };
@@ -1327,8 +1313,9 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		constexpr int WB = WMAX ? WMAX : 1;
 		const int Wd = WMAX ? WMAX : (int)W;                 // cells per row actually swept
 		uint32_t a[WB];                                      // band, register resident when WMAX > 0
-		uint32_t *g = A.scratch + sv.scratch;                // generic path: band in global scratch
-		if (WMAX == 0 && (uint64_t)sv.scratch + W > A.scratch_cap) { Res z; z.a = 0; z.b = 0; z.slot = slot; A.res[i] = z; continue; }
+		uint32_t *g = A.scratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // generic path: this thread's band in global scratch, interleaved with the other threads'
+		const size_t GT = (size_t)gridDim.x * blockDim.x;
+		if (WMAX == 0 && W > A.scratch_w) { Res z; z.a = 0; z.b = 0; z.slot = slot; A.res[i] = z; continue; }   // (the host sees the width in the counter, grows the scratch and redoes the batch)
 		bool dead = false;
 		uint32_t y = 1;
 
@@ -1464,7 +1451,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			uint32_t c_, q0_, n_;
 			get_run(A.W, (sv.task >> 4) - A.W.run_base, c_, q0_, n_);
 			const uint8_t *qs = A.codes + A.qi[q0_ + (sv.task & 15)].off;
-			for (int d = 0; d < Wd; ++d) { const int x = lo + d; g[d] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
+			for (int d = 0; d < Wd; ++d) { const int x = lo + d; g[d * GT] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
 			for (; y <= m; ++y) {
 				const int x0 = (int)y + lo;
 				const uint32_t *Srow = sS + (qs[y - 1] & 15) * 16;
@@ -1472,12 +1459,12 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 				uint32_t diag = g[0];
 				for (int d = 0; d < Wd; ++d) {
 					const int x = x0 + d;
-					const uint32_t up = d + 1 < Wd ? g[d + 1] : inf;
+					const uint32_t up = d + 1 < Wd ? g[(d + 1) * GT] : inf;
 					const uint32_t st = Srow[fetch_code(lanew, (uint32_t)(x - 1), L)];
 					uint32_t v = cell(diag, up, left, st, inf);
 					if (x < 0 || x > (int)L) v = inf;
 					else if (x == 0) v = y <= k ? key_col0(y) : inf;
-					diag = up; g[d] = v; left = v; rowmin = min(rowmin, v);
+					diag = up; g[d * GT] = v; left = v; rowmin = min(rowmin, v);
 				}
 				if (rowmin >= inf) { dead = true; break; }
 				if ((y & 15) == 0 && A.mode == BG_MODE_MIN) { k = min(k, A.best[slot]); inf = (k + 1) << 22; }
@@ -1498,7 +1485,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			if (WMAX) {
 				#pragma unroll
 				for (int d = 0; d < WB; ++d) if (d < (int)W) scan(d, a[d]);      // the cluster's own diagonals only: beyond them the sweep may see part of a neighbouring cluster's band
-			} else for (int d = 0; d < Wd; ++d) scan(d, g[d]);
+			} else for (int d = 0; d < Wd; ++d) scan(d, g[d * GT]);
 			const uint32_t ed = bk >> 11, sh = 2047u - (bk & 2047u);
 			if (bk != (KEY_NONE >> 11) && ed <= k) {
 				out = ed | (sh << 8) | (bshr << 16) | (1u << 31);
@@ -1614,7 +1601,7 @@ __global__ void k_compact_qinfo(const unsigned long long *__restrict__ qoff, con
 		uint32_t r = strand[q] & 0x7FFFFFFFu, len = 1, k = 0;
 		if (r >= nreads) { atomicExch(&counters[C_ERR], q + 1); r = 0; }
 		else { len = rlen[r]; k = rbudget[r]; if (!len || k > 254) { atomicExch(&counters[C_ERR], q + 1); len = 1; k = 0; } }
-		QInfo Q; Q.off = qoff[q]; Q.len = len; Q.slot = r; Q.k = (uint16_t)k; Q.P = (uint8_t)min(32u, len); Q.cls = 0;
+		QInfo Q; Q.off = qoff[q]; Q.len = len; Q.slot = r; Q.k = (uint16_t)k; Q.P = filt_code(len, k); Q.cls = 0;
 		qi[q] = Q;
 		if (k + 1 <= SEED_NP_MAX) atomicAdd(&sh[min(len / (k + 1), 31u)], 1u);
 	}
@@ -1853,7 +1840,7 @@ __global__ void k_work_stats(Work W, const QInfo *__restrict__ qi, const uint32_
 		for (uint32_t i = 0; i < n; ++i) {
 			const QInfo Q = qi[q0 + i];
 			nominal += 16ull * Q.len * L;
-			if (Q.cls & 1) seeded = true; else fcells += 16ull * Q.P * L;
+			if (Q.cls & 1) seeded = true; else fcells += 16ull * filt_rows(Q.P) * L;
 		}
 		if (seeded) scells += 16ull * L;                         // k_seed streams the clump once per run
 		tasks += n;
@@ -1889,9 +1876,9 @@ enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
 #define NSLICEBUF 3
 struct Slice {
 	DBuf<uint8_t> packed, codes; DBuf<uint64_t> qoff; DBuf<uint16_t> budget; DBuf<uint32_t> slot;
-	DBuf<QInfo> qi; DBuf<uint32_t> peq, qnib; DBuf<bg_run> runs; DBuf<unsigned long long> sl64;
+	DBuf<QInfo> qi; DBuf<uint32_t> qnib; DBuf<bg_run> runs; DBuf<unsigned long long> sl64;
 	cudaEvent_t copied = nullptr, computed = nullptr;
-	void release() { sl64.release(); packed.release(); codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); peq.release(); qnib.release(); runs.release(); }
+	void release() { sl64.release(); packed.release(); codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); qnib.release(); runs.release(); }
 };
 
 struct bg_ctx {
@@ -1914,13 +1901,13 @@ struct bg_ctx {
 	uint32_t num_clumps = 0, first_clump = 0;
 	// batch
 	DBuf<uint8_t> d_packed; DBuf<uint8_t> d_codes; DBuf<uint64_t> d_qoff; DBuf<uint16_t> d_budget; DBuf<uint32_t> d_slot;
-	DBuf<QInfo> d_qi; DBuf<uint32_t> d_peq, d_qnib; DBuf<bg_run> d_runs;
+	DBuf<QInfo> d_qi; DBuf<uint32_t> d_qnib; DBuf<bg_run> d_runs;
 	DBuf<uint32_t> d_best; DBuf<uint16_t> d_best16;
 	DBuf<unsigned long long> d_acx_off; DBuf<uint8_t> d_post; DBuf<uint32_t> d_bad, d_cg_cnt, d_cg_first, d_cg_cache; DBuf<bg_xhit> d_xhits;   // accelerator on the device, candidate-generation scratch
 	int acx_n = 0, acx_big = 0; uint32_t acx_nbad = 0, acx_clumps = 0, cg_blocks = 0; uint32_t runs_cap = 0;
 	DBuf<uint16_t> d_rlen, d_rbud; DBuf<uint32_t> d_strand, d_candoff, d_cand; DBuf<unsigned long long> d_rl64, d_sl64, d_roff;   // compact strand batches
 	DBuf<uint32_t> d_cls; DBuf<uint4> d_xs;                       // band-class bins of the survivors, expanded records (k_bin_*)
-	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch;
+	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch; uint32_t scratch_w = 320;   // cells per thread of the generic band launch
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
 	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;   // cells: [0] band, [1..4] work stats
 	uint32_t *h_pinned = nullptr;                                 // 16 x u32 pinned scratch for small readbacks
@@ -1993,7 +1980,7 @@ extern "C" void bg_free(bg_ctx *c) {
 	cudaStreamSynchronize(c->stream);
 	c->d_sterm.release(); c->d_db.release(); c->d_clump_off.release(); c->d_clump_len.release(); c->d_meta.release();
 	c->d_packed.release(); c->d_codes.release(); c->d_qoff.release(); c->d_budget.release(); c->d_slot.release();
-	c->d_qi.release(); c->d_peq.release(); c->d_qnib.release(); c->d_runs.release();
+	c->d_qi.release(); c->d_qnib.release(); c->d_runs.release();
 	c->d_best.release(); c->d_best16.release(); c->d_surv.release(); c->d_res.release(); c->d_acx_off.release(); c->d_post.release(); c->d_bad.release(); c->d_cg_cnt.release(); c->d_cg_first.release(); c->d_cg_cache.release(); c->d_xhits.release();
 	c->d_cls.release(); c->d_xs.release(); c->d_rlen.release(); c->d_rbud.release(); c->d_strand.release(); c->d_candoff.release(); c->d_cand.release(); c->d_rl64.release(); c->d_sl64.release(); c->d_roff.release();
 	c->d_hits.release(); c->d_hits_sorted.release(); c->d_scratch.release(); c->d_counters.release(); c->d_cells.release();
@@ -2162,7 +2149,7 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	const uint64_t ncodes = Q->offset[nq];
 	if (Q->flags & ~(uint32_t)BG_Q_PACKED4) return fail(BG_EINVAL, "bg_batch_upload: unknown query flags %u", Q->flags);
 	if (c->d_qoff.need(nq + 1) || c->d_budget.need(nq) || c->d_slot.need(nq) || c->d_qi.need(nq) ||
-	    c->d_peq.need((size_t)nq * 16) || c->d_qnib.need(ncodes / 8 + 3ull * nq + 8) || c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) ||
+	    c->d_qnib.need(ncodes / 8 + 3ull * nq + 8) || c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) ||
 	    c->d_counters.need(64) || c->d_cells.need(8)) return BG_ENOMEM;
 	{ int rc = copy_codes(Q, Q->offset[0], ncodes, c->d_packed, c->d_codes, c->stream, c->stream, c->ev[3]); if (rc) return rc; }
 	CU(cudaMemcpyAsync(c->d_qoff.p, Q->offset, (size_t)(nq + 1) * 8, cudaMemcpyHostToDevice, c->stream));
@@ -2181,7 +2168,6 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
 	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nq / 8192); for (uint32_t q = 0; q < nq; q += stp) mx = std::max<uint64_t>(mx, Q->offset[q + 1] - Q->offset[q]); c->mstage = stage_len(mx); }
 	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
-	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = Q->nslots;
 	return BG_OK;
@@ -2202,7 +2188,6 @@ static int finish_upload(bg_ctx *c) {
 	if (c->surv_cap_forced) { want = c->surv_cap; c->surv_cap_forced = false; }      // (bg_set_surv_cap: the next batch starts from exactly that size)
 	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
 	if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
-	if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
 	c->ran = false; c->sorted = false;
 	return BG_OK;
 }
@@ -2256,7 +2241,7 @@ extern "C" int bg_batch_upload(bg_ctx *c, const bg_queries *Q, const bg_task *ta
 }
 
 // Device view of one uploaded batch (or one slice of a pipelined one).
-struct BatchDev { const uint8_t *codes; const uint32_t *qnib, *peq; const QInfo *qi; Work W; };
+struct BatchDev { const uint8_t *codes; const uint32_t *qnib; const QInfo *qi; Work W; };
 
 static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint32_t stretches_max, uint32_t &npmax) {
 	// Bloom filter size: 1-2 words per window of a full bunch (16 queries x mean stretches x stride): a false positive
@@ -2338,10 +2323,12 @@ static int launch_filters(bg_ctx *c, cudaStream_t st, const BatchDev &B, const S
 	if (B.W.nruns && filter) {
 		FilterArgs F;
 		F.db = c->d_db.p; F.clump_off = c->d_clump_off.p; F.clump_len = c->d_clump_len.p; F.qi = B.qi;
-		F.peq = B.peq; F.W = B.W; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap; F.counters = c->d_counters.p; F.c16 = 16;
+		F.codes = B.codes; F.Sterm = c->d_sterm.p; F.W = B.W; F.surv = c->d_surv.p; F.surv_cap = c->surv_cap; F.counters = c->d_counters.p; F.c16 = 16;
 		F.todo = todo;
 		const uint64_t blocks = std::min<uint64_t>(B.W.nruns * 2, (uint64_t)c->sms * 16);   // 8 task ids per group, groups strided over a resident grid
-		k_filter<<<(unsigned)blocks, 128, 0, st>>>(F);
+		// one instance per prefix length; each skips the queries of the others (and all return at once when k_seed took every query)
+		k_filter<1><<<(unsigned)blocks, 128, 0, st>>>(F); k_filter<2><<<(unsigned)blocks, 128, 0, st>>>(F); k_filter<4><<<(unsigned)blocks, 128, 0, st>>>(F);
+		k_filter<8><<<(unsigned)blocks, 128, 0, st>>>(F); k_filter<16><<<(unsigned)blocks, 128, 0, st>>>(F); k_filter<32><<<(unsigned)blocks, 128, 0, st>>>(F);
 		CU(cudaGetLastError());
 	}
 	return BG_OK;
@@ -2357,7 +2344,7 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 	E.dbw = (const uint32_t *)c->d_db.p; E.meta = c->d_meta.p;
 	E.codes = B.codes; E.qnib = B.qnib; E.qi = B.qi; E.W = B.W;
 	E.surv = c->d_surv.p; E.surv_cap = c->surv_cap; E.counters = c->d_counters.p; E.cls = c->d_cls.p; E.xs = c->d_xs.p; E.res = c->d_res.p;
-	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = c->d_scratch.p; E.scratch_cap = (uint32_t)std::min<size_t>(c->d_scratch.cap, 0xFFFFFFFFu);
+	E.best = c->d_best.p; E.Sterm = c->d_sterm.p; E.scratch = nullptr; E.scratch_w = c->scratch_w;
 	E.band_cells = c->d_cells.p; E.mode = mode;
 	// staging slot of a thread: the reference pieces and packed query words of one survivor of up to `mstage` bases (longer ones read
 	// global memory directly); two slots per thread, 128 threads per block
@@ -2386,6 +2373,12 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 		for (int k = 0; k < NCLASS; ++k) if (occ[k] > 0) grid[k] = std::min<unsigned>(grid[k], (unsigned)c->sms * (unsigned)(bps_cap > 0 ? std::min(bps_cap, occ[k]) : occ[k]));
 		(void)cudaGetLastError();
 	}
+	{	// the generic class keeps its bands in global scratch: scratch_w cells per thread, at most 4 GB in all
+		const unsigned most = (unsigned)std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)128 * c->scratch_w));
+		grid[8] = std::min(grid[8], most);
+		if (c->d_scratch.need((size_t)grid[8] * 128 * c->scratch_w)) return BG_ENOMEM;
+		E.scratch = c->d_scratch.p;
+	}
 	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 32 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K]));   /* (the kernel also has 1 KB of static shared memory) */ \
 		k_extend<WM><<<grid[K], 128, smem[K], st>>>(E); } while (0)
 	EXT_LAUNCH(5, 0); EXT_LAUNCH(8, 1); EXT_LAUNCH(12, 2); EXT_LAUNCH(16, 3); EXT_LAUNCH(24, 4); EXT_LAUNCH(32, 5); EXT_LAUNCH(48, 6); EXT_LAUNCH(64, 7); EXT_LAUNCH(0, 8);
@@ -2411,7 +2404,7 @@ static int run_extend(bg_ctx *c, int mode, const uint16_t *best_in) {
 	CU(cudaMemsetAsync(c->d_counters.p, 0, 16, c->stream));
 	CU(cudaMemsetAsync(c->d_cells.p, 0, 8, c->stream));
 	CU(cudaEventRecord(c->ev[0], c->stream));
-	BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.peq = c->d_peq.p; B.qi = c->d_qi.p; B.W = work_of(c);
+	BatchDev B; B.codes = c->d_codes.p; B.qnib = c->d_qnib.p; B.qi = c->d_qi.p; B.W = work_of(c);
 	int rc = launch_filters(c, c->stream, B, c->SL, c->seed_npmax, c->nseed != 0, c->nseed < c->nq, nullptr); if (rc) return rc;
 	CU(cudaEventRecord(c->ev[1], c->stream));
 	rc = launch_extend(c, c->stream, B, mode, nullptr); if (rc) return rc;
@@ -2438,13 +2431,13 @@ extern "C" int bg_batch_run_extend(bg_ctx *c, int mode, const uint16_t *best_in)
 		int rc = run_extend(c, mode, best_in); if (rc) return rc;
 		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
-		const bool grow_s = c->h_pinned[C_SURV] > c->surv_cap, grow_g = c->h_pinned[C_SCRATCH] > c->d_scratch.cap;
+		const bool grow_s = c->h_pinned[C_SURV] > c->surv_cap, grow_g = c->h_pinned[C_SCRATCH] > c->scratch_w;
 		if (!grow_s && !grow_g) return BG_OK;
 		if (grow_s) {
 			c->surv_cap = c->h_pinned[C_SURV] + c->h_pinned[C_SURV] / 4;
 			if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		}
-		if (grow_g && c->d_scratch.need((size_t)c->h_pinned[C_SCRATCH] + 1024)) return BG_ENOMEM;
+		if (grow_g) c->scratch_w = c->h_pinned[C_SCRATCH] + 64;
 	}
 	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_pinned[C_SURV]);
 }
@@ -2473,13 +2466,13 @@ static int settle(bg_ctx *c) {
 		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 16, cudaMemcpyDeviceToHost, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 		memcpy(c->h_counters, c->h_pinned, 16);
-		bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->d_scratch.cap;
+		bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->scratch_w;
 		if (!grow_s && !grow_g) return BG_OK;
 		if (grow_s) {
 			c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
 			if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 		}
-		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
+		if (grow_g) c->scratch_w = c->h_counters[C_SCRATCH] + 64;
 		int rc = run_extend(c, c->last_mode, c->have_best_in ? c->last_best_in.data() : nullptr);
 		if (rc) return rc;
 		rc = run_select(c, c->last_mode);
@@ -2617,8 +2610,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 	const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
 	for (int attempt = 0; attempt < 4; ++attempt) {
 		if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
-		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
-		if (c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128)) return BG_ENOMEM;
+			if (c->d_best.need(Q->nslots) || c->d_best16.need(Q->nslots) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128)) return BG_ENOMEM;
 		cudaStream_t cs = c->stream, ps = c->copy_stream;
 		if (best_inout) CU(cudaMemcpyAsync(c->d_best16.p, best_inout, (size_t)Q->nslots * 2, cudaMemcpyHostToDevice, cs));
 		k_init_best<<<(Q->nslots + 255) / 256, 256, 0, cs>>>(c->d_best.p, best_inout ? c->d_best16.p : nullptr, Q->nslots);
@@ -2643,7 +2635,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			if (Q->offset[qb] < base) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return fail(BG_EINVAL, "bg_align_runs: query offsets are not ascending"); }
 			Slice &S = c->sl[i % NSLICEBUF];
 			if (S.qoff.need((size_t)n + 1) || S.budget.need(n) || S.slot.need(n) || S.qi.need(n) ||
-			    S.peq.need((size_t)n * 16) || S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) return BG_ENOMEM;
+			    S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) return BG_ENOMEM;
 			if (i >= NSLICEBUF) CU(cudaStreamWaitEvent(ps, S.computed, 0));   // the slice that used these buffers last is done with them
 			{ int rc = copy_codes(Q, base, base + bytes, S.packed, S.codes, ps, ps, S.copied); if (rc) return rc; }
 			CU(cudaMemcpyAsync(S.qoff.p, Q->offset + qa, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ps));
@@ -2654,10 +2646,9 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			CU(cudaStreamWaitEvent(cs, S.copied, 0));
 			k_qinfo<<<(n + 255) / 256, 256, 0, cs>>>(S.qoff.p, S.budget.p, S.slot.p, n, Q->nslots, S.qi.p, nullptr, c->d_counters.p, base);
 			k_qprep<<<(n + 127) / 128, 128, 0, cs>>>(S.codes.p, S.qi.p, n, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
-			k_qtables<<<(unsigned)(((uint64_t)n * 16 + 255) / 256), 256, 0, cs>>>(S.codes.p, S.qi.p, c->d_sterm.p, n, S.peq.p);
 			k_check_runs<<<(unsigned)((rb - ra + 255) / 256), 256, 0, cs>>>(S.runs.p, rb - ra, qa, n, c->d_counters.p);
 			CU(cudaMemcpyAsync(c->d_first.p + i, c->d_counters.p + C_SURV, 4, cudaMemcpyDeviceToDevice, cs));
-			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.peq = S.peq.p; B.qi = S.qi.p;
+			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.qi = S.qi.p;
 			B.W.runs = S.runs.p; B.W.nruns = rb - ra; B.W.nq = n; B.W.ntiles = 0; B.W.first_clump = c->first_clump; B.W.num_clumps = c->num_clumps;
 			B.W.q_base = qa; B.W.run_base = (uint32_t)ra;
 			int rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64 + i); if (rc) return rc;
@@ -2672,7 +2663,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 		CU(cudaStreamSynchronize(ps));
 		memcpy(c->h_counters, c->h_pinned, 16);
 		if (c->h_counters[C_ERR]) return fail(BG_EINVAL, "bg_align_runs: a query or run of the batch is malformed (query lengths >= 1, budgets <= 254 (burst.c:3076), slots < nslots, runs within the batch)");
-		const bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->d_scratch.cap;
+		const bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->scratch_w;
 		if (!grow_s && !grow_g) {
 			const uint64_t n = c->h_counters[C_HITS];
 			if (n > cap) { *nhits = n; return fail(BG_EOVERFLOW, "bg_align_runs_into: %llu hits, room for %llu", (unsigned long long)n, (unsigned long long)cap); }
@@ -2693,7 +2684,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			return BG_OK;
 		}
 		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
-		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
+		if (grow_g) c->scratch_w = c->h_counters[C_SCRATCH] + 64;
 	}
 	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
 }
@@ -2754,7 +2745,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	}
 	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_runs.need(nruns + 1) || c->d_cand.need(nruns + 1) ||
 	    c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) || c->d_qoff.need((size_t)nq + 1) ||
-	    c->d_qi.need(nq) || c->d_peq.need((size_t)nq * 16) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128) ||
+	    c->d_qi.need(nq) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8) || c->d_first.need(128) ||
 	    c->d_packed.need(rbytes + 32) || c->d_codes.need(ncodes_max + 32) || c->d_qnib.need(ncodes_max / 8 + 3ull * nq + 8)) return BG_ENOMEM;
 	size_t tmp1 = 0, tmp2 = 0;
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, cs));
@@ -2767,8 +2758,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	  if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull); }
 	for (int attempt = 0; attempt < 4; ++attempt) {
 		if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
-		if (!c->d_scratch.p && c->d_scratch.need(1u << 22)) return BG_ENOMEM;
-		// ---- host -> device on the copy stream: the reads and their lengths/budgets first, then the strands and candidates slice by slice;
+			// ---- host -> device on the copy stream: the reads and their lengths/budgets first, then the strands and candidates slice by slice;
 		//      the kernels of slice i (strand records, codes, runs, seed filter, banded sweep) run while slice i+1 travels ----
 		const double hstart = (double)clock() / CLOCKS_PER_SEC;
 		static cudaEvent_t te0 = nullptr;
@@ -2816,7 +2806,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			if (!n) continue;
 			Slice &S = c->sl[i % NSLICEBUF];
 			const uint64_t scodes = (uint64_t)n * (((uint64_t)maxlen + 15) & ~15ull);
-			if (S.sl64.need((size_t)n + 1) || S.qoff.need((size_t)n + 1) || S.qi.need(n) || S.peq.need((size_t)n * 16) || S.codes.need(scodes + 32) || S.qnib.need(scodes / 8 + 3ull * n + 8) || S.runs.need((size_t)(rb - ra) + 1)) {
+			if (S.sl64.need((size_t)n + 1) || S.qoff.need((size_t)n + 1) || S.qi.need(n) || S.codes.need(scodes + 32) || S.qnib.need(scodes / 8 + 3ull * n + 8) || S.runs.need((size_t)(rb - ra) + 1)) {
 				cudaStreamSynchronize(ps); cudaStreamSynchronize(cs); return BG_ENOMEM;
 			}
 			CU(cudaMemcpyAsync(c->d_strand.p + qa, R->strand + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
@@ -2830,10 +2820,9 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			if (i == 0) CU(cudaStreamWaitEvent(cs, c->sl[0].copied, 0));   // the packed reads
 			k_compact_codes<<<(unsigned)(((uint64_t)n * 8 + 255) / 256), 256, 0, cs>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p + qa, (const unsigned long long *)S.qoff.p, n, nr, S.codes.p);
 			k_qprep<<<(n + 127) / 128, 128, 0, cs>>>(S.codes.p, S.qi.p, n, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
-			k_qtables<<<(unsigned)(((uint64_t)n * 16 + 255) / 256), 256, 0, cs>>>(S.codes.p, S.qi.p, c->d_sterm.p, n, S.peq.p);
 			CU(cudaMemcpyAsync(c->d_first.p + i, c->d_counters.p + C_SURV, 4, cudaMemcpyDeviceToDevice, cs));
 			CU(cudaGetLastError());
-			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.peq = S.peq.p; B.qi = S.qi.p;
+			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.qi = S.qi.p;
 			B.W.runs = S.runs.p; B.W.nruns = rb - ra; B.W.nq = n; B.W.ntiles = 0; B.W.first_clump = c->first_clump; B.W.num_clumps = c->num_clumps;
 			B.W.q_base = qa; B.W.run_base = ra;
 			if (i == 0) CU(cudaEventRecord(c->ev[0], cs));
@@ -2849,7 +2838,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		memcpy(c->h_counters, c->h_pinned, 16);
 		c->nseed = c->h_pinned[9]; c->last_mode = mode; c->have_best_in = false; c->ran = true; c->sorted = false;
 		if (c->h_counters[C_ERR]) { c->kind = WORK_NONE; return fail(BG_EINVAL, "bg_align_bunches_into: malformed batch (strands must name reads < nreads, read lengths >= 1, budgets <= 254 (burst.c:3076), ascending candidate offsets)"); }
-		const bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->d_scratch.cap;
+		const bool grow_s = c->h_counters[C_SURV] > c->surv_cap, grow_g = c->h_counters[C_SCRATCH] > c->scratch_w;
 		if (!grow_s && !grow_g) {
 			const uint64_t n = c->h_counters[C_HITS];
 			*nhits = n;
@@ -2875,7 +2864,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			return BG_OK;
 		}
 		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
-		if (grow_g && c->d_scratch.need((size_t)c->h_counters[C_SCRATCH] + 1024)) return BG_ENOMEM;
+		if (grow_g) c->scratch_w = c->h_counters[C_SCRATCH] + 64;
 	}
 	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
 }
@@ -2940,7 +2929,7 @@ extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbu
 	for (uint32_t r = 0; r < nr; ++r) { total += R->len[r]; maxlen = std::max<uint32_t>(maxlen, R->len[r]); }
 	const uint64_t rbytes = (total + 3) / 4, ncodes_max = (uint64_t)nq * (((uint64_t)maxlen + 15) & ~15ull);
 	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) ||
-	    c->d_qoff.need((size_t)nq + 1) || c->d_qi.need(nq) || c->d_peq.need((size_t)nq * 16) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8) ||
+	    c->d_qoff.need((size_t)nq + 1) || c->d_qi.need(nq) || c->d_best.need(nr) || c->d_best16.need(nr) || c->d_counters.need(64) || c->d_cells.need(8) ||
 	    c->d_packed.need(rbytes + 32) || c->d_codes.need(ncodes_max + 32) || c->d_qnib.need(ncodes_max / 8 + 3ull * nq + 8)) return BG_ENOMEM;
 	size_t tmp1 = 0, tmp2 = 0;
 	CU(cub::DeviceScan::ExclusiveSum(nullptr, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
@@ -2965,7 +2954,6 @@ extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbu
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
 	c->mstage = stage_len(maxlen);
 	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
-	k_qtables<<<(unsigned)(((uint64_t)nq * 16 + 255) / 256), 256, 0, st>>>(c->d_codes.p, c->d_qi.p, c->d_sterm.p, nq, c->d_peq.p);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = nr;
 	// ---- candidates -> runs on the device ----

@@ -211,6 +211,14 @@ def bunch_workload(n_reads, read_len, n_err, db_bytes, clump_len, seed, qbunch=1
     nclumps = max(16, int(db_bytes // (nvec * 16)))
     packed, coff, clens = random_clumps_fast(nclumps, clump_len, np.random.default_rng(1000003))
     codes, off, clump, lane, start, rcflag = llsim_reads(packed, nclumps, clump_len, n_reads, read_len, n_err, rng)
+    return _bunch_form(codes, off, clump, lane, start, rcflag, n_reads, qbunch, packed, coff, clens,
+                       np.full(2 * n_reads, n_err, np.uint16) if budget is None else budget, 0)
+
+
+def _bunch_form(codes, off, clump, lane, start, rcflag, n_reads, qbunch, packed, coff, clens, budget, halo):
+    """Strands, bunches, candidates, tasks and runs of a read set (the common tail of the bench workloads).  Candidates of a
+    bunch = for every strand that matches the database, the clump it was cut from and `halo` clumps either side."""
+    nclumps = len(clens)
     rcodes = reverse_complement_all(codes, off)
     lens = np.diff(off).astype(np.int64)
     # strands: 2i = as sequenced, 2i+1 = its reverse complement; the strand equal to the DB lane matches
@@ -229,7 +237,12 @@ def bunch_workload(n_reads, read_len, n_err, db_bytes, clump_len, seed, qbunch=1
     match = smatch[order]
     nq = len(order)
     bunch_of = np.arange(nq) // qbunch
-    pairs = np.unique(np.stack([bunch_of[match], clump[slot[match]]], 1), axis=0)   # (bunch, clump), sorted
+    pb, pc = bunch_of[match], clump[slot[match]].astype(np.int64)
+    if halo:
+        d = np.arange(-halo, halo + 1, dtype=np.int64)
+        pc = (pc[:, None] + d[None, :]).reshape(-1); pb = np.repeat(pb, len(d))
+        keep = (pc >= 0) & (pc < nclumps); pb, pc = pb[keep], pc[keep]
+    pairs = np.unique(np.stack([pb, pc], 1), axis=0)   # (bunch, clump), sorted
     nb = (nq + qbunch - 1) // qbunch
     cand_off = np.zeros(nb + 1, np.uint64)
     np.add.at(cand_off, pairs[:, 0] + 1, 1)
@@ -244,14 +257,49 @@ def bunch_workload(n_reads, read_len, n_err, db_bytes, clump_len, seed, qbunch=1
     # the same visits as run records {clump, query0, nq}: one per (bunch, candidate clump)
     runs = np.zeros(len(cand), dtype=np.dtype([("clump", "<u4"), ("query0", "<u4"), ("nq", "<u4")]))
     runs["clump"] = cand; runs["query0"] = qstart; runs["nq"] = qcount
-    if budget is None:
-        budget = np.full(nq, n_err, np.uint16)
     # the compact form of the same batch (bg_align_bunches_into): reads as sequenced, strand = read | rc << 31 in sorted order
     strand = (sread[order].astype(np.uint32) | ((order >= n_reads).astype(np.uint32) << 31)).astype(np.uint32)
     return dict(packed=packed, clump_off=coff, clump_len=clens, qcodes=qcodes, qoff=qoff, slot=slot,
-                nslots=n_reads, budget=budget, tasks=tasks, runs=runs, cand_off=cand_off, cand=cand, qbunch=qbunch,
+                nslots=n_reads, budget=np.asarray(budget, np.uint16), tasks=tasks, runs=runs, cand_off=cand_off, cand=cand, qbunch=qbunch,
                 true_clump=clump, true_lane=lane, true_start=start, n_reads=n_reads, match=match,
                 rcodes=codes, rlen=lens.astype(np.uint16), strand=strand)
+
+
+def amplicon_workload(n_reads, read_len, max_edits, db_bytes, ref_len, seed, budget, qbunch=16, halo=29):
+    """BASELINE.json configs[2] shape: a database of `ref_len`-base marker genes in a mutation tree (phyla 25 %, families 10 %,
+    genera 5 %, 3 % and species ~1.5 % apart, substitutions only), sorted so that relatives share clumps (what the reference's
+    clustering is for); reads = one jittered window of a random reference with 0..max_edits substitutions; a bunch visits the
+    clumps of its reads and `halo` clumps either side (~59 visits per query for halo 29: BASELINE.md section 2).  Unlike the
+    shotgun shape most lanes of a visited clump lie within the budget of most queries of the bunch."""
+    rng = np.random.default_rng(seed)
+    nrefs = max(4096, int(db_bytes // ((ref_len + 1) // 2)) // 16 * 16)
+    def children(parents, k, frac):
+        ch = np.repeat(parents, k, axis=0)
+        m = rng.random(ch.shape, dtype=np.float32) < frac
+        sub = rng.integers(1, 4, ch.shape, dtype=np.uint8)
+        return np.where(m, (ch - 1 + sub) % 4 + 1, ch).astype(np.uint8)
+    nodes = rng.integers(1, 5, (1, ref_len), dtype=np.uint8)
+    for frac in (0.25, 0.10, 0.05, 0.03):
+        nodes = children(nodes, 4, frac)                               # 256 genera
+    refs = children(nodes, (nrefs + 255) // 256, 0.015)[:nrefs]
+    rows = [r.tobytes() for r in refs]
+    refs = refs[np.array(sorted(range(nrefs), key=rows.__getitem__))]
+    del rows
+    nclumps = nrefs // 16; nv = (ref_len + 1) // 2
+    m = np.zeros((nclumps, 16, nv * 2), np.uint8); m[:, :, :ref_len] = refs.reshape(nclumps, 16, ref_len)
+    packed = np.ascontiguousarray((m[:, :, 0::2] | (m[:, :, 1::2] << 4)).transpose(0, 2, 1)).reshape(-1)   # clump: nv vectors of 16 lanes
+    del m
+    coff = np.arange(nclumps, dtype=np.uint64) * np.uint64(nv * 16); clens = np.full(nclumps, ref_len, np.uint32)
+    src = rng.integers(0, nrefs, n_reads); start = 60 + rng.integers(-5, 6, n_reads)
+    reads = refs[src[:, None], start[:, None] + np.arange(read_len)[None, :]]
+    e = rng.integers(0, max_edits + 1, n_reads)
+    for k in range(max_edits):                                           # (positions may coincide: then a read carries fewer edits)
+        on = np.nonzero(e > k)[0]; pos = rng.integers(0, read_len, len(on))
+        reads[on, pos] = (reads[on, pos] - 1 + rng.integers(1, 4, len(on))) % 4 + 1
+    codes = reads.reshape(-1).astype(np.uint8)
+    off = np.arange(n_reads + 1, dtype=np.uint64) * np.uint64(read_len)
+    return _bunch_form(codes, off, (src // 16).astype(np.int64), (src % 16).astype(np.int64), start + 1, np.zeros(n_reads, bool), n_reads, qbunch,
+                       packed, coff, clens, np.full(2 * n_reads, budget, np.uint16), halo)
 
 
 def random_clumps_fast(nclumps, clump_len, rng):

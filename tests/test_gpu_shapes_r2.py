@@ -148,3 +148,49 @@ def test_compact_strand_batches_match_the_oracle(eng, oracle, mode):
         assert n == len(ohits) and np.array_equal(buf[:n], ohits), (mode, packed2, n, len(ohits))
         assert np.array_equal(b2, obest)
         assert n > 150
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_long_queries_large_budgets(eng, oracle, mode):
+    """The shape of the reference's manuscript data set (genes of up to 7 kbp against sheared genomes, budgets
+    up to 139): queries of 150 - 1500 bases with budgets of 7 - 150 against 2600-column clumps that hold a repeat.  Queries with more
+    than 16 stretches cannot take the pigeonhole filter: they go through the multi-word Myers prefix filter (k_filter<NW>, one
+    instance per prefix length), every seed cluster its own survivor, bands wider than 64 in the per-thread global scratch."""
+    rng = np.random.default_rng(900 + mode)
+    refs = synth.random_refs(16 * 5, 2600, rng, jitter=30)
+    for i in range(0, 80, 7):                                             # a repeat: the same 900 bases twice in one reference, 1100 apart
+        refs[i][1500:2400] = refs[i][400:1300]
+    for i in range(3, 80, 11):                                            # and a near copy of a reference in another clump
+        refs[(i + 37) % 80] = synth.mutate(refs[i], 12, rng)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, budget = [], []
+    for i in range(20):
+        L = int(rng.choice([150, 300, 640, 900, 1500])); ident = float(rng.choice([0.95, 0.92, 0.90]))
+        src = refs[int(rng.integers(0, 80))]; st = int(rng.integers(0, len(src) - L))
+        k = oracle.budget(ident, L)
+        r = synth.mutate(src[st:st + L], int(rng.integers(0, k + 1)), rng, p_sub=0.7, p_ins=0.15)
+        if i % 6 == 5:
+            r[len(r) // 3] = 5                                             # an N
+        reads.append(r); budget.append(oracle.budget(ident, len(r)))
+    budget = np.array(budget, np.uint16)
+    assert int(budget.max()) > 100 and int(budget.min()) < 16
+    codes, qoff = synth.concat_queries(reads)
+    order = synth.sort_strands(codes, qoff)
+    reads = [reads[i] for i in order]; budget = budget[order]
+    codes, qoff = synth.concat_queries(reads)
+    nq = len(reads)
+    runs, tq, tc, key = synth.bunch_runs(nq, 16, lambda b, q0, n: np.arange(len(clen)))
+    S = oracle.score_table(1)
+    ohits, obest = oracle.run_tasks(packed, off, clen, codes, qoff, budget, np.arange(nq, dtype=np.uint32), nq, tq, tc, S, mode)
+    ohits = ohits.copy(); ohits["task"] = key[ohits["task"]]
+    ohits = ohits[np.lexsort((ohits["lane"], ohits["task"]))]
+    assert len(ohits) >= nq
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    try:
+        for seedf in (True, False):
+            eng.set_seed_filter(seedf)
+            hits, best = eng.align(codes, qoff, budget, None, mode, runs=runs.astype(RUN_DTYPE))
+            assert np.array_equal(best, obest), seedf
+            assert len(hits) == len(ohits) and np.array_equal(hits, ohits), (seedf, len(hits), len(ohits))
+    finally:
+        eng.set_seed_filter(True)
