@@ -1153,6 +1153,7 @@ struct ExtendArgs {
 	const uint32_t *cls; const uint4 *xs;                // survivors of this launch binned by band class, as expanded records (k_bin_*)
 	uint32_t np_stage[NCLASS], qp_stage;                 // staging slot per thread and class: reference pieces, query word quads (uint4 each; 0 = read global memory)
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
+	uint32_t smem_w;                                      // generic bands of up to smem_w cells live in shared memory (cell d of thread t at word d * 128 + t)
 	uint32_t *scratch; uint32_t scratch_w;           // generic bands (wider than 64): scratch_w cells per thread of the generic launch, cell d of thread t at scratch[d * threads + t]
 	unsigned long long *band_cells;
 	int mode;
@@ -1314,7 +1315,8 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		const int Wd = WMAX ? WMAX : (int)W;                 // cells per row actually swept
 		uint32_t a[WB];                                      // band, register resident when WMAX > 0
 		uint32_t *g = A.scratch + (size_t)blockIdx.x * blockDim.x + threadIdx.x;   // generic path: this thread's band in global scratch, interleaved with the other threads'
-		const size_t GT = (size_t)gridDim.x * blockDim.x;
+		size_t GT = (size_t)gridDim.x * blockDim.x;
+		if (WMAX == 0 && W <= A.smem_w) { g = (uint32_t *)xstage + threadIdx.x; GT = blockDim.x; }   // the usual case: a tenth of the latency per cell
 		if (WMAX == 0 && W > A.scratch_w) { Res z; z.a = 0; z.b = 0; z.slot = slot; A.res[i] = z; continue; }   // (the host sees the width in the counter, grows the scratch and redoes the batch)
 		bool dead = false;
 		uint32_t y = 1;
@@ -1456,10 +1458,11 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 				const int x0 = (int)y + lo;
 				const uint32_t *Srow = sS + (qs[y - 1] & 15) * 16;
 				uint32_t rowmin = KEY_NONE, left = inf;
-				uint32_t diag = g[0];
+				uint32_t diag = g[0], upn = Wd > 1 ? g[GT] : inf;
 				for (int d = 0; d < Wd; ++d) {
 					const int x = x0 + d;
-					const uint32_t up = d + 1 < Wd ? g[(d + 1) * GT] : inf;
+					const uint32_t up = upn;
+					upn = d + 2 < Wd ? g[(d + 2) * GT] : inf;               // (read before this cell's store: cell d + 2 still holds the previous row)
 					const uint32_t st = Srow[fetch_code(lanew, (uint32_t)(x - 1), L)];
 					uint32_t v = cell(diag, up, left, st, inf);
 					if (x < 0 || x > (int)L) v = inf;
@@ -2375,9 +2378,11 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 	}
 	{	// the generic class keeps its bands in global scratch: scratch_w cells per thread, at most 4 GB in all
 		const unsigned most = (unsigned)std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)128 * c->scratch_w));
-		grid[8] = std::min(grid[8], most);
+		grid[8] = std::min(std::min(grid[8], most), (unsigned)c->sms);
 		if (c->d_scratch.need((size_t)grid[8] * 128 * c->scratch_w)) return BG_ENOMEM;
 		E.scratch = c->d_scratch.p;
+		E.smem_w = std::min<uint32_t>(c->scratch_w, 416);              // 416 cells x 128 threads x 4 B = 208 KB: one block per SM
+		smem[8] = (size_t)E.smem_w * 128 * 4;
 	}
 	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 32 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K]));   /* (the kernel also has 1 KB of static shared memory) */ \
 		k_extend<WM><<<grid[K], 128, smem[K], st>>>(E); } while (0)
