@@ -2186,7 +2186,7 @@ static int finish_upload(bg_ctx *c) {
 	if (c->nseed) seed_sizes(c, c->SL, (c->h_pinned[10] + c->nseed - 1) / c->nseed, c->h_pinned[11], c->seed_npmax);
 	memset(&c->stats, 0, sizeof(c->stats));
 	if (!c->surv_cap) c->surv_cap = 1u << 20;
-	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, 4ull * c->nq + c->ntasks / 8));
+	uint64_t want = std::min<uint64_t>(c->ntasks * 16, std::max<uint64_t>(c->surv_cap, std::min<uint64_t>(4ull * c->nq + c->ntasks / 8, 1ull << 26)));   // (at most 64 M entries up front: 6 GB of lists; more only when a batch proves to need it)
 	want = std::max<uint64_t>(want, 1024);
 	if (c->surv_cap_forced) { want = c->surv_cap; c->surv_cap_forced = false; }      // (bg_set_surv_cap: the next batch starts from exactly that size)
 	if (want > c->surv_cap || !c->d_surv.p) c->surv_cap = (uint32_t)std::min<uint64_t>(want, 0xFFFFFFF0ull);
@@ -2497,6 +2497,7 @@ extern "C" int bg_batch_count(bg_ctx *c, uint64_t *nhits) {
 // hits ordered by (task, lane) on the device: radix sort of 32+4-bit keys, then a gather
 static int sort_hits(bg_ctx *c, uint32_t n) {
 	if (c->sorted || !n) { c->sorted = true; return BG_OK; }
+	if (n > 0x7FFFFFFFu) return fail(BG_EOVERFLOW, "%u hits in one batch (the hit sort takes at most 2^31-1); use smaller batches", n);
 	if (c->d_keys2.need(n) || c->d_order.need(n) || c->d_order2.need(n) || c->d_hits_sorted.need(n)) return BG_ENOMEM;
 	size_t tmp = 0;
 	CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, 36, c->stream));
@@ -2640,9 +2641,9 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			if (Q->offset[qb] < base) { cudaStreamSynchronize(c->copy_stream); cudaStreamSynchronize(c->stream); return fail(BG_EINVAL, "bg_align_runs: query offsets are not ascending"); }
 			Slice &S = c->sl[i % NSLICEBUF];
 			if (S.qoff.need((size_t)n + 1) || S.budget.need(n) || S.slot.need(n) || S.qi.need(n) ||
-			    S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) return BG_ENOMEM;
+			    S.qnib.need(bytes / 8 + 3ull * n + 8) || S.runs.need(rb - ra + 1)) { cudaStreamSynchronize(ps); cudaStreamSynchronize(cs); return BG_ENOMEM; }   // earlier slices still read the caller's arrays
 			if (i >= NSLICEBUF) CU(cudaStreamWaitEvent(ps, S.computed, 0));   // the slice that used these buffers last is done with them
-			{ int rc = copy_codes(Q, base, base + bytes, S.packed, S.codes, ps, ps, S.copied); if (rc) return rc; }
+			{ int rc = copy_codes(Q, base, base + bytes, S.packed, S.codes, ps, ps, S.copied); if (rc) { cudaStreamSynchronize(ps); cudaStreamSynchronize(cs); return rc; } }
 			CU(cudaMemcpyAsync(S.qoff.p, Q->offset + qa, ((size_t)n + 1) * 8, cudaMemcpyHostToDevice, ps));
 			CU(cudaMemcpyAsync(S.budget.p, Q->budget + qa, (size_t)n * 2, cudaMemcpyHostToDevice, ps));
 			CU(cudaMemcpyAsync(S.slot.p, Q->slot + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));

@@ -324,7 +324,7 @@ static void load_edx(const char *fn, Refs *R) {
 	if (ver != 3 && ver != 2) { fprintf(stderr, "ERROR: invalid database version %u\n", ver); exit(1); }
 	if (ver == 2) { fprintf(stderr, "ERROR: Old DB version. Re-make with new version.\n"); exit(2); }
 	REBASE = (cb >> 6) & 1;
-	if ((cb >> 5) & 1) printf(" --> EDB: Fingerprints are DISABLED\n");
+	printf(" --> EDB: Fingerprints are DISABLED\n");                     /* burst.c:2856-2857: DO_FP = (DB has them) && -f; -f is not supported here, so always */
 	if ((cb >> 4) & 1) { fprintf(stderr, "ERROR: DB made with Xalpha; queries must use Xalpha.\n"); exit(1); }
 	uint64_t totRefHeadLen; uint32_t shear, totR, origTotR, numRclumps, maxLenR, numRefHeads;
 	rd(&totRefHeadLen, 8, 1, in); rd(&shear, 4, 1, in); rd(&totR, 4, 1, in); rd(&origTotR, 4, 1, in);
