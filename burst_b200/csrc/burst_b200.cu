@@ -36,6 +36,7 @@
 #include <stdarg.h>
 #include <algorithm>
 #include <vector>
+#include <chrono>
 #include <type_traits>
 #include "burst_b200.h"
 
@@ -2726,14 +2727,34 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	if ((uint64_t)nbunch * qbunch < R->nq || (uint64_t)(nbunch - 1) * qbunch >= R->nq) return fail(BG_EINVAL, "bg_align_bunches_into: %u bunches of %u do not cover %u strands", nbunch, qbunch, R->nq);
 	const uint64_t nruns = cand_off[nbunch];
 	if (cand_off[0] != 0 || nruns >= (1ull << 28)) return fail(BG_EINVAL, "bg_align_bunches_into: candidate offsets must start at 0 and end below 2^28");
+	const auto wall0 = std::chrono::steady_clock::now();
 	CU(cudaSetDevice(c->device));
 	c->kind = WORK_NONE; c->ran = false;
 	const uint32_t nq = R->nq, nr = R->nreads;
 	cudaStream_t cs = c->stream, ps = c->copy_stream;
+	// ---- the small arrays leave first, so that they travel while the host looks at the lengths (single-slice calls, first attempt) ----
+	static const int want_slices = getenv("BURST_B200_COMPACT_SLICES") ? std::max(1, std::min(32, atoi(getenv("BURST_B200_COMPACT_SLICES")))) : 1;
+	const int nsl = (int)std::min<uint64_t>((uint64_t)want_slices, std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
+	bool early = nsl == 1;
+	if (early) {
+		if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_cand.need(nruns + 1)) return BG_ENOMEM;
+		CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
+		CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
+		CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, ps));
+		CU(cudaEventRecord(c->sl[1].copied, ps));
+		CU(cudaMemcpyAsync(c->d_strand.p, R->strand, (size_t)nq * 4, cudaMemcpyHostToDevice, ps));
+		if (nruns) CU(cudaMemcpyAsync(c->d_cand.p, cand, (size_t)nruns * 4, cudaMemcpyHostToDevice, ps));
+		CU(cudaEventRecord(c->sl[2].computed, ps));                  // "strands and candidates are on the device"
+	}
 	// ---- one pass over the read lengths on the host: bytes of the packed stream, the longest read (bounds every device buffer, so that
 	//      nothing has to come back from the device before the end), and a sample for the window layout (as the run-list path does) ----
+	// (sum and bitwise OR vectorise; the OR of all lengths is an upper bound of the longest, at most twice it: it only sizes buffers)
 	uint64_t total = 0; uint32_t maxlen = 0;
-	for (uint32_t r = 0; r < nr; ++r) { total += R->len[r]; maxlen = std::max<uint32_t>(maxlen, R->len[r]); }
+	for (uint32_t r0 = 0; r0 < nr; r0 += 32768) {
+		const uint32_t r1 = std::min(nr, r0 + 32768u); uint32_t sum = 0; uint16_t orv = 0;
+		for (uint32_t r = r0; r < r1; ++r) { sum += R->len[r]; orv |= R->len[r]; }
+		total += sum; maxlen |= orv;
+	}
 	const uint64_t rbytes = R->flags == BG_R_PACKED2 ? (total + 3) / 4 : (total + 1) / 2, ncodes_max = (uint64_t)nq * (((uint64_t)maxlen + 15) & ~15ull);
 	SeedLayout SL = {0, 0, 0, 0, 0, 0, 0}; uint32_t npmax = 1;
 	{
@@ -2747,7 +2768,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, npmax);
 			SL.np_max = npmax;                                       // reads with more stretches than the sample showed go to k_filter
 		}
-		c->mstage = stage_len(maxlen);
+		{ uint32_t smax = 1; for (uint32_t r = 0; r < nr; r += step) smax = std::max<uint32_t>(smax, R->len[r]); c->mstage = stage_len(smax); }   // (a longer read still works: it reads global memory)
 	}
 	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_runs.need(nruns + 1) || c->d_cand.need(nruns + 1) ||
 	    c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) || c->d_qoff.need((size_t)nq + 1) ||
@@ -2766,12 +2787,12 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		if (c->d_surv.need(c->surv_cap) || c->d_xs.need((size_t)c->surv_cap * 3) || c->d_cls.need(64) || c->d_res.need(c->surv_cap) || c->d_hits.need(c->surv_cap) || c->d_keys.need(c->surv_cap)) return BG_ENOMEM;
 			// ---- host -> device on the copy stream: the reads and their lengths/budgets first, then the strands and candidates slice by slice;
 		//      the kernels of slice i (strand records, codes, runs, seed filter, banded sweep) run while slice i+1 travels ----
-		const double hstart = (double)clock() / CLOCKS_PER_SEC;
 		static cudaEvent_t te0 = nullptr;
 		const bool dbg = getenv("BURST_B200_TIMING") != nullptr;
 		static cudaEvent_t te[4] = {nullptr, nullptr, nullptr, nullptr};
 		if (dbg && !te0) { cudaEventCreate(&te0); for (int i = 1; i < 4; ++i) cudaEventCreate(&te[i]); }
 		te[0] = te0;
+		const auto wall1 = std::chrono::steady_clock::now();
 		if (dbg) cudaEventRecord(te0, cs);
 		if (best_inout) CU(cudaMemcpyAsync(c->d_best16.p, best_inout, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
 		k_init_best<<<(nr + 255) / 256, 256, 0, cs>>>(c->d_best.p, best_inout ? c->d_best16.p : nullptr, nr);
@@ -2779,11 +2800,13 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		CU(cudaMemsetAsync(c->d_cells.p, 0, 8, cs));
 		CU(cudaMemsetAsync(c->d_first.p, 0, 128 * 4, cs));
 		CU(cudaEventRecord(c->ev[0], cs));
-		CU(cudaStreamWaitEvent(ps, c->ev[0], 0));                 // (the previous call is done with the buffers)
-		CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
-		CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
-		CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, ps));
-		CU(cudaEventRecord(c->sl[1].copied, ps));
+		if (!early) {
+			CU(cudaStreamWaitEvent(ps, c->ev[0], 0));               // (the previous attempt is done with the buffers)
+			CU(cudaMemcpyAsync(c->d_rlen.p, R->len, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
+			CU(cudaMemcpyAsync(c->d_rbud.p, R->budget, (size_t)nr * 2, cudaMemcpyHostToDevice, ps));
+			CU(cudaMemcpyAsync(c->d_candoff.p, cand_off, ((size_t)nbunch + 1) * 4, cudaMemcpyHostToDevice, ps));
+			CU(cudaEventRecord(c->sl[1].copied, ps));
+		}
 		CU(cudaMemcpyAsync(c->d_packed.p, R->reads, rbytes, cudaMemcpyHostToDevice, ps));
 		CU(cudaEventRecord(c->sl[0].copied, ps));
 		CU(cudaStreamWaitEvent(cs, c->sl[1].copied, 0));
@@ -2794,8 +2817,6 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		// slices of whole bunches, growing (the first one short so that the kernels start early)
 		// (measured, profiles/: one slice is fastest on the bench workload -- the per-slice launches and kernel tails cost more than the
 		//  ~0.8 ms of copies they hide; BURST_B200_COMPACT_SLICES cuts the batch for hosts with slower links)
-		static const int want_slices = getenv("BURST_B200_COMPACT_SLICES") ? std::max(1, std::min(32, atoi(getenv("BURST_B200_COMPACT_SLICES")))) : 1;
-		const int nsl = (int)std::min<uint64_t>((uint64_t)want_slices, std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
 		std::vector<uint32_t> cut(nsl + 1, 0);
 		{ double tot = 0, w = 1, acc = 0; const double ratio = 1.4;
 		  for (int i = 0; i < nsl; ++i, w *= ratio) tot += w;
@@ -2815,10 +2836,12 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			if (S.sl64.need((size_t)n + 1) || S.qoff.need((size_t)n + 1) || S.qi.need(n) || S.codes.need(scodes + 32) || S.qnib.need(scodes / 8 + 3ull * n + 8) || S.runs.need((size_t)(rb - ra) + 1)) {
 				cudaStreamSynchronize(ps); cudaStreamSynchronize(cs); return BG_ENOMEM;
 			}
-			CU(cudaMemcpyAsync(c->d_strand.p + qa, R->strand + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
-			if (rb > ra) CU(cudaMemcpyAsync(c->d_cand.p + ra, cand + ra, (size_t)(rb - ra) * 4, cudaMemcpyHostToDevice, ps));
-			CU(cudaEventRecord(S.computed, ps));                     // (used here as "slice i is on the device")
-			CU(cudaStreamWaitEvent(cs, S.computed, 0));
+			if (!early) {
+				CU(cudaMemcpyAsync(c->d_strand.p + qa, R->strand + qa, (size_t)n * 4, cudaMemcpyHostToDevice, ps));
+				if (rb > ra) CU(cudaMemcpyAsync(c->d_cand.p + ra, cand + ra, (size_t)(rb - ra) * 4, cudaMemcpyHostToDevice, ps));
+				CU(cudaEventRecord(S.computed, ps));                   // (used here as "slice i is on the device")
+				CU(cudaStreamWaitEvent(cs, S.computed, 0));
+			} else CU(cudaStreamWaitEvent(cs, c->sl[2].computed, 0));
 			k_compact_slen<<<(n + 256) / 256, 256, 0, cs>>>(c->d_rlen.p, nr, c->d_strand.p + qa, n, S.sl64.p, c->d_counters.p);
 			CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, S.sl64.p, (unsigned long long *)S.qoff.p, (int)n + 1, cs));
 			k_compact_qinfo<<<(n + 255) / 256, 256, 0, cs>>>((const unsigned long long *)S.qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p + qa, n, nr, S.qi.p, c->d_counters.p + 16, c->d_counters.p);
@@ -2864,13 +2887,16 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 				cudaEventElapsedTime(&a, te[0], c->ev[0]); cudaEventElapsedTime(&b, c->ev[0], c->ev[1]); cudaEventElapsedTime(&d, c->ev[1], c->ev[2]); cudaEventElapsedTime(&e, c->ev[2], te[1]);
 				cudaEventElapsedTime(&f, te[1], te[2]); cudaEventElapsedTime(&g, te[2], te[3]);
 				(void)d;
-				fprintf(stderr, "[burst_b200] compact call: until the first filter launch %.3f ms, all slices (prep + filter + extend, copies behind them) %.3f, select + counters %.3f, sort %.3f, D2H %.3f (host time to enqueue everything %.3f ms)\n", a, b, e, f, g, ((double)clock() / CLOCKS_PER_SEC - hstart) * 1e3);
+				const auto wall2 = std::chrono::steady_clock::now();
+				fprintf(stderr, "[burst_b200] compact call: until the first filter launch %.3f ms, all slices (prep + filter + extend, copies behind them) %.3f, select + counters %.3f, sort %.3f, D2H %.3f (host: %.3f ms before the first enqueue, %.3f ms in all)\n", a, b, e, f, g,
+					std::chrono::duration<double, std::milli>(wall1 - wall0).count(), std::chrono::duration<double, std::milli>(wall2 - wall0).count());
 			}
 			c->kind = WORK_NONE; c->ran = false;                    // the per-slice buffers are not a resident batch: nothing to re-run or to take statistics of
 			return BG_OK;
 		}
 		if (grow_s) c->surv_cap = c->h_counters[C_SURV] + c->h_counters[C_SURV] / 4;
 		if (grow_g) c->scratch_w = c->h_counters[C_SCRATCH] + 64;
+		early = false;
 	}
 	return fail(BG_EOVERFLOW, "survivor list kept overflowing (%u entries)", c->h_counters[C_SURV]);
 }

@@ -148,6 +148,11 @@ def test_compact_strand_batches_match_the_oracle(eng, oracle, mode):
         assert n == len(ohits) and np.array_equal(buf[:n], ohits), (mode, packed2, n, len(ohits))
         assert np.array_equal(b2, obest)
         assert n > 150
+        # a survivor list that is too small: the call notices, enlarges it and redoes the batch (second attempt copies everything again)
+        eng.set_surv_cap(32)
+        buf[:] = 0; b2[:] = 0xFFFF
+        n = eng.align_bunches_into(stream, B["rlen"], B["rbudget"], B["strand"], 16, B["cand_off"], B["cand"], buf, b2, mode, packed2=packed2)
+        assert n == len(ohits) and np.array_equal(buf[:n], ohits) and np.array_equal(b2, obest), "after a survivor-list overflow"
 
 
 @pytest.mark.parametrize("mode", [0, 1])
