@@ -278,7 +278,7 @@ __global__ void k_qprep(const uint8_t *__restrict__ codes, QInfo *__restrict__ q
 // ---------------------------------------------------------------------------------------------
 // Diagonal clusters: a tiny sorted set of disjoint intervals (rare path, local memory is fine).
 // ---------------------------------------------------------------------------------------------
-#define CLUS_MAX 4
+#define CLUS_MAX 12                    // (the count travels in 4 bits of Surv::w_lane; 4 was too few on 14 kb lanes of sheared genomes: distant clusters fused into bands thousands of cells wide)
 struct Clus { int lo[CLUS_MAX + 1], hi[CLUS_MAX + 1]; int n; };
 
 __device__ __noinline__ void clus_add(Clus &C, int lo, int hi) {
@@ -1154,6 +1154,7 @@ struct ExtendArgs {
 	const uint32_t *cls; const uint4 *xs;                // survivors of this launch binned by band class, as expanded records (k_bin_*)
 	uint32_t np_stage[NCLASS], qp_stage;                 // staging slot per thread and class: reference pieces, query word quads (uint4 each; 0 = read global memory)
 	Res *res; uint32_t *best; const uint32_t *Sterm;   // Sterm[q*16+r] = S << 22
+	uint32_t gen_mode;                                    // experiments on the generic band path (BURST_B200_GEN_MODE)
 	uint32_t smem_w;                                      // generic bands of up to smem_w cells live in shared memory (cell d of thread t at word d * 128 + t)
 	uint32_t *scratch; uint32_t scratch_w;           // generic bands (wider than 64): scratch_w cells per thread of the generic launch, cell d of thread t at scratch[d * threads + t]
 	unsigned long long *band_cells;
@@ -1455,16 +1456,27 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			get_run(A.W, (sv.task >> 4) - A.W.run_base, c_, q0_, n_);
 			const uint8_t *qs = A.codes + A.qi[q0_ + (sv.task & 15)].off;
 			for (int d = 0; d < Wd; ++d) { const int x = lo + d; g[d * GT] = (x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
+			const int gnwords = (int)((L + 7) >> 3); uint32_t cw = 0; int cwi = INT32_MIN;
 			for (; y <= m; ++y) {
 				const int x0 = (int)y + lo;
 				const uint32_t *Srow = sS + (qs[y - 1] & 15) * 16;
 				uint32_t rowmin = KEY_NONE, left = inf;
 				uint32_t diag = g[0], upn = Wd > 1 ? g[GT] : inf;
+				uint32_t cnext = (A.gen_mode & 1u) ? fetch_code(lanew, (uint32_t)(x0 - 1), L) : 0u;
 				for (int d = 0; d < Wd; ++d) {
 					const int x = x0 + d;
 					const uint32_t up = upn;
 					upn = d + 2 < Wd ? g[(d + 2) * GT] : inf;               // (read before this cell's store: cell d + 2 still holds the previous row)
-					const uint32_t st = Srow[fetch_code(lanew, (uint32_t)(x - 1), L)];
+					// reference code of column x: one 32-bit word of the lane serves 8 cells (the band slides one column per row,
+					// so a load per cell would fetch every word W times over from L2)
+					uint32_t code;
+					if (A.gen_mode & 1u) { code = cnext; cnext = fetch_code(lanew, (uint32_t)x, L); }   // a load per cell, one cell ahead (default)
+					else {
+						const int col = x - 1, cwi_ = col >> 3;
+						if (cwi_ != cwi) { cwi = cwi_; cw = lane_word_or0(lanew, cwi_, gnwords); }
+						code = (col >= 0 && col < (int)L) ? (cw >> ((col & 7) * 4)) & 15u : 0u;
+					}
+					const uint32_t st = Srow[code];
 					uint32_t v = cell(diag, up, left, st, inf);
 					if (x < 0 || x > (int)L) v = inf;
 					else if (x == 0) v = y <= k ? key_col0(y) : inf;
@@ -1911,7 +1923,7 @@ struct bg_ctx {
 	int acx_n = 0, acx_big = 0; uint32_t acx_nbad = 0, acx_clumps = 0, cg_blocks = 0; uint32_t runs_cap = 0;
 	DBuf<uint16_t> d_rlen, d_rbud; DBuf<uint32_t> d_strand, d_candoff, d_cand; DBuf<unsigned long long> d_rl64, d_sl64, d_roff;   // compact strand batches
 	DBuf<uint32_t> d_cls; DBuf<uint4> d_xs;                       // band-class bins of the survivors, expanded records (k_bin_*)
-	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch; uint32_t scratch_w = 320;   // cells per thread of the generic band launch
+	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch; uint32_t scratch_w = 1024; bool wide_possible = false;   // cells per thread of the generic band launch
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
 	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;   // cells: [0] band, [1..4] work stats
 	uint32_t *h_pinned = nullptr;                                 // 16 x u32 pinned scratch for small readbacks
@@ -2140,9 +2152,11 @@ static int copy_codes(const bg_queries *Q, uint64_t b0, uint64_t b1, DBuf<uint8_
 
 // queries -> device, QInfo + tables
 // query length the k_extend staging slots are sized for, from the longest of a sample of the batch (a longer query still works: it reads global memory)
+static bool long_queries(uint64_t sampled_max) { return sampled_max > 400; }   // budgets above ~8 at -i 0.98: generic bands become likely
 static uint32_t stage_len(uint64_t sampled_max) {
 	static const int pad = getenv("BURST_B200_STAGE_PAD") ? atoi(getenv("BURST_B200_STAGE_PAD")) : 0;
-	return (uint32_t)std::min<uint64_t>(2048, ((sampled_max + 7) & ~7ull) + (uint64_t)pad);
+	static const uint64_t cap = getenv("BURST_B200_STAGE_CAP") ? (uint64_t)atoi(getenv("BURST_B200_STAGE_CAP")) : 320;
+	return (uint32_t)std::min<uint64_t>(cap, ((sampled_max + 7) & ~7ull) + (uint64_t)pad);   // (320: the slots of 128 threads still fit; a batch that also holds longer queries keeps staging its short ones)
 }
 
 static int upload_queries(bg_ctx *c, const bg_queries *Q) {
@@ -2170,7 +2184,7 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 			(unsigned long long)(Q->offset[q + 1] - Q->offset[q]), Q->budget[q], Q->slot[q], Q->nslots);
 	}
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
-	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nq / 8192); for (uint32_t q = 0; q < nq; q += stp) mx = std::max<uint64_t>(mx, Q->offset[q + 1] - Q->offset[q]); c->mstage = stage_len(mx); }
+	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nq / 8192); for (uint32_t q = 0; q < nq; q += stp) mx = std::max<uint64_t>(mx, Q->offset[q + 1] - Q->offset[q]); c->mstage = stage_len(mx); c->wide_possible = long_queries(mx); }
 	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = Q->nslots;
@@ -2377,12 +2391,21 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 		for (int k = 0; k < NCLASS; ++k) if (occ[k] > 0) grid[k] = std::min<unsigned>(grid[k], (unsigned)c->sms * (unsigned)(bps_cap > 0 ? std::min(bps_cap, occ[k]) : occ[k]));
 		(void)cudaGetLastError();
 	}
+	if (c->wide_possible) {   // long queries: the filters have counted the widest band by now -- size the scratch for it instead of finding out after a wasted sweep
+		uint32_t widest = 0;
+		CU(cudaMemcpyAsync(&widest, c->d_counters.p + C_SCRATCH, 4, cudaMemcpyDeviceToHost, st));
+		CU(cudaStreamSynchronize(st));
+		if (widest > c->scratch_w) c->scratch_w = widest + 64;
+	}
 	{	// the generic class keeps its bands in global scratch: scratch_w cells per thread, at most 4 GB in all
 		const unsigned most = (unsigned)std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)128 * c->scratch_w));
 		grid[8] = std::min(std::min(grid[8], most), (unsigned)c->sms);
 		if (c->d_scratch.need((size_t)grid[8] * 128 * c->scratch_w)) return BG_ENOMEM;
 		E.scratch = c->d_scratch.p;
-		E.smem_w = std::min<uint32_t>(c->scratch_w, 416);              // 416 cells x 128 threads x 4 B = 208 KB: one block per SM
+		static const uint32_t smem_w_cap = getenv("BURST_B200_SMEM_W") ? (uint32_t)atoi(getenv("BURST_B200_SMEM_W")) : 416u;
+		static const uint32_t gen_mode = getenv("BURST_B200_GEN_MODE") ? (uint32_t)atoi(getenv("BURST_B200_GEN_MODE")) : 1u;   // 1: reference code fetched per cell, one cell ahead (5.6 s against 8.1 s for a cached word on the manuscript data set: lanes reload at different cells and diverge)
+		E.gen_mode = gen_mode;
+		E.smem_w = std::min<uint32_t>(c->scratch_w, std::min<uint32_t>(smem_w_cap, 416));              // 416 cells x 128 threads x 4 B = 208 KB: one block per SM
 		smem[8] = (size_t)E.smem_w * 128 * 4;
 	}
 	#define EXT_LAUNCH(WM, K) do { if (smem[K] > 32 * 1024) CU(cudaFuncSetAttribute(k_extend<WM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem[K]));   /* (the kernel also has 1 KB of static shared memory) */ \
@@ -2393,7 +2416,9 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 		uint32_t h[64]; cudaError_t e1 = cudaStreamSynchronize(st); cudaMemcpy(h, c->d_cls.p, sizeof(h), cudaMemcpyDeviceToHost);
 		fprintf(stderr, "[burst_b200] extend: mstage %u qp %u sync=%s last=%s |", ms, E.qp_stage, cudaGetErrorString(e1), cudaGetErrorString(cudaPeekAtLastError()));
 		for (int k = 0; k < NCLASS; ++k) fprintf(stderr, " c%d[n=%u np=%u smem=%zu]", k, h[k], E.np_stage[k], smem[k]);
-		fprintf(stderr, "\n");
+		unsigned long long cells = 0; uint32_t cn[4] = {0, 0, 0, 0};
+		cudaMemcpy(&cells, c->d_cells.p, 8, cudaMemcpyDeviceToHost); cudaMemcpy(cn, c->d_counters.p, 16, cudaMemcpyDeviceToHost);
+		fprintf(stderr, " | band cells so far %llu, widest generic band %u, survivors so far %u\n", cells, cn[C_SCRATCH], cn[C_SURV]);
 	}
 	CU(cudaGetLastError());
 	return BG_OK;
@@ -2585,7 +2610,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			if (np <= SEED_NP_MAX) ++hist[std::min<uint64_t>(len / np, 31)];
 			mxlen = std::max(mxlen, len);
 		}
-		c->mstage = stage_len(mxlen);
+		c->mstage = stage_len(mxlen); c->wide_possible = long_queries(mxlen);
 		SL = choose_layout(c, hist, ns);
 		if (SL.stride) {
 			uint64_t sum = 0, cnt = 0; uint32_t mx = 1;
@@ -2768,7 +2793,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, npmax);
 			SL.np_max = npmax;                                       // reads with more stretches than the sample showed go to k_filter
 		}
-		{ uint32_t smax = 1; for (uint32_t r = 0; r < nr; r += step) smax = std::max<uint32_t>(smax, R->len[r]); c->mstage = stage_len(smax); }   // (a longer read still works: it reads global memory)
+		{ uint32_t smax = 1; for (uint32_t r = 0; r < nr; r += step) smax = std::max<uint32_t>(smax, R->len[r]); c->mstage = stage_len(smax); c->wide_possible = long_queries(smax); }   // (a longer read still works: it reads global memory)
 	}
 	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_runs.need(nruns + 1) || c->d_cand.need(nruns + 1) ||
 	    c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) || c->d_qoff.need((size_t)nq + 1) ||
@@ -2984,7 +3009,7 @@ extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbu
 	CU(cudaStreamSynchronize(st));
 	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_search_bunches_into: malformed batch (strands must name reads < nreads, read lengths >= 1, budgets <= 254)");
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
-	c->mstage = stage_len(maxlen);
+	c->mstage = stage_len(maxlen); c->wide_possible = long_queries(maxlen);
 	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = nr;
