@@ -22,6 +22,8 @@
 #include <string.h>
 #include <inttypes.h>
 #include <time.h>
+#include <pthread.h>
+#include <unistd.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -315,6 +317,16 @@ static void load_fasta_refs(const char *fn, Refs *R) {
 static void rd(void *dst, size_t sz, size_t n, FILE *f) {
 	if (fread(dst, sz, n, f) != n) { fputs("ERROR: truncated database file\n", stderr); exit(1); }
 }
+/* a large section of a file read by all host threads at once (page faults and copies of a 4 GB table are the cost, not the disk) */
+static void rd_at(FILE *f, void *dst, uint64_t bytes, uint64_t off) {
+	const int fd = fileno(f); const uint64_t CH = 32ull << 20; const int64_t nch = (int64_t)((bytes + CH - 1) / CH); int bad = 0;
+	#pragma omp parallel for schedule(dynamic, 1) num_threads(THREADS < 1 ? 1 : THREADS)
+	for (int64_t c = 0; c < nch; ++c) {
+		uint64_t a = (uint64_t)c * CH, n = MIN(CH, bytes - a);
+		while (n) { ssize_t g = pread(fd, (char *)dst + a, n, (off_t)(off + a)); if (g <= 0) { bad = 1; break; } a += (uint64_t)g; n -= (uint64_t)g; }
+	}
+	if (bad) { fputs("ERROR: truncated database file\n", stderr); exit(1); }
+}
 /* .edx reader (burst.c:2842-2975; layout written at 2758-2839) */
 static void load_edx(const char *fn, Refs *R) {
 	FILE *in = fopen(fn, "rb");
@@ -444,7 +456,7 @@ static void load_acx(const char *fn, Acx *A) {
 		uint64_t nk = 1ull << (2 * n);
 		if (fsz < 5 + nk * 4) continue;
 		uint32_t *Lens = xmalloc(nk * 4);
-		fseeko(in, 5, SEEK_SET); rd(Lens, 4, nk, in);
+		rd_at(in, Lens, nk * 4, 5);
 		uint64_t bytes = 0;
 		#pragma omp parallel for reduction(+:bytes) schedule(static)
 		for (uint64_t i = 0; i < nk; ++i) bytes += A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3;
@@ -467,8 +479,8 @@ static void load_acx(const char *fn, Acx *A) {
 					for (uint64_t i = lo; i < hi; ++i) { t += A->big ? (uint64_t)Lens[i] * 3 : (uint64_t)(Lens[i] / 2u) * 5 + (Lens[i] & 1) * 3; A->off[i + 1] = t; }
 				}
 			}
-			A->post = xmalloc(bytes + 16); rd(A->post, 1, bytes, in); memset(A->post + bytes, 0, 16);
-			A->bad = xmalloc((uint64_t)szBL * 4 + 4); rd(A->bad, 4, szBL, in); A->nbad = szBL;
+			A->post = xmalloc(bytes + 16); rd_at(in, A->post, bytes, 5 + nk * 4); memset(A->post + bytes, 0, 16);
+			A->bad = xmalloc((uint64_t)szBL * 4 + 4); fseeko(in, (off_t)(5 + nk * 4 + bytes), SEEK_SET); rd(A->bad, 4, szBL, in); A->nbad = szBL;
 			A->post_bytes = bytes;
 			if (DEVICE_CAND) { A->lens = Lens; Lens = NULL; }                  /* bg_load_acx takes the on-disk form */
 		}
@@ -1459,6 +1471,17 @@ static int is_edx(const char *fn) {                                  /* burst.c:
 	return (uint8_t)c >> 7;
 }
 
+typedef struct { bg_ctx **ctxs; int n, dev0; const uint8_t *S; int rc; char msg[256]; } EngineStart;
+static void *engine_start(void *p) {                                    /* --gpus N: devices dev0 .. dev0+N-1, one context each */
+	EngineStart *E = p;
+	for (int g = 0; g < E->n; ++g) {
+		E->ctxs[g] = NULL;
+		int rc = bg_init(E->dev0 + g, &E->ctxs[g]);
+		if (!rc) rc = bg_set_scoring(E->ctxs[g], E->S);
+		if (rc) { E->rc = rc; snprintf(E->msg, sizeof(E->msg), "%s", bg_last_error()); return NULL; }
+	}
+	return NULL;
+}
 int main(int argc, char *argv[]) {
 	Queries Q; memset(&Q, 0, sizeof(Q));
 	Refs R; char *ref_FN = 0, *query_FN = 0, *output_FN = 0, *xcel_FN = 0, *tax_FN = 0; int taxasuppress = 0, makedb = 0;
@@ -1549,16 +1572,12 @@ int main(int argc, char *argv[]) {
 #define PHASE(name) do { double t_ = now(); printf(" --> [time] %-28s %8.3f s\n", name, t_ - tph); tph = t_; } while (0)
 	init_char2num();
 
-	/* the engine first: without a CUDA device there is nothing this program can do */
+	/* the engine starts (CUDA context per device: 0.5 - 3 s on a cold box) while the files are read; without a device nothing below can run */
 	bg_ctx *ctxs[64]; int rc;
 	uint8_t S[256]; bg_default_scoring(Z, S);
-	for (int g = 0; g < NGPU; ++g) {                                     /* --gpus N: devices GPU_DEVICE .. GPU_DEVICE+N-1, one context each */
-		ctxs[g] = NULL;
-		if ((rc = bg_init(GPU_DEVICE + g, &ctxs[g]))) { fprintf(stderr, "ERROR: cannot start the GPU engine: %s\n", bg_last_error()); exit(3); }
-		if ((rc = bg_set_scoring(ctxs[g], S))) die_gpu("bg_set_scoring", rc);
-	}
-	bg_ctx *ctx = ctxs[0];
-	PHASE("GPU engine start");
+	EngineStart ES; memset(&ES, 0, sizeof(ES)); ES.ctxs = ctxs; ES.n = NGPU; ES.dev0 = GPU_DEVICE; ES.S = S;
+	pthread_t es_thread;
+	if (pthread_create(&es_thread, NULL, engine_start, &ES)) { fputs("ERROR: cannot start a thread\n", stderr); exit(4); }
 	Acx A; memset(&A, 0, sizeof(A));
 	if (DO_ACCEL) { load_acx(xcel_FN, &A); PHASE("accelerator load"); }
 	int usedb = is_edx(ref_FN);
@@ -1567,6 +1586,10 @@ int main(int argc, char *argv[]) {
 	if (tax_FN) load_taxonomy(tax_FN);
 	load_queries(query_FN, &Q);
 	PHASE("query parse/sort");
+	pthread_join(es_thread, NULL);
+	if (ES.rc) { fprintf(stderr, "ERROR: cannot start the GPU engine: %s\n", ES.msg); exit(3); }
+	bg_ctx *ctx = ctxs[0];
+	PHASE("GPU engine start (rest)");
 	if (!usedb) load_fasta_refs(ref_FN, &R);
 	else if (R.shear && (uint32_t)(Q.maxLenQ / THRES) > R.shear) {
 		fputs("ERROR: DB incompatible with selected queries/identity.\n", stderr);

@@ -115,18 +115,26 @@ def main():
     ap.add_argument("--dir", default="/tmp/wb")
     ap.add_argument("--skip-reference", action="store_true")
     ap.add_argument("--ours", default=None, help="binary under test (default burst_b200/host/burst-b200)")
+    ap.add_argument("--reuse", action="store_true", help="keep the files of an earlier run in --dir (same shape and sizes)")
     ap.add_argument("--ours-extra", default="", help="extra flags for the binary under test, e.g. --device-candidates")
     ap.add_argument("--acx-n", type=int, default=0, help="override the accelerator word length (12 or 15)")
     args = ap.parse_args()
     d = os.path.join(args.dir, args.shape); os.makedirs(d, exist_ok=True)
     t0 = time.time()
-    P = shotgun(args, d) if args.shape == "shotgun" else amplicon(args, d)
+    have = args.reuse and os.path.exists(os.path.join(d, "db.edx")) and os.path.exists(os.path.join(d, "reads.fa"))
+    if have:
+        P = (dict(qlen=105, ident="0.98", mode="BEST", extra=["-fr"], acx_n=15, ref_bin="burst15") if args.shape == "shotgun"
+             else dict(qlen=320, ident="0.97", mode="CAPITALIST", extra=["-b", "tax.txt"], acx_n=12, ref_bin="burst12"))
+    else:
+        P = shotgun(args, d) if args.shape == "shotgun" else amplicon(args, d)
     gen_s = time.time() - t0
     ours = args.ours or os.path.join(ROOT, "burst_b200", "host", "burst-b200")
     if args.acx_n:
         P["acx_n"] = args.acx_n; P["ref_bin"] = "burst%d" % args.acx_n
     ref = os.path.join(ROOT, "oracle", "_ref", P["ref_bin"])
-    mk, _ = run([ours, "-r", "refs.fa", "-d", "DNA", str(P["qlen"]), "-o", "db.edx", "-a", "db.acx", "-s", "1", "-i", P["ident"], "--acx-n", str(P["acx_n"])], d)
+    mk = 0.0
+    if not have:
+        mk, _ = run([ours, "-r", "refs.fa", "-d", "DNA", str(P["qlen"]), "-o", "db.edx", "-a", "db.acx", "-s", "1", "-i", P["ident"], "--acx-n", str(P["acx_n"]), "-t", str(args.threads)], d)
     common = ["-r", "db.edx", "-a", "db.acx", "-q", "reads.fa", "-m", P["mode"], "-i", P["ident"], "--noprogress"] + P["extra"]
     out = {"shape": args.shape, "mbp": args.mbp, "reads": args.reads, "threads": args.threads, "gpus": args.gpus, "generate_s": round(gen_s, 1), "makedb_s": round(mk, 1),
            "edx_bytes": os.path.getsize(os.path.join(d, "db.edx")), "acx_bytes": os.path.getsize(os.path.join(d, "db.acx")), "flags": " ".join(common)}
