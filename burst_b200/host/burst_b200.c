@@ -95,6 +95,31 @@ static int cmp_unibin(const void *a, const void *b) {
 	return A->six < B->six ? -1 : A->six > B->six;
 }
 
+/* qsort over all host threads: sorted pieces, then rounds of pairwise merges (both comparators here are total orders, so the
+ * result does not depend on how the work was cut) */
+static void psort(void *base, uint64_t n, size_t sz, int (*cmp)(const void *, const void *)) {
+	int T = THREADS < 1 ? 1 : THREADS;
+	if (T > 64) T = 64;
+	if (T == 1 || n < 65536) { qsort(base, n, sz, cmp); return; }
+	int P = 1; while (P * 2 <= T) P *= 2;                              /* pieces: a power of two */
+	uint64_t cut[65];
+	for (int i = 0; i <= P; ++i) cut[i] = n * (uint64_t)i / (uint64_t)P;
+	#pragma omp parallel for schedule(static, 1) num_threads(P)
+	for (int i = 0; i < P; ++i) qsort((char *)base + cut[i] * sz, cut[i + 1] - cut[i], sz, cmp);
+	char *tmp = xmalloc(n * sz), *src = base, *dst = tmp;
+	for (int w = 1; w < P; w *= 2) {
+		#pragma omp parallel for schedule(static, 1) num_threads(P / (2 * w))
+		for (int i = 0; i < P; i += 2 * w) {
+			uint64_t a = cut[i], am = cut[i + w], b = am, bm = cut[i + 2 * w], o = a;
+			while (a < am && b < bm) { if (cmp(src + b * sz, src + a * sz) < 0) memcpy(dst + o++ * sz, src + b++ * sz, sz); else memcpy(dst + o++ * sz, src + a++ * sz, sz); }
+			if (a < am) memcpy(dst + o * sz, src + a * sz, (am - a) * sz); else if (b < bm) memcpy(dst + o * sz, src + b * sz, (bm - b) * sz);
+		}
+		char *t = src; src = dst; dst = t;
+	}
+	if (src != (char *)base) memcpy(base, src, n * sz);
+	free(tmp);
+}
+
 /* strict two-line FASTA, as parse_tl_faster (burst.c:636-690) */
 static void load_queries(const char *fn, Queries *Q) {
 	FILE *f = fopen(fn, "rb");
@@ -134,12 +159,13 @@ static void load_queries(const char *fn, Queries *Q) {
 	if (maxLenQ > (1 << 16)) fputs("WARNING: Max query length is very long\n", stderr);
 	if (minLenQ < 5) fputs("WARNING: Min query length is less than 5 bases\n", stderr);
 	printf("Parsed %" PRIu64 " queries. Found min %u, max %u.\n", totQ, minLenQ, maxLenQ);
+	#pragma omp parallel for schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
 	for (uint64_t i = 0; i < totQ; ++i) translate(Seq[i], Len[i]);
 	/* sort (burst.c:3014-3031): strcmp on the code strings */
 	uint64_t *ix = xmalloc(totQ * sizeof(*ix));
 	for (uint64_t i = 0; i < totQ; ++i) ix[i] = i;
 	g_sortseq = Seq;
-	qsort(ix, totQ, sizeof(*ix), cmp_query_ix);
+	psort(ix, totQ, sizeof(*ix), cmp_query_ix);
 	/* uniqueness (burst.c:3036-3053) */
 	uint64_t numUniq = 1;
 	for (uint64_t i = 1; i < totQ; ++i) if (strcmp(Seq[ix[i - 1]], Seq[ix[i]])) ++numUniq;
@@ -172,6 +198,7 @@ static void load_queries(const char *fn, Queries *Q) {
 	memset(Q->QBins, 0, sizeof(Q->QBins));
 	if (DO_ACCEL) {                                                   /* burst.c:3113-3177 */
 		uint8_t *stat = xmalloc(newUniq + 1);
+		#pragma omp parallel for schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
 		for (uint64_t i = 0; i < newUniq; ++i) {
 			uint32_t len = SB[UB[i].six].len, ed = SB[UB[i].six].ed, totN = 0;
 			const char *s = UB[i].seq; stat[i] = 1;
@@ -189,10 +216,10 @@ static void load_queries(const char *fn, Queries *Q) {
 		for (uint64_t i = 0; i < newUniq; ++i) T[o[stat[i]]++] = UB[i];
 		memcpy(UB, T, newUniq * sizeof(*T)); free(T); free(stat);
 		printf("Unambig: %" PRIu64 ", ambig: %" PRIu64 ", super-ambig: %" PRIu64 "\n", c[1], c[0], c[2]);
-		qsort(UB, Q->QBins[0], sizeof(*UB), cmp_unibin);
-		qsort(UB + Q->QBins[0], Q->QBins[1] - Q->QBins[0], sizeof(*UB), cmp_unibin);
-		qsort(UB + Q->QBins[1], Q->QBins[2] - Q->QBins[1], sizeof(*UB), cmp_unibin);
-	} else if (Q->rc) qsort(UB, newUniq, sizeof(*UB), cmp_unibin);   /* burst.c:3178-3186 */
+		psort(UB, Q->QBins[0], sizeof(*UB), cmp_unibin);
+		psort(UB + Q->QBins[0], Q->QBins[1] - Q->QBins[0], sizeof(*UB), cmp_unibin);
+		psort(UB + Q->QBins[1], Q->QBins[2] - Q->QBins[1], sizeof(*UB), cmp_unibin);
+	} else if (Q->rc) psort(UB, newUniq, sizeof(*UB), cmp_unibin);   /* burst.c:3178-3186 */
 	free(ix); free(Head); free(Seq); free(Len);
 	Q->QHead = SrtHead; Q->totQ = totQ; Q->numUniqQ = numUniq; Q->newUniqQ = newUniq; Q->Offset = Offset;
 	Q->UniBins = UB; Q->ShrBins = SB; Q->maxLenQ = maxLenQ; Q->minLenQ = minLenQ;
