@@ -1320,8 +1320,9 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 		size_t GT = (size_t)gridDim.x * blockDim.x;
 		if (WMAX == 0 && W <= A.smem_w) { g = (uint32_t *)xstage + threadIdx.x; GT = blockDim.x; }   // the usual case: a tenth of the latency per cell
 		if (WMAX == 0 && W > A.scratch_w) { Res z; z.a = 0; z.b = 0; z.slot = slot; A.res[i] = z; continue; }   // (the host sees the width in the counter, grows the scratch and redoes the batch)
-		bool dead = false;
+		bool dead = false, striped = false;
 		uint32_t y = 1;
+		uint32_t sbk = KEY_NONE >> 11, sbshr = 0, sfp = 0;       // last-row selection of the striped sweep
 
 		if (WMAX) {
 			// The band slides one column per row, so row y needs exactly one new reference code (column y+lo+WB-1)
@@ -1451,6 +1452,65 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 				}
 			}
 			if (!dead) y = m + 1;
+		} else if (W > A.smem_w && m + 1 <= A.scratch_w) {
+			// Bands too wide for shared memory (runs of N in a genome make a prefix match for thousands of columns): swept in STRIPS of 32
+			// matrix columns, left to right.  In matrix coordinates a cell needs (y-1, x-1), (y-1, x) and (y, x-1) -- its own strip or the
+			// strip to the left -- so a strip keeps the previous row of its 32 columns in registers and only the strip's last column goes
+			// through global memory (one value per row, read back by the next strip): register speed instead of two scratch accesses per
+			// cell.  Cells outside the band or the matrix are "absent", exactly as the band sweep treats them; the last row is scanned as the
+			// strips pass it, left to right.
+			striped = true;
+			uint32_t c_, q0_, n_;
+			get_run(A.W, (sv.task >> 4) - A.W.run_base, c_, q0_, n_);
+			const uint8_t *qs = A.codes + A.qi[q0_ + (sv.task & 15)].off;
+			const int gnw = (int)((L + 7) >> 3);
+			for (uint32_t yy = 0; yy <= m; ++yy) g[(size_t)yy * GT] = inf;                 // column "left of the first strip"
+			const int xlast = min((int)m + lo + (int)W - 1, (int)L);
+			for (int X0 = lo & ~31; X0 <= xlast; X0 += 32) {
+				if (X0 + 31 < 0) continue;                                                  // left of the matrix: nothing but absent cells
+				int y0 = X0 - lo - (int)W + 1; if (y0 < 0) y0 = 0;
+				int y1 = X0 + 31 - lo; if (y1 > (int)m) y1 = (int)m;
+				if (y1 < y0) continue;
+				if (A.mode == BG_MODE_MIN) { k = min(k, __ldcg(A.best + slot)); inf = (k + 1) << 22; }
+				uint32_t rw[4];                                                             // reference codes of matrix columns X0 .. X0+31 = lane nibbles X0-1 .. X0+30
+				{ const int wi = (X0 - 1) >> 3; uint32_t w0 = lane_word_or0(lanew, wi, gnw);
+				  #pragma unroll
+				  for (int t = 0; t < 4; ++t) { const uint32_t w1 = lane_word_or0(lanew, wi + 1 + t, gnw); rw[t] = __funnelshift_r(w0, w1, 28); w0 = w1; } }
+				uint32_t prev[32];
+				uint32_t yy = (uint32_t)y0, bl_prev;
+				if (y0 == 0) {                                                              // row 0 of the matrix (burst.c:723-725)
+					#pragma unroll
+					for (int j = 0; j < 32; ++j) { const int x = X0 + j; prev[j] = (x >= lo && x <= lo + (int)W - 1 && x >= 0 && x <= (int)L) ? KEY_ZERO : inf; }
+					bl_prev = g[0]; g[0] = prev[31]; yy = 1;
+				} else {
+					#pragma unroll
+					for (int j = 0; j < 32; ++j) prev[j] = inf;                             // row y0-1 ends left of this strip
+					bl_prev = g[(size_t)(y0 - 1) * GT];
+				}
+				for (; yy <= (uint32_t)y1; ++yy) {
+					const uint32_t *Srow = sS + (qs[yy - 1] & 15) * 16;
+					const uint32_t bl_cur = g[(size_t)yy * GT];                             // (yy, X0-1), left there by the previous strip
+					const int blo = (int)yy + lo, bhi = blo + (int)W - 1;                   // this row's band
+					uint32_t left = bl_cur, diag = bl_prev;
+					#pragma unroll
+					for (int j = 0; j < 32; ++j) {
+						const int x = X0 + j;
+						const uint32_t up = prev[j];
+						uint32_t v = cell(diag, up, left, Srow[(rw[j >> 3] >> (4 * (j & 7))) & 15u], inf);
+						if (x < blo || x > bhi || x < 0 || x > (int)L) v = inf;
+						else if (x == 0) v = yy <= k ? key_col0(yy) : inf;
+						diag = up; prev[j] = v; left = v;
+						if (yy == m && x >= blo && x <= bhi && x >= 1 && x <= (int)L) {     // last-row selection (burst.c:826-842, 863-883)
+							const uint32_t kk = v >> 11;
+							if (kk < sbk) { sbk = kk; sbshr = v & 0x1FF; sfp = (uint32_t)x; }
+							else if (kk == sbk) sfp = (uint32_t)x;
+						}
+					}
+					bl_prev = bl_cur; g[(size_t)yy * GT] = prev[31];
+				}
+				cells += 32ull * (unsigned)(y1 - y0 + 1);
+			}
+			y = m + 1;
 		} else {
 			uint32_t c_, q0_, n_;
 			get_run(A.W, (sv.task >> 4) - A.W.run_base, c_, q0_, n_);
@@ -1486,11 +1546,11 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 				if ((y & 15) == 0 && A.mode == BG_MODE_MIN) { k = min(k, A.best[slot]); inf = (k + 1) << 22; }
 			}
 		}
-		cells += (unsigned long long)(dead ? y : m) * (unsigned)Wd;
-		uint32_t out = 0, fp = 0;
+		if (!striped) cells += (unsigned long long)(dead ? y : m) * (unsigned)Wd;
+		uint32_t out = 0, fp = sfp;
 		if (!dead) {
 			// last-row selection, left to right (burst.c:826-842, 863-883)
-			uint32_t bk = KEY_NONE >> 11, bshr = 0;
+			uint32_t bk = sbk, bshr = sbshr;
 			auto scan = [&](int d, uint32_t v) {
 				const int x = (int)m + lo + d;
 				if (x < 1 || x > (int)L) return;
@@ -1501,7 +1561,7 @@ __global__ void __launch_bounds__(128) k_extend(ExtendArgs A) {
 			if (WMAX) {
 				#pragma unroll
 				for (int d = 0; d < WB; ++d) if (d < (int)W) scan(d, a[d]);      // the cluster's own diagonals only: beyond them the sweep may see part of a neighbouring cluster's band
-			} else for (int d = 0; d < Wd; ++d) scan(d, g[d * GT]);
+			} else if (!striped) for (int d = 0; d < Wd; ++d) scan(d, g[d * GT]);
 			const uint32_t ed = bk >> 11, sh = 2047u - (bk & 2047u);
 			if (bk != (KEY_NONE >> 11) && ed <= k) {
 				out = ed | (sh << 8) | (bshr << 16) | (1u << 31);
@@ -1923,7 +1983,7 @@ struct bg_ctx {
 	int acx_n = 0, acx_big = 0; uint32_t acx_nbad = 0, acx_clumps = 0, cg_blocks = 0; uint32_t runs_cap = 0;
 	DBuf<uint16_t> d_rlen, d_rbud; DBuf<uint32_t> d_strand, d_candoff, d_cand; DBuf<unsigned long long> d_rl64, d_sl64, d_roff;   // compact strand batches
 	DBuf<uint32_t> d_cls; DBuf<uint4> d_xs;                       // band-class bins of the survivors, expanded records (k_bin_*)
-	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch; uint32_t scratch_w = 1024; bool wide_possible = false;   // cells per thread of the generic band launch
+	DBuf<Surv> d_surv; DBuf<Res> d_res; DBuf<bg_hit> d_hits, d_hits_sorted; DBuf<uint32_t> d_scratch; uint32_t scratch_w = 1024, len_hint = 0; bool wide_possible = false;   // cells per thread of the generic band launch
 	DBuf<unsigned long long> d_keys, d_keys2; DBuf<uint32_t> d_order, d_order2; DBuf<uint8_t> d_sort_tmp;
 	DBuf<uint32_t> d_counters; DBuf<unsigned long long> d_cells;   // cells: [0] band, [1..4] work stats
 	uint32_t *h_pinned = nullptr;                                 // 16 x u32 pinned scratch for small readbacks
@@ -2184,7 +2244,7 @@ static int upload_queries(bg_ctx *c, const bg_queries *Q) {
 			(unsigned long long)(Q->offset[q + 1] - Q->offset[q]), Q->budget[q], Q->slot[q], Q->nslots);
 	}
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
-	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nq / 8192); for (uint32_t q = 0; q < nq; q += stp) mx = std::max<uint64_t>(mx, Q->offset[q + 1] - Q->offset[q]); c->mstage = stage_len(mx); c->wide_possible = long_queries(mx); }
+	{ uint64_t mx = 0; const uint32_t stp = std::max<uint32_t>(1, nq / 8192); for (uint32_t q = 0; q < nq; q += stp) mx = std::max<uint64_t>(mx, Q->offset[q + 1] - Q->offset[q]); c->mstage = stage_len(mx); c->wide_possible = long_queries(mx); c->len_hint = (uint32_t)mx; }
 	k_qprep<<<(nq + 127) / 128, 128, 0, c->stream>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = Q->nslots;
@@ -2396,6 +2456,7 @@ static int launch_extend(bg_ctx *c, cudaStream_t st, const BatchDev &B, int mode
 		CU(cudaMemcpyAsync(&widest, c->d_counters.p + C_SCRATCH, 4, cudaMemcpyDeviceToHost, st));
 		CU(cudaStreamSynchronize(st));
 		if (widest > c->scratch_w) c->scratch_w = widest + 64;
+		if (widest > 416 && c->len_hint + 2 > c->scratch_w) c->scratch_w = c->len_hint + 64;   // the striped sweep of a band too wide for shared memory keeps one value per query row
 	}
 	{	// the generic class keeps its bands in global scratch: scratch_w cells per thread, at most 4 GB in all
 		const unsigned most = (unsigned)std::max<size_t>(1, ((size_t)1 << 30) / ((size_t)128 * c->scratch_w));
@@ -2610,7 +2671,7 @@ static int align_pipelined(bg_ctx *c, const bg_queries *Q, const bg_run *runs, u
 			if (np <= SEED_NP_MAX) ++hist[std::min<uint64_t>(len / np, 31)];
 			mxlen = std::max(mxlen, len);
 		}
-		c->mstage = stage_len(mxlen); c->wide_possible = long_queries(mxlen);
+		c->mstage = stage_len(mxlen); c->wide_possible = long_queries(mxlen); c->len_hint = (uint32_t)mxlen;
 		SL = choose_layout(c, hist, ns);
 		if (SL.stride) {
 			uint64_t sum = 0, cnt = 0; uint32_t mx = 1;
@@ -2793,7 +2854,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			seed_sizes(c, SL, cnt ? (uint32_t)((sum + cnt - 1) / cnt) : 1, mx, npmax);
 			SL.np_max = npmax;                                       // reads with more stretches than the sample showed go to k_filter
 		}
-		{ uint32_t smax = 1; for (uint32_t r = 0; r < nr; r += step) smax = std::max<uint32_t>(smax, R->len[r]); c->mstage = stage_len(smax); c->wide_possible = long_queries(smax); }   // (a longer read still works: it reads global memory)
+		{ uint32_t smax = 1; for (uint32_t r = 0; r < nr; r += step) smax = std::max<uint32_t>(smax, R->len[r]); c->mstage = stage_len(smax); c->wide_possible = long_queries(smax); c->len_hint = smax; }   // (a longer read still works: it reads global memory)
 	}
 	if (c->d_rlen.need(nr) || c->d_rbud.need(nr) || c->d_strand.need(nq) || c->d_candoff.need((size_t)nbunch + 1) || c->d_runs.need(nruns + 1) || c->d_cand.need(nruns + 1) ||
 	    c->d_rl64.need((size_t)nr + 1) || c->d_sl64.need((size_t)nq + 1) || c->d_roff.need((size_t)nr + 1) || c->d_qoff.need((size_t)nq + 1) ||
@@ -3009,7 +3070,7 @@ extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbu
 	CU(cudaStreamSynchronize(st));
 	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_search_bunches_into: malformed batch (strands must name reads < nreads, read lengths >= 1, budgets <= 254)");
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
-	c->mstage = stage_len(maxlen); c->wide_possible = long_queries(maxlen);
+	c->mstage = stage_len(maxlen); c->wide_possible = long_queries(maxlen); c->len_hint = maxlen;
 	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = nr;
