@@ -358,6 +358,79 @@ def main():
     e2e_s, d2h = compact_leg()
     clocks = sampler.stop()
 
+    # ---------------- reference sharding (N > 1): the path's one collective, measured ----------------
+    # SURVEY 8(e) / burst.c:4490-4519: the database is cut into N contiguous clump ranges, every GPU sees EVERY query; per step each GPU
+    # runs filter + extend on its range, then ncclAllReduce(MIN) over the per-slot minima in place on the device, then the selection
+    # against the combined minima.  Rank 0's read set (broadcast over NCCL) against the same database the replicated legs used, so the
+    # union of the ranks' hits must equal rank 0's single-GPU result above -- checked here, at full size.
+    ref_sharded = None
+    if world > 1 and args.config in ("c2", "target"):
+        from burst_b200 import sharded
+        dev = torch.device("cuda", local)
+
+        def bcast(a):
+            a = np.ascontiguousarray(a)
+            n = torch.tensor([a.nbytes if rank == 0 else 0], dtype=torch.int64, device=dev)
+            dist.broadcast(n, 0)
+            t = torch.from_numpy(a.view(np.uint8).reshape(-1)).to(dev) if rank == 0 else torch.empty(int(n.item()), dtype=torch.uint8, device=dev)
+            dist.broadcast(t, 0)
+            return t.cpu().numpy().view(a.dtype)
+        # the replicated database must be the same on every rank (the generator seeds it independently of the rank): compare a checksum
+        sample = w["packed"][:: max(1, len(w["packed"]) >> 20)].astype(np.int64)
+        ck = torch.tensor([int(sample.sum()), -int(sample.sum()), len(w["clump_len"]), -len(w["clump_len"])], dtype=torch.int64, device=dev)
+        dist.all_reduce(ck, op=dist.ReduceOp.MAX)
+        same_db = int(ck[0]) == -int(ck[1]) and int(ck[2]) == -int(ck[3])
+        if not same_db:
+            ref_sharded = {"skipped": "ranks hold different databases"}
+        else:
+            g_codes = bcast(w["qcodes"]); g_off = bcast(w["qoff"]); g_bud = bcast(w["budget"]); g_slot = bcast(w["slot"]); g_runs = bcast(runs)
+            eng2 = Engine(local, stream=stream.cuda_stream)
+            with torch.cuda.stream(stream):
+                drv = sharded.ReferenceSharded(eng2)
+                lo, hi = drv.load_db(w["packed"], w["clump_len"])
+                eng2.upload_runs(g_codes, g_off, g_bud, g_runs, slot=g_slot, nslots=w["nslots"])
+                for _ in range(args.warmup):
+                    drv.step_resident(MODE_MIN, w["nslots"])
+                barrier()
+                ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+                s0 = torch.cuda.Event(enable_timing=True); s1 = torch.cuda.Event(enable_timing=True)
+                s0.record(stream)
+                for k in range(args.steps):
+                    gbest_t = drv.step_resident(MODE_MIN, w["nslots"], events=ev[k])
+                s1.record(stream)
+                torch.cuda.synchronize()
+                barrier()
+                rs_ms = s0.elapsed_time(s1) / args.steps
+                ar_ms = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+                # the collective alone (ranks in step): the same tensor, back to back
+                a0 = torch.cuda.Event(enable_timing=True); a1 = torch.cuda.Event(enable_timing=True)
+                tmp = gbest_t.clone()
+                dist.all_reduce(tmp, op=dist.ReduceOp.MIN); barrier()
+                a0.record(stream)
+                for _ in range(10):
+                    dist.all_reduce(tmp, op=dist.ReduceOp.MIN)
+                a1.record(stream)
+                torch.cuda.synchronize()
+                ar_alone = a0.elapsed_time(a1) / 10
+                my_hits, _ = eng2.download()
+                gbest = gbest_t.cpu().numpy().astype(np.uint16)
+                allh = np.concatenate(sharded._all_gather_var(my_hits, None, dev))
+            allh = allh[np.lexsort((allh["lane"], allh["task"]))]
+            tt = torch.tensor([rs_ms, ar_ms, ar_alone], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            rs_ms, ar_ms, ar_alone = (float(x) for x in tt.cpu())
+            ref_sharded = {"value": args.reads / (rs_ms / 1e3), "unit": "reads/s", "ms_per_step": rs_ms,
+                           "allreduce_ms_in_step": ar_ms, "allreduce_ms_alone": ar_alone, "allreduce_bytes": int(w["nslots"]) * 4,
+                           "clumps_this_rank": [int(lo), int(hi)], "db_mb_per_gpu": args.db_mb / world,
+                           "workload": "rank 0's %d reads, every rank sees all of them; the %d MB database cut into %d contiguous clump ranges" % (args.reads, args.db_mb, world),
+                           "protocol": "per step and rank: k_seedw + k_extend on the local clump range -> ncclAllReduce(MIN, u32 x reads) in place on the engine's stream -> k_select against the combined minima (burst.c:4490-4519); one 16-byte counter read-back (survivor-list overflow check) after the extend, no other host synchronisation",
+                           "note": "allreduce_ms_in_step includes waiting for the slowest rank's extend; allreduce_ms_alone is the collective back to back with the ranks in step"}
+            if rank == 0:
+                hs = hits[np.lexsort((hits["lane"], hits["task"]))]
+                ref_sharded["parity"] = {"hits_equal_single_gpu": bool(len(allh) == len(hs) and np.array_equal(allh, hs)), "minima_equal_single_gpu": bool(np.array_equal(gbest, best)),
+                                         "hits": int(len(allh))}
+            eng2.close()
+
     times = torch.tensor([ms_total, e2e_s * 1e3, e2e_bytes_s * 1e3, e2e_pack4_s * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
@@ -413,6 +486,8 @@ def main():
                                     "dpx_peak_thread_inst_per_s": DPX_PEAK, "frac": 2.0 * st["band_cells"] / (st["ms_extend"] / 1e3) / DPX_PEAK,
                                     "note": "2 VIADDMNMX per band cell (select-with-tie-break of the packed pass-2 key); peak = VIADDMNMX.U32 issue rate measured on this pool's B200 by burst_b200/csrc/tools/pipe_microbench (profiles/r1d_pipe_microbench.txt: 571.6 G warp-inst/s at 1965 MHz, half the 4-per-clock issue rate: it shares the ALU pipe with the ~5 LOP3/SHF/VIMNMX each cell also needs)"},
                "clocks": clocks, "workload_gen_s": w["gen_s"]}
+        if ref_sharded is not None:
+            out["ref_sharded"] = ref_sharded
         if not args.no_cpu_baseline and world == 1:
             cb, _, refout = cpu_reference(args, w)
             out["cpu_baseline"] = cb

@@ -701,6 +701,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 	constexpr int NW = NCH * 4;                                           // words (of 8 columns) per item
 	const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, half = lane >> 4, l = lane & 15;
 	const uint32_t BW = 1u << (A.lbits - 5), HSM = A.hslots - 1, NPM = A.npmax;
+	const uint32_t NPI = 65536u / NPM + 1u;                                  // si / NPM == (si * NPI) >> 16 for si < 16 * NPM, NPM <= 32 (a runtime division costs ~20 instructions per match)
 	uint32_t *sM = smem;
 	uint32_t *bits = smem + 16 + warp * seedw_warp_words(A.lbits, A.hslots, NPM, STRIDE, NCH), *slots = bits + BW;   // slots: bucket heads, entry + 1 (0 = empty)
 	uint16_t *nxt = (uint16_t *)(slots + A.hslots);                        // chain links
@@ -916,7 +917,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
 										for (uint32_t j = 0; j < (uint32_t)STRIDE; ++j) {
 											const QWin w = window_of(S, j);
-											if (window_matches_table(sM, w.kn, w.ko & HM, rn, ro, A.SL.w)) seed(si / NPM, x1 - (int)w.y1);
+											if (window_matches_table(sM, w.kn, w.ko & HM, rn, ro, A.SL.w)) seed(((si * NPI) >> 16), x1 - (int)w.y1);
 										}
 									}
 								} else {
@@ -926,7 +927,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 										const uint4 rec = *(const uint4 *)(str + si * 4);
 										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
 										const QWin w = window_of(S, j);
-										if (w.kn == rn && (w.ko & HM) == ro) seed(si / NPM, x1 - (int)w.y1);
+										if (w.kn == rn && (w.ko & HM) == ro) seed(((si * NPI) >> 16), x1 - (int)w.y1);
 									}
 								}
 							};
@@ -973,7 +974,7 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 										QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
 										const QWin w = window_of(S, j);
 										if (w.kn == rn && (w.ko & HM) == ro) {
-											const uint32_t q = si / NPM, was = atomicCAS(&ost[owner * 4], NOQ, q);
+											const uint32_t q = ((si * NPI) >> 16), was = atomicCAS(&ost[owner * 4], NOQ, q);
 											const int dg = x1 - (int)w.y1;
 											if (was == NOQ || was == q) { atomicMin((int *)&ost[owner * 4 + 1], dg); atomicMax((int *)&ost[owner * 4 + 2], dg); }
 											else ost[owner * 4 + 3] = 1u;                    // a second query on this lane: the owner takes over
@@ -1963,7 +1964,7 @@ struct bg_ctx {
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
 	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
-	int seed_impl = 1, seed_nch = 8, seed_lbits = 0, seed_fb = 2, seed_hslots = 0;   // seed_fb: filter bits per window (1 or 2)
+	int seed_impl = 1, seed_nch = 0, seed_nch_auto = 8, seed_lbits = 0, seed_fb = 2, seed_hslots = 0;   // seed_nch 0: seed_nch_auto, chosen from the database's clump lengths at load;   // seed_fb: filter bits per window (1 or 2)
 	int _pad0 = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
 	uint32_t mstage = 0;                                          // longest query the k_extend staging slots are sized for (from the batch's lengths)
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
@@ -2042,7 +2043,7 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	if (const char *e = getenv("BURST_B200_SEED_CHUNK")) { const int v = atoi(e); if (v >= 1 && v <= 4096) c->seed_chunk = v; }
 	if (const char *e = getenv("BURST_B200_PIPE_SLICES")) { const int v = atoi(e); if (v >= 0 && v <= 64) c->pipe_slices = v; }
 	if (const char *e = getenv("BURST_B200_SEED_IMPL")) c->seed_impl = atoi(e) != 0;
-	if (const char *e = getenv("BURST_B200_SEED_NCH")) { const int v = atoi(e); if (v == 4 || v == 8) c->seed_nch = v; }
+	if (const char *e = getenv("BURST_B200_SEED_NCH")) { const int v = atoi(e); if (v == 0 || (v >= 4 && v <= 8)) c->seed_nch = v; }
 	if (const char *e = getenv("BURST_B200_SEED_FB")) { const int v = atoi(e); if (v == 1 || v == 2) c->seed_fb = v; }
 	if (const char *e = getenv("BURST_B200_SEED_LBITS")) { const int v = atoi(e); if (v == 0 || (v >= 10 && v <= 20)) c->seed_lbits = v; }
 	bg_default_scoring(1, c->S);
@@ -2095,7 +2096,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 	if (what == BG_PARAM_SEED_STAGE) { c->seed_stage = value != 0; return BG_OK; }
 	if (what == BG_PARAM_SEED_GROUPS) { if (value != 0 && value != 2 && value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed groups %d must be 0, 2, 4 or 8", value); c->seed_groups = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_IMPL) { c->seed_impl = value != 0; return BG_OK; }
-	if (what == BG_PARAM_SEED_NCH) { if (value != 4 && value != 8) return fail(BG_EINVAL, "bg_set_param: seed buffer chunks %d must be 4 or 8", value); c->seed_nch = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_NCH) { if (value != 0 && (value < 4 || value > 8)) return fail(BG_EINVAL, "bg_set_param: seed buffer chunks %d must be 0 (from the database) or 4..8", value); c->seed_nch = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_HSLOTS) { if (value && (value < 64 || value > 4096 || (value & (value - 1)))) return fail(BG_EINVAL, "bg_set_param: %d window-table buckets (must be 0 or a power of two 64..4096)", value); c->seed_hslots = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_FB) { if (value != 1 && value != 2) return fail(BG_EINVAL, "bg_set_param: filter bits per window %d must be 1 or 2", value); c->seed_fb = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_LBITS) { if (value && (value < 10 || value > 20)) return fail(BG_EINVAL, "bg_set_param: seed bitmap 2^%d bits out of range (0 = auto, 10..20)", value); c->seed_lbits = value; return BG_OK; }
@@ -2147,6 +2148,15 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 		uint64_t maxb = 0;
 		for (uint32_t i = 0; i < num_clumps; ++i) { meta[i].off = out_off[i]; meta[i].len = clump_len[i]; meta[i].flags = 0; maxb = std::max<uint64_t>(maxb, (out_off[i + 1] - out_off[i]) * 16); }
 		c->stage_bytes = (uint32_t)std::min<uint64_t>(maxb, 8192);
+		// k_seedw walks a clump in items of NCH chunks of 32 columns and probes every word of an item, valid or not: take the NCH in
+		// 4..8 that wastes the fewest probes over this database (an item also costs about twelve chunks' worth of bookkeeping -- measured: 214-column clumps in two items of 4 take 1.24 ms, in one of 7 0.91 ms; ties go
+		// to the larger item).  The usual sheared database has ONE clump length -- 214 columns for 100-base reads = 7 chunks.
+		{
+			uint64_t cost[9] = {0};
+			for (uint32_t i = 0; i < num_clumps; ++i) { const uint64_t ch = (clump_len[i] + 31) / 32; for (int n = 4; n <= 8; ++n) cost[n] += (ch + n - 1) / n * (uint64_t)(n + 12); }
+			int bestn = 8; for (int n = 7; n >= 4; --n) if (cost[n] < cost[bestn]) bestn = n;
+			c->seed_nch_auto = bestn;
+		}
 		CU(cudaMemcpyAsync(c->d_meta.p, meta.data(), (size_t)num_clumps * sizeof(ClumpMeta), cudaMemcpyHostToDevice, c->stream));
 		CU(cudaStreamSynchronize(c->stream));
 	}
@@ -2335,6 +2345,7 @@ static void seed_sizes(bg_ctx *c, SeedLayout &SL, uint32_t stretches_mean, uint3
 // the warp form of the seed filter: table sizes from the batch, grid = what is resident at once
 static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const SeedLayout &SL, uint32_t npmax) {
 	SeedWArgs S;
+	const int nch = c->seed_nch ? c->seed_nch : c->seed_nch_auto;
 	S.db = c->d_db.p; S.meta = c->d_meta.p; S.qi = B.qi; S.qnib = B.qnib; S.W = B.W; S.SL = SL; S.nwork = B.W.nruns;
 	uint32_t chunk = 1; while (chunk * 2 <= (uint32_t)c->seed_chunk * 8 && chunk < SEEDW_SPLIT) chunk <<= 1;   // a power of two that divides SEEDW_SPLIT (default 64 runs)
 	S.chunk = chunk; S.npmax = npmax;
@@ -2345,27 +2356,27 @@ static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const See
 	// filter: FB bits per window inside one 32-bit word.  Start from ~64 bits per window of a typical full bunch, then give up one
 	// power of two when that lets one more block live on an SM (measured on the bench shape: 2 bits in 2^14 at 4 blocks/SM beats
 	// 1 bit in 2^15 at 3 blocks/SM by 7 %, profiles/r2_tune_seedw.txt); a false positive costs one bucket probe
-	auto smem_of = [&](uint32_t lb) { return (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lb, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * sizeof(uint32_t); };
+	auto smem_of = [&](uint32_t lb) { return (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lb, S.hslots, npmax, SL.stride, (uint32_t)nch)) * sizeof(uint32_t); };
 	auto blocks_of = [&](uint32_t lb) { return std::min<size_t>(4, (size_t)(227 * 1024) / (smem_of(lb) + 1024)); };
 	uint32_t lbits = 12; while (lbits < 17 && (1u << lbits) < 64u * SL.words) ++lbits;
 	if (c->seed_lbits) lbits = (uint32_t)c->seed_lbits;
 	else if (lbits > 12 && (1u << (lbits - 1)) >= 32u * ne && blocks_of(lbits - 1) > blocks_of(lbits)) --lbits;
 	while (lbits > 10 && smem_of(lbits) > 200 * 1024) --lbits;
 	S.lbits = lbits;
-	const size_t smem = (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax, SL.stride, (uint32_t)c->seed_nch)) * sizeof(uint32_t);
+	const size_t smem = (16 + (size_t)SEEDW_WARPS * seedw_warp_words(lbits, S.hslots, npmax, SL.stride, (uint32_t)nch)) * sizeof(uint32_t);
 	if (smem > 220 * 1024) return fail(BG_EINVAL, "seed filter tables do not fit shared memory (stretches %u, stride %u)", npmax, SL.stride);
 	S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 	memcpy(S.m16, c->m16, sizeof(S.m16));
 	void (*kern)(SeedWArgs);
 	#define SEEDW_PICK(NCH, FB) (SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, NCH, FB> : k_seedw<8, false, NCH, FB>) : (SL.w == 16 ? k_seedw<4, true, NCH, FB> : k_seedw<4, false, NCH, FB>))
-	if (c->seed_nch == 4) kern = c->seed_fb == 2 ? SEEDW_PICK(4, 2) : SEEDW_PICK(4, 1);
-	else kern = c->seed_fb == 2 ? SEEDW_PICK(8, 2) : SEEDW_PICK(8, 1);
+	if (c->seed_fb != 2) kern = nch <= 4 ? SEEDW_PICK(4, 1) : SEEDW_PICK(8, 1);     // (one bit per window is a tuning setting: two item sizes only)
+	else kern = nch == 4 ? SEEDW_PICK(4, 2) : nch == 5 ? SEEDW_PICK(5, 2) : nch == 6 ? SEEDW_PICK(6, 2) : nch == 7 ? SEEDW_PICK(7, 2) : SEEDW_PICK(8, 2);
 	#undef SEEDW_PICK
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int bps = 0;
 	CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, kern, SEEDW_WARPS * 32, smem));
 	if (bps < 1) bps = 1;
-	if (getenv("BURST_B200_DEBUG")) fprintf(stderr, "[k_seedw] lbits %u hslots %u nch %d smem %zu B/block, %d blocks/SM\n", lbits, S.hslots, c->seed_nch, smem, bps);
+	if (getenv("BURST_B200_DEBUG")) fprintf(stderr, "[k_seedw] lbits %u hslots %u nch %d smem %zu B/block, %d blocks/SM\n", lbits, S.hslots, nch, smem, bps);
 	const uint64_t nchunk = (S.nwork + chunk - 1) / chunk;
 	const uint64_t blocks = std::min<uint64_t>((nchunk + SEEDW_WARPS - 1) / SEEDW_WARPS, (uint64_t)c->sms * bps);
 	kern<<<(unsigned)blocks, SEEDW_WARPS * 32, smem, st>>>(S);

@@ -141,6 +141,27 @@ class ReferenceSharded:
             self.eng.load_db(packed[int(off[self.lo]):int(off[self.hi])], clump_len[self.lo:self.hi], first_clump=self.lo)
         return self.lo, self.hi
 
+    def step_resident(self, mode, nslots, events=None):
+        """One pass over the batch already uploaded to the engine: filter + extend on this rank's clump range, the all-reduce(MIN) of the
+        per-slot minima in place on the device, selection against the combined minima -- all queued on the engine's stream (which must be
+        torch's current stream), no host synchronisation in between.  `events` = (before, after) CUDA events recorded around the collective.
+        Returns the device tensor of the combined minima (None on a rank without clumps, which still takes part in the collective)."""
+        have = self.hi > self.lo
+        if have:
+            self.eng.run_extend(mode)                       # (settles a survivor-list overflow itself before it returns)
+            best_t = _best_tensor(self.eng, nslots, self.on_cuda)
+        else:
+            best_t = torch.full((nslots,), 0xFFFF, dtype=torch.int32, device=self.device)
+        if self.world > 1 and mode == MODE_MIN:
+            if events:
+                events[0].record(torch.cuda.current_stream())
+            dist.all_reduce(best_t, op=dist.ReduceOp.MIN, group=self.group)  # the path's one collective (burst.c:4497-4517)
+            if events:
+                events[1].record(torch.cuda.current_stream())
+        if have:
+            self.eng.run_select(mode)
+        return best_t
+
     def align_runs(self, codes, offset, budget, runs, mode=MODE_MIN, slot=None, nslots=0, gather=True):
         runs = np.ascontiguousarray(runs, RUN_DTYPE)
         nq = len(offset) - 1
@@ -149,23 +170,13 @@ class ReferenceSharded:
         have = self.hi > self.lo
         if have:
             self.eng.upload_runs(codes, offset, budget, runs, slot=slot, nslots=nslots)
-            self.eng.run_extend(mode)
-            best_t = _best_tensor(self.eng, nslots, self.on_cuda)
-        else:
-            best_t = torch.full((nslots,), 0xFFFF, dtype=torch.int32, device=self.device)
-        if self.world > 1 and mode == MODE_MIN:
-            dist.all_reduce(best_t, op=dist.ReduceOp.MIN, group=self.group)  # the path's one collective
-        gbest = best_t.cpu().numpy().astype(np.uint16)      # (synchronises torch's stream = the engine's stream)
+        best_t = self.step_resident(mode, nslots)
         if have:
-            self.eng.run_select(mode)
-            hits, best = self.eng.download()
+            hits, best = self.eng.download()                # (the first host synchronisation of the batch)
             if mode == MODE_MIN:
-                # if the engine had to grow its survivor list it re-ran with local minima: re-apply the global ones
-                q = runs["query0"][hits["task"] // RUN_MAX] + hits["task"] % RUN_MAX
-                hits = hits[hits["ed"] == gbest[np.asarray(slot)[q]]]
-                best = gbest
+                best = best_t.cpu().numpy().astype(np.uint16)
         else:
-            hits, best = np.zeros(0, HIT_DTYPE), gbest
+            hits, best = np.zeros(0, HIT_DTYPE), best_t.cpu().numpy().astype(np.uint16)
         if not gather or self.world == 1:
             return hits, best
         if mode != MODE_MIN:

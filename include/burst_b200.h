@@ -108,7 +108,7 @@ enum { BG_PARAM_PIPE_MIN_RUNS = 6,   /* fewest runs worth a slice (default 4096)
        BG_PARAM_PIPE_RATIO = 7 };    /* size of each slice in percent of the one before; 0 (default) = 100 for byte codes (copy-bound), 140 for
                                         BG_Q_PACKED4 (kernel-bound: a short first copy, later copies hide behind the kernels) */
 enum { BG_PARAM_SEED_IMPL = 9,       /* 1 (default): warp-per-bunch seed filter (private window table, no block barriers); 0: the block form */
-       BG_PARAM_SEED_NCH = 10,       /* 32-column chunks per register buffer of the warp form: 8 (default) or 4 */
+       BG_PARAM_SEED_NCH = 10,       /* 32-column chunks per staged item of the warp form: 4..8; 0 (default) = the size that wastes the fewest probes on the loaded database */
        BG_PARAM_SEED_LBITS = 11,     /* log2 of the bits in a warp's window filter, 10..20 (0 = sized from the batch) */
        BG_PARAM_SEED_FB = 12,        /* bits set per window in that filter: 2 (default) or 1 */
        BG_PARAM_SEED_HSLOTS = 13 };  /* buckets of a warp's chained window table, a power of two 64..4096 (0 = sized from the batch) */
