@@ -36,6 +36,8 @@
 #include <stdarg.h>
 #include <algorithm>
 #include <vector>
+#include <mutex>
+#include <memory>
 #include <chrono>
 #include <type_traits>
 #include "burst_b200.h"
@@ -1667,6 +1669,93 @@ __global__ void k_compact_codes(const uint8_t *__restrict__ reads, uint32_t flag
 		*(uint4 *)(codes + qo + b0) = make_uint4(w[0], w[1], w[2], w[3]);
 	}
 }
+// The two kernels above in one pass for reads that arrive at 2 bits per base (every base a plain A/C/G/T): 8 threads per strand, 16 bases per
+// thread and step, read as ONE unaligned 32-bit window of the packed stream (two aligned loads + a funnel shift) instead of 16 byte loads;
+// the reverse complement is the window of the mirrored position with its 2-bit fields reversed (brev + swap within fields) and inverted
+// (A<->T, C<->G = 3 - code).  The thread writes its 16 code bytes (one 128-bit store) and its two words of 8 nibbles, the strand's first
+// thread the seed class and the counters k_qprep keeps.  0.65 ms -> 0.08 ms per 2 M strands of 100 bases.
+__device__ __forceinline__ unsigned long long spread2_to_bytes(uint32_t v16) {      // 8 fields of 2 bits -> 8 bytes
+	unsigned long long x = v16 & 0xFFFFu;
+	x = (x | (x << 24)) & 0x000000FF000000FFull;
+	x = (x | (x << 12)) & 0x000F000F000F000Full;
+	x = (x | (x << 6)) & 0x0303030303030303ull;
+	return x;
+}
+__device__ __forceinline__ uint32_t spread2_to_nibbles(uint32_t v16) {               // 8 fields of 2 bits -> 8 nibbles
+	uint32_t x = v16 & 0xFFFFu;
+	x = (x | (x << 8)) & 0x00FF00FFu;
+	x = (x | (x << 4)) & 0x0F0F0F0Fu;
+	x = (x | (x << 2)) & 0x33333333u;
+	return x;
+}
+__global__ void __launch_bounds__(256) k_compact_prep2(const uint32_t *__restrict__ reads32, const unsigned long long *__restrict__ roff, const uint16_t *__restrict__ rlen,
+		const uint16_t *__restrict__ rbudget, const uint32_t *__restrict__ strand, const unsigned long long *__restrict__ qoff, uint32_t nq, uint32_t nreads,
+		uint8_t *__restrict__ codes, QInfo *__restrict__ qi, SeedLayout SL, uint32_t *__restrict__ qnib, uint32_t *__restrict__ nseed, uint32_t *__restrict__ unseeded) {
+	// a resident grid walks the strands; the three counters are summed per block in shared memory and leave through ONE set of atomics per block
+	// (one set per warp -- 1.5 M atomics on three addresses for 2 M strands -- took longer than everything else in the kernel: 1.1 ms)
+	__shared__ uint32_t sh[4];
+	if (threadIdx.x < 4) sh[threadIdx.x] = 0;
+	__syncthreads();
+	const uint32_t sub = threadIdx.x & 7;
+	for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; q < ((nq + 31u) & ~31u); q += (gridDim.x * blockDim.x) >> 3) {
+	bool ok = q < nq, seed = false; uint32_t nst = 0;
+	uint32_t r = 0; bool rc = false;
+	if (ok) { const uint32_t sv = strand[q]; r = sv & 0x7FFFFFFFu; rc = sv >> 31; ok = r < nreads; }
+	if (ok) {
+		const uint32_t len = rlen[r];
+		const unsigned long long ro = roff[r], qo = qoff[q];
+		uint32_t *W = qnib + (qo >> 3) + 3ull * q;
+		if (sub == 0) { W[0] = 0; W[1] = 0; }
+		for (uint32_t b0 = sub * 16; b0 < len; b0 += 128) {
+			const uint32_t n = min(16u, len - b0);
+			uint32_t v;
+			if (!rc) {
+				const unsigned long long bit = 2ull * (ro + b0);
+				const uint32_t *pw = reads32 + (bit >> 5);
+				v = __funnelshift_r(__ldg(pw), __ldg(pw + 1), (uint32_t)bit & 31u);     // (the stream is padded: the second word exists)
+			} else {
+				const long long xs = (long long)ro + (long long)len - 16 - (long long)b0;   // first base of the mirrored window; field f = base xs + f
+				if (xs >= 0) {
+					const unsigned long long bit = 2ull * (unsigned long long)xs;
+					const uint32_t *pw = reads32 + (bit >> 5);
+					v = __funnelshift_r(__ldg(pw), __ldg(pw + 1), (uint32_t)bit & 31u);
+				} else v = __ldg(reads32) << (2 * (uint32_t)(-xs));                         // (only the first read of the stream: fields below its first base are not used)
+				v = __brev(v);
+				v = ((v >> 1) & 0x55555555u) | ((v & 0x55555555u) << 1);
+				v = ~v;
+			}
+			// code bytes (1..4), zero beyond the strand's end, as k_compact_codes leaves them
+			unsigned long long lo = spread2_to_bytes(v) + 0x0101010101010101ull, hi = spread2_to_bytes(v >> 16) + 0x0101010101010101ull;
+			if (n < 16) {
+				if (n <= 8) { hi = 0; if (n < 8) lo &= (1ull << (8 * n)) - 1ull; }
+				else hi &= (1ull << (8 * (n - 8))) - 1ull;
+			}
+			*(uint4 *)(codes + qo + b0) = make_uint4((uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32));
+			// the same bases as nibbles, the last word cut at the strand's end (k_qprep)
+			uint32_t w0 = spread2_to_nibbles(v) + 0x11111111u, w1 = spread2_to_nibbles(v >> 16) + 0x11111111u;
+			if (n < 8) w0 &= (1u << (4 * n)) - 1u;
+			else if (n < 16 && n > 8) w1 &= (1u << (4 * (n - 8))) - 1u;
+			W[2 + (b0 >> 3)] = w0;
+			if (n > 8) W[3 + (b0 >> 3)] = w1;
+		}
+		if (sub == 0) {
+			const uint32_t k = rbudget[r], np = k + 1u, plen = len / np;
+			seed = SL.stride && np <= SL.np_max && plen >= SL.w + SL.stride - 1;           // every base is plain: nothing else to check
+			qi[q].cls = (uint8_t)((seed ? 1u : 0u) | 2u);
+			if (seed) nst = np;
+		}
+	}
+	const uint32_t m = __ballot_sync(0xFFFFFFFFu, seed), tot = __reduce_add_sync(0xFFFFFFFFu, nst), mx = __reduce_max_sync(0xFFFFFFFFu, nst);
+	if (m && (threadIdx.x & 31) == 0) { atomicAdd(&sh[0], (uint32_t)__popc(m)); atomicAdd(&sh[1], tot); atomicMax(&sh[2], mx); }
+	const uint32_t u = __ballot_sync(0xFFFFFFFFu, q < nq && sub == 0 && !seed);
+	if (u && (threadIdx.x & 31) == 0) atomicAdd(&sh[3], (uint32_t)__popc(u));
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		if (sh[0]) { atomicAdd(nseed, sh[0]); atomicAdd(nseed + 1, sh[1]); atomicMax(nseed + 2, sh[2]); }
+		if (unseeded && sh[3]) atomicAdd(unseeded, sh[3]);
+	}
+}
 // the strand records (as k_qinfo) and the histogram of stretch lengths
 __global__ void k_compact_qinfo(const unsigned long long *__restrict__ qoff, const uint16_t *__restrict__ rlen, const uint16_t *__restrict__ rbudget,
 		const uint32_t *__restrict__ strand, uint32_t nq, uint32_t nreads, QInfo *__restrict__ qi, uint32_t *__restrict__ hist, uint32_t *__restrict__ counters) {
@@ -1933,17 +2022,18 @@ __global__ void k_work_stats(Work W, const QInfo *__restrict__ qi, const uint32_
 // host side
 // ---------------------------------------------------------------------------------------------
 template <typename T> struct DBuf {
-	T *p = nullptr; size_t cap = 0;
+	T *p = nullptr; size_t cap = 0; bool borrowed = false;       // borrowed: another context's allocation (bg_share_db), never freed or resized here
 	int need(size_t n) {
-		if (n <= cap) return 0;
-		if (p) cudaFree(p);
-		p = nullptr; cap = 0;
+		if (n <= cap && !borrowed) return 0;
+		if (p && !borrowed) cudaFree(p);
+		p = nullptr; cap = 0; borrowed = false;
 		size_t want = n + n / 8 + 64;
 		cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
 		if (e != cudaSuccess) { (void)cudaGetLastError(); return fail(BG_ENOMEM, "cudaMalloc(%zu bytes): %s", want * sizeof(T), cudaGetErrorString(e)); }
 		cap = want; return 0;
 	}
-	void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+	void release() { if (p && !borrowed) cudaFree(p); p = nullptr; cap = 0; borrowed = false; }
+	void borrow(const DBuf<T> &o) { release(); p = o.p; cap = o.cap; borrowed = o.p != nullptr; }
 };
 
 enum WorkKind { WORK_NONE = 0, WORK_ALL = 1, WORK_TASKS = 2, WORK_RUNS = 3 };
@@ -1958,8 +2048,18 @@ struct Slice {
 	void release() { sl64.release(); packed.release(); codes.release(); qoff.release(); budget.release(); slot.release(); qi.release(); qnib.release(); runs.release(); }
 };
 
+// Contexts that share one database (bg_share_db) also share a gate: the kernel sequence of one batch is queued behind the kernel sequence of
+// the batch queued before it, whichever context that was, so that the batches take the GPU one after the other while the copies of the next
+// one travel.  Without it two host threads that start together stay in lockstep -- both copy, then both compute with half the SMs each, then
+// both copy back -- and nothing overlaps (measured: 3.14 ms per step against 3.60 ms for one context).
+struct Gate {
+	std::mutex m; cudaEvent_t last = nullptr; std::vector<cudaEvent_t> ev;
+	~Gate() { for (cudaEvent_t e : ev) if (e) cudaEventDestroy(e); }
+};
+
 struct bg_ctx {
 	int device = 0;
+	std::shared_ptr<Gate> gate; cudaEvent_t gate_done = nullptr;
 	cudaStream_t stream = nullptr; bool own_stream = false;
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
@@ -2184,6 +2284,47 @@ extern "C" int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clum
 		i = j;
 	}
 	stage.release(); d_in_off.release();
+	return BG_OK;
+}
+
+// per-clump counters of the resident candidate-generation blocks (the accelerator names clumps of the whole database); private to a context
+static int acx_scratch(bg_ctx *c) {
+	c->acx_clumps = c->first_clump + c->num_clumps;
+	uint32_t blocks = (uint32_t)c->sms * 4;
+	while (blocks > (uint32_t)c->sms && (size_t)blocks * c->acx_clumps * 12 > (4ull << 30)) blocks -= (uint32_t)c->sms;
+	c->cg_blocks = blocks;
+	const size_t ne = (size_t)blocks * c->acx_clumps;
+	if (c->d_cg_cnt.need(ne) || c->d_cg_first.need(ne) || c->d_cg_cache.need(ne)) return BG_ENOMEM;
+	CU(cudaMemsetAsync(c->d_cg_cnt.p, 0, ne * 4, c->stream));
+	CU(cudaMemsetAsync(c->d_cg_first.p, 0xFF, ne * 4, c->stream));
+	CU(cudaStreamSynchronize(c->stream));
+	return BG_OK;
+}
+
+// A second context on the same device that uses the database (and accelerator) already loaded by `src` instead of a copy of its own:
+// two contexts = two batches in flight on one GPU (the copies of one behind the kernels of the other), one host thread each.
+// `src` must outlive `ctx` or be freed after it; loading a database of its own into `ctx` later simply drops the borrowed one.
+extern "C" int bg_share_db(bg_ctx *c, bg_ctx *src) {
+	if (!c || !src || c == src) return fail(BG_EINVAL, "bg_share_db: null or identical contexts");
+	if (c->device != src->device) return fail(BG_EINVAL, "bg_share_db: contexts on different devices (%d, %d)", c->device, src->device);
+	if (!src->num_clumps) return fail(BG_EINVAL, "bg_share_db: the source context holds no database");
+	CU(cudaSetDevice(c->device));
+	CU(cudaStreamSynchronize(src->stream));                        // the source's load is complete before anyone reads it from another stream
+	c->d_db.borrow(src->d_db); c->d_clump_off.borrow(src->d_clump_off); c->d_clump_len.borrow(src->d_clump_len); c->d_meta.borrow(src->d_meta);
+	c->num_clumps = src->num_clumps; c->first_clump = src->first_clump; c->stage_bytes = src->stage_bytes; c->seed_nch_auto = src->seed_nch_auto;
+	c->d_acx_off.borrow(src->d_acx_off); c->d_post.borrow(src->d_post); c->d_bad.borrow(src->d_bad);
+	c->acx_n = 0; c->acx_big = src->acx_big; c->acx_nbad = src->acx_nbad;
+	if (src->acx_n) { int rc = acx_scratch(c); if (rc) return rc; c->acx_n = src->acx_n; }
+	c->kind = WORK_NONE;
+	if (!src->gate) {
+		src->gate = std::make_shared<Gate>();
+		cudaEvent_t e = nullptr; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); src->gate->ev.push_back(e); src->gate_done = e;
+	}
+	if (c->gate != src->gate) {
+		std::lock_guard<std::mutex> g(src->gate->m);
+		cudaEvent_t e = nullptr; CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); src->gate->ev.push_back(e);
+		c->gate = src->gate; c->gate_done = e;
+	}
 	return BG_OK;
 }
 
@@ -2830,6 +2971,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 	const uint32_t nq = R->nq, nr = R->nreads;
 	cudaStream_t cs = c->stream, ps = c->copy_stream;
 	// ---- the small arrays leave first, so that they travel while the host looks at the lengths (single-slice calls, first attempt) ----
+	static const bool no_prep2 = getenv("BURST_B200_NO_PREP2") != nullptr;   // debugging: the two-kernel preparation also for 2-bit reads
 	static const int want_slices = getenv("BURST_B200_COMPACT_SLICES") ? std::max(1, std::min(32, atoi(getenv("BURST_B200_COMPACT_SLICES")))) : 1;
 	const int nsl = (int)std::min<uint64_t>((uint64_t)want_slices, std::max<uint64_t>(1, nruns / (uint64_t)c->pipe_min_runs));
 	bool early = nsl == 1;
@@ -2891,6 +3033,9 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		te[0] = te0;
 		const auto wall1 = std::chrono::steady_clock::now();
 		if (dbg) cudaEventRecord(te0, cs);
+		// contexts over one shared database: this batch's filter + sweep behind those of the batch queued last (taken below, before the first
+		// of them is launched; the copies and the light preparation kernels do not wait and run in the shadow of the other batch)
+		std::unique_lock<std::mutex> gate_lock;
 		if (best_inout) CU(cudaMemcpyAsync(c->d_best16.p, best_inout, (size_t)nr * 2, cudaMemcpyHostToDevice, cs));
 		k_init_best<<<(nr + 255) / 256, 256, 0, cs>>>(c->d_best.p, best_inout ? c->d_best16.p : nullptr, nr);
 		CU(cudaMemsetAsync(c->d_counters.p, 0, 256, cs));
@@ -2944,13 +3089,19 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 			k_compact_qinfo<<<(n + 255) / 256, 256, 0, cs>>>((const unsigned long long *)S.qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p + qa, n, nr, S.qi.p, c->d_counters.p + 16, c->d_counters.p);
 			if (rb > ra) k_compact_runs<<<(unsigned)((rb - ra + 255) / 256), 256, 0, cs>>>(c->d_candoff.p, c->d_cand.p, nbunch, ra, rb - ra, qbunch, nq, S.runs.p, c->d_counters.p);
 			if (i == 0) CU(cudaStreamWaitEvent(cs, c->sl[0].copied, 0));   // the packed reads
-			k_compact_codes<<<(unsigned)(((uint64_t)n * 8 + 255) / 256), 256, 0, cs>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p + qa, (const unsigned long long *)S.qoff.p, n, nr, S.codes.p);
-			k_qprep<<<(n + 127) / 128, 128, 0, cs>>>(S.codes.p, S.qi.p, n, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
+			if (R->flags == BG_R_PACKED2 && !no_prep2)
+				k_compact_prep2<<<(unsigned)std::min<uint64_t>(((uint64_t)n * 8 + 255) / 256, (uint64_t)c->sms * 8), 256, 0, cs>>>((const uint32_t *)c->d_packed.p, c->d_roff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p + qa, (const unsigned long long *)S.qoff.p, n, nr,
+					S.codes.p, S.qi.p, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
+			else {
+				k_compact_codes<<<(unsigned)(((uint64_t)n * 8 + 255) / 256), 256, 0, cs>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p + qa, (const unsigned long long *)S.qoff.p, n, nr, S.codes.p);
+				k_qprep<<<(n + 127) / 128, 128, 0, cs>>>(S.codes.p, S.qi.p, n, SL, S.qnib.p, c->d_counters.p + 9, c->d_first.p + 64 + i);
+			}
 			CU(cudaMemcpyAsync(c->d_first.p + i, c->d_counters.p + C_SURV, 4, cudaMemcpyDeviceToDevice, cs));
 			CU(cudaGetLastError());
 			BatchDev B; B.codes = S.codes.p; B.qnib = S.qnib.p; B.qi = S.qi.p;
 			B.W.runs = S.runs.p; B.W.nruns = rb - ra; B.W.nq = n; B.W.ntiles = 0; B.W.first_clump = c->first_clump; B.W.num_clumps = c->num_clumps;
 			B.W.q_base = qa; B.W.run_base = ra;
+			if (c->gate && !gate_lock.owns_lock()) { gate_lock = std::unique_lock<std::mutex>(c->gate->m); if (c->gate->last && c->gate->last != c->gate_done) CU(cudaStreamWaitEvent(cs, c->gate->last, 0)); }
 			if (i == 0) CU(cudaEventRecord(c->ev[0], cs));
 			rc = launch_filters(c, cs, B, SL, npmax, SL.stride != 0, true, c->d_first.p + 64 + i); if (rc) return rc;
 			rc = launch_extend(c, cs, B, mode, c->d_first.p + i); if (rc) return rc;
@@ -2959,6 +3110,7 @@ extern "C" int bg_align_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbun
 		k_select<<<(unsigned)c->sms * 4, 256, 0, cs>>>(c->d_surv.p, c->d_res.p, c->d_best.p, c->d_counters.p, c->surv_cap, c->d_hits.p, c->d_keys.p, mode);
 		CU(cudaGetLastError());
 		CU(cudaEventRecord(c->ev[3], cs));
+		if (c->gate && gate_lock.owns_lock()) { CU(cudaEventRecord(c->gate_done, cs)); c->gate->last = c->gate_done; gate_lock.unlock(); }
 		CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 64, cudaMemcpyDeviceToHost, cs));
 		CU(cudaStreamSynchronize(cs));
 		memcpy(c->h_counters, c->h_pinned, 16);
@@ -3029,16 +3181,7 @@ extern "C" int bg_load_acx(bg_ctx *c, const uint32_t *lens, const uint8_t *posti
 	if (post_bytes) CU(cudaMemcpyAsync(c->d_post.p, postings, post_bytes, cudaMemcpyHostToDevice, c->stream));
 	CU(cudaMemsetAsync(c->d_post.p + post_bytes, 0, 32, c->stream));
 	if (nbad) CU(cudaMemcpyAsync(c->d_bad.p, bad, (size_t)nbad * 4, cudaMemcpyHostToDevice, c->stream));
-	// per-clump counters of the resident candidate-generation blocks (the accelerator names clumps of the whole database)
-	c->acx_clumps = c->first_clump + c->num_clumps;
-	uint32_t blocks = (uint32_t)c->sms * 4;
-	while (blocks > (uint32_t)c->sms && (size_t)blocks * c->acx_clumps * 12 > (4ull << 30)) blocks -= (uint32_t)c->sms;
-	c->cg_blocks = blocks;
-	const size_t ne = (size_t)blocks * c->acx_clumps;
-	if (c->d_cg_cnt.need(ne) || c->d_cg_first.need(ne) || c->d_cg_cache.need(ne)) return BG_ENOMEM;
-	CU(cudaMemsetAsync(c->d_cg_cnt.p, 0, ne * 4, c->stream));
-	CU(cudaMemsetAsync(c->d_cg_first.p, 0xFF, ne * 4, c->stream));
-	CU(cudaStreamSynchronize(c->stream));
+	{ int rc = acx_scratch(c); if (rc) return rc; }
 	c->acx_n = word_len; c->acx_big = big; c->acx_nbad = nbad;
 	return BG_OK;
 }
@@ -3074,7 +3217,8 @@ extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbu
 	k_compact_slen<<<(nq + 256) / 256, 256, 0, st>>>(c->d_rlen.p, nr, c->d_strand.p, nq, c->d_sl64.p, c->d_counters.p);
 	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp1, c->d_rl64.p, c->d_roff.p, (int)nr + 1, st));
 	CU(cub::DeviceScan::ExclusiveSum(c->d_sort_tmp.p, tmp2, c->d_sl64.p, (unsigned long long *)c->d_qoff.p, (int)nq + 1, st));
-	k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, st>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
+	const bool prep2 = R->flags == BG_R_PACKED2 && !getenv("BURST_B200_NO_PREP2");
+	if (!prep2) k_compact_codes<<<(unsigned)(((uint64_t)nq * 8 + 255) / 256), 256, 0, st>>>(c->d_packed.p, R->flags, c->d_roff.p, c->d_rlen.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr, c->d_codes.p);
 	k_compact_qinfo<<<(nq + 255) / 256, 256, 0, st>>>((const unsigned long long *)c->d_qoff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, nq, nr, c->d_qi.p, c->d_counters.p + 16, c->d_counters.p);
 	CU(cudaGetLastError());
 	CU(cudaMemcpyAsync(c->h_pinned, c->d_counters.p, 256, cudaMemcpyDeviceToHost, st));
@@ -3082,7 +3226,9 @@ extern "C" int bg_search_bunches_into(bg_ctx *c, const bg_reads *R, uint32_t qbu
 	if (c->h_pinned[C_ERR]) return fail(BG_EINVAL, "bg_search_bunches_into: malformed batch (strands must name reads < nreads, read lengths >= 1, budgets <= 254)");
 	c->SL = choose_layout(c, c->h_pinned + 16, nq);
 	c->mstage = stage_len(maxlen); c->wide_possible = long_queries(maxlen); c->len_hint = maxlen;
-	k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
+	if (prep2) k_compact_prep2<<<(unsigned)std::min<uint64_t>(((uint64_t)nq * 8 + 255) / 256, (uint64_t)c->sms * 8), 256, 0, st>>>((const uint32_t *)c->d_packed.p, c->d_roff.p, c->d_rlen.p, c->d_rbud.p, c->d_strand.p, (const unsigned long long *)c->d_qoff.p, nq, nr,
+		c->d_codes.p, c->d_qi.p, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
+	else k_qprep<<<(nq + 127) / 128, 128, 0, st>>>(c->d_codes.p, c->d_qi.p, nq, c->SL, c->d_qnib.p, c->d_counters.p + 9, nullptr);
 	CU(cudaGetLastError());
 	c->nq = nq; c->nslots = nr;
 	// ---- candidates -> runs on the device ----

@@ -51,7 +51,7 @@ EXPORTS = ["bg_init", "bg_free", "bg_last_error", "bg_set_stream", "bg_set_scori
            "bg_batch_run_select", "bg_batch_count", "bg_batch_download", "bg_batch_stats",
            "bg_align_batch", "bg_free_hits", "bg_batch_upload_runs", "bg_align_runs", "bg_set_param", "bg_align_runs_into",
            "bg_host_alloc", "bg_host_free", "bg_align_bunches_into", "bg_stream", "bg_set_surv_cap",
-           "bg_load_acx", "bg_search_bunches_into"]
+           "bg_load_acx", "bg_search_bunches_into", "bg_share_db"]
 
 
 def load_library(path=None):
@@ -99,6 +99,7 @@ def load_library(path=None):
     L.bg_search_bunches_into.argtypes = [C.c_void_p, C.POINTER(BgReads), C.c_uint32, C.c_int, C.c_int, C.c_int,
                                          C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
     L.bg_host_free.argtypes = [C.c_void_p]
+    L.bg_share_db.argtypes = [C.c_void_p, C.c_void_p]
     return L
 
 
@@ -147,6 +148,12 @@ class Engine:
         clump_len = np.ascontiguousarray(clump_len, np.uint32)
         self._check(self.lib.bg_load_db(self.ctx, packed.ctypes.data, clump_len.ctypes.data,
                                         len(clump_len), first_clump))
+
+    def share_db(self, other):
+        """bg_share_db: use the database (and accelerator) `other` holds on the same device -- a second context for a second batch in flight.
+        `other` must stay open for as long as this engine is."""
+        self._check(self.lib.bg_share_db(self.ctx, other.ctx))
+        self._keep.append(other)
 
     @staticmethod
     def pack4(codes):

@@ -202,6 +202,13 @@ void bg_free_hits(bg_hit *hits);
 int  bg_align_runs_into(bg_ctx *ctx, const bg_queries *q, const bg_run *runs, uint64_t nruns,
                         int mode, uint16_t *best_inout, bg_hit *hits, uint64_t cap, uint64_t *nhits);
 
+/* Two batches in flight on one GPU.  `ctx` (same device as `src`) uses the database -- and the accelerator, when one is loaded -- that
+ * `src` already holds in HBM instead of a copy of its own; everything else (streams, batch buffers, survivor lists) stays private, so one
+ * host thread per context can run bg_align_*_into() / bg_search_bunches_into() concurrently: the host<->device copies of one batch
+ * travel behind the kernels of the other.  This is what the reference's thread team does with its per-thread scratch over one shared
+ * database (burst.c:4050-4077).  `src` must not be freed, nor load another database, before `ctx` is freed. */
+int  bg_share_db(bg_ctx *ctx, bg_ctx *src);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,7 +22,7 @@ uint64_t oracle_run_tasks(const uint8_t *packed, const uint64_t *clump_off, cons
 
 struct bg_ctx {
 	uint8_t S[256];
-	uint8_t *packed; uint64_t *clump_off; uint32_t *clump_len; uint32_t num_clumps, first_clump;
+	uint8_t *packed; uint64_t *clump_off; uint32_t *clump_len; uint32_t num_clumps, first_clump; int borrowed;   /* borrowed: database + accelerator belong to another context (bg_share_db) */
 	/* batch */
 	uint8_t *codes; uint64_t *qoff; uint16_t *budget; uint32_t *slot; uint32_t nq, nslots;
 	uint32_t *tq, *tc; uint64_t *orig; uint64_t ntasks;
@@ -47,7 +47,11 @@ static void free_batch(bg_ctx *c) {
 	free(c->best); free(c->hits); free(c->best32); c->best32 = NULL;
 	c->codes = NULL; c->qoff = NULL; c->budget = NULL; c->slot = NULL; c->tq = c->tc = NULL; c->orig = NULL; c->best = NULL; c->hits = NULL;
 }
-void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); free(c->packed); free(c->clump_off); free(c->clump_len); free(c->acx_off); free(c->acx_post); free(c->acx_bad); free(c); }
+static void drop_db(bg_ctx *c) {
+	if (!c->borrowed) { free(c->packed); free(c->clump_off); free(c->clump_len); free(c->acx_off); free(c->acx_post); free(c->acx_bad); }
+	c->packed = NULL; c->clump_off = NULL; c->clump_len = NULL; c->acx_off = NULL; c->acx_post = NULL; c->acx_bad = NULL; c->borrowed = 0; c->num_clumps = 0; c->acx_n = 0;
+}
+void bg_free(bg_ctx *c) { if (!c) return; free_batch(c); drop_db(c); free(c); }
 void *bg_host_alloc(uint64_t bytes) { return malloc(bytes ? bytes : 1); }
 void bg_host_free(void *p) { free(p); }
 int bg_set_stream(bg_ctx *c, void *s) { (void)c; (void)s; return BG_OK; }
@@ -55,6 +59,7 @@ int bg_set_param(bg_ctx *c, int what, int value) { (void)c; (void)what; (void)va
 int bg_set_scoring(bg_ctx *c, const uint8_t S[256]) { memcpy(c->S, S, 256); return BG_OK; }
 
 int bg_load_db(bg_ctx *c, const uint8_t *packed, const uint32_t *clump_len, uint32_t n, uint32_t first) {
+	if (c->borrowed) drop_db(c);
 	free(c->packed); free(c->clump_off); free(c->clump_len);
 	c->clump_off = malloc((n + 1) * 8); c->clump_len = malloc(n * 4);
 	uint64_t tot = 0;
@@ -238,12 +243,22 @@ int bg_load_acx(bg_ctx *c, const uint32_t *lens, const uint8_t *postings, uint64
 	if (word_len != 12 && word_len != 15) { snprintf(g_err, sizeof(g_err), "bg_load_acx: word length %d (must be 12 or 15)", word_len); return BG_EINVAL; }
 	if (!c->num_clumps) { snprintf(g_err, sizeof(g_err), "bg_load_acx: load the database first"); return BG_EINVAL; }
 	uint64_t nk = 1ull << (2 * word_len);
+	if (c->borrowed) { snprintf(g_err, sizeof(g_err), "bg_load_acx: this context borrows another's database (bg_share_db); load the accelerator there"); return BG_EINVAL; }
 	free(c->acx_off); free(c->acx_post); free(c->acx_bad);
 	c->acx_off = malloc((nk + 1) * 8); c->acx_off[0] = 0;
 	for (uint64_t i = 0; i < nk; ++i) c->acx_off[i + 1] = c->acx_off[i] + (big ? (uint64_t)lens[i] * 3 : (uint64_t)(lens[i] / 2) * 5 + (lens[i] & 1) * 3);
 	if (c->acx_off[nk] != post_bytes) { snprintf(g_err, sizeof(g_err), "bg_load_acx: the lengths describe %llu bytes of postings, %llu given", (unsigned long long)c->acx_off[nk], (unsigned long long)post_bytes); return BG_EINVAL; }
 	c->acx_post = malloc(post_bytes + 8); memcpy(c->acx_post, postings, post_bytes); memset(c->acx_post + post_bytes, 0, 8);
 	c->acx_bad = dup(bad, (size_t)nbad * 4); c->acx_nbad = nbad; c->acx_n = word_len; c->acx_big = big;
+	return BG_OK;
+}
+int bg_share_db(bg_ctx *c, bg_ctx *src) {
+	if (!c || !src || c == src) { snprintf(g_err, sizeof(g_err), "bg_share_db: null or identical contexts"); return BG_EINVAL; }
+	if (!src->num_clumps) { snprintf(g_err, sizeof(g_err), "bg_share_db: the source context holds no database"); return BG_EINVAL; }
+	drop_db(c);
+	c->packed = src->packed; c->clump_off = src->clump_off; c->clump_len = src->clump_len; c->num_clumps = src->num_clumps; c->first_clump = src->first_clump;
+	c->acx_off = src->acx_off; c->acx_post = src->acx_post; c->acx_bad = src->acx_bad; c->acx_nbad = src->acx_nbad; c->acx_n = src->acx_n; c->acx_big = src->acx_big;
+	c->borrowed = 1;
 	return BG_OK;
 }
 static int cmp_u64(const void *a, const void *b) { uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b; return x < y ? -1 : x > y; }

@@ -82,3 +82,22 @@ def test_compact_strand_batches(sim):
             buf = np.zeros(len(want_h) + 2, HIT_DTYPE); b2 = np.full(B["nreads"], 0xFFFF, np.uint16)
             n = sim.align_bunches_into(stream, B["rlen"], B["rbudget"], B["strand"], 8, B["cand_off"], B["cand"], buf, b2, mode, packed2=packed2)
             assert n == len(want_h) and np.array_equal(buf[:n], want_h) and np.array_equal(b2, want_b), (mode, packed2)
+
+
+def test_share_db_second_context(sim):
+    """bg_share_db: a second context that borrows the first one's database gives the same hits; it can be freed first, and loading
+    a database of its own drops the borrowed one without touching the owner's."""
+    from burst_b200.engine import Engine
+    packed, clen, codes, qoff, budget, runs = small_batch(seed=9)
+    sim.load_db(packed, clen)
+    want_h, want_b = sim.align(codes, qoff, budget, None, 0, runs=runs)
+    other = Engine(0, lib_path=SIMLIB)
+    with pytest.raises(RuntimeError):
+        Engine(0, lib_path=SIMLIB).share_db(other)          # nothing to share yet
+    other.share_db(sim)
+    h, b = other.align(codes, qoff, budget, None, 0, runs=runs)
+    assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
+    other.load_db(packed[: int(((clen[:16].astype(np.uint64) + 1) // 2 * 16).sum())], clen[:16])     # its own, smaller database
+    other.close()
+    h, b = sim.align(codes, qoff, budget, None, 0, runs=runs)                                        # the owner's is intact
+    assert np.array_equal(h, want_h) and np.array_equal(b, want_b)

@@ -199,3 +199,39 @@ def test_long_queries_large_budgets(eng, oracle, mode):
             assert len(hits) == len(ohits) and np.array_equal(hits, ohits), (seedf, len(hits), len(ohits))
     finally:
         eng.set_seed_filter(True)
+
+
+def test_two_contexts_share_one_database(eng, oracle):
+    """bg_share_db: two contexts on one GPU over one database in HBM, one host thread each, the one-call path at the same time
+    (the bench's in-flight e2e leg): both must return what a single context returns."""
+    import threading
+    from burst_b200.engine import Engine, HIT_DTYPE
+    rng = np.random.default_rng(77)
+    refs = synth.random_refs(16 * 40, 230, rng, jitter=10)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 320, 100, 2, rng)
+    codes, qoff = synth.concat_queries(reads)
+    budget = np.full(len(reads), 2, np.uint16)
+    runs = np.array([(int(origin[q, 0]), q, 1) for q in range(len(reads))] + [(c, q0, 16) for q0 in range(0, len(reads), 16) for c in (0, 7, len(clen) - 1)], dtype=RUN_DTYPE)
+    eng.load_db(packed, clen)
+    want_h, want_b = eng.align(codes, qoff, budget, None, 0, runs=runs)
+    assert len(want_h) >= len(reads)
+    other = Engine(0); other.share_db(eng)
+    out = {}
+
+    def work(name, e):
+        for it in range(6):
+            buf = np.zeros(len(want_h) + 8, HIT_DTYPE); best = np.full(len(reads), 0xFFFF, np.uint16)
+            n = e.align_runs_into(codes, qoff, budget, runs, buf, best, 0)
+            out[name, it] = (buf[:n].copy(), best)
+    th = [threading.Thread(target=work, args=("a", eng)), threading.Thread(target=work, args=("b", other))]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    assert len(out) == 12
+    for h, b in out.values():
+        assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
+    other.close()
+    h, b = eng.align(codes, qoff, budget, None, 0, runs=runs)              # the owner still holds its database
+    assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
