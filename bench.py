@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--clump-len", type=int, default=214)
     ap.add_argument("--cpu-sample-bunches", type=int, default=0, help="0 = auto (about 10-30 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="contexts (batches in flight) per GPU in the e2e leg")
+    ap.add_argument("--inflight", type=int, default=3, help="contexts (batches in flight) per GPU in the e2e leg")
     ap.add_argument("--config", default="c2", choices=["c2", "target", "c3"],
                     help="c2 (default, the headline): BASELINE.json configs[1], 1 M reads vs a 2 GB DB; target: north_star's 10 M x 100 bp vs a 31.5 GB .edx on one B200; "
                          "c3: configs[2] shape, 200 k x 292 bp amplicon reads (0-5 substitutions, budget 9) vs a 70 MB mutation-tree DB of 1400-base references, ~60 clump visits per strand")

@@ -2739,10 +2739,12 @@ static int sort_hits(bg_ctx *c, uint32_t n) {
 	if (n > 0x7FFFFFFFu) return fail(BG_EOVERFLOW, "%u hits in one batch (the hit sort takes at most 2^31-1); use smaller batches", n);
 	if (c->d_keys2.need(n) || c->d_order.need(n) || c->d_order2.need(n) || c->d_hits_sorted.need(n)) return BG_ENOMEM;
 	size_t tmp = 0;
-	CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, 36, c->stream));
+	int end_bit = 36;                                             // key = task << 4 | lane; a run list bounds the task index: sort only the bits that can differ
+	if (c->kind == WORK_RUNS && c->ntasks) { end_bit = 5; while (end_bit < 36 && ((c->ntasks - 1) >> (end_bit - 4))) ++end_bit; }
+	CU(cub::DeviceRadixSort::SortPairs(nullptr, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, end_bit, c->stream));
 	if (c->d_sort_tmp.need(tmp + 16)) return BG_ENOMEM;
 	k_iota<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_order.p, n);
-	CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, 36, c->stream));
+	CU(cub::DeviceRadixSort::SortPairs(c->d_sort_tmp.p, tmp, c->d_keys.p, c->d_keys2.p, c->d_order.p, c->d_order2.p, (int)n, 0, end_bit, c->stream));
 	k_gather_hits<<<(n + 255) / 256, 256, 0, c->stream>>>(c->d_hits.p, c->d_order2.p, n, c->d_hits_sorted.p);
 	CU(cudaGetLastError());
 	c->sorted = true;
