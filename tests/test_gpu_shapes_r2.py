@@ -235,3 +235,32 @@ def test_two_contexts_share_one_database(eng, oracle):
     other.close()
     h, b = eng.align(codes, qoff, budget, None, 0, runs=runs)              # the owner still holds its database
     assert np.array_equal(h, want_h) and np.array_equal(b, want_b)
+
+
+def test_compact_2bit_reads_of_any_length(eng, oracle):
+    """k_compact_prep2 (one kernel from 2-bit packed reads to code bytes, nibble words and seed classes, both orientations): reads
+    shorter than one 16-base step, longer than the 128 bases the eight threads of a strand cover per round, lengths that are not a
+    multiple of 16 or 8, the stream's first read met through its reverse complement -- against the oracle on the written-out strands."""
+    from burst_b200.engine import Engine, HIT_DTYPE
+    rng = np.random.default_rng(4242)
+    refs = synth.random_refs(16 * 12, 330, rng, jitter=6)
+    packed, off, clen = synth.pack_clumps(refs)
+    reads, origin = synth.reads_from_clumps(packed, off, clen, 90, 300, 4, rng, rc_rate=0.5)
+    lens = [17, 300, 129, 128, 127, 16, 33, 47, 250, 18] + [int(v) for v in rng.integers(18, 301, len(reads) - 10)]
+    reads = [r[:L] for r, L in zip(reads, lens)]
+    S = oracle.score_table(1)
+    eng.set_scoring(S); eng.load_db(packed, clen)
+    budgets = [oracle.budget(0.97, len(r)) for r in reads]
+    B = synth.strand_batch(reads, budgets, 16, lambda b, rd, rc: sorted({int(origin[r, 0]) for r in rd} | {int(v) for v in rng.integers(0, len(clen), 1)}))
+    ohits, obest = oracle.run_tasks(packed, off, clen, B["qcodes"], B["qoff"], B["budget"], B["slot"], B["nreads"], B["tq"], B["tc"], S, 0)
+    ohits = ohits.copy(); ohits["task"] = B["key"][ohits["task"]]
+    ohits = ohits[np.lexsort((ohits["lane"], ohits["task"]))]
+    buf = np.zeros(len(ohits) + 8, HIT_DTYPE); b2 = np.full(B["nreads"], 0xFFFF, np.uint16)
+    n = eng.align_bunches_into(Engine.pack2(B["rcodes"]), B["rlen"], B["rbudget"], B["strand"], 16, B["cand_off"], B["cand"], buf, b2, 0, packed2=True)
+    assert n == len(ohits) and np.array_equal(buf[:n], ohits), (n, len(ohits))
+    assert np.array_equal(b2, obest)
+    assert n >= 60
+    # the same reads at 4 bits per base go through the two-kernel preparation: same answer
+    buf4 = np.zeros(len(ohits) + 8, HIT_DTYPE); b4 = np.full(B["nreads"], 0xFFFF, np.uint16)
+    n4 = eng.align_bunches_into(Engine.pack4(B["rcodes"]), B["rlen"], B["rbudget"], B["strand"], 16, B["cand_off"], B["cand"], buf4, b4, 0, packed2=False)
+    assert n4 == n and np.array_equal(buf4[:n], buf[:n]) and np.array_equal(b4, b2)
