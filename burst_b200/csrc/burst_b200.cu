@@ -696,7 +696,7 @@ __host__ __device__ __forceinline__ uint32_t seedw_warp_words(uint32_t lbits, ui
 	return (1u << (lbits - 5)) + hslots + ((8 * npmax * stride + 3) & ~3u) + 64 * npmax + 16 + 4 * nch * 64 + 8 + 128 + 64 + 128 + 4;
 }
 
-template <int STRIDE, bool FULLW, int NCH, int FB>   // FB: bits per window in the filter (1 or 2)
+template <int STRIDE, bool FULLW, int NCH, int FB, int VM>   // FB: bits per window in the filter (1 or 2); VM: verification of flagged words, 0 = queue + helper lanes + shared-memory atomics, 1 = one pass per flagged lane, results by warp reduction
 __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 	extern __shared__ __align__(16) uint32_t smem[];
 	constexpr uint32_t FULL = 0xFFFFFFFFu;
@@ -942,9 +942,57 @@ __global__ void __launch_bounds__(SEEDW_WARPS * 32, 4) k_seedw(SeedWArgs A) {
 						};
 						const uint32_t s8 = m8, s4 = m4;                           // kept: a lane whose helpers report a second query redoes the item itself
 						if (serial) { own(m8, m4); m8 = m4 = 0; }
+						if (VM == 1) {
+							// ---- one pass per flagged lane: the 32 lanes take the (<= 32) words of the owner's item, each verifies its word if flagged; the matches
+							//      of the pass (query range, diagonal range) come back by warp reduction and the owner folds them into its record -- no queue, no
+							//      shared-memory atomics.  A record stays ONE cluster of ONE query exactly as below: on a second query or seeds out of reach the
+							//      record is left as it was and the owner redoes the item itself, into a proper list.
+							uint32_t fl = __ballot_sync(FULL, (m8 | m4) != 0u);
+							while (fl) {
+								const uint32_t owner = (uint32_t)__ffs(fl) - 1u; fl &= fl - 1u;
+								const uint32_t o8 = __shfl_sync(FULL, m8, owner), o4 = STRIDE == 4 ? __shfl_sync(FULL, m4, owner) : 0u;
+								const uint32_t o_cg = __shfl_sync(FULL, cg, owner), o_ip = __shfl_sync(FULL, iprev, owner), o_ip2 = __shfl_sync(FULL, iprev2, owner);
+								const uint32_t bit = lane < (uint32_t)NW ? 1u << (NW - 1 - lane) : 0u;
+								uint32_t qlo = NOQ, qhi = 0u; int dlo = 0x7FFFFFFF, dhi = (int)0x80000000;
+								if ((o8 | o4) & bit) {
+									const uint32_t osb = stgw_s + (owner >> 4) * 2 * ITEM + cb * ITEM + (owner & 15) * 16;
+									auto word = [&](int w) -> uint32_t { return w >= 0 ? lds32(osb + (uint32_t)(w >> 2) * 256 + (uint32_t)(w & 3) * 4) : (w == -1 ? o_ip : o_ip2); };
+									const uint32_t cu = word((int)lane), pv = word((int)lane - 1), pv2 = (STRIDE == 4 && (o4 & bit)) ? word((int)lane - 2) : 0u;
+									#pragma unroll
+									for (int e = (STRIDE == 4 ? 4 : 8); e <= 8; e += 4) {
+										if (!((e == 4 ? o4 : o8) & bit)) continue;
+										const uint32_t rn = e == 4 ? __funnelshift_r(pv, cu, 16) : cu, ro = (e == 4 ? __funnelshift_r(pv2, pv, 16) : pv) & HM;
+										const int x1 = (int)((o_cg * NW + lane) * 8 + (uint32_t)e);
+										for (uint32_t en = slots[(seed_hash(rn, ro) >> 10) & HSM]; en; en = nxt[en - 1]) {
+											const uint32_t si = (en - 1) / STRIDE, j = (en - 1) % STRIDE;
+											const uint4 rec = *(const uint4 *)(str + si * 4);
+											QStretch S; S.r0 = rec.x; S.r1 = rec.y; S.r2 = rec.z; S.E = rec.w;
+											const QWin w = window_of(S, j);
+											if (w.kn == rn && (w.ko & HM) == ro) {
+												const uint32_t q = (si * NPI) >> 16; const int dg = x1 - (int)w.y1;
+												qlo = min(qlo, q); qhi = max(qhi, q); dlo = min(dlo, dg); dhi = max(dhi, dg);
+											}
+										}
+									}
+								}
+								const uint32_t Qlo = __reduce_min_sync(FULL, qlo);
+								if (Qlo != NOQ) {
+									const uint32_t Qhi = __reduce_max_sync(FULL, qhi);
+									const int Dlo = __reduce_min_sync(FULL, dlo), Dhi = __reduce_max_sync(FULL, dhi);
+									if (lane == owner) {
+										const uint4 rec = *(const uint4 *)(ost + lane * 4);
+										const int nlo = min((int)rec.y, Dlo), nhi = max((int)rec.z, Dhi);
+										if (Qlo != Qhi || (rec.x != NOQ && rec.x != Qlo) || nhi - nlo > 2 * (int)kq[Qlo] + 1) own(s8, s4);
+										else *(uint4 *)(ost + lane * 4) = make_uint4(Qlo, (uint32_t)nlo, (uint32_t)nhi, 0u);
+									}
+								}
+								__syncwarp();
+							}
+							m8 = m4 = 0;
+						}
 						uint32_t cnt = (uint32_t)(__popc(m8) + __popc(m4));
-						if (__reduce_add_sync(FULL, cnt) > HQ) { own(m8, m4); m8 = m4 = 0; cnt = 0; }       // more flagged words than the queue holds (rare): everyone its own
-						if (__any_sync(FULL, cnt != 0u)) {
+						if (VM == 0 && __reduce_add_sync(FULL, cnt) > HQ) { own(m8, m4); m8 = m4 = 0; cnt = 0; }       // more flagged words than the queue holds (rare): everyone its own
+						if (VM == 0 && __any_sync(FULL, cnt != 0u)) {
 							// ---- enqueue ----
 							if (lane == 0) *hqn = 0;
 							__syncwarp();
@@ -2064,7 +2112,7 @@ struct bg_ctx {
 	int sms = 148;
 	int seed_filter = 1, seed_chunk = 8, seed_words = 0, seed_stage = 0;   // tuning: runs per warp, Bloom words per warp (0 = auto), bulk-copy staging
 	int seed_groups = 0;                                          // groups (runs per round) per block, 0 = chosen for occupancy
-	int seed_impl = 1, seed_nch = 0, seed_nch_auto = 8, seed_lbits = 0, seed_fb = 2, seed_hslots = 0;   // seed_nch 0: seed_nch_auto, chosen from the database's clump lengths at load;   // seed_fb: filter bits per window (1 or 2)
+	int seed_impl = 1, seed_nch = 0, seed_nch_auto = 8, seed_lbits = 0, seed_fb = 2, seed_hslots = 0, seed_vmode = 0;   // seed_nch 0: seed_nch_auto, chosen from the database's clump lengths at load;   // seed_fb: filter bits per window (1 or 2)
 	int _pad0 = 0;              // 1: warp-per-bunch k_seedw (default), 0: block form k_seed; chunks per register buffer; log2 bitmap bits (0 = from the batch)
 	uint32_t mstage = 0;                                          // longest query the k_extend staging slots are sized for (from the batch's lengths)
 	uint32_t seed_npmax = 1;                                      // stretches per query the window table holds (from the batch)
@@ -2144,6 +2192,7 @@ extern "C" int bg_init(int device, bg_ctx **out) {
 	if (const char *e = getenv("BURST_B200_PIPE_SLICES")) { const int v = atoi(e); if (v >= 0 && v <= 64) c->pipe_slices = v; }
 	if (const char *e = getenv("BURST_B200_SEED_IMPL")) c->seed_impl = atoi(e) != 0;
 	if (const char *e = getenv("BURST_B200_SEED_NCH")) { const int v = atoi(e); if (v == 0 || (v >= 4 && v <= 8)) c->seed_nch = v; }
+	if (const char *e = getenv("BURST_B200_SEED_VMODE")) { const int v = atoi(e); if (v == 0 || v == 1) c->seed_vmode = v; }
 	if (const char *e = getenv("BURST_B200_SEED_FB")) { const int v = atoi(e); if (v == 1 || v == 2) c->seed_fb = v; }
 	if (const char *e = getenv("BURST_B200_SEED_LBITS")) { const int v = atoi(e); if (v == 0 || (v >= 10 && v <= 20)) c->seed_lbits = v; }
 	bg_default_scoring(1, c->S);
@@ -2199,6 +2248,7 @@ extern "C" int bg_set_param(bg_ctx *c, int what, int value) {
 	if (what == BG_PARAM_SEED_NCH) { if (value != 0 && (value < 4 || value > 8)) return fail(BG_EINVAL, "bg_set_param: seed buffer chunks %d must be 0 (from the database) or 4..8", value); c->seed_nch = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_HSLOTS) { if (value && (value < 64 || value > 4096 || (value & (value - 1)))) return fail(BG_EINVAL, "bg_set_param: %d window-table buckets (must be 0 or a power of two 64..4096)", value); c->seed_hslots = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_FB) { if (value != 1 && value != 2) return fail(BG_EINVAL, "bg_set_param: filter bits per window %d must be 1 or 2", value); c->seed_fb = value; return BG_OK; }
+	if (what == BG_PARAM_SEED_VMODE) { if (value != 0 && value != 1) return fail(BG_EINVAL, "bg_set_param: verification mode %d must be 0 or 1", value); c->seed_vmode = value; return BG_OK; }
 	if (what == BG_PARAM_SEED_LBITS) { if (value && (value < 10 || value > 20)) return fail(BG_EINVAL, "bg_set_param: seed bitmap 2^%d bits out of range (0 = auto, 10..20)", value); c->seed_lbits = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_RATIO) { if (value && (value < 10 || value > 300)) return fail(BG_EINVAL, "bg_set_param: slice ratio %d must be 0 (auto) or 10..300", value); c->pipe_ratio = value; return BG_OK; }
 	if (what == BG_PARAM_PIPE_MIN_RUNS) { if (value < 1) return fail(BG_EINVAL, "bg_set_param: minimum runs per slice %d", value); c->pipe_min_runs = value; return BG_OK; }
@@ -2509,9 +2559,10 @@ static int launch_seedw(bg_ctx *c, cudaStream_t st, const BatchDev &B, const See
 	S.surv = c->d_surv.p; S.surv_cap = c->surv_cap; S.counters = c->d_counters.p;
 	memcpy(S.m16, c->m16, sizeof(S.m16));
 	void (*kern)(SeedWArgs);
-	#define SEEDW_PICK(NCH, FB) (SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, NCH, FB> : k_seedw<8, false, NCH, FB>) : (SL.w == 16 ? k_seedw<4, true, NCH, FB> : k_seedw<4, false, NCH, FB>))
-	if (c->seed_fb != 2) kern = nch <= 4 ? SEEDW_PICK(4, 1) : SEEDW_PICK(8, 1);     // (one bit per window is a tuning setting: two item sizes only)
-	else kern = nch == 4 ? SEEDW_PICK(4, 2) : nch == 5 ? SEEDW_PICK(5, 2) : nch == 6 ? SEEDW_PICK(6, 2) : nch == 7 ? SEEDW_PICK(7, 2) : SEEDW_PICK(8, 2);
+	#define SEEDW_PICK(NCH, FB, VM) (SL.stride == 8 ? (SL.w == 16 ? k_seedw<8, true, NCH, FB, VM> : k_seedw<8, false, NCH, FB, VM>) : (SL.w == 16 ? k_seedw<4, true, NCH, FB, VM> : k_seedw<4, false, NCH, FB, VM>))
+	if (c->seed_fb != 2) kern = nch <= 4 ? SEEDW_PICK(4, 1, 0) : SEEDW_PICK(8, 1, 0);     // (one bit per window is a tuning setting: two item sizes only)
+	else if (c->seed_vmode == 0) kern = nch == 4 ? SEEDW_PICK(4, 2, 0) : nch == 5 ? SEEDW_PICK(5, 2, 0) : nch == 6 ? SEEDW_PICK(6, 2, 0) : nch == 7 ? SEEDW_PICK(7, 2, 0) : SEEDW_PICK(8, 2, 0);
+	else kern = nch == 4 ? SEEDW_PICK(4, 2, 1) : nch == 5 ? SEEDW_PICK(5, 2, 1) : nch == 6 ? SEEDW_PICK(6, 2, 1) : nch == 7 ? SEEDW_PICK(7, 2, 1) : SEEDW_PICK(8, 2, 1);
 	#undef SEEDW_PICK
 	if (smem > 48 * 1024) CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 	int bps = 0;

@@ -22,7 +22,7 @@ Q_PACKED4 = 1
 R_PACKED4, R_PACKED2 = 1, 2
 PARAM_SEED_FILTER, PARAM_SEED_CHUNK, PARAM_SEED_WORDS, PARAM_SEED_STAGE, PARAM_PIPE_SLICES = 1, 2, 3, 4, 5
 PARAM_PIPE_MIN_RUNS, PARAM_PIPE_RATIO, PARAM_SEED_GROUPS = 6, 7, 8
-PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB, PARAM_SEED_HSLOTS = 9, 10, 11, 12, 13
+PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB, PARAM_SEED_HSLOTS, PARAM_SEED_VMODE = 9, 10, 11, 12, 13, 14
 
 
 class BgQueries(C.Structure):

@@ -111,7 +111,8 @@ enum { BG_PARAM_SEED_IMPL = 9,       /* 1 (default): warp-per-bunch seed filter 
        BG_PARAM_SEED_NCH = 10,       /* 32-column chunks per staged item of the warp form: 4..8; 0 (default) = the size that wastes the fewest probes on the loaded database */
        BG_PARAM_SEED_LBITS = 11,     /* log2 of the bits in a warp's window filter, 10..20 (0 = sized from the batch) */
        BG_PARAM_SEED_FB = 12,        /* bits set per window in that filter: 2 (default) or 1 */
-       BG_PARAM_SEED_HSLOTS = 13 };  /* buckets of a warp's chained window table, a power of two 64..4096 (0 = sized from the batch) */
+       BG_PARAM_SEED_HSLOTS = 13,    /* buckets of a warp's chained window table, a power of two 64..4096 (0 = sized from the batch) */
+       BG_PARAM_SEED_VMODE = 14 };   /* how the warp form verifies flagged words: 0 = queue + helper lanes, 1 = one pass per flagged lane with warp reductions */
 int  bg_set_param(bg_ctx *ctx, int what, int value);
 
 /* Page-locked host memory for the arrays handed to bg_align_runs_into() (queries, runs, hit buffer): makes the library's

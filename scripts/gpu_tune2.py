@@ -6,7 +6,7 @@ import argparse, os, sys
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from burst_b200 import synth
-from burst_b200.engine import (Engine, MODE_MIN, RUN_DTYPE, PARAM_SEED_CHUNK, PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB, PARAM_SEED_HSLOTS)
+from burst_b200.engine import (Engine, MODE_MIN, RUN_DTYPE, PARAM_SEED_CHUNK, PARAM_SEED_IMPL, PARAM_SEED_NCH, PARAM_SEED_LBITS, PARAM_SEED_FB, PARAM_SEED_HSLOTS, PARAM_SEED_VMODE)
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--reads", type=int, default=1_000_000)
@@ -21,7 +21,8 @@ runs = np.ascontiguousarray(w["runs"], RUN_DTYPE)
 ref = None
 for s in a.settings.split(","):
     f = [int(x) for x in s.split(":")]
-    impl, nch, lbits, chunk, fb = f[:5]; hs = f[5] if len(f) > 5 else 0
+    impl, nch, lbits, chunk, fb = f[:5]; hs = f[5] if len(f) > 5 else 0; vm = f[6] if len(f) > 6 else 0
+    eng.set_param(PARAM_SEED_VMODE, vm)
     eng.set_param(PARAM_SEED_HSLOTS, hs)
     eng.set_param(PARAM_SEED_IMPL, impl); eng.set_param(PARAM_SEED_NCH, nch); eng.set_param(PARAM_SEED_LBITS, lbits); eng.set_param(PARAM_SEED_CHUNK, chunk); eng.set_param(PARAM_SEED_FB, fb)
     eng.upload_runs(w["qcodes"], w["qoff"], w["budget"], runs, slot=w["slot"], nslots=w["nslots"])
@@ -35,5 +36,5 @@ for s in a.settings.split(","):
         ref = (hits, mins); same = "reference"
     else:
         same = "same" if (len(hits) == len(ref[0]) and np.array_equal(hits, ref[0]) and np.array_equal(mins, ref[1])) else "DIFFERENT (%d vs %d hits)" % (len(hits), len(ref[0]))
-    print("impl %d nch %d lbits %2d chunk %3d fb %d hs %4d : filter %.3f ms  extend %.3f ms  select %.3f ms  survivors %d hits %d  [%s]" % (
+    print("vm %d " % vm, end=""); print("impl %d nch %d lbits %2d chunk %3d fb %d hs %4d : filter %.3f ms  extend %.3f ms  select %.3f ms  survivors %d hits %d  [%s]" % (
         impl, nch, lbits, chunk, fb, hs, best["ms_filter"], best["ms_extend"], best["ms_select"], best["survivors"], best["hits"], same), flush=True)
