@@ -1315,9 +1315,10 @@ static const char *suppress_tax(char *buf, const char *tt, float score, uint32_t
 	return buf;
 }
 
-static void report_best(Rep *P, PodList *Pods) {                        /* burst.c:4847-4891 */
-	Queries *Q = P->Q; Refs *R = P->R; char *buf = xmalloc(1 << 20);
-	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+/* rows of queries [i0, i1) in order (burst.c:4847-4891) */
+static void report_best_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, char *buf) {
+	Queries *Q = P->Q; Refs *R = P->R; (void)Q;
+	for (uint64_t i = i0; i < i1; ++i) {
 		PodList *L = Pods + i; if (!L->n) continue;
 		const Pod *best = &L->p[L->n - 1];
 		for (int64_t k = (int64_t)L->n - 2; k >= 0; --k) {
@@ -1330,7 +1331,38 @@ static void report_best(Rep *P, PodList *Pods) {                        /* burst
 		if (taxa_parsed) { tax = taxa_lookup(R->RefHead[rix]); if (P->taxasuppress) tax = suppress_tax(buf, tax, best->score, 0, 0); }
 		print_row(P, i, best, rix, tax);
 	}
-	free(buf);
+}
+/* The rows of a query depend on nothing but its own pods, so the team formats blocks of queries into memory streams (printf's %f is
+ * most of the reporting time: 0.6 s per million rows on one thread) and the blocks are written out in query order: the same bytes as
+ * the sequential loop. */
+static void report_best(Rep *P, PodList *Pods) {
+	Queries *Q = P->Q;
+	const uint64_t CH = getenv("BURST_B200_REPORT_BLOCK") && atoi(getenv("BURST_B200_REPORT_BLOCK")) > 0 ? (uint64_t)atoi(getenv("BURST_B200_REPORT_BLOCK")) : 8192;   /* queries per block (the variable is for the tests) */
+	const uint64_t nch = (Q->numUniqQ + CH - 1) / CH;
+	int nthr = THREADS < 1 ? 1 : THREADS;
+	if (nthr == 1 || nch < 2) { char *buf = xmalloc(1 << 20); report_best_range(P, Pods, 0, Q->numUniqQ, buf); free(buf); return; }
+	const uint64_t WAVE = (uint64_t)nthr * 8;                               /* blocks in memory at a time */
+	char **blk = xcalloc(WAVE, sizeof(*blk)); size_t *len = xcalloc(WAVE, sizeof(*len));
+	for (uint64_t c0 = 0; c0 < nch; c0 += WAVE) {
+		const uint64_t c1 = MIN(nch, c0 + WAVE);
+		int failed = 0;
+		#pragma omp parallel num_threads(nthr)
+		{
+			char *buf = xmalloc(1 << 20);
+			#pragma omp for schedule(dynamic, 1)
+			for (uint64_t c = c0; c < c1; ++c) {
+				Rep P2 = *P; blk[c - c0] = NULL; len[c - c0] = 0;
+				P2.out = open_memstream(&blk[c - c0], &len[c - c0]);
+				if (!P2.out) { failed = 1; continue; }
+				report_best_range(&P2, Pods, c * CH, MIN(Q->numUniqQ, (c + 1) * CH), buf);
+				fclose(P2.out);
+			}
+			free(buf);
+		}
+		if (failed) { fputs("OOM: report buffers\n", stderr); exit(3); }
+		for (uint64_t c = c0; c < c1; ++c) { if (len[c - c0]) fwrite(blk[c - c0], 1, len[c - c0], P->out); free(blk[c - c0]); }
+	}
+	free(blk); free(len);
 }
 
 typedef struct { const Pod *rp; uint32_t rix; } RowRef;

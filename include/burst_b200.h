@@ -207,7 +207,9 @@ int  bg_align_runs_into(bg_ctx *ctx, const bg_queries *q, const bg_run *runs, ui
  * `src` already holds in HBM instead of a copy of its own; everything else (streams, batch buffers, survivor lists) stays private, so one
  * host thread per context can run bg_align_*_into() / bg_search_bunches_into() concurrently: the host<->device copies of one batch
  * travel behind the kernels of the other.  This is what the reference's thread team does with its per-thread scratch over one shared
- * database (burst.c:4050-4077).  `src` must not be freed, nor load another database, before `ctx` is freed. */
+ * database (burst.c:4050-4077).  In bg_align_bunches_into() the filter + sweep kernels of the sharing contexts are queued one batch behind
+ * the other (a shared event chain), so that two threads that start together do not fall into lockstep; the other entry points run their
+ * kernels concurrently.  `src` must not be freed, nor load another database, before `ctx` is freed. */
 int  bg_share_db(bg_ctx *ctx, bg_ctx *src);
 
 #ifdef __cplusplus

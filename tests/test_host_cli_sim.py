@@ -65,6 +65,20 @@ def test_bunch_size_does_not_change_rows(sim, tmp_path, threads):
     assert got == want
 
 
+@pytest.mark.parametrize("case", [c for c in CASES if "best" in c])
+def test_best_rows_formatted_by_the_thread_team_in_file_order(sim, case, tmp_path, monkeypatch):
+    """BEST reporting formats blocks of queries on all threads and writes the blocks in query order: with blocks of 7 queries and 5
+    threads the FILE must be byte-identical (not just the same set of rows) to the one-thread file, and equal to the reference's rows."""
+    got1, want = run_case(sim, case, tmp_path, extra=["-t", "1"])
+    raw1 = open(str(tmp_path / "out.b6"), "rb").read()
+    monkeypatch.setenv("BURST_B200_REPORT_BLOCK", "7")
+    got5, _ = run_case(sim, case, tmp_path, extra=["-t", "5"])
+    raw5 = open(str(tmp_path / "out.b6"), "rb").read()
+    assert got1 == want and got5 == want
+    if not case.startswith("acx"):                       # (-t changes the bunch size of the accelerated driver, and with it the order rows are found in -- not the rows)
+        assert raw5 == raw1
+
+
 def test_usage_errors_exit_codes(sim, tmp_path):
     r = subprocess.run([sim, "-r", "x.fa", "-q"], capture_output=True, text=True)
     assert r.returncode == 1
