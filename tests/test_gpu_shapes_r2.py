@@ -73,7 +73,10 @@ def test_c3_amplicon_shape(eng, oracle, mode):
     assert st["seed_queries"] == nq and st["seed_stride"] == 8
 
 
-def test_c4_shape_two_reference_shards(eng, oracle):
+@pytest.mark.parametrize("tiny", [False, True])
+def test_c4_shape_two_reference_shards(eng, oracle, tiny):
+    """tiny: each shard starts from a 32-entry survivor list, so bg_batch_run_extend has to notice the overflow, grow the list and redo
+    filter + extend BEFORE the minima are handed to the MIN-combination (a truncated list must never reach the all-reduce)."""
     rng = np.random.default_rng(404)
     refs = synth.random_refs(16 * 48, 306, rng, jitter=4)
     # a few references repeated in the other half of the DB, so that both shards hold hits of one read
@@ -107,6 +110,8 @@ def test_c4_shape_two_reference_shards(eng, oracle):
     for lo, hi in ((0, half), (half, nclumps)):
         end = int(off[hi]) if hi < nclumps else len(packed)
         eng.load_db(packed[int(off[lo]):end], clen[lo:hi], first_clump=lo)
+        if tiny:
+            eng.set_surv_cap(32)
         eng.upload_runs(codes, qoff, budget, runs)
         eng.run_extend(0); eng.run_select(1)
         h, b = eng.download()
