@@ -72,7 +72,7 @@ static void translate(char *s, size_t n) { for (size_t i = 0; i < n; ++i) s[i] =
 /* =============================================================================================
  * Queries (burst.c:2980-3223)
  * ============================================================================================= */
-typedef struct { char *seq; uint64_t six; uint8_t rc; } UniBin;      /* burst.c:269-274 */
+typedef struct { char *seq; uint64_t six; uint64_t key; uint8_t rc; } UniBin;      /* burst.c:269-274; key: the first 16 codes, see seq_key() */
 typedef struct { uint32_t len; uint16_t ed; } ShrBin;                /* burst.c:277-280 */
 typedef struct {
 	char **QHead; uint64_t totQ, numUniqQ, newUniqQ, *Offset, QBins[5];
@@ -81,14 +81,26 @@ typedef struct {
 	int rc, incl_whitespace, skipAmbig;
 } Queries;
 
+/* The reference orders queries by strcmp on their code strings (burst.c:3014-3031).  A sort that follows two pointers per comparison
+ * misses the cache twice per comparison; the first 16 codes (1..15, one nibble each, first base in the top nibble, 0 past the end) as
+ * one integer order exactly as strcmp orders those 16 bytes, so the sorts compare that key first and only look at the strings when
+ * the keys tie (for random 100-base reads: almost never). */
+static uint64_t seq_key(const char *s) {
+	uint64_t k = 0; int i = 0;
+	for (; i < 16 && s[i]; ++i) k = (k << 4) | ((uint8_t)s[i] & 15);
+	return i < 16 ? k << (4 * (16 - i)) : k;
+}
+typedef struct { uint64_t key, ix; } KeyIx;
 static char **g_sortseq;
 static int cmp_query_ix(const void *a, const void *b) {
-	uint64_t x = *(const uint64_t *)a, y = *(const uint64_t *)b;
-	int c = strcmp(g_sortseq[x], g_sortseq[y]);
-	return c ? c : (x < y ? -1 : x > y);      /* input order among duplicates = the reference at -t 1 */
+	const KeyIx *A = a, *B = b;
+	if (A->key != B->key) return A->key < B->key ? -1 : 1;
+	int c = strcmp(g_sortseq[A->ix], g_sortseq[B->ix]);
+	return c ? c : (A->ix < B->ix ? -1 : A->ix > B->ix);      /* input order among duplicates = the reference at -t 1 */
 }
 static int cmp_unibin(const void *a, const void *b) {
 	const UniBin *A = a, *B = b;
+	if (A->key != B->key) return A->key < B->key ? -1 : 1;
 	int c = strcmp(A->seq, B->seq);
 	if (c) return c;
 	if (A->rc != B->rc) return A->rc - B->rc;
@@ -131,6 +143,7 @@ static void load_queries(const char *fn, Queries *Q) {
 	memset(dump + sz, 0, 16);
 	if (!sz || *dump != '>') { fputs("ERROR: Malformatted FASTA file.\n", stderr); exit(1); }
 	uint64_t numNL = 0, numLT = 0;
+	#pragma omp parallel for reduction(+:numNL,numLT) schedule(static) num_threads(THREADS < 1 ? 1 : THREADS)
 	for (uint64_t i = 0; i < sz; ++i) numNL += dump[i] == '\n', numLT += dump[i] == '>';
 	numNL += numNL & 1;
 	if (numLT != numNL / 2) { fputs("ERROR: line count != '>' * 2\n", stderr); exit(1); }
@@ -162,38 +175,54 @@ static void load_queries(const char *fn, Queries *Q) {
 	#pragma omp parallel for schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
 	for (uint64_t i = 0; i < totQ; ++i) translate(Seq[i], Len[i]);
 	/* sort (burst.c:3014-3031): strcmp on the code strings */
-	uint64_t *ix = xmalloc(totQ * sizeof(*ix));
-	for (uint64_t i = 0; i < totQ; ++i) ix[i] = i;
+	KeyIx *kx = xmalloc(totQ * sizeof(*kx));
+	#pragma omp parallel for schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
+	for (uint64_t i = 0; i < totQ; ++i) { kx[i].key = seq_key(Seq[i]); kx[i].ix = i; }
 	g_sortseq = Seq;
-	psort(ix, totQ, sizeof(*ix), cmp_query_ix);
-	/* uniqueness (burst.c:3036-3053) */
-	uint64_t numUniq = 1;
-	for (uint64_t i = 1; i < totQ; ++i) if (strcmp(Seq[ix[i - 1]], Seq[ix[i]])) ++numUniq;
+	psort(kx, totQ, sizeof(*kx), cmp_query_ix);
+	/* uniqueness (burst.c:3036-3053): a new sequence starts where the key or, on equal keys, the string changes */
+	uint64_t *ix = xmalloc(totQ * sizeof(*ix));
+	uint8_t *fresh = xmalloc(totQ);
+	uint64_t numUniq = 0;
+	#pragma omp parallel for reduction(+:numUniq) schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
+	for (uint64_t i = 0; i < totQ; ++i) {
+		ix[i] = kx[i].ix;
+		fresh[i] = !i || kx[i - 1].key != kx[i].key || strcmp(Seq[kx[i - 1].ix], Seq[kx[i].ix]) != 0;
+		numUniq += fresh[i];
+	}
+	free(kx);
 	uint64_t *Offset = xmalloc((numUniq + 1) * sizeof(*Offset)), u = 0;
-	for (uint64_t i = 0; i < totQ; ++i) if (!i || strcmp(Seq[ix[i - 1]], Seq[ix[i]])) Offset[u++] = i;
+	for (uint64_t i = 0; i < totQ; ++i) if (fresh[i]) Offset[u++] = i;
 	Offset[numUniq] = totQ;
+	free(fresh);
 	char **SrtHead = xmalloc(totQ * sizeof(*SrtHead));
+	#pragma omp parallel for schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
 	for (uint64_t i = 0; i < totQ; ++i) SrtHead[i] = Head[ix[i]];
 	uint64_t newUniq = numUniq * (Q->rc ? 2 : 1);
 	UniBin *UB = xcalloc(newUniq, sizeof(*UB)); ShrBin *SB = xcalloc(numUniq, sizeof(*SB));
 	float reqID = 1 / THRES - 1;                                      /* burst.c:3069-3076, float32 */
 	uint64_t uniqTotLen = 0;
+	#pragma omp parallel for reduction(+:uniqTotLen) schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
 	for (uint64_t i = 0; i < numUniq; ++i) {
 		uint64_t r = ix[Offset[i]];
 		uint32_t len = Len[r], ed = reqID * len;
 		SB[i].len = len; SB[i].ed = (uint16_t)MIN(254, ed);
-		UB[i].seq = Seq[r]; UB[i].six = i; UB[i].rc = 0;
+		UB[i].seq = Seq[r]; UB[i].six = i; UB[i].rc = 0; UB[i].key = seq_key(Seq[r]);
 		uniqTotLen += len;
 	}
 	if (Q->rc) {                                                      /* burst.c:3087-3109 */
-		char *rcd = xmalloc(uniqTotLen + numUniq + 1), *w = rcd;
+		char *rcd = xmalloc(uniqTotLen + numUniq + 1);
+		uint64_t *woff = xmalloc((numUniq + 1) * sizeof(*woff));
+		woff[0] = 0;
+		for (uint64_t i = 0; i < numUniq; ++i) woff[i + 1] = woff[i] + SB[i].len + 1;
+		#pragma omp parallel for schedule(static, 4096) num_threads(THREADS < 1 ? 1 : THREADS)
 		for (uint64_t i = 0; i < numUniq; ++i) {
-			uint32_t len = SB[i].len; char *org = UB[i].seq;
+			uint32_t len = SB[i].len; char *org = UB[i].seq, *w = rcd + woff[i];
 			for (uint32_t j = 0; j < len; ++j) w[j] = (char)RVT[(uint8_t)org[len - j - 1] & 15];
 			w[len] = 0;
-			UB[numUniq + i].seq = w; UB[numUniq + i].rc = 1; UB[numUniq + i].six = i;
-			w += len + 1;
+			UB[numUniq + i].seq = w; UB[numUniq + i].rc = 1; UB[numUniq + i].six = i; UB[numUniq + i].key = seq_key(w);
 		}
+		free(woff);
 	}
 	memset(Q->QBins, 0, sizeof(Q->QBins));
 	if (DO_ACCEL) {                                                   /* burst.c:3113-3177 */

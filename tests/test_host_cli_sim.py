@@ -88,3 +88,46 @@ def test_usage_errors_exit_codes(sim, tmp_path):
     refs = os.path.join(GOLD, "fasta_best", "refs.fa")
     r = subprocess.run([sim, "-r", refs, "-q", "/nonexistent.fa", "-o", str(tmp_path / "o.b6")], capture_output=True, text=True)
     assert r.returncode == 2
+
+
+def test_query_order_with_shared_prefixes_and_the_thread_team(sim, tmp_path):
+    """Query preprocessing (burst.c:2980-3223) sorts code strings by strcmp; the host sorts (16-base key, index) pairs on all threads and
+    only follows the pointers when keys tie.  70 k reads whose first 17 bases come from 50 prefixes (every comparison inside a family ties on
+    the key), reads that are prefixes of other reads, and duplicates: the rows of a BEST run must come out in strcmp order of the code
+    strings with duplicates in input order, and -t 1 (plain qsort) and -t 8 (sorted pieces + merges) must write the same file."""
+    import numpy as np
+    rng = np.random.default_rng(99)
+    code = {"A": 1, "C": 2, "G": 3, "T": 4}
+    pre = ["".join("ACGT"[i] for i in rng.integers(0, 4, 17)) for _ in range(50)]
+    uniq = set()
+    while len(uniq) < 34000:
+        uniq.add(pre[int(rng.integers(0, 50))] + "".join("ACGT"[i] for i in rng.integers(0, 4, int(rng.integers(3, 8)))))
+    uniq = sorted(uniq)
+    reads = list(uniq) + [u[:-2] for u in uniq[:2000]] + [uniq[int(i)] for i in rng.integers(0, len(uniq), 36000)]
+    order = rng.permutation(len(reads))
+    reads = [reads[i] for i in order]
+    assert len(reads) >= 70000
+    with open(tmp_path / "q.fa", "w") as f:
+        f.write("".join(">r%d\n%s\n" % (i, r) for i, r in enumerate(reads)))
+    with open(tmp_path / "r.fa", "w") as f:
+        f.write("".join(">ref%d\n%s\n" % (i, "".join("ACGT"[j] for j in rng.integers(0, 4, 30))) for i in range(16)))
+    files = []
+    for t in ("1", "8"):
+        out = str(tmp_path / ("o%s.b6" % t))
+        r = subprocess.run([sim, "-r", str(tmp_path / "r.fa"), "-q", str(tmp_path / "q.fa"), "-o", out, "-m", "BEST", "-i", "0.5", "-t", t, "--noprogress"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        files.append(open(out, "rb").read())
+    assert files[0] == files[1]
+    names = [l.split(b"\t", 1)[0].decode() for l in files[0].splitlines()]
+    keyed = sorted(range(len(reads)), key=lambda i: (bytes(code[c] for c in reads[i]), i))
+    assert names == ["r%d" % i for i in keyed]
+    # both strands (-fr): 2 x 36 k unique strands, the merged sort of forward and reverse-complement strings (burst.c:3178-3186)
+    both = []
+    for t in ("1", "8"):
+        out = str(tmp_path / ("f%s.b6" % t))
+        r = subprocess.run([sim, "-r", str(tmp_path / "r.fa"), "-q", str(tmp_path / "q.fa"), "-o", out, "-m", "BEST", "-i", "0.5", "-fr", "-t", t, "--noprogress"],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        both.append(open(out, "rb").read())
+    assert both[0] == both[1] and len(both[0].splitlines()) == len(reads)
