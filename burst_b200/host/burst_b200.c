@@ -1344,9 +1344,39 @@ static const char *suppress_tax(char *buf, const char *tt, float score, uint32_t
 	return buf;
 }
 
+/* The rows of a query depend on nothing but its own pods (and, for CAPITALIST, on reference counts tallied beforehand), so the team
+ * formats blocks of queries into memory streams (printf's %f is most of the reporting time: 0.6 s per million rows on one thread) and
+ * the blocks are written out in query order: the same bytes as the sequential loop. */
+typedef void (*RangeFn)(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, void *shared);
+static void report_in_blocks(Rep *P, PodList *Pods, RangeFn fn, void *shared) {
+	Queries *Q = P->Q;
+	const uint64_t CH = getenv("BURST_B200_REPORT_BLOCK") && atoi(getenv("BURST_B200_REPORT_BLOCK")) > 0 ? (uint64_t)atoi(getenv("BURST_B200_REPORT_BLOCK")) : 8192;   /* queries per block (the variable is for the tests) */
+	const uint64_t nch = (Q->numUniqQ + CH - 1) / CH;
+	int nthr = THREADS < 1 ? 1 : THREADS;
+	if (nthr == 1 || nch < 2) { fn(P, Pods, 0, Q->numUniqQ, shared); return; }
+	const uint64_t WAVE = (uint64_t)nthr * 8;                               /* blocks in memory at a time */
+	char **blk = xcalloc(WAVE, sizeof(*blk)); size_t *len = xcalloc(WAVE, sizeof(*len));
+	for (uint64_t c0 = 0; c0 < nch; c0 += WAVE) {
+		const uint64_t c1 = MIN(nch, c0 + WAVE);
+		int failed = 0;
+		#pragma omp parallel for schedule(dynamic, 1) num_threads(nthr)
+		for (uint64_t c = c0; c < c1; ++c) {
+			Rep P2 = *P; blk[c - c0] = NULL; len[c - c0] = 0;
+			P2.out = open_memstream(&blk[c - c0], &len[c - c0]);
+			if (!P2.out) { failed = 1; continue; }
+			fn(&P2, Pods, c * CH, MIN(Q->numUniqQ, (c + 1) * CH), shared);
+			fclose(P2.out);
+		}
+		if (failed) { fputs("OOM: report buffers\n", stderr); exit(3); }
+		for (uint64_t c = c0; c < c1; ++c) { if (len[c - c0]) fwrite(blk[c - c0], 1, len[c - c0], P->out); free(blk[c - c0]); }
+	}
+	free(blk); free(len);
+}
+
 /* rows of queries [i0, i1) in order (burst.c:4847-4891) */
-static void report_best_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, char *buf) {
-	Queries *Q = P->Q; Refs *R = P->R; (void)Q;
+static void report_best_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, void *shared) {
+	Refs *R = P->R; (void)shared;
+	char *buf = xmalloc(1 << 20);
 	for (uint64_t i = i0; i < i1; ++i) {
 		PodList *L = Pods + i; if (!L->n) continue;
 		const Pod *best = &L->p[L->n - 1];
@@ -1360,39 +1390,9 @@ static void report_best_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, c
 		if (taxa_parsed) { tax = taxa_lookup(R->RefHead[rix]); if (P->taxasuppress) tax = suppress_tax(buf, tax, best->score, 0, 0); }
 		print_row(P, i, best, rix, tax);
 	}
+	free(buf);
 }
-/* The rows of a query depend on nothing but its own pods, so the team formats blocks of queries into memory streams (printf's %f is
- * most of the reporting time: 0.6 s per million rows on one thread) and the blocks are written out in query order: the same bytes as
- * the sequential loop. */
-static void report_best(Rep *P, PodList *Pods) {
-	Queries *Q = P->Q;
-	const uint64_t CH = getenv("BURST_B200_REPORT_BLOCK") && atoi(getenv("BURST_B200_REPORT_BLOCK")) > 0 ? (uint64_t)atoi(getenv("BURST_B200_REPORT_BLOCK")) : 8192;   /* queries per block (the variable is for the tests) */
-	const uint64_t nch = (Q->numUniqQ + CH - 1) / CH;
-	int nthr = THREADS < 1 ? 1 : THREADS;
-	if (nthr == 1 || nch < 2) { char *buf = xmalloc(1 << 20); report_best_range(P, Pods, 0, Q->numUniqQ, buf); free(buf); return; }
-	const uint64_t WAVE = (uint64_t)nthr * 8;                               /* blocks in memory at a time */
-	char **blk = xcalloc(WAVE, sizeof(*blk)); size_t *len = xcalloc(WAVE, sizeof(*len));
-	for (uint64_t c0 = 0; c0 < nch; c0 += WAVE) {
-		const uint64_t c1 = MIN(nch, c0 + WAVE);
-		int failed = 0;
-		#pragma omp parallel num_threads(nthr)
-		{
-			char *buf = xmalloc(1 << 20);
-			#pragma omp for schedule(dynamic, 1)
-			for (uint64_t c = c0; c < c1; ++c) {
-				Rep P2 = *P; blk[c - c0] = NULL; len[c - c0] = 0;
-				P2.out = open_memstream(&blk[c - c0], &len[c - c0]);
-				if (!P2.out) { failed = 1; continue; }
-				report_best_range(&P2, Pods, c * CH, MIN(Q->numUniqQ, (c + 1) * CH), buf);
-				fclose(P2.out);
-			}
-			free(buf);
-		}
-		if (failed) { fputs("OOM: report buffers\n", stderr); exit(3); }
-		for (uint64_t c = c0; c < c1; ++c) { if (len[c - c0]) fwrite(blk[c - c0], 1, len[c - c0], P->out); free(blk[c - c0]); }
-	}
-	free(blk); free(len);
-}
+static void report_best(Rep *P, PodList *Pods) { report_in_blocks(P, Pods, report_best_range, NULL); }
 
 typedef struct { const Pod *rp; uint32_t rix; } RowRef;
 /* expand a pod over the de-duplicated originals it stands for (burst.c:4601-4616) */
@@ -1438,6 +1438,8 @@ static void report_allpaths_or_forage(Rep *P, PodList *Pods, int forage) {   /* 
 
 static int cmp_str(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
 
+typedef struct { const size_t *RefCounts; const uint32_t *start; } CapShared;
+static void report_capitalist_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, void *shared);
 static void report_capitalist(Rep *P, PodList *Pods) {                  /* burst.c:4694-4846 */
 	Queries *Q = P->Q; Refs *R = P->R;
 	uint32_t maxIX = 0;
@@ -1463,9 +1465,18 @@ static void report_capitalist(Rep *P, PodList *Pods) {                  /* burst
 		}
 	}
 	printf("CAPITALIST: Processed %zu investments\n", tot);
+	free(D.ref); free(D.st);
+	CapShared CS = {RefCounts, start};
+	report_in_blocks(P, Pods, report_capitalist_range, &CS);             /* pass 3: a query's row needs its own pods and the finished counts only */
+	free(RefCounts); free(start);
+}
+static void report_capitalist_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, void *shared) {
+	Queries *Q = P->Q; Refs *R = P->R;
+	const size_t *RefCounts = ((CapShared *)shared)->RefCounts; const uint32_t *start = ((CapShared *)shared)->start;
+	DupeSet D = {0};
 	char **Taxa = NULL; uint32_t *Div = NULL; char *Taxon = NULL; uint64_t tcap = 0;
 	if (taxa_parsed) Taxon = xmalloc(1000000);
-	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+	for (uint64_t i = i0; i < i1; ++i) {
 		PodList *L = Pods + i; if (!L->n) continue;
 		const Pod *first = &L->p[start[i]], *best = first;
 		uint32_t tix = 0, bestmap = 0, bestrix = R->RefIxSrt[first->refIx], qlen = Q->ShrBins[i].len; float best_score = -1.f;
@@ -1530,7 +1541,7 @@ static void report_capitalist(Rep *P, PodList *Pods) {                  /* burst
 		}
 		print_row(P, i, best, bestrix, FinalTaxon);
 	}
-	free(RefCounts); free(start); free(D.ref); free(D.st); free(Taxa); free(Div); free(Taxon);
+	free(D.ref); free(D.st); free(Taxa); free(Div); free(Taxon);
 }
 
 /* =============================================================================================

@@ -65,9 +65,9 @@ def test_bunch_size_does_not_change_rows(sim, tmp_path, threads):
     assert got == want
 
 
-@pytest.mark.parametrize("case", [c for c in CASES if "best" in c])
+@pytest.mark.parametrize("case", [c for c in CASES if "best" in c or "capitalist" in c])
 def test_best_rows_formatted_by_the_thread_team_in_file_order(sim, case, tmp_path, monkeypatch):
-    """BEST reporting formats blocks of queries on all threads and writes the blocks in query order: with blocks of 7 queries and 5
+    """BEST and CAPITALIST (rows after the global tally) reporting formats blocks of queries on all threads and writes the blocks in query order: with blocks of 7 queries and 5
     threads the FILE must be byte-identical (not just the same set of rows) to the one-thread file, and equal to the reference's rows."""
     got1, want = run_case(sim, case, tmp_path, extra=["-t", "1"])
     raw1 = open(str(tmp_path / "out.b6"), "rb").read()
