@@ -1400,10 +1400,10 @@ typedef struct { const Pod *rp; uint32_t rix; } RowRef;
 	if ((R)->RefDedupIx) { for (uint32_t k_ = (R)->RefDedupIx[(rp)->refIx]; k_ < (R)->RefDedupIx[(rp)->refIx + 1]; ++k_) { uint32_t rixvar = (R)->TmpRIX[k_]; __VA_ARGS__ } } \
 	else { uint32_t rixvar = (R)->RefIxSrt[(rp)->refIx]; __VA_ARGS__ }
 
-static void report_allpaths_or_forage(Rep *P, PodList *Pods, int forage) {   /* burst.c:4582-4692 */
-	Queries *Q = P->Q; Refs *R = P->R;
+static void report_allpaths_range(Rep *P, PodList *Pods, uint64_t i0, uint64_t i1, void *shared) {   /* burst.c:4582-4692 */
+	Queries *Q = P->Q; Refs *R = P->R; const int forage = *(const int *)shared;
 	DupeSet D = {0}; RowRef *rows = NULL; uint64_t rcap = 0;
-	for (uint64_t i = 0; i < Q->numUniqQ; ++i) {
+	for (uint64_t i = i0; i < i1; ++i) {
 		PodList *L = Pods + i; if (!L->n) continue;
 		uint32_t qlen = Q->ShrBins[i].len, bm = 255; uint64_t nrows = 0; D.n = 0;
 		const Pod *best = &L->p[L->n - 1];
@@ -1435,6 +1435,7 @@ static void report_allpaths_or_forage(Rep *P, PodList *Pods, int forage) {   /* 
 	}
 	free(rows); free(D.ref); free(D.st);
 }
+static void report_allpaths_or_forage(Rep *P, PodList *Pods, int forage) { report_in_blocks(P, Pods, report_allpaths_range, &forage); }
 
 static int cmp_str(const void *a, const void *b) { return strcmp(*(char *const *)a, *(char *const *)b); }
 
